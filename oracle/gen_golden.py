@@ -1,0 +1,157 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (TEST INFRASTRUCTURE; build container only).
+
+    python oracle/gen_golden.py synthetic      # seeded synthetic networks, reference default-initialised weights
+    python oracle/gen_golden.py ferndale       # Examples/Ferndale.zip: real stations/grids/picks + trained checkpoint
+
+The reference classes (`/root/reference/Code/module.py`, `process_utils.py`) are imported as they are, with
+`oracle/refshim/` supplying the third-party packages that cannot be installed offline (see its README).  The reference
+reads `config.yaml` / `train_config.yaml` from the current directory at import time (module.py:27-46), so each mode
+runs from a scratch directory holding the matching YAML files.  `/root/reference` does not exist on the GPU box — only
+the committed fixtures travel.
+"""
+import os
+import sys
+import shutil
+import tempfile
+import zipfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+REF = '/root/reference'
+GOLD = os.path.join(REPO, 'tests', 'golden')
+
+
+def _import_reference(code_dir, workdir):
+    os.chdir(workdir)
+    sys.path.insert(0, os.path.join(HERE, 'refshim'))
+    sys.path.insert(0, code_dir)
+    sys.path.insert(0, REPO)
+    import torch
+    import module
+    import process_utils
+    from torch_geometric.data import Data
+    torch.set_grad_enabled(False)
+    return torch, module, process_utils, Data
+
+
+def _hook_outputs(mz):
+    store = {}
+
+    def mk(name):
+        def hook(_m, _inp, out):
+            store.setdefault(name, []).append(out.detach().clone())
+        return hook
+
+    for name in ('DataAggregation', 'Bipartite_ReadIn', 'SpatialAggregation1', 'SpatialAggregation2',
+                 'SpatialAggregation3', 'SpatialDirect', 'SpatialAttention', 'TemporalAttention'):
+        getattr(mz, name).register_forward_hook(mk(name))
+    return store
+
+
+def _pack(sd):
+    return {'sd/' + k: v.detach().cpu().numpy() for k, v in sd.items()}
+
+
+def _run_reference_window(torch, module, pu, Data, mz, locs, ind_use, grid, trv_times, P, t0, max_t, sig, dt,
+                          k_sta, k_spc, attr_scale, x_query, t_query, identity):
+    """set-up (process_continuous_days.py:627-634) + one window (:776-797) through the reference's own functions."""
+    S = len(ind_use)
+    G = grid.shape[0]
+    n_locs = locs.shape[0]
+    # graphs: extract_inputs_adjacencies (process_utils.py:701); the time-edge pointer arguments are association-only,
+    # so they are given minimal dummies (k_time_edges = 1, one reference time).
+    graph_params = [k_sta, k_spc, 1]
+    dummy_ptr = np.zeros(n_locs, dtype='int')
+    out = pu.extract_inputs_adjacencies(None, locs, ind_use, grid, None, np.zeros(1), dummy_ptr, dummy_ptr,
+                                        identity, graph_params, device='cpu')
+    A_sta_sta, A_src_src, A_prod_sta, A_prod_src, A_src_in_prod = out[0:5]
+    A_src_in_sta = torch.Tensor(np.concatenate((np.tile(np.arange(S), G).reshape(1, -1),
+                                                np.arange(G).repeat(S, axis=0).reshape(1, -1)), axis=0)).long()
+    spatial_vals = torch.Tensor(((np.repeat(np.expand_dims(grid, axis=1), S, axis=1)
+                                  - np.repeat(np.expand_dims(locs[ind_use], axis=0), G, axis=0)).reshape(-1, 3))
+                                / attr_scale)
+    A_src_in_edges = Data(x=spatial_vals, edge_index=A_src_in_prod)
+    locs_cart = torch.Tensor(identity(locs[ind_use]))
+    grid_cart = torch.Tensor(identity(grid))
+    mz.set_adjacencies(A_prod_sta, A_prod_src, A_src_in_edges, None, A_src_in_sta, A_src_src, None, None, None, None,
+                       locs_cart, grid_cart)
+    # input
+    [Inpts, Masks], [lp_t, lp_s, lp_p, _] = pu.extract_input_from_data(
+        None, P, np.array([t0]), ind_use, locs, grid, A_src_in_sta.numpy(), trv_times=trv_times, max_t=max_t,
+        kernel_sig_t=sig, dt=dt, device='cpu')
+    emb = pu.extract_input_from_data(None, P, np.array([t0]), ind_use, locs, grid, A_src_in_sta.numpy(),
+                                     trv_times=trv_times, max_t=max_t, kernel_sig_t=sig, dt=dt,
+                                     return_embedding=True, device='cpu')
+    embed_p, embed_s, ind_unique, abs_time_ref, n_ts, n_su = emb
+    Slice, Mask = Inpts[0], Masks[0]
+    store = _hook_outputs(mz)
+    y, x = mz.forward_fixed_source(Slice, Mask, torch.Tensor(lp_t[0]), torch.Tensor(lp_s[0]).long(),
+                                   torch.Tensor(lp_p[0].reshape(-1, 1)).float(), locs_cart, grid_cart,
+                                   torch.Tensor(x_query), torch.Tensor(t_query.reshape(-1, 1)))
+    res = dict(
+        A_sta_sta=A_sta_sta.numpy(), A_src_src=A_src_src.numpy(), read_in_attr=spatial_vals.numpy(),
+        Slice=Slice.numpy(), Mask=Mask.numpy(),
+        embed_p=embed_p.numpy().reshape(n_su, n_ts), embed_s=embed_s.numpy().reshape(n_su, n_ts),
+        ind_unique=np.asarray(ind_unique), ref0=np.float64(abs_time_ref[0]), n_ts=np.int64(n_ts),
+        x_latent=store['DataAggregation'][0].numpy(), read_in=store['Bipartite_ReadIn'][0].numpy(),
+        sa1=store['SpatialAggregation1'][0].numpy(), sa2=store['SpatialAggregation2'][0].numpy(),
+        x_spatial=store['SpatialAggregation3'][0].numpy(), y_latent=store['SpatialDirect'][0].numpy(),
+        x_query_embed=store['SpatialAttention'][0].numpy(), y=y.numpy(), x=x.numpy())
+    return res
+
+
+def synthetic():
+    work = tempfile.mkdtemp(prefix='genie_golden_')
+    for f in ('config.yaml', 'train_config.yaml'):
+        shutil.copy(os.path.join(REF, 'Code', f), work)
+    torch, module, pu, Data = _import_reference(os.path.join(REF, 'Code'), work)
+    from genie_b200 import synth
+
+    def identity(x):
+        return x
+
+    cases = [  # name, S_all, n_use, G, k_sta, k_spc, Q, seed
+        ('c1_10x100', 10, 10, 100, 8, 15, 64, 0),           # BASELINE.json configs[0]
+        ('mid_36of40x300', 40, 36, 300, 8, 15, 128, 3),     # station subset (ind_use != arange), k_s < S-2
+        ('small_6x40', 6, 6, 40, 8, 15, 16, 5),             # k_sta clipped to S-2 (process_utils.py:712)
+    ]
+    for name, S_all, n_use, G, k_sta, k_spc, Q, seed in cases:
+        net = synth.Network(S_all, G, seed=seed, width_km=60.0 if S_all <= 10 else 120.0)
+        rng = np.random.default_rng(100 + seed)
+        ind_use = np.sort(rng.choice(S_all, size=n_use, replace=False))
+        max_t = net.max_moveout()
+        sig, dt = 3.0, float(np.round(3.0 / 10.0, 2))
+        P = synth.make_picks(net, 0.0, 600.0, seed=seed + 1, events_per_3h=400.0, false_per_sta_min=2.0)
+        t0 = 200.0 + 3.0 * seed
+        trv_times = net.travel_times()
+        torch.manual_seed(seed)
+        mz = module.GCN_Detection_Network_extended(identity, identity, device='cpu')
+        mz.eval()
+        x_query = np.stack((rng.uniform(0, net.width, Q), rng.uniform(0, net.width, Q),
+                            rng.uniform(-40000.0, 0.0, Q)), axis=1)
+        t_query = np.arange(-3.0, 3.0 + 0.75, 0.75)
+        attr_scale = np.array([net.width, net.width, 42000.0]).reshape(1, -1)
+        res = _run_reference_window(torch, module, pu, Data, mz, net.sta, ind_use, net.grid, trv_times, P, t0, max_t,
+                                    sig, dt, k_sta, k_spc, attr_scale, x_query, t_query, identity)
+        res.update(_pack(mz.state_dict()))
+        res.update(sta=net.sta, grid=net.grid, ind_use=ind_use, trv_times=trv_times, picks=P, t0=np.float64(t0),
+                   max_t=np.float64(max_t), kernel_sig_t=np.float64(sig), dt=np.float64(dt),
+                   k_sta=np.int64(k_sta), k_spc=np.int64(k_spc), scale_rel=np.float64(module.scale_rel),
+                   scale_t=np.float64(module.scale_t), x_query=x_query, t_query=t_query, attr_scale=attr_scale)
+        np.savez_compressed(os.path.join(GOLD, name + '.npz'), **res)
+        print(name, 'P=%d picks=%d Slice.sum=%.6f nnz=%d x_latent.abs=%.6f y.max=%.6f x.max=%.6f' % (
+            res['Slice'].shape[0], len(P), res['Slice'].sum(), (res['Slice'] != 0).sum(),
+            np.abs(res['x_latent']).sum(), res['y'].max(), res['x'].max()))
+
+
+if __name__ == '__main__':
+    mode = sys.argv[1] if len(sys.argv) > 1 else 'synthetic'
+    if mode == 'synthetic':
+        synthetic()
+    elif mode == 'ferndale':
+        from gen_golden_ferndale import ferndale
+        ferndale()
+    else:
+        raise SystemExit('usage: gen_golden.py synthetic|ferndale')

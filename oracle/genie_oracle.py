@@ -1,0 +1,344 @@
+"""CPU oracle for the GENIE product-graph front end (TEST INFRASTRUCTURE — never on the product path).
+
+A functional restatement, in plain torch-CPU fp32 / numpy fp64, of the algorithm of the reference's hot path
+(SURVEY.md §8a rows a1–a5).  Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` /
+`--impl reference` legs may import this file; `genie_b200/` never does.
+
+Pinning: every function below is checked (tests/test_oracle_golden.py) against `tests/golden/*.npz`, which were produced
+by `oracle/gen_golden.py` running the UNMODIFIED reference classes (`/root/reference/Code/module.py`,
+`process_utils.py`) in the build container through the import stubs in `oracle/refshim/`.  The reference ships no tests
+or golden vectors of its own for this path, and its arithmetic lives in un-vendored, un-pinned
+third-party wheels (torch_geometric `MessagePassing.propagate`, torch_scatter `scatter`, torch_cluster `knn`;
+`Code/install_dependencies.txt:9-17`), whose documented semantics are restated in `propagate_*` / `scatter_max` / `knn`
+below.  So: parity is pinned against the reference's own Python classes executed here, with the third-party message
+passing semantics restated — not against a reference-held golden vector (none exists).
+
+Conventions: edge lists are int64 `[2, E]`, row 0 = message source j, row 1 = target i; product node id
+= g*S + s in dense mode; all floating point tensors fp32; the pick → time-bin index map is computed in fp64 and
+truncated toward zero exactly as numpy does.
+
+State is passed as a flat dict with the reference's own state_dict key names
+(`DataAggregation.init_trns.weight`, ..., every `nn.PReLU` a 1-element `weight`).
+"""
+import math
+
+import numpy as np
+import torch
+
+# --------------------------------------------------------------------------------------------------------------------
+# small building blocks
+# --------------------------------------------------------------------------------------------------------------------
+
+
+def _lin(sd, name, x):
+    """nn.Linear: x @ W^T + b."""
+    return torch.nn.functional.linear(x, sd[name + '.weight'], sd[name + '.bias'])
+
+
+def _prelu(sd, name, x):
+    """nn.PReLU with a single slope."""
+    a = sd[name + '.weight'].reshape(())
+    return torch.where(x >= 0, x, a * x)
+
+
+def propagate_sum(msg, index, n_out):
+    """PyG aggr='add': out[i] = sum_{e: index[e]=i} msg[e]  (index_add_, the op PyG-CPU dispatches to)."""
+    out = torch.zeros((n_out,) + tuple(msg.shape[1:]), dtype=msg.dtype)
+    return out.index_add_(0, index, msg)
+
+
+def propagate_mean(msg, index, n_out):
+    """PyG aggr='mean': sum / max(count, 1); a node with no in-edges gets 0."""
+    s = propagate_sum(msg, index, n_out)
+    cnt = torch.zeros(n_out, dtype=msg.dtype).index_add_(0, index, torch.ones(index.numel(), dtype=msg.dtype))
+    return s / cnt.clamp(min=1).view((-1,) + (1,) * (msg.dim() - 1))
+
+
+def segment_softmax(src, index, n_seg):
+    """torch_geometric.utils.softmax over groups of equal `index` (dim 0)."""
+    idx = index.view((-1,) + (1,) * (src.dim() - 1)).expand_as(src)
+    mx = torch.full((n_seg,) + tuple(src.shape[1:]), float('-inf'), dtype=src.dtype)
+    mx = mx.scatter_reduce(0, idx, src, reduce='amax', include_self=True)
+    ex = (src - mx.gather(0, idx)).exp()
+    den = torch.zeros((n_seg,) + tuple(src.shape[1:]), dtype=src.dtype).scatter_add_(0, idx, ex)
+    return ex / (den.gather(0, idx) + 1e-16)
+
+
+def knn(x, y, k):
+    """torch_cluster.knn(x, y, k): for each row of y the k nearest rows of x; [2, |y|k], row0 = y idx, row1 = x idx."""
+    from scipy.spatial import cKDTree
+    xn = np.asarray(x, dtype=np.float64)
+    yn = np.asarray(y, dtype=np.float64)
+    k = int(min(k, xn.shape[0]))
+    ind = cKDTree(xn).query(yn, k=k)[1].reshape(yn.shape[0], k)
+    return torch.from_numpy(np.stack((np.repeat(np.arange(yn.shape[0]), k), ind.reshape(-1)), axis=0)).long()
+
+
+def knn_graph_no_self(pos_km, k):
+    """`remove_self_loops(knn(x, x, k + 1).flip(0))` — process_utils.py:718-719.  Row 0 = source j, row 1 = target i."""
+    e = knn(pos_km, pos_km, k + 1).flip(0).contiguous()
+    return e[:, e[0] != e[1]]
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# graph assembly (process_utils.py:701-742, dense Cartesian-product mode)
+# --------------------------------------------------------------------------------------------------------------------
+
+
+def build_adjacencies_dense(sta_cart_m, grid_cart_m, k_sta, k_spc):
+    """Restates extract_inputs_adjacencies (process_utils.py:712-722) for Cartesian coordinates in metres.
+
+    Returns A_sta_sta [2,S*k_s], A_src_src [2,G*k_g], A_prod_sta_sta, A_prod_src_src, A_src_in_prod, A_src_in_sta.
+    """
+    S, G = sta_cart_m.shape[0], grid_cart_m.shape[0]
+    k_sta = int(min(k_sta, S - 2))                                              # :712
+    A_sta = knn_graph_no_self((np.asarray(sta_cart_m, dtype=np.float64) / 1000.0).astype(np.float32), k_sta)   # :718
+    A_src = knn_graph_no_self((np.asarray(grid_cart_m, dtype=np.float64) / 1000.0).astype(np.float32), k_spc)  # :719
+    # :720  every grid node g carries a copy of the station graph, shifted by S*g
+    A_prod_sta = (A_sta.repeat(1, G) + S * torch.arange(G).repeat_interleave(A_sta.shape[1]).view(1, -1)).contiguous()
+    # :721  every station s carries a copy of the grid graph, node (g, s) = S*g + s
+    A_prod_src = (S * A_src.repeat(1, S) + torch.arange(S).repeat_interleave(A_src.shape[1]).view(1, -1)).contiguous()
+    # :722  product node -> its grid node
+    A_src_in_prod = torch.stack((torch.arange(S * G), torch.arange(G).repeat_interleave(S)), dim=0).contiguous()
+    # process_continuous_days.py:629  (station, grid) of every product node
+    A_src_in_sta = torch.stack((torch.arange(S).repeat(G), torch.arange(G).repeat_interleave(S)), dim=0).contiguous()
+    return A_sta, A_src, A_prod_sta, A_prod_src, A_src_in_prod, A_src_in_sta
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# a1 — pick window -> Slice / Mask (process_utils.py:460-642, use_sign_input False, trv_times given)
+# --------------------------------------------------------------------------------------------------------------------
+
+
+def input_time_axis(t0, max_t, kernel_sig_t, dt):
+    """abs_time_ref of process_utils.py:502 and its length; fp64, numpy arange semantics (start + i*dt)."""
+    t0 = float(t0)
+    t_offset = 3.0 * kernel_sig_t                                              # :500
+    ref = np.arange(t0 - t_offset, t0 + max_t + t_offset + dt, dt)             # :502
+    return ref, int(len(ref))
+
+
+def input_scatter(P, t0, ind_use, n_locs, A_src_in_sta, trv_times, max_t, kernel_sig_t, dt, return_parts=False):
+    """Restates extract_input_from_data (process_utils.py:460-629).
+
+    P [n,5] float64 (time, station, amp, prob, phase 0/1); ind_use int array of used (absolute) station ids;
+    A_src_in_sta int [2,P] (row 0 = index into ind_use, row 1 = grid node); trv_times fp32 [G, n_locs, 2].
+    Returns Slice [P,4] fp32, Mask [P,4] fp32 (and, with return_parts, the per-station series and the integer maps).
+
+    Stations without a pick in the window read zeros in the reference (they are left out of `ind_unique`, :490, and of
+    `ifind`, :586); here every used station owns a (possibly all-zero) series, which gives the same values.
+    """
+    P = np.asarray(P, dtype=np.float64)
+    t0 = float(t0)
+    ind_use = np.asarray(ind_use).astype('int')
+    A = np.asarray(A_src_in_sta).astype('int')
+    S_use = len(ind_use)
+    ref, n_ts = input_time_axis(t0, max_t, kernel_sig_t, dt)
+
+    keep = (P[:, 0] > (t0 - 2.0 * kernel_sig_t)) & (P[:, 0] < (t0 + max_t + 2.0 * kernel_sig_t))   # :476
+    Pw = P[keep]
+    perm = -1 * np.ones(n_locs, dtype='int')
+    perm[ind_use] = np.arange(S_use)                                                               # :485-486
+    sta_loc = perm[Pw[:, 1].astype('int')]
+    Pw, sta_loc = Pw[sta_loc > -1], sta_loc[sta_loc > -1]                                          # :480-482
+
+    n_extra = np.ceil(3 * kernel_sig_t / dt)                                                       # :520
+    offs = np.arange(-n_extra, n_extra + 1).astype('int')                                          # :521
+    series = np.zeros((2, S_use * n_ts), dtype=np.float32)
+    for ph in (0, 1):
+        sel = np.where(Pw[:, 4] == ph)[0]                                                          # :508-509
+        near = ((Pw[sel, 0] - ref[0]) / dt).astype('int')                                          # :515-516
+        idx = near.reshape(-1, 1) + offs.reshape(1, -1)                                            # :535
+        ok = (idx >= 0) & (idx < n_ts)                                                             # :538
+        idx = np.minimum(np.maximum(0, idx), n_ts - 1)                                             # :541
+        dtv = Pw[sel, 0].reshape(-1, 1).repeat(len(offs), axis=1) - ref[idx]                       # :544
+        vals = (ok * np.exp(-0.5 * (dtv ** 2) / (kernel_sig_t ** 2))).reshape(-1)                  # :546
+        w = (idx + sta_loc[sel].reshape(-1, 1) * n_ts).reshape(-1)                                 # :557
+        np.maximum.at(series[ph], w, vals.astype(np.float32))                                      # :563 scatter-max, 0 fill
+    series = series.reshape(2, S_use, n_ts)
+    series[:, :, 0] = 0.0                                                                          # :565-568
+    series[:, :, n_ts - 1] = 0.0
+    either = series.max(axis=0)                                                                    # :569
+
+    # :599  fp32 travel time + fp64 t0 - fp64 ref[0], divided by fp64 dt, truncated toward zero
+    tb = ((trv_times[A[1], ind_use[A[0]], :] + np.array([t0]) - ref[0]) / dt).astype('int')
+    inb = (tb >= 0) & (tb < n_ts)
+    tbc = np.clip(tb, 0, n_ts - 1)
+    s = A[0]
+    f0 = np.where(inb[:, 0], either[s, tbc[:, 0]], 0.0)                                            # :605
+    f1 = np.where(inb[:, 1], either[s, tbc[:, 1]], 0.0)                                            # :606
+    f2 = np.where(inb[:, 0], series[0, s, tbc[:, 0]], 0.0)                                         # :607
+    f3 = np.where(inb[:, 1], series[1, s, tbc[:, 1]], 0.0)                                         # :608
+    Slice = np.stack((f0, f1, f2, f3), axis=1).astype(np.float32)                                  # :627-628
+    Mask = (np.abs(Slice) > 0.01).astype(np.float32)                                               # :629
+    if return_parts:
+        return Slice, Mask, dict(series=series, time_bin=tb.astype(np.int64), n_ts=n_ts, ref0=float(ref[0]),
+                                 n_picks=int(len(Pw)))
+    return Slice, Mask
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# a2 — DataAggregation (module.py:52-98)
+# --------------------------------------------------------------------------------------------------------------------
+
+
+def data_aggregation(sd, pre, Slice, Mask, A_in_sta, A_in_src, return_parts=False):
+    """module.py:85-98.  `pre` is the state_dict prefix ('DataAggregation.')."""
+    n = Slice.shape[0]
+
+    def agg(edges, x):
+        return propagate_mean(x.index_select(0, edges[0]), edges[1], n)
+
+    tr0 = _prelu(sd, pre + 'activate', _lin(sd, pre + 'init_trns', torch.cat((Slice, Mask), dim=-1)))        # :87-88
+    tr1 = _lin(sd, pre + 'l1_t1_2', torch.cat((tr0, agg(A_in_sta, _prelu(sd, pre + 'activate11', tr0)), Mask), dim=1))
+    tr2 = _lin(sd, pre + 'l1_t2_2', torch.cat((tr0, agg(A_in_src, _prelu(sd, pre + 'activate12', tr0)), Mask), dim=1))
+    tr = _prelu(sd, pre + 'activate1', torch.cat((tr1, tr2), dim=1))                                          # :90-92
+    a = _prelu(sd, pre + 'activate21', _lin(sd, pre + 'l2_t1_1', tr))
+    b = _prelu(sd, pre + 'activate22', _lin(sd, pre + 'l2_t2_1', tr))
+    o1 = _lin(sd, pre + 'l2_t1_2', torch.cat((tr, agg(A_in_sta, a), Mask), dim=1))                            # :94
+    o2 = _lin(sd, pre + 'l2_t2_2', torch.cat((tr, agg(A_in_src, b), Mask), dim=1))                            # :95
+    out = _prelu(sd, pre + 'activate2', torch.cat((o1, o2), dim=1))                                           # :96
+    if return_parts:
+        return out, dict(tr0=tr0, tr=tr)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# a3 — BipartiteGraphOperator (module.py:214-229)
+# --------------------------------------------------------------------------------------------------------------------
+
+
+def bipartite_read_in(sd, pre, x_latent, edge_attr, edge_index, Mask):
+    """module.py:224-229: per product node MLP, masked, summed onto its grid node, then a per-grid-node MLP."""
+    M = int(edge_index[1].max()) + 1                                                                          # :227
+    h = Mask.max(1, keepdim=True)[0] * _prelu(sd, pre + 'activate1',
+                                              _lin(sd, pre + 'fc1', torch.cat((x_latent, edge_attr), dim=-1)))
+    xg = propagate_sum(h.index_select(0, edge_index[0]), edge_index[1], M)
+    return _prelu(sd, pre + 'activate2', _lin(sd, pre + 'fc2', xg))
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# a4 — SpatialAggregation (module.py:231-249)
+# --------------------------------------------------------------------------------------------------------------------
+
+
+def spatial_aggregation(sd, pre, x, A_src, pos, scale_rel):
+    """module.py:243-249.  The 'global' feature is a mean over EDGES of PReLU3(fglobal(x_j)) (:249)."""
+    n = x.shape[0]
+    p = pos / scale_rel
+    xj = x.index_select(0, A_src[0])
+    glob = _prelu(sd, pre + 'activate3', _lin(sd, pre + 'fglobal', xj)).mean(0, keepdim=True)
+    msg = _prelu(sd, pre + 'activate1', _lin(sd, pre + 'fc1', torch.cat(
+        (xj, p.index_select(0, A_src[1]) - p.index_select(0, A_src[0]), glob.repeat(xj.shape[0], 1)), dim=-1)))
+    agg = propagate_mean(msg, A_src[1], n)
+    return _prelu(sd, pre + 'activate2', _lin(sd, pre + 'fc2', torch.cat((x, agg), dim=-1)))
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# a5 — read-out heads (module.py:251-331) and the whole forward_fixed_source (module.py:999-1020)
+# --------------------------------------------------------------------------------------------------------------------
+
+
+def spatial_direct(sd, pre, x):
+    """module.py:251-260."""
+    return _prelu(sd, pre + 'activate', _lin(sd, pre + 'f_direct', x))
+
+
+def spatial_attention(sd, pre, x, x_query, x_context, scale_rel, k=10, n_heads=5, n_latent=15, edge_index=None):
+    """module.py:280-297 (the f_queries variant of the current code)."""
+    if edge_index is None:
+        edge_index = knn(x_context / 1000.0, x_query / 1000.0, k).flip(0)                                     # :282
+    ea = (x_query.index_select(0, edge_index[1]) - x_context.index_select(0, edge_index[0])) / scale_rel     # :283
+    xj = x.index_select(0, edge_index[0])
+    q = _lin(sd, pre + 'f_queries', ea).view(-1, n_heads, n_latent)
+    c = _lin(sd, pre + 'f_context', torch.cat((xj, ea), dim=-1)).view(-1, n_heads, n_latent)
+    v = _lin(sd, pre + 'f_values', torch.cat((xj, ea), dim=-1)).view(-1, n_heads, n_latent)
+    alpha = _prelu(sd, pre + 'activate1', (q * c).sum(-1) / math.sqrt(n_latent))                              # :293
+    alpha = segment_softmax(alpha, edge_index[1], x_query.shape[0])
+    out = propagate_sum(alpha.unsqueeze(-1) * v, edge_index[1], x_query.shape[0])
+    return _prelu(sd, pre + 'activate2', _lin(sd, pre + 'proj', out.mean(1)))                                 # :285
+
+
+def temporal_attention(sd, pre, x, t_query, scale_t, n_heads=5, n_latent=15):
+    """module.py:325-331."""
+    c = _lin(sd, pre + 'f_context_2', _prelu(sd, pre + 'activate1', _lin(sd, pre + 'f_context_1', x)))
+    v = _lin(sd, pre + 'f_values_2', _prelu(sd, pre + 'activate2', _lin(sd, pre + 'f_values_1', x)))
+    q = _lin(sd, pre + 'temporal_query_2', _prelu(sd, pre + 'activate3',
+                                                   _lin(sd, pre + 'temporal_query_1', t_query / scale_t)))
+    c = c.view(-1, n_heads, n_latent)
+    v = v.view(-1, n_heads, n_latent)
+    q = q.view(-1, n_heads, n_latent)
+    s = (c.unsqueeze(1) * q.unsqueeze(0)).sum(-1, keepdim=True) / math.sqrt(n_latent)      # [N, T, heads, 1]
+    z = _prelu(sd, pre + 'activate4', (s * v.unsqueeze(1)).mean(2))                        # [N, T, latent]
+    return _lin(sd, pre + 'proj_2', _prelu(sd, pre + 'activate5', _lin(sd, pre + 'proj_1', z)))
+
+
+def front_end(sd, Slice, Mask, A_in_sta, A_in_src, read_in_attr, read_in_index, A_src, grid_cart, scale_rel,
+              return_parts=False):
+    """a2 -> a3 -> a4 x3: the product-graph front end of module.py:1010-1014."""
+    x_latent = data_aggregation(sd, 'DataAggregation.', Slice, Mask, A_in_sta, A_in_src)
+    r = bipartite_read_in(sd, 'Bipartite_ReadIn.', x_latent, read_in_attr, read_in_index, Mask)
+    x1 = spatial_aggregation(sd, 'SpatialAggregation1.', r, A_src, grid_cart, scale_rel)
+    x2 = spatial_aggregation(sd, 'SpatialAggregation2.', x1, A_src, grid_cart, scale_rel)
+    x3 = spatial_aggregation(sd, 'SpatialAggregation3.', x2, A_src, grid_cart, scale_rel)
+    if return_parts:
+        return x3, dict(x_latent=x_latent, read_in=r, sa1=x1, sa2=x2)
+    return x3
+
+
+def forward_fixed_source(sd, Slice, Mask, A_in_sta, A_in_src, read_in_attr, read_in_index, A_src, grid_cart,
+                         x_query_cart, t_query, scale_rel, scale_t, return_parts=False, query_edges=None):
+    """module.py:999-1020 (use_absolute_pos False): returns y [G,T,1] and x [Q,T,1]."""
+    x_spatial, parts = front_end(sd, Slice, Mask, A_in_sta, A_in_src, read_in_attr, read_in_index, A_src, grid_cart,
+                                 scale_rel, return_parts=True)
+    y_latent = spatial_direct(sd, 'SpatialDirect.', x_spatial)
+    y = temporal_attention(sd, 'TemporalAttention.', y_latent, t_query, scale_t)
+    xq = spatial_attention(sd, 'SpatialAttention.', x_spatial, x_query_cart, grid_cart, scale_rel,
+                           edge_index=query_edges)
+    x = temporal_attention(sd, 'TemporalAttention.', xq, t_query, scale_t)
+    if return_parts:
+        parts.update(x_spatial=x_spatial, y_latent=y_latent, x_query_embed=xq)
+        return y, x, parts
+    return y, x
+
+
+def init_state(seed=2, scale=1.0):
+    """Random-init weights with the reference's key names / shapes (nn.Linear & nn.PReLU defaults are NOT reproduced —
+    tests that need the reference's own init load a golden state_dict instead).  Used for seeded synthetic parity."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def lin(name, n_in, n_out):
+        bound = scale / math.sqrt(n_in)
+        sd[name + '.weight'] = (torch.rand(n_out, n_in, generator=g) * 2 - 1) * bound
+        sd[name + '.bias'] = (torch.rand(n_out, generator=g) * 2 - 1) * bound
+
+    def prelu(name):
+        sd[name + '.weight'] = torch.full((1,), 0.25) + 0.1 * (torch.rand(1, generator=g) - 0.5)
+
+    p = 'DataAggregation.'
+    lin(p + 'init_trns', 8, 30); lin(p + 'l1_t1_1', 30, 30); lin(p + 'l1_t1_2', 64, 30)
+    lin(p + 'l1_t2_1', 4, 30); lin(p + 'l1_t2_2', 64, 30); lin(p + 'l2_t1_1', 60, 30); lin(p + 'l2_t1_2', 94, 15)
+    lin(p + 'l2_t2_1', 60, 30); lin(p + 'l2_t2_2', 94, 15)
+    for a in ('activate', 'activate11', 'activate12', 'activate1', 'activate21', 'activate22', 'activate2'):
+        prelu(p + a)
+    p = 'Bipartite_ReadIn.'
+    lin(p + 'fc1', 33, 30); lin(p + 'fc2', 30, 15); prelu(p + 'activate1'); prelu(p + 'activate2')
+    for i, cin in ((1, 15), (2, 30), (3, 30)):
+        p = 'SpatialAggregation%d.' % i
+        lin(p + 'fc1', cin + 8, 30); lin(p + 'fc2', 30 + cin, 30); lin(p + 'fglobal', cin, 5)
+        prelu(p + 'activate1'); prelu(p + 'activate2'); prelu(p + 'activate3')
+    p = 'SpatialDirect.'
+    lin(p + 'f_direct', 30, 30); prelu(p + 'activate')
+    p = 'SpatialAttention.'
+    sd[p + 'param_vector'] = torch.rand(1, 5, 15, generator=g) - 0.5
+    lin(p + 'f_queries', 3, 75); lin(p + 'f_context', 33, 75); lin(p + 'f_values', 33, 75)
+    lin(p + 'f_direct', 30, 30); lin(p + 'proj', 15, 30); prelu(p + 'activate1'); prelu(p + 'activate2')
+    p = 'TemporalAttention.'
+    lin(p + 'temporal_query_1', 1, 30); lin(p + 'temporal_query_2', 30, 75)
+    lin(p + 'f_context_1', 30, 30); lin(p + 'f_context_2', 30, 75)
+    lin(p + 'f_values_1', 30, 30); lin(p + 'f_values_2', 30, 75)
+    lin(p + 'proj_1', 15, 30); lin(p + 'proj_2', 30, 1)
+    for a in ('activate1', 'activate2', 'activate3', 'activate4', 'activate5'):
+        prelu(p + a)
+    return sd

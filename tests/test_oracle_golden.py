@@ -1,0 +1,73 @@
+"""The oracle restatement against the reference's own outputs (tests/golden, made by oracle/gen_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import genie_oracle as go
+
+SYNTH = ['c1_10x100', 'mid_36of40x300', 'small_6x40']
+
+
+def _graphs(d):
+    S = len(d['ind_use'])
+    G = d['grid'].shape[0]
+    out = go.build_adjacencies_dense(d['sta'][d['ind_use']], d['grid'], int(d['k_sta']), int(d['k_spc']))
+    return (S, G) + tuple(out)
+
+
+@pytest.mark.parametrize('name', SYNTH)
+def test_adjacencies_match_reference(name):
+    d, _ = load_golden(name)
+    S, G, A_sta, A_src, A_ps, A_pg, A_sip, A_sis = _graphs(d)
+    assert np.array_equal(A_sta.numpy(), d['A_sta_sta'])
+    assert np.array_equal(A_src.numpy(), d['A_src_src'])
+    assert A_ps.shape[1] == A_sta.shape[1] * G and A_pg.shape[1] == A_src.shape[1] * S
+
+
+@pytest.mark.parametrize('name', SYNTH)
+def test_input_scatter_bit_exact(name):
+    d, _ = load_golden(name)
+    S, G, A_sta, A_src, A_ps, A_pg, A_sip, A_sis = _graphs(d)
+    Slice, Mask, parts = go.input_scatter(d['picks'], float(d['t0']), d['ind_use'], d['sta'].shape[0], A_sis.numpy(),
+                                          d['trv_times'], float(d['max_t']), float(d['kernel_sig_t']), float(d['dt']),
+                                          return_parts=True)
+    assert parts['n_ts'] == int(d['n_ts']) and parts['ref0'] == float(d['ref0'])
+    assert np.array_equal(Slice, d['Slice'])          # same numpy expressions -> identical bits
+    assert np.array_equal(Mask, d['Mask'])
+    # per-station series against the reference's return_embedding output (only stations with picks are kept there)
+    perm = -np.ones(d['sta'].shape[0], dtype=int)
+    perm[d['ind_use']] = np.arange(S)
+    loc = perm[d['ind_unique']]
+    assert np.array_equal(parts['series'][0][loc], d['embed_p'])
+    assert np.array_equal(parts['series'][1][loc], d['embed_s'])
+    rest = np.setdiff1d(np.arange(S), loc)
+    assert not parts['series'][:, rest].any()
+
+
+@pytest.mark.parametrize('name', SYNTH)
+def test_front_end_and_heads_match_reference(name):
+    d, sd = load_golden(name)
+    S, G, A_sta, A_src, A_ps, A_pg, A_sip, A_sis = _graphs(d)
+    Slice, Mask = torch.from_numpy(d['Slice']), torch.from_numpy(d['Mask'])
+    y, x, parts = go.forward_fixed_source(
+        sd, Slice, Mask, A_ps, A_pg, torch.from_numpy(d['read_in_attr']), A_sip, A_src,
+        torch.from_numpy(d['grid']).float(), torch.from_numpy(d['x_query']).float(),
+        torch.from_numpy(d['t_query']).float().reshape(-1, 1), float(d['scale_rel']), float(d['scale_t']),
+        return_parts=True)
+    for key in ('x_latent', 'read_in', 'sa1', 'sa2', 'x_spatial', 'y_latent', 'x_query_embed'):
+        assert rel_err(parts[key].numpy(), d[key]) < 2e-6, key
+    assert rel_err(y.numpy(), d['y']) < 2e-6
+    assert rel_err(x.numpy(), d['x']) < 2e-6
+
+
+def test_mean_of_empty_neighbourhood_is_zero():
+    msg = torch.ones(3, 2)
+    out = go.propagate_mean(msg, torch.tensor([0, 0, 2]), 4)
+    assert out.tolist() == [[1.0, 1.0], [0.0, 0.0], [1.0, 1.0], [0.0, 0.0]]
+
+
+def test_time_axis_bin_count_follows_fp64():
+    # 3*3.5/0.35 = 30.000000000000004 in fp64 -> ceil 31 -> 63 bins
+    assert np.ceil(3 * 3.5 / np.round(3.5 / 10.0, 2)) == 31
+    assert np.ceil(3 * 3.0 / np.round(3.0 / 10.0, 2)) == 30
