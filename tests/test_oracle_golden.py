@@ -6,7 +6,7 @@ import torch
 from conftest import load_golden, rel_err
 from oracle import genie_oracle as go
 
-SYNTH = ['c1_10x100', 'mid_36of40x300', 'small_6x40']
+SYNTH = ['c1_10x100', 'mid_36of40x300', 'small_6x40', 'ferndale_t38940']
 
 
 def _graphs(d):
@@ -71,3 +71,16 @@ def test_time_axis_bin_count_follows_fp64():
     # 3*3.5/0.35 = 30.000000000000004 in fp64 -> ceil 31 -> 63 bins
     assert np.ceil(3 * 3.5 / np.round(3.5 / 10.0, 2)) == 31
     assert np.ceil(3 * 3.0 / np.round(3.0 / 10.0, 2)) == 30
+
+
+def test_ferndale_known_answers():
+    """Digests of the reference run on Examples/Ferndale.zip agree with the survey's independent run."""
+    d, _ = load_golden('ferndale_t38940')
+    assert d['Slice'].shape == (11550, 4) and int((d['Slice'] != 0).sum()) == 23047 and int(d['Mask'].sum()) == 22701
+    assert abs(float(d['Slice'].astype(np.float64).sum()) - 12107.058853) < 1e-3
+    assert abs(float(d['x_latent'].astype(np.float64).sum()) - 33790.148093) < 5e-2
+    assert abs(float(np.abs(d['x_latent'].astype(np.float64)).sum()) - 45289.203036) < 5e-2
+    assert abs(float(d['x_latent'].max()) - 3.682671) < 1e-5
+    assert abs(float(d['read_in'].astype(np.float64).sum()) - 901.758727) < 1e-2
+    assert abs(float(d['x_spatial'].max()) - 7.177079) < 1e-5
+    assert abs(float(d['y'].max()) - 0.946654) < 1e-5
