@@ -1,0 +1,133 @@
+"""ctypes binding of include/genie_b200.h (libgenie_b200.so).
+
+This is the stub a maintainer of the reference would add to call the B200 library from `module.py` /
+`process_utils.py`.  torch is used only to own device memory and streams: every call receives raw
+device pointers (`tensor.data_ptr()`) and the current CUDA stream handle.
+
+There is no CPU fallback: if the library is missing it is built with nvcc; if that is impossible, or no CUDA device is
+present when an op is called, an exception is raised.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, 'libgenie_b200.so')
+_lib = None
+
+GRAPH_CARTESIAN, GRAPH_EXPLICIT = 0, 1
+
+c_f32p = ctypes.c_void_p   # device pointers are passed as opaque addresses
+
+
+class GraphDesc(ctypes.Structure):
+    _fields_ = [('mode', ctypes.c_int32), ('n_sta', ctypes.c_int32), ('n_grid', ctypes.c_int32),
+                ('reserved', ctypes.c_int32), ('n_prod', ctypes.c_int64),
+                ('sta_rowptr', ctypes.c_void_p), ('sta_col', ctypes.c_void_p),
+                ('src_rowptr', ctypes.c_void_p), ('src_col', ctypes.c_void_p),
+                ('grid_rowptr', ctypes.c_void_p), ('grid_col', ctypes.c_void_p),
+                ('grid_outdeg', ctypes.c_void_p), ('prod_grid', ctypes.c_void_p)]
+
+
+class Linear(ctypes.Structure):
+    _fields_ = [('weight', ctypes.c_void_p), ('bias', ctypes.c_void_p)]
+
+
+class SAWeights(ctypes.Structure):
+    _fields_ = [('fc1', Linear), ('fc2', Linear), ('fglobal', Linear),
+                ('activate1', ctypes.c_void_p), ('activate2', ctypes.c_void_p), ('activate3', ctypes.c_void_p)]
+
+
+class FrontendWeights(ctypes.Structure):
+    _fields_ = [('da_init_trns', Linear), ('da_l1_t1_2', Linear), ('da_l1_t2_2', Linear),
+                ('da_l2_t1_1', Linear), ('da_l2_t2_1', Linear), ('da_l2_t1_2', Linear), ('da_l2_t2_2', Linear),
+                ('da_activate', ctypes.c_void_p), ('da_activate11', ctypes.c_void_p),
+                ('da_activate12', ctypes.c_void_p), ('da_activate1', ctypes.c_void_p),
+                ('da_activate21', ctypes.c_void_p), ('da_activate22', ctypes.c_void_p),
+                ('da_activate2', ctypes.c_void_p),
+                ('ri_fc1', Linear), ('ri_fc2', Linear),
+                ('ri_activate1', ctypes.c_void_p), ('ri_activate2', ctypes.c_void_p),
+                ('sa', SAWeights * 3)]
+
+
+class InputParams(ctypes.Structure):
+    _fields_ = [('t0', ctypes.c_double), ('max_t', ctypes.c_double), ('kernel_sig_t', ctypes.c_double),
+                ('dt', ctypes.c_double), ('ref0', ctypes.c_double), ('ref_step', ctypes.c_double),
+                ('n_ts', ctypes.c_int32), ('n_extra', ctypes.c_int32), ('n_locs', ctypes.c_int32),
+                ('n_sta_use', ctypes.c_int32)]
+
+
+# name -> (restype, argtypes); every symbol include/genie_b200.h declares
+_P = ctypes.c_void_p
+SIGNATURES = {
+    'genie_last_error': (ctypes.c_char_p, []),
+    'genie_abi_version': (ctypes.c_int, []),
+    'genie_launch_count': (ctypes.c_int64, []),
+    'genie_plan_create': (ctypes.c_int, [ctypes.POINTER(GraphDesc), ctypes.POINTER(_P)]),
+    'genie_plan_destroy': (None, [_P]),
+    'genie_plan_workspace_bytes': (ctypes.c_size_t, [_P]),
+    'genie_frontend_packed_floats': (ctypes.c_size_t, []),
+    'genie_frontend_pack_weights': (ctypes.c_int, [ctypes.POINTER(FrontendWeights), _P, _P]),
+    'genie_input_scatter_fwd': (ctypes.c_int, [_P, ctypes.POINTER(InputParams), _P, ctypes.c_int64, _P, _P, _P, _P, _P,
+                                               _P, _P, _P, _P, _P]),
+    'genie_data_aggregation_fwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    'genie_bipartite_readin_fwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    'genie_spatial_aggregation_fwd': (ctypes.c_int, [_P, _P, ctypes.c_int32, _P, _P, ctypes.c_float, _P, _P, _P]),
+    'genie_frontend_fwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _P, ctypes.c_float, _P, _P, _P, _P, _P]),
+}
+
+
+class GenieError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load(build_if_missing=True):
+    """Load libgenie_b200.so (building it in-tree first if it is absent and nvcc is available)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        if not build_if_missing:
+            raise GenieError('libgenie_b200.so is missing: run `python -m genie_b200.build`')
+        from . import build as _build
+        _build.build()
+    lib = ctypes.CDLL(_LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError here = header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if lib.genie_abi_version() != 1:
+        raise GenieError('libgenie_b200.so ABI version mismatch')
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise GenieError('libgenie_b200: %s (status %d)' % (load().genie_last_error().decode(), rc))
+
+
+def dptr(t, dtype=None, name='tensor'):
+    """Raw device address of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise GenieError('%s must live on a CUDA device (there is no CPU path)' % name)
+    if not t.is_contiguous():
+        raise GenieError('%s must be contiguous' % name)
+    if dtype is not None and t.dtype != dtype:
+        raise GenieError('%s must be %s, got %s' % (name, dtype, t.dtype))
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def launch_count():
+    return int(load().genie_launch_count())

@@ -1,0 +1,225 @@
+// extern "C" surface of libgenie_b200.so (declared in include/genie_b200.h).
+#include <atomic>
+#include <new>
+
+#include "internal.h"
+
+using namespace gl;
+
+namespace {
+thread_local std::string g_last_error;
+std::atomic<int64_t> g_launches{0};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+}  // namespace
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+Workspace carve_workspace(const genie_plan* p, void* base) {
+    Workspace w;
+    const size_t P = (size_t)p->g.n_prod, G = (size_t)p->g.n_grid;
+    size_t off = 0;
+    auto take = [&](size_t n_floats) {
+        float* ptr = base ? reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off) : nullptr;
+        off += align_up(n_floats * sizeof(float), 256);
+        return ptr;
+    };
+    w.tr0 = take(P * LD_TR0);
+    w.zc = take(P * LD_ZC);
+    w.va = take(P * LD_V);
+    w.vb = take(P * LD_V);
+    w.xg = take(G * 32);
+    w.r = take(G * 16);
+    w.px = take(G * 32);
+    w.sa_a = take(G * 32);
+    w.sa_b = take(G * 32);
+    w.partial = take(1024 * 8);
+    w.bytes = off;
+    return w;
+}
+
+extern "C" {
+
+const char* genie_last_error(void) { return g_last_error.c_str(); }
+int genie_abi_version(void) { return GENIE_B200_ABI_VERSION; }
+int64_t genie_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int genie_plan_create(const genie_graph_desc_t* d, genie_plan_t** out) {
+    if (!d || !out) {
+        set_error("genie_plan_create: null argument");
+        return GENIE_ERR_INVALID;
+    }
+    if (d->mode != GENIE_GRAPH_CARTESIAN && d->mode != GENIE_GRAPH_EXPLICIT) {
+        set_error("genie_plan_create: unknown graph mode");
+        return GENIE_ERR_INVALID;
+    }
+    if (d->n_grid < 0 || d->n_prod < 0 || d->n_sta < 0) {
+        set_error("genie_plan_create: negative size");
+        return GENIE_ERR_INVALID;
+    }
+    if (d->mode == GENIE_GRAPH_CARTESIAN && (int64_t)d->n_sta * d->n_grid != d->n_prod) {
+        set_error("genie_plan_create: CARTESIAN mode needs n_prod == n_sta * n_grid");
+        return GENIE_ERR_INVALID;
+    }
+    if (d->mode == GENIE_GRAPH_EXPLICIT && d->n_prod > 0 && d->prod_grid == nullptr) {
+        set_error("genie_plan_create: EXPLICIT mode needs prod_grid");
+        return GENIE_ERR_INVALID;
+    }
+    if (d->n_prod > 0 && (!d->sta_rowptr || !d->src_rowptr)) {
+        set_error("genie_plan_create: missing product-graph row pointers");
+        return GENIE_ERR_INVALID;
+    }
+    if (d->n_grid > 0 && (!d->grid_rowptr || !d->grid_outdeg)) {
+        set_error("genie_plan_create: missing grid-graph arrays");
+        return GENIE_ERR_INVALID;
+    }
+    genie_plan* p = new (std::nothrow) genie_plan();
+    if (!p) {
+        set_error("genie_plan_create: out of host memory");
+        return GENIE_ERR_INVALID;
+    }
+    p->g = *d;
+    p->n_edges_grid = -1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) {
+        set_error(std::string("genie_plan_create: no usable CUDA device: ") + cudaGetErrorString(e));
+        delete p;
+        return GENIE_ERR_CUDA;
+    }
+    *out = p;
+    return GENIE_OK;
+}
+
+void genie_plan_destroy(genie_plan_t* plan) { delete plan; }
+
+size_t genie_plan_workspace_bytes(const genie_plan_t* plan) {
+    if (!plan) return 0;
+    return carve_workspace(plan, nullptr).bytes;
+}
+
+size_t genie_frontend_packed_floats(void) { return (size_t)PACKED_FLOATS; }
+
+int genie_frontend_pack_weights(const genie_frontend_weights_t* w, float* packed_dev, void* stream) {
+    if (!w || !packed_dev) {
+        set_error("genie_frontend_pack_weights: null argument");
+        return GENIE_ERR_INVALID;
+    }
+    const void* const* ptrs = reinterpret_cast<const void* const*>(w);
+    for (size_t i = 0; i < sizeof(*w) / sizeof(void*); ++i) {
+        if (ptrs[i] == nullptr) {
+            set_error("genie_frontend_pack_weights: null weight pointer at slot " + std::to_string(i));
+            return GENIE_ERR_INVALID;
+        }
+    }
+    return launch_pack_weights(w, packed_dev, static_cast<cudaStream_t>(stream));
+}
+
+int genie_input_scatter_fwd(const genie_plan_t* plan, const genie_input_params_t* prm, const double* picks_dev,
+                            int64_t n_picks, const int32_t* sta_perm_dev, const int32_t* ind_use_dev,
+                            const float* trv_times_dev, const int32_t* node_sta_dev, const int32_t* node_grid_dev,
+                            float* series_dev, float* slice_out_dev, float* mask_out_dev, int64_t* time_bin_out_dev,
+                            void* stream) {
+    if (!plan || !prm || !sta_perm_dev || !ind_use_dev || !trv_times_dev || !series_dev || !slice_out_dev ||
+        !mask_out_dev || (n_picks > 0 && !picks_dev)) {
+        set_error("genie_input_scatter_fwd: null argument");
+        return GENIE_ERR_INVALID;
+    }
+    if (prm->n_ts < 2 || prm->n_extra < 0 || prm->n_sta_use <= 0 || prm->n_locs <= 0 || !(prm->dt > 0.0)) {
+        set_error("genie_input_scatter_fwd: bad input parameters");
+        return GENIE_ERR_INVALID;
+    }
+    const bool have_nodes = node_sta_dev != nullptr && node_grid_dev != nullptr;
+    if ((node_sta_dev != nullptr) != (node_grid_dev != nullptr) ||
+        (plan->g.mode == GENIE_GRAPH_EXPLICIT && !have_nodes)) {
+        set_error("genie_input_scatter_fwd: node_sta/node_grid must both be given (required in EXPLICIT mode)");
+        return GENIE_ERR_INVALID;
+    }
+    if (plan->g.mode == GENIE_GRAPH_CARTESIAN && !have_nodes && plan->g.n_sta != prm->n_sta_use) {
+        set_error("genie_input_scatter_fwd: n_sta_use differs from the plan's n_sta");
+        return GENIE_ERR_INVALID;
+    }
+    return launch_input_scatter(plan, prm, picks_dev, n_picks, sta_perm_dev, ind_use_dev, trv_times_dev, node_sta_dev,
+                                node_grid_dev, series_dev, slice_out_dev, mask_out_dev, time_bin_out_dev,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int genie_data_aggregation_fwd(const genie_plan_t* plan, const float* packed_dev, const float* slice_dev,
+                               const float* mask_dev, float* x_latent_out_dev, void* workspace_dev, void* stream) {
+    if (!plan || !packed_dev || !slice_dev || !mask_dev || !x_latent_out_dev || !workspace_dev) {
+        set_error("genie_data_aggregation_fwd: null argument");
+        return GENIE_ERR_INVALID;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Workspace w = carve_workspace(plan, workspace_dev);
+    int rc;
+    if ((rc = launch_da_init(plan, packed_dev, slice_dev, mask_dev, w.tr0, st))) return rc;
+    if ((rc = launch_da_layer1(plan, packed_dev, w.tr0, mask_dev, w.zc, w.va, w.vb, st))) return rc;
+    return launch_da_layer2_readin(plan, packed_dev, L2_GATHER | L2_STORE_LATENT, w.zc, w.va, w.vb, nullptr,
+                                   x_latent_out_dev, nullptr, mask_dev, nullptr, st);
+}
+
+int genie_bipartite_readin_fwd(const genie_plan_t* plan, const float* packed_dev, const float* x_latent_dev,
+                               const float* edge_attr_dev, const float* mask_dev, float* out_dev, void* workspace_dev,
+                               void* stream) {
+    if (!plan || !packed_dev || !x_latent_dev || !edge_attr_dev || !mask_dev || !out_dev || !workspace_dev) {
+        set_error("genie_bipartite_readin_fwd: null argument");
+        return GENIE_ERR_INVALID;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Workspace w = carve_workspace(plan, workspace_dev);
+    GENIE_CUDA_CHECK(cudaMemsetAsync(w.xg, 0, (size_t)plan->g.n_grid * 32 * sizeof(float), st));
+    int rc;
+    if ((rc = launch_da_layer2_readin(plan, packed_dev, L2_READIN, nullptr, nullptr, nullptr, x_latent_dev, nullptr,
+                                      edge_attr_dev, mask_dev, w.xg, st)))
+        return rc;
+    return launch_readin_finalize(plan, packed_dev, w.xg, out_dev, 15, st);
+}
+
+int genie_spatial_aggregation_fwd(const genie_plan_t* plan, const float* packed_dev, int32_t layer, const float* x_dev,
+                                  const float* pos_dev, float scale_rel, float* out_dev, void* workspace_dev,
+                                  void* stream) {
+    if (!plan || !packed_dev || !x_dev || !pos_dev || !out_dev || !workspace_dev) {
+        set_error("genie_spatial_aggregation_fwd: null argument");
+        return GENIE_ERR_INVALID;
+    }
+    Workspace w = carve_workspace(plan, workspace_dev);
+    return launch_spatial_aggregation(plan, packed_dev, layer, x_dev, layer == 0 ? 15 : 30, pos_dev, scale_rel, w.px,
+                                      w.partial, out_dev, 30, static_cast<cudaStream_t>(stream));
+}
+
+int genie_frontend_fwd(const genie_plan_t* plan, const float* packed_dev, const float* slice_dev,
+                       const float* mask_dev, const float* edge_attr_dev, const float* pos_dev, float scale_rel,
+                       float* x_latent_out_dev, float* readin_out_dev, float* x_spatial_out_dev, void* workspace_dev,
+                       void* stream) {
+    if (!plan || !packed_dev || !slice_dev || !mask_dev || !edge_attr_dev || !pos_dev || !x_spatial_out_dev ||
+        !workspace_dev) {
+        set_error("genie_frontend_fwd: null argument");
+        return GENIE_ERR_INVALID;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Workspace w = carve_workspace(plan, workspace_dev);
+    int rc;
+    GENIE_CUDA_CHECK(cudaMemsetAsync(w.xg, 0, (size_t)plan->g.n_grid * 32 * sizeof(float), st));
+    if ((rc = launch_da_init(plan, packed_dev, slice_dev, mask_dev, w.tr0, st))) return rc;
+    if ((rc = launch_da_layer1(plan, packed_dev, w.tr0, mask_dev, w.zc, w.va, w.vb, st))) return rc;
+    const int mode = L2_GATHER | L2_READIN | (x_latent_out_dev ? L2_STORE_LATENT : 0);
+    if ((rc = launch_da_layer2_readin(plan, packed_dev, mode, w.zc, w.va, w.vb, nullptr, x_latent_out_dev,
+                                      edge_attr_dev, mask_dev, w.xg, st)))
+        return rc;
+    float* r = readin_out_dev ? readin_out_dev : w.r;
+    const int ld_r = readin_out_dev ? 15 : 16;
+    if ((rc = launch_readin_finalize(plan, packed_dev, w.xg, r, ld_r, st))) return rc;
+    if ((rc = launch_spatial_aggregation(plan, packed_dev, 0, r, ld_r, pos_dev, scale_rel, w.px, w.partial, w.sa_a, 32,
+                                         st)))
+        return rc;
+    if ((rc = launch_spatial_aggregation(plan, packed_dev, 1, w.sa_a, 32, pos_dev, scale_rel, w.px, w.partial, w.sa_b,
+                                         32, st)))
+        return rc;
+    return launch_spatial_aggregation(plan, packed_dev, 2, w.sa_b, 32, pos_dev, scale_rel, w.px, w.partial,
+                                      x_spatial_out_dev, 30, st);
+}
+
+}  // extern "C"

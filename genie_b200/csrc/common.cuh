@@ -1,0 +1,75 @@
+// Device helpers shared by the front-end kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "internal.h"
+
+#define FULL_MASK 0xffffffffu
+
+__device__ __forceinline__ float prelu(float x, float a) { return x >= 0.f ? x : a * x; }
+
+// acc[0..29] += a * wrow[0..29]; wrow is a 32-float, 16-byte aligned shared-memory row (same address for all lanes of
+// a warp -> broadcast, no bank conflicts).
+__device__ __forceinline__ void fma_row30(float (&acc)[30], float a, const float* __restrict__ wrow) {
+    const float4* w4 = reinterpret_cast<const float4*>(wrow);
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+        float4 w = w4[c];
+        acc[4 * c + 0] = fmaf(a, w.x, acc[4 * c + 0]);
+        acc[4 * c + 1] = fmaf(a, w.y, acc[4 * c + 1]);
+        acc[4 * c + 2] = fmaf(a, w.z, acc[4 * c + 2]);
+        acc[4 * c + 3] = fmaf(a, w.w, acc[4 * c + 3]);
+    }
+    float2 w = *reinterpret_cast<const float2*>(wrow + 28);
+    acc[28] = fmaf(a, w.x, acc[28]);
+    acc[29] = fmaf(a, w.y, acc[29]);
+}
+
+// acc[0..15] += a * wrow[0..15] (16-float aligned row).
+__device__ __forceinline__ void fma_row16(float (&acc)[16], float a, const float* __restrict__ wrow) {
+    const float4* w4 = reinterpret_cast<const float4*>(wrow);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float4 w = w4[c];
+        acc[4 * c + 0] = fmaf(a, w.x, acc[4 * c + 0]);
+        acc[4 * c + 1] = fmaf(a, w.y, acc[4 * c + 1]);
+        acc[4 * c + 2] = fmaf(a, w.z, acc[4 * c + 2]);
+        acc[4 * c + 3] = fmaf(a, w.w, acc[4 * c + 3]);
+    }
+}
+
+// Neighbour range of one edge type for product node i.
+struct NbrRange {
+    int64_t beg, end;   // positions in the col array
+    int64_t mul, add;   // neighbour node id = col * mul + add
+};
+
+__device__ __forceinline__ void node_ranges(const GraphView& gv, int64_t i, NbrRange& sta, NbrRange& src) {
+    if (gv.mode == GENIE_GRAPH_CARTESIAN) {
+        const int64_t g = i / gv.S;
+        const int64_t s = i - g * gv.S;
+        sta.beg = gv.sta_rowptr[s];
+        sta.end = gv.sta_rowptr[s + 1];
+        sta.mul = 1;
+        sta.add = g * gv.S;
+        src.beg = gv.src_rowptr[g];
+        src.end = gv.src_rowptr[g + 1];
+        src.mul = gv.S;
+        src.add = s;
+    } else {
+        sta.beg = gv.sta_rowptr[i];
+        sta.end = gv.sta_rowptr[i + 1];
+        sta.mul = 1;
+        sta.add = 0;
+        src.beg = gv.src_rowptr[i];
+        src.end = gv.src_rowptr[i + 1];
+        src.mul = 1;
+        src.add = 0;
+    }
+}
+
+__device__ __forceinline__ int node_grid(const GraphView& gv, int64_t i) {
+    return gv.mode == GENIE_GRAPH_CARTESIAN ? (int)(i / gv.S) : gv.prod_grid[i];
+}

@@ -1,0 +1,439 @@
+// DataAggregation (module.py:52-98) and BipartiteGraphOperator (module.py:214-229) forward kernels — generic path.
+//
+// The reference evaluates, per product node i (Slice/Mask rows x0 = [slice ‖ mask]):
+//   tr0 = PReLU_a (W0 x0)
+//   tr  = PReLU_1([W11 [tr0 ‖ mean_sta PReLU_11(tr0_j) ‖ mask] ‖ W12 [tr0 ‖ mean_src PReLU_12(tr0_j) ‖ mask]])
+//   out = PReLU_2([W21b [tr ‖ mean_sta a_j ‖ mask] ‖ W22b [tr ‖ mean_src b_j ‖ mask]]),  a = PReLU_21(W21a tr), b = ...
+// Three kernels, separated by the two global dependencies (neighbours' tr0, neighbours' a/b):
+//   da_init_kernel     x0 -> tr0                                                     (row stride 32 floats)
+//   da_layer1_kernel   gather tr0 -> tr -> {ca, cb, va, vb}, where the 15-wide halves of the last linear layer are
+//                      split by linearity:  W21b[tr ‖ mean a ‖ mask] = (W_tr tr + W_m mask + b) + mean_j (W_agg a_j)
+//                      = ca + mean_sta(va_j), so layer 2 gathers 15-wide rows instead of 30-wide ones.
+//   da_layer2_readin_kernel   gather va/vb -> x_latent -> (optional store) -> fc1, mask, sum over the node's grid
+//                      node (BipartiteGraphOperator) -> xg accumulator; readin_finalize_kernel applies fc2.
+// Warps gather (one product node per warp, lanes = channels: every neighbour row is one coalesced 128-byte / 64-byte
+// request); the dense per-node MLPs run thread-per-node on a transposed shared-memory feature tile with the weights
+// broadcast from shared memory.
+#include "common.cuh"
+
+using namespace gl;
+
+namespace {
+
+constexpr int TM = 128;        // product nodes per tile
+constexpr int LDF = TM + 1;    // feature-tile row stride (floats): conflict-free for both access patterns
+
+// --------------------------------------------------------------------------------------------------------------------
+// K1: tr0 = PReLU(init_trns([slice ‖ mask]))
+// --------------------------------------------------------------------------------------------------------------------
+constexpr int K1_THREADS = 256;
+
+__global__ void __launch_bounds__(K1_THREADS) da_init_kernel(const float* __restrict__ packed,
+                                                             const float* __restrict__ slice,
+                                                             const float* __restrict__ mask, float* __restrict__ tr0,
+                                                             int64_t P) {
+    __shared__ __align__(16) float sW[8 * LD + LD];
+    __shared__ __align__(16) float sOut[K1_THREADS * LD_TR0];
+    for (int i = threadIdx.x; i < 8 * LD + LD; i += K1_THREADS) sW[i] = packed[DA_W0 + i];
+    const float a0 = packed[DA_SLOPES + SL_A0];
+    __syncthreads();
+
+    const int64_t i0 = (int64_t)blockIdx.x * K1_THREADS;
+    const int n = threadIdx.x;
+    const int64_t i = i0 + n;
+    float acc[30];
+#pragma unroll
+    for (int o = 0; o < 30; ++o) acc[o] = sW[8 * LD + o];
+    if (i < P) {
+        const float4 sv = reinterpret_cast<const float4*>(slice)[i];
+        const float4 mv = reinterpret_cast<const float4*>(mask)[i];
+        fma_row30(acc, sv.x, sW + 0 * LD);
+        fma_row30(acc, sv.y, sW + 1 * LD);
+        fma_row30(acc, sv.z, sW + 2 * LD);
+        fma_row30(acc, sv.w, sW + 3 * LD);
+        fma_row30(acc, mv.x, sW + 4 * LD);
+        fma_row30(acc, mv.y, sW + 5 * LD);
+        fma_row30(acc, mv.z, sW + 6 * LD);
+        fma_row30(acc, mv.w, sW + 7 * LD);
+    }
+    // stage the row in shared memory (16-byte chunks XOR-swizzled by the row index: conflict-free), then write the
+    // tile out as one contiguous, fully coalesced block.
+    float4* srow = reinterpret_cast<float4*>(sOut + n * LD_TR0);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float4 v;
+        v.x = prelu(acc[(4 * c + 0) < 30 ? (4 * c + 0) : 0], a0);
+        v.y = prelu(acc[(4 * c + 1) < 30 ? (4 * c + 1) : 0], a0);
+        v.z = (4 * c + 2) < 30 ? prelu(acc[(4 * c + 2) < 30 ? (4 * c + 2) : 0], a0) : 0.f;
+        v.w = (4 * c + 3) < 30 ? prelu(acc[(4 * c + 3) < 30 ? (4 * c + 3) : 0], a0) : 0.f;
+        srow[c ^ (n & 7)] = v;
+    }
+    __syncthreads();
+    float4* dst = reinterpret_cast<float4*>(tr0 + i0 * LD_TR0);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int f = it * K1_THREADS + threadIdx.x;   // float4 index inside the tile
+        const int row = f >> 3, pos = f & 7;
+        if (i0 + row < P) dst[row * 8 + (pos ^ (row & 7))] = reinterpret_cast<const float4*>(sOut)[f];
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// gathers (one warp per target node, lanes = channels)
+// --------------------------------------------------------------------------------------------------------------------
+
+// mean over the neighbours of PReLU(X[j][lane], slope); X rows are 32 floats.  All 32 lanes participate.
+__device__ __forceinline__ float gather_mean32(const float* __restrict__ X, const NbrRange r,
+                                               const int32_t* __restrict__ col, float slope, int lane) {
+    float acc = 0.f;
+    for (int64_t e0 = r.beg; e0 < r.end; e0 += 32) {
+        const int cnt = (int)min((int64_t)32, r.end - e0);
+        const int32_t c = lane < cnt ? col[e0 + lane] : 0;
+        for (int u = 0; u < cnt; u += 8) {
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int64_t j = (int64_t)__shfl_sync(FULL_MASK, c, (u + q) & 31) * r.mul + r.add;
+                v[q] = (u + q) < cnt ? X[j * 32 + lane] : 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc += prelu(v[q], slope);
+        }
+    }
+    const int64_t deg = r.end - r.beg;
+    return deg > 0 ? acc / (float)deg : 0.f;
+}
+
+// Two 16-wide gathers at once: lanes 0-15 average rows of VA over range ra, lanes 16-31 rows of VB over range rb.
+__device__ __forceinline__ float gather_mean16x2(const float* __restrict__ VA, const float* __restrict__ VB,
+                                                 const NbrRange ra, const NbrRange rb,
+                                                 const int32_t* __restrict__ cola, const int32_t* __restrict__ colb,
+                                                 int lane) {
+    const int half = lane >> 4, l = lane & 15;
+    const NbrRange r = half ? rb : ra;
+    const float* __restrict__ V = half ? VB : VA;
+    const int32_t* __restrict__ col = half ? colb : cola;
+    const int64_t deg = r.end - r.beg;
+    const int64_t dmax = max(ra.end - ra.beg, rb.end - rb.beg);
+    float acc = 0.f;
+    for (int64_t e0 = 0; e0 < dmax; e0 += 16) {
+        const int cnt = (int)max((int64_t)0, min((int64_t)16, deg - e0));
+        const int32_t c = l < cnt ? col[r.beg + e0 + l] : 0;
+        const int cmax = (int)min((int64_t)16, dmax - e0);
+        for (int u = 0; u < cmax; u += 8) {
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int64_t j = (int64_t)__shfl_sync(FULL_MASK, c, (lane & 16) | ((u + q) & 15)) * r.mul + r.add;
+                v[q] = (u + q) < cnt ? V[j * LD_V + l] : 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc += v[q];
+        }
+    }
+    return deg > 0 ? acc / (float)deg : 0.f;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// K2: layer 1 (+ the node-local part of layer 2)
+// --------------------------------------------------------------------------------------------------------------------
+constexpr int K2_THREADS = 256;
+constexpr int K2_W_FLOATS = DA_END - DA_W11;
+constexpr int K2_F_ROWS = 94;   // 0-29 tr0 | 30-59 mean_sta | 60-89 mean_src | 90-93 mask ; rows 0-59 later hold tr
+constexpr size_t K2_SMEM = (size_t)(K2_W_FLOATS + K2_F_ROWS * LDF) * sizeof(float);
+
+__global__ void __launch_bounds__(K2_THREADS, 2)
+    da_layer1_kernel(const GraphView gv, const float* __restrict__ packed, const float* __restrict__ tr0,
+                     const float* __restrict__ mask, float* __restrict__ zc, float* __restrict__ va,
+                     float* __restrict__ vb, int64_t n_tiles) {
+    extern __shared__ __align__(16) float smem[];
+    float* sW = smem;                  // packed[DA_W11 .. DA_END)
+    float* F = smem + K2_W_FLOATS;     // [94][LDF]
+    {
+        const float4* src = reinterpret_cast<const float4*>(packed + DA_W11);
+        float4* dst = reinterpret_cast<float4*>(sW);
+        for (int i = threadIdx.x; i < K2_W_FLOATS / 4; i += K2_THREADS) dst[i] = src[i];
+    }
+    __syncthreads();
+    const float* sl = sW + (DA_SLOPES - DA_W11);
+    const float a11 = sl[SL_A11], a12 = sl[SL_A12], a1 = sl[SL_A1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = threadIdx.x & (TM - 1);
+    const int br = threadIdx.x >> 7;   // 0: station-edge branch (l*_t1_*), 1: source-edge branch (l*_t2_*)
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t i0 = tile * TM;
+        // ---- stage A: gather ------------------------------------------------------------------------------------------
+        for (int m = warp; m < TM; m += K2_THREADS / 32) {
+            const int64_t i = i0 + m;
+            float own = 0.f, m1 = 0.f, m2 = 0.f, mk = 0.f;
+            if (i < gv.P) {
+                NbrRange rs, rg;
+                node_ranges(gv, i, rs, rg);
+                own = tr0[i * LD_TR0 + lane];
+                m1 = gather_mean32(tr0, rs, gv.sta_col, a11, lane);
+                m2 = gather_mean32(tr0, rg, gv.src_col, a12, lane);
+                if (lane < 4) mk = mask[i * 4 + lane];
+            }
+            if (lane < 30) {
+                F[lane * LDF + m] = own;
+                F[(30 + lane) * LDF + m] = m1;
+                F[(60 + lane) * LDF + m] = m2;
+            }
+            if (lane < 4) F[(90 + lane) * LDF + m] = mk;
+        }
+        __syncthreads();
+        // ---- stage B: tr = PReLU1([l1_t1_2(..) ‖ l1_t2_2(..)]) ------------------------------------------------------
+        {
+            const float* W = sW + (br ? (DA_W12 - DA_W11) : 0);
+            const float* B = sW + ((br ? DA_B12 : DA_B11) - DA_W11);
+            float acc[30];
+#pragma unroll
+            for (int o = 0; o < 30; ++o) acc[o] = B[o];
+#pragma unroll 2
+            for (int k = 0; k < 30; ++k) fma_row30(acc, F[k * LDF + n], W + k * LD);
+            const float* Fm = F + (30 + 30 * br) * LDF;
+#pragma unroll 2
+            for (int k = 0; k < 30; ++k) fma_row30(acc, Fm[k * LDF + n], W + (30 + k) * LD);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) fma_row30(acc, F[(90 + k) * LDF + n], W + (60 + k) * LD);
+            __syncthreads();   // every thread has finished reading rows 0-89
+#pragma unroll
+            for (int o = 0; o < 30; ++o) F[(br * 30 + o) * LDF + n] = prelu(acc[o], a1);
+        }
+        __syncthreads();
+        // ---- stage C: h = PReLU(l2_t*_1 tr);  v = W_agg h;  c = W_tr tr + W_m mask + b ---------------------------------
+        {
+            const float* Wa = sW + ((br ? DA_W22A : DA_W21A) - DA_W11);
+            const float* Ba = sW + ((br ? DA_B22A : DA_B21A) - DA_W11);
+            const float ah = br ? sl[SL_A22] : sl[SL_A21];
+            float h[30];
+#pragma unroll
+            for (int o = 0; o < 30; ++o) h[o] = Ba[o];
+#pragma unroll 2
+            for (int k = 0; k < 60; ++k) fma_row30(h, F[k * LDF + n], Wa + k * LD);
+            float v[16];
+#pragma unroll
+            for (int o = 0; o < 16; ++o) v[o] = 0.f;
+            const float* Wv = sW + ((br ? DA_WVB : DA_WVA) - DA_W11);
+#pragma unroll
+            for (int k = 0; k < 30; ++k) fma_row16(v, prelu(h[k], ah), Wv + k * LD16);
+            const float* Wc = sW + ((br ? DA_WCB : DA_WCA) - DA_W11);
+            const float* Bc = sW + ((br ? DA_BCB : DA_BCA) - DA_W11);
+            float c[16];
+#pragma unroll
+            for (int o = 0; o < 16; ++o) c[o] = Bc[o];
+#pragma unroll 2
+            for (int k = 0; k < 60; ++k) fma_row16(c, F[k * LDF + n], Wc + k * LD16);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) fma_row16(c, F[(90 + k) * LDF + n], Wc + (60 + k) * LD16);
+            const int64_t i = i0 + n;
+            if (i < gv.P) {
+                float4* zp = reinterpret_cast<float4*>(zc + i * LD_ZC + br * 16);
+                float4* vp = reinterpret_cast<float4*>((br ? vb : va) + i * LD_V);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    zp[q] = make_float4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
+                    vp[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                }
+            }
+        }
+        __syncthreads();   // F is rewritten by the next tile's gather
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// K3: layer 2 aggregation -> x_latent -> BipartiteGraphOperator.fc1 / mask / sum over stations
+// --------------------------------------------------------------------------------------------------------------------
+constexpr int K3_THREADS = 256;
+constexpr int K3_W_FLOATS = RI_END - RI_WFC1;
+
+template <int MODE>
+__global__ void __launch_bounds__(K3_THREADS)
+    da_layer2_readin_kernel(const GraphView gv, const float* __restrict__ packed, const float* __restrict__ zc,
+                            const float* __restrict__ va, const float* __restrict__ vb,
+                            const float* __restrict__ latent_in, float* __restrict__ latent_out,
+                            const float* __restrict__ edge_attr, const float* __restrict__ mask,
+                            float* __restrict__ xg, int64_t n_tiles) {
+    __shared__ __align__(16) float sW[K3_W_FLOATS];
+    __shared__ float L[30 * LDF];     // x_latent tile, transposed
+    __shared__ float Hs[30 * LDF];    // masked fc1 output, transposed
+    __shared__ int gid[TM];
+    for (int i = threadIdx.x; i < K3_W_FLOATS; i += K3_THREADS) sW[i] = packed[RI_WFC1 + i];
+    const float a2 = packed[DA_SLOPES + SL_A2];
+    __syncthreads();
+    const float ri_a1 = sW[RI_SLOPES - RI_WFC1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t i0 = tile * TM;
+        if (MODE & L2_GATHER) {
+            const int half = lane >> 4, l = lane & 15;
+            for (int m = warp; m < TM; m += K3_THREADS / 32) {
+                const int64_t i = i0 + m;
+                float x = 0.f;
+                if (i < gv.P) {
+                    NbrRange rs, rg;
+                    node_ranges(gv, i, rs, rg);
+                    const float own = zc[i * LD_ZC + lane];
+                    const float mean = gather_mean16x2(va, vb, rs, rg, gv.sta_col, gv.src_col, lane);
+                    x = prelu(own + mean, a2);
+                }
+                if (l < 15) L[(half * 15 + l) * LDF + m] = x;
+            }
+        } else {
+            for (int idx = threadIdx.x; idx < TM * 30; idx += K3_THREADS) {
+                const int m = idx / 30, ch = idx - m * 30;
+                L[ch * LDF + m] = (i0 + m) < gv.P ? latent_in[i0 * 30 + idx] : 0.f;
+            }
+        }
+        __syncthreads();
+        if (MODE & L2_STORE_LATENT) {
+            for (int idx = threadIdx.x; idx < TM * 30; idx += K3_THREADS) {
+                const int m = idx / 30, ch = idx - m * 30;
+                if ((i0 + m) < gv.P) latent_out[i0 * 30 + idx] = L[ch * LDF + m];
+            }
+        }
+        if (MODE & L2_READIN) {
+            // fc1 split over two threads per node: outputs [0,16) and [16,32) (30, 31 are zero padding)
+            const int n = threadIdx.x & (TM - 1);
+            const int br = threadIdx.x >> 7;
+            const int64_t i = i0 + n;
+            float acc[16];
+#pragma unroll
+            for (int o = 0; o < 16; ++o) acc[o] = sW[(RI_BFC1 - RI_WFC1) + br * 16 + o];
+#pragma unroll 2
+            for (int k = 0; k < 30; ++k) fma_row16(acc, L[k * LDF + n], sW + k * LD + br * 16);
+            float mmax = 0.f;
+            if (i < gv.P) {
+                const float e0 = edge_attr[i * 3 + 0], e1 = edge_attr[i * 3 + 1], e2 = edge_attr[i * 3 + 2];
+                fma_row16(acc, e0, sW + 30 * LD + br * 16);
+                fma_row16(acc, e1, sW + 31 * LD + br * 16);
+                fma_row16(acc, e2, sW + 32 * LD + br * 16);
+                const float4 mv = reinterpret_cast<const float4*>(mask)[i];
+                mmax = fmaxf(fmaxf(mv.x, mv.y), fmaxf(mv.z, mv.w));
+            }
+#pragma unroll
+            for (int o = 0; o < 16; ++o)
+                if (br * 16 + o < 30) Hs[(br * 16 + o) * LDF + n] = (i < gv.P) ? mmax * prelu(acc[o], ri_a1) : 0.f;
+            if (br == 0) gid[n] = (i < gv.P) ? node_grid(gv, i) : -1;
+            __syncthreads();
+            // segmented sum over runs of equal grid node inside the tile; one atomic per (run, channel, 16-node strip)
+            if (threadIdx.x < 240) {
+                const int c = threadIdx.x >> 3, q = threadIdx.x & 7;
+                int cur = gid[q * 16];
+                float sum = 0.f;
+#pragma unroll 4
+                for (int t = 0; t < 16; ++t) {
+                    const int m = q * 16 + t;
+                    const int g = gid[m];
+                    if (g != cur) {
+                        if (cur >= 0) atomicAdd(&xg[(int64_t)cur * 32 + c], sum);
+                        cur = g;
+                        sum = 0.f;
+                    }
+                    sum += Hs[c * LDF + m];
+                }
+                if (cur >= 0) atomicAdd(&xg[(int64_t)cur * 32 + c], sum);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// K4: out = PReLU(fc2 xg)
+// --------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) readin_finalize_kernel(const float* __restrict__ packed,
+                                                              const float* __restrict__ xg, float* __restrict__ out,
+                                                              int ld_out, int G) {
+    __shared__ __align__(16) float sW[30 * LD16 + LD16];
+    for (int i = threadIdx.x; i < 30 * LD16 + LD16; i += 128) sW[i] = packed[RI_WFC2 + i];
+    const float a2 = packed[RI_SLOPES + 1];
+    __syncthreads();
+    const int g = blockIdx.x * 128 + threadIdx.x;
+    if (g >= G) return;
+    float acc[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) acc[o] = sW[30 * LD16 + o];
+    const float4* row = reinterpret_cast<const float4*>(xg + (int64_t)g * 32);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float4 x = row[c];
+        fma_row16(acc, x.x, sW + (4 * c + 0) * LD16);
+        fma_row16(acc, x.y, sW + (4 * c + 1) * LD16);
+        if (4 * c + 2 < 30) fma_row16(acc, x.z, sW + (4 * c + 2) * LD16);
+        if (4 * c + 3 < 30) fma_row16(acc, x.w, sW + (4 * c + 3) * LD16);
+    }
+#pragma unroll
+    for (int o = 0; o < 15; ++o) out[(int64_t)g * ld_out + o] = prelu(acc[o], a2);
+}
+
+}  // namespace
+
+// --------------------------------------------------------------------------------------------------------------------
+// launchers
+// --------------------------------------------------------------------------------------------------------------------
+int launch_da_init(const genie_plan* p, const float* packed, const float* slice, const float* mask, float* tr0,
+                   cudaStream_t st) {
+    const int64_t P = p->g.n_prod;
+    if (P == 0) return GENIE_OK;
+    const int64_t blocks = (P + K1_THREADS - 1) / K1_THREADS;
+    da_init_kernel<<<(unsigned)blocks, K1_THREADS, 0, st>>>(packed, slice, mask, tr0, P);
+    GENIE_LAUNCH_CHECK();
+    return GENIE_OK;
+}
+
+int launch_da_layer1(const genie_plan* p, const float* packed, const float* tr0, const float* mask, float* zc, float* va,
+                     float* vb, cudaStream_t st) {
+    const int64_t P = p->g.n_prod;
+    if (P == 0) return GENIE_OK;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)K2_SMEM));
+        attr_set = true;
+    }
+    const int64_t n_tiles = (P + TM - 1) / TM;
+    const int64_t grid = n_tiles < (int64_t)p->sm_count * 2 ? n_tiles : (int64_t)p->sm_count * 2;
+    da_layer1_kernel<<<(unsigned)grid, K2_THREADS, K2_SMEM, st>>>(make_view(p), packed, tr0, mask, zc, va, vb, n_tiles);
+    GENIE_LAUNCH_CHECK();
+    return GENIE_OK;
+}
+
+int launch_da_layer2_readin(const genie_plan* p, const float* packed, int mode, const float* zc, const float* va,
+                            const float* vb, const float* latent_in, float* latent_out, const float* edge_attr,
+                            const float* mask, float* xg, cudaStream_t st) {
+    const int64_t P = p->g.n_prod;
+    if (P == 0) return GENIE_OK;
+    const int64_t n_tiles = (P + TM - 1) / TM;
+    const int64_t cap = (int64_t)p->sm_count * 4;
+    const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
+    const GraphView gv = make_view(p);
+#define GENIE_L2_CASE(M)                                                                                              \
+    case M:                                                                                                            \
+        da_layer2_readin_kernel<M><<<grid, K3_THREADS, 0, st>>>(gv, packed, zc, va, vb, latent_in, latent_out,      \
+                                                                  edge_attr, mask, xg, n_tiles);                     \
+        break;
+    switch (mode) {
+        GENIE_L2_CASE(L2_GATHER | L2_READIN)
+        GENIE_L2_CASE(L2_GATHER | L2_STORE_LATENT | L2_READIN)
+        GENIE_L2_CASE(L2_GATHER | L2_STORE_LATENT)
+        GENIE_L2_CASE(L2_READIN)
+        default:
+            set_error("launch_da_layer2_readin: unsupported mode");
+            return GENIE_ERR_INVALID;
+    }
+#undef GENIE_L2_CASE
+    GENIE_LAUNCH_CHECK();
+    return GENIE_OK;
+}
+
+int launch_readin_finalize(const genie_plan* p, const float* packed, const float* xg, float* out, int ld_out,
+                           cudaStream_t st) {
+    const int G = p->g.n_grid;
+    if (G == 0) return GENIE_OK;
+    readin_finalize_kernel<<<(G + 127) / 128, 128, 0, st>>>(packed, xg, out, ld_out, G);
+    GENIE_LAUNCH_CHECK();
+    return GENIE_OK;
+}

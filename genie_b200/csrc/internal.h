@@ -1,0 +1,103 @@
+// Internal declarations shared by the translation units of libgenie_b200.so (not part of the C-ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/genie_b200.h"
+#include "layout.h"
+
+struct genie_plan {
+    genie_graph_desc_t g;
+    int sm_count;
+    int64_t n_edges_grid;   // number of grid-graph edges (host copy of grid_rowptr[G]), fetched lazily
+};
+
+// Device-side view of the product graph.  CARTESIAN: node i = g*S + s; sta neighbours g*S + col, src neighbours
+// col*S + s.  EXPLICIT: neighbours are col directly.
+struct GraphView {
+    int mode;
+    int S;
+    int G;
+    int64_t P;
+    const int64_t* sta_rowptr;
+    const int32_t* sta_col;
+    const int64_t* src_rowptr;
+    const int32_t* src_col;
+    const int32_t* prod_grid;
+};
+
+inline GraphView make_view(const genie_plan* p) {
+    GraphView v;
+    v.mode = p->g.mode;
+    v.S = p->g.n_sta;
+    v.G = p->g.n_grid;
+    v.P = p->g.n_prod;
+    v.sta_rowptr = p->g.sta_rowptr;
+    v.sta_col = p->g.sta_col;
+    v.src_rowptr = p->g.src_rowptr;
+    v.src_col = p->g.src_col;
+    v.prod_grid = p->g.prod_grid;
+    return v;
+}
+
+// Workspace carve-up (floats).  All regions 256-byte aligned.
+struct Workspace {
+    float* tr0;      // [P][32]
+    float* zc;       // [P][32]
+    float* va;       // [P][16]
+    float* vb;       // [P][16]
+    float* xg;       // [G][32]   read-in accumulator (sum over stations)
+    float* r;        // [G][16]   read-in output (15 used)
+    float* px;       // [G][32]   SpatialAggregation: W_x x_j
+    float* sa_a;     // [G][32]   ping
+    float* sa_b;     // [G][32]   pong
+    float* partial;  // [1024][8] per-CTA partial sums of the global feature
+    size_t bytes;
+};
+Workspace carve_workspace(const genie_plan* p, void* base);
+
+void set_error(const std::string& msg);
+void count_launch(int n = 1);
+
+#define GENIE_CUDA_CHECK(expr)                                                                         \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                             \
+            return GENIE_ERR_CUDA;                                                                      \
+        }                                                                                               \
+    } while (0)
+
+#define GENIE_LAUNCH_CHECK()                                                                            \
+    do {                                                                                                \
+        cudaError_t _e = cudaGetLastError();                                                            \
+        if (_e != cudaSuccess) {                                                                        \
+            set_error(std::string("kernel launch failed: ") + cudaGetErrorString(_e));                  \
+            return GENIE_ERR_CUDA;                                                                      \
+        }                                                                                               \
+        count_launch();                                                                                 \
+    } while (0)
+
+// ---- launchers (each returns a GENIE_* status) -----------------------------------------------------------------------
+int launch_pack_weights(const genie_frontend_weights_t* w, float* packed, cudaStream_t st);
+
+int launch_da_init(const genie_plan* p, const float* packed, const float* slice, const float* mask, float* tr0,
+                   cudaStream_t st);
+int launch_da_layer1(const genie_plan* p, const float* packed, const float* tr0, const float* mask, float* zc, float* va,
+                     float* vb, cudaStream_t st);
+// mode bits for the layer-2 / read-in kernel
+enum { L2_GATHER = 1, L2_STORE_LATENT = 2, L2_READIN = 4 };
+int launch_da_layer2_readin(const genie_plan* p, const float* packed, int mode, const float* zc, const float* va,
+                            const float* vb, const float* latent_in, float* latent_out, const float* edge_attr,
+                            const float* mask, float* xg, cudaStream_t st);
+int launch_readin_finalize(const genie_plan* p, const float* packed, const float* xg, float* out, int ld_out,
+                           cudaStream_t st);
+int launch_spatial_aggregation(const genie_plan* p, const float* packed, int layer, const float* x, int ld_x,
+                               const float* pos, float scale_rel, float* px, float* partial, float* out, int ld_out,
+                               cudaStream_t st);
+int launch_input_scatter(const genie_plan* p, const genie_input_params_t* prm, const double* picks, int64_t n_picks,
+                         const int32_t* sta_perm, const int32_t* ind_use, const float* trv_times,
+                         const int32_t* node_sta, const int32_t* node_grid, float* series, float* slice_out,
+                         float* mask_out, int64_t* time_bin_out, cudaStream_t st);

@@ -1,0 +1,62 @@
+// Packed (kernel-side) weight layout of the front end.  All offsets are in floats and multiples of 4 (16-byte aligned
+// for float4 shared-memory loads).  Every matrix is stored K-major ("transposed": row k holds the weights that multiply
+// input feature k), with the output dimension padded to LD (30 -> 32) or LD16 (15 -> 16); padding is zero.
+#pragma once
+
+namespace gl {
+
+constexpr int H = 30;      // hidden width of the reference (n_hidden, module.py:53)
+constexpr int LD = 32;     // padded 30-wide output rows
+constexpr int LD16 = 16;   // padded 15-wide output rows
+
+// ---- DataAggregation (module.py:52-98) ------------------------------------------------------------------------------
+constexpr int DA_W0 = 0;                        // init_trns          [8][32]   rows 0-3 Slice, 4-7 Mask
+constexpr int DA_B0 = DA_W0 + 8 * LD;           //                    [32]
+constexpr int DA_W11 = DA_B0 + LD;              // l1_t1_2            [64][32]  rows 0-29 tr0, 30-59 mean_sta, 60-63 Mask
+constexpr int DA_B11 = DA_W11 + 64 * LD;
+constexpr int DA_W12 = DA_B11 + LD;             // l1_t2_2            [64][32]  rows 0-29 tr0, 30-59 mean_src, 60-63 Mask
+constexpr int DA_B12 = DA_W12 + 64 * LD;
+constexpr int DA_W21A = DA_B12 + LD;            // l2_t1_1            [60][32]
+constexpr int DA_B21A = DA_W21A + 60 * LD;
+constexpr int DA_W22A = DA_B21A + LD;           // l2_t2_1            [60][32]
+constexpr int DA_B22A = DA_W22A + 60 * LD;
+constexpr int DA_WCA = DA_B22A + LD;            // l2_t1_2[:, 0:60 | 90:94]   [64][16]  rows 0-59 tr, 60-63 Mask
+constexpr int DA_BCA = DA_WCA + 64 * LD16;      // l2_t1_2.bias       [16]
+constexpr int DA_WCB = DA_BCA + LD16;           // l2_t2_2[:, 0:60 | 90:94]   [64][16]
+constexpr int DA_BCB = DA_WCB + 64 * LD16;
+constexpr int DA_WVA = DA_BCB + LD16;           // l2_t1_2[:, 60:90]  [30][16]  applied BEFORE the mean (linearity)
+constexpr int DA_WVB = DA_WVA + 30 * LD16;      // l2_t2_2[:, 60:90]  [30][16]
+constexpr int DA_SLOPES = DA_WVB + 30 * LD16;   // [8]: activate, 11, 12, 1, 21, 22, 2, -
+constexpr int DA_END = DA_SLOPES + 8;
+enum { SL_A0 = 0, SL_A11 = 1, SL_A12 = 2, SL_A1 = 3, SL_A21 = 4, SL_A22 = 5, SL_A2 = 6 };
+
+// ---- BipartiteGraphOperator (module.py:214-229) ---------------------------------------------------------------------
+constexpr int RI_WFC1 = DA_END;                 // fc1  [33][32]  rows 0-29 x_latent, 30-32 edge attr
+constexpr int RI_BFC1 = RI_WFC1 + 33 * LD;
+constexpr int RI_WFC2 = RI_BFC1 + LD;           // fc2  [30][16]
+constexpr int RI_BFC2 = RI_WFC2 + 30 * LD16;
+constexpr int RI_SLOPES = RI_BFC2 + LD16;       // [4]: activate1, activate2, -, -
+constexpr int RI_END = RI_SLOPES + 4;
+
+// ---- SpatialAggregation x3 (module.py:231-249) ----------------------------------------------------------------------
+constexpr int SA_WX = 0;                        // fc1[:, 0:C]        [30][32]  rows >= C zero
+constexpr int SA_WPG = SA_WX + 30 * LD;         // fc1[:, C:C+8]      [8][32]   rows 0-2 pos diff, 3-7 global
+constexpr int SA_B1 = SA_WPG + 8 * LD;
+constexpr int SA_W2 = SA_B1 + LD;               // fc2                [60][32]  rows 0..C-1 x_i, rows 30-59 aggregate
+constexpr int SA_B2 = SA_W2 + 60 * LD;
+constexpr int SA_WGL = SA_B2 + LD;              // fglobal            [30][8]   rows >= C zero
+constexpr int SA_BGL = SA_WGL + 30 * 8;
+constexpr int SA_SLOPES = SA_BGL + 8;           // [4]: activate1, activate2, activate3, -
+constexpr int SA_SIZE = SA_SLOPES + 4;
+constexpr int SA_BASE = RI_END;
+
+constexpr int PACKED_FLOATS = SA_BASE + 3 * SA_SIZE;
+
+static_assert(DA_W11 % 4 == 0 && DA_END % 4 == 0 && RI_END % 4 == 0 && SA_SIZE % 4 == 0, "16-byte alignment");
+
+// ---- node-feature row strides in the workspace (floats) -------------------------------------------------------------
+constexpr int LD_TR0 = 32;   // tr0 rows padded to 128 B: one L2 line per gathered neighbour row
+constexpr int LD_ZC = 32;    // [ca(15) 0 | cb(15) 0]
+constexpr int LD_V = 16;     // va / vb rows (64 B = two sectors)
+
+}  // namespace gl

@@ -1,0 +1,387 @@
+"""Drop-in replacement for the hot-path classes of the reference's `Code/module.py`.
+
+`from genie_b200.module import *` gives `GCN_Detection_Network_extended` with the reference's constructor, method
+signatures and state_dict key names (module.py:882-1020), so `train_GENIE_model.py:1382` / `process_continuous_days.py:
+335-337, 634, 797` work against it unchanged.  The product-graph front end (DataAggregation -> Bipartite_ReadIn ->
+SpatialAggregation1..3, >= 97 % of the reference's forward time) runs in libgenie_b200.so; the sub-modules of the same
+names only hold the parameters.  The small per-grid-node read-out heads (SpatialDirect, TemporalAttention,
+SpatialAttention) are restated in plain torch without torch_geometric.
+
+Like the reference (module.py:27-46) the module reads `config.yaml` / `train_config.yaml` from the working directory at
+import time when they exist; otherwise the reference's shipped defaults are used.
+"""
+import math
+import os
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import capi, ops
+from .plan import GraphPlan
+
+# ---- import-time configuration (module.py:27-46) ----------------------------------------------------------------------
+_cfg, _tcfg = {}, {}
+try:
+    import yaml
+    if os.path.exists('config.yaml'):
+        with open('config.yaml', 'r') as _f:
+            _cfg = yaml.safe_load(_f) or {}
+    if os.path.exists('train_config.yaml'):
+        with open('train_config.yaml', 'r') as _f:
+            _tcfg = yaml.safe_load(_f) or {}
+except ImportError:          # pragma: no cover
+    pass
+
+use_updated_model_definition = bool(_cfg.get('use_updated_model_definition', False))
+scale_rel = float(_cfg.get('scale_rel', 30000.0))
+k_sta_edges = int(_cfg.get('k_sta_edges', 8))
+kernel_sig_t = float(_tcfg.get('kernel_sig_t', 3.0))
+scale_t = kernel_sig_t * 3.0
+eps = kernel_sig_t * 5.0
+use_phase_types = bool(_cfg.get('use_phase_types', True))
+use_absolute_pos = bool(_cfg.get('use_absolute_pos', False))
+
+device = torch.device('cuda')
+
+
+# ---- parameter holders of the CUDA front end -------------------------------------------------------------------------
+
+class DataAggregation(nn.Module):
+    """Parameters of module.py:52-83 (the unused l1_t1_1 / l1_t2_1 stay in the state_dict).  Forward: libgenie_b200."""
+
+    def __init__(self, in_channels, out_channels, n_hidden=30, n_dim_mask=4, use_absolute_pos=use_absolute_pos):
+        super().__init__()
+        if use_absolute_pos:
+            raise NotImplementedError('genie_b200: use_absolute_pos=True is not supported yet')
+        if (in_channels, out_channels, n_hidden, n_dim_mask) != (4, 15, 30, 4):
+            raise NotImplementedError('genie_b200: DataAggregation is built for (4, 15, n_hidden=30, n_dim_mask=4)')
+        self.in_channels, self.out_channels, self.n_hidden = in_channels, out_channels, n_hidden
+        self.activate = nn.PReLU()
+        self.init_trns = nn.Linear(in_channels + n_dim_mask, n_hidden)
+        self.l1_t1_1 = nn.Linear(n_hidden, n_hidden)
+        self.l1_t1_2 = nn.Linear(2 * n_hidden + n_dim_mask, n_hidden)
+        self.l1_t2_1 = nn.Linear(in_channels, n_hidden)
+        self.l1_t2_2 = nn.Linear(2 * n_hidden + n_dim_mask, n_hidden)
+        self.activate11 = nn.PReLU()
+        self.activate12 = nn.PReLU()
+        self.activate1 = nn.PReLU()
+        self.l2_t1_1 = nn.Linear(2 * n_hidden, n_hidden)
+        self.l2_t1_2 = nn.Linear(3 * n_hidden + n_dim_mask, out_channels)
+        self.l2_t2_1 = nn.Linear(2 * n_hidden, n_hidden)
+        self.l2_t2_2 = nn.Linear(3 * n_hidden + n_dim_mask, out_channels)
+        self.activate21 = nn.PReLU()
+        self.activate22 = nn.PReLU()
+        self.activate2 = nn.PReLU()
+
+
+class BipartiteGraphOperator(nn.Module):
+    """Parameters of module.py:214-222."""
+
+    def __init__(self, ndim_in, ndim_out, ndim_edges=3):
+        super().__init__()
+        if (ndim_in, ndim_out, ndim_edges) != (30, 15, 3):
+            raise NotImplementedError('genie_b200: BipartiteGraphOperator is built for (30, 15, ndim_edges=3)')
+        self.fc1 = nn.Linear(ndim_in + ndim_edges, ndim_in)
+        self.fc2 = nn.Linear(ndim_in, ndim_out)
+        self.activate1 = nn.PReLU()
+        self.activate2 = nn.PReLU()
+
+
+class SpatialAggregation(nn.Module):
+    """Parameters of module.py:231-241."""
+
+    def __init__(self, in_channels, out_channels, scale_rel=scale_rel, n_dim=3, n_global=5, n_hidden=30):
+        super().__init__()
+        if in_channels not in (15, 30) or (out_channels, n_dim, n_global, n_hidden) != (30, 3, 5, 30):
+            raise NotImplementedError('genie_b200: SpatialAggregation is built for (15|30 -> 30)')
+        self.fc1 = nn.Linear(in_channels + n_dim + n_global, n_hidden)
+        self.fc2 = nn.Linear(n_hidden + in_channels, out_channels)
+        self.fglobal = nn.Linear(in_channels, n_global)
+        self.activate1 = nn.PReLU()
+        self.activate2 = nn.PReLU()
+        self.activate3 = nn.PReLU()
+        self.scale_rel = scale_rel
+
+
+# ---- read-out heads (plain torch) -------------------------------------------------------------------------------------
+
+class SpatialDirect(nn.Module):
+    """module.py:251-260."""
+
+    def __init__(self, inpt_dim, out_channels):
+        super().__init__()
+        self.f_direct = nn.Linear(inpt_dim, out_channels)
+        self.activate = nn.PReLU()
+
+    def forward(self, inpts):
+        return self.activate(self.f_direct(inpts))
+
+
+def knn_query_edges(x_context, x_query, k, chunk=4096):
+    """`knn(x_context/1000, x_query/1000, k).flip(0)` (module.py:282) without torch_cluster: brute force on the device.
+
+    Returns int64 [2, Q*k]: row 0 = context (source) index, nearest first, row 1 = query (target) index."""
+    xc, xq = x_context / 1000.0, x_query / 1000.0
+    k = min(k, xc.shape[0])
+    idx = []
+    for q0 in range(0, xq.shape[0], chunk):
+        d = torch.cdist(xq[q0:q0 + chunk].double(), xc.double())
+        idx.append(torch.topk(d, k, dim=1, largest=False, sorted=True)[1])
+    idx = torch.cat(idx, dim=0) if idx else torch.zeros((0, k), dtype=torch.long, device=xc.device)
+    tgt = torch.arange(xq.shape[0], device=xc.device).repeat_interleave(k)
+    return torch.stack((idx.reshape(-1), tgt), dim=0)
+
+
+class SpatialAttention(nn.Module):
+    """module.py:262-297 (k-nearest-context attention read-out onto arbitrary query points)."""
+
+    def __init__(self, inpt_dim, out_channels, n_dim, n_latent, n_hidden=30, n_heads=5, scale_rel=scale_rel):
+        super().__init__()
+        self.param_vector = nn.Parameter(nn.init.xavier_uniform_(torch.Tensor(1, n_heads, n_latent)))
+        self.f_queries = nn.Linear(n_dim, n_heads * n_latent)
+        self.f_context = nn.Linear(inpt_dim + n_dim, n_heads * n_latent)
+        self.f_values = nn.Linear(inpt_dim + n_dim, n_heads * n_latent)
+        self.f_direct = nn.Linear(inpt_dim, out_channels)
+        self.proj = nn.Linear(n_latent, out_channels)
+        self.scale = np.sqrt(n_latent)
+        self.n_heads, self.n_latent, self.scale_rel = n_heads, n_latent, scale_rel
+        self.activate1 = nn.PReLU()
+        self.activate2 = nn.PReLU()
+        self._edge_cache = None
+
+    def _edges(self, x_query, x_context, k):
+        key = (x_query.data_ptr(), x_query._version, tuple(x_query.shape), x_context.data_ptr(), x_context._version,
+               tuple(x_context.shape), k)
+        if self._edge_cache is None or self._edge_cache[0] != key:
+            self._edge_cache = (key, knn_query_edges(x_context, x_query, k), x_query, x_context)
+        return self._edge_cache[1]
+
+    def forward(self, inpts, x_query, x_context, k=10):
+        edge_index = self._edges(x_query, x_context, k)
+        Q = x_query.shape[0]
+        kk = edge_index.shape[1] // max(Q, 1)
+        edge_attr = (x_query[edge_index[1]] - x_context[edge_index[0]]) / self.scale_rel
+        x_j = inpts[edge_index[0]]
+        cat = torch.cat((x_j, edge_attr), dim=-1)
+        q = self.f_queries(edge_attr).view(-1, self.n_heads, self.n_latent)
+        c = self.f_context(cat).view(-1, self.n_heads, self.n_latent)
+        v = self.f_values(cat).view(-1, self.n_heads, self.n_latent)
+        alpha = self.activate1((q * c).sum(-1) / self.scale)
+        # every query owns exactly kk consecutive edges -> the segment softmax / sum are dense over a [Q, kk] view
+        alpha = torch.softmax(alpha.view(Q, kk, self.n_heads), dim=1)
+        out = (alpha.unsqueeze(-1) * v.view(Q, kk, self.n_heads, self.n_latent)).sum(1)
+        return self.activate2(self.proj(out.mean(1)))
+
+
+class TemporalAttention(nn.Module):
+    """module.py:299-331."""
+
+    def __init__(self, inpt_dim, out_channels, n_latent, n_hidden=30, n_heads=5, scale_t=scale_t):
+        super().__init__()
+        self.temporal_query_1 = nn.Linear(1, n_hidden)
+        self.temporal_query_2 = nn.Linear(n_hidden, n_heads * n_latent)
+        self.f_context_1 = nn.Linear(inpt_dim, n_hidden)
+        self.f_context_2 = nn.Linear(n_hidden, n_heads * n_latent)
+        self.f_values_1 = nn.Linear(inpt_dim, n_hidden)
+        self.f_values_2 = nn.Linear(n_hidden, n_heads * n_latent)
+        self.proj_1 = nn.Linear(n_latent, n_hidden)
+        self.proj_2 = nn.Linear(n_hidden, out_channels)
+        self.scale = np.sqrt(n_latent)
+        self.n_heads, self.n_latent, self.scale_t = n_heads, n_latent, scale_t
+        self.activate1 = nn.PReLU()
+        self.activate2 = nn.PReLU()
+        self.activate3 = nn.PReLU()
+        self.activate4 = nn.PReLU()
+        self.activate5 = nn.PReLU()
+
+    def forward(self, inpts, t_query):
+        c = self.f_context_2(self.activate1(self.f_context_1(inpts))).view(-1, self.n_heads, self.n_latent)
+        v = self.f_values_2(self.activate2(self.f_values_1(inpts))).view(-1, self.n_heads, self.n_latent)
+        q = self.temporal_query_2(self.activate3(self.temporal_query_1(t_query / self.scale_t)))
+        q = q.view(-1, self.n_heads, self.n_latent)
+        s = torch.einsum('nhl,thl->nth', c, q) / self.scale                       # [N, T, heads]
+        z = torch.einsum('nth,nhl->ntl', s, v) / self.n_heads                     # mean over heads
+        return self.proj_2(self.activate5(self.proj_1(self.activate4(z))))
+
+
+# ---- association branch: parameters only (not on the forward_fixed_source path) -----------------
+
+class BipartiteGraphReadOutOperator(nn.Module):
+    """Parameters of module.py:333-343."""
+
+    def __init__(self, ndim_in, ndim_out, ndim_edges=3):
+        super().__init__()
+        self.fc1 = nn.Linear(ndim_in + ndim_edges, ndim_in)
+        self.fc2 = nn.Linear(ndim_in, ndim_out)
+        self.activate1 = nn.PReLU()
+        self.activate2 = nn.PReLU()
+
+
+class DataAggregationAssociationPhase(nn.Module):
+    """Parameters of module.py:356-387."""
+
+    def __init__(self, in_channels, out_channels, n_hidden=30, n_dim_latent=30, n_dim_mask=5):
+        super().__init__()
+        self.activate = nn.PReLU()
+        self.init_trns = nn.Linear(in_channels + n_dim_latent + n_dim_mask, n_hidden)
+        self.l1_t1_1 = nn.Linear(n_hidden, n_hidden)
+        self.l1_t1_2 = nn.Linear(2 * n_hidden + n_dim_mask, n_hidden)
+        self.l1_t2_1 = nn.Linear(n_hidden, n_hidden)
+        self.l1_t2_2 = nn.Linear(2 * n_hidden + n_dim_mask, n_hidden)
+        self.activate11 = nn.PReLU()
+        self.activate12 = nn.PReLU()
+        self.activate1 = nn.PReLU()
+        self.l2_t1_1 = nn.Linear(2 * n_hidden, n_hidden)
+        self.l2_t1_2 = nn.Linear(3 * n_hidden + n_dim_mask, out_channels)
+        self.l2_t2_1 = nn.Linear(2 * n_hidden, n_hidden)
+        self.l2_t2_2 = nn.Linear(3 * n_hidden + n_dim_mask, out_channels)
+        self.activate21 = nn.PReLU()
+        self.activate22 = nn.PReLU()
+        self.activate2 = nn.PReLU()
+
+
+class LocalSliceLgCollapse(nn.Module):
+    """Parameters of module.py:610-622."""
+
+    def __init__(self, ndim_in, ndim_out, n_edge=2, n_hidden=30, eps=eps, use_phase_types=use_phase_types,
+                 device='cuda'):
+        super().__init__()
+        self.fc1 = nn.Linear(ndim_in + n_edge, n_hidden)
+        self.fc2 = nn.Linear(n_hidden, ndim_out)
+        self.activate1 = nn.PReLU()
+        self.activate2 = nn.PReLU()
+        self.eps, self.device, self.use_phase_types = eps, device, use_phase_types
+
+
+class StationSourceAttentionMergedPhases(nn.Module):
+    """Parameters of module.py:662-699."""
+
+    def __init__(self, ndim_src_in, ndim_arv_in, ndim_out, n_latent, ndim_extra=1, n_heads=5, n_hidden=30,
+                 scale_rel=scale_rel, k_sta_edges=k_sta_edges, eps=eps, use_neighbor_assoc_edges=False,
+                 use_phase_types=use_phase_types, device=device):
+        super().__init__()
+        if use_neighbor_assoc_edges:
+            ndim_extra = ndim_extra + 1 + 3
+        self.f_arrival_query_1 = nn.Linear(2 * ndim_arv_in + 6, n_hidden)
+        self.f_arrival_query_2 = nn.Linear(n_hidden, n_heads * n_latent)
+        self.f_src_context_1 = nn.Linear(ndim_src_in + ndim_extra + 2, n_hidden)
+        self.f_src_context_2 = nn.Linear(n_hidden, n_heads * n_latent)
+        self.f_values_1 = nn.Linear(2 * ndim_arv_in + ndim_extra + 7, n_hidden)
+        self.f_values_2 = nn.Linear(n_hidden, n_heads * n_latent)
+        self.proj_1 = nn.Linear(n_latent, n_hidden)
+        self.proj_2 = nn.Linear(n_hidden, ndim_out)
+        self.activate1 = nn.PReLU()
+        self.activate2 = nn.PReLU()
+        self.activate3 = nn.PReLU()
+        self.activate4 = nn.PReLU()
+        self.n_heads, self.n_latent, self.eps = n_heads, n_latent, eps
+
+
+# ---- the model ----------------------------------------------------------------------------------------------------------
+
+class GCN_Detection_Network_extended(nn.Module):
+    """module.py:882-1020 (the default, `use_updated_model_definition: False`, definition)."""
+
+    def __init__(self, ftrns1, ftrns2, scale_rel=scale_rel, use_absolute_pos=use_absolute_pos, device='cuda'):
+        super().__init__()
+        if use_updated_model_definition:
+            raise NotImplementedError('genie_b200: use_updated_model_definition=True (DataAggregationEdges, '
+                                      'module.py:102) is not implemented yet')
+        if use_absolute_pos:
+            raise NotImplementedError('genie_b200: use_absolute_pos=True is not supported yet')
+        self.DataAggregation = DataAggregation(4, 15).to(device)
+        self.Bipartite_ReadIn = BipartiteGraphOperator(30, 15, ndim_edges=3).to(device)
+        self.SpatialAggregation1 = SpatialAggregation(15, 30, scale_rel=scale_rel).to(device)
+        self.SpatialAggregation2 = SpatialAggregation(30, 30, scale_rel=scale_rel).to(device)
+        self.SpatialAggregation3 = SpatialAggregation(30, 30, scale_rel=scale_rel).to(device)
+        self.SpatialDirect = SpatialDirect(30, 30).to(device)
+        self.SpatialAttention = SpatialAttention(30, 30, 3, 15, scale_rel=scale_rel).to(device)
+        self.TemporalAttention = TemporalAttention(30, 1, 15).to(device)
+        self.BipartiteGraphReadOutOperator = BipartiteGraphReadOutOperator(30, 15).to(device)
+        self.DataAggregationAssociationPhase = DataAggregationAssociationPhase(15, 15).to(device)
+        self.LocalSliceLgCollapseP = LocalSliceLgCollapse(30, 15, device=device).to(device)
+        self.LocalSliceLgCollapseS = LocalSliceLgCollapse(30, 15, device=device).to(device)
+        self.Arrivals = StationSourceAttentionMergedPhases(30, 15, 2, 15, n_heads=3, device=device).to(device)
+        self.use_absolute_pos = use_absolute_pos
+        self.scale_rel = scale_rel
+        self.ftrns1, self.ftrns2 = ftrns1, ftrns2
+        self._plan = None
+        self._plan_key = None
+        self._packed = None
+        self._read_in_attr = None
+
+    # -- graph plans ---------------------------------------------------------------------------------------------------
+    def set_adjacencies(self, A_in_sta, A_in_src, A_src_in_edges, A_Lg_in_src, A_src_in_sta, A_src, A_edges_p, A_edges_s,
+                        dt_partition, tlatent, pos_loc, pos_src):
+        """module.py:941-961: cache the graphs; additionally build the GraphPlan the CUDA kernels use."""
+        self.A_in_sta, self.A_in_src, self.A_src_in_edges = A_in_sta, A_in_src, A_src_in_edges
+        self.A_Lg_in_src, self.A_src_in_sta, self.A_src = A_Lg_in_src, A_src_in_sta, A_src
+        self.A_edges_p, self.A_edges_s, self.dt_partition, self.tlatent = A_edges_p, A_edges_s, dt_partition, tlatent
+        n_sta, n_grid = int(pos_loc.shape[0]), int(pos_src.shape[0])
+        self._plan = GraphPlan.from_edge_lists(A_in_sta, A_in_src, A_src_in_edges.edge_index, A_src, n_sta, n_grid,
+                                               device=pos_src.device)
+        self._read_in_attr = A_src_in_edges.x.to(pos_src.device).float().contiguous()
+        self._plan_key = None
+
+    def set_adjacencies_cartesian(self, A_sta_sta, A_src_src, read_in_attr, n_sta, n_grid, device=None):
+        """Dense mode without ever materialising the product edge lists (needed beyond a few 10^7 product nodes):
+        the two kNN graphs of process_utils.py:718-719 and the read-in edge features `A_src_in_edges.x` [P,3]."""
+        device = device if device is not None else read_in_attr.device
+        self._plan = GraphPlan.cartesian(A_sta_sta, A_src_src, n_sta, n_grid, device=device)
+        self._read_in_attr = read_in_attr.to(device).float().contiguous()
+        self.A_src = A_src_src
+        self._plan_key = None
+
+    def _plan_for(self, A_in_sta, A_in_src, A_src_in_edges, A_src, n_sta, n_grid, dev):
+        """`forward` receives the graphs on every call (module.py:908): plans are cached on tensor identity."""
+        key = (A_in_sta.data_ptr(), A_in_src.data_ptr(), A_src_in_edges.edge_index.data_ptr(), A_src.data_ptr(),
+               A_in_sta.shape[1], A_in_src.shape[1], n_sta, n_grid)
+        if self._plan is None or self._plan_key != key:
+            self._plan = GraphPlan.from_edge_lists(A_in_sta, A_in_src, A_src_in_edges.edge_index, A_src, n_sta, n_grid,
+                                                   device=dev)
+            self._read_in_attr = A_src_in_edges.x.to(dev).float().contiguous()
+            self._plan_key = key
+        return self._plan
+
+    # -- CUDA front end ------------------------------------------------------------------------------------------------
+    def _packed_weights(self, dev):
+        if self._packed is None or self._packed.device != torch.device(dev):
+            self._packed = ops.PackedWeights(dev)
+        return self._packed.update(self)
+
+    def front_end(self, Slice, Mask, x_temp_cuda_cart, want_latent=False, want_readin=False):
+        """DataAggregation -> Bipartite_ReadIn -> SpatialAggregation1..3 in libgenie_b200 (module.py:1010-1014)."""
+        if self._plan is None:
+            raise RuntimeError('set_adjacencies must be called before forward_fixed*')
+        if not Slice.is_cuda:
+            raise capi.GenieError('genie_b200 has no CPU path: inputs must be CUDA tensors')
+        if torch.is_grad_enabled() and (Slice.requires_grad or any(p.requires_grad for p in
+                                                                   self.DataAggregation.parameters())) \
+                and self.training:
+            raise NotImplementedError('genie_b200: backward of the CUDA front end is not implemented yet; '
+                                      'call under torch.no_grad() / model.eval()')
+        packed = self._packed_weights(Slice.device)
+        return ops.frontend_fwd(self._plan, packed, Slice, Mask, self._read_in_attr, x_temp_cuda_cart,
+                                float(self.scale_rel), want_latent=want_latent, want_readin=want_readin)
+
+    def forward_fixed_source(self, Slice, Mask, tpick, ipick, phase_label, locs_use_cart, x_temp_cuda_cart,
+                             x_query_cart, t_query):
+        """module.py:999-1020 -> (y [G,T,1], x [Q,T,1])."""
+        with torch.no_grad():
+            x_spatial = self.front_end(Slice, Mask, x_temp_cuda_cart)[0]
+            y_latent = self.SpatialDirect(x_spatial)
+            y = self.TemporalAttention(y_latent, t_query)
+            x = self.SpatialAttention(x_spatial, x_query_cart, x_temp_cuda_cart)
+            x = self.TemporalAttention(x, t_query)
+        return y, x
+
+    def forward_fixed(self, *args, **kwargs):
+        raise NotImplementedError('genie_b200: the association branch (forward_fixed, module.py:963) is outside the '
+                                  'hot path built so far (SURVEY.md §8f rank 2)')
+
+    def forward(self, Slice, Mask, A_in_sta, A_in_src, A_src_in_edges, A_Lg_in_src, A_src_in_sta, A_src, A_edges_p,
+                A_edges_s, dt_partition, tlatent, tpick, ipick, phase_label, locs_use_cart, x_temp_cuda_cart,
+                x_query_cart, x_query_src_cart, t_query, tq_sample, trv_out_q):
+        raise NotImplementedError('genie_b200: the full training forward (module.py:908, association outputs) is '
+                                  'outside the hot path built so far (SURVEY.md §8f rank 2)')

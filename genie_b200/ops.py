@@ -1,0 +1,173 @@
+"""Operator-level Python wrappers over the C-ABI (one function per entry point of include/genie_b200.h).
+
+Every function takes CUDA tensors, allocates its outputs with torch and launches on torch's current stream.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import capi
+
+F32 = torch.float32
+
+
+def _lin(ws, field, mod):
+    lin = getattr(ws, field)
+    lin.weight = capi.dptr(mod.weight.detach(), F32, field + '.weight')
+    lin.bias = capi.dptr(mod.bias.detach(), F32, field + '.bias')
+
+
+class PackedWeights(object):
+    """Kernel-layout copy of the front-end parameters; re-packed whenever a source tensor changes."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        n = int(capi.load().genie_frontend_packed_floats())
+        self.buf = torch.zeros(n, dtype=F32, device=self.device)
+        self._key = None
+
+    @staticmethod
+    def _sources(model):
+        da, ri = model.DataAggregation, model.Bipartite_ReadIn
+        sas = (model.SpatialAggregation1, model.SpatialAggregation2, model.SpatialAggregation3)
+        ts = [da.init_trns, da.l1_t1_2, da.l1_t2_2, da.l2_t1_1, da.l2_t2_1, da.l2_t1_2, da.l2_t2_2, da.activate,
+              da.activate11, da.activate12, da.activate1, da.activate21, da.activate22, da.activate2, ri.fc1, ri.fc2,
+              ri.activate1, ri.activate2]
+        for sa in sas:
+            ts += [sa.fc1, sa.fc2, sa.fglobal, sa.activate1, sa.activate2, sa.activate3]
+        return da, ri, sas, ts
+
+    def update(self, model):
+        da, ri, sas, mods = self._sources(model)
+        key = tuple((p.data_ptr(), p._version) for m in mods for p in m.parameters())
+        if key == self._key:
+            return self.buf
+        for m in mods:
+            for p in m.parameters():
+                if p.device != self.device or p.dtype != F32 or not p.is_contiguous():
+                    raise capi.GenieError('front-end parameters must be contiguous fp32 tensors on %s' % self.device)
+        ws = capi.FrontendWeights()
+        for f, m in (('da_init_trns', da.init_trns), ('da_l1_t1_2', da.l1_t1_2), ('da_l1_t2_2', da.l1_t2_2),
+                     ('da_l2_t1_1', da.l2_t1_1), ('da_l2_t2_1', da.l2_t2_1), ('da_l2_t1_2', da.l2_t1_2),
+                     ('da_l2_t2_2', da.l2_t2_2), ('ri_fc1', ri.fc1), ('ri_fc2', ri.fc2)):
+            _lin(ws, f, m)
+        for f, m in (('da_activate', da.activate), ('da_activate11', da.activate11), ('da_activate12', da.activate12),
+                     ('da_activate1', da.activate1), ('da_activate21', da.activate21),
+                     ('da_activate22', da.activate22), ('da_activate2', da.activate2),
+                     ('ri_activate1', ri.activate1), ('ri_activate2', ri.activate2)):
+            setattr(ws, f, capi.dptr(m.weight.detach(), F32, f))
+        for i, sa in enumerate(sas):
+            _lin(ws.sa[i], 'fc1', sa.fc1)
+            _lin(ws.sa[i], 'fc2', sa.fc2)
+            _lin(ws.sa[i], 'fglobal', sa.fglobal)
+            for a in ('activate1', 'activate2', 'activate3'):
+                setattr(ws.sa[i], a, capi.dptr(getattr(sa, a).weight.detach(), F32, a))
+        with torch.cuda.device(self.device):
+            capi.check(capi.load().genie_frontend_pack_weights(ctypes.byref(ws), capi.dptr(self.buf),
+                                                               capi.stream_ptr(self.device)))
+        self._key = key
+        return self.buf
+
+
+def _f32c(t, name):
+    if t.dtype != F32:
+        t = t.float()
+    return t.contiguous()
+
+
+def data_aggregation_fwd(plan, packed, Slice, Mask):
+    """DataAggregation.forward (module.py:85-98): Slice, Mask [P,4] -> x_latent [P,30]."""
+    Slice, Mask = _f32c(Slice, 'Slice'), _f32c(Mask, 'Mask')
+    out = torch.empty((plan.n_prod, 30), dtype=F32, device=plan.device)
+    with torch.cuda.device(plan.device):
+        capi.check(capi.load().genie_data_aggregation_fwd(
+            plan.handle, capi.dptr(packed, F32), capi.dptr(Slice, F32, 'Slice'), capi.dptr(Mask, F32, 'Mask'),
+            capi.dptr(out), capi.dptr(plan.workspace()), capi.stream_ptr(plan.device)))
+    return out
+
+
+def bipartite_readin_fwd(plan, packed, x_latent, edge_attr, Mask):
+    """BipartiteGraphOperator.forward (module.py:224-229): -> [G,15]."""
+    x_latent, edge_attr, Mask = _f32c(x_latent, 'x'), _f32c(edge_attr, 'attr'), _f32c(Mask, 'Mask')
+    out = torch.empty((plan.n_grid, 15), dtype=F32, device=plan.device)
+    with torch.cuda.device(plan.device):
+        capi.check(capi.load().genie_bipartite_readin_fwd(
+            plan.handle, capi.dptr(packed, F32), capi.dptr(x_latent, F32), capi.dptr(edge_attr, F32),
+            capi.dptr(Mask, F32), capi.dptr(out), capi.dptr(plan.workspace()), capi.stream_ptr(plan.device)))
+    return out
+
+
+def spatial_aggregation_fwd(plan, packed, layer, x, pos, scale_rel):
+    """SpatialAggregation.forward (module.py:243-249), layer = 0,1,2: [G,C] -> [G,30]."""
+    x, pos = _f32c(x, 'x'), _f32c(pos, 'pos')
+    if x.shape[1] != (15 if layer == 0 else 30):
+        raise capi.GenieError('SpatialAggregation%d expects %d input channels' % (layer + 1, 15 if layer == 0 else 30))
+    out = torch.empty((plan.n_grid, 30), dtype=F32, device=plan.device)
+    with torch.cuda.device(plan.device):
+        capi.check(capi.load().genie_spatial_aggregation_fwd(
+            plan.handle, capi.dptr(packed, F32), int(layer), capi.dptr(x, F32), capi.dptr(pos, F32),
+            ctypes.c_float(scale_rel), capi.dptr(out), capi.dptr(plan.workspace()), capi.stream_ptr(plan.device)))
+    return out
+
+
+def frontend_fwd(plan, packed, Slice, Mask, edge_attr, pos, scale_rel, want_latent=False, want_readin=False, out=None):
+    """DataAggregation -> Bipartite_ReadIn -> SpatialAggregation1..3 (module.py:1010-1014) in one call."""
+    Slice, Mask = _f32c(Slice, 'Slice'), _f32c(Mask, 'Mask')
+    edge_attr, pos = _f32c(edge_attr, 'attr'), _f32c(pos, 'pos')
+    if Slice.shape != (plan.n_prod, 4) or Mask.shape != (plan.n_prod, 4) or edge_attr.shape != (plan.n_prod, 3):
+        raise capi.GenieError('Slice/Mask must be [P,4] and the read-in edge features [P,3] with P = %d' % plan.n_prod)
+    if pos.shape != (plan.n_grid, 3):
+        raise capi.GenieError('grid positions must be [G,3] with G = %d' % plan.n_grid)
+    x_spatial = out if out is not None else torch.empty((plan.n_grid, 30), dtype=F32, device=plan.device)
+    latent = torch.empty((plan.n_prod, 30), dtype=F32, device=plan.device) if want_latent else None
+    readin = torch.empty((plan.n_grid, 15), dtype=F32, device=plan.device) if want_readin else None
+    with torch.cuda.device(plan.device):
+        capi.check(capi.load().genie_frontend_fwd(
+            plan.handle, capi.dptr(packed, F32), capi.dptr(Slice, F32), capi.dptr(Mask, F32),
+            capi.dptr(edge_attr, F32), capi.dptr(pos, F32), ctypes.c_float(scale_rel), capi.dptr(latent),
+            capi.dptr(readin), capi.dptr(x_spatial), capi.dptr(plan.workspace()), capi.stream_ptr(plan.device)))
+    return x_spatial, latent, readin
+
+
+# ---- a1 ----------------------------------------------------------------------------------------------------------------
+
+def input_params(t0, max_t, kernel_sig_t, dt, n_locs, n_sta_use):
+    """The fp64 scalars the reference derives with numpy (process_utils.py:500-502, 520), by the same expressions."""
+    t0, max_t, kernel_sig_t, dt = float(t0), float(max_t), float(kernel_sig_t), float(dt)
+    t_offset = 3.0 * kernel_sig_t
+    start = t0 - t_offset
+    stop = t0 + max_t + t_offset + dt
+    prm = capi.InputParams()
+    prm.t0, prm.max_t, prm.kernel_sig_t, prm.dt = t0, max_t, kernel_sig_t, dt
+    prm.ref0 = start
+    prm.ref_step = (start + dt) - start                 # numpy.arange fills start + i*((start+dt)-start)
+    prm.n_ts = int(math.ceil((stop - start) / dt))      # len(numpy.arange(start, stop, dt))
+    prm.n_extra = int(np.ceil(3 * kernel_sig_t / dt))
+    prm.n_locs, prm.n_sta_use = int(n_locs), int(n_sta_use)
+    return prm
+
+
+def input_scatter_fwd(plan, prm, picks, sta_perm, ind_use, trv_times, node_sta=None, node_grid=None,
+                      want_time_bin=False, series=None):
+    """extract_input_from_data (process_utils.py:460-629) on the device: picks [n,5] fp64 -> Slice, Mask [P,4]."""
+    dev = plan.device
+    if picks.dtype != torch.float64:
+        raise capi.GenieError('picks must be float64 (pick times lose precision in fp32)')
+    picks = picks.contiguous()
+    if trv_times.shape[-1] != 2 or trv_times.shape[0] != plan.n_grid or trv_times.shape[1] != prm.n_locs:
+        raise capi.GenieError('trv_times must be [G, n_locs, 2]')
+    Slice = torch.empty((plan.n_prod, 4), dtype=F32, device=dev)
+    Mask = torch.empty((plan.n_prod, 4), dtype=F32, device=dev)
+    if series is None:
+        series = torch.empty((2, prm.n_sta_use, prm.n_ts), dtype=F32, device=dev)
+    tb = torch.empty((plan.n_prod, 2), dtype=torch.int64, device=dev) if want_time_bin else None
+    with torch.cuda.device(dev):
+        capi.check(capi.load().genie_input_scatter_fwd(
+            plan.handle, ctypes.byref(prm), capi.dptr(picks, torch.float64, 'picks'), int(picks.shape[0]),
+            capi.dptr(sta_perm, torch.int32, 'sta_perm'), capi.dptr(ind_use, torch.int32, 'ind_use'),
+            capi.dptr(_f32c(trv_times, 'trv_times'), F32), capi.dptr(node_sta, torch.int32, 'node_sta'),
+            capi.dptr(node_grid, torch.int32, 'node_grid'), capi.dptr(series, F32), capi.dptr(Slice), capi.dptr(Mask),
+            capi.dptr(tb), capi.stream_ptr(dev)))
+    return Slice, Mask, tb, series

@@ -1,0 +1,157 @@
+"""Graph plans: the compact, destination-sorted form of the reference's edge lists that the CUDA kernels consume.
+
+The reference passes explicit int64 `[2, E]` edge lists (row 0 = message source j, row 1 = target i;
+process_utils.py:718-722) to `GCN_Detection_Network_extended.set_adjacencies` (module.py:941).  In its default dense
+mode those product-graph lists are pure index patterns over the Cartesian product of the station kNN graph and the grid
+kNN graph; `GraphPlan.from_edge_lists` recognises the pattern and keeps only the two small graphs (the product edges
+stay implicit — at 1000 stations x 50000 grid nodes the explicit lists would be 24 GB).  Any other product graph
+(sub-graph mode, process_utils.py:744-849) is kept as an explicit CSR.
+"""
+import ctypes
+
+import torch
+
+from . import capi
+
+
+def csr_by_destination(edge_index, n_nodes):
+    """[2,E] (source, target) -> (rowptr int64 [n+1], col int32 [E]) sorted by target, source order kept."""
+    src, dst = edge_index[0].long(), edge_index[1].long()
+    if src.numel() and (int(dst.max()) >= n_nodes or int(dst.min()) < 0 or int(src.min()) < 0):
+        raise ValueError('edge target out of range')
+    order = torch.sort(dst, stable=True)[1]
+    col = src[order].to(torch.int32).contiguous()
+    rowptr = torch.zeros(n_nodes + 1, dtype=torch.int64, device=edge_index.device)
+    if src.numel():
+        rowptr[1:] = torch.cumsum(torch.bincount(dst, minlength=n_nodes), 0)
+    return rowptr.contiguous(), col
+
+
+def _is_cartesian(A_in_sta, A_in_src, prod_target, S, G):
+    """Checks the index patterns of process_utils.py:720-722; returns (A_sta_sta, A_src_src) or None."""
+    P = S * G
+    dev = A_in_sta.device
+    if prod_target is not None:
+        if prod_target.numel() != P:
+            return None
+        if not torch.equal(prod_target.long(), torch.arange(G, device=dev).repeat_interleave(S)):
+            return None
+    Es, Eg = A_in_sta.shape[1], A_in_src.shape[1]
+    if G == 0 or S == 0 or Es % G or Eg % S:
+        return None
+    es, eg = Es // G, Eg // S
+    base_sta = A_in_sta[:, :es].long()
+    if es and (int(base_sta.max()) >= S):
+        return None
+    # A_prod_sta_sta = A_sta_sta.repeat(1, G) + S * g          (:720)
+    chunk = max(1, (1 << 24) // max(es, 1))
+    for g0 in range(0, G, chunk):
+        g1 = min(G, g0 + chunk)
+        want = base_sta.unsqueeze(1) + S * torch.arange(g0, g1, device=dev).view(1, -1, 1)
+        if not torch.equal(A_in_sta[:, g0 * es:g1 * es].long().view(2, g1 - g0, es), want):
+            return None
+    # A_prod_src_src = S * A_src_src.repeat(1, S) + s           (:721)
+    first = A_in_src[:, :eg].long()
+    if eg and bool((first % S != 0).any()):
+        return None
+    base_src = first // S
+    chunk = max(1, (1 << 24) // max(eg, 1))
+    for s0 in range(0, S, chunk):
+        s1 = min(S, s0 + chunk)
+        want = S * base_src.unsqueeze(1) + torch.arange(s0, s1, device=dev).view(1, -1, 1)
+        if not torch.equal(A_in_src[:, s0 * eg:s1 * eg].long().view(2, s1 - s0, eg), want):
+            return None
+    return base_sta, base_src
+
+
+class GraphPlan(object):
+    """Owns the device index arrays and the C-side plan handle (genie_plan_t)."""
+
+    def __init__(self, mode, n_sta, n_grid, n_prod, sta, src, grid, grid_outdeg, prod_grid, device):
+        self.mode, self.n_sta, self.n_grid, self.n_prod = mode, int(n_sta), int(n_grid), int(n_prod)
+        self.device = torch.device(device)
+        self._keep = (sta, src, grid, grid_outdeg, prod_grid)     # keep the tensors alive
+        self.sta_rowptr, self.sta_col = sta
+        self.src_rowptr, self.src_col = src
+        self.grid_rowptr, self.grid_col = grid
+        self.grid_outdeg = grid_outdeg
+        self.prod_grid = prod_grid
+        d = capi.GraphDesc()
+        d.mode, d.n_sta, d.n_grid, d.reserved, d.n_prod = mode, self.n_sta, self.n_grid, 0, self.n_prod
+        d.sta_rowptr = capi.dptr(self.sta_rowptr, torch.int64, 'sta_rowptr')
+        d.sta_col = capi.dptr(self.sta_col, torch.int32, 'sta_col')
+        d.src_rowptr = capi.dptr(self.src_rowptr, torch.int64, 'src_rowptr')
+        d.src_col = capi.dptr(self.src_col, torch.int32, 'src_col')
+        d.grid_rowptr = capi.dptr(self.grid_rowptr, torch.int64, 'grid_rowptr')
+        d.grid_col = capi.dptr(self.grid_col, torch.int32, 'grid_col')
+        d.grid_outdeg = capi.dptr(self.grid_outdeg, torch.int32, 'grid_outdeg')
+        d.prod_grid = capi.dptr(self.prod_grid, torch.int32, 'prod_grid') if prod_grid is not None else None
+        self._desc = d
+        lib = capi.load()
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            capi.check(lib.genie_plan_create(ctypes.byref(d), ctypes.byref(handle)))
+        self.handle = handle
+        self.workspace_bytes = int(lib.genie_plan_workspace_bytes(handle))
+        self._workspace = None
+
+    def __del__(self):
+        h = getattr(self, 'handle', None)
+        if h is not None and h.value:
+            try:
+                capi.load().genie_plan_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    def workspace(self):
+        if self._workspace is None:
+            self._workspace = torch.empty(max(self.workspace_bytes, 256), dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    # ---- constructors ------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _grid_parts(A_src, n_grid):
+        grid = csr_by_destination(A_src, n_grid)
+        outdeg = torch.bincount(A_src[0].long(), minlength=n_grid).to(torch.int32).contiguous()
+        return grid, outdeg
+
+    @classmethod
+    def cartesian(cls, A_sta_sta, A_src_src, n_sta, n_grid, A_src=None, device=None):
+        """Dense mode from the two small kNN graphs (process_utils.py:718-719); product edges stay implicit."""
+        device = torch.device(device if device is not None else A_sta_sta.device)
+        A_sta_sta, A_src_src = A_sta_sta.to(device), A_src_src.to(device)
+        sta = csr_by_destination(A_sta_sta, n_sta)
+        src = csr_by_destination(A_src_src, n_grid)
+        if A_src is None or A_src is A_src_src:
+            grid = src
+            outdeg = torch.bincount(A_src_src[0].long(), minlength=n_grid).to(torch.int32).contiguous()
+        else:
+            grid, outdeg = cls._grid_parts(A_src.to(device), n_grid)
+        return cls(capi.GRAPH_CARTESIAN, n_sta, n_grid, n_sta * n_grid, sta, src, grid, outdeg, None, device)
+
+    @classmethod
+    def explicit(cls, A_in_sta, A_in_src, prod_target, A_src, n_prod, n_grid, device=None):
+        """Arbitrary product graph (sub-graph mode): CSR over the product nodes themselves."""
+        device = torch.device(device if device is not None else A_in_sta.device)
+        sta = csr_by_destination(A_in_sta.to(device), n_prod)
+        src = csr_by_destination(A_in_src.to(device), n_prod)
+        grid, outdeg = cls._grid_parts(A_src.to(device), n_grid)
+        prod_grid = prod_target.to(device).to(torch.int32).contiguous()
+        return cls(capi.GRAPH_EXPLICIT, 0, n_grid, n_prod, sta, src, grid, outdeg, prod_grid, device)
+
+    @classmethod
+    def from_edge_lists(cls, A_in_sta, A_in_src, read_in_index, A_src, n_sta, n_grid, device=None):
+        """What set_adjacencies receives (module.py:941): picks CARTESIAN when the lists follow :720-722."""
+        device = torch.device(device if device is not None else A_in_sta.device)
+        A_in_sta, A_in_src, A_src = A_in_sta.to(device), A_in_src.to(device), A_src.to(device)
+        n_prod = int(read_in_index.shape[1])
+        src_nodes = read_in_index[0].to(device)
+        if not torch.equal(src_nodes.long(), torch.arange(n_prod, device=device)):
+            raise ValueError('A_src_in_edges.edge_index[0] must be arange(P) (module.py:229, process_utils.py:722)')
+        prod_target = read_in_index[1].to(device)
+        if n_sta * n_grid == n_prod:
+            small = _is_cartesian(A_in_sta, A_in_src, prod_target, n_sta, n_grid)
+            if small is not None:
+                return cls.cartesian(small[0], small[1], n_sta, n_grid, A_src=A_src, device=device)
+        return cls.explicit(A_in_sta, A_in_src, prod_target, A_src, n_prod, n_grid, device=device)

@@ -1,0 +1,157 @@
+"""Host-side mirrors of the reference's `Code/process_utils.py` entry points that feed the hot path.
+
+* `extract_input_from_data`  — same signature and return structure as process_utils.py:460, but the per-station series,
+  the travel-time-shifted gather and Slice/Mask live on the GPU (libgenie_b200 `genie_input_scatter_fwd`).
+* `extract_inputs_adjacencies` — the dense-mode graph builder of process_utils.py:701-742.  kNN graphs are static per
+  station set and are built on the host with a k-d tree (acceptable until the device kNN lands).
+* `InputExtractor` — the streaming form used by bench.py: travel times, station tables and (optionally) a whole day of
+  picks stay resident in HBM; one call per window.
+"""
+import numpy as np
+import torch
+from scipy.spatial import cKDTree
+
+from . import ops
+from .plan import GraphPlan
+
+
+# ---- graphs -------------------------------------------------------------------------------------------------------------
+
+def knn_graph(pos_km, k):
+    """`remove_self_loops(knn(x, x, k+1).flip(0))` (process_utils.py:718-719): int64 [2,E], row 0 source, row 1 target."""
+    pos_km = np.asarray(pos_km, dtype=np.float32).astype(np.float64)
+    n = pos_km.shape[0]
+    kk = int(min(k + 1, n))
+    ind = cKDTree(pos_km).query(pos_km, k=kk)[1].reshape(n, kk)
+    tgt = np.repeat(np.arange(n), kk)
+    src = ind.reshape(-1)
+    keep = src != tgt
+    return torch.from_numpy(np.stack((src[keep], tgt[keep]), axis=0)).long()
+
+
+def extract_inputs_adjacencies_cartesian(locs_cart, grid_cart, k_sta_edges, k_spc_edges):
+    """The two small graphs of process_utils.py:712-719 for Cartesian coordinates in metres."""
+    k_sta = int(min(k_sta_edges, locs_cart.shape[0] - 2))
+    A_sta_sta = knn_graph((np.asarray(locs_cart, dtype=np.float64) / 1000.0).astype(np.float32), k_sta)
+    A_src_src = knn_graph((np.asarray(grid_cart, dtype=np.float64) / 1000.0).astype(np.float32), k_spc_edges)
+    return A_sta_sta, A_src_src
+
+
+def product_edge_lists(A_sta_sta, A_src_src, n_sta, n_grid):
+    """A_prod_sta_sta, A_prod_src_src, A_src_in_prod, A_src_in_sta of process_utils.py:720-722 /
+    process_continuous_days.py:629 (small networks only: these lists are what the CARTESIAN plan avoids)."""
+    S, G = n_sta, n_grid
+    A_prod_sta = (A_sta_sta.repeat(1, G) + S * torch.arange(G).repeat_interleave(A_sta_sta.shape[1]).view(1, -1))
+    A_prod_src = (S * A_src_src.repeat(1, S) + torch.arange(S).repeat_interleave(A_src_src.shape[1]).view(1, -1))
+    A_src_in_prod = torch.stack((torch.arange(S * G), torch.arange(G).repeat_interleave(S)), dim=0)
+    A_src_in_sta = torch.stack((torch.arange(S).repeat(G), torch.arange(G).repeat_interleave(S)), dim=0)
+    return A_prod_sta.contiguous(), A_prod_src.contiguous(), A_src_in_prod.contiguous(), A_src_in_sta.contiguous()
+
+
+# ---- a1 -----------------------------------------------------------------------------------------------------------------
+
+class InputExtractor(object):
+    """Device-resident state of `extract_input_from_data` for one (station set, source grid)."""
+
+    def __init__(self, plan, trv_times, ind_use, n_locs, max_t, kernel_sig_t, dt, node_sta=None, node_grid=None):
+        dev = plan.device
+        self.plan, self.max_t, self.kernel_sig_t, self.dt = plan, float(max_t), float(kernel_sig_t), float(dt)
+        self.n_locs = int(n_locs)
+        ind_use = np.asarray(ind_use).astype('int')
+        self.n_sta_use = len(ind_use)
+        perm = -1 * np.ones(self.n_locs, dtype=np.int32)
+        perm[ind_use] = np.arange(self.n_sta_use, dtype=np.int32)                       # process_utils.py:485-486
+        self.sta_perm = torch.from_numpy(perm).to(dev)
+        self.ind_use = torch.from_numpy(ind_use.astype(np.int32)).to(dev)
+        self.trv_times = trv_times if torch.is_tensor(trv_times) else torch.from_numpy(np.ascontiguousarray(trv_times))
+        self.trv_times = self.trv_times.to(dev, torch.float32).contiguous()
+        self.node_sta = None if node_sta is None else torch.as_tensor(node_sta).to(dev, torch.int32).contiguous()
+        self.node_grid = None if node_grid is None else torch.as_tensor(node_grid).to(dev, torch.int32).contiguous()
+        self._series = None
+        self._day = None
+
+    def params(self, t0):
+        return ops.input_params(t0, self.max_t, self.kernel_sig_t, self.dt, self.n_locs, self.n_sta_use)
+
+    def set_day(self, P):
+        """Keep a whole pick table [n,5] (sorted by time here) resident on the device."""
+        P = np.asarray(P, dtype=np.float64)
+        P = P[np.argsort(P[:, 0], kind='stable')]
+        self._day = (P[:, 0].copy(), torch.from_numpy(np.ascontiguousarray(P)).to(self.plan.device))
+
+    def window_rows(self, t0):
+        """Row range of the resident pick table that can touch window t0 (process_utils.py:476)."""
+        times = self._day[0]
+        lo = np.searchsorted(times, t0 - 2.0 * self.kernel_sig_t, side='left')
+        hi = np.searchsorted(times, t0 + self.max_t + 2.0 * self.kernel_sig_t, side='right')
+        return int(lo), int(hi)
+
+    def __call__(self, t0, picks=None, want_time_bin=False):
+        """picks: CUDA float64 [n,5] (any superset of the window's picks); None = use the resident day table."""
+        prm = self.params(t0)
+        if picks is None:
+            lo, hi = self.window_rows(float(t0))
+            picks = self._day[1][lo:hi]
+        if self._series is None or self._series.shape[2] != prm.n_ts:
+            self._series = torch.empty((2, self.n_sta_use, prm.n_ts), dtype=torch.float32, device=self.plan.device)
+        Slice, Mask, tb, _ = ops.input_scatter_fwd(self.plan, prm, picks, self.sta_perm, self.ind_use, self.trv_times,
+                                                   self.node_sta, self.node_grid, want_time_bin, self._series)
+        return (Slice, Mask, tb) if want_time_bin else (Slice, Mask)
+
+
+def extract_pick_inputs_from_data(P_slice, locs, ind_use, time_samples, max_t, t_win=10.0):
+    """process_utils.py:644-697 (use_batch False): picks of the window as (relative time, station index, phase, row)."""
+    n_sta = len(locs)
+    perm = -1 * np.ones(n_sta).astype('int')
+    perm[ind_use] = np.arange(len(ind_use))
+    ts = float(np.asarray(time_samples).reshape(-1)[0])
+    sel = np.where(np.abs(P_slice[:, 0] - (ts + max_t / 2.0)) <= (t_win + max_t / 2.0))[0]
+    meta = P_slice[sel, :]
+    idx = perm[meta[:, 1].astype('int')]
+    keep = np.where(idx > -1)[0]
+    meta, idx = meta[keep], idx[keep]
+    order = np.lexsort((meta[:, 0], idx))
+    return [[meta[order, 0] - ts], [idx[order]], [meta[order, 4]], [meta[order]]]
+
+
+_extractors = {}
+
+
+def extract_input_from_data(trv_pairwise, P, t0, ind_use, locs, x_grid, A_src_in_sta, trv_times=None, max_t=300.0,
+                            kernel_sig_t=5.0, dt=0.2, batch_grids=False, use_asserts=True, verbose=False,
+                            use_sign_input=False, return_embedding=False, device='cuda', plan=None):
+    """Same call as process_utils.py:460; returns `[Inpts, Masks], [lp_times, lp_stations, lp_phases, lp_meta]` with
+    Inpts/Masks CUDA tensors.  `trv_times` ([G, n_locs, 2]) is required; per-(grid, station set) state is cached."""
+    if trv_times is None or use_sign_input or batch_grids or return_embedding:
+        raise NotImplementedError('genie_b200.extract_input_from_data: needs trv_times; use_sign_input, batch_grids '
+                                  'and return_embedding are not supported')
+    t0v = float(np.asarray(t0).reshape(-1)[0])
+    ind_use = np.asarray(ind_use).astype('int')
+    A = A_src_in_sta.cpu().numpy() if torch.is_tensor(A_src_in_sta) else np.asarray(A_src_in_sta)
+    key = (id(trv_times), id(A_src_in_sta), len(ind_use), int(ind_use.sum()), float(max_t), float(kernel_sig_t),
+           float(dt), str(device))
+    ex = _extractors.get(key)
+    if ex is None:
+        G, S = int(x_grid.shape[0]), len(ind_use)
+        if plan is None:
+            # a node -> (station, grid) table is enough for a1; the plan only carries sizes here
+            dense = A.shape[1] == S * G and np.array_equal(A[0], np.tile(np.arange(S), G)) and \
+                np.array_equal(A[1], np.repeat(np.arange(G), S))
+            empty = torch.zeros((2, 0), dtype=torch.long)
+            if dense:
+                plan = GraphPlan.cartesian(empty, empty, S, G, device=device)
+            else:
+                plan = GraphPlan.explicit(empty, empty, torch.from_numpy(A[1].astype(np.int64)), empty, A.shape[1], G,
+                                          device=device)
+        nodes = (None, None) if plan.mode == 0 else (A[0], A[1])
+        ex = InputExtractor(plan, trv_times, ind_use, locs.shape[0], max_t, kernel_sig_t, dt, nodes[0], nodes[1])
+        _extractors.clear()
+        _extractors[key] = ex
+    P = np.asarray(P, dtype=np.float64)
+    keep = (P[:, 0] > (t0v - 2.0 * kernel_sig_t)) & (P[:, 0] < (t0v + max_t + 2.0 * kernel_sig_t))      # :476
+    P_slice = P[keep]
+    P_slice = P_slice[ex.sta_perm.cpu().numpy()[P_slice[:, 1].astype('int')] > -1]                     # :480-482
+    picks_dev = torch.from_numpy(np.ascontiguousarray(P_slice)).to(ex.plan.device)
+    Slice, Mask = ex(t0v, picks_dev)
+    lp = extract_pick_inputs_from_data(P_slice, locs, ind_use, np.array([t0v]), max_t)
+    return [[Slice], [Mask]], lp

@@ -1,0 +1,180 @@
+/*
+ * genie_b200.h — C-ABI of libgenie_b200.so: the B200 (sm_100a) product-graph front end of GENIE.
+ *
+ * The reference (imcbrearty/GENIE) has no FFI of its own: the hot path is reached through the Python classes of
+ * Code/module.py and the helper functions of Code/process_utils.py, whose arithmetic runs inside torch_geometric /
+ * torch_scatter / torch_cluster.  Every entry point below replaces one of those call sites; the citation after each
+ * declaration is the reference interface it stands in for.  INTEGRATION.md shows the ctypes binding a maintainer of the
+ * reference would add (genie_b200/capi.py is that binding).
+ *
+ * Conventions
+ *   - plain C types only; every pointer named *_dev / every `const float*` tensor argument is a DEVICE pointer owned
+ *     by the caller (torch allocates them); the library never allocates or frees device memory and never synchronises
+ *     the stream.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - all floating point tensors are fp32, row-major, dense; index arrays are int32 (columns) / int64 (row pointers).
+ *   - return value: 0 = ok, non-zero = error; genie_last_error() returns a thread-local message.
+ *   - re-entrant across distinct plans / workspaces; calls that share a workspace must be stream-ordered.
+ */
+#ifndef GENIE_B200_H_
+#define GENIE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GENIE_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define GENIE_API __attribute__((visibility("default")))
+#else
+#define GENIE_API
+#endif
+
+enum { GENIE_OK = 0, GENIE_ERR_INVALID = 1, GENIE_ERR_CUDA = 2, GENIE_ERR_UNSUPPORTED = 3 };
+
+/* ---- graph description -------------------------------------------------------------------------------------------
+ * Replaces the explicit int64 [2,E] edge lists the reference builds once per station set
+ * (process_utils.py:718-722 extract_inputs_adjacencies, :744-849 extract_inputs_adjacencies_subgraph) and hands to
+ * GCN_Detection_Network_extended.set_adjacencies (module.py:941).  All graphs are stored CSR *by destination*
+ * (row i lists the message sources j of target i), which is what mean/sum aggregation needs.
+ *
+ * GENIE_GRAPH_CARTESIAN: product node id = g*n_sta + s (process_continuous_days.py:629).  The product edges are never
+ *   materialised: sta_* is the station kNN graph A_sta_sta over n_sta nodes and src_* the grid kNN graph A_src_src
+ *   over n_grid nodes; (g,s) <- (g,s') for s' in sta(s) and (g,s) <- (g',s) for g' in src(g)  (process_utils.py:720-721).
+ * GENIE_GRAPH_EXPLICIT: arbitrary product graph (sub-graph mode): sta_* and src_* are CSR over the n_prod product
+ *   nodes themselves (A_in_sta / A_in_src of module.py:85), prod_grid[i] is the grid node product node i feeds
+ *   (A_src_in_edges.edge_index[1], module.py:229).
+ * grid_* is always the grid-node graph A_src used by SpatialAggregation (module.py:243); grid_outdeg[j] is the number
+ * of edges that leave grid node j (the 'global' feature of module.py:249 is a mean over edges).
+ */
+enum { GENIE_GRAPH_CARTESIAN = 0, GENIE_GRAPH_EXPLICIT = 1 };
+
+typedef struct genie_graph_desc {
+    int32_t mode;
+    int32_t n_sta;              /* S (CARTESIAN only, else 0) */
+    int32_t n_grid;             /* G */
+    int32_t reserved;
+    int64_t n_prod;             /* P (= S*G in CARTESIAN mode) */
+    const int64_t* sta_rowptr;  /* [S+1] or [P+1] */
+    const int32_t* sta_col;
+    const int64_t* src_rowptr;  /* [G+1] or [P+1] */
+    const int32_t* src_col;
+    const int64_t* grid_rowptr; /* [G+1] */
+    const int32_t* grid_col;
+    const int32_t* grid_outdeg; /* [G] */
+    const int32_t* prod_grid;   /* [P], EXPLICIT only (NULL otherwise); must be < n_grid */
+} genie_graph_desc_t;
+
+typedef struct genie_plan genie_plan_t;
+
+/* Validates `desc` (host-side checks only) and keeps a copy.  Replaces GCN_Detection_Network_extended.set_adjacencies,
+ * module.py:941-961. */
+GENIE_API int genie_plan_create(const genie_graph_desc_t* desc, genie_plan_t** plan_out);
+GENIE_API void genie_plan_destroy(genie_plan_t* plan);
+/* Bytes of caller-provided scratch the forward entry points need for this plan (intermediate node features). */
+GENIE_API size_t genie_plan_workspace_bytes(const genie_plan_t* plan);
+
+/* ---- weights -------------------------------------------------------------------------------------------------------
+ * Device pointers straight into the reference's state_dict tensors (nn.Linear weight [out,in] row-major, bias [out],
+ * nn.PReLU weight [1]); names are the reference's attribute names (module.py:53-83, 214-222, 231-241).
+ * DataAggregation.l1_t1_1 / l1_t2_1 are unused by the reference's forward (module.py:90-91) and so absent here.
+ */
+typedef struct genie_linear { const float* weight; const float* bias; } genie_linear_t;
+
+typedef struct genie_frontend_weights {
+    /* DataAggregation(4, 15) — module.py:52-98 */
+    genie_linear_t da_init_trns;                 /* 8  -> 30 */
+    genie_linear_t da_l1_t1_2, da_l1_t2_2;       /* 64 -> 30 */
+    genie_linear_t da_l2_t1_1, da_l2_t2_1;       /* 60 -> 30 */
+    genie_linear_t da_l2_t1_2, da_l2_t2_2;       /* 94 -> 15 */
+    const float *da_activate, *da_activate11, *da_activate12, *da_activate1, *da_activate21, *da_activate22,
+        *da_activate2;
+    /* BipartiteGraphOperator(30, 15, ndim_edges = 3) — module.py:214-229 */
+    genie_linear_t ri_fc1;                       /* 33 -> 30 */
+    genie_linear_t ri_fc2;                       /* 30 -> 15 */
+    const float *ri_activate1, *ri_activate2;
+    /* SpatialAggregation(15,30), (30,30), (30,30) — module.py:231-249 */
+    struct {
+        genie_linear_t fc1;                      /* C+8  -> 30 */
+        genie_linear_t fc2;                      /* 30+C -> 30 */
+        genie_linear_t fglobal;                  /* C    -> 5  */
+        const float *activate1, *activate2, *activate3;
+    } sa[3];
+} genie_frontend_weights_t;
+
+/* Number of floats of the packed (kernel-layout) weight buffer. */
+GENIE_API size_t genie_frontend_packed_floats(void);
+/* Re-lays the reference-layout weights into `packed_dev` (one small kernel; call again whenever weights change). */
+GENIE_API int genie_frontend_pack_weights(const genie_frontend_weights_t* w, float* packed_dev, void* stream);
+
+/* ---- a1: pick window -> Slice / Mask ---------------------------------------------------------------------------------
+ * Replaces process_utils.extract_input_from_data (process_utils.py:460-629; use_sign_input False, trv_times given).
+ * The fp64 quantities that the reference derives on the host with numpy (`abs_time_ref[0]`, the arange step
+ * `(start+dt)-start`, `len(abs_time_ref)`, `ceil(3*sigma/dt)`) are computed by the caller with the same expressions and
+ * passed in, so the integer pick->bin and node->bin maps are bit-identical to numpy's.
+ */
+typedef struct genie_input_params {
+    double t0;              /* window origin time (s) */
+    double max_t;           /* maximum moveout (s) */
+    double kernel_sig_t;    /* sigma (s) */
+    double dt;              /* series sampling (s) */
+    double ref0;            /* abs_time_ref[0] = t0 - 3*sigma            (process_utils.py:500-502) */
+    double ref_step;        /* abs_time_ref[1] - abs_time_ref[0] as numpy.arange produces it */
+    int32_t n_ts;           /* len(abs_time_ref) */
+    int32_t n_extra;        /* ceil(3*sigma/dt)                           (process_utils.py:520) */
+    int32_t n_locs;         /* number of stations of the absolute station table */
+    int32_t n_sta_use;      /* number of used stations (len(ind_use)) */
+} genie_input_params_t;
+
+/* picks_dev      fp64 [n_picks,5] (time, absolute station, amp, prob, phase 0/1), any order.
+ * sta_perm_dev   int32 [n_locs]: absolute station -> index into ind_use, or -1 (process_utils.py:485-486).
+ * ind_use_dev    int32 [n_sta_use]: used station -> absolute station.
+ * trv_times_dev  fp32 [n_grid, n_locs, 2] travel times (s).
+ * node_sta_dev / node_grid_dev: int32 [n_prod] (A_src_in_sta rows 0/1) or both NULL in CARTESIAN mode.
+ * series_dev     fp32 scratch [2, n_sta_use, n_ts] (overwritten).
+ * slice_out_dev, mask_out_dev: fp32 [n_prod,4].  time_bin_out_dev: optional int64 [n_prod,2] (the integer index map).
+ */
+GENIE_API int genie_input_scatter_fwd(const genie_plan_t* plan, const genie_input_params_t* prm, const double* picks_dev,
+                            int64_t n_picks, const int32_t* sta_perm_dev, const int32_t* ind_use_dev,
+                            const float* trv_times_dev, const int32_t* node_sta_dev, const int32_t* node_grid_dev,
+                            float* series_dev, float* slice_out_dev, float* mask_out_dev, int64_t* time_bin_out_dev,
+                            void* stream);
+
+/* ---- a2: DataAggregation.forward — module.py:85-98 -----------------------------------------------------------------
+ * slice_dev, mask_dev fp32 [P,4] -> x_latent_out_dev fp32 [P,30]. */
+GENIE_API int genie_data_aggregation_fwd(const genie_plan_t* plan, const float* packed_dev, const float* slice_dev,
+                               const float* mask_dev, float* x_latent_out_dev, void* workspace_dev, void* stream);
+
+/* ---- a3: BipartiteGraphOperator.forward — module.py:224-229 --------------------------------------------------------
+ * x_latent_dev [P,30], edge_attr_dev [P,3] (A_src_in_edges.x), mask_dev [P,4] -> out_dev [G,15]. */
+GENIE_API int genie_bipartite_readin_fwd(const genie_plan_t* plan, const float* packed_dev, const float* x_latent_dev,
+                               const float* edge_attr_dev, const float* mask_dev, float* out_dev,
+                               void* workspace_dev, void* stream);
+
+/* ---- a4: SpatialAggregation.forward — module.py:243-249 ------------------------------------------------------------
+ * layer = 0,1,2 (SpatialAggregation1..3): x_dev [G,C] (C = 15,30,30), pos_dev [G,3] Cartesian metres -> out_dev [G,30]. */
+GENIE_API int genie_spatial_aggregation_fwd(const genie_plan_t* plan, const float* packed_dev, int32_t layer, const float* x_dev,
+                                  const float* pos_dev, float scale_rel, float* out_dev, void* workspace_dev,
+                                  void* stream);
+
+/* ---- fused a2+a3+a4x3: the front end of forward_fixed_source — module.py:1010-1014 ---------------------------------
+ * x_latent_out_dev [P,30] and readin_out_dev [G,15] are optional (NULL = not materialised);
+ * x_spatial_out_dev [G,30] is SpatialAggregation3's output. */
+GENIE_API int genie_frontend_fwd(const genie_plan_t* plan, const float* packed_dev, const float* slice_dev,
+                       const float* mask_dev, const float* edge_attr_dev, const float* pos_dev, float scale_rel,
+                       float* x_latent_out_dev, float* readin_out_dev, float* x_spatial_out_dev,
+                       void* workspace_dev, void* stream);
+
+/* ---- misc ---------------------------------------------------------------------------------------------------------- */
+GENIE_API const char* genie_last_error(void);
+GENIE_API int genie_abi_version(void);
+/* Number of kernels this library has launched in the calling process (bench.py's `gpu_launches`). */
+GENIE_API int64_t genie_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENIE_B200_H_ */

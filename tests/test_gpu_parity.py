@@ -1,0 +1,256 @@
+"""Parity of the CUDA path (through the C-ABI) against the golden fixtures and the CPU oracle.  Needs a GPU.
+
+Tolerance: BASELINE.json's north star — fp32 outputs within 1e-4 relative (max |a-b| / max |b|); the integer
+pick -> time-bin map bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+GOLD = ['c1_10x100', 'mid_36of40x300', 'small_6x40', 'ferndale_t38940']
+TOL = 1e-4
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.fail('these tests need a CUDA device (run with -m gpu on the B200 box)')
+    return torch.device('cuda:0')
+
+
+def _model(sd, dev, scale_rel, scale_t):
+    from genie_b200.module import GCN_Detection_Network_extended
+    m = GCN_Detection_Network_extended(None, None, scale_rel=scale_rel, device=dev)
+    m.load_state_dict(sd)
+    m.TemporalAttention.scale_t = scale_t
+    m.eval()
+    return m
+
+
+def _graphs(d):
+    from oracle import genie_oracle as go
+    return go.build_adjacencies_dense(d['sta'][d['ind_use']], d['grid'], int(d['k_sta']), int(d['k_spc']))
+
+
+@pytest.mark.parametrize('name', GOLD)
+def test_input_scatter_matches_reference(name):
+    """a1: Slice/Mask against the reference's extract_input_from_data; time-bin map bit-exact against the oracle."""
+    from genie_b200.plan import GraphPlan
+    from genie_b200.process_utils import InputExtractor
+    from oracle import genie_oracle as go
+    dev = _dev()
+    d, _ = load_golden(name)
+    S, G = len(d['ind_use']), d['grid'].shape[0]
+    A_sta, A_src, _, _, _, A_sis = _graphs(d)
+    plan = GraphPlan.cartesian(A_sta, A_src, S, G, device=dev)
+    ex = InputExtractor(plan, d['trv_times'], d['ind_use'], d['sta'].shape[0], float(d['max_t']),
+                        float(d['kernel_sig_t']), float(d['dt']))
+    picks = torch.from_numpy(d['picks']).to(dev)
+    Slice, Mask, tb = ex(float(d['t0']), picks, want_time_bin=True)
+    _, _, parts = go.input_scatter(d['picks'], float(d['t0']), d['ind_use'], d['sta'].shape[0], A_sis.numpy(),
+                                   d['trv_times'], float(d['max_t']), float(d['kernel_sig_t']), float(d['dt']),
+                                   return_parts=True)
+    assert np.array_equal(tb.cpu().numpy(), parts['time_bin'])            # integer map: bit-exact
+    assert ex.params(float(d['t0'])).n_ts == int(d['n_ts'])
+    assert np.abs(Slice.cpu().numpy() - d['Slice']).max() <= 1e-6
+    assert np.array_equal(Mask.cpu().numpy(), d['Mask'])
+    # same result through the explicit node table (sub-graph style addressing)
+    ex2 = InputExtractor(plan, d['trv_times'], d['ind_use'], d['sta'].shape[0], float(d['max_t']),
+                         float(d['kernel_sig_t']), float(d['dt']), A_sis[0].numpy(), A_sis[1].numpy())
+    S2, M2 = ex2(float(d['t0']), picks)
+    assert torch.equal(S2, Slice) and torch.equal(M2, Mask)
+
+
+@pytest.mark.parametrize('name', GOLD)
+def test_operators_match_reference(name):
+    """a2, a3, a4 one by one, each fed the reference's own input for that stage."""
+    from genie_b200 import ops
+    from genie_b200.plan import GraphPlan
+    dev = _dev()
+    d, sd = load_golden(name)
+    S, G = len(d['ind_use']), d['grid'].shape[0]
+    A_sta, A_src, A_ps, A_pg, A_sip, _ = _graphs(d)
+    m = _model(sd, dev, float(d['scale_rel']), float(d['scale_t']))
+    packed = m._packed_weights(dev)
+    t = lambda k: torch.from_numpy(d[k]).to(dev)
+    pos = torch.from_numpy(d['grid']).float().to(dev)
+    plans = {
+        'cartesian': GraphPlan.cartesian(A_sta, A_src, S, G, device=dev),
+        'explicit': GraphPlan.explicit(A_ps, A_pg, A_sip[1], A_src, S * G, G, device=dev),
+    }
+    for kind, plan in plans.items():
+        lat = ops.data_aggregation_fwd(plan, packed, t('Slice'), t('Mask'))
+        assert rel_err(lat.cpu().numpy(), d['x_latent']) < TOL, kind
+        r = ops.bipartite_readin_fwd(plan, packed, t('x_latent'), t('read_in_attr'), t('Mask'))
+        assert rel_err(r.cpu().numpy(), d['read_in']) < TOL, kind
+        for layer, (src, dst) in enumerate((('read_in', 'sa1'), ('sa1', 'sa2'), ('sa2', 'x_spatial'))):
+            o = ops.spatial_aggregation_fwd(plan, packed, layer, t(src), pos, float(d['scale_rel']))
+            assert rel_err(o.cpu().numpy(), d[dst]) < TOL, (kind, layer)
+        xs, lat2, r2 = ops.frontend_fwd(plan, packed, t('Slice'), t('Mask'), t('read_in_attr'), pos,
+                                        float(d['scale_rel']), want_latent=True, want_readin=True)
+        assert rel_err(xs.cpu().numpy(), d['x_spatial']) < TOL, kind
+        assert rel_err(lat2.cpu().numpy(), d['x_latent']) < TOL, kind
+        assert rel_err(r2.cpu().numpy(), d['read_in']) < TOL, kind
+
+
+@pytest.mark.parametrize('name', GOLD)
+def test_forward_fixed_source_matches_reference(name):
+    """The nn.Module surface: set_adjacencies with the reference's explicit edge lists + forward_fixed_source."""
+    from genie_b200 import capi
+    from oracle.refshim.torch_geometric.data import Data
+    dev = _dev()
+    d, sd = load_golden(name)
+    S, G = len(d['ind_use']), d['grid'].shape[0]
+    A_sta, A_src, A_ps, A_pg, A_sip, A_sis = _graphs(d)
+    m = _model(sd, dev, float(d['scale_rel']), float(d['scale_t']))
+    t = lambda k: torch.from_numpy(d[k]).to(dev)
+    locs = torch.from_numpy(d['sta'][d['ind_use']]).float().to(dev)
+    grid = torch.from_numpy(d['grid']).float().to(dev)
+    A_edges = Data(x=t('read_in_attr'), edge_index=A_sip.to(dev))
+    m.set_adjacencies(A_ps.to(dev), A_pg.to(dev), A_edges, None, A_sis.to(dev), A_src.to(dev), None, None, None, None,
+                      locs, grid)
+    assert m._plan.mode == capi.GRAPH_CARTESIAN            # the index pattern of process_utils.py:720-722 is recognised
+    n0 = capi.launch_count()
+    y, x = m.forward_fixed_source(t('Slice'), t('Mask'), None, None, None, locs, grid,
+                                  torch.from_numpy(d['x_query']).float().to(dev),
+                                  torch.from_numpy(d['t_query']).float().reshape(-1, 1).to(dev))
+    assert capi.launch_count() - n0 >= 10                  # our kernels ran (no silent fallback exists)
+    assert rel_err(y.cpu().numpy(), d['y']) < TOL
+    assert rel_err(x.cpu().numpy(), d['x']) < TOL
+
+
+def _random_case(S, G, k_s, k_g, seed, dev):
+    from genie_b200 import synth
+    from genie_b200.process_utils import extract_inputs_adjacencies_cartesian
+    net = synth.Network(S, G, seed=seed)
+    A_sta, A_src = extract_inputs_adjacencies_cartesian(net.sta, net.grid, k_s, k_g)
+    rng = np.random.default_rng(seed)
+    P = S * G
+    Slice = (rng.random((P, 4)) * (rng.random((P, 4)) < 0.35)).astype(np.float32)
+    Mask = (np.abs(Slice) > 0.01).astype(np.float32)
+    attr = net.read_in_offsets(np.array([net.width, net.width, 42000.0]))
+    return net, A_sta, A_src, torch.from_numpy(Slice), torch.from_numpy(Mask), torch.from_numpy(attr)
+
+
+@pytest.mark.parametrize('S,G,k_s,k_g', [(100, 500, 15, 15), (37, 211, 8, 15), (130, 64, 10, 5)])
+def test_front_end_matches_oracle_seeded(S, G, k_s, k_g):
+    """Seeded synthetic networks against the CPU oracle computed on the spot (ragged tiles: P not a multiple of 128)."""
+    from genie_b200 import ops
+    from genie_b200.plan import GraphPlan
+    from genie_b200.process_utils import product_edge_lists
+    from oracle import genie_oracle as go
+    dev = _dev()
+    net, A_sta, A_src, Slice, Mask, attr = _random_case(S, G, k_s, k_g, 11, dev)
+    sd = go.init_state(seed=2)
+    A_ps, A_pg, A_sip, _ = product_edge_lists(A_sta, A_src, S, G)
+    grid = torch.from_numpy(net.grid).float()
+    want, parts = go.front_end(sd, Slice, Mask, A_ps, A_pg, attr, A_sip, A_src, grid, 30000.0, return_parts=True)
+    from genie_b200.module import GCN_Detection_Network_extended
+    m = GCN_Detection_Network_extended(None, None, device=dev)
+    m.load_state_dict(sd, strict=False)
+    packed = m._packed_weights(dev)
+    plan = GraphPlan.cartesian(A_sta, A_src, S, G, device=dev)
+    xs, lat, r = ops.frontend_fwd(plan, packed, Slice.to(dev), Mask.to(dev), attr.to(dev), grid.to(dev), 30000.0,
+                                  want_latent=True, want_readin=True)
+    assert rel_err(lat.cpu().numpy(), parts['x_latent'].numpy()) < TOL
+    assert rel_err(r.cpu().numpy(), parts['read_in'].numpy()) < TOL
+    assert rel_err(xs.cpu().numpy(), want.numpy()) < TOL
+
+
+def test_irregular_explicit_graph_matches_oracle():
+    """Sub-graph style product graph: variable in-degree, isolated nodes (mean of nothing = 0), unsorted edge order."""
+    from genie_b200 import ops
+    from genie_b200.plan import GraphPlan
+    from oracle import genie_oracle as go
+    dev = _dev()
+    rng = np.random.default_rng(5)
+    G, P = 57, 3001
+    prod_grid = np.sort(rng.integers(0, G, P))
+    prod_grid[:3] = 0
+    E1, E2 = 7 * P, 11 * P
+    A1 = torch.from_numpy(np.stack((rng.integers(0, P, E1), rng.integers(0, P - 40, E1)), 0)).long()   # last 40 isolated
+    A2 = torch.from_numpy(np.stack((rng.integers(0, P, E2), rng.integers(40, P, E2)), 0)).long()       # first 40 isolated
+    A_src = torch.from_numpy(np.stack((rng.integers(0, G, 9 * G), rng.integers(0, G - 1, 9 * G)), 0)).long()
+    Slice = torch.from_numpy((rng.random((P, 4)) * (rng.random((P, 4)) < 0.4)).astype(np.float32))
+    Mask = (Slice.abs() > 0.01).float()
+    attr = torch.from_numpy(rng.normal(size=(P, 3)).astype(np.float32))
+    pos = torch.from_numpy(rng.uniform(0, 1e5, (G, 3)).astype(np.float32))
+    read_idx = torch.stack((torch.arange(P), torch.from_numpy(prod_grid).long()), 0)
+    sd = go.init_state(seed=3)
+    # the oracle's read-in sizes its output by max target + 1 (module.py:227): make the last grid node present
+    assert prod_grid.max() == G - 1
+    want, parts = go.front_end(sd, Slice, Mask, A1, A2, attr, read_idx, A_src, pos, 30000.0, return_parts=True)
+    from genie_b200.module import GCN_Detection_Network_extended
+    m = GCN_Detection_Network_extended(None, None, device=dev)
+    m.load_state_dict(sd, strict=False)
+    packed = m._packed_weights(dev)
+    plan = GraphPlan.from_edge_lists(A1.to(dev), A2.to(dev), read_idx.to(dev), A_src.to(dev), 1, G, device=dev)
+    assert plan.mode == 1
+    xs, lat, r = ops.frontend_fwd(plan, packed, Slice.to(dev), Mask.to(dev), attr.to(dev), pos.to(dev), 30000.0,
+                                  want_latent=True, want_readin=True)
+    assert rel_err(lat.cpu().numpy(), parts['x_latent'].numpy()) < TOL
+    assert rel_err(r.cpu().numpy(), parts['read_in'].numpy()) < TOL
+    assert rel_err(xs.cpu().numpy(), want.numpy()) < TOL
+
+
+def test_station_permutation_invariance_large():
+    """Size-independent property at a size the oracle cannot reach quickly: relabelling the stations (graphs, inputs and
+    read-in features permuted consistently) permutes x_latent and leaves the grid-level output unchanged."""
+    from genie_b200 import ops
+    from genie_b200.plan import GraphPlan
+    from oracle import genie_oracle as go
+    dev = _dev()
+    S, G = 1000, 1500
+    net, A_sta, A_src, Slice, Mask, attr = _random_case(S, G, 15, 15, 21, dev)
+    sd = go.init_state(seed=4)
+    from genie_b200.module import GCN_Detection_Network_extended
+    m = GCN_Detection_Network_extended(None, None, device=dev)
+    m.load_state_dict(sd, strict=False)
+    packed = m._packed_weights(dev)
+    grid = torch.from_numpy(net.grid).float().to(dev)
+    plan = GraphPlan.cartesian(A_sta, A_src, S, G, device=dev)
+    xs, lat, _ = ops.frontend_fwd(plan, packed, Slice.to(dev), Mask.to(dev), attr.to(dev), grid, 30000.0,
+                                  want_latent=True)
+    perm = torch.from_numpy(np.random.default_rng(0).permutation(S))          # new station id -> old station id
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(S)
+    A_sta_p = inv[A_sta]                                                       # relabel both endpoints
+    pm = lambda x: x.view(G, S, -1)[:, perm, :].reshape(G * S, -1).contiguous()
+    plan_p = GraphPlan.cartesian(A_sta_p, A_src, S, G, device=dev)
+    xs_p, lat_p, _ = ops.frontend_fwd(plan_p, packed, pm(Slice).to(dev), pm(Mask).to(dev), pm(attr).to(dev), grid,
+                                      30000.0, want_latent=True)
+    assert rel_err(lat_p.cpu().numpy(), pm(lat.cpu()).numpy()) < 1e-5
+    assert rel_err(xs_p.cpu().numpy(), xs.cpu().numpy()) < 1e-5
+    # run-to-run: everything but the cross-tile read-in atomics is order-fixed
+    xs2, lat2, _ = ops.frontend_fwd(plan, packed, Slice.to(dev), Mask.to(dev), attr.to(dev), grid, 30000.0,
+                                    want_latent=True)
+    assert torch.equal(lat2, lat)
+    assert rel_err(xs2.cpu().numpy(), xs.cpu().numpy()) < 1e-5
+
+
+def test_config2_against_oracle():
+    """BASELINE.json configs[1]: 100 stations x 5000 grid nodes, k = 15 / 15 (P = 500 000), full front end vs oracle."""
+    from genie_b200 import ops
+    from genie_b200.plan import GraphPlan
+    from genie_b200.process_utils import product_edge_lists
+    from oracle import genie_oracle as go
+    dev = _dev()
+    S, G = 100, 5000
+    net, A_sta, A_src, Slice, Mask, attr = _random_case(S, G, 15, 15, 31, dev)
+    sd = go.init_state(seed=2)
+    A_ps, A_pg, A_sip, _ = product_edge_lists(A_sta, A_src, S, G)
+    grid = torch.from_numpy(net.grid).float()
+    want, parts = go.front_end(sd, Slice, Mask, A_ps, A_pg, attr, A_sip, A_src, grid, 30000.0, return_parts=True)
+    from genie_b200.module import GCN_Detection_Network_extended
+    m = GCN_Detection_Network_extended(None, None, device=dev)
+    m.load_state_dict(sd, strict=False)
+    plan = GraphPlan.from_edge_lists(A_ps.to(dev), A_pg.to(dev), A_sip.to(dev), A_src.to(dev), S, G, device=dev)
+    assert plan.mode == 0
+    xs, lat, r = ops.frontend_fwd(plan, m._packed_weights(dev), Slice.to(dev), Mask.to(dev), attr.to(dev),
+                                  grid.to(dev), 30000.0, want_latent=True, want_readin=True)
+    assert rel_err(lat.cpu().numpy(), parts['x_latent'].numpy()) < TOL
+    assert rel_err(r.cpu().numpy(), parts['read_in'].numpy()) < TOL
+    assert rel_err(xs.cpu().numpy(), want.numpy()) < TOL

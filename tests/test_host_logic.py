@@ -1,0 +1,130 @@
+"""CPU-only tests: the C-ABI library loads and exports what include/genie_b200.h declares; host-side plan logic."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import REPO, load_golden
+from oracle import genie_oracle as go
+
+
+def _declared_symbols():
+    text = open(os.path.join(REPO, 'include', 'genie_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(genie_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from genie_b200 import capi
+    lib = capi.load()                                  # builds with nvcc if missing
+    names = _declared_symbols()
+    assert len(names) >= 13
+    for n in names:
+        assert hasattr(lib, n), n
+    assert set(names) == set(capi.SIGNATURES)           # the ctypes binding covers the whole header
+    assert lib.genie_abi_version() == 1
+    assert lib.genie_frontend_packed_floats() > 20000
+    assert lib.genie_launch_count() == 0                # nothing was launched (no GPU here)
+
+
+def test_plan_create_rejects_bad_descriptors():
+    from genie_b200 import capi
+    lib = capi.load()
+    h = ctypes.c_void_p()
+    d = capi.GraphDesc()
+    d.mode = 7
+    assert lib.genie_plan_create(ctypes.byref(d), ctypes.byref(h)) != 0
+    assert b'mode' in lib.genie_last_error()
+    d.mode, d.n_sta, d.n_grid, d.n_prod = 0, 3, 4, 13
+    assert lib.genie_plan_create(ctypes.byref(d), ctypes.byref(h)) != 0
+    assert b'n_sta * n_grid' in lib.genie_last_error()
+    assert lib.genie_plan_create(None, ctypes.byref(h)) != 0
+
+
+def test_ops_fail_loudly_without_cuda():
+    from genie_b200 import capi
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    with pytest.raises(capi.GenieError):
+        capi.dptr(torch.zeros(4), torch.float32, 'x')
+
+
+def test_csr_by_destination():
+    from genie_b200.plan import csr_by_destination
+    e = torch.tensor([[5, 1, 2, 0, 3], [2, 0, 2, 3, 0]])
+    rowptr, col = csr_by_destination(e, 5)
+    assert rowptr.tolist() == [0, 2, 2, 4, 5, 5]
+    assert col.tolist() == [1, 3, 5, 2, 0]              # stable: source order kept inside each row
+    with pytest.raises(ValueError):
+        csr_by_destination(torch.tensor([[0], [9]]), 5)
+
+
+@pytest.mark.parametrize('name', ['c1_10x100', 'small_6x40'])
+def test_cartesian_pattern_detection(name):
+    from genie_b200.plan import _is_cartesian
+    d, _ = load_golden(name)
+    S, G = len(d['ind_use']), d['grid'].shape[0]
+    A_sta, A_src, A_ps, A_pg, A_sip, _ = go.build_adjacencies_dense(d['sta'][d['ind_use']], d['grid'], int(d['k_sta']),
+                                                                    int(d['k_spc']))
+    got = _is_cartesian(A_ps, A_pg, A_sip[1], S, G)
+    assert got is not None and torch.equal(got[0], A_sta) and torch.equal(got[1], A_src)
+    bad = A_ps.clone()
+    bad[0, -1] = (bad[0, -1] + 1) % (S * G)
+    assert _is_cartesian(bad, A_pg, A_sip[1], S, G) is None
+    bad = A_pg.clone()
+    bad[1, 3] = (bad[1, 3] + 1) % (S * G)
+    assert _is_cartesian(A_ps, bad, A_sip[1], S, G) is None
+
+
+def test_knn_graph_matches_oracle_and_reference():
+    from genie_b200.process_utils import extract_inputs_adjacencies_cartesian
+    d, _ = load_golden('mid_36of40x300')
+    A_sta, A_src = extract_inputs_adjacencies_cartesian(d['sta'][d['ind_use']], d['grid'], int(d['k_sta']), int(d['k_spc']))
+    assert np.array_equal(A_sta.numpy(), d['A_sta_sta']) and np.array_equal(A_src.numpy(), d['A_src_src'])
+
+
+@pytest.mark.parametrize('t0,max_t,sig', [(200.0, 60.0, 3.0), (38940.0, 83.0, 3.5), (86399.7, 300.0, 3.0),
+                                          (1234.5678, 127.0, 2.5)])
+def test_input_params_follow_numpy_arange(t0, max_t, sig):
+    """ref0 + i*ref_step and n_ts reproduce numpy.arange bit for bit (process_utils.py:502)."""
+    from genie_b200 import ops
+    dt = float(np.round(sig / 10.0, 2))
+    prm = ops.input_params(t0, max_t, sig, dt, 10, 10)
+    ref, n_ts = go.input_time_axis(t0, max_t, sig, dt)
+    assert prm.n_ts == n_ts and prm.ref0 == ref[0]
+    i = np.arange(n_ts, dtype=np.float64)
+    assert np.array_equal(prm.ref0 + i * prm.ref_step, ref)
+    assert prm.n_extra == int(np.ceil(3 * sig / dt))
+
+
+def test_extract_pick_inputs_matches_reference_semantics():
+    from genie_b200.process_utils import extract_pick_inputs_from_data
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(0)
+    P = np.stack((rng.uniform(0, 500, 400), rng.integers(0, 12, 400).astype(float), np.ones(400), np.ones(400),
+                  rng.integers(0, 2, 400).astype(float)), 1)
+    ind_use = np.array([0, 2, 3, 5, 7, 8, 11])
+    t, max_t = np.array([120.0]), 60.0
+    lp_t, lp_s, lp_p, lp_m = extract_pick_inputs_from_data(P, np.zeros((12, 3)), ind_use, t, max_t)
+    # process_utils.py:660-691 restated with the k-d tree the reference uses
+    lp = cKDTree(P[:, [0]]).query_ball_point(t.reshape(-1, 1) + max_t / 2.0, r=10.0 + max_t / 2.0)[0]
+    perm = -np.ones(12, dtype=int)
+    perm[ind_use] = np.arange(len(ind_use))
+    meta = P[sorted(lp)]
+    idx = perm[meta[:, 1].astype(int)]
+    meta, idx = meta[idx > -1], idx[idx > -1]
+    order = np.lexsort((meta[:, 0], idx))
+    assert np.array_equal(lp_m[0], meta[order]) and np.array_equal(lp_s[0], idx[order])
+    assert np.array_equal(lp_t[0], meta[order, 0] - 120.0) and np.array_equal(lp_p[0], meta[order, 4])
+
+
+def test_synthetic_network_is_seeded():
+    from genie_b200 import synth
+    a, b = synth.Network(20, 50, seed=3), synth.Network(20, 50, seed=3)
+    assert np.array_equal(a.sta, b.sta) and np.array_equal(a.grid, b.grid)
+    P = synth.make_picks(a, 0.0, 300.0, seed=1)
+    assert P.shape[1] == 5 and np.all(np.diff(P[:, 0]) >= 0) and set(np.unique(P[:, 4])) <= {0.0, 1.0}
+    assert a.travel_times().shape == (50, 20, 2) and a.travel_times().max() < a.max_moveout()
