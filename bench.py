@@ -1,0 +1,378 @@
+"""bench.py — time-windows/sec of GENIE's product-graph front end on B200 (BASELINE.json's metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (N>1: launched under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores (oracle port)
+
+One step = one time window = input scatter (a1: picks -> Slice/Mask) + front end (a2-a4: DataAggregation ->
+Bipartite_ReadIn -> SpatialAggregation x3) + read-out heads, i.e. one pass of the inference loop of the reference's
+process_continuous_days.py:788-805 for one origin-time sample.  Workload: the synthetic 1000-station x 50000-grid-node
+network of SURVEY.md §8d (dense product graph, P = 5e7 product nodes, k = 15/15), 24 h of synthetic picks.
+
+Prints ONE JSON line (rank 0).  Keys beyond the driver's contract:
+  value     windows/s with the day's picks, travel times and graphs resident in HBM (device-timed, max over ranks)
+  e2e       the same metric through the public API with HOST buffers: per window the picks are copied from pinned host
+            memory, and y [G,T,1] / x [Q,T,1] are copied back (the reference's loop does exactly this, :797-805)
+  roofline  dominant kernel: algorithmic bytes per launch / its mean device time (cudaEvents recorded by the library on
+            the launching stream inside the timed region), against MEASURED_PEAKS.json's HBM copy bandwidth
+  cpu_baseline  the oracle (CPU port of the reference algorithm) timed on this box's host cores on a bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = 'time-windows/sec at 1k stations x 50k grid nodes'
+UNIT = 'windows/s'
+WORKLOADS = {
+    # name: (stations, grid nodes, k_sta, k_grid)
+    'c4_1000x50000_dense': (1000, 50000, 15, 15),
+    'c2_100x5000_dense': (100, 5000, 15, 15),
+    'c1_10x100_dense': (10, 100, 8, 15),
+}
+KERNEL_SIG_T, DT, STEP_S, N_QUERY, SCALE_REL = 3.0, 0.3, 3.0, 10000, 30000.0
+DAY_S = 86400.0
+# algorithmic (compulsory) bytes per product node, fp32 intermediates — SURVEY.md §8d / DESIGN.md §4
+BYTES_PER_NODE_WINDOW = 764.0
+BYTES_PER_NODE_KERNEL = {'da_init_kernel': 152.0, 'da_layer1_kernel': 360.0, 'da_layer2_readin_kernel': 252.0,
+                         'da_layer1_tc_kernel': 360.0}
+
+
+def _peaks():
+    p = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def _traffic(kernel):
+    """Per-launch DRAM bytes of `kernel` from the committed ncu --set full capture (profiles/roofline_traffic.json)."""
+    p = os.path.join(REPO, 'profiles', 'roofline_traffic.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(kernel)
+    return None
+
+
+def _query_points(net, n, seed=3):
+    rng = np.random.default_rng(seed)
+    return np.stack((rng.uniform(0, net.width, n), rng.uniform(0, net.width, n), rng.uniform(-40000.0, 0.0, n)), axis=1)
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs (B200_PROFILING.md's clocks line)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
+                                       '--format=csv,noheader,nounits', '-lms', '50'], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(',')]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1])); pw.append(float(c[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, c[3:7]):
+                if v == 'Active':
+                    reasons.add(nme)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)),
+                       reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---- the reference algorithm on the host cores (oracle port) ------------------------------------------------------------
+
+def cpu_reference(workload, steps, warmup, grid_sample=None):
+    """Times oracle.forward_fixed_source + oracle.input_scatter (torch-CPU fp32, all host threads) on a bounded sample:
+    all stations, the first `grid_sample` grid nodes (Morton order => a compact sub-volume) with their own kNN graph.
+    Cost is linear in the number of product nodes, so windows/s at full size = sample rate * Gs/G."""
+    import torch
+    from genie_b200 import synth
+    from oracle import genie_oracle as go
+    S, G, k_s, k_g = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if grid_sample is None:
+        per_step_nodes = 5.0e5 * min(1.0, 30.0 / max(steps + warmup, 1))     # ~2 s per 5e5 nodes on 8-16 cores
+        grid_sample = int(max(20, min(G, per_step_nodes // S)))
+    Gs = min(G, grid_sample)
+    net = synth.Network(S, G, seed=0)
+    grid = net.grid[:Gs]
+    A = go.build_adjacencies_dense(net.sta, grid, k_s, k_g)
+    trv = net.travel_times(0, Gs)
+    attr = torch.from_numpy(net.read_in_offsets(SCALE_REL, 0, Gs))
+    max_t = net.max_moveout()
+    n_win = steps + warmup
+    picks = synth.make_picks(net, 0.0, n_win * STEP_S + max_t + 4 * KERNEL_SIG_T, seed=1)
+    sd = go.init_state(seed=2)
+    xq = torch.from_numpy(_query_points(net, min(N_QUERY, max(100, N_QUERY * Gs // G)))).float()
+    tq = torch.arange(-3.0, 3.01, 0.75).reshape(-1, 1)
+    gridt = torch.from_numpy(grid).float()
+    ind_use = np.arange(S)
+    qe = None
+    times = []
+    with torch.no_grad():
+        for i in range(n_win):
+            t0 = i * STEP_S
+            t_a = time.perf_counter()
+            lo = np.searchsorted(picks[:, 0], t0 - 2 * KERNEL_SIG_T)
+            hi = np.searchsorted(picks[:, 0], t0 + max_t + 2 * KERNEL_SIG_T, side='right')
+            Sl, Mk = go.input_scatter(picks[lo:hi], t0, ind_use, S, A[5].numpy(), trv, max_t, KERNEL_SIG_T, DT)
+            y, x = go.forward_fixed_source(sd, torch.from_numpy(Sl), torch.from_numpy(Mk), A[2], A[3], attr, A[4], A[1],
+                                           gridt, xq, tq, SCALE_REL, 3.0 * KERNEL_SIG_T)
+            t_b = time.perf_counter()
+            if i >= warmup:
+                times.append(t_b - t_a)
+    total = float(np.sum(times))
+    wps_sample = len(times) / total
+    value = wps_sample * Gs / G
+    sample = ('oracle (torch-CPU fp32 port of module.py:999-1020 + process_utils.py:460-629) on all %d stations x the '
+              'first %d of %d grid nodes (P=%d), %d windows after %d warm-up; %.3f s/window on the sample; value = '
+              'sample windows/s x %d/%d (cost linear in P, extrapolated)' % (S, Gs, G, S * Gs, len(times), warmup,
+                                                                             total / len(times), Gs, G))
+    return dict(value=value, unit=UNIT, cores=cores, kind='port', sample=sample), total / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    S, G, k_s, k_g = WORKLOADS[args.workload]
+    cb, s_per_step = cpu_reference(args.workload, args.steps, args.warmup)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 / cb['value'], 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': args.workload, 'stations': S, 'grid_nodes': G, 'product_nodes': S * G, 'k_sta': k_s,
+                   'k_grid': k_g, 'parallelism': 'host threads (torch intra-op), rank 0 only'},
+        'cpu_baseline': cb,
+        'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- this repo's CUDA path ---------------------------------------------------------------------------------------------
+
+class Workload(object):
+    """Device-resident state of one replica: network, graphs, travel times, a day of picks, model."""
+
+    def __init__(self, name, dev, day_s=DAY_S):
+        import torch
+        from genie_b200 import synth
+        from genie_b200.module import GCN_Detection_Network_extended
+        from genie_b200.process_utils import InputExtractor, extract_inputs_adjacencies_cartesian
+        S, G, k_s, k_g = WORKLOADS[name]
+        self.S, self.G, self.P, self.dev = S, G, S * G, dev
+        net = synth.Network(S, G, seed=0)
+        self.net = net
+        A_sta, A_src = extract_inputs_adjacencies_cartesian(net.sta, net.grid, k_s, k_g)
+        sta_d = torch.from_numpy(net.sta).to(dev)
+        grid_d = torch.from_numpy(net.grid).to(dev)
+        trv = torch.empty((G, S, 2), dtype=torch.float32, device=dev)
+        attr = torch.empty((G * S, 3), dtype=torch.float32, device=dev)
+        for lo in range(0, G, 4096):                       # synth.Network.travel_times / read_in_offsets, on the device
+            hi = min(G, lo + 4096)
+            diff = grid_d[lo:hi, None, :] - sta_d[None, :, :]
+            d = diff.norm(dim=2)
+            trv[lo:hi, :, 0] = (d / synth.VP).float()
+            trv[lo:hi, :, 1] = (d / synth.VS).float()
+            attr[lo * S:hi * S] = (diff / SCALE_REL).reshape(-1, 3).float()
+        torch.manual_seed(2)
+        m = GCN_Detection_Network_extended(None, None, scale_rel=SCALE_REL, device=dev).eval()
+        m.set_adjacencies_cartesian(A_sta, A_src, attr, S, G, device=dev)
+        self.model = m
+        self.max_t = net.max_moveout()
+        self.ex = InputExtractor(m._plan, trv, np.arange(S), S, self.max_t, KERNEL_SIG_T, DT)
+        self.picks = synth.make_picks(net, 0.0, day_s, seed=1)
+        self.ex.set_day(self.picks)
+        self.locs = sta_d.float()
+        self.grid = grid_d.float().contiguous()
+        self.xq = torch.from_numpy(_query_points(net, N_QUERY)).float().to(dev)
+        self.tq = torch.arange(-3.0, 3.01, 0.75, device=dev).reshape(-1, 1)
+        self.n_windows = int((day_s - self.max_t) // STEP_S)
+        # host-side staging for the end-to-end leg
+        self.picks_host = torch.from_numpy(self.ex._day[1].cpu().numpy()).pin_memory()
+        self.y_host = torch.empty((G, self.tq.shape[0], 1), dtype=torch.float32).pin_memory()
+        self.x_host = torch.empty((N_QUERY, self.tq.shape[0], 1), dtype=torch.float32).pin_memory()
+
+    def window_resident(self, w):
+        """Hot path with everything resident in HBM."""
+        Slice, Mask = self.ex(w * STEP_S)
+        return self.model.forward_fixed_source(Slice, Mask, None, None, None, self.locs, self.grid, self.xq, self.tq)
+
+    def window_e2e(self, w):
+        """Public API with host buffers: H2D of the window's picks, D2H of y and x (process_continuous_days.py:797-805)."""
+        import torch
+        lo, hi = self.ex.window_rows(w * STEP_S)
+        picks = self.picks_host[lo:hi].to(self.dev, non_blocking=True)
+        Slice, Mask = self.ex(w * STEP_S, picks)
+        y, x = self.model.forward_fixed_source(Slice, Mask, None, None, None, self.locs, self.grid, self.xq, self.tq)
+        self.y_host.copy_(y, non_blocking=True)
+        self.x_host.copy_(x, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return (hi - lo) * 5 * 8, (y.numel() + x.numel()) * 4
+
+
+def run_genie(args):
+    import torch
+    import torch.distributed as dist
+    from genie_b200 import capi
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py: no CUDA device — genie_b200 has no CPU path (use --impl reference for the host baseline)')
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    S, G, k_s, k_g = WORKLOADS[args.workload]
+    t_setup = time.time()
+    wl = Workload(args.workload, dev, day_s=args.day_seconds)
+    torch.cuda.synchronize()
+    t_setup = time.time() - t_setup
+    K, W = args.steps, args.warmup
+    # rank r streams windows r, r + world, ...: windows are independent, no data-path collective
+    windows = [(rank + i * world) % wl.n_windows for i in range(2 * (K + W))]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- leg 1: resident inputs (value) -------------------------------------------------------------------------------
+    for w in windows[:W]:
+        wl.window_resident(w)
+    barrier()
+    capi.timing_enable(True)
+    capi.timing_collect(reset=True)
+    n0 = capi.launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    beg.record()
+    for w in windows[W:W + K]:
+        wl.window_resident(w)
+    end.record()
+    barrier()
+    ms = beg.elapsed_time(end)
+    launches = capi.launch_count() - n0
+    kt = capi.timing_collect(reset=True)
+    capi.timing_enable(False)
+    # ---- leg 2: end to end with host buffers (e2e) ----------------------------------------------------------------------
+    for w in windows[W + K:W + K + W]:
+        wl.window_e2e(w)
+    barrier()
+    beg2, end2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    beg2.record()
+    h2d = d2h = 0
+    for w in windows[W + K + W:W + K + W + K]:
+        a, b = wl.window_e2e(w)
+        h2d += a
+        d2h += b
+    end2.record()
+    barrier()
+    ms2 = beg2.elapsed_time(end2)
+    clocks = sampler.stop() if sampler is not None else None
+    if world > 1:
+        t = torch.tensor([ms, ms2], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms2 = float(t[0]), float(t[1])
+        cnt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        launches = int(cnt[0])
+    if rank == 0:
+        peak, peak_src = _peaks()
+        timed = {k: v for k, v in kt.items() if v[1] > 0}
+        dom = max(timed, key=lambda k: timed[k][0])
+        dom_ms = timed[dom][0] / timed[dom][1]
+        dom_bytes = BYTES_PER_NODE_KERNEL.get(dom, BYTES_PER_NODE_WINDOW) * wl.P
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+        kernel_total = sum(v[0] for v in timed.values())
+        line = {
+            'metric': METRIC, 'value': world * K / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': args.workload, 'stations': S, 'grid_nodes': G, 'product_nodes': S * G, 'k_sta': k_s,
+                       'k_grid': k_g, 'kernel_sig_t': KERNEL_SIG_T, 'dt': DT, 'window_step_s': STEP_S,
+                       'n_query': N_QUERY, 'n_t_query': 9, 'picks_resident': int(wl.picks.shape[0]),
+                       'parallelism': 'windows round-robin over %d replica(s), no data-path collective' % world,
+                       'l2_policy': 'inputs larger than L2: every window streams %.1f GB of node features through '
+                                    'HBM (L2 = 126 MB), no explicit flush' % (BYTES_PER_NODE_WINDOW * wl.P / 1e9),
+                       'setup_s': round(t_setup, 1)},
+            'e2e': {'value': world * K / (ms2 * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d // K,
+                    'd2h_bytes_per_step': d2h // K, 'ms_per_step': ms2 / K},
+            'gpu_launches': launches,
+            'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                         'frac': achieved / peak, 'traffic': _traffic(dom), 'peak_source': peak_src,
+                         'algorithmic_bytes_per_launch': dom_bytes, 'ms_per_launch': dom_ms,
+                         'kernel_share_of_step': timed[dom][0] / ms,
+                         'window': {'algorithmic_bytes': BYTES_PER_NODE_WINDOW * wl.P,
+                                    'achieved': BYTES_PER_NODE_WINDOW * wl.P / (ms / K * 1e-3) / 1e9,
+                                    'frac': BYTES_PER_NODE_WINDOW * wl.P / (ms / K * 1e-3) / 1e9 / peak},
+                         'kernels_ms_per_step': {k: round(v[0] / K, 4) for k, v in sorted(timed.items())},
+                         'library_kernels_share_of_step': kernel_total / ms},
+            'clocks': clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_reference(args.workload, 3, 1)[0]
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='genie', choices=['genie', 'reference'])
+    ap.add_argument('--workload', default='c4_1000x50000_dense', choices=sorted(WORKLOADS))
+    ap.add_argument('--day-seconds', type=float, default=DAY_S)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'genie' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_genie(args)
+
+
+if __name__ == '__main__':
+    main()

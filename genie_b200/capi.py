@@ -64,6 +64,11 @@ SIGNATURES = {
     'genie_last_error': (ctypes.c_char_p, []),
     'genie_abi_version': (ctypes.c_int, []),
     'genie_launch_count': (ctypes.c_int64, []),
+    'genie_timing_enable': (ctypes.c_int, [ctypes.c_int]),
+    'genie_timing_kernel_count': (ctypes.c_int, []),
+    'genie_timing_kernel_name': (ctypes.c_char_p, [ctypes.c_int]),
+    'genie_timing_collect': (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
+                                            ctypes.c_int]),
     'genie_plan_create': (ctypes.c_int, [ctypes.POINTER(GraphDesc), ctypes.POINTER(_P)]),
     'genie_plan_destroy': (None, [_P]),
     'genie_plan_workspace_bytes': (ctypes.c_size_t, [_P]),
@@ -131,3 +136,17 @@ def stream_ptr(device=None):
 
 def launch_count():
     return int(load().genie_launch_count())
+
+
+def timing_enable(on=True):
+    check(load().genie_timing_enable(1 if on else 0))
+
+
+def timing_collect(reset=True):
+    """{kernel name: (total device ms, launches)} of the launches recorded since the last reset."""
+    lib = load()
+    n = lib.genie_timing_kernel_count()
+    ms = (ctypes.c_double * n)()
+    cnt = (ctypes.c_int64 * n)()
+    check(lib.genie_timing_collect(ms, cnt, 1 if reset else 0))
+    return {lib.genie_timing_kernel_name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(n)}

@@ -1,6 +1,8 @@
 // extern "C" surface of libgenie_b200.so (declared in include/genie_b200.h).
 #include <atomic>
+#include <mutex>
 #include <new>
+#include <vector>
 
 #include "internal.h"
 
@@ -15,6 +17,54 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 void set_error(const std::string& msg) { g_last_error = msg; }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- optional per-kernel device timing ---------------------------------------------------------------------------------
+namespace {
+struct TimingSlot {
+    int kid;
+    cudaEvent_t beg, end;
+};
+std::atomic<int> g_timing_on{0};
+std::mutex g_timing_mu;
+std::vector<TimingSlot*> g_timing_pending, g_timing_free;
+double g_timing_ms[KID_COUNT];
+int64_t g_timing_n[KID_COUNT];
+const char* const kKernelNames[KID_COUNT] = {"pack_weights_kernel", "input_series_kernel", "input_gather_kernel",
+                                             "da_init_kernel",      "da_layer1_kernel",    "da_layer2_readin_kernel",
+                                             "readin_finalize_kernel", "sa_pre_kernel",    "sa_main_kernel"};
+}  // namespace
+
+TimedLaunch::TimedLaunch(int kid_, cudaStream_t st_) : kid(kid_), st(st_), slot(nullptr) {
+    if (!g_timing_on.load(std::memory_order_relaxed)) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+    TimingSlot* s = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_timing_mu);
+        if (!g_timing_free.empty()) {
+            s = g_timing_free.back();
+            g_timing_free.pop_back();
+        }
+    }
+    if (!s) {
+        s = new TimingSlot();
+        if (cudaEventCreate(&s->beg) != cudaSuccess || cudaEventCreate(&s->end) != cudaSuccess) {
+            delete s;
+            return;
+        }
+    }
+    s->kid = kid;
+    cudaEventRecord(s->beg, st);
+    slot = s;
+}
+
+TimedLaunch::~TimedLaunch() {
+    if (!slot) return;
+    TimingSlot* s = static_cast<TimingSlot*>(slot);
+    cudaEventRecord(s->end, st);
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    g_timing_pending.push_back(s);
+}
 
 Workspace carve_workspace(const genie_plan* p, void* base) {
     Workspace w;
@@ -44,6 +94,40 @@ extern "C" {
 const char* genie_last_error(void) { return g_last_error.c_str(); }
 int genie_abi_version(void) { return GENIE_B200_ABI_VERSION; }
 int64_t genie_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int genie_timing_enable(int on) {
+    g_timing_on.store(on ? 1 : 0, std::memory_order_relaxed);
+    return GENIE_OK;
+}
+int genie_timing_kernel_count(void) { return (int)KID_COUNT; }
+const char* genie_timing_kernel_name(int k) { return (k >= 0 && k < KID_COUNT) ? kKernelNames[k] : ""; }
+int genie_timing_collect(double* total_ms, int64_t* launches, int reset) {
+    std::vector<TimingSlot*> pend;
+    {
+        std::lock_guard<std::mutex> lk(g_timing_mu);
+        pend.swap(g_timing_pending);
+    }
+    for (TimingSlot* s : pend) {
+        float ms = 0.f;
+        GENIE_CUDA_CHECK(cudaEventSynchronize(s->end));
+        GENIE_CUDA_CHECK(cudaEventElapsedTime(&ms, s->beg, s->end));
+        g_timing_ms[s->kid] += (double)ms;
+        g_timing_n[s->kid] += 1;
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_timing_mu);
+        for (TimingSlot* s : pend) g_timing_free.push_back(s);
+    }
+    for (int k = 0; k < KID_COUNT; ++k) {
+        if (total_ms) total_ms[k] = g_timing_ms[k];
+        if (launches) launches[k] = g_timing_n[k];
+        if (reset) {
+            g_timing_ms[k] = 0.0;
+            g_timing_n[k] = 0;
+        }
+    }
+    return GENIE_OK;
+}
 
 int genie_plan_create(const genie_graph_desc_t* d, genie_plan_t** out) {
     if (!d || !out) {

@@ -379,6 +379,7 @@ int launch_da_init(const genie_plan* p, const float* packed, const float* slice,
     const int64_t P = p->g.n_prod;
     if (P == 0) return GENIE_OK;
     const int64_t blocks = (P + K1_THREADS - 1) / K1_THREADS;
+    TimedLaunch tl(KID_DA_INIT, st);
     da_init_kernel<<<(unsigned)blocks, K1_THREADS, 0, st>>>(packed, slice, mask, tr0, P);
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;
@@ -396,6 +397,7 @@ int launch_da_layer1(const genie_plan* p, const float* packed, const float* tr0,
     }
     const int64_t n_tiles = (P + TM - 1) / TM;
     const int64_t grid = n_tiles < (int64_t)p->sm_count * 2 ? n_tiles : (int64_t)p->sm_count * 2;
+    TimedLaunch tl(KID_DA_LAYER1, st);
     da_layer1_kernel<<<(unsigned)grid, K2_THREADS, K2_SMEM, st>>>(make_view(p), packed, tr0, mask, zc, va, vb, n_tiles);
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;
@@ -410,6 +412,7 @@ int launch_da_layer2_readin(const genie_plan* p, const float* packed, int mode, 
     const int64_t cap = (int64_t)p->sm_count * 4;
     const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
     const GraphView gv = make_view(p);
+    TimedLaunch tl(KID_DA_LAYER2_READIN, st);
 #define GENIE_L2_CASE(M)                                                                                              \
     case M:                                                                                                            \
         da_layer2_readin_kernel<M><<<grid, K3_THREADS, 0, st>>>(gv, packed, zc, va, vb, latent_in, latent_out,      \
@@ -433,6 +436,7 @@ int launch_readin_finalize(const genie_plan* p, const float* packed, const float
                            cudaStream_t st) {
     const int G = p->g.n_grid;
     if (G == 0) return GENIE_OK;
+    TimedLaunch tl(KID_READIN_FINALIZE, st);
     readin_finalize_kernel<<<(G + 127) / 128, 128, 0, st>>>(packed, xg, out, ld_out, G);
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;

@@ -99,11 +99,13 @@ int launch_input_scatter(const genie_plan* p, const genie_input_params_t* prm, c
     if (n_picks > 0) {
         const int64_t total = n_picks * (2 * (int64_t)prm->n_extra + 1);
         const int64_t blocks = (total + 255) / 256;
+        TimedLaunch tl(KID_INPUT_SERIES, st);
         input_series_kernel<<<(unsigned)blocks, 256, 0, st>>>(*prm, picks, n_picks, sta_perm, series);
         GENIE_LAUNCH_CHECK();
     }
     if (P > 0) {
         const int64_t blocks = (P + 255) / 256;
+        TimedLaunch tl(KID_INPUT_GATHER, st);
         input_gather_kernel<<<(unsigned)blocks, 256, 0, st>>>(*prm, p->g.mode, p->g.n_sta, P, ind_use, trv_times,
                                                                node_sta, node_grid, series, slice_out, mask_out,
                                                                time_bin_out);

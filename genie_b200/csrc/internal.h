@@ -61,6 +61,28 @@ Workspace carve_workspace(const genie_plan* p, void* base);
 void set_error(const std::string& msg);
 void count_launch(int n = 1);
 
+// Kernel ids of the optional per-kernel device timing (genie_timing_* in the C-ABI).
+enum KernelId {
+    KID_PACK = 0,
+    KID_INPUT_SERIES,
+    KID_INPUT_GATHER,
+    KID_DA_INIT,
+    KID_DA_LAYER1,
+    KID_DA_LAYER2_READIN,
+    KID_READIN_FINALIZE,
+    KID_SA_PRE,
+    KID_SA_MAIN,
+    KID_COUNT
+};
+// Brackets one kernel launch with cudaEvents on its stream when timing is enabled (no-op otherwise).
+struct TimedLaunch {
+    TimedLaunch(int kid, cudaStream_t st);
+    ~TimedLaunch();
+    int kid;
+    cudaStream_t st;
+    void* slot;
+};
+
 #define GENIE_CUDA_CHECK(expr)                                                                         \
     do {                                                                                                \
         cudaError_t _e = (expr);                                                                        \

@@ -80,6 +80,7 @@ __global__ void pack_weights_kernel(const genie_frontend_weights_t w, float* __r
 }  // namespace
 
 int launch_pack_weights(const genie_frontend_weights_t* w, float* packed, cudaStream_t st) {
+    TimedLaunch tl(KID_PACK, st);
     pack_weights_kernel<<<1, 256, 0, st>>>(*w, packed);
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;

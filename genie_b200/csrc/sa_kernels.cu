@@ -128,8 +128,12 @@ int launch_spatial_aggregation(const genie_plan* p, const float* packed, int lay
     int nb = (G + SA_WARPS - 1) / SA_WARPS;
     const int cap = p->sm_count * 2 < 1024 ? p->sm_count * 2 : 1024;
     if (nb > cap) nb = cap;
-    sa_pre_kernel<<<nb, SA_THREADS, 0, st>>>(w, x, ld_x, C, p->g.grid_outdeg, G, px, partial);
+    {
+        TimedLaunch tl(KID_SA_PRE, st);
+        sa_pre_kernel<<<nb, SA_THREADS, 0, st>>>(w, x, ld_x, C, p->g.grid_outdeg, G, px, partial);
+    }
     GENIE_LAUNCH_CHECK();
+    TimedLaunch tl(KID_SA_MAIN, st);
     sa_main_kernel<<<nb, SA_THREADS, 0, st>>>(w, x, ld_x, C, px, pos, scale_rel, p->g.grid_rowptr, p->g.grid_col, G,
                                                partial, nb, out, ld_out);
     GENIE_LAUNCH_CHECK();

@@ -174,6 +174,16 @@ GENIE_API int genie_abi_version(void);
 /* Number of kernels this library has launched in the calling process (bench.py's `gpu_launches`). */
 GENIE_API int64_t genie_launch_count(void);
 
+/* Optional per-kernel device timing (bench.py's roofline leg; the reference has no counterpart: it only prints
+ * time.time() deltas behind `verbose`, process_utils.py:469-470, 639-640).  While enabled, every kernel launch is
+ * bracketed by cudaEvents recorded on the launching stream (skipped while that stream is being captured into a CUDA
+ * graph).  genie_timing_collect waits for the recorded events, adds their durations to per-kernel totals and copies the
+ * totals into total_ms[genie_timing_kernel_count()] / launches[...] (either may be NULL); reset != 0 clears them. */
+GENIE_API int genie_timing_enable(int on);
+GENIE_API int genie_timing_kernel_count(void);
+GENIE_API const char* genie_timing_kernel_name(int k);
+GENIE_API int genie_timing_collect(double* total_ms, int64_t* launches, int reset);
+
 #ifdef __cplusplus
 }
 #endif
