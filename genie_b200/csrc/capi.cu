@@ -30,7 +30,7 @@ std::vector<TimingSlot*> g_timing_pending, g_timing_free;
 double g_timing_ms[KID_COUNT];
 int64_t g_timing_n[KID_COUNT];
 const char* const kKernelNames[KID_COUNT] = {"pack_weights_kernel", "input_series_kernel", "input_gather_kernel",
-                                             "da_init_kernel",      "da_layer1_kernel",    "da_layer2_readin_kernel",
+                                             "da_init_kernel",      "da_layer1_kernel",    "da_layer1_tc_kernel", "da_layer2_readin_kernel",
                                              "readin_finalize_kernel", "sa_pre_kernel",    "sa_main_kernel"};
 }  // namespace
 
@@ -87,6 +87,17 @@ Workspace carve_workspace(const genie_plan* p, void* base) {
     w.partial = take(1024 * 8);
     w.bytes = off;
     return w;
+}
+
+// Layer 0 + layer 1 of DataAggregation: tensor-core kernel when the plan allows it (the generic kernel is launched as
+// well and exits at once unless the packed weights make the tensor-core kernel ineligible; see layout.h TCS_OK).
+static int launch_da_layers01(const genie_plan* plan, const float* packed, const float* slice, const float* mask,
+                              const Workspace& w, cudaStream_t st) {
+    const bool tc = da_tc_supported(plan);
+    int rc;
+    if ((rc = launch_da_init(plan, packed, slice, mask, w.tr0, tc, st))) return rc;
+    if (tc && (rc = launch_da_layer1_tc(plan, packed, w.tr0, mask, w.zc, w.va, w.vb, st))) return rc;
+    return launch_da_layer1(plan, packed, w.tr0, mask, w.zc, w.va, w.vb, tc, st);
 }
 
 extern "C" {
@@ -239,8 +250,7 @@ int genie_data_aggregation_fwd(const genie_plan_t* plan, const float* packed_dev
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Workspace w = carve_workspace(plan, workspace_dev);
     int rc;
-    if ((rc = launch_da_init(plan, packed_dev, slice_dev, mask_dev, w.tr0, st))) return rc;
-    if ((rc = launch_da_layer1(plan, packed_dev, w.tr0, mask_dev, w.zc, w.va, w.vb, st))) return rc;
+    if ((rc = launch_da_layers01(plan, packed_dev, slice_dev, mask_dev, w, st))) return rc;
     return launch_da_layer2_readin(plan, packed_dev, L2_GATHER | L2_STORE_LATENT, w.zc, w.va, w.vb, nullptr,
                                    x_latent_out_dev, nullptr, mask_dev, nullptr, st);
 }
@@ -287,8 +297,7 @@ int genie_frontend_fwd(const genie_plan_t* plan, const float* packed_dev, const 
     Workspace w = carve_workspace(plan, workspace_dev);
     int rc;
     GENIE_CUDA_CHECK(cudaMemsetAsync(w.xg, 0, (size_t)plan->g.n_grid * 32 * sizeof(float), st));
-    if ((rc = launch_da_init(plan, packed_dev, slice_dev, mask_dev, w.tr0, st))) return rc;
-    if ((rc = launch_da_layer1(plan, packed_dev, w.tr0, mask_dev, w.zc, w.va, w.vb, st))) return rc;
+    if ((rc = launch_da_layers01(plan, packed_dev, slice_dev, mask_dev, w, st))) return rc;
     const int mode = L2_GATHER | L2_READIN | (x_latent_out_dev ? L2_STORE_LATENT : 0);
     if ((rc = launch_da_layer2_readin(plan, packed_dev, mode, w.zc, w.va, w.vb, nullptr, x_latent_out_dev,
                                       edge_attr_dev, mask_dev, w.xg, st)))

@@ -31,11 +31,14 @@ constexpr int K1_THREADS = 256;
 __global__ void __launch_bounds__(K1_THREADS) da_init_kernel(const float* __restrict__ packed,
                                                              const float* __restrict__ slice,
                                                              const float* __restrict__ mask, float* __restrict__ tr0,
-                                                             int64_t P) {
+                                                             int64_t P, int tc_plan) {
     __shared__ __align__(16) float sW[8 * LD + LD];
     __shared__ __align__(16) float sOut[K1_THREADS * LD_TR0];
     for (int i = threadIdx.x; i < 8 * LD + LD; i += K1_THREADS) sW[i] = packed[DA_W0 + i];
     const float a0 = packed[DA_SLOPES + SL_A0];
+    // tensor-core path (da_tc_kernels.cu): store p = PReLU12(tr0) instead of tr0
+    const bool post = tc_plan && packed[TC_BASE + TC_SCAL + TCS_OK] != 0.f;
+    const float a12 = post ? packed[DA_SLOPES + SL_A12] : 1.f;
     __syncthreads();
 
     const int64_t i0 = (int64_t)blockIdx.x * K1_THREADS;
@@ -62,10 +65,10 @@ __global__ void __launch_bounds__(K1_THREADS) da_init_kernel(const float* __rest
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         float4 v;
-        v.x = prelu(acc[(4 * c + 0) < 30 ? (4 * c + 0) : 0], a0);
-        v.y = prelu(acc[(4 * c + 1) < 30 ? (4 * c + 1) : 0], a0);
-        v.z = (4 * c + 2) < 30 ? prelu(acc[(4 * c + 2) < 30 ? (4 * c + 2) : 0], a0) : 0.f;
-        v.w = (4 * c + 3) < 30 ? prelu(acc[(4 * c + 3) < 30 ? (4 * c + 3) : 0], a0) : 0.f;
+        v.x = prelu(prelu(acc[(4 * c + 0) < 30 ? (4 * c + 0) : 0], a0), a12);
+        v.y = prelu(prelu(acc[(4 * c + 1) < 30 ? (4 * c + 1) : 0], a0), a12);
+        v.z = (4 * c + 2) < 30 ? prelu(prelu(acc[(4 * c + 2) < 30 ? (4 * c + 2) : 0], a0), a12) : 0.f;
+        v.w = (4 * c + 3) < 30 ? prelu(prelu(acc[(4 * c + 3) < 30 ? (4 * c + 3) : 0], a0), a12) : 0.f;
         srow[c ^ (n & 7)] = v;
     }
     __syncthreads();
@@ -145,8 +148,9 @@ constexpr size_t K2_SMEM = (size_t)(K2_W_FLOATS + K2_F_ROWS * LDF) * sizeof(floa
 __global__ void __launch_bounds__(K2_THREADS, 2)
     da_layer1_kernel(const GraphView gv, const float* __restrict__ packed, const float* __restrict__ tr0,
                      const float* __restrict__ mask, float* __restrict__ zc, float* __restrict__ va,
-                     float* __restrict__ vb, int64_t n_tiles) {
+                     float* __restrict__ vb, int64_t n_tiles, int tc_plan) {
     extern __shared__ __align__(16) float smem[];
+    if (tc_plan && packed[TC_BASE + TC_SCAL + TCS_OK] != 0.f) return;   // da_layer1_tc_kernel did the work
     float* sW = smem;                  // packed[DA_W11 .. DA_END)
     float* F = smem + K2_W_FLOATS;     // [94][LDF]
     {
@@ -375,18 +379,18 @@ __global__ void __launch_bounds__(128) readin_finalize_kernel(const float* __res
 // launchers
 // --------------------------------------------------------------------------------------------------------------------
 int launch_da_init(const genie_plan* p, const float* packed, const float* slice, const float* mask, float* tr0,
-                   cudaStream_t st) {
+                   bool tc_plan, cudaStream_t st) {
     const int64_t P = p->g.n_prod;
     if (P == 0) return GENIE_OK;
     const int64_t blocks = (P + K1_THREADS - 1) / K1_THREADS;
     TimedLaunch tl(KID_DA_INIT, st);
-    da_init_kernel<<<(unsigned)blocks, K1_THREADS, 0, st>>>(packed, slice, mask, tr0, P);
+    da_init_kernel<<<(unsigned)blocks, K1_THREADS, 0, st>>>(packed, slice, mask, tr0, P, tc_plan ? 1 : 0);
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;
 }
 
 int launch_da_layer1(const genie_plan* p, const float* packed, const float* tr0, const float* mask, float* zc, float* va,
-                     float* vb, cudaStream_t st) {
+                     float* vb, bool tc_plan, cudaStream_t st) {
     const int64_t P = p->g.n_prod;
     if (P == 0) return GENIE_OK;
     static bool attr_set = false;
@@ -398,7 +402,8 @@ int launch_da_layer1(const genie_plan* p, const float* packed, const float* tr0,
     const int64_t n_tiles = (P + TM - 1) / TM;
     const int64_t grid = n_tiles < (int64_t)p->sm_count * 2 ? n_tiles : (int64_t)p->sm_count * 2;
     TimedLaunch tl(KID_DA_LAYER1, st);
-    da_layer1_kernel<<<(unsigned)grid, K2_THREADS, K2_SMEM, st>>>(make_view(p), packed, tr0, mask, zc, va, vb, n_tiles);
+    da_layer1_kernel<<<(unsigned)grid, K2_THREADS, K2_SMEM, st>>>(make_view(p), packed, tr0, mask, zc, va, vb, n_tiles,
+                                                              tc_plan ? 1 : 0);
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;
 }

@@ -68,6 +68,7 @@ enum KernelId {
     KID_INPUT_GATHER,
     KID_DA_INIT,
     KID_DA_LAYER1,
+    KID_DA_LAYER1_TC,
     KID_DA_LAYER2_READIN,
     KID_READIN_FINALIZE,
     KID_SA_PRE,
@@ -105,10 +106,15 @@ struct TimedLaunch {
 // ---- launchers (each returns a GENIE_* status) -----------------------------------------------------------------------
 int launch_pack_weights(const genie_frontend_weights_t* w, float* packed, cudaStream_t st);
 
+// tc_plan: the plan is eligible for the tensor-core layer-1 kernel (da_tc_supported).  Whether that kernel or the generic
+// one does the work is then decided ON THE DEVICE from the packed weights (layout.h TCS_OK): both are launched, one exits.
+bool da_tc_supported(const genie_plan* p);
 int launch_da_init(const genie_plan* p, const float* packed, const float* slice, const float* mask, float* tr0,
-                   cudaStream_t st);
+                   bool tc_plan, cudaStream_t st);
 int launch_da_layer1(const genie_plan* p, const float* packed, const float* tr0, const float* mask, float* zc, float* va,
-                     float* vb, cudaStream_t st);
+                     float* vb, bool tc_plan, cudaStream_t st);
+int launch_da_layer1_tc(const genie_plan* p, const float* packed, const float* pfeat, const float* mask, float* zc,
+                        float* va, float* vb, cudaStream_t st);
 // mode bits for the layer-2 / read-in kernel
 enum { L2_GATHER = 1, L2_STORE_LATENT = 2, L2_READIN = 4 };
 int launch_da_layer2_readin(const genie_plan* p, const float* packed, int mode, const float* zc, const float* va,

@@ -50,9 +50,36 @@ constexpr int SA_SLOPES = SA_BGL + 8;           // [4]: activate1, activate2, ac
 constexpr int SA_SIZE = SA_SLOPES + 4;
 constexpr int SA_BASE = RI_END;
 
-constexpr int PACKED_FLOATS = SA_BASE + 3 * SA_SIZE;
+constexpr int GENERIC_END = SA_BASE + 3 * SA_SIZE;
 
-static_assert(DA_W11 % 4 == 0 && DA_END % 4 == 0 && RI_END % 4 == 0 && SA_SIZE % 4 == 0, "16-byte alignment");
+// ---- tensor-core blob of DataAggregation layer 1 (da_tc_kernels.cu) ----------------------------------------------------
+// Every B operand of tcgen05.mma is stored [N rows][K] K-major in the canonical no-swizzle UMMA layout
+//   float index = ((k / 4) * N + n) * 4 + (k % 4)            (8-row x 16-byte core matrices, LBO = 16 N bytes, SBO = 128)
+// twice: the tf32 "hi" part (low 13 mantissa bits cleared) and the fp32 remainder "lo" (3xTF32 split).
+//   B1A  N=64 K=40  rows 0-29 l1_t1_2, rows 32-61 l1_t2_2; k 0-29 tr0, k 30-33 mask, k 34 bias (operand column = 1)
+//   B1B  N=32 K=32  l1_t1_2[:, 30:60]  (mean over station neighbours)
+//   B1C  N=32 K=32  l1_t2_2[:, 30:60]  (mean over source neighbours)
+//   B2   N=96 K=64  rows 0-29 l2_t1_1, 32-61 l2_t2_1, 64-78 l2_t1_2[:, tr|mask], 80-94 l2_t2_2[:, tr|mask];
+//                   k 0-29 tr[0:30], k 30,31 mask0,1, k 32-61 tr[30:60], k 62,63 mask2,3
+//   B3A  N=16 K=32  l2_t1_2[:, 60:90];  B3B  N=16 K=32  l2_t2_2[:, 60:90]
+constexpr int TC_BASE = (GENERIC_END + 63) / 64 * 64;   // 256-byte aligned
+constexpr int TC_B1A_HI = 0, TC_B1A_LO = TC_B1A_HI + 64 * 40;
+constexpr int TC_B1B_HI = TC_B1A_LO + 64 * 40, TC_B1B_LO = TC_B1B_HI + 32 * 32;
+constexpr int TC_B1C_HI = TC_B1B_LO + 32 * 32, TC_B1C_LO = TC_B1C_HI + 32 * 32;
+constexpr int TC_B2_HI = TC_B1C_LO + 32 * 32, TC_B2_LO = TC_B2_HI + 96 * 64;
+constexpr int TC_B3A_HI = TC_B2_LO + 96 * 64, TC_B3A_LO = TC_B3A_HI + 16 * 32;
+constexpr int TC_B3B_HI = TC_B3A_LO + 16 * 32, TC_B3B_LO = TC_B3B_HI + 16 * 32;
+constexpr int TC_BIAS2 = TC_B3B_LO + 16 * 32;           // [96] bias of the B2 columns
+constexpr int TC_SCAL = TC_BIAS2 + 96;                  // [8], see enum below
+constexpr int TC_FLOATS = TC_SCAL + 8;
+// TC_OK = 1 when activate12's slope is > 1e-3: layer 0 then stores p = PReLU12(tr0) (sums over source neighbours need
+// no per-edge activation; tr0 and PReLU11(tr0) are recovered from p exactly up to rounding), else the generic kernels run.
+enum { TCS_OK = 0, TCS_A1 = 1, TCS_A21 = 2, TCS_A22 = 3, TCS_R11 = 4, TCS_INV12 = 5, TCS_A12 = 6 };
+
+constexpr int PACKED_FLOATS = TC_BASE + TC_FLOATS;
+
+static_assert(DA_W11 % 4 == 0 && DA_END % 4 == 0 && RI_END % 4 == 0 && SA_SIZE % 4 == 0 && TC_FLOATS % 4 == 0,
+              "16-byte alignment");
 
 // ---- node-feature row strides in the workspace (floats) -------------------------------------------------------------
 constexpr int LD_TR0 = 32;   // tr0 rows padded to 128 B: one L2 line per gathered neighbour row

@@ -18,6 +18,82 @@ __device__ void pack_v(float* dst, const float* b, int n) {
     for (int idx = threadIdx.x; idx < n; idx += blockDim.x) dst[idx] = b[idx];
 }
 
+// ---- tensor-core blob (layout.h: TC_*) ---------------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_hi_part(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+template <class F>
+__device__ void pack_umma(float* hi, float* lo, int N, int K, F value) {
+    for (int idx = threadIdx.x; idx < N * K; idx += blockDim.x) {
+        const int n = idx / K, k = idx - n * K;
+        const float v = value(n, k);
+        const float h = tf32_hi_part(v);
+        const int at = ((k >> 2) * N + n) * 4 + (k & 3);
+        hi[at] = h;
+        lo[at] = v - h;
+    }
+}
+
+__device__ void pack_tc(const genie_frontend_weights_t& w, float* __restrict__ t) {
+    const float *W11 = w.da_l1_t1_2.weight, *W12 = w.da_l1_t2_2.weight;          // [30][64]
+    const float *b11 = w.da_l1_t1_2.bias, *b12 = w.da_l1_t2_2.bias;
+    const float *W21a = w.da_l2_t1_1.weight, *W22a = w.da_l2_t2_1.weight;        // [30][60]
+    const float *W21b = w.da_l2_t1_2.weight, *W22b = w.da_l2_t2_2.weight;        // [15][94]
+    pack_umma(t + TC_B1A_HI, t + TC_B1A_LO, 64, 40, [=](int n, int k) -> float {
+        const int o = n & 31;
+        const float* W = n < 32 ? W11 : W12;
+        const float* b = n < 32 ? b11 : b12;
+        if (o >= 30) return 0.f;
+        if (k < 30) return W[o * 64 + k];
+        if (k < 34) return W[o * 64 + 60 + (k - 30)];
+        if (k == 34) return b[o];
+        return 0.f;
+    });
+    pack_umma(t + TC_B1B_HI, t + TC_B1B_LO, 32, 32,
+              [=](int n, int k) -> float { return (n < 30 && k < 30) ? W11[n * 64 + 30 + k] : 0.f; });
+    pack_umma(t + TC_B1C_HI, t + TC_B1C_LO, 32, 32,
+              [=](int n, int k) -> float { return (n < 30 && k < 30) ? W12[n * 64 + 30 + k] : 0.f; });
+    pack_umma(t + TC_B2_HI, t + TC_B2_LO, 96, 64, [=](int n, int k) -> float {
+        // operand column k -> input feature: tr[0:30] at 0-29, mask0,1 at 30,31, tr[30:60] at 32-61, mask2,3 at 62,63
+        const int kt = k < 30 ? k : (k >= 32 && k < 62) ? k - 2 : -1;
+        const int km = k == 30 ? 0 : k == 31 ? 1 : k == 62 ? 2 : k == 63 ? 3 : -1;
+        if (n < 64) {
+            const int o = n & 31;
+            if (o >= 30 || kt < 0) return 0.f;
+            return (n < 32 ? W21a : W22a)[o * 60 + kt];
+        }
+        const int o = (n - 64) & 15;
+        if (o >= 15) return 0.f;
+        const float* W = n < 80 ? W21b : W22b;
+        if (kt >= 0) return W[o * 94 + kt];
+        if (km >= 0) return W[o * 94 + 90 + km];
+        return 0.f;
+    });
+    pack_umma(t + TC_B3A_HI, t + TC_B3A_LO, 16, 32,
+              [=](int n, int k) -> float { return (n < 15 && k < 30) ? W21b[n * 94 + 60 + k] : 0.f; });
+    pack_umma(t + TC_B3B_HI, t + TC_B3B_LO, 16, 32,
+              [=](int n, int k) -> float { return (n < 15 && k < 30) ? W22b[n * 94 + 60 + k] : 0.f; });
+    for (int n = threadIdx.x; n < 96; n += blockDim.x) {
+        float b = 0.f;
+        if (n < 30) b = w.da_l2_t1_1.bias[n];
+        else if (n >= 32 && n < 62) b = w.da_l2_t2_1.bias[n - 32];
+        else if (n >= 64 && n < 79) b = w.da_l2_t1_2.bias[n - 64];
+        else if (n >= 80 && n < 95) b = w.da_l2_t2_2.bias[n - 80];
+        t[TC_BIAS2 + n] = b;
+    }
+    if (threadIdx.x == 0) {
+        const float a11 = w.da_activate11[0], a12 = w.da_activate12[0];
+        const bool ok = a12 > 1e-3f && a12 < 1e3f;      // false for NaN too
+        t[TC_SCAL + TCS_OK] = ok ? 1.f : 0.f;
+        t[TC_SCAL + TCS_A1] = w.da_activate1[0];
+        t[TC_SCAL + TCS_A21] = w.da_activate21[0];
+        t[TC_SCAL + TCS_A22] = w.da_activate22[0];
+        t[TC_SCAL + TCS_R11] = ok ? a11 / a12 : 0.f;
+        t[TC_SCAL + TCS_INV12] = ok ? 1.f / a12 : 0.f;
+        t[TC_SCAL + TCS_A12] = a12;
+        t[TC_SCAL + 7] = 0.f;
+    }
+}
+
 __global__ void pack_weights_kernel(const genie_frontend_weights_t w, float* __restrict__ p) {
     for (int i = threadIdx.x; i < PACKED_FLOATS; i += blockDim.x) p[i] = 0.f;
     __syncthreads();
@@ -75,6 +151,7 @@ __global__ void pack_weights_kernel(const genie_frontend_weights_t w, float* __r
             q[SA_SLOPES + 2] = w.sa[l].activate3[0];
         }
     }
+    pack_tc(w, p + TC_BASE);
 }
 
 }  // namespace
