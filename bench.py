@@ -285,11 +285,16 @@ def run_genie(args):
     sampler = ClockSampler(local) if rank == 0 else None
     beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    profile = os.environ.get('GENIE_BENCH_PROFILE') == '1'     # ncu --profile-from-start off: capture the timed loop only
+    if profile:
+        torch.cuda.profiler.start()
     beg.record()
     for w in windows[W:W + K]:
         wl.window_resident(w)
     end.record()
     barrier()
+    if profile:
+        torch.cuda.profiler.stop()
     ms = beg.elapsed_time(end)
     launches = capi.launch_count() - n0
     kt = capi.timing_collect(reset=True)

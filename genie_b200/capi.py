@@ -23,11 +23,12 @@ c_f32p = ctypes.c_void_p   # device pointers are passed as opaque addresses
 
 class GraphDesc(ctypes.Structure):
     _fields_ = [('mode', ctypes.c_int32), ('n_sta', ctypes.c_int32), ('n_grid', ctypes.c_int32),
-                ('reserved', ctypes.c_int32), ('n_prod', ctypes.c_int64),
+                ('sta_max_deg', ctypes.c_int32), ('n_prod', ctypes.c_int64),
                 ('sta_rowptr', ctypes.c_void_p), ('sta_col', ctypes.c_void_p),
                 ('src_rowptr', ctypes.c_void_p), ('src_col', ctypes.c_void_p),
                 ('grid_rowptr', ctypes.c_void_p), ('grid_col', ctypes.c_void_p),
-                ('grid_outdeg', ctypes.c_void_p), ('prod_grid', ctypes.c_void_p)]
+                ('grid_outdeg', ctypes.c_void_p), ('prod_grid', ctypes.c_void_p),
+                ('grid_order', ctypes.c_void_p)]
 
 
 class Linear(ctypes.Structure):

@@ -58,10 +58,12 @@ struct TileInfo {
     int g, s0, cnt;
 };
 
-__device__ __forceinline__ TileInfo tile_of(int64_t t, int G, int S, int R) {
+// tile t -> (station tile st = t / G, grid node = the (t % G)-th node of the locality order)
+__device__ __forceinline__ TileInfo tile_of(int64_t t, int G, int S, int R, const int32_t* __restrict__ order) {
     TileInfo ti;
     const int st = (int)(t / G);
-    ti.g = (int)(t - (int64_t)st * G);
+    const int gi = (int)(t - (int64_t)st * G);
+    ti.g = order ? __ldg(order + gi) : gi;
     ti.s0 = st * R;
     ti.cnt = min(R, S - ti.s0);
     return ti;
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         // ================================ TMA producer ================================================================
         int stage = 0, phase = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const TileInfo ti = tile_of(t, G, S, R);
+            const TileInfo ti = tile_of(t, G, S, R, gv.grid_order);
             const int64_t beg = gv.src_rowptr[ti.g];
             const int deg = (int)(gv.src_rowptr[ti.g + 1] - beg);
             for (int j0 = -1; j0 < deg; j0 += 32) {
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         int stage = 0, phase = 0;
         int64_t it = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-            const TileInfo ti = tile_of(t, G, S, R);
+            const TileInfo ti = tile_of(t, G, S, R, gv.grid_order);
             const int buf = (int)(it & 1);
             const int deg = (int)(gv.src_rowptr[ti.g + 1] - gv.src_rowptr[ti.g]);
             float4 mk = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -351,7 +353,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const float* bias2 = sW + TC_BIAS2;
         uint32_t ph_d = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const TileInfo ti = tile_of(t, G, S, R);
+            const TileInfo ti = tile_of(t, G, S, R, gv.grid_order);
             const bool valid = r < ti.cnt;
             const int64_t node = (int64_t)ti.g * S + ti.s0 + r;
             float4 mk = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -412,7 +414,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 if (valid) {
                     float4* dst = reinterpret_cast<float4*>(zc + node * LD_ZC + c);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    for (int q = 0; q < 4; ++q)      // streaming: written once, read by the next kernel - keep L2 for the gathers
+                        __stcs(dst + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
                 }
             }
             tmem_st_wait();
@@ -430,7 +433,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 if (valid) {
                     float4* dst = reinterpret_cast<float4*>((c ? vb : va) + node * LD_V);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    for (int q = 0; q < 4; ++q)
+                        __stcs(dst + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
                 }
             }
             tc_fence_before_sync();
@@ -438,41 +442,57 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
     } else if (warp >= WG_T0 && warp < WG_T0 + N_T_WARPS) {
         // ================================ station-gather warps (8 lanes x float4 per row) ================================
+        // Row slots of this quarter-warp: rr = (warp - WG_T0) * 4 + q + 16 j, j = 0..7.  The station graph is the same for
+        // every grid node, so the (<= 16) neighbour ids of the 8 slots stay in registers while the station tile is unchanged
+        // (lane `sub` keeps entries sub and sub + 8) and are broadcast with shuffles.
         const int q = lane >> 3, sub = lane & 7;
         const float r11 = sc[TCS_R11];
+        constexpr int ROWS_T = 128 / (N_T_WARPS * 4);
+        int idx_lo[ROWS_T], idx_hi[ROWS_T], degs[ROWS_T];
+        int cur_s0 = -1;
         int64_t it = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-            const TileInfo ti = tile_of(t, G, S, R);
+            const TileInfo ti = tile_of(t, G, S, R, gv.grid_order);
             const int buf = (int)(it & 1);
+            if (ti.s0 != cur_s0) {
+                cur_s0 = ti.s0;
+#pragma unroll
+                for (int j = 0; j < ROWS_T; ++j) {
+                    const int rr = (warp - WG_T0) * 4 + q + 16 * j;
+                    int64_t beg = 0;
+                    int deg = 0;
+                    if (rr < ti.cnt) {
+                        beg = gv.sta_rowptr[ti.s0 + rr];
+                        deg = (int)(gv.sta_rowptr[ti.s0 + rr + 1] - beg);
+                    }
+                    degs[j] = deg;
+                    idx_lo[j] = sub < deg ? gv.sta_col[beg + sub] : -1;
+                    idx_hi[j] = sub + 8 < deg ? gv.sta_col[beg + sub + 8] : -1;
+                }
+            }
             if (it >= 2) mbar_wait(&bars->opB_free[buf], (uint32_t)(((it >> 1) - 1) & 1));
             unsigned char* a_hi = smem + SM_A + buf * A_BUF;
             const float* pg = p + ((int64_t)ti.g * S) * 32 + 4 * sub;
-            for (int rr = (warp - WG_T0) * 4 + q; rr < 128; rr += N_T_WARPS * 4) {
-                const bool valid = rr < ti.cnt;
-                int64_t beg = 0;
-                int deg = 0;
-                if (valid) {
-                    beg = gv.sta_rowptr[ti.s0 + rr];
-                    deg = (int)(gv.sta_rowptr[ti.s0 + rr + 1] - beg);
+#pragma unroll
+            for (int j = 0; j < ROWS_T; ++j) {
+                const int rr = (warp - WG_T0) * 4 + q + 16 * j;
+                const int deg = degs[j];
+                // all 16 loads are issued unconditionally (absent edges re-read row 0 of the block and are masked in the
+                // sum): predicated loads would be serialised through one temporary register
+                float4 v[16];
+                unsigned okmask = 0;
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int jj = __shfl_sync(FULL_MASK, u < 8 ? idx_lo[j] : idx_hi[j], (lane & 24) | (u & 7));
+                    okmask |= (jj >= 0 ? 1u : 0u) << u;
+                    v[u] = __ldg(reinterpret_cast<const float4*>(pg + (int64_t)max(jj, 0) * 32));
                 }
-                int dmax = deg;
-                dmax = max(dmax, __shfl_xor_sync(FULL_MASK, dmax, 8));
-                dmax = max(dmax, __shfl_xor_sync(FULL_MASK, dmax, 16));
                 float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
-                for (int e0 = 0; e0 < dmax; e0 += 8) {
-                    const int mine = (e0 + sub < deg) ? gv.sta_col[beg + e0 + sub] : -1;
-                    float4 v[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int j = __shfl_sync(FULL_MASK, mine, (lane & 24) | u);
-                        v[u] = j >= 0 ? __ldg(reinterpret_cast<const float4*>(pg + (int64_t)j * 32))
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        s01 = __fadd2_rn(s01, make_float2(prelu_f(v[u].x, r11), prelu_f(v[u].y, r11)));
-                        s23 = __fadd2_rn(s23, make_float2(prelu_f(v[u].z, r11), prelu_f(v[u].w, r11)));
-                    }
+                for (int u = 0; u < 16; ++u) {
+                    const float w = (okmask >> u) & 1u ? 1.f : 0.f;
+                    s01 = __ffma2_rn(make_float2(prelu_f(v[u].x, r11), prelu_f(v[u].y, r11)), make_float2(w, w), s01);
+                    s23 = __ffma2_rn(make_float2(prelu_f(v[u].z, r11), prelu_f(v[u].w, r11)), make_float2(w, w), s23);
                 }
                 const float inv = deg > 0 ? 1.f / (float)deg : 0.f;
                 const float m0 = s01.x * inv, m1 = s01.y * inv, m2 = s23.x * inv, m3 = s23.y * inv;
@@ -510,7 +530,7 @@ EncodeTiledFn encode_fn() {
 bool da_tc_supported(const genie_plan* p) {
     const genie_graph_desc_t& g = p->g;
     return g.mode == GENIE_GRAPH_CARTESIAN && g.n_sta >= 32 && g.n_prod > 0 && g.n_prod < (int64_t)0x7fffff00 &&
-           encode_fn() != nullptr;
+           g.sta_max_deg >= 1 && g.sta_max_deg <= 16 && encode_fn() != nullptr;
 }
 
 int launch_da_layer1_tc(const genie_plan* p, const float* packed, const float* pfeat, const float* mask, float* zc,

@@ -26,6 +26,7 @@ struct GraphView {
     const int64_t* src_rowptr;
     const int32_t* src_col;
     const int32_t* prod_grid;
+    const int32_t* grid_order;
 };
 
 inline GraphView make_view(const genie_plan* p) {
@@ -39,6 +40,7 @@ inline GraphView make_view(const genie_plan* p) {
     v.src_rowptr = p->g.src_rowptr;
     v.src_col = p->g.src_col;
     v.prod_grid = p->g.prod_grid;
+    v.grid_order = p->g.grid_order;
     return v;
 }
 

@@ -9,6 +9,7 @@ stay implicit — at 1000 stations x 50000 grid nodes the explicit lists would b
 """
 import ctypes
 
+import numpy as np
 import torch
 
 from . import capi
@@ -25,6 +26,21 @@ def csr_by_destination(edge_index, n_nodes):
     if src.numel():
         rowptr[1:] = torch.cumsum(torch.bincount(dst, minlength=n_nodes), 0)
     return rowptr.contiguous(), col
+
+
+def locality_order(rowptr, col, n):
+    """A permutation of 0..n-1 in which graph neighbours are close together: reverse Cuthill-McKee of the symmetrised
+    graph (host side, once per plan).  The kernels only use it to ORDER their tiles so that the neighbour tiles a CTA
+    fetches were fetched recently by another CTA and still sit in L2; results do not depend on it."""
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+    rp = rowptr.cpu().numpy().astype(np.int64)
+    cl = col.cpu().numpy().astype(np.int32)
+    if n == 0 or len(cl) == 0:
+        return np.arange(n, dtype=np.int32)
+    a = csr_matrix((np.ones(len(cl), dtype=np.int8), cl, rp), shape=(n, n))
+    a = (a + a.T).tocsr()
+    return np.ascontiguousarray(reverse_cuthill_mckee(a, symmetric_mode=True), dtype=np.int32)
 
 
 def _is_cartesian(A_in_sta, A_in_src, prod_target, S, G):
@@ -67,17 +83,27 @@ def _is_cartesian(A_in_sta, A_in_src, prod_target, S, G):
 class GraphPlan(object):
     """Owns the device index arrays and the C-side plan handle (genie_plan_t)."""
 
-    def __init__(self, mode, n_sta, n_grid, n_prod, sta, src, grid, grid_outdeg, prod_grid, device):
+    def __init__(self, mode, n_sta, n_grid, n_prod, sta, src, grid, grid_outdeg, prod_grid, device, grid_order=None):
         self.mode, self.n_sta, self.n_grid, self.n_prod = mode, int(n_sta), int(n_grid), int(n_prod)
         self.device = torch.device(device)
-        self._keep = (sta, src, grid, grid_outdeg, prod_grid)     # keep the tensors alive
+        self.sta_max_deg, self.grid_order = 0, None
+        if mode == capi.GRAPH_CARTESIAN and n_sta > 0 and n_grid > 0:
+            deg = sta[0][1:] - sta[0][:-1]
+            self.sta_max_deg = int(deg.max()) if deg.numel() else 0
+            if grid_order is None:
+                grid_order = locality_order(src[0], src[1], n_grid)
+            grid_order = np.ascontiguousarray(grid_order, dtype=np.int32)
+            if not np.array_equal(np.sort(grid_order), np.arange(n_grid)):
+                raise ValueError('grid_order must be a permutation of the grid nodes')
+            self.grid_order = torch.from_numpy(grid_order).to(self.device).contiguous()
+        self._keep = (sta, src, grid, grid_outdeg, prod_grid, self.grid_order)     # keep the tensors alive
         self.sta_rowptr, self.sta_col = sta
         self.src_rowptr, self.src_col = src
         self.grid_rowptr, self.grid_col = grid
         self.grid_outdeg = grid_outdeg
         self.prod_grid = prod_grid
         d = capi.GraphDesc()
-        d.mode, d.n_sta, d.n_grid, d.reserved, d.n_prod = mode, self.n_sta, self.n_grid, 0, self.n_prod
+        d.mode, d.n_sta, d.n_grid, d.sta_max_deg, d.n_prod = mode, self.n_sta, self.n_grid, self.sta_max_deg, self.n_prod
         d.sta_rowptr = capi.dptr(self.sta_rowptr, torch.int64, 'sta_rowptr')
         d.sta_col = capi.dptr(self.sta_col, torch.int32, 'sta_col')
         d.src_rowptr = capi.dptr(self.src_rowptr, torch.int64, 'src_rowptr')
@@ -86,6 +112,7 @@ class GraphPlan(object):
         d.grid_col = capi.dptr(self.grid_col, torch.int32, 'grid_col')
         d.grid_outdeg = capi.dptr(self.grid_outdeg, torch.int32, 'grid_outdeg')
         d.prod_grid = capi.dptr(self.prod_grid, torch.int32, 'prod_grid') if prod_grid is not None else None
+        d.grid_order = capi.dptr(self.grid_order, torch.int32, 'grid_order') if self.grid_order is not None else None
         self._desc = d
         lib = capi.load()
         handle = ctypes.c_void_p()
@@ -117,7 +144,7 @@ class GraphPlan(object):
         return grid, outdeg
 
     @classmethod
-    def cartesian(cls, A_sta_sta, A_src_src, n_sta, n_grid, A_src=None, device=None):
+    def cartesian(cls, A_sta_sta, A_src_src, n_sta, n_grid, A_src=None, device=None, grid_order=None):
         """Dense mode from the two small kNN graphs (process_utils.py:718-719); product edges stay implicit."""
         device = torch.device(device if device is not None else A_sta_sta.device)
         A_sta_sta, A_src_src = A_sta_sta.to(device), A_src_src.to(device)
@@ -128,7 +155,8 @@ class GraphPlan(object):
             outdeg = torch.bincount(A_src_src[0].long(), minlength=n_grid).to(torch.int32).contiguous()
         else:
             grid, outdeg = cls._grid_parts(A_src.to(device), n_grid)
-        return cls(capi.GRAPH_CARTESIAN, n_sta, n_grid, n_sta * n_grid, sta, src, grid, outdeg, None, device)
+        return cls(capi.GRAPH_CARTESIAN, n_sta, n_grid, n_sta * n_grid, sta, src, grid, outdeg, None, device,
+                   grid_order=grid_order)
 
     @classmethod
     def explicit(cls, A_in_sta, A_in_src, prod_target, A_src, n_prod, n_grid, device=None):

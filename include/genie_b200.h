@@ -56,7 +56,7 @@ typedef struct genie_graph_desc {
     int32_t mode;
     int32_t n_sta;              /* S (CARTESIAN only, else 0) */
     int32_t n_grid;             /* G */
-    int32_t reserved;
+    int32_t sta_max_deg;        /* CARTESIAN: largest in-degree of the station graph, or 0 if unknown (generic kernels) */
     int64_t n_prod;             /* P (= S*G in CARTESIAN mode) */
     const int64_t* sta_rowptr;  /* [S+1] or [P+1] */
     const int32_t* sta_col;
@@ -66,6 +66,10 @@ typedef struct genie_graph_desc {
     const int32_t* grid_col;
     const int32_t* grid_outdeg; /* [G] */
     const int32_t* prod_grid;   /* [P], EXPLICIT only (NULL otherwise); must be < n_grid */
+    const int32_t* grid_order;  /* [G] optional (NULL = 0..G-1): a permutation of the grid nodes in which graph neighbours
+                                   are close together (e.g. reverse Cuthill-McKee of grid/src graph).  Only the ORDER in
+                                   which tiles are processed follows it (L2 reuse of neighbour tiles); data layout and
+                                   results do not depend on it. */
 } genie_graph_desc_t;
 
 typedef struct genie_plan genie_plan_t;

@@ -128,3 +128,23 @@ def test_synthetic_network_is_seeded():
     P = synth.make_picks(a, 0.0, 300.0, seed=1)
     assert P.shape[1] == 5 and np.all(np.diff(P[:, 0]) >= 0) and set(np.unique(P[:, 4])) <= {0.0, 1.0}
     assert a.travel_times().shape == (50, 20, 2) and a.travel_times().max() < a.max_moveout()
+
+
+def test_locality_order_is_a_permutation_with_short_edges():
+    """plan.locality_order: a permutation of the grid nodes (torch-convertible) that keeps kNN neighbours close."""
+    import torch
+    from genie_b200 import synth
+    from genie_b200.plan import csr_by_destination, locality_order
+    from genie_b200.process_utils import knn_graph
+    net = synth.Network(20, 3000, seed=5)
+    A = knn_graph(net.grid / 1000.0, 15)
+    rp, col = csr_by_destination(A, 3000)
+    order = locality_order(rp, col, 3000)
+    assert order.dtype == np.int32 and order.flags['C_CONTIGUOUS']
+    assert np.array_equal(np.sort(order), np.arange(3000))
+    torch.from_numpy(order)                                   # must be convertible (no negative strides)
+    pos = np.empty(3000, dtype=np.int64)
+    pos[order] = np.arange(3000)
+    d = np.abs(pos[A[0].numpy()] - pos[A[1].numpy()])
+    assert d.max() < 1000                                     # graph bandwidth far below the node count
+    assert np.array_equal(locality_order(rp[:1], col[:0], 0), np.arange(0))
