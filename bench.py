@@ -42,8 +42,9 @@ KERNEL_SIG_T, DT, STEP_S, N_QUERY, SCALE_REL = 3.0, 0.3, 3.0, 10000, 30000.0
 DAY_S = 86400.0
 # algorithmic (compulsory) bytes per product node, fp32 intermediates — SURVEY.md §8d / DESIGN.md §4
 BYTES_PER_NODE_WINDOW = 764.0
-BYTES_PER_NODE_KERNEL = {'da_init_kernel': 152.0, 'da_layer1_kernel': 360.0, 'da_layer2_readin_kernel': 252.0,
-                         'da_layer1_tc_kernel': 360.0}
+BYTES_PER_NODE_KERNEL = {'da_init_kernel': 160.0, 'da_layer1_kernel': 400.0, 'da_layer2_readin_kernel': 284.0,
+                         'da_layer1_tc_kernel': 400.0, 'src_mean32_kernel': 256.0, 'da_layer1_s_kernel': 528.0,
+                         'src_mean16_kernel': 128.0, 'da_layer2_s_kernel': 284.0}
 
 
 def _peaks():

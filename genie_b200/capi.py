@@ -17,6 +17,7 @@ _LIB_PATH = os.path.join(_HERE, 'libgenie_b200.so')
 _lib = None
 
 GRAPH_CARTESIAN, GRAPH_EXPLICIT = 0, 1
+ABI_VERSION = 2
 
 c_f32p = ctypes.c_void_p   # device pointers are passed as opaque addresses
 
@@ -28,7 +29,11 @@ class GraphDesc(ctypes.Structure):
                 ('src_rowptr', ctypes.c_void_p), ('src_col', ctypes.c_void_p),
                 ('grid_rowptr', ctypes.c_void_p), ('grid_col', ctypes.c_void_p),
                 ('grid_outdeg', ctypes.c_void_p), ('prod_grid', ctypes.c_void_p),
-                ('grid_order', ctypes.c_void_p)]
+                ('grid_order', ctypes.c_void_p),
+                ('n_sta_tiles', ctypes.c_int32), ('n_grid_groups', ctypes.c_int32),
+                ('sta_tile_rows', ctypes.c_void_p), ('sta_tile_meta', ctypes.c_void_p),
+                ('sta_tile_nbr', ctypes.c_void_p), ('sta_tile_invdeg', ctypes.c_void_p),
+                ('grid_grp_ptr', ctypes.c_void_p), ('grid_grp_nodes', ctypes.c_void_p)]
 
 
 class Linear(ctypes.Structure):
@@ -107,7 +112,7 @@ def load(build_if_missing=True):
         fn = getattr(lib, name)      # AttributeError here = header / library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.genie_abi_version() != 1:
+    if lib.genie_abi_version() != ABI_VERSION:
         raise GenieError('libgenie_b200.so ABI version mismatch')
     _lib = lib
     return lib

@@ -31,7 +31,9 @@ double g_timing_ms[KID_COUNT];
 int64_t g_timing_n[KID_COUNT];
 const char* const kKernelNames[KID_COUNT] = {"pack_weights_kernel", "input_series_kernel", "input_gather_kernel",
                                              "da_init_kernel",      "da_layer1_kernel",    "da_layer1_tc_kernel", "da_layer2_readin_kernel",
-                                             "readin_finalize_kernel", "sa_pre_kernel",    "sa_main_kernel"};
+                                             "readin_finalize_kernel", "sa_pre_kernel",    "sa_main_kernel",
+                                             "src_mean32_kernel",   "src_mean16_kernel",   "da_layer1_s_kernel",
+                                             "da_layer2_s_kernel"};
 }  // namespace
 
 TimedLaunch::TimedLaunch(int kid_, cudaStream_t st_) : kid(kid_), st(st_), slot(nullptr) {
@@ -76,6 +78,7 @@ Workspace carve_workspace(const genie_plan* p, void* base) {
         return ptr;
     };
     w.tr0 = take(P * LD_TR0);
+    w.msrc = split_supported(p) ? take(P * LD_TR0) : nullptr;
     w.zc = take(P * LD_ZC);
     w.va = take(P * LD_V);
     w.vb = take(P * LD_V);
@@ -89,15 +92,47 @@ Workspace carve_workspace(const genie_plan* p, void* base) {
     return w;
 }
 
-// Layer 0 + layer 1 of DataAggregation: tensor-core kernel when the plan allows it (the generic kernel is launched as
-// well and exits at once unless the packed weights make the tensor-core kernel ineligible; see layout.h TCS_OK).
+// Layer 0 + layer 1 of DataAggregation.  Which kernels do the work is decided ON THE DEVICE from the packed weights
+// (layout.h TCS_OK: the tensor-core kernels need PReLU12 to be invertible): both families are launched, one exits at once.
+//   plans with tiling tables: source pass (src_mean) + station pass (da_layer1_s) on tcgen05
+//   other CARTESIAN plans:    one-pass tcgen05 kernel (da_layer1_tc)
+//   fallback / EXPLICIT:      generic FFMA kernel (da_layer1)
 static int launch_da_layers01(const genie_plan* plan, const float* packed, const float* slice, const float* mask,
                               const Workspace& w, cudaStream_t st) {
-    const bool tc = da_tc_supported(plan);
+    const bool split = split_supported(plan);
+    const bool tc = split || da_tc_supported(plan);
     int rc;
     if ((rc = launch_da_init(plan, packed, slice, mask, w.tr0, tc, st))) return rc;
-    if (tc && (rc = launch_da_layer1_tc(plan, packed, w.tr0, mask, w.zc, w.va, w.vb, st))) return rc;
+    if (split) {
+        const float* gate = packed + TC_BASE + TC_SCAL + TCS_OK;
+        if ((rc = launch_src_mean(plan, 32, w.tr0, w.msrc, gate, st))) return rc;
+        if ((rc = launch_da_layer1_s(plan, packed, w.tr0, w.msrc, mask, w.zc, w.va, w.vb, st))) return rc;
+    } else if (tc) {
+        if ((rc = launch_da_layer1_tc(plan, packed, w.tr0, mask, w.zc, w.va, w.vb, st))) return rc;
+    }
     return launch_da_layer1(plan, packed, w.tr0, mask, w.zc, w.va, w.vb, tc, st);
+}
+
+// Layer 2 of DataAggregation (+ Bipartite_ReadIn when `readin_out` is given) from zc / va / vb.
+static int launch_da_layer2(const genie_plan* plan, const float* packed, const Workspace& w, const float* mask,
+                            const float* edge_attr, float* latent_out, float* readin_out, int ld_r, cudaStream_t st) {
+    int rc;
+    if (split_supported(plan) && plan->g.n_sta_tiles <= 32 && edge_attr != nullptr) {
+        float* m2 = w.tr0;                                 // layer-0 features are dead: re-use their buffer
+        if ((rc = launch_src_mean(plan, 16, w.vb, m2, nullptr, st))) return rc;
+        return launch_da_layer2_s(plan, packed, w.zc, w.va, m2, mask, edge_attr, latent_out, readin_out ? readin_out : w.r,
+                                  readin_out ? ld_r : 16, st);
+    }
+    if (readin_out) {
+        GENIE_CUDA_CHECK(cudaMemsetAsync(w.xg, 0, (size_t)plan->g.n_grid * 32 * sizeof(float), st));
+        const int mode = L2_GATHER | L2_READIN | (latent_out ? L2_STORE_LATENT : 0);
+        if ((rc = launch_da_layer2_readin(plan, packed, mode, w.zc, w.va, w.vb, nullptr, latent_out, edge_attr, mask, w.xg,
+                                          st)))
+            return rc;
+        return launch_readin_finalize(plan, packed, w.xg, readin_out, ld_r, st);
+    }
+    return launch_da_layer2_readin(plan, packed, L2_GATHER | L2_STORE_LATENT, w.zc, w.va, w.vb, nullptr, latent_out,
+                                   nullptr, mask, nullptr, st);
 }
 
 extern "C" {
@@ -251,8 +286,7 @@ int genie_data_aggregation_fwd(const genie_plan_t* plan, const float* packed_dev
     Workspace w = carve_workspace(plan, workspace_dev);
     int rc;
     if ((rc = launch_da_layers01(plan, packed_dev, slice_dev, mask_dev, w, st))) return rc;
-    return launch_da_layer2_readin(plan, packed_dev, L2_GATHER | L2_STORE_LATENT, w.zc, w.va, w.vb, nullptr,
-                                   x_latent_out_dev, nullptr, mask_dev, nullptr, st);
+    return launch_da_layer2(plan, packed_dev, w, mask_dev, nullptr, x_latent_out_dev, nullptr, 0, st);
 }
 
 int genie_bipartite_readin_fwd(const genie_plan_t* plan, const float* packed_dev, const float* x_latent_dev,
@@ -296,15 +330,10 @@ int genie_frontend_fwd(const genie_plan_t* plan, const float* packed_dev, const 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Workspace w = carve_workspace(plan, workspace_dev);
     int rc;
-    GENIE_CUDA_CHECK(cudaMemsetAsync(w.xg, 0, (size_t)plan->g.n_grid * 32 * sizeof(float), st));
     if ((rc = launch_da_layers01(plan, packed_dev, slice_dev, mask_dev, w, st))) return rc;
-    const int mode = L2_GATHER | L2_READIN | (x_latent_out_dev ? L2_STORE_LATENT : 0);
-    if ((rc = launch_da_layer2_readin(plan, packed_dev, mode, w.zc, w.va, w.vb, nullptr, x_latent_out_dev,
-                                      edge_attr_dev, mask_dev, w.xg, st)))
-        return rc;
     float* r = readin_out_dev ? readin_out_dev : w.r;
     const int ld_r = readin_out_dev ? 15 : 16;
-    if ((rc = launch_readin_finalize(plan, packed_dev, w.xg, r, ld_r, st))) return rc;
+    if ((rc = launch_da_layer2(plan, packed_dev, w, mask_dev, edge_attr_dev, x_latent_out_dev, r, ld_r, st))) return rc;
     if ((rc = launch_spatial_aggregation(plan, packed_dev, 0, r, ld_r, pos_dev, scale_rel, w.px, w.partial, w.sa_a, 32,
                                          st)))
         return rc;

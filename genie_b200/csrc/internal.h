@@ -46,7 +46,8 @@ inline GraphView make_view(const genie_plan* p) {
 
 // Workspace carve-up (floats).  All regions 256-byte aligned.
 struct Workspace {
-    float* tr0;      // [P][32]
+    float* tr0;      // [P][32]   layer-0 features; re-used for mean_src(v_b) [P][16] once layer 1 is done
+    float* msrc;     // [P][32]   mean over source neighbours of the layer-0 features (split kernels only)
     float* zc;       // [P][32]
     float* va;       // [P][16]
     float* vb;       // [P][16]
@@ -75,6 +76,10 @@ enum KernelId {
     KID_READIN_FINALIZE,
     KID_SA_PRE,
     KID_SA_MAIN,
+    KID_SRC_MEAN32,
+    KID_SRC_MEAN16,
+    KID_DA_LAYER1_S,
+    KID_DA_LAYER2_S,
     KID_COUNT
 };
 // Brackets one kernel launch with cudaEvents on its stream when timing is enabled (no-op otherwise).
@@ -127,6 +132,15 @@ int launch_readin_finalize(const genie_plan* p, const float* packed, const float
 int launch_spatial_aggregation(const genie_plan* p, const float* packed, int layer, const float* x, int ld_x,
                                const float* pos, float scale_rel, float* px, float* partial, float* out, int ld_out,
                                cudaStream_t st);
+// split source-pass / station-pass kernels (plans with tiling tables; src_mean_kernels.cu, da_s1_kernel.cu, da_s2_kernel.cu)
+bool split_supported(const genie_plan* p);
+// out[g,s,:] = mean_{g' in N_src(g)} X[g',s,:], rows of `width` floats (32 or 16); gate: optional device flag, 0 = skip
+int launch_src_mean(const genie_plan* p, int width, const float* X, float* out, const float* gate, cudaStream_t st);
+int launch_da_layer1_s(const genie_plan* p, const float* packed, const float* pfeat, const float* msrc,
+                       const float* mask, float* zc, float* va, float* vb, cudaStream_t st);
+int launch_da_layer2_s(const genie_plan* p, const float* packed, const float* zc, const float* va, const float* m2,
+                       const float* mask, const float* edge_attr, float* latent_out, float* out, int ld_out,
+                       cudaStream_t st);
 int launch_input_scatter(const genie_plan* p, const genie_input_params_t* prm, const double* picks, int64_t n_picks,
                          const int32_t* sta_perm, const int32_t* ind_use, const float* trv_times,
                          const int32_t* node_sta, const int32_t* node_grid, float* series, float* slice_out,

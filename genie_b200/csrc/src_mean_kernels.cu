@@ -1,0 +1,104 @@
+// Source pass of DataAggregation (module.py:91, 95: `propagate(A_in_src, x=...)` with mean aggregation) — CARTESIAN graphs.
+//
+//   out[g, s, :] = 1/deg(g) * sum_{g' in N_src(g)} X[g', s, :]          (0 when g has no in-edges: PyG's mean of nothing)
+//
+// The product edge (g,s) <- (g',s) keeps the station, so for a slab of stations the pass is a sparse G x G matrix applied
+// to dense rows.  The kernel walks compact groups of grid nodes (genie_graph_desc_t.grid_grp_*, built by recursive
+// bisection of the grid graph): the source-neighbour sets of the ~64 nodes of a group overlap heavily (union ~200 rows
+// instead of 64 x 15), and ONE 1024-thread CTA per SM works on one (group, station slab) tile at a time, so the union of
+// neighbour rows (<= 265 x 512 B) sits in that SM's L1 while the group's nodes re-read it: L2 sees every row ~3 times
+// instead of 15, DRAM once (tiles are visited slab-major: all groups of one slab, G x 512 B = 26 MB, stay L2 resident).
+// Lanes map to 16-byte chunks of a row (8 lanes per 128-byte row), so every request is a fully used 128-byte line; there
+// is no shared memory, no barrier and no atomics: warps drift apart freely, and the leaders pull the next tile's rows
+// into L1 while the stragglers finish.
+#include "common.cuh"
+
+using namespace gl;
+
+namespace {
+
+constexpr int SM_THREADS = 1024;
+
+// W = floats per row (32: layer-0 features p, 16: layer-2 messages v_b); SB = stations per slab (power of two)
+template <int W, int SB>
+__global__ void __launch_bounds__(SM_THREADS, 1)
+    src_mean_kernel(const float* __restrict__ X, float* __restrict__ out, int S, const int64_t* __restrict__ rowptr,
+                    const int32_t* __restrict__ col, const int32_t* __restrict__ grp_ptr,
+                    const int32_t* __restrict__ grp_nodes, int n_groups, int n_slabs, const float* __restrict__ gate) {
+    if (gate != nullptr && *gate == 0.f) return;     // the one-pass kernels run instead (layout.h TCS_OK)
+    constexpr int LPR = W / 4;                       // lanes per row
+    const int64_t n_tiles = (int64_t)n_groups * n_slabs;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int slab = (int)(t / n_groups);
+        const int grp = (int)(t - (int64_t)slab * n_groups);
+        const int gbeg = __ldg(grp_ptr + grp);
+        const int gcnt = __ldg(grp_ptr + grp + 1) - gbeg;
+        const int s0 = slab * SB;
+        const int items = gcnt * SB * LPR;
+        for (int i = threadIdx.x; i < items; i += SM_THREADS) {
+            const int c = i % LPR;
+            const int row = i / LPR;
+            const int sl = row % SB;
+            const int gl = row / SB;
+            const int s = s0 + sl;
+            if (s >= S) continue;
+            const int g = __ldg(grp_nodes + gbeg + gl);
+            const int64_t beg = __ldg(rowptr + g);
+            const int deg = (int)(__ldg(rowptr + g + 1) - beg);
+            const float4* __restrict__ base = reinterpret_cast<const float4*>(X) + (int64_t)s * LPR + c;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j0 = 0; j0 < deg; j0 += 8) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    // absent edges re-read the first neighbour and are masked out of the sum (keeps all 8 loads in flight)
+                    const int j = min(j0 + u, deg - 1);
+                    const int gj = __ldg(col + beg + j);
+                    v[u] = __ldg(base + (int64_t)gj * S * LPR);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float w = (j0 + u) < deg ? 1.f : 0.f;
+                    acc.x = fmaf(v[u].x, w, acc.x);
+                    acc.y = fmaf(v[u].y, w, acc.y);
+                    acc.z = fmaf(v[u].z, w, acc.z);
+                    acc.w = fmaf(v[u].w, w, acc.w);
+                }
+            }
+            const float inv = deg > 0 ? 1.f / (float)deg : 0.f;
+            acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+            __stcs(reinterpret_cast<float4*>(out) + ((int64_t)g * S + s) * LPR + c, acc);
+        }
+    }
+}
+
+}  // namespace
+
+bool split_supported(const genie_plan* p) {
+    const genie_graph_desc_t& g = p->g;
+    return g.mode == GENIE_GRAPH_CARTESIAN && g.n_sta_tiles > 0 && g.n_grid_groups > 0 && g.sta_tile_rows &&
+           g.sta_tile_meta && g.sta_tile_nbr && g.sta_tile_invdeg && g.grid_grp_ptr && g.grid_grp_nodes && g.n_prod > 0 &&
+           g.n_prod < (int64_t)0x7fffff00;
+}
+
+int launch_src_mean(const genie_plan* p, int width, const float* X, float* out, const float* gate, cudaStream_t st) {
+    const genie_graph_desc_t& g = p->g;
+    constexpr int SB = 4;
+    const int n_slabs = (g.n_sta + SB - 1) / SB;
+    const int64_t n_tiles = (int64_t)g.n_grid_groups * n_slabs;
+    const unsigned grid = (unsigned)(n_tiles < p->sm_count ? n_tiles : p->sm_count);
+    if (width == 32) {
+        TimedLaunch tl(KID_SRC_MEAN32, st);
+        src_mean_kernel<32, SB><<<grid, SM_THREADS, 0, st>>>(X, out, g.n_sta, g.src_rowptr, g.src_col, g.grid_grp_ptr,
+                                                             g.grid_grp_nodes, g.n_grid_groups, n_slabs, gate);
+    } else if (width == 16) {
+        TimedLaunch tl(KID_SRC_MEAN16, st);
+        src_mean_kernel<16, SB><<<grid, SM_THREADS, 0, st>>>(X, out, g.n_sta, g.src_rowptr, g.src_col, g.grid_grp_ptr,
+                                                             g.grid_grp_nodes, g.n_grid_groups, n_slabs, gate);
+    } else {
+        set_error("launch_src_mean: unsupported row width");
+        return GENIE_ERR_INVALID;
+    }
+    GENIE_LAUNCH_CHECK();
+    return GENIE_OK;
+}

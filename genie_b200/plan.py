@@ -43,6 +43,88 @@ def locality_order(rowptr, col, n):
     return np.ascontiguousarray(reverse_cuthill_mckee(a, symmetric_mode=True), dtype=np.int32)
 
 
+# ---- on-chip tiling tables of the split (source pass / station pass) kernels ----------------------------------------------
+TILE_M = 128        # product-node rows of one station tile (= MMA M)
+ROWS_MAX = 288      # station rows (tile + halo) staged in shared memory per tile; row ROWS_MAX is an all-zero row
+GROUP_SIZE = 64     # grid nodes per source-pass group
+
+
+def bisection_groups(rowptr, col, n, size):
+    """Partitions the nodes of a graph into compact groups of <= `size` nodes by recursive bisection along reverse
+    Cuthill-McKee orders of the (symmetrised) sub-graphs: no coordinates needed, and the union of the neighbour sets of a
+    group stays small (the on-chip reuse factor of the kernels).  Returns (ptr int32 [ng+1], nodes int32 [n]); groups
+    are emitted in depth-first order, so consecutive groups are close in the graph."""
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+    rp = np.asarray(rowptr.cpu() if torch.is_tensor(rowptr) else rowptr).astype(np.int64)
+    cl = np.asarray(col.cpu() if torch.is_tensor(col) else col).astype(np.int32)
+    if n == 0:
+        return np.zeros(1, dtype=np.int32), np.zeros(0, dtype=np.int32)
+    a = csr_matrix((np.ones(len(cl), dtype=np.int8), cl, rp), shape=(n, n))
+    a = (a + a.T).tocsr()
+    groups = []
+    stack = [np.arange(n, dtype=np.int64)]
+    while stack:
+        idx = stack.pop()
+        m = len(idx)
+        if m <= size:
+            groups.append(idx)
+            continue
+        o = reverse_cuthill_mckee(a[idx][:, idx], symmetric_mode=True)
+        nl = (m // 2 + size - 1) // size * size
+        if nl >= m:
+            nl = m // 2
+        stack.append(idx[o[nl:]])
+        stack.append(idx[o[:nl]])           # left half is processed first (depth-first order)
+    ptr = np.zeros(len(groups) + 1, dtype=np.int32)
+    ptr[1:] = np.cumsum([len(x) for x in groups])
+    return ptr, np.concatenate(groups).astype(np.int32)
+
+
+def station_tiles(rowptr, col, n_sta, tile_m=TILE_M, rows_max=ROWS_MAX):
+    """Station tiles of the station-pass kernels: every tile is a compact set of <= tile_m stations plus the halo of
+    their in-neighbours, <= rows_max rows in all.  Returns None when no tile size >= 32 fits, else a dict of numpy arrays
+      rows   int32  [NT, rows_max]   station id of each staged row (tile stations first, then the halo; padding 0)
+      meta   int32  [NT, 2]          (stations in the tile, staged rows)
+      nbr    uint16 [NT, tile_m, 16] staged-row index of every in-neighbour (padding: rows_max = the zero row)
+      invdeg fp32   [NT, tile_m]     1 / in-degree (0 for isolated stations: PyG's mean of nothing is 0)."""
+    rp = np.asarray(rowptr.cpu() if torch.is_tensor(rowptr) else rowptr).astype(np.int64)
+    cl = np.asarray(col.cpu() if torch.is_tensor(col) else col).astype(np.int64)
+    deg = rp[1:] - rp[:-1]
+    if n_sta == 0 or (len(deg) and deg.max() > 16):
+        return None
+    for t in range(tile_m, 31, -16):
+        ptr, nodes = bisection_groups(rp, cl, n_sta, t)
+        nt = len(ptr) - 1
+        rows = np.zeros((nt, rows_max), dtype=np.int32)
+        meta = np.zeros((nt, 2), dtype=np.int32)
+        nbr = np.full((nt, tile_m, 16), rows_max, dtype=np.uint16)
+        invdeg = np.zeros((nt, tile_m), dtype=np.float32)
+        ok = True
+        for i in range(nt):
+            own = nodes[ptr[i]:ptr[i + 1]].astype(np.int64)
+            local = {int(s): r for r, s in enumerate(own)}
+            lst = list(own)
+            for r, s in enumerate(own):
+                js = cl[rp[s]:rp[s + 1]]
+                for q, j in enumerate(js):
+                    j = int(j)
+                    if j not in local:
+                        local[j] = len(lst)
+                        lst.append(j)
+                    nbr[i, r, q] = local[j]
+                if len(js):
+                    invdeg[i, r] = np.float32(1.0) / np.float32(len(js))
+            if len(lst) > rows_max:
+                ok = False
+                break
+            rows[i, :len(lst)] = lst
+            meta[i] = (len(own), len(lst))
+        if ok:
+            return dict(rows=rows, meta=meta, nbr=nbr, invdeg=invdeg, tile=t)
+    return None
+
+
 def _is_cartesian(A_in_sta, A_in_src, prod_target, S, G):
     """Checks the index patterns of process_utils.py:720-722; returns (A_sta_sta, A_src_src) or None."""
     P = S * G
@@ -83,7 +165,8 @@ def _is_cartesian(A_in_sta, A_in_src, prod_target, S, G):
 class GraphPlan(object):
     """Owns the device index arrays and the C-side plan handle (genie_plan_t)."""
 
-    def __init__(self, mode, n_sta, n_grid, n_prod, sta, src, grid, grid_outdeg, prod_grid, device, grid_order=None):
+    def __init__(self, mode, n_sta, n_grid, n_prod, sta, src, grid, grid_outdeg, prod_grid, device, grid_order=None,
+                 tiling=True, group_size=GROUP_SIZE):
         self.mode, self.n_sta, self.n_grid, self.n_prod = mode, int(n_sta), int(n_grid), int(n_prod)
         self.device = torch.device(device)
         self.sta_max_deg, self.grid_order = 0, None
@@ -96,7 +179,18 @@ class GraphPlan(object):
             if not np.array_equal(np.sort(grid_order), np.arange(n_grid)):
                 raise ValueError('grid_order must be a permutation of the grid nodes')
             self.grid_order = torch.from_numpy(grid_order).to(self.device).contiguous()
-        self._keep = (sta, src, grid, grid_outdeg, prod_grid, self.grid_order)     # keep the tensors alive
+        # on-chip tiling tables of the split kernels (dense mode; None -> the one-pass kernels are used)
+        self.tiles = None
+        if mode == capi.GRAPH_CARTESIAN and n_sta >= 32 and n_grid > 0 and 1 <= self.sta_max_deg <= 16 and tiling:
+            st = station_tiles(sta[0], sta[1], self.n_sta)
+            if st is not None:
+                gp, gn = bisection_groups(src[0], src[1], self.n_grid, int(group_size))
+                put = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+                self.tiles = dict(n_tiles=int(st['meta'].shape[0]), n_groups=int(len(gp) - 1), tile=int(st['tile']),
+                                  rows=put(st['rows']), meta=put(st['meta']),
+                                  nbr=put(st['nbr'].view(np.int16)), invdeg=put(st['invdeg']),
+                                  grp_ptr=put(gp), grp_nodes=put(gn))
+        self._keep = (sta, src, grid, grid_outdeg, prod_grid, self.grid_order, self.tiles)     # keep the tensors alive
         self.sta_rowptr, self.sta_col = sta
         self.src_rowptr, self.src_col = src
         self.grid_rowptr, self.grid_col = grid
@@ -113,6 +207,15 @@ class GraphPlan(object):
         d.grid_outdeg = capi.dptr(self.grid_outdeg, torch.int32, 'grid_outdeg')
         d.prod_grid = capi.dptr(self.prod_grid, torch.int32, 'prod_grid') if prod_grid is not None else None
         d.grid_order = capi.dptr(self.grid_order, torch.int32, 'grid_order') if self.grid_order is not None else None
+        if self.tiles is not None:
+            t = self.tiles
+            d.n_sta_tiles, d.n_grid_groups = t['n_tiles'], t['n_groups']
+            d.sta_tile_rows = capi.dptr(t['rows'], torch.int32, 'sta_tile_rows')
+            d.sta_tile_meta = capi.dptr(t['meta'], torch.int32, 'sta_tile_meta')
+            d.sta_tile_nbr = capi.dptr(t['nbr'], torch.int16, 'sta_tile_nbr')
+            d.sta_tile_invdeg = capi.dptr(t['invdeg'], torch.float32, 'sta_tile_invdeg')
+            d.grid_grp_ptr = capi.dptr(t['grp_ptr'], torch.int32, 'grid_grp_ptr')
+            d.grid_grp_nodes = capi.dptr(t['grp_nodes'], torch.int32, 'grid_grp_nodes')
         self._desc = d
         lib = capi.load()
         handle = ctypes.c_void_p()
@@ -144,7 +247,8 @@ class GraphPlan(object):
         return grid, outdeg
 
     @classmethod
-    def cartesian(cls, A_sta_sta, A_src_src, n_sta, n_grid, A_src=None, device=None, grid_order=None):
+    def cartesian(cls, A_sta_sta, A_src_src, n_sta, n_grid, A_src=None, device=None, grid_order=None, tiling=True,
+                  group_size=GROUP_SIZE):
         """Dense mode from the two small kNN graphs (process_utils.py:718-719); product edges stay implicit."""
         device = torch.device(device if device is not None else A_sta_sta.device)
         A_sta_sta, A_src_src = A_sta_sta.to(device), A_src_src.to(device)
@@ -156,7 +260,7 @@ class GraphPlan(object):
         else:
             grid, outdeg = cls._grid_parts(A_src.to(device), n_grid)
         return cls(capi.GRAPH_CARTESIAN, n_sta, n_grid, n_sta * n_grid, sta, src, grid, outdeg, None, device,
-                   grid_order=grid_order)
+                   grid_order=grid_order, tiling=tiling, group_size=group_size)
 
     @classmethod
     def explicit(cls, A_in_sta, A_in_src, prod_target, A_src, n_prod, n_grid, device=None):

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GENIE_B200_ABI_VERSION 1
+#define GENIE_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define GENIE_API __attribute__((visibility("default")))
@@ -70,7 +70,26 @@ typedef struct genie_graph_desc {
                                    are close together (e.g. reverse Cuthill-McKee of grid/src graph).  Only the ORDER in
                                    which tiles are processed follows it (L2 reuse of neighbour tiles); data layout and
                                    results do not depend on it. */
+    /* Optional on-chip tiling tables of the split source-pass / station-pass kernels (CARTESIAN only; leave the
+     * counts 0 to run the one-pass kernels).  They only say HOW the work is tiled; results do not depend on them.
+     *   station tiles: NT compact sets of <= 128 stations with the halo of their station-graph in-neighbours, at most
+     *     GENIE_TILE_ROWS_MAX staged rows each:  sta_tile_rows int32 [NT][ROWS_MAX] station id per staged row (the
+     *     tile's own stations first), sta_tile_meta int32 [NT][2] = (own stations, staged rows), sta_tile_nbr uint16
+     *     [NT][128][16] staged-row index of each in-neighbour (padding = ROWS_MAX, the zero row), sta_tile_invdeg fp32
+     *     [NT][128] = 1 / in-degree (0 if isolated).  Every station must belong to exactly one tile.
+     *   grid groups: NG compact groups of grid nodes (any sizes), grid_grp_ptr int32 [NG+1] into grid_grp_nodes int32 [G]
+     *     (a permutation of the grid nodes); the source-neighbour rows of one group are re-used through L1. */
+    int32_t n_sta_tiles;
+    int32_t n_grid_groups;
+    const int32_t* sta_tile_rows;
+    const int32_t* sta_tile_meta;
+    const uint16_t* sta_tile_nbr;
+    const float* sta_tile_invdeg;
+    const int32_t* grid_grp_ptr;
+    const int32_t* grid_grp_nodes;
 } genie_graph_desc_t;
+
+#define GENIE_TILE_ROWS_MAX 288
 
 typedef struct genie_plan genie_plan_t;
 

@@ -160,6 +160,41 @@ def test_front_end_matches_oracle_seeded(S, G, k_s, k_g):
     assert rel_err(xs.cpu().numpy(), want.numpy()) < TOL
 
 
+def test_one_pass_kernels_match_split_kernels():
+    """Plans without tiling tables run the one-pass kernels (tcgen05 layer 1 with L2 gathers, FFMA layer 2 with atomics);
+    plans with them run the split source-pass / station-pass kernels.  Same mathematics, different tiling."""
+    from genie_b200 import ops
+    from genie_b200.plan import GraphPlan
+    from oracle import genie_oracle as go
+    dev = _dev()
+    S, G = 300, 700                                          # 3 station tiles with halos, 11 grid groups
+    net, A_sta, A_src, Slice, Mask, attr = _random_case(S, G, 15, 15, 17, dev)
+    sd = go.init_state(seed=5)
+    from genie_b200.module import GCN_Detection_Network_extended
+    m = GCN_Detection_Network_extended(None, None, device=dev)
+    m.load_state_dict(sd, strict=False)
+    packed = m._packed_weights(dev)
+    grid = torch.from_numpy(net.grid).float().to(dev)
+    outs = []
+    for tiling in (True, False):
+        plan = GraphPlan.cartesian(A_sta, A_src, S, G, device=dev, tiling=tiling)
+        assert (plan.tiles is not None) == tiling
+        if tiling:
+            assert plan.tiles['n_tiles'] == 3
+        outs.append(ops.frontend_fwd(plan, packed, Slice.to(dev), Mask.to(dev), attr.to(dev), grid, 30000.0,
+                                     want_latent=True, want_readin=True))
+        lat_only = ops.data_aggregation_fwd(plan, packed, Slice.to(dev), Mask.to(dev))
+        assert rel_err(lat_only.cpu().numpy(), outs[-1][1].cpu().numpy()) < 1e-5
+    for a, b in zip(outs[0], outs[1]):
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 2e-5
+    # the station pass has no atomics: bit-reproducible run to run
+    plan = GraphPlan.cartesian(A_sta, A_src, S, G, device=dev)
+    again = ops.frontend_fwd(plan, packed, Slice.to(dev), Mask.to(dev), attr.to(dev), grid, 30000.0, want_latent=True,
+                             want_readin=True)
+    for a, b in zip(outs[0], again):
+        assert torch.equal(a, b)
+
+
 def test_irregular_explicit_graph_matches_oracle():
     """Sub-graph style product graph: variable in-degree, isolated nodes (mean of nothing = 0), unsorted edge order."""
     from genie_b200 import ops

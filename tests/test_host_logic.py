@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert set(names) == set(capi.SIGNATURES)           # the ctypes binding covers the whole header
-    assert lib.genie_abi_version() == 1
+    assert lib.genie_abi_version() == capi.ABI_VERSION
     assert lib.genie_frontend_packed_floats() > 20000
     assert lib.genie_launch_count() == 0                # nothing was launched (no GPU here)
 
@@ -148,3 +148,55 @@ def test_locality_order_is_a_permutation_with_short_edges():
     d = np.abs(pos[A[0].numpy()] - pos[A[1].numpy()])
     assert d.max() < 1000                                     # graph bandwidth far below the node count
     assert np.array_equal(locality_order(rp[:1], col[:0], 0), np.arange(0))
+
+
+@pytest.mark.parametrize('S,k', [(300, 15), (64, 8), (1000, 15), (33, 4)])
+def test_station_tiles_reproduce_the_station_mean(S, k):
+    """The tiling tables of the station-pass kernels (plan.station_tiles): every station in exactly one tile, staged
+    rows cover every in-neighbour, and gathering through the tables equals the direct mean over in-edges."""
+    from genie_b200 import synth
+    from genie_b200.plan import ROWS_MAX, TILE_M, csr_by_destination, station_tiles
+    from genie_b200.process_utils import knn_graph
+    rng = np.random.default_rng(S)
+    net = synth.Network(S, 10, seed=S, morton=False)            # unordered stations: the tiler must find the locality
+    A = knn_graph(net.sta / 1000.0, k)
+    A = A[:, rng.random(A.shape[1]) > 0.05]                     # ragged in-degrees
+    A = A[:, A[1] != 7]                                         # one isolated station
+    rowptr, col = csr_by_destination(A, S)
+    st = station_tiles(rowptr, col, S)
+    assert st is not None
+    rows, meta, nbr, invdeg = st['rows'], st['meta'], st['nbr'], st['invdeg']
+    assert meta[:, 0].max() <= TILE_M and meta[:, 1].max() <= ROWS_MAX
+    own = np.concatenate([rows[t, :meta[t, 0]] for t in range(len(meta))])
+    assert np.array_equal(np.sort(own), np.arange(S))
+    x = rng.normal(size=(S, 5)).astype(np.float32)
+    want = np.zeros_like(x)
+    rp, cl = rowptr.numpy(), col.numpy()
+    for s in range(S):
+        if rp[s + 1] > rp[s]:
+            want[s] = x[cl[rp[s]:rp[s + 1]]].mean(0)
+    got = np.zeros_like(x)
+    for t in range(len(meta)):
+        staged = np.concatenate((x[rows[t]], np.zeros((1, 5), np.float32)))          # row ROWS_MAX = the zero row
+        for r in range(meta[t, 0]):
+            assert (nbr[t, r] <= ROWS_MAX).all() and ((nbr[t, r] < meta[t, 1]) | (nbr[t, r] == ROWS_MAX)).all()
+            got[rows[t, r]] = staged[nbr[t, r].astype(np.int64)].sum(0) * invdeg[t, r]
+    assert np.abs(got - want).max() < 1e-5
+    assert invdeg[[t for t in range(len(meta)) if 7 in rows[t, :meta[t, 0]]][0]].min() == 0.0
+
+
+def test_bisection_groups_partition_and_compactness():
+    from genie_b200 import synth
+    from genie_b200.plan import bisection_groups, csr_by_destination
+    from genie_b200.process_utils import knn_graph
+    G = 3000
+    net = synth.Network(10, G, seed=3, morton=False)
+    rowptr, col = csr_by_destination(knn_graph(net.grid / 1000.0, 15), G)
+    ptr, nodes = bisection_groups(rowptr, col, G, 64)
+    assert ptr[0] == 0 and ptr[-1] == G and np.array_equal(np.sort(nodes), np.arange(G))
+    sizes = np.diff(ptr)
+    assert sizes.max() <= 64 and sizes.min() >= 1
+    rp, cl = rowptr.numpy(), col.numpy()
+    union = [len(set(np.concatenate([cl[rp[g]:rp[g + 1]] for g in nodes[ptr[i]:ptr[i + 1]]]).tolist()))
+             for i in range(len(sizes))]
+    assert np.sum(sizes) * 15 / np.sum(union) > 3.0             # neighbour rows are re-used > 3x inside a group
