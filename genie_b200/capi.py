@@ -75,6 +75,7 @@ SIGNATURES = {
     'genie_timing_kernel_name': (ctypes.c_char_p, [ctypes.c_int]),
     'genie_timing_collect': (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
                                             ctypes.c_int]),
+    'genie_debug_trace': (ctypes.c_int, [_P, ctypes.c_int]),
     'genie_plan_create': (ctypes.c_int, [ctypes.POINTER(GraphDesc), ctypes.POINTER(_P)]),
     'genie_plan_destroy': (None, [_P]),
     'genie_plan_workspace_bytes': (ctypes.c_size_t, [_P]),

@@ -175,6 +175,11 @@ int genie_timing_collect(double* total_ms, int64_t* launches, int reset) {
     return GENIE_OK;
 }
 
+int genie_debug_trace(int64_t* trace_dev, int tiles) {
+    set_s1_trace(reinterpret_cast<long long*>(trace_dev), trace_dev ? tiles : 0);
+    return GENIE_OK;
+}
+
 int genie_plan_create(const genie_graph_desc_t* d, genie_plan_t** out) {
     if (!d || !out) {
         set_error("genie_plan_create: null argument");

@@ -61,6 +61,12 @@ static_assert(sizeof(Bars) <= 256, "barrier block");
 
 __device__ __forceinline__ float prelu_f(float x, float a) { return x >= 0.f ? x : a * x; }
 
+// Development aid (genie_debug_trace): CTA 0 stamps clock64() at the hand-off points of its first tiles, 24 slots per tile.
+#define S1_TRACE(slot)                                                                      \
+    do {                                                                                    \
+        if (trace != nullptr && blockIdx.x == 0 && it < trace_tiles) trace[it * 24 + (slot)] = clock64(); \
+    } while (0)
+
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -111,7 +117,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                        const float* __restrict__ mask, float* __restrict__ zc, float* __restrict__ va,
                        float* __restrict__ vb, int S, int NT, const int32_t* __restrict__ tile_rows,
                        const int32_t* __restrict__ tile_meta, const uint16_t* __restrict__ tile_nbr,
-                       const float* __restrict__ tile_invdeg, int64_t n_tiles) {
+                       const float* __restrict__ tile_invdeg, int64_t n_tiles, long long* __restrict__ trace, int trace_tiles) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const float* tcw = packed + TC_BASE;
     if (tcw[TC_SCAL + TCS_OK] == 0.f) return;   // slopes not eligible: the generic kernels run instead (uniform exit)
@@ -157,35 +163,54 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
 
     if (warp >= WG_P0) {
         // ================================ producers: cp.async row gather ==============================================
+        // Thread `tid` owns the 16-byte chunk c = tid & 7 of the staged rows rr + 16 j (rr = tid >> 3).  The halo rows are
+        // only ever read as PReLU11(tr0): the thread converts the chunks it copied itself (element-wise, so no other
+        // thread is involved) before it arrives on the buffer's barrier; the tile's own rows stay p (the gather warpgroup
+        // needs tr0 of its own row first and converts them itself).
         const int tid = threadIdx.x - WG_P0 * 32;
+        const int rr = tid >> 3, c = tid & 7;
+        const float r11 = sc[TCS_R11];
+        constexpr int JMAX = (ROWS + 15) / 16;
         int64_t it = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const int g = (int)(t / NT), T = (int)(t - (int64_t)g * NT);
             const int buf = (int)(it & 1);
             const int n_own = __ldg(tile_meta + 2 * T), n_rows = __ldg(tile_meta + 2 * T + 1);
             const int32_t* rows = tile_rows + (int64_t)T * ROWS;
+            int ids[JMAX];
+#pragma unroll
+            for (int j = 0; j < JMAX; ++j) ids[j] = (rr + 16 * j) < n_rows ? __ldg(rows + rr + 16 * j) : -1;
+            const int id_m = tid < n_own ? __ldg(rows + tid) : -1;
             if (it >= NBUF) mbar_wait(&bars->empty[buf], (uint32_t)(((it >> 1) - 1) & 1));
-            const uint32_t sb = smem_u32(smem + SM_BUF + buf * SB_SIZE);
+            if (tid == 0) S1_TRACE(17);
+            unsigned char* sbp = smem + SM_BUF + buf * SB_SIZE;
+            const uint32_t sb = smem_u32(sbp);
             const int64_t node0 = (int64_t)g * S;
-            for (int i = tid; i < n_rows * 8; i += 128) {
-                const int r = i >> 3, c = i & 7;
-                const int64_t node = node0 + __ldg(rows + r);
-                cp_async16(sb + SB_P + r * 128 + c * 16, p + node * 32 + c * 4);
+#pragma unroll
+            for (int j = 0; j < JMAX; ++j)
+                if (ids[j] >= 0) cp_async16(sb + SB_P + (rr + 16 * j) * 128 + c * 16, p + (node0 + ids[j]) * 32 + c * 4);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r = rr + 16 * j;
+                if (r < n_own) cp_async16(sb + SB_MS + r * 128 + ((c ^ (r & 7)) << 4), msrc + (node0 + ids[j]) * 32 + c * 4);
             }
-            for (int i = tid; i < n_own * 8; i += 128) {
-                const int r = i >> 3, c = i & 7;
-                const int64_t node = node0 + __ldg(rows + r);
-                cp_async16(sb + SB_MS + r * 128 + ((c ^ (r & 7)) << 4), msrc + node * 32 + c * 4);
+            if (id_m >= 0) cp_async16(sb + SB_MK + tid * 16, mask + (node0 + id_m) * 4);
+            asm volatile("cp.async.wait_all;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < JMAX; ++j) {
+                const int r = rr + 16 * j;
+                if (r >= n_own && ids[j] >= 0) {
+                    float4* a = reinterpret_cast<float4*>(sbp + SB_P + r * 128 + c * 16);
+                    const float4 v = *a;
+                    *a = make_float4(prelu_f(v.x, r11), prelu_f(v.y, r11), prelu_f(v.z, r11), prelu_f(v.w, r11));
+                }
             }
-            for (int r = tid; r < n_own; r += 128) {
-                const int64_t node = node0 + __ldg(rows + r);
-                cp_async16(sb + SB_MK + r * 16, mask + node * 4);
-            }
-            cp_async_arrive_noinc(&bars->full[buf]);
+            mbar_arrive(&bars->full[buf]);
+            if (tid == 0) S1_TRACE(18);
         }
     } else if (warp == WARP_MMA) {
         // ================================ MMA issuer ==================================================================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t wbase = smem_u32(sW);
             const uint32_t i64 = umma_idesc_tf32(128, 64), i32 = umma_idesc_tf32(128, 32);
             const uint32_t i96 = umma_idesc_tf32(128, 96), i16 = umma_idesc_tf32(128, 16);
@@ -196,6 +221,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                 mbar_wait(&bars->opA_full, (uint32_t)(it & 1));
                 if (it > 0) mbar_wait(&bars->d_free, (uint32_t)((it - 1) & 1));
                 tc_fence_after_sync();
+                S1_TRACE(0);
                 // ---- stage B: D[0,64) = [tr1 | tr2] pre-activation --------------------------------------------------
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
@@ -219,10 +245,12 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                 }
                 umma_commit(&bars->opA_free);
                 umma_commit(&bars->d_full);
+                S1_TRACE(1);
                 // ---- stage C: D[0,96) (bias preloaded by the epilogue) += tr-row * B2 ----------------------------------
                 mbar_wait(&bars->aE_full, ph_a);
                 ph_a ^= 1;
                 tc_fence_after_sync();
+                S1_TRACE(2);
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
                     const uint32_t b2 = wbase + 4 * (pass == 2 ? TC_B2_LO : TC_B2_HI);
@@ -232,10 +260,12 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                                      umma_desc_kmajor(b2 + ks * 2 * 96 * 16, 96 * 16, 128), i96, 1u);
                 }
                 umma_commit(&bars->d_full);
+                S1_TRACE(3);
                 // ---- stage D: D[0,16) = v_a, D[16,32) = v_b --------------------------------------------------------------
                 mbar_wait(&bars->aE_full, ph_a);
                 ph_a ^= 1;
                 tc_fence_after_sync();
+                S1_TRACE(4);
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
                     const uint32_t b3a = wbase + 4 * (pass == 2 ? TC_B3A_LO : TC_B3A_HI);
@@ -249,6 +279,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                     }
                 }
                 umma_commit(&bars->d_full);
+                S1_TRACE(5);
             }
         }
     } else if (warp >= WG_G0 && warp < WG_G0 + 4) {
@@ -261,35 +292,31 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const int T = (int)(t % NT);
             const int buf = (int)(it & 1);
-            const int n_own = __ldg(tile_meta + 2 * T), n_rows = __ldg(tile_meta + 2 * T + 1);
+            const int n_own = __ldg(tile_meta + 2 * T);
             // neighbour table of this row (staged-row indices; padding = the zero row) and 1 / degree
             const uint4* nb = reinterpret_cast<const uint4*>(tile_nbr + ((int64_t)T * 128 + r) * 16);
             const uint4 n0 = __ldg(nb), n1 = __ldg(nb + 1);
             const float invdeg = __ldg(tile_invdeg + T * 128 + r);
             unsigned char* sb = smem + SM_BUF + buf * SB_SIZE;
             mbar_wait(&bars->full[buf], (uint32_t)((it >> 1) & 1));
-            // ---- in place: staged rows p = PReLU12(tr0) -> PReLU11(tr0); keep tr0 of the own row ---------------------------
+            if (r == 0) S1_TRACE(12);
+            // ---- own row: keep tr0 = PReLU12^-1(p), leave PReLU11(tr0) in place (the halo rows were converted by the producers)
             float4 own[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) own[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < n_own) {
+                unsigned char* ra = sb + SB_P + r * 128;
 #pragma unroll
-            for (int rep = 0; rep < (ROWS + 127) / 128; ++rep) {
-                const int row = r + rep * 128;
-                if (row < n_rows) {
-                    unsigned char* ra = sb + SB_P + row * 128;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        float4* a = reinterpret_cast<float4*>(ra + ((k ^ key) << 4));
-                        const float4 v = *a;
-                        if (rep == 0)
-                            own[k] = make_float4(prelu_f(v.x, inv12), prelu_f(v.y, inv12), prelu_f(v.z, inv12),
-                                                 prelu_f(v.w, inv12));
-                        *a = make_float4(prelu_f(v.x, r11), prelu_f(v.y, r11), prelu_f(v.z, r11), prelu_f(v.w, r11));
-                    }
+                for (int k = 0; k < 8; ++k) {
+                    float4* a = reinterpret_cast<float4*>(ra + ((k ^ key) << 4));
+                    const float4 v = *a;
+                    own[k] = make_float4(prelu_f(v.x, inv12), prelu_f(v.y, inv12), prelu_f(v.z, inv12), prelu_f(v.w, inv12));
+                    *a = make_float4(prelu_f(v.x, r11), prelu_f(v.y, r11), prelu_f(v.z, r11), prelu_f(v.w, r11));
                 }
             }
             unrotate8(own, key);
             named_bar_sync(1, 128);
+            if (r == 0) S1_TRACE(13);
             // ---- sum of the station neighbours' rows (16-byte chunk k ^ key of every row: conflict free) ------------------
             float4 acc[8];
 #pragma unroll
@@ -312,8 +339,10 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
             float4 mk = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid) mk = *reinterpret_cast<const float4*>(sb + SB_MK + r * 16);
             // ---- A operands -> tensor memory (free once stage B of the previous tile has completed) ------------------------
+            if (r == 0) S1_TRACE(14);
             if (it > 0) mbar_wait(&bars->opA_free, (uint32_t)((it - 1) & 1));
             tc_fence_after_sync();
+            if (r == 0) S1_TRACE(15);
             {
                 float a[16];
 #pragma unroll
@@ -356,6 +385,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
             tmem_st_wait();
             tc_fence_before_sync();
             mbar_arrive(&bars->opA_full);
+            if (r == 0) S1_TRACE(16);
         }
     } else if (warp >= WG_E0 && warp < WG_E0 + 4) {
         // ================================ epilogue warpgroup (thread per row) ==========================================
@@ -365,7 +395,8 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
         const float a1 = sc[TCS_A1], a21 = sc[TCS_A21], a22 = sc[TCS_A22];
         const float* bias2 = sW + TC_BIAS2;
         uint32_t ph_d = 0;
-        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        int64_t it = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const int g = (int)(t / NT), T = (int)(t - (int64_t)g * NT);
             const bool valid = r < __ldg(tile_meta + 2 * T);
             const int64_t node = (int64_t)g * S + (valid ? __ldg(tile_rows + (int64_t)T * ROWS + r) : 0);
@@ -375,6 +406,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
             mbar_wait(&bars->d_full, ph_d);
             ph_d ^= 1;
             tc_fence_after_sync();
+            if (r == 0) S1_TRACE(6);
 #pragma unroll
             for (int c = 0; c < 64; c += 16) {
                 float v[16];
@@ -405,10 +437,12 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
             tmem_st_wait();
             tc_fence_before_sync();
             mbar_arrive(&bars->aE_full);
+            if (r == 0) S1_TRACE(7);
             // ---- stage C epilogue: PReLU(h) -> A operand of stage D; c -> global ------------------------------------------
             mbar_wait(&bars->d_full, ph_d);
             ph_d ^= 1;
             tc_fence_after_sync();
+            if (r == 0) S1_TRACE(8);
 #pragma unroll
             for (int c = 0; c < 64; c += 16) {
                 float v[16];
@@ -434,10 +468,12 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
             tmem_st_wait();
             tc_fence_before_sync();
             mbar_arrive(&bars->aE_full);
+            if (r == 0) S1_TRACE(9);
             // ---- stage D epilogue: v_a, v_b -> global -------------------------------------------------------------------------
             mbar_wait(&bars->d_full, ph_d);
             ph_d ^= 1;
             tc_fence_after_sync();
+            if (r == 0) S1_TRACE(10);
 #pragma unroll
             for (int c = 0; c < 32; c += 16) {
                 float v[16];
@@ -452,6 +488,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
             }
             tc_fence_before_sync();
             mbar_arrive(&bars->d_free);
+            if (r == 0) S1_TRACE(11);
         }
     }
     // ---- teardown -------------------------------------------------------------------------------------------------------
@@ -461,6 +498,13 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
 }
 
 }  // namespace
+
+static long long* g_s1_trace = nullptr;
+static int g_s1_trace_tiles = 0;
+void set_s1_trace(long long* buf, int tiles) {
+    g_s1_trace = buf;
+    g_s1_trace_tiles = tiles;
+}
 
 int launch_da_layer1_s(const genie_plan* p, const float* packed, const float* pfeat, const float* msrc,
                        const float* mask, float* zc, float* va, float* vb, cudaStream_t st) {
@@ -475,7 +519,8 @@ int launch_da_layer1_s(const genie_plan* p, const float* packed, const float* pf
     TimedLaunch tl(KID_DA_LAYER1_S, st);
     da_layer1_s_kernel<<<(unsigned)grid, S1_THREADS, SM_TOTAL, st>>>(packed, pfeat, msrc, mask, zc, va, vb, g.n_sta,
                                                                      g.n_sta_tiles, g.sta_tile_rows, g.sta_tile_meta,
-                                                                     g.sta_tile_nbr, g.sta_tile_invdeg, n_tiles);
+                                                                     g.sta_tile_nbr, g.sta_tile_invdeg, n_tiles,
+                                                                     g_s1_trace, g_s1_trace_tiles);
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;
 }

@@ -128,7 +128,11 @@ __global__ void __launch_bounds__(S2_THREADS, 1)
 
     if (warp < 4) {
         // ================================ producers: cp.async row gather ==============================================
+        // 64-byte rows: thread `tid` owns chunk c4 = tid & 3 of rows r4 + 32 j; 128-byte rows: chunk c8 = tid & 7 of rows
+        // r8 + 16 j.  The station ids of all its rows are fetched in one batch before the copies are issued.
         const int tid = threadIdx.x;
+        const int r4 = tid >> 2, c4 = tid & 3, r8 = tid >> 3, c8 = tid & 7;
+        constexpr int J4 = (ROWS + 31) / 32;
         for (int64_t q = 0; q < n_q; ++q) {
             const int k = (int)(q / NT), T = (int)(q - (int64_t)k * NT);
             const int g = blockIdx.x + k * gridDim.x;
@@ -136,23 +140,28 @@ __global__ void __launch_bounds__(S2_THREADS, 1)
             const int64_t n = q / N_WG;
             const int n_own = __ldg(tile_meta + 2 * T), n_rows = __ldg(tile_meta + 2 * T + 1);
             const int32_t* rows = tile_rows + (int64_t)T * ROWS;
+            int id4[J4], id8[8];
+#pragma unroll
+            for (int j = 0; j < J4; ++j) id4[j] = (r4 + 32 * j) < n_rows ? __ldg(rows + r4 + 32 * j) : -1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) id8[j] = (r8 + 16 * j) < n_own ? __ldg(rows + r8 + 16 * j) : -1;
             if (n > 0) mbar_wait(&bars->empty[b], (uint32_t)((n - 1) & 1));
             const uint32_t sb = smem_u32(smem + SM_BUF + b * SB_SIZE);
             const int64_t node0 = (int64_t)g * S;
-            for (int i = tid; i < n_rows * 4; i += 128) {
-                const int r = i >> 2, c = i & 3;
-                const int64_t node = node0 + __ldg(rows + r);
-                cp_async16(sb + SB_VA + r * 64 + c * 16, va + node * LD_V + c * 4);
+#pragma unroll
+            for (int j = 0; j < J4; ++j)
+                if (id4[j] >= 0) cp_async16(sb + SB_VA + (r4 + 32 * j) * 64 + c4 * 16, va + (node0 + id4[j]) * LD_V + c4 * 4);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r = r8 + 16 * j;
+                if (id8[j] >= 0)
+                    cp_async16(sb + SB_ZC + r * 128 + ((c8 ^ (r & 7)) << 4), zc + (node0 + id8[j]) * LD_ZC + c8 * 4);
             }
-            for (int i = tid; i < n_own * 8; i += 128) {
-                const int r = i >> 3, c = i & 7;
-                const int64_t node = node0 + __ldg(rows + r);
-                cp_async16(sb + SB_ZC + r * 128 + ((c ^ (r & 7)) << 4), zc + node * LD_ZC + c * 4);
-            }
-            for (int i = tid; i < n_own * 4; i += 128) {
-                const int r = i >> 2, c = i & 3;
-                const int64_t node = node0 + __ldg(rows + r);
-                cp_async16(sb + SB_M2 + r * 64 + ((c ^ ((r >> 1) & 3)) << 4), m2 + node * LD_V + c * 4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = r4 + 32 * j;
+                if (r < n_own)
+                    cp_async16(sb + SB_M2 + r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4), m2 + (node0 + id4[j]) * LD_V + c4 * 4);
             }
             cp_async_arrive_noinc(&bars->full[b]);
         }

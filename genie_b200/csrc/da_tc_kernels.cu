@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
     } else if (warp == WARP_MMA) {
         // ================================ MMA issuer ==================================================================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t wbase = smem_u32(sW);
             const uint32_t i64 = umma_idesc_tf32(128, 64), i32 = umma_idesc_tf32(128, 32);
             const uint32_t i96 = umma_idesc_tf32(128, 96), i16 = umma_idesc_tf32(128, 16);

@@ -138,6 +138,7 @@ bool split_supported(const genie_plan* p);
 int launch_src_mean(const genie_plan* p, int width, const float* X, float* out, const float* gate, cudaStream_t st);
 int launch_da_layer1_s(const genie_plan* p, const float* packed, const float* pfeat, const float* msrc,
                        const float* mask, float* zc, float* va, float* vb, cudaStream_t st);
+void set_s1_trace(long long* buf, int tiles);
 int launch_da_layer2_s(const genie_plan* p, const float* packed, const float* zc, const float* va, const float* m2,
                        const float* mask, const float* edge_attr, float* latent_out, float* out, int ld_out,
                        cudaStream_t st);

@@ -19,14 +19,18 @@ namespace {
 
 constexpr int SM_THREADS = 1024;
 
-// W = floats per row (32: layer-0 features p, 16: layer-2 messages v_b); SB = stations per slab (power of two)
+// W = floats per row (32: layer-0 features p, 16: layer-2 messages v_b); SB = stations per slab (even)
 template <int W, int SB>
 __global__ void __launch_bounds__(SM_THREADS, 1)
     src_mean_kernel(const float* __restrict__ X, float* __restrict__ out, int S, const int64_t* __restrict__ rowptr,
                     const int32_t* __restrict__ col, const int32_t* __restrict__ grp_ptr,
                     const int32_t* __restrict__ grp_nodes, int n_groups, int n_slabs, const float* __restrict__ gate) {
     if (gate != nullptr && *gate == 0.f) return;     // the one-pass kernels run instead (layout.h TCS_OK)
-    constexpr int LPR = W / 4;                       // lanes per row
+    constexpr int LPR = W / 4;                       // lanes (16-byte chunks) per row
+    constexpr int PAIRS = SB / 2;                    // every lane sums the same chunk of TWO consecutive stations
+    const float4* __restrict__ X4 = reinterpret_cast<const float4*>(X);
+    float4* __restrict__ O4 = reinterpret_cast<float4*>(out);
+    const uint32_t gstride = (uint32_t)S * LPR;      // float4 units between consecutive grid nodes (P * LPR < 2^32 checked)
     const int64_t n_tiles = (int64_t)n_groups * n_slabs;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int slab = (int)(t / n_groups);
@@ -34,40 +38,46 @@ __global__ void __launch_bounds__(SM_THREADS, 1)
         const int gbeg = __ldg(grp_ptr + grp);
         const int gcnt = __ldg(grp_ptr + grp + 1) - gbeg;
         const int s0 = slab * SB;
-        const int items = gcnt * SB * LPR;
+        const int items = gcnt * PAIRS * LPR;
         for (int i = threadIdx.x; i < items; i += SM_THREADS) {
             const int c = i % LPR;
-            const int row = i / LPR;
-            const int sl = row % SB;
-            const int gl = row / SB;
-            const int s = s0 + sl;
+            const int pr = (i / LPR) % PAIRS;
+            const int gl = i / (LPR * PAIRS);
+            const int s = s0 + 2 * pr;
             if (s >= S) continue;
+            const bool two = s + 1 < S;
             const int g = __ldg(grp_nodes + gbeg + gl);
-            const int64_t beg = __ldg(rowptr + g);
-            const int deg = (int)(__ldg(rowptr + g + 1) - beg);
-            const float4* __restrict__ base = reinterpret_cast<const float4*>(X) + (int64_t)s * LPR + c;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int j0 = 0; j0 < deg; j0 += 8) {
-                float4 v[8];
+            const int beg = (int)__ldg(rowptr + g);
+            const int deg = (int)__ldg(rowptr + g + 1) - beg;
+            const uint32_t off = (uint32_t)s * LPR + c;                   // chunk c of station s inside a grid node's block
+            const uint32_t off2 = two ? off + LPR : off;                  // same chunk of station s + 1 (clamped at the edge)
+            const int32_t* __restrict__ cp = col + beg;
+            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+            int j = 0;
+            for (; j + 5 <= deg; j += 5) {                                // k = 15 in-edges: three unmasked batches of five
+                float4 v0[5], v1[5];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    // absent edges re-read the first neighbour and are masked out of the sum (keeps all 8 loads in flight)
-                    const int j = min(j0 + u, deg - 1);
-                    const int gj = __ldg(col + beg + j);
-                    v[u] = __ldg(base + (int64_t)gj * S * LPR);
+                for (int u = 0; u < 5; ++u) {
+                    const uint32_t base = (uint32_t)__ldg(cp + j + u) * gstride;
+                    v0[u] = __ldg(X4 + (base + off));
+                    v1[u] = __ldg(X4 + (base + off2));
                 }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const float w = (j0 + u) < deg ? 1.f : 0.f;
-                    acc.x = fmaf(v[u].x, w, acc.x);
-                    acc.y = fmaf(v[u].y, w, acc.y);
-                    acc.z = fmaf(v[u].z, w, acc.z);
-                    acc.w = fmaf(v[u].w, w, acc.w);
+                for (int u = 0; u < 5; ++u) {
+                    a0.x += v0[u].x; a0.y += v0[u].y; a0.z += v0[u].z; a0.w += v0[u].w;
+                    a1.x += v1[u].x; a1.y += v1[u].y; a1.z += v1[u].z; a1.w += v1[u].w;
                 }
             }
+            for (; j < deg; ++j) {
+                const uint32_t base = (uint32_t)__ldg(cp + j) * gstride;
+                const float4 v0 = __ldg(X4 + (base + off)), v1 = __ldg(X4 + (base + off2));
+                a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+                a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+            }
             const float inv = deg > 0 ? 1.f / (float)deg : 0.f;
-            acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
-            __stcs(reinterpret_cast<float4*>(out) + ((int64_t)g * S + s) * LPR + c, acc);
+            const uint32_t o = (uint32_t)g * gstride + off;
+            __stcs(O4 + o, make_float4(a0.x * inv, a0.y * inv, a0.z * inv, a0.w * inv));
+            if (two) __stcs(O4 + (o + LPR), make_float4(a1.x * inv, a1.y * inv, a1.z * inv, a1.w * inv));
         }
     }
 }
@@ -78,7 +88,7 @@ bool split_supported(const genie_plan* p) {
     const genie_graph_desc_t& g = p->g;
     return g.mode == GENIE_GRAPH_CARTESIAN && g.n_sta_tiles > 0 && g.n_grid_groups > 0 && g.sta_tile_rows &&
            g.sta_tile_meta && g.sta_tile_nbr && g.sta_tile_invdeg && g.grid_grp_ptr && g.grid_grp_nodes && g.n_prod > 0 &&
-           g.n_prod < (int64_t)0x7fffff00;
+           g.n_prod < (int64_t)0x7fffff00 / 4;     // 32-bit float4 indices in the source pass
 }
 
 int launch_src_mean(const genie_plan* p, int width, const float* X, float* out, const float* gate, cudaStream_t st) {

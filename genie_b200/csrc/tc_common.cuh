@@ -10,6 +10,15 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a fully converged warp.  Code under `if (elect_one())` is known to the compiler to run in a single thread:
+// the uniform-datapath operands of tcgen05.mma / tcgen05.commit are then formed directly in uniform registers.  Under
+// `if (lane == 0)` it cannot know that and wraps EVERY such instruction in an elect/broadcast loop (~50 cycles each).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier --------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -48,8 +48,15 @@ def run(S, G, k_s, k_g, label):
     med, best = timed(lambda: ops.frontend_fwd(plan, packed, Slice, Mask, attr, pos, 30000.0, out=out))
     print('  front end (fused call): median %.3f ms best %.3f ms -> %.1f windows/s; 764 B/node => %.0f GB/s' % (
         med, best, 1e3 / med, 764.0 * P / med / 1e6), flush=True)
-    lib = capi.load()
-    ws = plan.workspace()
+    capi.timing_enable(True)
+    capi.timing_collect(reset=True)
+    for _ in range(3):
+        ops.frontend_fwd(plan, packed, Slice, Mask, attr, pos, 30000.0, out=out)
+    torch.cuda.synchronize()
+    for k, (ms, n) in sorted(capi.timing_collect(reset=True).items()):
+        if n:
+            print('    %-28s %8.3f ms x %d' % (k, ms / n, n // 3), flush=True)
+    capi.timing_enable(False)
     # stage by stage
     med1, _ = timed(lambda: ops.data_aggregation_fwd(plan, packed, Slice, Mask))
     print('  data_aggregation_fwd (K1+K2+K3 w/ latent store): %.3f ms' % med1, flush=True)
