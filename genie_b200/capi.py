@@ -17,7 +17,7 @@ _LIB_PATH = os.path.join(_HERE, 'libgenie_b200.so')
 _lib = None
 
 GRAPH_CARTESIAN, GRAPH_EXPLICIT = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_f32p = ctypes.c_void_p   # device pointers are passed as opaque addresses
 
@@ -33,7 +33,8 @@ class GraphDesc(ctypes.Structure):
                 ('n_sta_tiles', ctypes.c_int32), ('n_grid_groups', ctypes.c_int32),
                 ('sta_tile_rows', ctypes.c_void_p), ('sta_tile_meta', ctypes.c_void_p),
                 ('sta_tile_nbr', ctypes.c_void_p), ('sta_tile_invdeg', ctypes.c_void_p),
-                ('grid_grp_ptr', ctypes.c_void_p), ('grid_grp_nodes', ctypes.c_void_p)]
+                ('grid_grp_ptr', ctypes.c_void_p), ('grid_grp_nodes', ctypes.c_void_p),
+                ('n_grid_owned', ctypes.c_int32)]
 
 
 class Linear(ctypes.Structure):
@@ -86,6 +87,10 @@ SIGNATURES = {
     'genie_data_aggregation_fwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     'genie_bipartite_readin_fwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     'genie_spatial_aggregation_fwd': (ctypes.c_int, [_P, _P, ctypes.c_int32, _P, _P, ctypes.c_float, _P, _P, _P]),
+    'genie_da_layer1_fwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _P]),
+    'genie_workspace_region': (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p),
+                                              ctypes.POINTER(ctypes.c_size_t)]),
+    'genie_da_layer2_readin_fwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     'genie_frontend_fwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _P, ctypes.c_float, _P, _P, _P, _P, _P]),
 }
 

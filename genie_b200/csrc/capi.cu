@@ -205,6 +205,10 @@ int genie_plan_create(const genie_graph_desc_t* d, genie_plan_t** out) {
         set_error("genie_plan_create: missing product-graph row pointers");
         return GENIE_ERR_INVALID;
     }
+    if (d->n_grid_owned < 0 || d->n_grid_owned > d->n_grid || (d->n_grid_owned > 0 && d->mode != GENIE_GRAPH_CARTESIAN)) {
+        set_error("genie_plan_create: n_grid_owned must be in [0, n_grid] and needs CARTESIAN mode");
+        return GENIE_ERR_INVALID;
+    }
     if (d->n_grid > 0 && (!d->grid_rowptr || !d->grid_outdeg)) {
         set_error("genie_plan_create: missing grid-graph arrays");
         return GENIE_ERR_INVALID;
@@ -309,6 +313,40 @@ int genie_bipartite_readin_fwd(const genie_plan_t* plan, const float* packed_dev
                                       edge_attr_dev, mask_dev, w.xg, st)))
         return rc;
     return launch_readin_finalize(plan, packed_dev, w.xg, out_dev, 15, st);
+}
+
+int genie_da_layer1_fwd(const genie_plan_t* plan, const float* packed_dev, const float* slice_dev, const float* mask_dev,
+                        void* workspace_dev, void* stream) {
+    if (!plan || !packed_dev || !slice_dev || !mask_dev || !workspace_dev) {
+        set_error("genie_da_layer1_fwd: null argument");
+        return GENIE_ERR_INVALID;
+    }
+    Workspace w = carve_workspace(plan, workspace_dev);
+    return launch_da_layers01(plan, packed_dev, slice_dev, mask_dev, w, static_cast<cudaStream_t>(stream));
+}
+
+int genie_workspace_region(const genie_plan_t* plan, void* workspace_dev, int32_t which, void** ptr_out,
+                           size_t* bytes_out) {
+    if (!plan || !workspace_dev || !ptr_out || !bytes_out || which != GENIE_WS_VB) {
+        set_error("genie_workspace_region: bad argument");
+        return GENIE_ERR_INVALID;
+    }
+    Workspace w = carve_workspace(plan, workspace_dev);
+    *ptr_out = w.vb;
+    *bytes_out = (size_t)plan->g.n_prod * LD_V * sizeof(float);
+    return GENIE_OK;
+}
+
+int genie_da_layer2_readin_fwd(const genie_plan_t* plan, const float* packed_dev, const float* mask_dev,
+                               const float* edge_attr_dev, float* x_latent_out_dev, float* readin_out_dev,
+                               void* workspace_dev, void* stream) {
+    if (!plan || !packed_dev || !mask_dev || !edge_attr_dev || !readin_out_dev || !workspace_dev) {
+        set_error("genie_da_layer2_readin_fwd: null argument");
+        return GENIE_ERR_INVALID;
+    }
+    Workspace w = carve_workspace(plan, workspace_dev);
+    return launch_da_layer2(plan, packed_dev, w, mask_dev, edge_attr_dev, x_latent_out_dev, readin_out_dev, 15,
+                            static_cast<cudaStream_t>(stream));
 }
 
 int genie_spatial_aggregation_fwd(const genie_plan_t* plan, const float* packed_dev, int32_t layer, const float* x_dev,

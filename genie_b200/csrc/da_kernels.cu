@@ -439,7 +439,7 @@ int launch_da_layer2_readin(const genie_plan* p, const float* packed, int mode, 
 
 int launch_readin_finalize(const genie_plan* p, const float* packed, const float* xg, float* out, int ld_out,
                            cudaStream_t st) {
-    const int G = p->g.n_grid;
+    const int G = p->g.n_grid_owned > 0 ? p->g.n_grid_owned : p->g.n_grid;     // halo grid nodes have no read-in row
     if (G == 0) return GENIE_OK;
     TimedLaunch tl(KID_READIN_FINALIZE, st);
     readin_finalize_kernel<<<(G + 127) / 128, 128, 0, st>>>(packed, xg, out, ld_out, G);

@@ -509,7 +509,7 @@ void set_s1_trace(long long* buf, int tiles) {
 int launch_da_layer1_s(const genie_plan* p, const float* packed, const float* pfeat, const float* msrc,
                        const float* mask, float* zc, float* va, float* vb, cudaStream_t st) {
     const genie_graph_desc_t& g = p->g;
-    const int64_t n_tiles = (int64_t)g.n_sta_tiles * g.n_grid;
+    const int64_t n_tiles = (int64_t)g.n_sta_tiles * (g.n_grid_owned > 0 ? g.n_grid_owned : g.n_grid);
     static bool attr_set = false;
     if (!attr_set) {
         GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer1_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));

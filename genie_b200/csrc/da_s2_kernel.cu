@@ -312,16 +312,17 @@ int launch_da_layer2_s(const genie_plan* p, const float* packed, const float* zc
         GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer2_s_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
         attr_set = true;
     }
-    const unsigned grid = (unsigned)(g.n_grid < p->sm_count ? g.n_grid : p->sm_count);
+    const int n_own = g.n_grid_owned > 0 ? g.n_grid_owned : g.n_grid;
+    const unsigned grid = (unsigned)(n_own < p->sm_count ? n_own : p->sm_count);
     TimedLaunch tl(KID_DA_LAYER2_S, st);
     if (latent_out)
         da_layer2_s_kernel<true><<<grid, S2_THREADS, SM_TOTAL, st>>>(packed, zc, va, m2, mask, edge_attr, latent_out, out,
-                                                                     ld_out, g.n_sta, g.n_grid, g.n_sta_tiles,
+                                                                     ld_out, g.n_sta, n_own, g.n_sta_tiles,
                                                                      g.sta_tile_rows, g.sta_tile_meta, g.sta_tile_nbr,
                                                                      g.sta_tile_invdeg);
     else
         da_layer2_s_kernel<false><<<grid, S2_THREADS, SM_TOTAL, st>>>(packed, zc, va, m2, mask, edge_attr, nullptr, out,
-                                                                      ld_out, g.n_sta, g.n_grid, g.n_sta_tiles,
+                                                                      ld_out, g.n_sta, n_own, g.n_sta_tiles,
                                                                       g.sta_tile_rows, g.sta_tile_meta, g.sta_tile_nbr,
                                                                       g.sta_tile_invdeg);
     GENIE_LAUNCH_CHECK();

@@ -131,6 +131,41 @@ def frontend_fwd(plan, packed, Slice, Mask, edge_attr, pos, scale_rel, want_late
     return x_spatial, latent, readin
 
 
+# ---- the front end in two halves (grid-sharded plans, genie_b200/sharded.py) -----------------------------------------------
+
+def da_layer1_fwd(plan, packed, Slice, Mask):
+    """DataAggregation up to the layer-2 messages (module.py:88-93); results stay in the plan's workspace."""
+    Slice, Mask = _f32c(Slice, 'Slice'), _f32c(Mask, 'Mask')
+    if Slice.shape != (plan.n_prod, 4) or Mask.shape != (plan.n_prod, 4):
+        raise capi.GenieError('Slice/Mask must be [P,4] with P = %d' % plan.n_prod)
+    with torch.cuda.device(plan.device):
+        capi.check(capi.load().genie_da_layer1_fwd(plan.handle, capi.dptr(packed, F32), capi.dptr(Slice, F32),
+                                                   capi.dptr(Mask, F32), capi.dptr(plan.workspace()),
+                                                   capi.stream_ptr(plan.device)))
+
+
+def message_rows(plan):
+    """View [n_grid, n_sta * 16] of the layer-2 source messages v_b inside the workspace (one row per grid node)."""
+    ws = plan.workspace()
+    ptr, nbytes = ctypes.c_void_p(), ctypes.c_size_t()
+    capi.check(capi.load().genie_workspace_region(plan.handle, capi.dptr(ws), 0, ctypes.byref(ptr), ctypes.byref(nbytes)))
+    off = ptr.value - ws.data_ptr()
+    return ws[off:off + nbytes.value].view(F32).view(plan.n_grid, plan.n_sta * 16)
+
+
+def da_layer2_readin_fwd(plan, packed, Mask, edge_attr, want_latent=False):
+    """Rest of DataAggregation (module.py:94-98) + Bipartite_ReadIn (module.py:224-229) for the owned grid nodes."""
+    Mask, edge_attr = _f32c(Mask, 'Mask'), _f32c(edge_attr, 'attr')
+    n_own = plan.n_grid_owned or plan.n_grid
+    out = torch.empty((n_own, 15), dtype=F32, device=plan.device)
+    latent = torch.empty((plan.n_prod, 30), dtype=F32, device=plan.device) if want_latent else None
+    with torch.cuda.device(plan.device):
+        capi.check(capi.load().genie_da_layer2_readin_fwd(plan.handle, capi.dptr(packed, F32), capi.dptr(Mask, F32),
+                                                          capi.dptr(edge_attr, F32), capi.dptr(latent), capi.dptr(out),
+                                                          capi.dptr(plan.workspace()), capi.stream_ptr(plan.device)))
+    return out, latent
+
+
 # ---- a1 ----------------------------------------------------------------------------------------------------------------
 
 def input_params(t0, max_t, kernel_sig_t, dt, n_locs, n_sta_use):

@@ -166,8 +166,9 @@ class GraphPlan(object):
     """Owns the device index arrays and the C-side plan handle (genie_plan_t)."""
 
     def __init__(self, mode, n_sta, n_grid, n_prod, sta, src, grid, grid_outdeg, prod_grid, device, grid_order=None,
-                 tiling=True, group_size=GROUP_SIZE):
+                 tiling=True, group_size=GROUP_SIZE, n_grid_owned=0):
         self.mode, self.n_sta, self.n_grid, self.n_prod = mode, int(n_sta), int(n_grid), int(n_prod)
+        self.n_grid_owned = int(n_grid_owned)          # grid sharding: nodes >= n_grid_owned are halo copies (0 = none)
         self.device = torch.device(device)
         self.sta_max_deg, self.grid_order = 0, None
         if mode == capi.GRAPH_CARTESIAN and n_sta > 0 and n_grid > 0:
@@ -185,6 +186,12 @@ class GraphPlan(object):
             st = station_tiles(sta[0], sta[1], self.n_sta)
             if st is not None:
                 gp, gn = bisection_groups(src[0], src[1], self.n_grid, int(group_size))
+                if self.n_grid_owned:                       # halo nodes are gathered FROM, never computed: drop them
+                    keep = gn < self.n_grid_owned
+                    cnt = np.add.reduceat(keep.astype(np.int64), gp[:-1]) if len(gp) > 1 else np.zeros(0, np.int64)
+                    cnt = cnt[cnt > 0]
+                    gn = gn[keep]
+                    gp = np.concatenate(([0], np.cumsum(cnt))).astype(np.int32)
                 put = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
                 self.tiles = dict(n_tiles=int(st['meta'].shape[0]), n_groups=int(len(gp) - 1), tile=int(st['tile']),
                                   rows=put(st['rows']), meta=put(st['meta']),
@@ -216,6 +223,7 @@ class GraphPlan(object):
             d.sta_tile_invdeg = capi.dptr(t['invdeg'], torch.float32, 'sta_tile_invdeg')
             d.grid_grp_ptr = capi.dptr(t['grp_ptr'], torch.int32, 'grid_grp_ptr')
             d.grid_grp_nodes = capi.dptr(t['grp_nodes'], torch.int32, 'grid_grp_nodes')
+        d.n_grid_owned = self.n_grid_owned
         self._desc = d
         lib = capi.load()
         handle = ctypes.c_void_p()
@@ -248,7 +256,7 @@ class GraphPlan(object):
 
     @classmethod
     def cartesian(cls, A_sta_sta, A_src_src, n_sta, n_grid, A_src=None, device=None, grid_order=None, tiling=True,
-                  group_size=GROUP_SIZE):
+                  group_size=GROUP_SIZE, n_grid_owned=0):
         """Dense mode from the two small kNN graphs (process_utils.py:718-719); product edges stay implicit."""
         device = torch.device(device if device is not None else A_sta_sta.device)
         A_sta_sta, A_src_src = A_sta_sta.to(device), A_src_src.to(device)
@@ -260,7 +268,16 @@ class GraphPlan(object):
         else:
             grid, outdeg = cls._grid_parts(A_src.to(device), n_grid)
         return cls(capi.GRAPH_CARTESIAN, n_sta, n_grid, n_sta * n_grid, sta, src, grid, outdeg, None, device,
-                   grid_order=grid_order, tiling=tiling, group_size=group_size)
+                   grid_order=grid_order, tiling=tiling, group_size=group_size, n_grid_owned=n_grid_owned)
+
+    @classmethod
+    def grid_only(cls, A_src, n_grid, device):
+        """A plan with no product nodes: only the grid graph of SpatialAggregation (module.py:243)."""
+        device = torch.device(device)
+        empty = torch.zeros((2, 0), dtype=torch.long, device=device)
+        grid, outdeg = cls._grid_parts(A_src.to(device), n_grid)
+        return cls(capi.GRAPH_EXPLICIT, 0, n_grid, 0, csr_by_destination(empty, 0), csr_by_destination(empty, 0), grid,
+                   outdeg, torch.zeros(0, dtype=torch.int32, device=device), device)
 
     @classmethod
     def explicit(cls, A_in_sta, A_in_src, prod_target, A_src, n_prod, n_grid, device=None):

@@ -1,0 +1,154 @@
+"""Grid sharding of the product-graph front end over the GPUs of one node (BASELINE.json configs[4]).
+
+The reference runs on one device (`module.py:2`); it has no counterpart of this file.  For networks whose node features
+exceed one GPU (2000 stations x 200000 grid nodes = 4e8 product nodes) the grid nodes are dealt to the ranks:
+
+* `GridPartition` — every rank computes the same partition on the host: the compact grid-node groups of
+  `plan.bisection_groups` (depth-first order, spatially coherent) are assigned to ranks in contiguous runs of about equal
+  node counts.  A rank's local grid = its owned nodes followed by the 1-hop halo of their source-graph in-neighbours.
+* `ShardedFrontEnd.forward` — per window:
+    1. layer 0 + 1 of DataAggregation on the local grid (inputs of halo nodes are computed locally: Slice/Mask are cheap,
+       so layer 0 needs no exchange; layer 1 is only computed for owned nodes),
+    2. ONE exchange: the layer-2 message rows of halo nodes are fetched from their owners (`all_to_all_single`, NCCL over
+       NVLink; S x 64 B per halo grid node),
+    3. layer 2 + Bipartite_ReadIn for the owned nodes (a grid node's stations all live on its rank, so the sum over stations
+       never crosses shards: no all-reduce of station partials is needed in this layout),
+    4. all-gather of the `[G,15]` read-in rows; SpatialAggregation x3 (0.1 % of the work) runs replicated on every rank.
+The compute steps go through a backend object; the product backend is `CudaBackend` (C-ABI kernels).  Tests substitute a CPU
+backend to check the partition / exchange logic with world_size 2 over gloo.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .plan import GROUP_SIZE, bisection_groups, csr_by_destination
+
+
+class GridPartition(object):
+    """Deterministic assignment of grid nodes to ranks + the halo / exchange index lists of every rank (host side)."""
+
+    def __init__(self, A_src_src, n_grid, world, group_size=GROUP_SIZE):
+        self.n_grid, self.world = int(n_grid), int(world)
+        rowptr, col = csr_by_destination(A_src_src.cpu(), n_grid)
+        self.rowptr, self.col = rowptr.numpy(), col.numpy().astype(np.int64)
+        gp, gn = bisection_groups(self.rowptr, self.col, n_grid, group_size)
+        # contiguous runs of groups with ~ n_grid / world nodes each
+        bounds = np.searchsorted(gp, np.arange(1, world) * (n_grid / float(world)), side='left')
+        bounds = np.concatenate(([0], np.clip(bounds, 0, len(gp) - 1), [len(gp) - 1]))
+        self.owned = [np.ascontiguousarray(gn[gp[bounds[r]]:gp[bounds[r + 1]]].astype(np.int64)) for r in range(world)]
+        self.owner = np.empty(n_grid, dtype=np.int64)
+        for r in range(world):
+            self.owner[self.owned[r]] = r
+        self.halo = []
+        for r in range(world):
+            nb = np.unique(np.concatenate([self.col[self.rowptr[g]:self.rowptr[g + 1]] for g in self.owned[r]]
+                                          or [np.zeros(0, np.int64)]))
+            nb = nb[self.owner[nb] != r]
+            self.halo.append(nb[np.lexsort((nb, self.owner[nb]))])             # grouped by owner, ascending id inside
+
+    def local_nodes(self, rank):
+        """Global ids of the local grid of `rank`: owned nodes first, then the halo."""
+        return np.concatenate((self.owned[rank], self.halo[rank]))
+
+    def local_graph(self, rank):
+        """Source graph restricted to the local grid (local ids): in-edges of owned nodes only; halo rows are empty."""
+        nodes = self.local_nodes(rank)
+        g2l = -np.ones(self.n_grid, dtype=np.int64)
+        g2l[nodes] = np.arange(len(nodes))
+        own = self.owned[rank]
+        deg = self.rowptr[own + 1] - self.rowptr[own]
+        tgt = np.repeat(np.arange(len(own)), deg)
+        src = g2l[np.concatenate([self.col[self.rowptr[g]:self.rowptr[g + 1]] for g in own] or [np.zeros(0, np.int64)])]
+        assert (src >= 0).all()
+        return torch.from_numpy(np.stack((src, tgt), axis=0)).long()
+
+    def exchange_lists(self, rank):
+        """(send_rows, send_counts, recv_counts): local row ids (owned part) this rank sends, ordered by destination rank
+        and, per destination, in the order of that rank's halo list; counts per peer."""
+        g2l = -np.ones(self.n_grid, dtype=np.int64)
+        g2l[self.owned[rank]] = np.arange(len(self.owned[rank]))
+        send, send_counts = [], []
+        for q in range(self.world):
+            want = self.halo[q][self.owner[self.halo[q]] == rank] if q != rank else np.zeros(0, np.int64)
+            send.append(g2l[want])
+            send_counts.append(len(want))
+        recv_counts = [int((self.owner[self.halo[rank]] == q).sum()) for q in range(self.world)]
+        return np.concatenate(send), send_counts, recv_counts
+
+
+class CudaBackend(object):
+    """The product compute path: libgenie_b200 kernels on the local plan (see include/genie_b200.h)."""
+
+    def __init__(self, model, A_sta_sta, A_src_local, n_sta, n_local, n_owned, read_in_attr_local, A_src_global, n_grid,
+                 device):
+        from .plan import GraphPlan
+        self.model, self.device = model, torch.device(device)
+        self.plan = GraphPlan.cartesian(A_sta_sta, A_src_local, n_sta, n_local, device=device, n_grid_owned=n_owned)
+        self.plan_grid = GraphPlan.grid_only(A_src_global, n_grid, device)
+        self.attr = read_in_attr_local.to(device).float().contiguous()
+        self._mask = None
+
+    def layer1(self, Slice, Mask):
+        from . import ops
+        self._mask = Mask
+        ops.da_layer1_fwd(self.plan, self.model._packed_weights(self.device), Slice, Mask)
+
+    def message_rows(self):
+        from . import ops
+        return ops.message_rows(self.plan)
+
+    def layer2_readin(self):
+        from . import ops
+        return ops.da_layer2_readin_fwd(self.plan, self.model._packed_weights(self.device), self._mask, self.attr)[0]
+
+    def spatial(self, read_in, pos, scale_rel):
+        from . import ops
+        packed = self.model._packed_weights(self.device)
+        x = read_in
+        for layer in range(3):
+            x = ops.spatial_aggregation_fwd(self.plan_grid, packed, layer, x, pos, scale_rel)
+        return x
+
+
+class ShardedFrontEnd(object):
+    """DataAggregation -> Bipartite_ReadIn -> SpatialAggregation x3 with the grid nodes sharded over the process group."""
+
+    def __init__(self, partition, rank, backend, device, group=None):
+        self.part, self.rank, self.backend, self.group = partition, int(rank), backend, group
+        self.device = torch.device(device)
+        self.n_owned = len(partition.owned[rank])
+        send_rows, self.send_counts, self.recv_counts = partition.exchange_lists(rank)
+        self.send_rows = torch.from_numpy(send_rows).to(self.device)
+        self.max_owned = max(len(o) for o in partition.owned)
+        order = np.concatenate([np.concatenate((o, -np.ones(self.max_owned - len(o), dtype=np.int64)))
+                                for o in partition.owned])
+        keep = order >= 0
+        inv = np.empty(partition.n_grid, dtype=np.int64)
+        inv[order[keep]] = np.nonzero(keep)[0]
+        self.gather_index = torch.from_numpy(inv).to(self.device)          # global node -> row of the padded all-gather
+
+    def exchange(self, rows):
+        """rows [n_local, W]: fills the halo part (rows >= n_owned) from the owners' copies."""
+        send = rows.index_select(0, self.send_rows).contiguous()
+        recv = rows[self.n_owned:]
+        if recv.shape[0] != sum(self.recv_counts):
+            raise RuntimeError('halo size mismatch')
+        W = rows.shape[1]
+        out = torch.empty((sum(self.recv_counts), W), dtype=rows.dtype, device=rows.device)
+        dist.all_to_all_single(out, send, output_split_sizes=self.recv_counts, input_split_sizes=self.send_counts,
+                               group=self.group)
+        recv.copy_(out)
+        return send.numel() * send.element_size()
+
+    def forward(self, Slice_local, Mask_local, pos_grid, scale_rel):
+        """Slice/Mask of the LOCAL product nodes ([n_local * S, 4], owned grid nodes first) -> x_spatial [G,30] (replicated)."""
+        be = self.backend
+        be.layer1(Slice_local, Mask_local)
+        self.exchange(be.message_rows())
+        r_own = be.layer2_readin()                                           # [n_owned, 15]
+        pad = torch.zeros((self.max_owned, r_own.shape[1]), dtype=r_own.dtype, device=r_own.device)
+        pad[:self.n_owned] = r_own
+        allr = torch.empty((self.part.world * self.max_owned, r_own.shape[1]), dtype=r_own.dtype, device=r_own.device)
+        dist.all_gather_into_tensor(allr, pad, group=self.group)
+        read_in = allr.index_select(0, self.gather_index)                    # [G,15] in global node order
+        return be.spatial(read_in, pos_grid, scale_rel), read_in

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GENIE_B200_ABI_VERSION 2
+#define GENIE_B200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define GENIE_API __attribute__((visibility("default")))
@@ -87,6 +87,10 @@ typedef struct genie_graph_desc {
     const float* sta_tile_invdeg;
     const int32_t* grid_grp_ptr;
     const int32_t* grid_grp_nodes;
+    /* Grid sharding (CARTESIAN only): the first n_grid_owned grid nodes are owned by this rank, the remaining ones are
+     * halo copies of other ranks' nodes (their inputs are present, their layer-1 outputs arrive by exchange: see
+     * genie_da_layer1_fwd).  0 = all n_grid nodes are owned.  grid_grp_nodes must then list owned nodes only. */
+    int32_t n_grid_owned;
 } genie_graph_desc_t;
 
 #define GENIE_TILE_ROWS_MAX 288
@@ -190,6 +194,21 @@ GENIE_API int genie_frontend_fwd(const genie_plan_t* plan, const float* packed_d
                        const float* mask_dev, const float* edge_attr_dev, const float* pos_dev, float scale_rel,
                        float* x_latent_out_dev, float* readin_out_dev, float* x_spatial_out_dev,
                        void* workspace_dev, void* stream);
+
+/* ---- the same front end in two halves, for grid-sharded plans (genie_b200/sharded.py) ----------------------------------
+ * genie_da_layer1_fwd runs DataAggregation up to the layer-2 messages (module.py:88-93) and leaves them in the workspace;
+ * genie_workspace_region exposes the message rows v_b (`which` = GENIE_WS_VB: fp32 [n_prod,16], one row per product node)
+ * so that the caller can fill the rows of its halo grid nodes from their owners (NCCL all-to-all);
+ * genie_da_layer2_readin_fwd then finishes DataAggregation (module.py:94-98) and applies Bipartite_ReadIn
+ * (module.py:224-229) for the owned grid nodes: readin_out_dev fp32 [n_grid_owned,15], x_latent_out_dev optional. */
+enum { GENIE_WS_VB = 0 };
+GENIE_API int genie_da_layer1_fwd(const genie_plan_t* plan, const float* packed_dev, const float* slice_dev,
+                                  const float* mask_dev, void* workspace_dev, void* stream);
+GENIE_API int genie_workspace_region(const genie_plan_t* plan, void* workspace_dev, int32_t which, void** ptr_out,
+                                     size_t* bytes_out);
+GENIE_API int genie_da_layer2_readin_fwd(const genie_plan_t* plan, const float* packed_dev, const float* mask_dev,
+                                         const float* edge_attr_dev, float* x_latent_out_dev, float* readin_out_dev,
+                                         void* workspace_dev, void* stream);
 
 /* ---- misc ---------------------------------------------------------------------------------------------------------- */
 GENIE_API const char* genie_last_error(void);

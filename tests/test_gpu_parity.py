@@ -289,3 +289,47 @@ def test_config2_against_oracle():
     assert rel_err(lat.cpu().numpy(), parts['x_latent'].numpy()) < TOL
     assert rel_err(r.cpu().numpy(), parts['read_in'].numpy()) < TOL
     assert rel_err(xs.cpu().numpy(), want.numpy()) < TOL
+
+
+def test_sharded_front_end_single_process():
+    """Grid sharding with the product backend (genie_b200.sharded.CudaBackend): two ranks emulated one after the other on
+    one GPU (the halo exchange done by hand from GridPartition's lists) must reproduce the unsharded front end."""
+    from genie_b200 import ops
+    from genie_b200.plan import GraphPlan
+    from genie_b200.sharded import CudaBackend, GridPartition
+    from oracle import genie_oracle as go
+    dev = _dev()
+    S, G, world = 160, 900, 2
+    net, A_sta, A_src, Slice, Mask, attr = _random_case(S, G, 15, 15, 41, dev)
+    sd = go.init_state(seed=7)
+    from genie_b200.module import GCN_Detection_Network_extended
+    m = GCN_Detection_Network_extended(None, None, device=dev)
+    m.load_state_dict(sd, strict=False)
+    grid = torch.from_numpy(net.grid).float().to(dev)
+    plan = GraphPlan.cartesian(A_sta, A_src, S, G, device=dev)
+    want_xs, _, want_r = ops.frontend_fwd(plan, m._packed_weights(dev), Slice.to(dev), Mask.to(dev), attr.to(dev), grid,
+                                          30000.0, want_readin=True)
+    part = GridPartition(A_src, G, world)
+    bes, nodes = [], []
+    for r in range(world):
+        nd = torch.from_numpy(part.local_nodes(r))
+        loc = lambda x: x.view(G, S, -1).index_select(0, nd).reshape(len(nd) * S, -1).contiguous().to(dev)
+        be = CudaBackend(m, A_sta, part.local_graph(r), S, len(nd), len(part.owned[r]), loc(attr), A_src, G, dev)
+        assert be.plan.tiles is not None and be.plan.n_grid_owned == len(part.owned[r])
+        be.layer1(loc(Slice), loc(Mask))
+        bes.append(be)
+        nodes.append(nd)
+    rows = [be.message_rows() for be in bes]
+    g2l = [{int(g): i for i, g in enumerate(nd.tolist())} for nd in nodes]
+    for r in range(world):                                   # what all_to_all_single does in ShardedFrontEnd.exchange
+        n_own = len(part.owned[r])
+        rows[r][n_own:] = float('nan')
+        for i, g in enumerate(part.halo[r].tolist()):
+            q = int(part.owner[g])
+            rows[r][n_own + i] = rows[q][g2l[q][g]]
+    read_in = torch.empty((G, 15), device=dev)
+    for r in range(world):
+        read_in[torch.from_numpy(part.owned[r]).to(dev)] = bes[r].layer2_readin()
+    assert rel_err(read_in.cpu().numpy(), want_r.cpu().numpy()) < 1e-5
+    xs = bes[0].spatial(read_in, grid, 30000.0)
+    assert rel_err(xs.cpu().numpy(), want_xs.cpu().numpy()) < 1e-5
