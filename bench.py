@@ -37,6 +37,9 @@ WORKLOADS = {
     'c4_1000x50000_dense': (1000, 50000, 15, 15),
     'c2_100x5000_dense': (100, 5000, 15, 15),
     'c1_10x100_dense': (10, 100, 8, 15),
+    # grid-sharded over the ranks (genie_b200/sharded.py): every window is computed cooperatively, needs --gpus >= 2
+    'c5_2000x200000_sharded': (2000, 200000, 15, 15),
+    'c5s_1000x20000_sharded': (1000, 20000, 15, 15),
 }
 KERNEL_SIG_T, DT, STEP_S, N_QUERY, SCALE_REL = 3.0, 0.3, 3.0, 10000, 30000.0
 DAY_S = 86400.0
@@ -249,6 +252,82 @@ class Workload(object):
         return (hi - lo) * 5 * 8, (y.numel() + x.numel()) * 4
 
 
+class ShardedWorkload(object):
+    """One network sharded by grid nodes over all ranks (BASELINE.json configs[4]); same interface as Workload."""
+
+    def __init__(self, name, dev, rank, world, day_s=DAY_S):
+        import torch
+        from genie_b200 import synth
+        from genie_b200.module import GCN_Detection_Network_extended
+        from genie_b200.process_utils import InputExtractor, extract_inputs_adjacencies_cartesian
+        from genie_b200.sharded import CudaBackend, GridPartition, ShardedFrontEnd
+        S, G, k_s, k_g = WORKLOADS[name]
+        self.S, self.G, self.dev, self.rank = S, G, dev, rank
+        net = synth.Network(S, G, seed=0)
+        A_sta, A_src = extract_inputs_adjacencies_cartesian(net.sta, net.grid, k_s, k_g)
+        part = GridPartition(A_src, G, world)
+        nodes = part.local_nodes(rank)
+        self.n_local, self.n_owned = len(nodes), len(part.owned[rank])
+        self.P = S * G                                            # whole-job product nodes
+        sta_d = torch.from_numpy(net.sta).to(dev)
+        grid_d = torch.from_numpy(net.grid).to(dev)
+        loc_d = grid_d[torch.from_numpy(nodes).to(dev)]
+        trv = torch.empty((self.n_local, S, 2), dtype=torch.float32, device=dev)
+        attr = torch.empty((self.n_local * S, 3), dtype=torch.float32, device=dev)
+        for lo in range(0, self.n_local, 4096):
+            hi = min(self.n_local, lo + 4096)
+            diff = loc_d[lo:hi, None, :] - sta_d[None, :, :]
+            d = diff.norm(dim=2)
+            trv[lo:hi, :, 0] = (d / synth.VP).float()
+            trv[lo:hi, :, 1] = (d / synth.VS).float()
+            attr[lo * S:hi * S] = (diff / SCALE_REL).reshape(-1, 3).float()
+        torch.manual_seed(2)
+        self.model = GCN_Detection_Network_extended(None, None, scale_rel=SCALE_REL, device=dev).eval()
+        be = CudaBackend(self.model, A_sta, part.local_graph(rank), S, self.n_local, self.n_owned, attr, A_src, G, dev)
+        self.fe = ShardedFrontEnd(part, rank, be, dev)
+        self.halo_rows = [len(h) for h in part.halo]
+        self.max_t = net.max_moveout()
+        self.ex = InputExtractor(be.plan, trv, np.arange(S), S, self.max_t, KERNEL_SIG_T, DT)
+        self.picks = synth.make_picks(net, 0.0, day_s, seed=1)
+        self.ex.set_day(self.picks)
+        self.grid = grid_d.float().contiguous()
+        self.xq = torch.from_numpy(_query_points(net, N_QUERY)).float().to(dev)
+        self.tq = torch.arange(-3.0, 3.01, 0.75, device=dev).reshape(-1, 1)
+        self.n_windows = int((day_s - self.max_t) // STEP_S)
+        self.picks_host = torch.from_numpy(self.ex._day[1].cpu().numpy()).pin_memory()
+        self.y_host = torch.empty((G, self.tq.shape[0], 1), dtype=torch.float32).pin_memory()
+        self.x_host = torch.empty((N_QUERY, self.tq.shape[0], 1), dtype=torch.float32).pin_memory()
+
+    def _window(self, Slice, Mask):
+        import torch
+        m = self.model
+        with torch.no_grad():
+            x_spatial, _ = self.fe.forward(Slice, Mask, self.grid, SCALE_REL)
+            if self.rank != 0:                      # the read-out heads are per grid node / query point: rank 0 emits them
+                return None, None
+            y = m.TemporalAttention(m.SpatialDirect(x_spatial), self.tq)
+            x = m.TemporalAttention(m.SpatialAttention(x_spatial, self.xq, self.grid), self.tq)
+        return y, x
+
+    def window_resident(self, w):
+        Slice, Mask = self.ex(w * STEP_S)
+        return self._window(Slice, Mask)
+
+    def window_e2e(self, w):
+        import torch
+        lo, hi = self.ex.window_rows(w * STEP_S)
+        picks = self.picks_host[lo:hi].to(self.dev, non_blocking=True)
+        Slice, Mask = self.ex(w * STEP_S, picks)
+        y, x = self._window(Slice, Mask)
+        d2h = 0
+        if y is not None:
+            self.y_host.copy_(y, non_blocking=True)
+            self.x_host.copy_(x, non_blocking=True)
+            d2h = (y.numel() + x.numel()) * 4
+        torch.cuda.current_stream().synchronize()
+        return (hi - lo) * 5 * 8, d2h
+
+
 def run_genie(args):
     import torch
     import torch.distributed as dist
@@ -264,12 +343,22 @@ def run_genie(args):
         dist.init_process_group('nccl', device_id=dev)
     S, G, k_s, k_g = WORKLOADS[args.workload]
     t_setup = time.time()
-    wl = Workload(args.workload, dev, day_s=args.day_seconds)
+    sharded = args.workload.endswith('_sharded')
+    if sharded:
+        if world < 2:
+            raise RuntimeError('bench.py: %s is the grid-sharded workload, launch it with --gpus >= 2' % args.workload)
+        wl = ShardedWorkload(args.workload, dev, rank, world, day_s=args.day_seconds)
+        # every rank works on the SAME window (its shard of the grid): fixed total work, strong scaling
+        windows = [i % wl.n_windows for i in range(2 * (args.steps + args.warmup))]
+        units = 1
+    else:
+        wl = Workload(args.workload, dev, day_s=args.day_seconds)
+        # rank r streams windows r, r + world, ...: windows are independent, no data-path collective
+        windows = [(rank + i * world) % wl.n_windows for i in range(2 * (args.steps + args.warmup))]
+        units = world
     torch.cuda.synchronize()
     t_setup = time.time() - t_setup
     K, W = args.steps, args.warmup
-    # rank r streams windows r, r + world, ...: windows are independent, no data-path collective
-    windows = [(rank + i * world) % wl.n_windows for i in range(2 * (K + W))]
 
     def barrier():
         if world > 1:
@@ -319,29 +408,37 @@ def run_genie(args):
         t = torch.tensor([ms, ms2], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms2 = float(t[0]), float(t[1])
-        cnt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        cnt = torch.tensor([launches, h2d, d2h], dtype=torch.int64, device=dev)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         launches = int(cnt[0])
+        if sharded:
+            h2d, d2h = int(cnt[1]), int(cnt[2])
     if rank == 0:
         peak, peak_src = _peaks()
         timed = {k: v for k, v in kt.items() if v[1] > 0}
         dom = max(timed, key=lambda k: timed[k][0])
         dom_ms = timed[dom][0] / timed[dom][1]
-        dom_bytes = BYTES_PER_NODE_KERNEL.get(dom, BYTES_PER_NODE_WINDOW) * wl.P
+        launch_nodes = wl.n_owned * wl.S if sharded else wl.P          # product nodes one launch (rank 0) processes
+        dom_bytes = BYTES_PER_NODE_KERNEL.get(dom, BYTES_PER_NODE_WINDOW) * launch_nodes
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
         kernel_total = sum(v[0] for v in timed.values())
         line = {
-            'metric': METRIC, 'value': world * K / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
-            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'metric': METRIC if not sharded else 'time-windows/sec, %d stations x %d grid nodes sharded over the GPUs' % (S, G),
+            'value': units * K / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'strong' if sharded else 'weak',
+            'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
             'config': {'workload': args.workload, 'stations': S, 'grid_nodes': G, 'product_nodes': S * G, 'k_sta': k_s,
                        'k_grid': k_g, 'kernel_sig_t': KERNEL_SIG_T, 'dt': DT, 'window_step_s': STEP_S,
                        'n_query': N_QUERY, 'n_t_query': 9, 'picks_resident': int(wl.picks.shape[0]),
-                       'parallelism': 'windows round-robin over %d replica(s), no data-path collective' % world,
+                       'parallelism': ('grid nodes sharded over %d ranks (halo rows per rank %s): one all-to-all of '
+                                       'layer-2 message rows + one all-gather of read-in rows per window' % (
+                                           world, wl.halo_rows)) if sharded else
+                       'windows round-robin over %d replica(s), no data-path collective' % world,
                        'l2_policy': 'inputs larger than L2: every window streams %.1f GB of node features through '
                                     'HBM (L2 = 126 MB), no explicit flush' % (BYTES_PER_NODE_WINDOW * wl.P / 1e9),
                        'setup_s': round(t_setup, 1)},
-            'e2e': {'value': world * K / (ms2 * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d // K,
+            'e2e': {'value': units * K / (ms2 * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d // K,
                     'd2h_bytes_per_step': d2h // K, 'ms_per_step': ms2 / K},
             'gpu_launches': launches,
             'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
@@ -350,7 +447,7 @@ def run_genie(args):
                          'kernel_share_of_step': timed[dom][0] / ms,
                          'window': {'algorithmic_bytes': BYTES_PER_NODE_WINDOW * wl.P,
                                     'achieved': BYTES_PER_NODE_WINDOW * wl.P / (ms / K * 1e-3) / 1e9,
-                                    'frac': BYTES_PER_NODE_WINDOW * wl.P / (ms / K * 1e-3) / 1e9 / peak},
+                                    'frac': BYTES_PER_NODE_WINDOW * wl.P / (ms / K * 1e-3) / 1e9 / (peak * (world if sharded else 1))},
                          'kernels_ms_per_step': {k: round(v[0] / K, 4) for k, v in sorted(timed.items())},
                          'library_kernels_share_of_step': kernel_total / ms},
             'clocks': clocks,

@@ -91,20 +91,25 @@ bool split_supported(const genie_plan* p) {
            g.n_prod < (int64_t)0x7fffff00 / 4;     // 32-bit float4 indices in the source pass
 }
 
-int launch_src_mean(const genie_plan* p, int width, const float* X, float* out, const float* gate, cudaStream_t st) {
+template <int W, int SB>
+static void launch_src_mean_t(const genie_plan* p, const float* X, float* out, const float* gate, cudaStream_t st) {
     const genie_graph_desc_t& g = p->g;
-    constexpr int SB = 4;
     const int n_slabs = (g.n_sta + SB - 1) / SB;
     const int64_t n_tiles = (int64_t)g.n_grid_groups * n_slabs;
     const unsigned grid = (unsigned)(n_tiles < p->sm_count ? n_tiles : p->sm_count);
+    src_mean_kernel<W, SB><<<grid, SM_THREADS, 0, st>>>(X, out, g.n_sta, g.src_rowptr, g.src_col, g.grid_grp_ptr,
+                                                        g.grid_grp_nodes, g.n_grid_groups, n_slabs, gate);
+}
+
+int launch_src_mean(const genie_plan* p, int width, const float* X, float* out, const float* gate, cudaStream_t st) {
+    // one slab = 512 bytes of every neighbour row: 4 stations of 128-byte rows, 8 stations of 64-byte rows
+    // (64 grid nodes x 2 station pairs x 8 lanes = 1024 items: one item per thread of the CTA)
     if (width == 32) {
         TimedLaunch tl(KID_SRC_MEAN32, st);
-        src_mean_kernel<32, SB><<<grid, SM_THREADS, 0, st>>>(X, out, g.n_sta, g.src_rowptr, g.src_col, g.grid_grp_ptr,
-                                                             g.grid_grp_nodes, g.n_grid_groups, n_slabs, gate);
+        launch_src_mean_t<32, 4>(p, X, out, gate, st);
     } else if (width == 16) {
         TimedLaunch tl(KID_SRC_MEAN16, st);
-        src_mean_kernel<16, SB><<<grid, SM_THREADS, 0, st>>>(X, out, g.n_sta, g.src_rowptr, g.src_col, g.grid_grp_ptr,
-                                                             g.grid_grp_nodes, g.n_grid_groups, n_slabs, gate);
+        launch_src_mean_t<16, 8>(p, X, out, gate, st);
     } else {
         set_error("launch_src_mean: unsupported row width");
         return GENIE_ERR_INVALID;
