@@ -27,37 +27,35 @@ constexpr int LDF = TM + 1;    // feature-tile row stride (floats): conflict-fre
 // K1: tr0 = PReLU(init_trns([slice ‖ mask]))
 // --------------------------------------------------------------------------------------------------------------------
 constexpr int K1_THREADS = 256;
+// init_trns weights + bias in the constant bank (FFMA reads them as uniform operands: no shared-memory broadcasts);
+// refreshed from the packed weights by a stream-ordered device-to-device copy before every launch.
+__constant__ float c_init[8 * LD + LD];
 
 __global__ void __launch_bounds__(K1_THREADS) da_init_kernel(const float* __restrict__ packed,
                                                              const float* __restrict__ slice,
                                                              const float* __restrict__ mask, float* __restrict__ tr0,
                                                              int64_t P, int tc_plan) {
-    __shared__ __align__(16) float sW[8 * LD + LD];
     __shared__ __align__(16) float sOut[K1_THREADS * LD_TR0];
-    for (int i = threadIdx.x; i < 8 * LD + LD; i += K1_THREADS) sW[i] = packed[DA_W0 + i];
     const float a0 = packed[DA_SLOPES + SL_A0];
     // tensor-core path (da_tc_kernels.cu): store p = PReLU12(tr0) instead of tr0
     const bool post = tc_plan && packed[TC_BASE + TC_SCAL + TCS_OK] != 0.f;
     const float a12 = post ? packed[DA_SLOPES + SL_A12] : 1.f;
-    __syncthreads();
 
     const int64_t i0 = (int64_t)blockIdx.x * K1_THREADS;
     const int n = threadIdx.x;
     const int64_t i = i0 + n;
     float acc[30];
 #pragma unroll
-    for (int o = 0; o < 30; ++o) acc[o] = sW[8 * LD + o];
+    for (int o = 0; o < 30; ++o) acc[o] = c_init[8 * LD + o];
     if (i < P) {
-        const float4 sv = reinterpret_cast<const float4*>(slice)[i];
-        const float4 mv = reinterpret_cast<const float4*>(mask)[i];
-        fma_row30(acc, sv.x, sW + 0 * LD);
-        fma_row30(acc, sv.y, sW + 1 * LD);
-        fma_row30(acc, sv.z, sW + 2 * LD);
-        fma_row30(acc, sv.w, sW + 3 * LD);
-        fma_row30(acc, mv.x, sW + 4 * LD);
-        fma_row30(acc, mv.y, sW + 5 * LD);
-        fma_row30(acc, mv.z, sW + 6 * LD);
-        fma_row30(acc, mv.w, sW + 7 * LD);
+        const float4 sv = __ldcs(reinterpret_cast<const float4*>(slice) + i);
+        const float4 mv = __ldg(reinterpret_cast<const float4*>(mask) + i);
+        const float in[8] = {sv.x, sv.y, sv.z, sv.w, mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int o = 0; o < 30; ++o) acc[o] = fmaf(in[k], c_init[k * LD + o], acc[o]);
+        }
     }
     // stage the row in shared memory (16-byte chunks XOR-swizzled by the row index: conflict-free), then write the
     // tile out as one contiguous, fully coalesced block.
@@ -383,6 +381,7 @@ int launch_da_init(const genie_plan* p, const float* packed, const float* slice,
     const int64_t P = p->g.n_prod;
     if (P == 0) return GENIE_OK;
     const int64_t blocks = (P + K1_THREADS - 1) / K1_THREADS;
+    GENIE_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_init, packed + DA_W0, sizeof(float) * (8 * LD + LD), 0, cudaMemcpyDeviceToDevice, st));
     TimedLaunch tl(KID_DA_INIT, st);
     da_init_kernel<<<(unsigned)blocks, K1_THREADS, 0, st>>>(packed, slice, mask, tr0, P, tc_plan ? 1 : 0);
     GENIE_LAUNCH_CHECK();

@@ -19,6 +19,7 @@
 // gathered from L2.  All hand-offs are mbarriers with bounded spins (a protocol bug traps, it never hangs).
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <cstdlib>
 
 using namespace gl;
 using namespace tc;
@@ -64,7 +65,8 @@ __device__ __forceinline__ float prelu_f(float x, float a) { return x >= 0.f ? x
 // Development aid (genie_debug_trace): CTA 0 stamps clock64() at the hand-off points of its first tiles, 24 slots per tile.
 #define S1_TRACE(slot)                                                                      \
     do {                                                                                    \
-        if (trace != nullptr && blockIdx.x == 0 && it < trace_tiles) trace[it * 24 + (slot)] = clock64(); \
+        if (trace != nullptr && blockIdx.x == 0 && it >= trace_start && it < trace_start + trace_tiles)                  \
+            trace[(it - trace_start) * 24 + (slot)] = clock64();                                \
     } while (0)
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                        const float* __restrict__ mask, float* __restrict__ zc, float* __restrict__ va,
                        float* __restrict__ vb, int S, int NT, const int32_t* __restrict__ tile_rows,
                        const int32_t* __restrict__ tile_meta, const uint16_t* __restrict__ tile_nbr,
-                       const float* __restrict__ tile_invdeg, int64_t n_tiles, long long* __restrict__ trace, int trace_tiles) {
+                       const float* __restrict__ tile_invdeg, int64_t n_tiles, long long* __restrict__ trace, int trace_tiles, int trace_start) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const float* tcw = packed + TC_BASE;
     if (tcw[TC_SCAL + TCS_OK] == 0.f) return;   // slopes not eligible: the generic kernels run instead (uniform exit)
@@ -500,10 +502,12 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
 }  // namespace
 
 static long long* g_s1_trace = nullptr;
-static int g_s1_trace_tiles = 0;
+static int g_s1_trace_tiles = 0, g_s1_trace_start = 0;
 void set_s1_trace(long long* buf, int tiles) {
     g_s1_trace = buf;
     g_s1_trace_tiles = tiles;
+    const char* e = getenv("GENIE_TRACE_START");
+    g_s1_trace_start = e ? atoi(e) : 0;
 }
 
 int launch_da_layer1_s(const genie_plan* p, const float* packed, const float* pfeat, const float* msrc,
@@ -520,7 +524,7 @@ int launch_da_layer1_s(const genie_plan* p, const float* packed, const float* pf
     da_layer1_s_kernel<<<(unsigned)grid, S1_THREADS, SM_TOTAL, st>>>(packed, pfeat, msrc, mask, zc, va, vb, g.n_sta,
                                                                      g.n_sta_tiles, g.sta_tile_rows, g.sta_tile_meta,
                                                                      g.sta_tile_nbr, g.sta_tile_invdeg, n_tiles,
-                                                                     g_s1_trace, g_s1_trace_tiles);
+                                                                     g_s1_trace, g_s1_trace_tiles, g_s1_trace_start);
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;
 }

@@ -38,6 +38,11 @@ constexpr int SM_BAR = SM_WPART + N_WG * 2 * 4 * 32 * 4;
 constexpr int SM_TOTAL = SM_BAR + 128;
 static_assert(SM_TOTAL <= 232448, "shared memory budget");
 
+// fc1 of the read-in (33 x 30 + bias) in the constant bank: FFMA reads its weight operand straight from c[][] (uniform, no
+// register-file write-back), which takes the weight broadcasts off the shared-memory pipe (the bound of this kernel in
+// profiles/r1k).  Refreshed from the caller's packed weights by a stream-ordered device-to-device copy before every launch.
+__constant__ float c_ri[W_FLOATS];
+
 struct Bars {
     uint64_t full[N_WG], empty[N_WG];
     int count[G_SLOTS];
@@ -249,14 +254,20 @@ __global__ void __launch_bounds__(S2_THREADS, 1)
             {
                 float acc30[30];
 #pragma unroll
-                for (int o = 0; o < 30; ++o) acc30[o] = sW[(RI_BFC1 - RI_WFC1) + o];
+                for (int o = 0; o < 30; ++o) acc30[o] = c_ri[(RI_BFC1 - RI_WFC1) + o];
 #pragma unroll
-                for (int i = 0; i < 15; ++i) fma_row30(acc30, x[i], sW + i * LD);
+                for (int i = 0; i < 15; ++i) {
 #pragma unroll
-                for (int i = 0; i < 15; ++i) fma_row30(acc30, x[16 + i], sW + (15 + i) * LD);
-                fma_row30(acc30, e0, sW + 30 * LD);
-                fma_row30(acc30, e1, sW + 31 * LD);
-                fma_row30(acc30, e2, sW + 32 * LD);
+                    for (int o = 0; o < 30; ++o) acc30[o] = fmaf(x[i], c_ri[i * LD + o], acc30[o]);
+                }
+#pragma unroll
+                for (int i = 0; i < 15; ++i) {
+#pragma unroll
+                    for (int o = 0; o < 30; ++o) acc30[o] = fmaf(x[16 + i], c_ri[(15 + i) * LD + o], acc30[o]);
+                }
+#pragma unroll
+                for (int o = 0; o < 30; ++o)
+                    acc30[o] = fmaf(e0, c_ri[30 * LD + o], fmaf(e1, c_ri[31 * LD + o], fmaf(e2, c_ri[32 * LD + o], acc30[o])));
                 const float mmax = valid ? fmaxf(fmaxf(mk.x, mk.y), fmaxf(mk.z, mk.w)) : 0.f;
 #pragma unroll
                 for (int o = 0; o < 30; ++o) h[o] = valid ? mmax * prelu(acc30[o], ri_a1) : 0.f;
@@ -314,6 +325,7 @@ int launch_da_layer2_s(const genie_plan* p, const float* packed, const float* zc
     }
     const int n_own = g.n_grid_owned > 0 ? g.n_grid_owned : g.n_grid;
     const unsigned grid = (unsigned)(n_own < p->sm_count ? n_own : p->sm_count);
+    GENIE_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_ri, packed + RI_WFC1, sizeof(float) * W_FLOATS, 0, cudaMemcpyDeviceToDevice, st));
     TimedLaunch tl(KID_DA_LAYER2_S, st);
     if (latent_out)
         da_layer2_s_kernel<true><<<grid, S2_THREADS, SM_TOTAL, st>>>(packed, zc, va, m2, mask, edge_attr, latent_out, out,

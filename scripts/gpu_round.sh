@@ -13,6 +13,6 @@ if [ "$2" != "skip-ncu" ]; then
 GENIE_BENCH_PROFILE=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 300 --csv \
   --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --day-seconds 2000 > gpurun_out/${tag}_ncu_bench.log 2>&1
 GENIE_BENCH_PROFILE=1 timeout 1200 ncu --profile-from-start off --set full --clock-control none --import-source on \
-  -k regex:'da_layer1_tc|da_layer2' -c 2 -o gpurun_out/${tag}_prof -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --day-seconds 2000 > gpurun_out/${tag}_ncu_full.log 2>&1
+  -k regex:'da_init|src_mean|da_layer1_s|da_layer2_s' -c 5 -o gpurun_out/${tag}_prof -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --day-seconds 2000 > gpurun_out/${tag}_ncu_full.log 2>&1
 tail -3 gpurun_out/${tag}_ncu_full.log
 fi

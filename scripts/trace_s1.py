@@ -33,7 +33,7 @@ ops.frontend_fwd(plan, packed, Slice, Mask, attr, pos, 30000.0)
 torch.cuda.synchronize()
 capi.check(capi.load().genie_debug_trace(None, 0))
 t = trace.cpu().numpy().astype(np.float64)
-n = min(NTR, (plan.tiles['n_tiles'] * G + 147) // 148) - 2
+n = min(NTR, (plan.tiles['n_tiles'] * G + 147) // 148 - int(os.environ.get('GENIE_TRACE_START', 0))) - 2
 t = t[8:n]
 print('tiles traced', len(t), 'cycles per tile (mma slot 0 to next slot 0): %.0f' % np.mean(np.diff(t[:, 0])))
 def d(a, b, name):
