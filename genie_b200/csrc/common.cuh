@@ -27,6 +27,35 @@ __device__ __forceinline__ void fma_row30(float (&acc)[30], float a, const float
     acc[29] = fmaf(a, w.y, acc[29]);
 }
 
+// Packed pair of fp32 values for Blackwell's two-wide FFMA2 (fma.rn.f32x2): acc += {a, a} * {w0, w1}.  With a scalar `a`
+// and weights from the constant bank ptxas emits FFMA2 R, Ra.F32, URw.F32x2, R: one issue slot for two FMAs.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void ffma2(f32x2_t& acc, float a, float w0, float w1) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(pack2(a, a)), "l"(pack2(w0, w1)));
+}
+
+__device__ __forceinline__ void fadd2(f32x2_t& acc, f32x2_t v) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(v)); }
+// Two-wide accumulation of 16-byte chunks: acc += v (four floats, two FADD2).
+struct f32x4_t {
+    f32x2_t lo, hi;
+};
+__device__ __forceinline__ void fadd4(f32x4_t& acc, const float4& v) {
+    fadd2(acc.lo, pack2(v.x, v.y));
+    fadd2(acc.hi, pack2(v.z, v.w));
+}
+__device__ __forceinline__ float4 to_float4(const f32x4_t& a) {
+    float4 r;
+    unpack2(a.lo, r.x, r.y);
+    unpack2(a.hi, r.z, r.w);
+    return r;
+}
+
 // acc[0..15] += a * wrow[0..15] (16-float aligned row).
 __device__ __forceinline__ void fma_row16(float (&acc)[16], float a, const float* __restrict__ wrow) {
     const float4* w4 = reinterpret_cast<const float4*>(wrow);

@@ -44,9 +44,9 @@ __global__ void __launch_bounds__(K1_THREADS) da_init_kernel(const float* __rest
     const int64_t i0 = (int64_t)blockIdx.x * K1_THREADS;
     const int n = threadIdx.x;
     const int64_t i = i0 + n;
-    float acc[30];
+    f32x2_t acc2[15];
 #pragma unroll
-    for (int o = 0; o < 30; ++o) acc[o] = c_init[8 * LD + o];
+    for (int o = 0; o < 15; ++o) acc2[o] = pack2(c_init[8 * LD + 2 * o], c_init[8 * LD + 2 * o + 1]);
     if (i < P) {
         const float4 sv = __ldcs(reinterpret_cast<const float4*>(slice) + i);
         const float4 mv = __ldg(reinterpret_cast<const float4*>(mask) + i);
@@ -54,9 +54,12 @@ __global__ void __launch_bounds__(K1_THREADS) da_init_kernel(const float* __rest
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
 #pragma unroll
-            for (int o = 0; o < 30; ++o) acc[o] = fmaf(in[k], c_init[k * LD + o], acc[o]);
+            for (int o = 0; o < 15; ++o) ffma2(acc2[o], in[k], c_init[k * LD + 2 * o], c_init[k * LD + 2 * o + 1]);
         }
     }
+    float acc[30];
+#pragma unroll
+    for (int o = 0; o < 15; ++o) unpack2(acc2[o], acc[2 * o], acc[2 * o + 1]);
     // stage the row in shared memory (16-byte chunks XOR-swizzled by the row index: conflict-free), then write the
     // tile out as one contiguous, fully coalesced block.
     float4* srow = reinterpret_cast<float4*>(sOut + n * LD_TR0);

@@ -321,9 +321,10 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
             if (r == 0) S1_TRACE(13);
             // ---- sum of the station neighbours' rows (16-byte chunk k ^ key of every row: conflict free) ------------------
             float4 acc[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
             {
+                f32x4_t a2[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a2[k].lo = a2[k].hi = 0ull;
                 const uint32_t w[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -331,10 +332,11 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                     const unsigned char* ra = sb + SB_P + idx * 128;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const float4 v = *reinterpret_cast<const float4*>(ra + ((k ^ key) << 4));
-                        acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
+                        fadd4(a2[k], *reinterpret_cast<const float4*>(ra + ((k ^ key) << 4)));
                     }
                 }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = to_float4(a2[k]);
             }
             unrotate8(acc, key);
             const bool valid = r < n_own;

@@ -198,9 +198,10 @@ __global__ void __launch_bounds__(S2_THREADS, 1)
             mbar_wait(&bars->full[wg], (uint32_t)(n & 1));
             // ---- sum of the station neighbours' v_a rows (chunk k ^ key of every row) ----------------------------------------
             float4 acc[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
             {
+                f32x4_t a2[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) a2[c].lo = a2[c].hi = 0ull;
                 const uint32_t w[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -208,10 +209,11 @@ __global__ void __launch_bounds__(S2_THREADS, 1)
                     const unsigned char* ra = sb + SB_VA + idx * 64;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        const float4 v = *reinterpret_cast<const float4*>(ra + ((c ^ key) << 4));
-                        acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
+                        fadd4(a2[c], *reinterpret_cast<const float4*>(ra + ((c ^ key) << 4)));
                     }
                 }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[c] = to_float4(a2[c]);
             }
             {   // un-rotate: acc[c] <- chunk c
                 const bool s0 = key & 1, s1 = key & 2;
@@ -252,22 +254,29 @@ __global__ void __launch_bounds__(S2_THREADS, 1)
             // ---- h = max(mask) * PReLU(fc1 [x_latent | attr]) ------------------------------------------------------------------
             float h[32];
             {
+                f32x2_t acc2[15];
+#pragma unroll
+                for (int o = 0; o < 15; ++o) acc2[o] = pack2(c_ri[(RI_BFC1 - RI_WFC1) + 2 * o], c_ri[(RI_BFC1 - RI_WFC1) + 2 * o + 1]);
+#pragma unroll
+                for (int i = 0; i < 15; ++i) {
+#pragma unroll
+                    for (int o = 0; o < 15; ++o) ffma2(acc2[o], x[i], c_ri[i * LD + 2 * o], c_ri[i * LD + 2 * o + 1]);
+                }
+#pragma unroll
+                for (int i = 0; i < 15; ++i) {
+#pragma unroll
+                    for (int o = 0; o < 15; ++o)
+                        ffma2(acc2[o], x[16 + i], c_ri[(15 + i) * LD + 2 * o], c_ri[(15 + i) * LD + 2 * o + 1]);
+                }
+#pragma unroll
+                for (int o = 0; o < 15; ++o) {
+                    ffma2(acc2[o], e0, c_ri[30 * LD + 2 * o], c_ri[30 * LD + 2 * o + 1]);
+                    ffma2(acc2[o], e1, c_ri[31 * LD + 2 * o], c_ri[31 * LD + 2 * o + 1]);
+                    ffma2(acc2[o], e2, c_ri[32 * LD + 2 * o], c_ri[32 * LD + 2 * o + 1]);
+                }
                 float acc30[30];
 #pragma unroll
-                for (int o = 0; o < 30; ++o) acc30[o] = c_ri[(RI_BFC1 - RI_WFC1) + o];
-#pragma unroll
-                for (int i = 0; i < 15; ++i) {
-#pragma unroll
-                    for (int o = 0; o < 30; ++o) acc30[o] = fmaf(x[i], c_ri[i * LD + o], acc30[o]);
-                }
-#pragma unroll
-                for (int i = 0; i < 15; ++i) {
-#pragma unroll
-                    for (int o = 0; o < 30; ++o) acc30[o] = fmaf(x[16 + i], c_ri[(15 + i) * LD + o], acc30[o]);
-                }
-#pragma unroll
-                for (int o = 0; o < 30; ++o)
-                    acc30[o] = fmaf(e0, c_ri[30 * LD + o], fmaf(e1, c_ri[31 * LD + o], fmaf(e2, c_ri[32 * LD + o], acc30[o])));
+                for (int o = 0; o < 15; ++o) unpack2(acc2[o], acc30[2 * o], acc30[2 * o + 1]);
                 const float mmax = valid ? fmaxf(fmaxf(mk.x, mk.y), fmaxf(mk.z, mk.w)) : 0.f;
 #pragma unroll
                 for (int o = 0; o < 30; ++o) h[o] = valid ? mmax * prelu(acc30[o], ri_a1) : 0.f;

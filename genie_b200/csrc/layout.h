@@ -74,11 +74,33 @@ constexpr int TC_SCAL = TC_BIAS2 + 96;                  // [8], see enum below
 constexpr int TC_FLOATS = TC_SCAL + 8;
 // TC_OK = 1 when activate12's slope is > 1e-3: layer 0 then stores p = PReLU12(tr0) (sums over source neighbours need
 // no per-edge activation; tr0 and PReLU11(tr0) are recovered from p exactly up to rounding), else the generic kernels run.
-enum { TCS_OK = 0, TCS_A1 = 1, TCS_A21 = 2, TCS_A22 = 3, TCS_R11 = 4, TCS_INV12 = 5, TCS_A12 = 6 };
+// TC_OK = 1 also requires activate11's slope > 1e-3: the station-pass kernel stages PReLU11(tr0) and recovers tr0 from it.
+enum { TCS_OK = 0, TCS_A1 = 1, TCS_A21 = 2, TCS_A22 = 3, TCS_R11 = 4, TCS_INV12 = 5, TCS_A12 = 6, TCS_INV11 = 7 };
 
-constexpr int PACKED_FLOATS = TC_BASE + TC_FLOATS;
+// ---- weight blob of the two-pipeline station-pass kernel (da_s1_kernel.cu) ---------------------------------------------
+// Same canonical no-swizzle K-major UMMA layout and hi / lo split as above, with every A operand 32 columns wide:
+//   S1A  N=64 K=32  rows 0-29 l1_t1_2, rows 32-61 l1_t2_2; k 0-29 tr0, k 30,31 mask0, mask1
+//   S1B  N=32 K=32  l1_t1_2[:, 30:60 | mask2, mask3]      (mean over station neighbours in k 0-29, mask2,3 in k 30,31)
+//   S1C  N=32 K=32  l1_t2_2[:, 30:60 | mask2, mask3]      (mean over source neighbours)
+//   S2   N=96 K=64  as B2
+//   S3A / S3B       as B3A / B3B
+// Biases ride on the "lo" pass of the A operand (pass A_lo x B_hi): the lo parts of the mask columns are zero, so the
+// kernel writes 1.0 into lo columns 30 and 31 and uses, for that pass only, a copy of the k 24-31 block of B_hi whose
+// rows 30 / 31 hold the hi / lo parts of the bias:   S1A_BIAS [N=64][K=8],  S2_BIAS [N=96][K=8].
+constexpr int T2_BASE = (TC_BASE + TC_FLOATS + 63) / 64 * 64;
+constexpr int T2_S1A_HI = 0, T2_S1A_LO = T2_S1A_HI + 64 * 32, T2_S1A_BIAS = T2_S1A_LO + 64 * 32;
+constexpr int T2_S1B_HI = T2_S1A_BIAS + 64 * 8, T2_S1B_LO = T2_S1B_HI + 32 * 32;
+constexpr int T2_S1C_HI = T2_S1B_LO + 32 * 32, T2_S1C_LO = T2_S1C_HI + 32 * 32;
+constexpr int T2_S2_HI = T2_S1C_LO + 32 * 32, T2_S2_LO = T2_S2_HI + 96 * 64, T2_S2_BIAS = T2_S2_LO + 96 * 64;
+constexpr int T2_S3A_HI = T2_S2_BIAS + 96 * 8, T2_S3A_LO = T2_S3A_HI + 16 * 32;
+constexpr int T2_S3B_HI = T2_S3A_LO + 16 * 32, T2_S3B_LO = T2_S3B_HI + 16 * 32;
+constexpr int T2_SCAL = T2_S3B_LO + 16 * 32;            // [8] copy of the TCS_* scalars
+constexpr int T2_FLOATS = T2_SCAL + 8;
 
-static_assert(DA_W11 % 4 == 0 && DA_END % 4 == 0 && RI_END % 4 == 0 && SA_SIZE % 4 == 0 && TC_FLOATS % 4 == 0,
+constexpr int PACKED_FLOATS = T2_BASE + T2_FLOATS;
+
+static_assert(DA_W11 % 4 == 0 && DA_END % 4 == 0 && RI_END % 4 == 0 && SA_SIZE % 4 == 0 && TC_FLOATS % 4 == 0 &&
+                  T2_FLOATS % 4 == 0,
               "16-byte alignment");
 
 // ---- node-feature row strides in the workspace (floats) -------------------------------------------------------------

@@ -82,7 +82,7 @@ __device__ void pack_tc(const genie_frontend_weights_t& w, float* __restrict__ t
     }
     if (threadIdx.x == 0) {
         const float a11 = w.da_activate11[0], a12 = w.da_activate12[0];
-        const bool ok = a12 > 1e-3f && a12 < 1e3f;      // false for NaN too
+        const bool ok = a12 > 1e-3f && a12 < 1e3f && a11 > 1e-3f && a11 < 1e3f;      // false for NaN too
         t[TC_SCAL + TCS_OK] = ok ? 1.f : 0.f;
         t[TC_SCAL + TCS_A1] = w.da_activate1[0];
         t[TC_SCAL + TCS_A21] = w.da_activate21[0];
@@ -90,8 +90,78 @@ __device__ void pack_tc(const genie_frontend_weights_t& w, float* __restrict__ t
         t[TC_SCAL + TCS_R11] = ok ? a11 / a12 : 0.f;
         t[TC_SCAL + TCS_INV12] = ok ? 1.f / a12 : 0.f;
         t[TC_SCAL + TCS_A12] = a12;
-        t[TC_SCAL + 7] = 0.f;
+        t[TC_SCAL + TCS_INV11] = ok ? 1.f / a11 : 0.f;
     }
+}
+
+// The k 24-31 block of an [N][K] hi matrix with rows 30 / 31 replaced by the hi / lo parts of a bias vector (layout.h T2_*).
+template <class F, class B>
+__device__ void pack_bias_block(float* dst, int N, F value, B bias) {
+    for (int idx = threadIdx.x; idx < N * 8; idx += blockDim.x) {
+        const int n = idx >> 3, k = idx & 7;
+        float v;
+        if (k == 6) v = tf32_hi_part(bias(n));
+        else if (k == 7) v = bias(n) - tf32_hi_part(bias(n));
+        else v = tf32_hi_part(value(n, 24 + k));
+        dst[((k >> 2) * N + n) * 4 + (k & 3)] = v;
+    }
+}
+
+__device__ void pack_t2(const genie_frontend_weights_t& w, float* __restrict__ t, const float* __restrict__ tc) {
+    const float *W11 = w.da_l1_t1_2.weight, *W12 = w.da_l1_t2_2.weight;          // [30][64]
+    const float *b11 = w.da_l1_t1_2.bias, *b12 = w.da_l1_t2_2.bias;
+    const float *W21a = w.da_l2_t1_1.weight, *W22a = w.da_l2_t2_1.weight;        // [30][60]
+    const float *W21b = w.da_l2_t1_2.weight, *W22b = w.da_l2_t2_2.weight;        // [15][94]
+    auto s1a = [=](int n, int k) -> float {
+        const int o = n & 31;
+        const float* W = n < 32 ? W11 : W12;
+        if (o >= 30) return 0.f;
+        return k < 30 ? W[o * 64 + k] : W[o * 64 + 60 + (k - 30)];       // k 30, 31: mask0, mask1
+    };
+    pack_umma(t + T2_S1A_HI, t + T2_S1A_LO, 64, 32, s1a);
+    pack_bias_block(t + T2_S1A_BIAS, 64, s1a, [=](int n) -> float {
+        const int o = n & 31;
+        return o < 30 ? (n < 32 ? b11 : b12)[o] : 0.f;
+    });
+    pack_umma(t + T2_S1B_HI, t + T2_S1B_LO, 32, 32, [=](int n, int k) -> float {
+        if (n >= 30) return 0.f;
+        return k < 30 ? W11[n * 64 + 30 + k] : W11[n * 64 + 62 + (k - 30)];      // k 30, 31: mask2, mask3
+    });
+    pack_umma(t + T2_S1C_HI, t + T2_S1C_LO, 32, 32, [=](int n, int k) -> float {
+        if (n >= 30) return 0.f;
+        return k < 30 ? W12[n * 64 + 30 + k] : W12[n * 64 + 62 + (k - 30)];
+    });
+    auto s2 = [=](int n, int k) -> float {
+        // operand column k -> input feature: tr[0:30] at 0-29, mask0,1 at 30,31, tr[30:60] at 32-61, mask2,3 at 62,63
+        const int kt = k < 30 ? k : (k >= 32 && k < 62) ? k - 2 : -1;
+        const int km = k == 30 ? 0 : k == 31 ? 1 : k == 62 ? 2 : k == 63 ? 3 : -1;
+        if (n < 64) {
+            const int o = n & 31;
+            if (o >= 30 || kt < 0) return 0.f;
+            return (n < 32 ? W21a : W22a)[o * 60 + kt];
+        }
+        const int o = (n - 64) & 15;
+        if (o >= 15) return 0.f;
+        const float* W = n < 80 ? W21b : W22b;
+        if (kt >= 0) return W[o * 94 + kt];
+        if (km >= 0) return W[o * 94 + 90 + km];
+        return 0.f;
+    };
+    pack_umma(t + T2_S2_HI, t + T2_S2_LO, 96, 64, s2);
+    const float *b21a = w.da_l2_t1_1.bias, *b22a = w.da_l2_t2_1.bias, *b21b = w.da_l2_t1_2.bias, *b22b = w.da_l2_t2_2.bias;
+    pack_bias_block(t + T2_S2_BIAS, 96, s2, [=](int n) -> float {
+        if (n < 30) return b21a[n];
+        if (n >= 32 && n < 62) return b22a[n - 32];
+        if (n >= 64 && n < 79) return b21b[n - 64];
+        if (n >= 80 && n < 95) return b22b[n - 80];
+        return 0.f;
+    });
+    pack_umma(t + T2_S3A_HI, t + T2_S3A_LO, 16, 32,
+              [=](int n, int k) -> float { return (n < 15 && k < 30) ? W21b[n * 94 + 60 + k] : 0.f; });
+    pack_umma(t + T2_S3B_HI, t + T2_S3B_LO, 16, 32,
+              [=](int n, int k) -> float { return (n < 15 && k < 30) ? W22b[n * 94 + 60 + k] : 0.f; });
+    __syncthreads();                                        // pack_tc's scalars
+    if (threadIdx.x < 8) t[T2_SCAL + threadIdx.x] = tc[TC_SCAL + threadIdx.x];
 }
 
 __global__ void pack_weights_kernel(const genie_frontend_weights_t w, float* __restrict__ p) {
@@ -152,6 +222,7 @@ __global__ void pack_weights_kernel(const genie_frontend_weights_t w, float* __r
         }
     }
     pack_tc(w, p + TC_BASE);
+    pack_t2(w, p + T2_BASE, p + TC_BASE);
 }
 
 }  // namespace
