@@ -18,8 +18,8 @@ using namespace gl;
 
 namespace {
 
-constexpr int S2_THREADS = 512;
-constexpr int N_WG = 3;                              // compute warpgroups = buffers
+constexpr int S2_THREADS = 640;
+constexpr int N_WG = 4;                              // compute warpgroups = buffers
 constexpr int ROWS = GENIE_TILE_ROWS_MAX;
 constexpr int NT_MAX = 32;                           // station tiles per grid node
 constexpr int G_SLOTS = 8;                           // grid nodes in flight inside one CTA (a tile can start while the

@@ -33,7 +33,7 @@ ops.frontend_fwd(plan, packed, Slice, Mask, attr, pos, 30000.0)
 torch.cuda.synchronize()
 capi.check(capi.load().genie_debug_trace(None, 0))
 t = trace.cpu().numpy().astype(np.float64)
-n = min(NTR, (plan.tiles['n_tiles'] * G + 147) // 148 - int(os.environ.get('GENIE_TRACE_START', 0))) - 2
+n = min(NTR, (plan.tiles['n_tiles'] * G + 147) // 148 // 2 - int(os.environ.get('GENIE_TRACE_START', 0))) - 2
 t = t[8:n]
 print('tiles traced', len(t), 'cycles per tile (mma slot 0 to next slot 0): %.0f' % np.mean(np.diff(t[:, 0])))
 def d(a, b, name):
@@ -49,10 +49,10 @@ d(9, 4, 'mma wake-up after epilogue C')
 d(4, 5, 'mma: issue stage D (24 MMAs)')
 d(5, 10, 'stage D execution after issue')
 d(10, 11, 'epilogue D (ld 32, store va vb)')
-d(12, 13, 'gather: convert rows in place')
-d(13, 14, 'gather: 16 neighbour rows + unrotate')
+d(12, 14, 'gather: 16 neighbour rows + unrotate')
 d(14, 15, 'gather: wait for operand slot')
-d(15, 16, 'gather: write operands to TMEM')
+d(15, 16, 'gather: write STA operand to TMEM')
+d(11, 19, 'epilogue: OWN / SRC operands of the next tile (incl. wait for buffer)')
 d(17, 18, 'producer: issue cp.async')
 print('  %-52s %8.0f' % ('gather: wait for buffer full (after prev operands written)', np.mean(t[1:, 12] - t[:-1, 16])))
 print('  %-52s %8.0f' % ('mma: wait for operands after prev stage D issue', np.mean(t[1:, 0] - t[:-1, 5])))
