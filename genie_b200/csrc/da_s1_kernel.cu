@@ -48,7 +48,8 @@ constexpr int SB_SIZE = SB_MK + 128 * 16;
 constexpr int SM_W = 0;                              // tensor-core weight blob (layout.h T2_*)
 constexpr int SM_BUF = (T2_FLOATS * 4 + 1023) / 1024 * 1024;
 constexpr int SM_BAR = SM_BUF + NPIPE * SB_SIZE;
-constexpr int SM_TOTAL = SM_BAR + 256;
+constexpr int SM_SCR = SM_BAR + 256;                 // [8 epilogue warps][32 rows][64 B] store-transposition scratch
+constexpr int SM_TOTAL = SM_SCR + 8 * 2048;
 static_assert(SB_SIZE % 16 == 0 && SM_BUF % 1024 == 0 && SM_BAR % 8 == 0, "alignment");
 static_assert(SM_TOTAL <= 232448, "shared memory budget");
 
@@ -84,13 +85,6 @@ __device__ __forceinline__ float prelu_f(float x, float a) { return x >= 0.f ? x
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void prefetch_l2_128(const void* src) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], 128;" ::"l"(src) : "memory");
-}
-__device__ __forceinline__ void prefetch_l2_16(const void* src) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], 16;" ::"l"(src) : "memory");
-}
-
 // 16 consecutive fp32 values -> 3xTF32 parts -> TMEM columns [hi, hi+16) and [lo, lo+16)
 __device__ __forceinline__ void st_split16(uint32_t taddr_hi, uint32_t taddr_lo, const float (&v)[16]) {
     float h[16], l[16];
@@ -127,6 +121,27 @@ __device__ __forceinline__ void unrotate8(float4 (&v)[8], int key) {
             v[k | (1 << b)] = sw ? a : c;
         }
     }
+}
+
+// Coalescing store of 16 consecutive floats per row (thread = row of the warp's 32-row block): the chunk goes through a
+// warp-private 2 KB scratch (16-byte pieces XOR-swizzled: conflict free both ways) and leaves as 64-byte runs, four lanes
+// per row — 8 lines per store instruction instead of 32 (a thread-per-row STG.128 costs one L1 wavefront per lane).
+//   sid[j] = station id of row (lane >> 2) + 8 j of the warp's block, or -1; dst + (node0 + sid) * ld is the row's address.
+__device__ __forceinline__ void store16_rows(const float (&v)[16], unsigned char* scr, int lane, const int (&sid)[4],
+                                             float* __restrict__ dst, int64_t node0, int ld) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<float4*>(scr + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) =
+            make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    __syncwarp();
+    const int chunk = lane & 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int row = (lane >> 2) + 8 * j;
+        const float4 x = *reinterpret_cast<const float4*>(scr + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+        if (sid[j] >= 0) __stcs(reinterpret_cast<float4*>(dst + (node0 + sid[j]) * ld) + chunk, x);
+    }
+    __syncwarp();
 }
 
 // Epilogue-warpgroup half of the stage-B operands of one tile: [tr0 | mask0,1] (tr0 recovered from the staged PReLU11(tr0)
@@ -187,7 +202,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                        float* __restrict__ vb, int S, int NT, const int32_t* __restrict__ tile_rows,
                        const int32_t* __restrict__ tile_meta, const uint16_t* __restrict__ tile_nbr,
                        const float* __restrict__ tile_invdeg, int64_t n_tiles, long long* __restrict__ trace, int trace_tiles,
-                       int trace_start) {
+                       int trace_start, int dbg) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const float* tcw = packed + T2_BASE;
     if (tcw[T2_SCAL + TCS_OK] == 0.f) return;   // slopes not eligible: the generic kernels run instead (uniform exit)
@@ -267,30 +282,23 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
             }
             if (id_m0 >= 0) cp_async16(sb + SB_MK + tid * 16, mask + (node0 + id_m0) * 4);
             if (id_m1 >= 0) cp_async16(sb + SB_MK + (tid + 64) * 16, mask + (node0 + id_m1) * 4);
-            {   // L2 prefetch of the next tile of this pipeline (whole 128-byte rows; lanes with c == 0 issue them)
-                const int64_t t2 = t + 2 * (int64_t)gridDim.x;
-                if (t2 < n_tiles && c == 0) {
-                    const int g2 = (int)(t2 / NT), T2 = (int)(t2 - (int64_t)g2 * NT);
-                    const int n_own2 = __ldg(tile_meta + 2 * T2), n_rows2 = __ldg(tile_meta + 2 * T2 + 1);
-                    const int32_t* rows2 = tile_rows + (int64_t)T2 * ROWS;
-                    const int64_t node2 = (int64_t)g2 * S;
-                    for (int r = rr; r < n_rows2; r += 8) {
-                        const int id = __ldg(rows2 + r);
-                        prefetch_l2_128(p + (node2 + id) * 32);
-                        if (r < n_own2) {
-                            prefetch_l2_128(msrc + (node2 + id) * 32);
-                            prefetch_l2_16(mask + (node2 + id) * 4);
-                        }
-                    }
-                }
-            }
             asm volatile("cp.async.wait_all;" ::: "memory");
+            // in-place conversion in batches of CB chunks: all loads of a batch are in flight before its first store
+            if (!(dbg & 1)) {
+                constexpr int CB = 9;
+                static_assert(JMAX % CB == 0, "conversion batches");
 #pragma unroll
-            for (int j = 0; j < JMAX; ++j) {
-                if (ids[j] >= 0) {
-                    float4* a = reinterpret_cast<float4*>(sbp + SB_P + (rr + 8 * j) * 128 + c * 16);
-                    const float4 v = *a;
-                    *a = make_float4(prelu_f(v.x, r11), prelu_f(v.y, r11), prelu_f(v.z, r11), prelu_f(v.w, r11));
+                for (int j0 = 0; j0 < JMAX; j0 += CB) {
+                    if (ids[j0] < 0) break;            // rows are dense from the front: the whole batch is padding
+                    float4 v[CB];
+#pragma unroll
+                    for (int u = 0; u < CB; ++u)
+                        v[u] = *reinterpret_cast<const float4*>(sbp + SB_P + (rr + 8 * (j0 + u)) * 128 + c * 16);
+#pragma unroll
+                    for (int u = 0; u < CB; ++u)
+                        if (ids[j0 + u] >= 0)
+                            *reinterpret_cast<float4*>(sbp + SB_P + (rr + 8 * (j0 + u)) * 128 + c * 16) = make_float4(
+                                prelu_f(v[u].x, r11), prelu_f(v[u].y, r11), prelu_f(v[u].z, r11), prelu_f(v[u].w, r11));
                 }
             }
             mbar_arrive(&bars->full[q]);
@@ -450,19 +458,19 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
         const float a1 = sc[TCS_A1], a21 = sc[TCS_A21], a22 = sc[TCS_A22], inv11 = sc[TCS_INV11];
         const int key = lane & 7;
         const unsigned char* sb = smem + SM_BUF + q * SB_SIZE;
+        unsigned char* scr = smem + SM_SCR + (warp - WG_E0) * 2048;
+        const int row0 = ((warp - WG_E0) & 3) * 32;                 // first tile row of this warp
         uint32_t ph_d = 0;
         int64_t k = 0;
         // The warpgroup also writes the OWN / SRC halves of the stage-B operands (the gather warpgroup writes STA): for the
         // first tile up front, for every later tile right after the previous tile's last epilogue.
         bool valid = false;
-        int64_t node = 0;
         float4 mk = make_float4(0.f, 0.f, 0.f, 0.f);
         {
             const int64_t t = blockIdx.x + (int64_t)q * gridDim.x;
             if (t < n_tiles) {
                 const int g = (int)(t / NT), T = (int)(t - (int64_t)g * NT);
                 valid = r < __ldg(tile_meta + 2 * T);
-                node = (int64_t)g * S + (valid ? __ldg(tile_rows + (int64_t)T * ROWS + r) : 0);
                 mbar_wait(&bars->full[q], 0u);
                 mk = s1_own_operands(sb, r, valid, key, inv11, lane_base);
                 mbar_arrive(&bars->empty[q]);
@@ -472,6 +480,17 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
             }
         }
         for (int64_t t = blockIdx.x + (int64_t)q * gridDim.x; t < n_tiles; t += 2 * (int64_t)gridDim.x, ++k) {
+            const int g = (int)(t / NT), T = (int)(t - (int64_t)g * NT);
+            const int64_t node0 = (int64_t)g * S;
+            int sid[4];
+            {
+                const int n_own = __ldg(tile_meta + 2 * T);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int rw = row0 + (lane >> 2) + 8 * j;
+                    sid[j] = rw < n_own ? __ldg(tile_rows + (int64_t)T * ROWS + rw) : -1;
+                }
+            }
             // ---- stage B epilogue: tr = PReLU1(X) -> A operand of stage C (mask in the four spare columns) -----------------
             mbar_wait(&bars->d_full[q], ph_d);
             ph_d ^= 1;
@@ -520,12 +539,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                 float v[16];
                 tmem_ld16(lane_base + TM_DC + 64 + c, v);
                 tmem_ld_wait();
-                if (valid) {
-                    float4* dst = reinterpret_cast<float4*>(zc + node * LD_ZC + c);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        __stcs(dst + u, make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]));
-                }
+                store16_rows(v, scr, lane, sid, zc + c, node0, LD_ZC);
             }
             tmem_st_wait();
             tc_fence_before_sync();
@@ -541,12 +555,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                 float v[16];
                 tmem_ld16(lane_base + TM_DD + c, v);
                 tmem_ld_wait();
-                if (valid) {
-                    float4* dst = reinterpret_cast<float4*>((c ? vb : va) + node * LD_V);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        __stcs(dst + u, make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]));
-                }
+                store16_rows(v, scr, lane, sid, c ? vb : va, node0, LD_V);
             }
             tc_fence_before_sync();
             mbar_arrive(&bars->d_free[q]);
@@ -556,7 +565,6 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
             if (t2 < n_tiles) {
                 const int g2 = (int)(t2 / NT), T2 = (int)(t2 - (int64_t)g2 * NT);
                 valid = r < __ldg(tile_meta + 2 * T2);
-                node = (int64_t)g2 * S + (valid ? __ldg(tile_rows + (int64_t)T2 * ROWS + r) : 0);
                 mbar_wait(&bars->full[q], (uint32_t)((k + 1) & 1));
                 mk = s1_own_operands(sb, r, valid, key, inv11, lane_base);
                 mbar_arrive(&bars->empty[q]);
@@ -576,7 +584,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
 }  // namespace
 
 static long long* g_s1_trace = nullptr;
-static int g_s1_trace_tiles = 0, g_s1_trace_start = 0;
+static int g_s1_trace_tiles = 0, g_s1_trace_start = 0, g_s1_dbg = 0;
 void set_s1_trace(long long* buf, int tiles) {
     g_s1_trace = buf;
     g_s1_trace_tiles = tiles;
@@ -590,6 +598,8 @@ int launch_da_layer1_s(const genie_plan* p, const float* packed, const float* pf
     const int64_t n_tiles = (int64_t)g.n_sta_tiles * (g.n_grid_owned > 0 ? g.n_grid_owned : g.n_grid);
     static bool attr_set = false;
     if (!attr_set) {
+        const char* e = getenv("GENIE_S1_DBG");   // development only: bit 0 skips the in-place conversion (wrong results: timing only)
+        g_s1_dbg = e ? atoi(e) : 0;
         GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer1_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
         attr_set = true;
     }
@@ -598,7 +608,7 @@ int launch_da_layer1_s(const genie_plan* p, const float* packed, const float* pf
     da_layer1_s_kernel<<<(unsigned)grid, S1_THREADS, SM_TOTAL, st>>>(packed, pfeat, msrc, mask, zc, va, vb, g.n_sta,
                                                                      g.n_sta_tiles, g.sta_tile_rows, g.sta_tile_meta,
                                                                      g.sta_tile_nbr, g.sta_tile_invdeg, n_tiles,
-                                                                     g_s1_trace, g_s1_trace_tiles, g_s1_trace_start);
+                                                                     g_s1_trace, g_s1_trace_tiles, g_s1_trace_start, g_s1_dbg);
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;
 }

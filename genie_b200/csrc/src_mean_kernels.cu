@@ -20,7 +20,7 @@ namespace {
 constexpr int SM_THREADS = 1024;
 
 // W = floats per row (32: layer-0 features p, 16: layer-2 messages v_b); SB = stations per slab (even)
-template <int W, int SB>
+template <int W, int SB, bool PREFETCH>
 __global__ void __launch_bounds__(SM_THREADS, 1)
     src_mean_kernel(const float* __restrict__ X, float* __restrict__ out, int S, const int64_t* __restrict__ rowptr,
                     const int32_t* __restrict__ col, const int32_t* __restrict__ grp_ptr,
@@ -39,6 +39,34 @@ __global__ void __launch_bounds__(SM_THREADS, 1)
         const int gcnt = __ldg(grp_ptr + grp + 1) - gbeg;
         const int s0 = slab * SB;
         const int items = gcnt * PAIRS * LPR;
+        if (PREFETCH) {     // measured on B200 (r1r): 5.1 -> 8.5 ms, the extra L1 requests cost more than the misses: kept off
+            // Pull the neighbour rows of this CTA's NEXT tile into L1 while this tile is summed (the union of a group's rows
+            // then hits instead of stalling the warps on its first touch).  The PAIRS * LPR threads of a grid node share its
+            // deg x (slab bytes / 128) lines.
+            const int64_t tn = t + gridDim.x;
+            if (tn < n_tiles) {
+                const int slab_n = (int)(tn / n_groups);
+                const int grp_n = (int)(tn - (int64_t)slab_n * n_groups);
+                const int gbeg_n = __ldg(grp_ptr + grp_n);
+                const int gcnt_n = __ldg(grp_ptr + grp_n + 1) - gbeg_n;
+                constexpr int LINES = SB * W * 4 / 128;          // 128-byte lines of one neighbour row inside the slab
+                constexpr int TPN = PAIRS * LPR;                 // threads per grid node
+                const int i = threadIdx.x;
+                if (i < gcnt_n * TPN) {
+                    const int gl = i / TPN, sub = i - gl * TPN;
+                    const int g = __ldg(grp_nodes + gbeg_n + gl);
+                    const int beg = (int)__ldg(rowptr + g);
+                    const int deg = (int)__ldg(rowptr + g + 1) - beg;
+                    const char* base = reinterpret_cast<const char*>(X) + (size_t)slab_n * SB * W * 4;
+                    for (int n = sub; n < deg * LINES; n += TPN) {
+                        const int j = n / LINES, line = n - j * LINES;
+                        if (slab_n * SB + line * (128 / (W * 4)) >= S) continue;     // ragged last slab
+                        const uint32_t nb = (uint32_t)__ldg(col + beg + j);
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (size_t)nb * gstride * 16 + line * 128));
+                    }
+                }
+            }
+        }
         for (int i = threadIdx.x; i < items; i += SM_THREADS) {
             const int c = i % LPR;
             const int pr = (i / LPR) % PAIRS;
@@ -97,7 +125,7 @@ static void launch_src_mean_t(const genie_plan* p, const float* X, float* out, c
     const int n_slabs = (g.n_sta + SB - 1) / SB;
     const int64_t n_tiles = (int64_t)g.n_grid_groups * n_slabs;
     const unsigned grid = (unsigned)(n_tiles < p->sm_count ? n_tiles : p->sm_count);
-    src_mean_kernel<W, SB><<<grid, SM_THREADS, 0, st>>>(X, out, g.n_sta, g.src_rowptr, g.src_col, g.grid_grp_ptr,
+    src_mean_kernel<W, SB, false><<<grid, SM_THREADS, 0, st>>>(X, out, g.n_sta, g.src_rowptr, g.src_col, g.grid_grp_ptr,
                                                         g.grid_grp_nodes, g.n_grid_groups, n_slabs, gate);
 }
 
