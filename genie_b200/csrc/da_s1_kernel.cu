@@ -68,18 +68,19 @@ struct Bars {
     uint64_t full[NPIPE], empty[NPIPE];
     uint64_t opA_full[NPIPE], opA_free[NPIPE];
     uint64_t d_full[NPIPE], aE_full[NPIPE], d_free[NPIPE];
+    uint64_t raw[NPIPE];           // copies landed (producers -> gather warpgroup, which converts the rows in place)
     uint32_t tmem_base;
 };
 static_assert(sizeof(Bars) <= 256, "barrier block");
 
 __device__ __forceinline__ float prelu_f(float x, float a) { return x >= 0.f ? x : a * x; }
 
-// Development aid (genie_debug_trace): pipeline 0 of CTA 0 stamps clock64() at the hand-off points of its tiles, 24 slots
-// per tile.
+// Development aid (genie_debug_trace): CTA 0 stamps clock64() at the hand-off points of its tiles, 24 slots per tile and
+// pipeline (trace[tile][pipeline][slot]).
 #define S1_TRACE(slot)                                                                                     \
     do {                                                                                                   \
-        if (trace != nullptr && blockIdx.x == 0 && q == 0 && k >= trace_start && k < trace_start + trace_tiles) \
-            trace[(k - trace_start) * 24 + (slot)] = clock64();                                            \
+        if (trace != nullptr && blockIdx.x == 0 && k >= trace_start && k < trace_start + trace_tiles)      \
+            trace[(k - trace_start) * 48 + q * 24 + (slot)] = clock64();                                   \
     } while (0)
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                        float* __restrict__ vb, int S, int NT, const int32_t* __restrict__ tile_rows,
                        const int32_t* __restrict__ tile_meta, const uint16_t* __restrict__ tile_nbr,
                        const float* __restrict__ tile_invdeg, int64_t n_tiles, long long* __restrict__ trace, int trace_tiles,
-                       int trace_start, int dbg) {
+                       int trace_start) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const float* tcw = packed + T2_BASE;
     if (tcw[T2_SCAL + TCS_OK] == 0.f) return;   // slopes not eligible: the generic kernels run instead (uniform exit)
@@ -225,13 +226,14 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
     }
     if (threadIdx.x == 0) {
         for (int b = 0; b < NPIPE; ++b) {
-            mbar_init(&bars->full[b], P_THREADS);
+            mbar_init(&bars->full[b], 128);           // gather warpgroup, after the in-place conversion
             mbar_init(&bars->empty[b], 256);          // gather + epilogue warpgroups
             mbar_init(&bars->opA_full[b], 256);
             mbar_init(&bars->opA_free[b], 1);
             mbar_init(&bars->d_full[b], 1);
             mbar_init(&bars->aE_full[b], 128);
             mbar_init(&bars->d_free[b], 128);
+            mbar_init(&bars->raw[b], P_THREADS);
         }
         fence_barrier_init();
     }
@@ -249,13 +251,11 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
     if (warp >= WG_P0) {
         // ================================ producers of pipeline q: cp.async row gather =================================
         // Thread `tid` owns the 16-byte chunk c = tid & 7 of the staged rows rr + 8 j (rr = tid >> 3).  The staged p rows
-        // are only ever read as PReLU11(tr0): the thread converts the chunks it copied itself (element-wise, so no other
-        // thread is involved) before it arrives on the buffer's barrier.  The rows of the pipeline's NEXT tile are
-        // prefetched into L2 while this tile's copies are in flight.
+        // are only ever read as PReLU11(tr0): the (otherwise waiting) gather warpgroup converts them in place once the
+        // copies have landed.
         const int q = (warp - WG_P0) >> 1;
         const int tid = threadIdx.x - (WG_P0 + 2 * q) * 32;
         const int rr = tid >> 3, c = tid & 7;
-        const float r11 = sc[TCS_R11];
         constexpr int JMAX = (ROWS + 7) / 8;
         unsigned char* sbp = smem + SM_BUF + q * SB_SIZE;
         const uint32_t sb = smem_u32(sbp);
@@ -283,25 +283,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
             if (id_m0 >= 0) cp_async16(sb + SB_MK + tid * 16, mask + (node0 + id_m0) * 4);
             if (id_m1 >= 0) cp_async16(sb + SB_MK + (tid + 64) * 16, mask + (node0 + id_m1) * 4);
             asm volatile("cp.async.wait_all;" ::: "memory");
-            // in-place conversion in batches of CB chunks: all loads of a batch are in flight before its first store
-            if (!(dbg & 1)) {
-                constexpr int CB = 9;
-                static_assert(JMAX % CB == 0, "conversion batches");
-#pragma unroll
-                for (int j0 = 0; j0 < JMAX; j0 += CB) {
-                    if (ids[j0] < 0) break;            // rows are dense from the front: the whole batch is padding
-                    float4 v[CB];
-#pragma unroll
-                    for (int u = 0; u < CB; ++u)
-                        v[u] = *reinterpret_cast<const float4*>(sbp + SB_P + (rr + 8 * (j0 + u)) * 128 + c * 16);
-#pragma unroll
-                    for (int u = 0; u < CB; ++u)
-                        if (ids[j0 + u] >= 0)
-                            *reinterpret_cast<float4*>(sbp + SB_P + (rr + 8 * (j0 + u)) * 128 + c * 16) = make_float4(
-                                prelu_f(v[u].x, r11), prelu_f(v[u].y, r11), prelu_f(v[u].z, r11), prelu_f(v[u].w, r11));
-                }
-            }
-            mbar_arrive(&bars->full[q]);
+            mbar_arrive(&bars->raw[q]);
             if (tid == 0) S1_TRACE(18);
         }
     } else if (warp < NPIPE) {
@@ -390,6 +372,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
         const int r = ((warp - WG_G0) & 3) * 32 + lane;
         const uint32_t lane_base = tm + q * TM_PIPE + ((uint32_t)((warp & 3) * 32) << 16);
         const int key = lane & 7;
+        const float r11 = sc[TCS_R11];
         unsigned char* sb = smem + SM_BUF + q * SB_SIZE;
         int64_t k = 0;
         for (int64_t t = blockIdx.x + (int64_t)q * gridDim.x; t < n_tiles; t += 2 * (int64_t)gridDim.x, ++k) {
@@ -399,6 +382,28 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
             const uint4* nb = reinterpret_cast<const uint4*>(tile_nbr + ((int64_t)T * 128 + r) * 16);
             const uint4 n0 = __ldg(nb), n1 = __ldg(nb + 1);
             const float invdeg = __ldg(tile_invdeg + T * 128 + r);
+            // ---- staged p rows -> PReLU11(tr0), in place: 16-byte chunk r & 7 of the rows (r >> 3) + 16 j, in batches whose
+            //      loads are all in flight before the first store ----------------------------------------------------------
+            mbar_wait(&bars->raw[q], (uint32_t)(k & 1));
+            {
+                const int n_rows = __ldg(tile_meta + 2 * T + 1);
+                unsigned char* cb = sb + SB_P + (r >> 3) * 128 + (r & 7) * 16;
+                constexpr int CB = 9;
+                static_assert((ROWS + 15) / 16 == 2 * CB, "conversion batches");
+#pragma unroll
+                for (int j0 = 0; j0 < 2 * CB; j0 += CB) {
+                    if ((r >> 3) + 16 * j0 >= n_rows) break;
+                    float4 v[CB];
+#pragma unroll
+                    for (int u = 0; u < CB; ++u) v[u] = *reinterpret_cast<const float4*>(cb + (j0 + u) * 16 * 128);
+#pragma unroll
+                    for (int u = 0; u < CB; ++u)
+                        if ((r >> 3) + 16 * (j0 + u) < n_rows)
+                            *reinterpret_cast<float4*>(cb + (j0 + u) * 16 * 128) = make_float4(
+                                prelu_f(v[u].x, r11), prelu_f(v[u].y, r11), prelu_f(v[u].z, r11), prelu_f(v[u].w, r11));
+                }
+            }
+            mbar_arrive(&bars->full[q]);
             mbar_wait(&bars->full[q], (uint32_t)(k & 1));
             if (r == 0) S1_TRACE(12);
             // ---- sum of the station neighbours' rows (16-byte chunk k ^ key of every row: conflict free) ------------------
@@ -584,7 +589,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
 }  // namespace
 
 static long long* g_s1_trace = nullptr;
-static int g_s1_trace_tiles = 0, g_s1_trace_start = 0, g_s1_dbg = 0;
+static int g_s1_trace_tiles = 0, g_s1_trace_start = 0;
 void set_s1_trace(long long* buf, int tiles) {
     g_s1_trace = buf;
     g_s1_trace_tiles = tiles;
@@ -598,8 +603,6 @@ int launch_da_layer1_s(const genie_plan* p, const float* packed, const float* pf
     const int64_t n_tiles = (int64_t)g.n_sta_tiles * (g.n_grid_owned > 0 ? g.n_grid_owned : g.n_grid);
     static bool attr_set = false;
     if (!attr_set) {
-        const char* e = getenv("GENIE_S1_DBG");   // development only: bit 0 skips the in-place conversion (wrong results: timing only)
-        g_s1_dbg = e ? atoi(e) : 0;
         GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer1_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
         attr_set = true;
     }
@@ -608,7 +611,7 @@ int launch_da_layer1_s(const genie_plan* p, const float* packed, const float* pf
     da_layer1_s_kernel<<<(unsigned)grid, S1_THREADS, SM_TOTAL, st>>>(packed, pfeat, msrc, mask, zc, va, vb, g.n_sta,
                                                                      g.n_sta_tiles, g.sta_tile_rows, g.sta_tile_meta,
                                                                      g.sta_tile_nbr, g.sta_tile_invdeg, n_tiles,
-                                                                     g_s1_trace, g_s1_trace_tiles, g_s1_trace_start, g_s1_dbg);
+                                                                     g_s1_trace, g_s1_trace_tiles, g_s1_trace_start);
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;
 }

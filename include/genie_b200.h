@@ -227,7 +227,7 @@ GENIE_API const char* genie_timing_kernel_name(int k);
 GENIE_API int genie_timing_collect(double* total_ms, int64_t* launches, int reset);
 
 /* Development aid: while trace_dev != NULL, CTA 0 of the layer-1 station-pass kernel stamps clock64() at its pipeline
- * hand-off points into trace_dev[tile * 24 + slot] for its first `tiles` tiles (slots: scripts/trace_s1.py). */
+ * hand-off points into trace_dev[(tile * 2 + pipeline) * 24 + slot] for `tiles` tiles per pipeline (slots: scripts/trace_s1.py). */
 GENIE_API int genie_debug_trace(int64_t* trace_dev, int tiles);
 
 #ifdef __cplusplus

@@ -25,14 +25,19 @@ pos = torch.from_numpy(net.grid).float().to(dev)
 m = GCN_Detection_Network_extended(None, None, device=dev).eval()
 packed = m._packed_weights(dev)
 NTR = 160
-trace = torch.zeros((NTR, 24), dtype=torch.int64, device=dev)
+trace = torch.zeros((NTR, 48), dtype=torch.int64, device=dev)
 for _ in range(2):
     ops.frontend_fwd(plan, packed, Slice, Mask, attr, pos, 30000.0)
 capi.check(capi.load().genie_debug_trace(ctypes.c_void_p(trace.data_ptr()), NTR))
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
 ops.frontend_fwd(plan, packed, Slice, Mask, attr, pos, 30000.0)
+e1.record()
 torch.cuda.synchronize()
+print('front end %.2f ms' % e0.elapsed_time(e1))
 capi.check(capi.load().genie_debug_trace(None, 0))
-t = trace.cpu().numpy().astype(np.float64)
+tt = trace.cpu().numpy().astype(np.float64).reshape(NTR, 2, 24)
+t = tt[:, 0, :]
 n = min(NTR, (plan.tiles['n_tiles'] * G + 147) // 148 // 2 - int(os.environ.get('GENIE_TRACE_START', 0))) - 2
 t = t[8:n]
 print('tiles traced', len(t), 'cycles per tile (mma slot 0 to next slot 0): %.0f' % np.mean(np.diff(t[:, 0])))
@@ -53,7 +58,20 @@ d(12, 14, 'gather: 16 neighbour rows + unrotate')
 d(14, 15, 'gather: wait for operand slot')
 d(15, 16, 'gather: write STA operand to TMEM')
 d(11, 19, 'epilogue: OWN / SRC operands of the next tile (incl. wait for buffer)')
-d(17, 18, 'producer: issue cp.async')
+d(17, 18, 'producer: issue cp.async + landing')
 print('  %-52s %8.0f' % ('gather: wait for buffer full (after prev operands written)', np.mean(t[1:, 12] - t[:-1, 16])))
 print('  %-52s %8.0f' % ('mma: wait for operands after prev stage D issue', np.mean(t[1:, 0] - t[:-1, 5])))
 print('  %-52s %8.0f' % ('producer: fill latency (issue -> full seen by gather)', np.mean(t[:, 12] - t[:, 18])))
+
+# timeline of a few tiles, both pipelines (cycles relative to the first event shown)
+names = {17: 'P  buffer free', 18: 'P  buffer full', 12: 'G  gather start', 14: 'G  gather done', 16: 'G  STA written', 0: 'M  stage B issue',
+         6: 'E  eB start', 7: 'E  eB done', 8: 'E  eC start', 9: 'E  eC done', 10: 'E  eD start', 11: 'E  eD done', 19: 'E  next OWN/SRC written'}
+ev = []
+for k in range(40, 43):
+    for q in range(2):
+        for s_, nm in names.items():
+            if tt[k, q, s_] > 0:
+                ev.append((tt[k, q, s_], 'tile %d pipe %d  %s' % (k, q, nm)))
+ev.sort()
+for tm_, nm in ev:
+    print('%9.0f  %s' % (tm_ - ev[0][0], nm))
