@@ -17,7 +17,7 @@ _LIB_PATH = os.path.join(_HERE, 'libgenie_b200.so')
 _lib = None
 
 GRAPH_CARTESIAN, GRAPH_EXPLICIT = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 3
 
 c_f32p = ctypes.c_void_p   # device pointers are passed as opaque addresses
 
@@ -34,10 +34,7 @@ class GraphDesc(ctypes.Structure):
                 ('sta_tile_rows', ctypes.c_void_p), ('sta_tile_meta', ctypes.c_void_p),
                 ('sta_tile_nbr', ctypes.c_void_p), ('sta_tile_invdeg', ctypes.c_void_p),
                 ('grid_grp_ptr', ctypes.c_void_p), ('grid_grp_nodes', ctypes.c_void_p),
-                ('n_grid_owned', ctypes.c_int32), ('n_src_quads', ctypes.c_int32),
-                ('src_quad_nodes', ctypes.c_void_p), ('src_quad_invdeg', ctypes.c_void_p),
-                ('src_quad_ptr', ctypes.c_void_p), ('src_quad_list', ctypes.c_void_p),
-                ('src_grp_quad_ptr', ctypes.c_void_p)]
+                ('n_grid_owned', ctypes.c_int32)]
 
 
 class Linear(ctypes.Structure):

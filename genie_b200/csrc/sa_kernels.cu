@@ -79,12 +79,13 @@ __global__ void __launch_bounds__(SA_THREADS)
     __syncthreads();
     const float a1 = w[SA_SLOPES + 0], a2 = w[SA_SLOPES + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float wp0 = sWpg[0 * LD + lane], wp1 = sWpg[1 * LD + lane], wp2 = sWpg[2 * LD + lane];
+    const float inv_scale = 1.f / scale_rel;
+    const float wp0 = sWpg[0 * LD + lane] * inv_scale, wp1 = sWpg[1 * LD + lane] * inv_scale, wp2 = sWpg[2 * LD + lane] * inv_scale;
     const float cgl = cg[lane];
     for (int i = blockIdx.x * SA_WARPS + warp; i < G; i += gridDim.x * SA_WARPS) {
-        const float pix = pos[(int64_t)i * 3 + 0] / scale_rel;
-        const float piy = pos[(int64_t)i * 3 + 1] / scale_rel;
-        const float piz = pos[(int64_t)i * 3 + 2] / scale_rel;
+        const float pix = pos[(int64_t)i * 3 + 0];
+        const float piy = pos[(int64_t)i * 3 + 1];
+        const float piz = pos[(int64_t)i * 3 + 2];
         const int64_t beg = rowptr[i], end = rowptr[i + 1];
         float acc = 0.f;
         for (int64_t e0 = beg; e0 < end; e0 += 32) {
@@ -92,10 +93,10 @@ __global__ void __launch_bounds__(SA_THREADS)
             const int32_t cj = lane < cnt ? col[e0 + lane] : 0;
             for (int u = 0; u < cnt; ++u) {
                 const int64_t j = __shfl_sync(FULL_MASK, cj, u);
-                const float dx = pix - pos[j * 3 + 0] / scale_rel;
-                const float dy = piy - pos[j * 3 + 1] / scale_rel;
-                const float dz = piz - pos[j * 3 + 2] / scale_rel;
-                float m = px[j * 32 + lane] + cgl;
+                const float dx = pix - __ldg(pos + j * 3 + 0);      // (pos_i - pos_j) / scale_rel: the scale is folded into wp*
+                const float dy = piy - __ldg(pos + j * 3 + 1);
+                const float dz = piz - __ldg(pos + j * 3 + 2);
+                float m = __ldg(px + j * 32 + lane) + cgl;
                 m = fmaf(dx, wp0, m);
                 m = fmaf(dy, wp1, m);
                 m = fmaf(dz, wp2, m);
@@ -133,8 +134,12 @@ int launch_spatial_aggregation(const genie_plan* p, const float* packed, int lay
         sa_pre_kernel<<<nb, SA_THREADS, 0, st>>>(w, x, ld_x, C, p->g.grid_outdeg, G, px, partial);
     }
     GENIE_LAUNCH_CHECK();
+    // more, shorter CTAs for the per-node kernel: one warp per target node is latency bound (15 dependent-free row gathers
+    // from L2 and ~75 shuffled FMAs per node), so occupancy is what counts
+    int nb_main = (G + SA_WARPS - 1) / SA_WARPS;
+    if (nb_main > p->sm_count * 8) nb_main = p->sm_count * 8;
     TimedLaunch tl(KID_SA_MAIN, st);
-    sa_main_kernel<<<nb, SA_THREADS, 0, st>>>(w, x, ld_x, C, px, pos, scale_rel, p->g.grid_rowptr, p->g.grid_col, G,
+    sa_main_kernel<<<nb_main, SA_THREADS, 0, st>>>(w, x, ld_x, C, px, pos, scale_rel, p->g.grid_rowptr, p->g.grid_col, G,
                                                partial, nb, out, ld_out);
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;

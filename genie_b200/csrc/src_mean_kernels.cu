@@ -12,6 +12,7 @@
 // is no shared memory, no barrier and no atomics: warps drift apart freely, and the leaders pull the next tile's rows
 // into L1 while the stragglers finish.
 #include "common.cuh"
+#include <cstdlib>
 
 using namespace gl;
 
@@ -110,86 +111,6 @@ __global__ void __launch_bounds__(SM_THREADS, 1)
     }
 }
 
-// ---- quad variant -------------------------------------------------------------------------------------------------------
-// The nodes of a group are matched into quads whose merged neighbour list (genie_graph_desc_t.src_quad_*) holds every
-// distinct row once with a 4-bit membership mask: a row shared by several nodes of the quad is loaded once and added to
-// each of their accumulators (k = 15 nearest neighbours in 3-D: ~31 loads per quad instead of 60 — the L1 wavefronts, the
-// bound of the pass, halve).  One warp = one quad x one slab of 512 bytes of every row (lanes = 16-byte chunks), so the
-// masks are warp-uniform; a 512-thread CTA covers the <= 16 quads of one group, two CTAs per SM work on neighbouring
-// groups of the same slab, and the union of a group's rows is still shared through L1.
-constexpr int SQ_THREADS = 512;
-
-__device__ __forceinline__ void masked_add(f32x4_t (&a)[4], const float4& v, uint32_t w) {
-    if (w & (1u << 28)) fadd4(a[0], v);
-    if (w & (2u << 28)) fadd4(a[1], v);
-    if (w & (4u << 28)) fadd4(a[2], v);
-    if (w & (8u << 28)) fadd4(a[3], v);
-}
-
-template <int W>
-__global__ void __launch_bounds__(SQ_THREADS, 2)
-    src_mean_quad_kernel(const float* __restrict__ X, float* __restrict__ out, int S, const int32_t* __restrict__ quad_ptr,
-                         const uint32_t* __restrict__ quad_list, const int32_t* __restrict__ quad_nodes,
-                         const float* __restrict__ quad_invdeg, const int32_t* __restrict__ grp_quad_ptr, int n_groups,
-                         int n_slabs, const float* __restrict__ gate) {
-    if (gate != nullptr && *gate == 0.f) return;     // the one-pass kernels run instead (layout.h TCS_OK)
-    constexpr int LPR = W / 4;                       // lanes (16-byte chunks) per row
-    constexpr int SB = 32 / LPR;                     // stations per slab: one warp spans 512 bytes of every row
-    constexpr uint32_t ID = 0x0fffffffu;
-    const float4* __restrict__ X4 = reinterpret_cast<const float4*>(X);
-    float4* __restrict__ O4 = reinterpret_cast<float4*>(out);
-    const uint32_t gstride = (uint32_t)S * LPR;      // float4 units between consecutive grid nodes (P * LPR < 2^32 checked)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t n_tiles = (int64_t)n_groups * n_slabs;
-    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int slab = (int)(t / n_groups);
-        const int grp = (int)(t - (int64_t)slab * n_groups);
-        const int q0 = __ldg(grp_quad_ptr + grp);
-        const int nq = __ldg(grp_quad_ptr + grp + 1) - q0;
-        const int s = slab * SB + lane / LPR;
-        if (s >= S) continue;                        // ragged last slab
-        const uint32_t off = (uint32_t)s * LPR + (lane % LPR);
-        for (int qi = warp; qi < nq; qi += SQ_THREADS / 32) {
-            const int quad = q0 + qi;
-            int e = __ldg(quad_ptr + quad);
-            const int end = __ldg(quad_ptr + quad + 1);
-            f32x4_t a[4];
-#pragma unroll
-            for (int b = 0; b < 4; ++b) a[b].lo = a[b].hi = 0ull;
-            for (; e + 8 <= end; e += 8) {
-                const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(quad_list + e));
-                const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(quad_list + e + 4));
-                const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-                float4 v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = __ldg(X4 + ((w[u] & ID) * gstride + off));
-#pragma unroll
-                for (int u = 0; u < 8; ++u) masked_add(a, v[u], w[u]);
-            }
-            if (e < end) {                           // segments are padded to a multiple of four entries
-                const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(quad_list + e));
-                const uint32_t w[4] = {w0.x, w0.y, w0.z, w0.w};
-                float4 v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = __ldg(X4 + ((w[u] & ID) * gstride + off));
-#pragma unroll
-                for (int u = 0; u < 4; ++u) masked_add(a, v[u], w[u]);
-            }
-            const int4 nd = __ldg(reinterpret_cast<const int4*>(quad_nodes) + quad);
-            const float4 inv = __ldg(reinterpret_cast<const float4*>(quad_invdeg) + quad);
-            const int nds[4] = {nd.x, nd.y, nd.z, nd.w};
-            const float invs[4] = {inv.x, inv.y, inv.z, inv.w};
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                if (nds[b] < 0) continue;
-                const float4 r = to_float4(a[b]);
-                __stcs(O4 + ((uint32_t)nds[b] * gstride + off),
-                       make_float4(r.x * invs[b], r.y * invs[b], r.z * invs[b], r.w * invs[b]));
-            }
-        }
-    }
-}
-
 }  // namespace
 
 bool split_supported(const genie_plan* p) {
@@ -209,37 +130,29 @@ static void launch_src_mean_t(const genie_plan* p, const float* X, float* out, c
                                                         g.grid_grp_nodes, g.n_grid_groups, n_slabs, gate);
 }
 
-template <int W>
-static void launch_src_mean_quad(const genie_plan* p, const float* X, float* out, const float* gate, cudaStream_t st) {
-    const genie_graph_desc_t& g = p->g;
-    constexpr int SB = 32 / (W / 4);
-    const int n_slabs = (g.n_sta + SB - 1) / SB;
-    const int64_t n_tiles = (int64_t)g.n_grid_groups * n_slabs;
-    const int64_t cap = 2 * (int64_t)p->sm_count;
-    const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
-    src_mean_quad_kernel<W><<<grid, SQ_THREADS, 0, st>>>(X, out, g.n_sta, g.src_quad_ptr, g.src_quad_list, g.src_quad_nodes,
-                                                         g.src_quad_invdeg, g.src_grp_quad_ptr, g.n_grid_groups, n_slabs, gate);
-}
-
 int launch_src_mean(const genie_plan* p, int width, const float* X, float* out, const float* gate, cudaStream_t st) {
-    const genie_graph_desc_t& gd = p->g;
-    const bool quads = gd.n_src_quads > 0 && gd.src_quad_ptr && gd.src_quad_list && gd.src_quad_nodes &&
-                       gd.src_quad_invdeg && gd.src_grp_quad_ptr && gd.n_grid < (1 << 28);
-    if (quads && (width == 32 || width == 16)) {
-        TimedLaunch tl(width == 32 ? KID_SRC_MEAN32 : KID_SRC_MEAN16, st);
-        if (width == 32) launch_src_mean_quad<32>(p, X, out, gate, st);
-        else launch_src_mean_quad<16>(p, X, out, gate, st);
-        GENIE_LAUNCH_CHECK();
-        return GENIE_OK;
-    }
     // one slab = 512 bytes of every neighbour row: 4 stations of 128-byte rows, 8 stations of 64-byte rows
     // (64 grid nodes x 2 station pairs x 8 lanes = 1024 items: one item per thread of the CTA)
+    // One slab = 8 stations of every neighbour row (1024 B of 128-byte rows, 512 B of 64-byte rows): measured best on B200
+    // together with groups of 256 grid nodes (r1zd / r1ze sweeps: 5.2 -> 3.9 ms and 3.6 -> 3.3 ms at C4).
+    static int slab32 = 0, slab16 = 0;             // development knobs: bytes of every neighbour row one tile covers
+    if (slab32 == 0) {
+        const char* e = getenv("GENIE_SRC_SLAB32");
+        slab32 = e ? atoi(e) : 1024;
+        e = getenv("GENIE_SRC_SLAB16");
+        slab16 = e ? atoi(e) : 512;
+    }
     if (width == 32) {
         TimedLaunch tl(KID_SRC_MEAN32, st);
-        launch_src_mean_t<32, 4>(p, X, out, gate, st);
+        if (slab32 == 256) launch_src_mean_t<32, 2>(p, X, out, gate, st);
+        else if (slab32 == 512) launch_src_mean_t<32, 4>(p, X, out, gate, st);
+        else if (slab32 == 2048) launch_src_mean_t<32, 16>(p, X, out, gate, st);
+        else launch_src_mean_t<32, 8>(p, X, out, gate, st);
     } else if (width == 16) {
         TimedLaunch tl(KID_SRC_MEAN16, st);
-        launch_src_mean_t<16, 8>(p, X, out, gate, st);
+        if (slab16 == 256) launch_src_mean_t<16, 4>(p, X, out, gate, st);
+        else if (slab16 == 1024) launch_src_mean_t<16, 16>(p, X, out, gate, st);
+        else launch_src_mean_t<16, 8>(p, X, out, gate, st);
     } else {
         set_error("launch_src_mean: unsupported row width");
         return GENIE_ERR_INVALID;

@@ -9,6 +9,8 @@ stay implicit — at 1000 stations x 50000 grid nodes the explicit lists would b
 """
 import ctypes
 
+import os
+
 import numpy as np
 import torch
 
@@ -46,7 +48,7 @@ def locality_order(rowptr, col, n):
 # ---- on-chip tiling tables of the split (source pass / station pass) kernels ----------------------------------------------
 TILE_M = 128        # product-node rows of one station tile (= MMA M)
 ROWS_MAX = 288      # station rows (tile + halo) staged in shared memory per tile; row ROWS_MAX is an all-zero row
-GROUP_SIZE = 64     # grid nodes per source-pass group
+GROUP_SIZE = int(os.environ.get('GENIE_GROUP_SIZE', 256))    # grid nodes per source-pass group (measured best on B200)
 
 
 def bisection_groups(rowptr, col, n, size):
@@ -125,67 +127,6 @@ def station_tiles(rowptr, col, n_sta, tile_m=TILE_M, rows_max=ROWS_MAX):
     return None
 
 
-def source_quads(rowptr, col, grp_ptr, grp_nodes, pad=4):
-    """Quad tables of the source pass: the nodes of every grid group are matched greedily (largest overlap of the
-    neighbour sets first) into quads of <= 4 nodes; a quad's four neighbour lists are merged into ONE list of distinct rows
-    with a 4-bit membership mask each, so a row shared by several nodes of the quad is loaded once (k = 15 nearest
-    neighbours in 3-D: ~31 distinct rows per quad instead of 60).  Returns a dict of numpy arrays
-      nodes   int32  [NQ, 4]    grid node of each slot (-1 = empty)
-      invdeg  fp32   [NQ, 4]    1 / in-degree (0 for nodes without in-edges: PyG's mean of nothing is 0)
-      ptr     int32  [NQ + 1]   offsets into `list`; every quad's segment is padded to a multiple of `pad` (4) entries
-      list    uint32 [L]        (mask << 28) | neighbour grid node        (padding: mask 0, a valid node)
-      grp_ptr int32  [NG + 1]   first quad of every group."""
-    rp = np.asarray(rowptr.cpu() if torch.is_tensor(rowptr) else rowptr).astype(np.int64)
-    cl = np.asarray(col.cpu() if torch.is_tensor(col) else col).astype(np.int64)
-    if len(rp) - 1 >= (1 << 28):
-        return None
-    nodes, invdeg, ptr, lst, gq = [], [], [0], [], [0]
-    for gi in range(len(grp_ptr) - 1):
-        own = grp_nodes[grp_ptr[gi]:grp_ptr[gi + 1]]
-        nsets = {int(g): set(cl[rp[g]:rp[g + 1]].tolist()) for g in own}
-        left = [int(g) for g in own]
-        quads = []
-        while left:
-            quad, union = [left.pop(0)], None
-            union = set(nsets[quad[0]])
-            while len(quad) < 4 and left:
-                best = max(left, key=lambda b_: len(union & nsets[b_]))
-                left.remove(best)
-                quad.append(best)
-                union |= nsets[best]
-            quads.append(quad)
-        for quad in quads:
-            masks = {}
-            inv = [0.0] * 4
-            for slot, g in enumerate(quad):
-                js = cl[rp[g]:rp[g + 1]]
-                if len(js):
-                    inv[slot] = float(np.float32(1.0) / np.float32(len(js)))
-                for j in js:
-                    j = int(j)
-                    masks[j] = masks.get(j, 0) + (1 << slot)      # a repeated edge is listed (and added) again below
-            ent = []
-            for slot, g in enumerate(quad):                       # multigraph edges: keep the multiplicity exact
-                js = cl[rp[g]:rp[g + 1]]
-                seen = {}
-                for j in js:
-                    seen[int(j)] = seen.get(int(j), 0) + 1
-                for j, c in seen.items():
-                    for _ in range(c - 1):
-                        ent.append((1 << slot, j))
-                        masks[j] -= (1 << slot)
-            ent = [(m, j) for j, m in sorted(masks.items()) if m > 0] + ent
-            while len(ent) % pad:
-                ent.append((0, quad[0]))
-            lst.extend(((m << 28) | j) for m, j in ent)
-            ptr.append(len(lst))
-            nodes.append(quad + [-1] * (4 - len(quad)))
-            invdeg.append(inv)
-        gq.append(len(nodes))
-    return dict(nodes=np.asarray(nodes, dtype=np.int32).reshape(-1, 4), invdeg=np.asarray(invdeg, dtype=np.float32).reshape(-1, 4),
-                ptr=np.asarray(ptr, dtype=np.int32), list=np.asarray(lst, dtype=np.uint32), grp_ptr=np.asarray(gq, dtype=np.int32))
-
-
 def _is_cartesian(A_in_sta, A_in_src, prod_target, S, G):
     """Checks the index patterns of process_utils.py:720-722; returns (A_sta_sta, A_src_src) or None."""
     P = S * G
@@ -258,11 +199,6 @@ class GraphPlan(object):
                                   rows=put(st['rows']), meta=put(st['meta']),
                                   nbr=put(st['nbr'].view(np.int16)), invdeg=put(st['invdeg']),
                                   grp_ptr=put(gp), grp_nodes=put(gn))
-                sq = source_quads(src[0], src[1], gp, gn)
-                if sq is not None:
-                    self.tiles.update(n_quads=int(sq['nodes'].shape[0]), quad_nodes=put(sq['nodes']),
-                                      quad_invdeg=put(sq['invdeg']), quad_ptr=put(sq['ptr']),
-                                      quad_list=put(sq['list'].view(np.int32)), grp_quad_ptr=put(sq['grp_ptr']))
         self._keep = (sta, src, grid, grid_outdeg, prod_grid, self.grid_order, self.tiles)     # keep the tensors alive
         self.sta_rowptr, self.sta_col = sta
         self.src_rowptr, self.src_col = src
@@ -289,13 +225,6 @@ class GraphPlan(object):
             d.sta_tile_invdeg = capi.dptr(t['invdeg'], torch.float32, 'sta_tile_invdeg')
             d.grid_grp_ptr = capi.dptr(t['grp_ptr'], torch.int32, 'grid_grp_ptr')
             d.grid_grp_nodes = capi.dptr(t['grp_nodes'], torch.int32, 'grid_grp_nodes')
-            if 'n_quads' in t:
-                d.n_src_quads = t['n_quads']
-                d.src_quad_nodes = capi.dptr(t['quad_nodes'], torch.int32, 'src_quad_nodes')
-                d.src_quad_invdeg = capi.dptr(t['quad_invdeg'], torch.float32, 'src_quad_invdeg')
-                d.src_quad_ptr = capi.dptr(t['quad_ptr'], torch.int32, 'src_quad_ptr')
-                d.src_quad_list = capi.dptr(t['quad_list'], torch.int32, 'src_quad_list')
-                d.src_grp_quad_ptr = capi.dptr(t['grp_quad_ptr'], torch.int32, 'src_grp_quad_ptr')
         d.n_grid_owned = self.n_grid_owned
         self._desc = d
         lib = capi.load()

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GENIE_B200_ABI_VERSION 4
+#define GENIE_B200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define GENIE_API __attribute__((visibility("default")))
@@ -91,20 +91,6 @@ typedef struct genie_graph_desc {
      * halo copies of other ranks' nodes (their inputs are present, their layer-1 outputs arrive by exchange: see
      * genie_da_layer1_fwd).  0 = all n_grid nodes are owned.  grid_grp_nodes must then list owned nodes only. */
     int32_t n_grid_owned;
-    /* Optional quad tables of the source pass (with the grid groups above; leave n_src_quads 0 to sum every node's
-     * neighbour list on its own).  The nodes of a group are cut into quads of <= 4 nodes whose neighbour lists are merged:
-     *   src_quad_nodes int32 [NQ][4] (-1 = empty slot), src_quad_invdeg fp32 [NQ][4] = 1 / in-degree (0 if none),
-     *   src_quad_ptr int32 [NQ+1] offsets into src_quad_list uint32 [L], entries (mask << 28) | neighbour grid node, bit b of
-     *   mask set when the row is a source neighbour of slot b (a row with multiplicity is listed once per edge; every
-     *   quad's segment is padded to a multiple of 4 entries with mask 0), src_grp_quad_ptr int32 [NG+1] = first quad of
-     *   every group.  Every owned grid node must appear in exactly one quad.  Results do not depend on the tables beyond
-     *   the order of the fp32 additions. */
-    int32_t n_src_quads;
-    const int32_t* src_quad_nodes;
-    const float* src_quad_invdeg;
-    const int32_t* src_quad_ptr;
-    const uint32_t* src_quad_list;
-    const int32_t* src_grp_quad_ptr;
 } genie_graph_desc_t;
 
 #define GENIE_TILE_ROWS_MAX 288

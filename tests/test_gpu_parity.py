@@ -160,6 +160,37 @@ def test_front_end_matches_oracle_seeded(S, G, k_s, k_g):
     assert rel_err(xs.cpu().numpy(), want.numpy()) < TOL
 
 
+@pytest.mark.parametrize('a11,a12', [(0.07, 0.9), (1.7, 0.02), (5e-4, 0.3), (0.3, 0.0), (-0.2, 0.25)])
+def test_prelu_slopes_pick_the_kernel_family(a11, a12):
+    """The tensor-core station pass stages PReLU11(tr0) and PReLU12(tr0) and recovers tr0 from them, which needs both slopes
+    in (1e-3, 1e3); otherwise the generic FFMA kernels run (decided on the device from the packed weights, layout.h TCS_OK).
+    Either way the result is the reference's (module.py:88-96)."""
+    from genie_b200 import ops
+    from genie_b200.plan import GraphPlan
+    from genie_b200.process_utils import product_edge_lists
+    from oracle import genie_oracle as go
+    dev = _dev()
+    S, G = 150, 260
+    net, A_sta, A_src, Slice, Mask, attr = _random_case(S, G, 15, 15, 23, dev)
+    sd = go.init_state(seed=7)
+    sd['DataAggregation.activate11.weight'] = torch.full((1,), a11)
+    sd['DataAggregation.activate12.weight'] = torch.full((1,), a12)
+    A_ps, A_pg, A_sip, _ = product_edge_lists(A_sta, A_src, S, G)
+    grid = torch.from_numpy(net.grid).float()
+    want, parts = go.front_end(sd, Slice, Mask, A_ps, A_pg, attr, A_sip, A_src, grid, 30000.0, return_parts=True)
+    from genie_b200.module import GCN_Detection_Network_extended
+    m = GCN_Detection_Network_extended(None, None, device=dev)
+    m.load_state_dict(sd, strict=False)
+    packed = m._packed_weights(dev)
+    plan = GraphPlan.cartesian(A_sta, A_src, S, G, device=dev)
+    assert plan.tiles is not None
+    xs, lat, r = ops.frontend_fwd(plan, packed, Slice.to(dev), Mask.to(dev), attr.to(dev), grid.to(dev), 30000.0,
+                                  want_latent=True, want_readin=True)
+    assert rel_err(lat.cpu().numpy(), parts['x_latent'].numpy()) < TOL
+    assert rel_err(r.cpu().numpy(), parts['read_in'].numpy()) < TOL
+    assert rel_err(xs.cpu().numpy(), want.numpy()) < TOL
+
+
 def test_one_pass_kernels_match_split_kernels():
     """Plans without tiling tables run the one-pass kernels (tcgen05 layer 1 with L2 gathers, FFMA layer 2 with atomics);
     plans with them run the split source-pass / station-pass kernels.  Same mathematics, different tiling."""

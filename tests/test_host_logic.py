@@ -200,46 +200,3 @@ def test_bisection_groups_partition_and_compactness():
     union = [len(set(np.concatenate([cl[rp[g]:rp[g + 1]] for g in nodes[ptr[i]:ptr[i + 1]]]).tolist()))
              for i in range(len(sizes))]
     assert np.sum(sizes) * 15 / np.sum(union) > 3.0             # neighbour rows are re-used > 3x inside a group
-
-
-def test_source_quads_reproduce_the_source_mean():
-    """plan.source_quads: every grid node sits in exactly one quad, and summing the quad's merged neighbour list under the
-    node's mask bit gives the node's own neighbour sum (multi-edges included); mean = PyG's (module.py:91, 95)."""
-    from genie_b200 import plan
-    rng = np.random.RandomState(5)
-    G, k = 700, 15
-    pos = rng.rand(G, 3)
-    d = ((pos[:, None, :] - pos[None, :, :]) ** 2).sum(-1)
-    nbr = np.argsort(d, axis=1)[:, :k]                                # includes the node itself, like the reference's knn
-    src = nbr.reshape(-1)
-    dst = np.repeat(np.arange(G), k)
-    src[:3] = src[3]                                                  # a repeated edge into node 0
-    keep = np.ones(len(src), bool)
-    keep[dst == 5] = False                                            # node 5 has no in-edges
-    A = torch.from_numpy(np.stack([src[keep], dst[keep]]))
-    rp, cl = plan.csr_by_destination(A, G)
-    gp, gn = plan.bisection_groups(rp, cl, G, 64)
-    sq = plan.source_quads(rp, cl, gp, gn)
-    assert sorted(sq['nodes'][sq['nodes'] >= 0].tolist()) == list(range(G))
-    assert np.all(np.diff(sq['ptr']) % 4 == 0) and sq['grp_ptr'][-1] == sq['nodes'].shape[0]
-    x = rng.rand(G).astype(np.float64)
-    want = np.zeros(G)
-    rpn, cln = rp.numpy(), cl.numpy()
-    for g in range(G):
-        js = cln[rpn[g]:rpn[g + 1]]
-        want[g] = x[js].mean() if len(js) else 0.0
-    got = np.zeros(G)
-    for qd in range(sq['nodes'].shape[0]):
-        ent = sq['list'][sq['ptr'][qd]:sq['ptr'][qd + 1]]
-        for b in range(4):
-            g = sq['nodes'][qd, b]
-            if g < 0:
-                continue
-            sel = ((ent >> 28) >> b) & 1
-            got[g] = x[(ent & 0x0fffffff)[sel == 1]].sum() * sq['invdeg'][qd, b]
-    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-9)
-    # quads of one group stay inside the group
-    for gi in range(len(gp) - 1):
-        own = set(gn[gp[gi]:gp[gi + 1]].tolist())
-        q = sq['nodes'][sq['grp_ptr'][gi]:sq['grp_ptr'][gi + 1]]
-        assert set(q[q >= 0].tolist()) == own
