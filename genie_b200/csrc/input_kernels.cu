@@ -38,7 +38,8 @@ __global__ void input_series_kernel(const genie_input_params_t prm, const double
     const double d = __dsub_rn(t, ref);
     const double arg = __ddiv_rn(__dmul_rn(-0.5, __dmul_rn(d, d)), __dmul_rn(prm.kernel_sig_t, prm.kernel_sig_t));
     const float v = (float)exp(arg);
-    int* cell = reinterpret_cast<int*>(series + ((int64_t)ph * prm.n_sta_use + s) * prm.n_ts + bin);
+    // scratch layout [station][bin][phase]: the gather kernel reads both phases of a bin with one 8-byte load
+    int* cell = reinterpret_cast<int*>(series + (((int64_t)s * prm.n_ts + bin) * 2 + ph));
     atomicMax(cell, __float_as_int(v));
 }
 
@@ -51,8 +52,13 @@ __global__ void input_gather_kernel(const genie_input_params_t prm, int mode, in
     if (i >= P) return;
     int s, g;
     if (mode == GENIE_GRAPH_CARTESIAN && node_sta == nullptr) {
-        g = (int)(i / S);
-        s = (int)(i - (int64_t)g * S);
+        if (P < (int64_t)0x7fffffff) {             // 32-bit division: the 64-bit one costs ~100 instructions
+            g = (int)((uint32_t)i / (uint32_t)S);
+            s = (int)((uint32_t)i - (uint32_t)g * (uint32_t)S);
+        } else {
+            g = (int)(i / S);
+            s = (int)(i - (int64_t)g * S);
+        }
     } else {
         s = node_sta[i];
         g = node_grid[i];
@@ -61,14 +67,15 @@ __global__ void input_gather_kernel(const genie_input_params_t prm, int mode, in
     const float2 tt = *reinterpret_cast<const float2*>(trv + ((int64_t)g * prm.n_locs + sta_abs) * 2);
     const long long bp = (long long)__ddiv_rn(__dsub_rn(__dadd_rn((double)tt.x, prm.t0), prm.ref0), prm.dt);
     const long long bs = (long long)__ddiv_rn(__dsub_rn(__dadd_rn((double)tt.y, prm.t0), prm.ref0), prm.dt);
-    const float* sp = series + (int64_t)s * prm.n_ts;
-    const float* ss = series + ((int64_t)prm.n_sta_use + s) * prm.n_ts;
+    const float2* sr = reinterpret_cast<const float2*>(series) + (int64_t)s * prm.n_ts;      // [bin] = (P series, S series)
     const bool okp = bp > 0 && bp < (long long)prm.n_ts - 1;
     const bool oks = bs > 0 && bs < (long long)prm.n_ts - 1;
-    const float pp = okp ? sp[bp] : 0.f;   // P series at the P bin
-    const float sp_ = okp ? ss[bp] : 0.f;  // S series at the P bin
-    const float ps = oks ? sp[bs] : 0.f;   // P series at the S bin
-    const float ss_ = oks ? ss[bs] : 0.f;  // S series at the S bin
+    const float2 at_p = okp ? __ldg(sr + bp) : make_float2(0.f, 0.f);
+    const float2 at_s = oks ? __ldg(sr + bs) : make_float2(0.f, 0.f);
+    const float pp = at_p.x;   // P series at the P bin
+    const float sp_ = at_p.y;  // S series at the P bin
+    const float ps = at_s.x;   // P series at the S bin
+    const float ss_ = at_s.y;  // S series at the S bin
     float4 o;
     o.x = fmaxf(pp, sp_);
     o.y = fmaxf(ps, ss_);
@@ -79,7 +86,7 @@ __global__ void input_gather_kernel(const genie_input_params_t prm, int mode, in
     m.y = fabsf(o.y) > 0.01f ? 1.f : 0.f;
     m.z = fabsf(o.z) > 0.01f ? 1.f : 0.f;
     m.w = fabsf(o.w) > 0.01f ? 1.f : 0.f;
-    reinterpret_cast<float4*>(slice_out)[i] = o;
+    __stcs(reinterpret_cast<float4*>(slice_out) + i, o);     // read once, by the next kernel
     reinterpret_cast<float4*>(mask_out)[i] = m;
     if (time_bin_out != nullptr) {
         time_bin_out[i * 2 + 0] = bp;

@@ -161,7 +161,7 @@ typedef struct genie_input_params {
  * ind_use_dev    int32 [n_sta_use]: used station -> absolute station.
  * trv_times_dev  fp32 [n_grid, n_locs, 2] travel times (s).
  * node_sta_dev / node_grid_dev: int32 [n_prod] (A_src_in_sta rows 0/1) or both NULL in CARTESIAN mode.
- * series_dev     fp32 scratch [2, n_sta_use, n_ts] (overwritten).
+ * series_dev     fp32 scratch, 2 * n_sta_use * n_ts floats (overwritten; internal layout [station][bin][phase]).
  * slice_out_dev, mask_out_dev: fp32 [n_prod,4].  time_bin_out_dev: optional int64 [n_prod,2] (the integer index map).
  */
 GENIE_API int genie_input_scatter_fwd(const genie_plan_t* plan, const genie_input_params_t* prm, const double* picks_dev,
