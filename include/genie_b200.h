@@ -13,7 +13,9 @@
  *     the stream.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
  *   - all floating point tensors are fp32, row-major, dense; index arrays are int32 (columns) / int64 (row pointers).
  *   - return value: 0 = ok, non-zero = error; genie_last_error() returns a thread-local message.
- *   - re-entrant across distinct plans / workspaces; calls that share a workspace must be stream-ordered.
+ *   - re-entrant across distinct plans / workspaces; calls that share a workspace must be stream-ordered.  Two small
+ *     weight blocks (init_trns, read-in fc1) are refreshed in __constant__ memory, in stream order, before the kernels that
+ *     read them: forward calls with DIFFERENT packed weights must therefore not overlap on one device (same weights: fine).
  */
 #ifndef GENIE_B200_H_
 #define GENIE_B200_H_
