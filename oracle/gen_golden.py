@@ -1,6 +1,7 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference (TEST INFRASTRUCTURE; build container only).
 
     python oracle/gen_golden.py synthetic      # seeded synthetic networks, reference default-initialised weights
+    python oracle/gen_golden.py synthetic_edges  # same, `use_updated_model_definition: True` (DataAggregationEdges)
     python oracle/gen_golden.py ferndale       # Examples/Ferndale.zip: real stations/grids/picks + trained checkpoint
 
 The reference classes (`/root/reference/Code/module.py`, `process_utils.py`) are imported as they are, with
@@ -102,11 +103,20 @@ def _run_reference_window(torch, module, pu, Data, mz, locs, ind_use, grid, trv_
     return res
 
 
-def synthetic():
+def synthetic(edges=False):
+    """edges=True: the reference's `use_updated_model_definition: True` classes (DataAggregationEdges, module.py:102-174,
+    1024-1111); the YAML copy in the scratch directory is switched, the reference sources are untouched."""
     work = tempfile.mkdtemp(prefix='genie_golden_')
     for f in ('config.yaml', 'train_config.yaml'):
         shutil.copy(os.path.join(REF, 'Code', f), work)
+    if edges:
+        import re
+        cfg = open(os.path.join(work, 'config.yaml')).read()
+        cfg, n = re.subn(r'(?m)^use_updated_model_definition:\s*\w+', 'use_updated_model_definition: True', cfg)
+        assert n == 1
+        open(os.path.join(work, 'config.yaml'), 'w').write(cfg)
     torch, module, pu, Data = _import_reference(os.path.join(REF, 'Code'), work)
+    assert bool(module.use_updated_model_definition) == edges
     from genie_b200 import synth
 
     def identity(x):
@@ -117,6 +127,8 @@ def synthetic():
         ('mid_36of40x300', 40, 36, 300, 8, 15, 128, 3),     # station subset (ind_use != arange), k_s < S-2
         ('small_6x40', 6, 6, 40, 8, 15, 16, 5),             # k_sta clipped to S-2 (process_utils.py:712)
     ]
+    if edges:
+        cases = [('c1_10x100_edges', 10, 10, 100, 8, 15, 64, 0), ('mid_36of40x300_edges', 40, 36, 300, 8, 15, 128, 3)]
     for name, S_all, n_use, G, k_sta, k_spc, Q, seed in cases:
         net = synth.Network(S_all, G, seed=seed, width_km=60.0 if S_all <= 10 else 120.0)
         rng = np.random.default_rng(100 + seed)
@@ -150,6 +162,8 @@ if __name__ == '__main__':
     mode = sys.argv[1] if len(sys.argv) > 1 else 'synthetic'
     if mode == 'synthetic':
         synthetic()
+    elif mode == 'synthetic_edges':
+        synthetic(edges=True)
     elif mode == 'ferndale':
         from gen_golden_ferndale import ferndale
         ferndale()

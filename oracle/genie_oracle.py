@@ -203,6 +203,38 @@ def data_aggregation(sd, pre, Slice, Mask, A_in_sta, A_in_src, return_parts=Fals
     return out
 
 
+def edge_features(pos_loc, pos_src, A_src_in_sta, A_in_sta, A_in_src, scale_rel):
+    """pos_rel_sta / pos_rel_src of the `use_updated_model_definition: True` model (module.py:1102-1111): per product edge
+    [dx, dy, dz, |d|] of (source node - target node), embedded as sign(v) * exp(-0.5 v^2 / scale_rel^2)."""
+    def emb(pos, idx, edges):
+        d = pos[idx[edges[0]]] - pos[idx[edges[1]]]
+        d = torch.cat((d, torch.norm(d, dim=1, keepdim=True)), dim=1)
+        return torch.sign(d) * torch.exp(-0.5 * (d ** 2) / (scale_rel ** 2))
+    return emb(pos_loc, A_src_in_sta[0], A_in_sta), emb(pos_src, A_src_in_sta[1], A_in_src)
+
+
+def data_aggregation_edges(sd, pre, Slice, Mask, A_in_sta, A_in_src, pos_rel_sta, pos_rel_src, return_parts=False):
+    """a2' — DataAggregationEdges.forward / message (module.py:143-174): as data_aggregation, but every message is
+    [x_j | pos_rel(edge)] (4 more channels), so l*_t*_2 take 68 / 98 inputs ordered [tr | mean x_j | mean pos_rel | mask]."""
+    n = Slice.shape[0]
+
+    def agg(edges, x, pos_rel):
+        return propagate_mean(torch.cat((x.index_select(0, edges[0]), pos_rel), dim=1), edges[1], n)        # :164-174
+
+    tr0 = _prelu(sd, pre + 'activate', _lin(sd, pre + 'init_trns', torch.cat((Slice, Mask), dim=-1)))        # :145-146
+    tr1 = _lin(sd, pre + 'l1_t1_2', torch.cat((tr0, agg(A_in_sta, _prelu(sd, pre + 'activate11', tr0), pos_rel_sta), Mask), dim=1))
+    tr2 = _lin(sd, pre + 'l1_t2_2', torch.cat((tr0, agg(A_in_src, _prelu(sd, pre + 'activate12', tr0), pos_rel_src), Mask), dim=1))
+    tr = _prelu(sd, pre + 'activate1', torch.cat((tr1, tr2), dim=1))                                          # :161-163
+    a = _prelu(sd, pre + 'activate21', _lin(sd, pre + 'l2_t1_1', tr))
+    b = _prelu(sd, pre + 'activate22', _lin(sd, pre + 'l2_t2_1', tr))
+    o1 = _lin(sd, pre + 'l2_t1_2', torch.cat((tr, agg(A_in_sta, a, pos_rel_sta), Mask), dim=1))               # :165
+    o2 = _lin(sd, pre + 'l2_t2_2', torch.cat((tr, agg(A_in_src, b, pos_rel_src), Mask), dim=1))               # :166
+    out = _prelu(sd, pre + 'activate2', torch.cat((o1, o2), dim=1))                                           # :167
+    if return_parts:
+        return out, dict(tr0=tr0, tr=tr)
+    return out
+
+
 # --------------------------------------------------------------------------------------------------------------------
 # a3 — BipartiteGraphOperator (module.py:214-229)
 # --------------------------------------------------------------------------------------------------------------------
@@ -274,9 +306,13 @@ def temporal_attention(sd, pre, x, t_query, scale_t, n_heads=5, n_latent=15):
 
 
 def front_end(sd, Slice, Mask, A_in_sta, A_in_src, read_in_attr, read_in_index, A_src, grid_cart, scale_rel,
-              return_parts=False):
-    """a2 -> a3 -> a4 x3: the product-graph front end of module.py:1010-1014."""
-    x_latent = data_aggregation(sd, 'DataAggregation.', Slice, Mask, A_in_sta, A_in_src)
+              return_parts=False, pos_rel=None):
+    """a2 -> a3 -> a4 x3: the product-graph front end of module.py:1010-1014.  `pos_rel` = (pos_rel_sta, pos_rel_src) selects
+    the `use_updated_model_definition: True` DataAggregationEdges (module.py:1176)."""
+    if pos_rel is not None:
+        x_latent = data_aggregation_edges(sd, 'DataAggregation.', Slice, Mask, A_in_sta, A_in_src, pos_rel[0], pos_rel[1])
+    else:
+        x_latent = data_aggregation(sd, 'DataAggregation.', Slice, Mask, A_in_sta, A_in_src)
     r = bipartite_read_in(sd, 'Bipartite_ReadIn.', x_latent, read_in_attr, read_in_index, Mask)
     x1 = spatial_aggregation(sd, 'SpatialAggregation1.', r, A_src, grid_cart, scale_rel)
     x2 = spatial_aggregation(sd, 'SpatialAggregation2.', x1, A_src, grid_cart, scale_rel)
@@ -287,10 +323,10 @@ def front_end(sd, Slice, Mask, A_in_sta, A_in_src, read_in_attr, read_in_index, 
 
 
 def forward_fixed_source(sd, Slice, Mask, A_in_sta, A_in_src, read_in_attr, read_in_index, A_src, grid_cart,
-                         x_query_cart, t_query, scale_rel, scale_t, return_parts=False, query_edges=None):
-    """module.py:999-1020 (use_absolute_pos False): returns y [G,T,1] and x [Q,T,1]."""
+                         x_query_cart, t_query, scale_rel, scale_t, return_parts=False, query_edges=None, pos_rel=None):
+    """module.py:999-1020 / 1165-1186 (use_absolute_pos False): returns y [G,T,1] and x [Q,T,1]."""
     x_spatial, parts = front_end(sd, Slice, Mask, A_in_sta, A_in_src, read_in_attr, read_in_index, A_src, grid_cart,
-                                 scale_rel, return_parts=True)
+                                 scale_rel, return_parts=True, pos_rel=pos_rel)
     y_latent = spatial_direct(sd, 'SpatialDirect.', x_spatial)
     y = temporal_attention(sd, 'TemporalAttention.', y_latent, t_query, scale_t)
     xq = spatial_attention(sd, 'SpatialAttention.', x_spatial, x_query_cart, grid_cart, scale_rel,
@@ -302,7 +338,7 @@ def forward_fixed_source(sd, Slice, Mask, A_in_sta, A_in_src, read_in_attr, read
     return y, x
 
 
-def init_state(seed=2, scale=1.0):
+def init_state(seed=2, scale=1.0, edges=False):
     """Random-init weights with the reference's key names / shapes (nn.Linear & nn.PReLU defaults are NOT reproduced —
     tests that need the reference's own init load a golden state_dict instead).  Used for seeded synthetic parity."""
     g = torch.Generator().manual_seed(seed)
@@ -317,9 +353,10 @@ def init_state(seed=2, scale=1.0):
         sd[name + '.weight'] = torch.full((1,), 0.25) + 0.1 * (torch.rand(1, generator=g) - 0.5)
 
     p = 'DataAggregation.'
-    lin(p + 'init_trns', 8, 30); lin(p + 'l1_t1_1', 30, 30); lin(p + 'l1_t1_2', 64, 30)
-    lin(p + 'l1_t2_1', 4, 30); lin(p + 'l1_t2_2', 64, 30); lin(p + 'l2_t1_1', 60, 30); lin(p + 'l2_t1_2', 94, 15)
-    lin(p + 'l2_t2_1', 60, 30); lin(p + 'l2_t2_2', 94, 15)
+    e4 = 4 if edges else 0            # DataAggregationEdges: four edge-feature channels more (module.py:118-130)
+    lin(p + 'init_trns', 8, 30); lin(p + 'l1_t1_1', 30, 30); lin(p + 'l1_t1_2', 64 + e4, 30)
+    lin(p + 'l1_t2_1', 4, 30); lin(p + 'l1_t2_2', 64 + e4, 30); lin(p + 'l2_t1_1', 60, 30); lin(p + 'l2_t1_2', 94 + e4, 15)
+    lin(p + 'l2_t2_1', 60, 30); lin(p + 'l2_t2_2', 94 + e4, 15)
     for a in ('activate', 'activate11', 'activate12', 'activate1', 'activate21', 'activate22', 'activate2'):
         prelu(p + a)
     p = 'Bipartite_ReadIn.'

@@ -61,6 +61,27 @@ def test_front_end_and_heads_match_reference(name):
     assert rel_err(x.numpy(), d['x']) < 2e-6
 
 
+@pytest.mark.parametrize('name', ['c1_10x100_edges', 'mid_36of40x300_edges'])
+def test_edge_feature_model_matches_reference(name):
+    """a2': the reference's `use_updated_model_definition: True` classes (DataAggregationEdges, module.py:102-174) run
+    unmodified by oracle/gen_golden.py synthetic_edges."""
+    d, sd = load_golden(name)
+    assert sd['DataAggregation.l1_t1_2.weight'].shape == (30, 68) and sd['DataAggregation.l2_t2_2.weight'].shape == (15, 98)
+    S, G, A_sta, A_src, A_ps, A_pg, A_sip, A_sis = _graphs(d)
+    Slice, Mask = torch.from_numpy(d['Slice']), torch.from_numpy(d['Mask'])
+    sta = torch.from_numpy(d['sta'][d['ind_use']]).float()
+    grid = torch.from_numpy(d['grid']).float()
+    pos_rel = go.edge_features(sta, grid, A_sis, A_ps, A_pg, float(d['scale_rel']))
+    y, x, parts = go.forward_fixed_source(
+        sd, Slice, Mask, A_ps, A_pg, torch.from_numpy(d['read_in_attr']), A_sip, A_src, grid,
+        torch.from_numpy(d['x_query']).float(), torch.from_numpy(d['t_query']).float().reshape(-1, 1),
+        float(d['scale_rel']), float(d['scale_t']), return_parts=True, pos_rel=pos_rel)
+    for key in ('x_latent', 'read_in', 'sa1', 'sa2', 'x_spatial', 'y_latent', 'x_query_embed'):
+        assert rel_err(parts[key].numpy(), d[key]) < 2e-6, key
+    assert rel_err(y.numpy(), d['y']) < 2e-6
+    assert rel_err(x.numpy(), d['x']) < 2e-6
+
+
 def test_mean_of_empty_neighbourhood_is_zero():
     msg = torch.ones(3, 2)
     out = go.propagate_mean(msg, torch.tensor([0, 0, 2]), 4)
