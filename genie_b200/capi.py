@@ -18,6 +18,7 @@ _lib = None
 
 GRAPH_CARTESIAN, GRAPH_EXPLICIT = 0, 1
 ABI_VERSION = 3
+EDGE_TERM_LD = 48           # GENIE_EDGE_TERM_LD
 
 c_f32p = ctypes.c_void_p   # device pointers are passed as opaque addresses
 
@@ -80,6 +81,7 @@ SIGNATURES = {
     'genie_plan_create': (ctypes.c_int, [ctypes.POINTER(GraphDesc), ctypes.POINTER(_P)]),
     'genie_plan_destroy': (None, [_P]),
     'genie_plan_workspace_bytes': (ctypes.c_size_t, [_P]),
+    'genie_plan_set_edge_terms': (ctypes.c_int, [_P, _P, _P]),
     'genie_frontend_packed_floats': (ctypes.c_size_t, []),
     'genie_frontend_pack_weights': (ctypes.c_int, [ctypes.POINTER(FrontendWeights), _P, _P]),
     'genie_input_scatter_fwd': (ctypes.c_int, [_P, ctypes.POINTER(InputParams), _P, ctypes.c_int64, _P, _P, _P, _P, _P,

@@ -100,7 +100,8 @@ Workspace carve_workspace(const genie_plan* p, void* base) {
 static int launch_da_layers01(const genie_plan* plan, const float* packed, const float* slice, const float* mask,
                               const Workspace& w, cudaStream_t st) {
     const bool split = split_supported(plan);
-    const bool tc = split || da_tc_supported(plan);
+    // the edge-feature terms are implemented in the split and the generic kernels, not in the one-pass tensor-core kernel
+    const bool tc = split || (da_tc_supported(plan) && plan->edge_sta == nullptr);
     int rc;
     if ((rc = launch_da_init(plan, packed, slice, mask, w.tr0, tc, st))) return rc;
     if (split) {
@@ -172,6 +173,16 @@ int genie_timing_collect(double* total_ms, int64_t* launches, int reset) {
             g_timing_n[k] = 0;
         }
     }
+    return GENIE_OK;
+}
+
+int genie_plan_set_edge_terms(genie_plan_t* plan, const float* edge_sta_dev, const float* edge_src_dev) {
+    if (!plan || ((edge_sta_dev == nullptr) != (edge_src_dev == nullptr))) {
+        set_error("genie_plan_set_edge_terms: null plan, or only one of the two tables given");
+        return GENIE_ERR_INVALID;
+    }
+    plan->edge_sta = edge_sta_dev;
+    plan->edge_src = edge_src_dev;
     return GENIE_OK;
 }
 

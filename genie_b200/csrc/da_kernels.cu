@@ -188,6 +188,16 @@ __global__ void __launch_bounds__(K2_THREADS, 2)
             if (lane < 4) F[(90 + lane) * LDF + m] = mk;
         }
         __syncthreads();
+        // edge-feature model (genie_plan_set_edge_terms): per-node additive terms of this thread's branch, or NULL
+        const float* et = nullptr;
+        if (gv.edge_sta != nullptr && i0 + n < gv.P) {
+            int64_t idx = i0 + n;
+            if (gv.mode == GENIE_GRAPH_CARTESIAN) {
+                const int64_t g = idx / gv.S;
+                idx = br ? g : idx - g * gv.S;
+            }
+            et = (br ? gv.edge_src : gv.edge_sta) + idx * GENIE_EDGE_TERM_LD;
+        }
         // ---- stage B: tr = PReLU1([l1_t1_2(..) ‖ l1_t2_2(..)]) ------------------------------------------------------
         {
             const float* W = sW + (br ? (DA_W12 - DA_W11) : 0);
@@ -195,6 +205,10 @@ __global__ void __launch_bounds__(K2_THREADS, 2)
             float acc[30];
 #pragma unroll
             for (int o = 0; o < 30; ++o) acc[o] = B[o];
+            if (et != nullptr) {
+#pragma unroll
+                for (int o = 0; o < 30; ++o) acc[o] += __ldg(et + o);
+            }
 #pragma unroll 2
             for (int k = 0; k < 30; ++k) fma_row30(acc, F[k * LDF + n], W + k * LD);
             const float* Fm = F + (30 + 30 * br) * LDF;
@@ -228,6 +242,10 @@ __global__ void __launch_bounds__(K2_THREADS, 2)
             float c[16];
 #pragma unroll
             for (int o = 0; o < 16; ++o) c[o] = Bc[o];
+            if (et != nullptr) {
+#pragma unroll
+                for (int o = 0; o < 15; ++o) c[o] += __ldg(et + 32 + o);
+            }
 #pragma unroll 2
             for (int k = 0; k < 60; ++k) fma_row16(c, F[k * LDF + n], Wc + k * LD16);
 #pragma unroll

@@ -197,13 +197,14 @@ __device__ __forceinline__ float4 s1_own_operands(const unsigned char* sb, int r
     return mk;
 }
 
+template <bool EDGE>
 __global__ void __launch_bounds__(S1_THREADS, 1)
     da_layer1_s_kernel(const float* __restrict__ packed, const float* __restrict__ p, const float* __restrict__ msrc,
                        const float* __restrict__ mask, float* __restrict__ zc, float* __restrict__ va,
                        float* __restrict__ vb, int S, int NT, const int32_t* __restrict__ tile_rows,
                        const int32_t* __restrict__ tile_meta, const uint16_t* __restrict__ tile_nbr,
-                       const float* __restrict__ tile_invdeg, int64_t n_tiles, long long* __restrict__ trace, int trace_tiles,
-                       int trace_start) {
+                       const float* __restrict__ tile_invdeg, int64_t n_tiles, const float* __restrict__ edge_sta,
+                       const float* __restrict__ edge_src, long long* __restrict__ trace, int trace_tiles, int trace_start) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const float* tcw = packed + T2_BASE;
     if (tcw[T2_SCAL + TCS_OK] == 0.f) return;   // slopes not eligible: the generic kernels run instead (uniform exit)
@@ -496,6 +497,14 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                     sid[j] = rw < n_own ? __ldg(tile_rows + (int64_t)T * ROWS + rw) : -1;
                 }
             }
+            // edge-feature model (genie_plan_set_edge_terms): rows of the additive terms of this thread's station / grid node
+            const float* et_sta = nullptr;
+            const float* et_src = nullptr;
+            if (EDGE) {
+                const int srow = valid ? __ldg(tile_rows + (int64_t)T * ROWS + r) : 0;
+                et_sta = edge_sta + (int64_t)srow * GENIE_EDGE_TERM_LD;
+                et_src = edge_src + (int64_t)g * GENIE_EDGE_TERM_LD;
+            }
             // ---- stage B epilogue: tr = PReLU1(X) -> A operand of stage C (mask in the four spare columns) -----------------
             mbar_wait(&bars->d_full[q], ph_d);
             ph_d ^= 1;
@@ -506,6 +515,14 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                 float v[16];
                 tmem_ld16(lane_base + TM_X + c, v);
                 tmem_ld_wait();
+                if (EDGE) {       // edge-feature model: tr1 += station term, tr2 += grid-node term
+                    const float4* e4 = reinterpret_cast<const float4*>((c < 32 ? et_sta : et_src) + (c & 16));
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 e = __ldg(e4 + u);
+                        v[4 * u] += e.x; v[4 * u + 1] += e.y; v[4 * u + 2] += e.z; v[4 * u + 3] += e.w;
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = prelu_f(v[i], a1);
                 if (c == 16) {
@@ -544,6 +561,14 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                 float v[16];
                 tmem_ld16(lane_base + TM_DC + 64 + c, v);
                 tmem_ld_wait();
+                if (EDGE) {       // edge-feature model: c_a += station term, c_b += grid-node term
+                    const float4* e4 = reinterpret_cast<const float4*>((c ? et_src : et_sta) + 32);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 e = __ldg(e4 + u);
+                        v[4 * u] += e.x; v[4 * u + 1] += e.y; v[4 * u + 2] += e.z; v[4 * u + 3] += e.w;
+                    }
+                }
                 store16_rows(v, scr, lane, sid, zc + c, node0, LD_ZC);
             }
             tmem_st_wait();
@@ -603,15 +628,20 @@ int launch_da_layer1_s(const genie_plan* p, const float* packed, const float* pf
     const int64_t n_tiles = (int64_t)g.n_sta_tiles * (g.n_grid_owned > 0 ? g.n_grid_owned : g.n_grid);
     static bool attr_set = false;
     if (!attr_set) {
-        GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer1_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer1_s_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer1_s_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
         attr_set = true;
     }
     const int64_t grid = n_tiles < p->sm_count ? n_tiles : p->sm_count;
     TimedLaunch tl(KID_DA_LAYER1_S, st);
-    da_layer1_s_kernel<<<(unsigned)grid, S1_THREADS, SM_TOTAL, st>>>(packed, pfeat, msrc, mask, zc, va, vb, g.n_sta,
-                                                                     g.n_sta_tiles, g.sta_tile_rows, g.sta_tile_meta,
-                                                                     g.sta_tile_nbr, g.sta_tile_invdeg, n_tiles,
-                                                                     g_s1_trace, g_s1_trace_tiles, g_s1_trace_start);
+    if (p->edge_sta != nullptr)
+        da_layer1_s_kernel<true><<<(unsigned)grid, S1_THREADS, SM_TOTAL, st>>>(
+            packed, pfeat, msrc, mask, zc, va, vb, g.n_sta, g.n_sta_tiles, g.sta_tile_rows, g.sta_tile_meta, g.sta_tile_nbr,
+            g.sta_tile_invdeg, n_tiles, p->edge_sta, p->edge_src, g_s1_trace, g_s1_trace_tiles, g_s1_trace_start);
+    else
+        da_layer1_s_kernel<false><<<(unsigned)grid, S1_THREADS, SM_TOTAL, st>>>(
+            packed, pfeat, msrc, mask, zc, va, vb, g.n_sta, g.n_sta_tiles, g.sta_tile_rows, g.sta_tile_meta, g.sta_tile_nbr,
+            g.sta_tile_invdeg, n_tiles, nullptr, nullptr, g_s1_trace, g_s1_trace_tiles, g_s1_trace_start);
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;
 }

@@ -12,6 +12,9 @@ struct genie_plan {
     genie_graph_desc_t g;
     int sm_count;
     int64_t n_edges_grid;   // number of grid-graph edges (host copy of grid_rowptr[G]), fetched lazily
+    // Edge-feature model (genie_plan_set_edge_terms): per-node additive terms of layer 1, NULL = off.
+    const float* edge_sta;  // [S or P][GENIE_EDGE_TERM_LD]
+    const float* edge_src;  // [G or P][GENIE_EDGE_TERM_LD]
 };
 
 // Device-side view of the product graph.  CARTESIAN: node i = g*S + s; sta neighbours g*S + col, src neighbours
@@ -27,6 +30,8 @@ struct GraphView {
     const int32_t* src_col;
     const int32_t* prod_grid;
     const int32_t* grid_order;
+    const float* edge_sta;   // edge-feature model: rows indexed by the station (CARTESIAN) / product node (EXPLICIT), or NULL
+    const float* edge_src;   //                     rows indexed by the grid node (CARTESIAN) / product node (EXPLICIT), or NULL
 };
 
 inline GraphView make_view(const genie_plan* p) {
@@ -41,6 +46,8 @@ inline GraphView make_view(const genie_plan* p) {
     v.src_col = p->g.src_col;
     v.prod_grid = p->g.prod_grid;
     v.grid_order = p->g.grid_order;
+    v.edge_sta = p->edge_sta;
+    v.edge_src = p->edge_src;
     return v;
 }
 

@@ -50,6 +50,8 @@ device = torch.device('cuda')
 class DataAggregation(nn.Module):
     """Parameters of module.py:52-83 (the unused l1_t1_1 / l1_t2_1 stay in the state_dict).  Forward: libgenie_b200."""
 
+    n_edge = 0      # edge-feature channels of every message (DataAggregationEdges: 4)
+
     def __init__(self, in_channels, out_channels, n_hidden=30, n_dim_mask=4, use_absolute_pos=use_absolute_pos):
         super().__init__()
         if use_absolute_pos:
@@ -57,22 +59,29 @@ class DataAggregation(nn.Module):
         if (in_channels, out_channels, n_hidden, n_dim_mask) != (4, 15, 30, 4):
             raise NotImplementedError('genie_b200: DataAggregation is built for (4, 15, n_hidden=30, n_dim_mask=4)')
         self.in_channels, self.out_channels, self.n_hidden = in_channels, out_channels, n_hidden
+        ne = self.n_edge
         self.activate = nn.PReLU()
         self.init_trns = nn.Linear(in_channels + n_dim_mask, n_hidden)
         self.l1_t1_1 = nn.Linear(n_hidden, n_hidden)
-        self.l1_t1_2 = nn.Linear(2 * n_hidden + n_dim_mask, n_hidden)
+        self.l1_t1_2 = nn.Linear(2 * n_hidden + n_dim_mask + ne, n_hidden)
         self.l1_t2_1 = nn.Linear(in_channels, n_hidden)
-        self.l1_t2_2 = nn.Linear(2 * n_hidden + n_dim_mask, n_hidden)
+        self.l1_t2_2 = nn.Linear(2 * n_hidden + n_dim_mask + ne, n_hidden)
         self.activate11 = nn.PReLU()
         self.activate12 = nn.PReLU()
         self.activate1 = nn.PReLU()
         self.l2_t1_1 = nn.Linear(2 * n_hidden, n_hidden)
-        self.l2_t1_2 = nn.Linear(3 * n_hidden + n_dim_mask, out_channels)
+        self.l2_t1_2 = nn.Linear(3 * n_hidden + n_dim_mask + ne, out_channels)
         self.l2_t2_1 = nn.Linear(2 * n_hidden, n_hidden)
-        self.l2_t2_2 = nn.Linear(3 * n_hidden + n_dim_mask, out_channels)
+        self.l2_t2_2 = nn.Linear(3 * n_hidden + n_dim_mask + ne, out_channels)
         self.activate21 = nn.PReLU()
         self.activate22 = nn.PReLU()
         self.activate2 = nn.PReLU()
+
+
+class DataAggregationEdges(DataAggregation):
+    """Parameters of module.py:102-140 (`use_updated_model_definition: True`): every message carries four edge-feature
+    channels, so l1_t*_2 / l2_t*_2 take 68 / 98 inputs ordered [tr | mean x_j | mean pos_rel | mask]."""
+    n_edge = 4
 
 
 class BipartiteGraphOperator(nn.Module):
@@ -221,24 +230,32 @@ class BipartiteGraphReadOutOperator(nn.Module):
 class DataAggregationAssociationPhase(nn.Module):
     """Parameters of module.py:356-387."""
 
+    n_edge = 0
+
     def __init__(self, in_channels, out_channels, n_hidden=30, n_dim_latent=30, n_dim_mask=5):
         super().__init__()
+        ne = self.n_edge
         self.activate = nn.PReLU()
         self.init_trns = nn.Linear(in_channels + n_dim_latent + n_dim_mask, n_hidden)
         self.l1_t1_1 = nn.Linear(n_hidden, n_hidden)
-        self.l1_t1_2 = nn.Linear(2 * n_hidden + n_dim_mask, n_hidden)
+        self.l1_t1_2 = nn.Linear(2 * n_hidden + n_dim_mask + ne, n_hidden)
         self.l1_t2_1 = nn.Linear(n_hidden, n_hidden)
-        self.l1_t2_2 = nn.Linear(2 * n_hidden + n_dim_mask, n_hidden)
+        self.l1_t2_2 = nn.Linear(2 * n_hidden + n_dim_mask + ne, n_hidden)
         self.activate11 = nn.PReLU()
         self.activate12 = nn.PReLU()
         self.activate1 = nn.PReLU()
         self.l2_t1_1 = nn.Linear(2 * n_hidden, n_hidden)
-        self.l2_t1_2 = nn.Linear(3 * n_hidden + n_dim_mask, out_channels)
+        self.l2_t1_2 = nn.Linear(3 * n_hidden + n_dim_mask + ne, out_channels)
         self.l2_t2_1 = nn.Linear(2 * n_hidden, n_hidden)
-        self.l2_t2_2 = nn.Linear(3 * n_hidden + n_dim_mask, out_channels)
+        self.l2_t2_2 = nn.Linear(3 * n_hidden + n_dim_mask + ne, out_channels)
         self.activate21 = nn.PReLU()
         self.activate22 = nn.PReLU()
         self.activate2 = nn.PReLU()
+
+
+class DataAggregationAssociationPhaseEdges(DataAggregationAssociationPhase):
+    """Parameters of module.py:406-440."""
+    n_edge = 4
 
 
 class LocalSliceLgCollapse(nn.Module):
@@ -280,17 +297,36 @@ class StationSourceAttentionMergedPhases(nn.Module):
 
 # ---- the model ----------------------------------------------------------------------------------------------------------
 
-class GCN_Detection_Network_extended(nn.Module):
-    """module.py:882-1020 (the default, `use_updated_model_definition: False`, definition)."""
+def edge_feature_means(pos, rowptr, col):
+    """Mean over every node's in-edges of the reference's edge embedding (module.py:1102-1111):
+    v = [pos_j - pos_i, |pos_j - pos_i|], pos_rel = sign(v) * exp(-0.5 v^2 / scale_rel^2).  `rowptr`, `col`: CSR by target
+    node with the SOURCE node of every edge; returns a function of scale_rel -> [n, 4] (0 for nodes without in-edges)."""
+    n = rowptr.numel() - 1
+    deg = (rowptr[1:] - rowptr[:-1])
+    tgt = torch.repeat_interleave(torch.arange(n, device=pos.device), deg)
+    d = pos[col.long()] - pos[tgt]
+    d = torch.cat((d, torch.norm(d, dim=1, keepdim=True)), dim=1)
 
-    def __init__(self, ftrns1, ftrns2, scale_rel=scale_rel, use_absolute_pos=use_absolute_pos, device='cuda'):
+    def means(scale):
+        e = torch.sign(d) * torch.exp(-0.5 * (d ** 2) / (scale ** 2))
+        out = torch.zeros((n, 4), dtype=e.dtype, device=e.device).index_add_(0, tgt, e)
+        return out / deg.clamp(min=1).to(e.dtype).unsqueeze(1)
+    return means
+
+
+class GCN_Detection_Network_extended(nn.Module):
+    """module.py:882-1020, or — `use_updated_model_definition: True` in config.yaml, or `updated_model=True` — the
+    DataAggregationEdges definition of module.py:1024-1186.  In the latter the four edge-feature channels of every message
+    reduce, by linearity of the mean and of l*_t*_2, to per-node additive terms that do not depend on the window
+    (include/genie_b200.h genie_plan_set_edge_terms); the kernels are the same."""
+
+    def __init__(self, ftrns1, ftrns2, scale_rel=scale_rel, use_absolute_pos=use_absolute_pos, device='cuda',
+                 updated_model=None):
         super().__init__()
-        if use_updated_model_definition:
-            raise NotImplementedError('genie_b200: use_updated_model_definition=True (DataAggregationEdges, '
-                                      'module.py:102) is not implemented yet')
+        self.updated_model = use_updated_model_definition if updated_model is None else bool(updated_model)
         if use_absolute_pos:
             raise NotImplementedError('genie_b200: use_absolute_pos=True is not supported yet')
-        self.DataAggregation = DataAggregation(4, 15).to(device)
+        self.DataAggregation = (DataAggregationEdges if self.updated_model else DataAggregation)(4, 15).to(device)
         self.Bipartite_ReadIn = BipartiteGraphOperator(30, 15, ndim_edges=3).to(device)
         self.SpatialAggregation1 = SpatialAggregation(15, 30, scale_rel=scale_rel).to(device)
         self.SpatialAggregation2 = SpatialAggregation(30, 30, scale_rel=scale_rel).to(device)
@@ -299,7 +335,8 @@ class GCN_Detection_Network_extended(nn.Module):
         self.SpatialAttention = SpatialAttention(30, 30, 3, 15, scale_rel=scale_rel).to(device)
         self.TemporalAttention = TemporalAttention(30, 1, 15).to(device)
         self.BipartiteGraphReadOutOperator = BipartiteGraphReadOutOperator(30, 15).to(device)
-        self.DataAggregationAssociationPhase = DataAggregationAssociationPhase(15, 15).to(device)
+        self.DataAggregationAssociationPhase = (DataAggregationAssociationPhaseEdges if self.updated_model
+                                                else DataAggregationAssociationPhase)(15, 15).to(device)
         self.LocalSliceLgCollapseP = LocalSliceLgCollapse(30, 15, device=device).to(device)
         self.LocalSliceLgCollapseS = LocalSliceLgCollapse(30, 15, device=device).to(device)
         self.Arrivals = StationSourceAttentionMergedPhases(30, 15, 2, 15, n_heads=3, device=device).to(device)
@@ -310,6 +347,8 @@ class GCN_Detection_Network_extended(nn.Module):
         self._plan_key = None
         self._packed = None
         self._read_in_attr = None
+        self._edge_means = None       # updated model: (means_sta(scale), means_src(scale)) of the current plan
+        self._edge_terms = None       # (key, t_sta, t_src, re-laid weight tensors)
 
     # -- graph plans ---------------------------------------------------------------------------------------------------
     def set_adjacencies(self, A_in_sta, A_in_src, A_src_in_edges, A_Lg_in_src, A_src_in_sta, A_src, A_edges_p, A_edges_s,
@@ -323,15 +362,63 @@ class GCN_Detection_Network_extended(nn.Module):
                                                device=pos_src.device)
         self._read_in_attr = A_src_in_edges.x.to(pos_src.device).float().contiguous()
         self._plan_key = None
+        self._set_edge_means(pos_loc, pos_src, A_src_in_sta)
 
-    def set_adjacencies_cartesian(self, A_sta_sta, A_src_src, read_in_attr, n_sta, n_grid, device=None):
+    def set_adjacencies_cartesian(self, A_sta_sta, A_src_src, read_in_attr, n_sta, n_grid, device=None, pos_loc=None,
+                                  pos_src=None):
         """Dense mode without ever materialising the product edge lists (needed beyond a few 10^7 product nodes):
-        the two kNN graphs of process_utils.py:718-719 and the read-in edge features `A_src_in_edges.x` [P,3]."""
+        the two kNN graphs of process_utils.py:718-719 and the read-in edge features `A_src_in_edges.x` [P,3]
+        (+ the Cartesian station / grid positions for the updated model's edge features)."""
         device = device if device is not None else read_in_attr.device
         self._plan = GraphPlan.cartesian(A_sta_sta, A_src_src, n_sta, n_grid, device=device)
         self._read_in_attr = read_in_attr.to(device).float().contiguous()
         self.A_src = A_src_src
         self._plan_key = None
+        self._set_edge_means(pos_loc, pos_src, None)
+
+    def _set_edge_means(self, pos_loc, pos_src, A_src_in_sta):
+        """Updated model: pos_rel_sta / pos_rel_src of module.py:1102-1111, already averaged over every node's in-edges.
+        CARTESIAN plans: one row per station / grid node (the product edge (s',g) -> (s,g) has the offset of s' - s);
+        EXPLICIT plans: one row per product node."""
+        self._edge_means, self._edge_terms = None, None
+        if not self.updated_model:
+            return
+        if pos_loc is None or pos_src is None:
+            raise capi.GenieError('the updated model definition needs the station and grid positions (pos_loc, pos_src)')
+        plan = self._plan
+        dev = plan.device
+        pos_loc, pos_src = pos_loc.to(dev).float(), pos_src.to(dev).float()
+        if plan.mode == capi.GRAPH_CARTESIAN:
+            self._edge_means = (edge_feature_means(pos_loc, plan.sta_rowptr, plan.sta_col),
+                                edge_feature_means(pos_src, plan.src_rowptr, plan.src_col))
+        else:
+            if A_src_in_sta is None:
+                raise capi.GenieError('explicit product graphs need A_src_in_sta for the edge features')
+            idx = A_src_in_sta.to(dev).long()
+            self._edge_means = (edge_feature_means(pos_loc[idx[0]], plan.sta_rowptr, plan.sta_col),
+                                edge_feature_means(pos_src[idx[1]], plan.src_rowptr, plan.src_col))
+
+    def _update_edge_terms(self):
+        """Tables of genie_plan_set_edge_terms + the l*_t*_2 weights without their four edge-feature columns."""
+        da = self.DataAggregation
+        ws = (da.l1_t1_2.weight, da.l1_t2_2.weight, da.l2_t1_2.weight, da.l2_t2_2.weight)
+        key = (id(self._edge_means), float(self.scale_rel)) + tuple((w.data_ptr(), w._version) for w in ws)
+        if self._edge_terms is not None and self._edge_terms[0] == key:
+            return self._edge_terms
+        m_sta, m_src = self._edge_means[0](float(self.scale_rel)), self._edge_means[1](float(self.scale_rel))
+        w11, w12, w21, w22 = (w.detach() for w in ws)
+
+        def table(m, wa, wb):
+            t = torch.zeros((m.shape[0], capi.EDGE_TERM_LD), dtype=torch.float32, device=m.device)
+            t[:, 0:30] = m @ wa[:, 60:64].t()
+            t[:, 32:47] = m @ wb[:, 90:94].t()
+            return t.contiguous()
+        t_sta, t_src = table(m_sta, w11, w21), table(m_src, w12, w22)
+        relaid = (torch.cat((w11[:, :60], w11[:, 64:]), dim=1).contiguous(), torch.cat((w12[:, :60], w12[:, 64:]), dim=1).contiguous(),
+                  torch.cat((w21[:, :90], w21[:, 94:]), dim=1).contiguous(), torch.cat((w22[:, :90], w22[:, 94:]), dim=1).contiguous())
+        self._edge_terms = (key, t_sta, t_src, relaid)
+        self._plan.set_edge_terms(t_sta, t_src)
+        return self._edge_terms
 
     def _plan_for(self, A_in_sta, A_in_src, A_src_in_edges, A_src, n_sta, n_grid, dev):
         """`forward` receives the graphs on every call (module.py:908): plans are cached on tensor identity."""
@@ -342,13 +429,20 @@ class GCN_Detection_Network_extended(nn.Module):
                                                    device=dev)
             self._read_in_attr = A_src_in_edges.x.to(dev).float().contiguous()
             self._plan_key = key
+            if self.updated_model:
+                raise NotImplementedError('genie_b200: the updated model needs set_adjacencies (positions) first')
         return self._plan
 
     # -- CUDA front end ------------------------------------------------------------------------------------------------
     def _packed_weights(self, dev):
         if self._packed is None or self._packed.device != torch.device(dev):
             self._packed = ops.PackedWeights(dev)
-        return self._packed.update(self)
+        relaid = None
+        if self.updated_model:
+            if self._edge_means is None:
+                raise RuntimeError('set_adjacencies must be called before the weights of the updated model are packed')
+            relaid = self._update_edge_terms()[3]
+        return self._packed.update(self, relaid)
 
     def front_end(self, Slice, Mask, x_temp_cuda_cart, want_latent=False, want_readin=False):
         """DataAggregation -> Bipartite_ReadIn -> SpatialAggregation1..3 in libgenie_b200 (module.py:1010-1014)."""

@@ -39,9 +39,13 @@ class PackedWeights(object):
             ts += [sa.fc1, sa.fc2, sa.fglobal, sa.activate1, sa.activate2, sa.activate3]
         return da, ri, sas, ts
 
-    def update(self, model):
+    def update(self, model, relaid=None):
+        """`relaid`: updated model definition only — (l1_t1_2, l1_t2_2, l2_t1_2, l2_t2_2) weights without their four
+        edge-feature columns ([30,64] / [15,94]); those columns live in the plan's edge-term tables."""
         da, ri, sas, mods = self._sources(model)
         key = tuple((p.data_ptr(), p._version) for m in mods for p in m.parameters())
+        if relaid is not None:
+            key = key + tuple(t.data_ptr() for t in relaid)
         if key == self._key:
             return self.buf
         for m in mods:
@@ -53,6 +57,14 @@ class PackedWeights(object):
                      ('da_l2_t1_1', da.l2_t1_1), ('da_l2_t2_1', da.l2_t2_1), ('da_l2_t1_2', da.l2_t1_2),
                      ('da_l2_t2_2', da.l2_t2_2), ('ri_fc1', ri.fc1), ('ri_fc2', ri.fc2)):
             _lin(ws, f, m)
+        if relaid is not None:
+            for f, t in zip(('da_l1_t1_2', 'da_l1_t2_2', 'da_l2_t1_2', 'da_l2_t2_2'), relaid):
+                getattr(ws, f).weight = capi.dptr(t, F32, f + '.weight (re-laid)')
+            self._relaid = relaid                   # keep the tensors alive
+        else:
+            for m, n_in in ((da.l1_t1_2, 64), (da.l1_t2_2, 64), (da.l2_t1_2, 94), (da.l2_t2_2, 94)):
+                if m.weight.shape[1] != n_in:
+                    raise capi.GenieError('DataAggregation weights of the updated model need their re-laid copies')
         for f, m in (('da_activate', da.activate), ('da_activate11', da.activate11), ('da_activate12', da.activate12),
                      ('da_activate1', da.activate1), ('da_activate21', da.activate21),
                      ('da_activate22', da.activate22), ('da_activate2', da.activate2),

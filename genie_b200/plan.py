@@ -244,6 +244,19 @@ class GraphPlan(object):
                 pass
             self.handle = None
 
+    def set_edge_terms(self, t_sta, t_src):
+        """genie_plan_set_edge_terms: per-node additive terms of the edge-feature model ([n, 48] fp32 each), or None, None."""
+        if t_sta is None:
+            capi.check(capi.load().genie_plan_set_edge_terms(self.handle, None, None))
+        else:
+            rows = (self.n_sta, self.n_grid) if self.mode == capi.GRAPH_CARTESIAN else (self.n_prod, self.n_prod)
+            for t, n in ((t_sta, rows[0]), (t_src, rows[1])):
+                if tuple(t.shape) != (n, capi.EDGE_TERM_LD):
+                    raise capi.GenieError('edge-term table must be [%d, %d]' % (n, capi.EDGE_TERM_LD))
+            capi.check(capi.load().genie_plan_set_edge_terms(self.handle, capi.dptr(t_sta, torch.float32, 'edge_sta'),
+                                                             capi.dptr(t_src, torch.float32, 'edge_src')))
+        self._edge_terms = (t_sta, t_src)              # keep the tensors alive
+
     def workspace(self):
         if self._workspace is None:
             self._workspace = torch.empty(max(self.workspace_bytes, 256), dtype=torch.uint8, device=self.device)

@@ -103,6 +103,18 @@ typedef struct genie_plan genie_plan_t;
  * module.py:941-961. */
 GENIE_API int genie_plan_create(const genie_graph_desc_t* desc, genie_plan_t** plan_out);
 GENIE_API void genie_plan_destroy(genie_plan_t* plan);
+/* Edge-feature model (`use_updated_model_definition: True`: DataAggregationEdges, module.py:102-174).  Every message of
+ * that model is [x_j | pos_rel(edge)], and the mean over a node's in-edges of the 4 pos_rel channels does not depend on the
+ * window, so the four extra input columns of l1_t*_2 / l2_t*_2 reduce to per-node additive terms (exact, by linearity):
+ *   edge_sta_dev [S (CARTESIAN) or P (EXPLICIT)][GENIE_EDGE_TERM_LD]:
+ *       [0,30)  = l1_t1_2.weight[:, 60:64] . mean_{station in-edges} pos_rel_sta      (added to tr1 before activate1)
+ *       [32,47) = l2_t1_2.weight[:, 90:94] . mean_{station in-edges} pos_rel_sta      (added to the l2_t1_2 output)
+ *   edge_src_dev [G or P][GENIE_EDGE_TERM_LD]: the same with l1_t2_2 / l2_t2_2 and the source in-edges.
+ * The weights structure then carries l1_t*_2 / l2_t*_2 WITHOUT those four columns ([30][64] / [15][94]).  The tables are
+ * the caller's (they must outlive the forward calls); NULL, NULL switches the terms off.  genie_b200/module.py builds
+ * them in set_adjacencies / whenever the weights change. */
+#define GENIE_EDGE_TERM_LD 48
+GENIE_API int genie_plan_set_edge_terms(genie_plan_t* plan, const float* edge_sta_dev, const float* edge_src_dev);
 /* Bytes of caller-provided scratch the forward entry points need for this plan (intermediate node features). */
 GENIE_API size_t genie_plan_workspace_bytes(const genie_plan_t* plan);
 

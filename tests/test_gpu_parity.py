@@ -21,9 +21,9 @@ def _dev():
     return torch.device('cuda:0')
 
 
-def _model(sd, dev, scale_rel, scale_t):
+def _model(sd, dev, scale_rel, scale_t, updated_model=False):
     from genie_b200.module import GCN_Detection_Network_extended
-    m = GCN_Detection_Network_extended(None, None, scale_rel=scale_rel, device=dev)
+    m = GCN_Detection_Network_extended(None, None, scale_rel=scale_rel, device=dev, updated_model=updated_model)
     m.load_state_dict(sd)
     m.TemporalAttention.scale_t = scale_t
     m.eval()
@@ -133,6 +133,68 @@ def _random_case(S, G, k_s, k_g, seed, dev):
     Mask = (np.abs(Slice) > 0.01).astype(np.float32)
     attr = net.read_in_offsets(np.array([net.width, net.width, 42000.0]))
     return net, A_sta, A_src, torch.from_numpy(Slice), torch.from_numpy(Mask), torch.from_numpy(attr)
+
+
+@pytest.mark.parametrize('name', ['c1_10x100_edges', 'mid_36of40x300_edges'])
+def test_updated_model_definition_matches_reference(name):
+    """a2': `use_updated_model_definition: True` (DataAggregationEdges, module.py:102-174, 1024-1186) through the
+    nn.Module surface, against fixtures made by the unmodified reference (oracle/gen_golden.py synthetic_edges); the
+    state_dict loads with strict=True (l1_t*_2 [30,68], l2_t*_2 [15,98])."""
+    from genie_b200 import capi
+    from oracle.refshim.torch_geometric.data import Data
+    dev = _dev()
+    d, sd = load_golden(name)
+    A_sta, A_src, A_ps, A_pg, A_sip, A_sis = _graphs(d)
+    m = _model(sd, dev, float(d['scale_rel']), float(d['scale_t']), updated_model=True)
+    t = lambda k: torch.from_numpy(d[k]).to(dev)
+    locs = torch.from_numpy(d['sta'][d['ind_use']]).float().to(dev)
+    grid = torch.from_numpy(d['grid']).float().to(dev)
+    A_edges = Data(x=t('read_in_attr'), edge_index=A_sip.to(dev))
+    m.set_adjacencies(A_ps.to(dev), A_pg.to(dev), A_edges, None, A_sis.to(dev), A_src.to(dev), None, None, None, None,
+                      locs, grid)
+    xs, lat, r = m.front_end(t('Slice'), t('Mask'), grid, want_latent=True, want_readin=True)
+    assert rel_err(lat.cpu().numpy(), d['x_latent']) < TOL
+    assert rel_err(r.cpu().numpy(), d['read_in']) < TOL
+    assert rel_err(xs.cpu().numpy(), d['x_spatial']) < TOL
+    y, x = m.forward_fixed_source(t('Slice'), t('Mask'), None, None, None, locs, grid,
+                                  torch.from_numpy(d['x_query']).float().to(dev),
+                                  torch.from_numpy(d['t_query']).float().reshape(-1, 1).to(dev))
+    assert rel_err(y.cpu().numpy(), d['y']) < TOL
+    assert rel_err(x.cpu().numpy(), d['x']) < TOL
+
+
+@pytest.mark.parametrize('S,G,tiling', [(150, 260, True), (150, 260, False), (20, 90, True)])
+def test_updated_model_definition_matches_oracle_seeded(S, G, tiling):
+    """The edge-feature terms in the split tensor-core station pass (tiling tables), in the generic kernels (no tables /
+    fewer than 32 stations) and on an EXPLICIT plan (per-product-node terms), against the pinned oracle."""
+    from genie_b200.plan import GraphPlan
+    from genie_b200.process_utils import product_edge_lists
+    from genie_b200 import capi
+    from oracle import genie_oracle as go
+    dev = _dev()
+    net, A_sta, A_src, Slice, Mask, attr = _random_case(S, G, 15, 15, 29, dev)
+    sd = go.init_state(seed=9, edges=True)
+    A_ps, A_pg, A_sip, A_sis = product_edge_lists(A_sta, A_src, S, G)
+    sta, grid = torch.from_numpy(net.sta).float(), torch.from_numpy(net.grid).float()
+    pos_rel = go.edge_features(sta, grid, A_sis, A_ps, A_pg, 30000.0)
+    want, parts = go.front_end(sd, Slice, Mask, A_ps, A_pg, attr, A_sip, A_src, grid, 30000.0, return_parts=True,
+                               pos_rel=pos_rel)
+    from genie_b200.module import GCN_Detection_Network_extended
+    m = GCN_Detection_Network_extended(None, None, device=dev, updated_model=True)
+    m.load_state_dict(sd, strict=False)
+    m.eval()
+    plans = [GraphPlan.cartesian(A_sta, A_src, S, G, device=dev, tiling=tiling)]
+    if not tiling:
+        plans.append(GraphPlan.explicit(A_ps, A_pg, A_sip[1], A_src, S * G, G, device=dev))
+    for plan in plans:
+        assert (plan.tiles is not None) == (tiling and S >= 32)
+        m._plan, m._read_in_attr = plan, attr.to(dev)
+        m._set_edge_means(sta.to(dev), grid.to(dev), A_sis.to(dev))
+        with torch.no_grad():
+            xs, lat, r = m.front_end(Slice.to(dev), Mask.to(dev), grid.to(dev), want_latent=True, want_readin=True)
+        assert rel_err(lat.cpu().numpy(), parts['x_latent'].numpy()) < TOL
+        assert rel_err(r.cpu().numpy(), parts['read_in'].numpy()) < TOL
+        assert rel_err(xs.cpu().numpy(), want.numpy()) < TOL
 
 
 @pytest.mark.parametrize('S,G,k_s,k_g', [(100, 500, 15, 15), (37, 211, 8, 15), (130, 64, 10, 5)])
