@@ -59,6 +59,13 @@ class FrontendWeights(ctypes.Structure):
                 ('sa', SAWeights * 3)]
 
 
+class NearestParams(ctypes.Structure):
+    _fields_ = [('offset_per_batch', ctypes.c_double), ('offset_per_station', ctypes.c_double),
+                ('kernel_sig_t', ctypes.c_double), ('n_all', ctypes.c_int64), ('n_p', ctypes.c_int64),
+                ('n_s', ctypes.c_int64), ('n_batch', ctypes.c_int32), ('n_grid', ctypes.c_int32),
+                ('n_locs', ctypes.c_int32), ('n_sta_use', ctypes.c_int32)]
+
+
 class InputParams(ctypes.Structure):
     _fields_ = [('t0', ctypes.c_double), ('max_t', ctypes.c_double), ('kernel_sig_t', ctypes.c_double),
                 ('dt', ctypes.c_double), ('ref0', ctypes.c_double), ('ref_step', ctypes.c_double),
@@ -84,6 +91,7 @@ SIGNATURES = {
     'genie_plan_set_edge_terms': (ctypes.c_int, [_P, _P, _P]),
     'genie_frontend_packed_floats': (ctypes.c_size_t, []),
     'genie_frontend_pack_weights': (ctypes.c_int, [ctypes.POINTER(FrontendWeights), _P, _P]),
+    'genie_input_nearest_fwd': (ctypes.c_int, [ctypes.POINTER(NearestParams), _P, _P, _P, _P, _P, _P, _P, _P]),
     'genie_input_scatter_fwd': (ctypes.c_int, [_P, ctypes.POINTER(InputParams), _P, ctypes.c_int64, _P, _P, _P, _P, _P,
                                                _P, _P, _P, _P, _P]),
     'genie_data_aggregation_fwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P]),

@@ -296,6 +296,23 @@ int genie_input_scatter_fwd(const genie_plan_t* plan, const genie_input_params_t
                                 static_cast<cudaStream_t>(stream));
 }
 
+int genie_input_nearest_fwd(const genie_nearest_params_t* prm, const double* times_all_dev, const double* times_p_dev,
+                            const double* times_s_dev, const int32_t* ind_use_dev, const float* trv_times_dev,
+                            float* slice_out_dev, float* mask_out_dev, void* stream) {
+    if (!prm || !ind_use_dev || !trv_times_dev || !slice_out_dev || !mask_out_dev || (prm->n_all > 0 && !times_all_dev) ||
+        (prm->n_p > 0 && !times_p_dev) || (prm->n_s > 0 && !times_s_dev)) {
+        set_error("genie_input_nearest_fwd: null argument");
+        return GENIE_ERR_INVALID;
+    }
+    if (prm->n_batch < 0 || prm->n_grid < 0 || prm->n_sta_use <= 0 || prm->n_locs <= 0 || prm->n_all < 0 || prm->n_p < 0 ||
+        prm->n_s < 0 || !(prm->kernel_sig_t > 0.0)) {
+        set_error("genie_input_nearest_fwd: bad parameters");
+        return GENIE_ERR_INVALID;
+    }
+    return launch_input_nearest(prm, times_all_dev, times_p_dev, times_s_dev, ind_use_dev, trv_times_dev, slice_out_dev,
+                                mask_out_dev, static_cast<cudaStream_t>(stream));
+}
+
 int genie_data_aggregation_fwd(const genie_plan_t* plan, const float* packed_dev, const float* slice_dev,
                                const float* mask_dev, float* x_latent_out_dev, void* workspace_dev, void* stream) {
     if (!plan || !packed_dev || !slice_dev || !mask_dev || !x_latent_out_dev || !workspace_dev) {

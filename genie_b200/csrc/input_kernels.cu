@@ -94,7 +94,65 @@ __global__ void input_gather_kernel(const genie_input_params_t prm, int mode, in
     }
 }
 
+// a1': nearest-pick features (process_utils.py:194-268).  One thread per (sample, product node).
+__device__ __forceinline__ double nearest_distance(const double* __restrict__ times, int64_t n, double q) {
+    int64_t lo = 0, hi = n;                      // numpy.searchsorted(times, q) (side='left'): first index with times[i] >= q
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(times + mid) < q) lo = mid + 1;
+        else hi = mid;
+    }
+    const int64_t i0 = min(max(lo - 1, (int64_t)0), n - 1), i1 = min(max(lo, (int64_t)0), n - 1);     // :199-203
+    return fmin(fabs(__dsub_rn(q, __ldg(times + i0))), fabs(__dsub_rn(q, __ldg(times + i1))));
+}
+
+__global__ void input_nearest_kernel(const genie_nearest_params_t prm, const double* __restrict__ t_all,
+                                     const double* __restrict__ t_p, const double* __restrict__ t_s,
+                                     const int32_t* __restrict__ ind_use, const float* __restrict__ trv,
+                                     float* __restrict__ slice_out, float* __restrict__ mask_out) {
+    const int64_t n_node = (int64_t)prm.n_grid * prm.n_sta_use;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n_node * prm.n_batch) return;
+    const int b = (int)(tid / n_node);
+    const int64_t i = tid - (int64_t)b * n_node;
+    const int g = (int)(i / prm.n_sta_use), s = (int)(i - (int64_t)g * prm.n_sta_use);
+    const int sta_abs = __ldg(ind_use + s);
+    const float2 tt = __ldg(reinterpret_cast<const float2*>(trv + ((int64_t)g * prm.n_locs + sta_abs) * 2));
+    const double shift = __dmul_rn((double)sta_abs, prm.offset_per_station);
+    const double qp = __dadd_rn(__dadd_rn((double)tt.x, __dmul_rn((double)b, prm.offset_per_batch)), shift);      // :194
+    const double qs = __dadd_rn(__dadd_rn((double)tt.y, __dmul_rn((double)b, prm.offset_per_batch)), shift);      // :195
+    const double s2 = __dmul_rn(prm.kernel_sig_t, prm.kernel_sig_t);
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    if (prm.n_all > 0) {
+        const double dp = nearest_distance(t_all, prm.n_all, qp), ds = nearest_distance(t_all, prm.n_all, qs);
+        v[0] = exp(__ddiv_rn(__dmul_rn(-0.5, __dmul_rn(dp, dp)), s2));
+        v[1] = exp(__ddiv_rn(__dmul_rn(-0.5, __dmul_rn(ds, ds)), s2));
+    }
+    if (prm.n_p > 0) {
+        const double d = nearest_distance(t_p, prm.n_p, qp);
+        v[2] = exp(__ddiv_rn(__dmul_rn(-0.5, __dmul_rn(d, d)), s2));
+    }
+    if (prm.n_s > 0) {
+        const double d = nearest_distance(t_s, prm.n_s, qs);
+        v[3] = exp(__ddiv_rn(__dmul_rn(-0.5, __dmul_rn(d, d)), s2));
+    }
+    reinterpret_cast<float4*>(slice_out)[tid] = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+    reinterpret_cast<float4*>(mask_out)[tid] = make_float4(v[0] > 0.01 ? 1.f : 0.f, v[1] > 0.01 ? 1.f : 0.f,
+                                                           v[2] > 0.01 ? 1.f : 0.f, v[3] > 0.01 ? 1.f : 0.f);
+}
+
 }  // namespace
+
+int launch_input_nearest(const genie_nearest_params_t* prm, const double* t_all, const double* t_p, const double* t_s,
+                         const int32_t* ind_use, const float* trv_times, float* slice_out, float* mask_out, cudaStream_t st) {
+    const int64_t total = (int64_t)prm->n_grid * prm->n_sta_use * prm->n_batch;
+    if (total == 0) return GENIE_OK;
+    TimedLaunch tl(KID_INPUT_GATHER, st);
+    input_nearest_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(*prm, t_all, t_p, t_s, ind_use, trv_times,
+                                                                           slice_out, mask_out);
+    GENIE_LAUNCH_CHECK();
+    return GENIE_OK;
+}
 
 int launch_input_scatter(const genie_plan* p, const genie_input_params_t* prm, const double* picks, int64_t n_picks,
                          const int32_t* sta_perm, const int32_t* ind_use, const float* trv_times,

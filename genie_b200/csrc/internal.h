@@ -149,6 +149,8 @@ void set_s1_trace(long long* buf, int tiles);
 int launch_da_layer2_s(const genie_plan* p, const float* packed, const float* zc, const float* va, const float* m2,
                        const float* mask, const float* edge_attr, float* latent_out, float* out, int ld_out,
                        cudaStream_t st);
+int launch_input_nearest(const genie_nearest_params_t* prm, const double* t_all, const double* t_p, const double* t_s,
+                         const int32_t* ind_use, const float* trv_times, float* slice_out, float* mask_out, cudaStream_t st);
 int launch_input_scatter(const genie_plan* p, const genie_input_params_t* prm, const double* picks, int64_t n_picks,
                          const int32_t* sta_perm, const int32_t* ind_use, const float* trv_times,
                          const int32_t* node_sta, const int32_t* node_grid, float* series, float* slice_out,

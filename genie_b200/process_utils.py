@@ -11,7 +11,7 @@ import numpy as np
 import torch
 from scipy.spatial import cKDTree
 
-from . import ops
+from . import capi, ops
 from .plan import GraphPlan
 
 
@@ -115,6 +115,76 @@ def extract_pick_inputs_from_data(P_slice, locs, ind_use, time_samples, max_t, t
 
 
 _extractors = {}
+_legacy_cache = {}
+
+
+def extract_inputs_from_data_fixed_grids_with_phase_type(trv, locs, ind_use, arrivals, phase_labels, arrivals_tree,
+                                                          time_samples, x_grid, x_grid_trv, lat_range, lon_range,
+                                                          depth_range, max_t, training_params, graph_params, pred_params,
+                                                          ftrns1, ftrns2, verbose=False, device='cuda'):
+    """Same call as process_utils.py:102 (the input features of `use_updated_input: False` and of training): returns
+    `[Inpts, Masks], [lp_times, lp_stations, lp_phases, lp_meta]`, Inpts / Masks being fp32 CUDA tensors [G * n_sta, 4] per
+    time sample.  The pick selection and the merged, offset time axis of :137-189 are a few thousand numbers and are built on
+    the host with the reference's own numpy expressions; the G x S x 4 nearest-pick searches run in libgenie_b200."""
+    import ctypes
+    arrivals = np.asarray(arrivals, dtype=np.float64)
+    phase_labels = np.asarray(phase_labels)
+    time_samples = np.asarray(time_samples, dtype=np.float64).reshape(-1)
+    n_batch, n_spc, n_sta = len(time_samples), int(x_grid.shape[0]), int(locs.shape[0])
+    t_win, kernel_sig_t = float(pred_params[0]), float(pred_params[1])
+    if arrivals_tree is not None:                                                                          # :138
+        lp = arrivals_tree.query_ball_point(time_samples.reshape(-1, 1) + max_t / 2.0, r=t_win + max_t / 2.0)
+        lp = [np.array(list(l)).astype('int') for l in lp]
+    else:
+        lp = [np.where(np.abs(arrivals[:, 0] - (ts + max_t / 2.0)) <= t_win + max_t / 2.0)[0] for ts in time_samples]
+    ind_sta_select = np.unique(ind_use)                                                                    # :152
+    offset_per_batch = 1.5 * max_t                                                                         # :177
+    offset_per_station = 1.5 * n_batch * offset_per_batch                                                  # :178
+    arrivals_offset = np.hstack([-time_samples[i] + i * offset_per_batch + offset_per_station * arrivals[lp[i], 1]
+                                 for i in range(n_batch)])                                                 # :180
+    t_sel = np.hstack([arrivals[lp[i], 0] for i in range(n_batch)]) + arrivals_offset                      # :182
+    ph_sel = np.hstack([phase_labels[lp[i]] for i in range(n_batch)])
+    order = np.argsort(t_sel)                                                                              # :188
+    t_sel, ph_sel = np.ascontiguousarray(t_sel[order]), ph_sel[order]
+    axes = [t_sel, np.ascontiguousarray(t_sel[ph_sel == 0]), np.ascontiguousarray(t_sel[ph_sel == 1])]    # :209-210
+    dev = torch.device(device)
+    if not dev.type == 'cuda':
+        raise capi.GenieError('genie_b200 has no CPU path: device must be a CUDA device')
+    key = (id(x_grid_trv), tuple(x_grid_trv.shape), str(dev))
+    if _legacy_cache.get('key') != key:
+        trv_dev = (x_grid_trv if torch.is_tensor(x_grid_trv) else torch.from_numpy(np.ascontiguousarray(x_grid_trv)))
+        _legacy_cache.update(key=key, trv=trv_dev.to(dev).float().contiguous(), ref=x_grid_trv)
+    trv_dev = _legacy_cache['trv']
+    ind_dev = torch.from_numpy(ind_sta_select.astype(np.int32)).to(dev)
+    axes_dev = [torch.from_numpy(a).to(dev) if len(a) else None for a in axes]
+    n_node = n_spc * len(ind_sta_select)
+    Slice = torch.empty((n_batch, n_node, 4), dtype=torch.float32, device=dev)
+    Mask = torch.empty((n_batch, n_node, 4), dtype=torch.float32, device=dev)
+    prm = capi.NearestParams(offset_per_batch, offset_per_station, kernel_sig_t, len(axes[0]), len(axes[1]), len(axes[2]),
+                             n_batch, n_spc, n_sta, len(ind_sta_select))
+    ptr = lambda t: capi.dptr(t, torch.float64) if t is not None else None
+    with torch.cuda.device(dev):
+        capi.check(capi.load().genie_input_nearest_fwd(
+            ctypes.byref(prm), ptr(axes_dev[0]), ptr(axes_dev[1]), ptr(axes_dev[2]), capi.dptr(ind_dev, torch.int32),
+            capi.dptr(trv_dev, torch.float32), capi.dptr(Slice), capi.dptr(Mask), capi.stream_ptr(dev)))
+    # per-sample pick lists (:270-291)
+    lp_times, lp_stations, lp_phases, lp_meta = [], [], [], []
+    for i in range(n_batch):
+        perm_vec = -1 * np.ones(n_sta)
+        perm_vec[ind_sta_select] = np.arange(len(ind_sta_select))
+        meta = arrivals[lp[i], :]
+        phase_vals = phase_labels[lp[i]]
+        times = meta[:, 0]
+        indices = perm_vec[meta[:, 1].astype('int')]
+        ineed = np.where(indices > -1)[0]
+        times, indices, phase_vals, meta = times[ineed], indices[ineed], phase_vals[ineed], meta[ineed]
+        lex_sort = np.lexsort((times, indices))
+        lp_times.append(times[lex_sort] - time_samples[i])
+        lp_stations.append(indices[lex_sort])
+        lp_phases.append(phase_vals[lex_sort])
+        lp_meta.append(meta[lex_sort])
+    return [[Slice[i] for i in range(n_batch)], [Mask[i] for i in range(n_batch)]], \
+        [lp_times, lp_stations, lp_phases, lp_meta]
 
 
 def extract_input_from_data(trv_pairwise, P, t0, ind_use, locs, x_grid, A_src_in_sta, trv_times=None, max_t=300.0,

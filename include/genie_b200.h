@@ -184,6 +184,33 @@ GENIE_API int genie_input_scatter_fwd(const genie_plan_t* plan, const genie_inpu
                             float* series_dev, float* slice_out_dev, float* mask_out_dev, int64_t* time_bin_out_dev,
                             void* stream);
 
+/* ---- a1': nearest-pick input features -----------------------------------------------------------------------------------
+ * Replaces the device-sized part of process_utils.extract_inputs_from_data_fixed_grids_with_phase_type
+ * (process_utils.py:194-268; the input features used when `use_updated_input: False` and in training): per sample b, product
+ * node (g, s) and phase, the query time  (trv[g, sta, phase] + b * offset_per_batch) + sta * offset_per_station  (fp64, in
+ * that order) is located with searchsorted(left) on a sorted time axis; the distance to the nearer of its two neighbours
+ * (indices clipped to the axis, :199-203) goes through exp((-0.5 * d^2) / sigma^2) in fp64.  Channels 0, 1: the axis of all
+ * selected picks at the P / S query; channels 2, 3: the axes of the P picks / S picks (0 when the axis is empty).
+ * The caller builds the axes on the host exactly as the reference does (:137-189, a few thousand picks).
+ *   times_all_dev / times_p_dev / times_s_dev   fp64, sorted ascending, n_all / n_p / n_s entries (NULL allowed when 0).
+ *   ind_use_dev    int32 [n_sta_use] used station -> absolute station (sorted: np.unique(ind_use), :152).
+ *   trv_times_dev  fp32 [G, n_locs, 2].
+ *   slice_out_dev, mask_out_dev   fp32 [n_batch, G * n_sta_use, 4] (grid-major as :268); Mask = value > 0.01 on the fp64 value.
+ */
+typedef struct genie_nearest_params {
+    double offset_per_batch;     /* 1.5 * max_t                                  (process_utils.py:177) */
+    double offset_per_station;   /* 1.5 * n_batch * offset_per_batch             (process_utils.py:178) */
+    double kernel_sig_t;
+    int64_t n_all, n_p, n_s;
+    int32_t n_batch;
+    int32_t n_grid;
+    int32_t n_locs;
+    int32_t n_sta_use;
+} genie_nearest_params_t;
+GENIE_API int genie_input_nearest_fwd(const genie_nearest_params_t* prm, const double* times_all_dev, const double* times_p_dev,
+                                      const double* times_s_dev, const int32_t* ind_use_dev, const float* trv_times_dev,
+                                      float* slice_out_dev, float* mask_out_dev, void* stream);
+
 /* ---- a2: DataAggregation.forward — module.py:85-98 -----------------------------------------------------------------
  * slice_dev, mask_dev fp32 [P,4] -> x_latent_out_dev fp32 [P,30]. */
 GENIE_API int genie_data_aggregation_fwd(const genie_plan_t* plan, const float* packed_dev, const float* slice_dev,

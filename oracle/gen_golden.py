@@ -2,6 +2,7 @@
 
     python oracle/gen_golden.py synthetic      # seeded synthetic networks, reference default-initialised weights
     python oracle/gen_golden.py synthetic_edges  # same, `use_updated_model_definition: True` (DataAggregationEdges)
+    python oracle/gen_golden.py legacy_input     # a1': extract_inputs_from_data_fixed_grids_with_phase_type
     python oracle/gen_golden.py ferndale       # Examples/Ferndale.zip: real stations/grids/picks + trained checkpoint
 
 The reference classes (`/root/reference/Code/module.py`, `process_utils.py`) are imported as they are, with
@@ -158,12 +159,49 @@ def synthetic(edges=False):
             np.abs(res['x_latent']).sum(), res['y'].max(), res['x'].max()))
 
 
+def legacy_input():
+    """a1': extract_inputs_from_data_fixed_grids_with_phase_type (process_utils.py:102-308), the nearest-pick input
+    features used when `use_updated_input: False` and in training.  Two time samples per call exercise the batch offsets."""
+    work = tempfile.mkdtemp(prefix='genie_golden_')
+    for f in ('config.yaml', 'train_config.yaml'):
+        shutil.copy(os.path.join(REF, 'Code', f), work)
+    torch, module, pu, Data = _import_reference(os.path.join(REF, 'Code'), work)
+    from scipy.spatial import cKDTree
+    from genie_b200 import synth
+    for name, S_all, n_use, G, seed, t_win, sig in (('legacy_12of14x60', 14, 12, 60, 4, 10.0, 3.0),
+                                                    ('legacy_8x30_short', 8, 8, 30, 6, 5.0, 2.0)):
+        net = synth.Network(S_all, G, seed=seed, width_km=60.0 if 'short' not in name else 12.0)
+        rng = np.random.default_rng(200 + seed)
+        ind_use = np.sort(rng.choice(S_all, size=n_use, replace=False))
+        max_t = net.max_moveout()
+        P = synth.make_picks(net, 0.0, 400.0, seed=seed + 1, events_per_3h=600.0, false_per_sta_min=3.0)
+        P = P[np.argsort(P[:, 0])]
+        time_samples = np.array([120.0 + seed, 131.5 + seed])
+        trv_times = net.travel_times()                       # [G, S_all, 2]
+        tree = cKDTree(P[:, 0][:, None])
+        rng_lat = [0.0, 1.0]
+        [Inpts, Masks], [lp_t, lp_s, lp_p, lp_m] = pu.extract_inputs_from_data_fixed_grids_with_phase_type(
+            None, net.sta, ind_use, P, P[:, 4], tree, time_samples, net.grid, trv_times, rng_lat, rng_lat, rng_lat, max_t,
+            None, [8, 15, 10], [t_win, sig], None, None)
+        res = dict(sta=net.sta, grid=net.grid, ind_use=ind_use, picks=P, time_samples=time_samples, trv_times=trv_times,
+                   max_t=np.float64(max_t), t_win=np.float64(t_win), kernel_sig_t=np.float64(sig))
+        for i in range(len(time_samples)):
+            res['Inpts%d' % i], res['Masks%d' % i] = np.asarray(Inpts[i]), np.asarray(Masks[i])
+            res['lp_times%d' % i], res['lp_stations%d' % i] = np.asarray(lp_t[i]), np.asarray(lp_s[i])
+            res['lp_phases%d' % i], res['lp_meta%d' % i] = np.asarray(lp_p[i]), np.asarray(lp_m[i])
+        np.savez_compressed(os.path.join(GOLD, name + '.npz'), **res)
+        print(name, 'max_t=%.2f picks=%d' % (max_t, len(P)), [float(np.asarray(x).sum()) for x in Inpts],
+              [int((np.asarray(x) > 0).sum()) for x in Inpts], Inpts[0].dtype, Inpts[0].shape)
+
+
 if __name__ == '__main__':
     mode = sys.argv[1] if len(sys.argv) > 1 else 'synthetic'
     if mode == 'synthetic':
         synthetic()
     elif mode == 'synthetic_edges':
         synthetic(edges=True)
+    elif mode == 'legacy_input':
+        legacy_input()
     elif mode == 'ferndale':
         from gen_golden_ferndale import ferndale
         ferndale()

@@ -177,6 +177,82 @@ def input_scatter(P, t0, ind_use, n_locs, A_src_in_sta, trv_times, max_t, kernel
     return Slice, Mask
 
 
+def legacy_pick_window(arrivals, time_samples, max_t, t_win):
+    """process_utils.py:137-139: picks within t_win + max_t/2 of the centre of every sample's move-out window (the reference
+    asks a cKDTree on the pick times; a closed ball of radius r is |t - c| <= r)."""
+    return [np.where(np.abs(arrivals[:, 0] - (ts + max_t / 2.0)) <= t_win + max_t / 2.0)[0] for ts in time_samples]
+
+
+def legacy_input_features(arrivals, phase_labels, ind_use, time_samples, x_grid_trv, max_t, t_win, kernel_sig_t,
+                          return_parts=False):
+    """a1' — extract_inputs_from_data_fixed_grids_with_phase_type (process_utils.py:102-308): per product node and phase the
+    distance from the predicted arrival time to the NEAREST pick (any phase: channels 0, 1; same phase: channels 2, 3),
+    through exp(-0.5 d^2 / sigma^2).  The reference lays all stations and samples on ONE sorted time axis (offsets of
+    1.5 max_t per sample and 1.5 n_batch 1.5 max_t per station, :177-183) and looks at the two searchsorted neighbours
+    (:197-207); that construction is kept literally, including what it does at the ends of the axis.
+    Returns ([Inpts], [Masks]) as float64 [G * n_sta_use, 4] per sample (grid-major, stations in np.unique(ind_use) order)."""
+    n_batch = len(time_samples)
+    n_spc = x_grid_trv.shape[0]
+    lp = legacy_pick_window(arrivals, time_samples, max_t, t_win)
+    ind_sta_select = np.unique(ind_use)                                                                   # :152
+    n_node = n_spc * len(ind_sta_select)
+    offset_per_batch = 1.5 * max_t                                                                        # :177
+    offset_per_station = 1.5 * n_batch * offset_per_batch                                                 # :178
+    arrivals_offset = np.hstack([-time_samples[i] + i * offset_per_batch + offset_per_station * arrivals[lp[i], 1]
+                                 for i in range(n_batch)])                                                # :180
+    t_sel = np.hstack([arrivals[lp[i], 0] for i in range(n_batch)]) + arrivals_offset                     # :182
+    ph_sel = np.hstack([phase_labels[lp[i]] for i in range(n_batch)])
+    order = np.argsort(t_sel)                                                                             # :188
+    t_sel, ph_sel = t_sel[order], ph_sel[order]
+    n_arvs = len(t_sel)
+    sta_col = np.tile(ind_sta_select, n_spc).astype(np.float64)                                           # :156
+    batch = np.repeat(np.arange(n_batch), n_node).astype(np.float64)
+    q = [np.tile(x_grid_trv[:, ind_sta_select, ph].reshape(-1).astype(np.float64), n_batch) + batch * offset_per_batch
+         + np.tile(sta_col, n_batch) * offset_per_station for ph in (0, 1)]                               # :194-195
+
+    def nearest(times, query):                                                                            # :197-207
+        ip = np.searchsorted(times, query)
+        pad = np.minimum(np.maximum(ip.reshape(-1, 1) + np.array([-1, 0]).reshape(1, -1), 0), len(times) - 1)
+        return np.abs(query[:, np.newaxis] - times[pad]).min(1)
+
+    feats = np.zeros((n_batch * n_node, 4))
+    if n_arvs > 0:
+        feats[:, 0] = np.exp(-0.5 * (nearest(t_sel, q[0]) ** 2) / (kernel_sig_t ** 2))                    # :254
+        feats[:, 1] = np.exp(-0.5 * (nearest(t_sel, q[1]) ** 2) / (kernel_sig_t ** 2))
+    for ph in (0, 1):                                                                                     # :209-222
+        tp = t_sel[ph_sel == ph]
+        if len(tp) > 0:
+            feats[:, 2 + ph] = np.exp(-0.5 * (nearest(tp, q[ph]) ** 2) / (kernel_sig_t ** 2))             # :258-261
+    Inpts = [feats[i * n_node:(i + 1) * n_node] for i in range(n_batch)]
+    Masks = [1.0 * (x > 0.01) for x in Inpts]                                                             # :268
+    if return_parts:
+        return Inpts, Masks, dict(lp=lp, t_sel=t_sel, ph_sel=ph_sel, offset_per_batch=offset_per_batch,
+                                  offset_per_station=offset_per_station)
+    return Inpts, Masks
+
+
+def legacy_pick_lists(arrivals, phase_labels, ind_use, time_samples, lp, n_sta):
+    """process_utils.py:270-291: the per-sample pick lists (times relative to the sample, station slot, phase, meta),
+    sorted by (station slot, time)."""
+    sta_select = np.unique(ind_use)
+    out = ([], [], [], [])
+    for i in range(len(time_samples)):
+        perm_vec = -1 * np.ones(n_sta)
+        perm_vec[sta_select] = np.arange(len(sta_select))
+        meta = arrivals[lp[i], :]
+        phase_vals = phase_labels[lp[i]]
+        times = meta[:, 0]
+        indices = perm_vec[meta[:, 1].astype('int')]
+        ineed = np.where(indices > -1)[0]
+        times, indices, phase_vals, meta = times[ineed], indices[ineed], phase_vals[ineed], meta[ineed]
+        lex_sort = np.lexsort((times, indices))
+        out[0].append(times[lex_sort] - time_samples[i])
+        out[1].append(indices[lex_sort])
+        out[2].append(phase_vals[lex_sort])
+        out[3].append(meta[lex_sort])
+    return out
+
+
 # --------------------------------------------------------------------------------------------------------------------
 # a2 — DataAggregation (module.py:52-98)
 # --------------------------------------------------------------------------------------------------------------------

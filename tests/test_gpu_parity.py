@@ -135,6 +135,56 @@ def _random_case(S, G, k_s, k_g, seed, dev):
     return net, A_sta, A_src, torch.from_numpy(Slice), torch.from_numpy(Mask), torch.from_numpy(attr)
 
 
+@pytest.mark.parametrize('name', ['legacy_12of14x60', 'legacy_8x30_short'])
+def test_legacy_input_features_match_reference(name):
+    """a1': extract_inputs_from_data_fixed_grids_with_phase_type (process_utils.py:102-308) through the reference's own
+    call signature, against the unmodified reference: the fp64 feature rounded to fp32 and the 0.01 mask, bit for bit
+    up to the last bit of the device's fp64 exp."""
+    from scipy.spatial import cKDTree
+    from genie_b200.process_utils import extract_inputs_from_data_fixed_grids_with_phase_type as legacy
+    dev = _dev()
+    d, _ = load_golden(name)
+    P = d['picks']
+    tree = cKDTree(P[:, 0][:, None])
+    for use_tree in (tree, None):
+        [Inpts, Masks], lists = legacy(None, d['sta'], d['ind_use'], P, P[:, 4], use_tree, d['time_samples'], d['grid'],
+                                       d['trv_times'], None, None, None, float(d['max_t']), None, [8, 15, 10],
+                                       [float(d['t_win']), float(d['kernel_sig_t'])], None, None, device=dev)
+        for i in range(len(d['time_samples'])):
+            want = d['Inpts%d' % i].astype(np.float32)
+            got = Inpts[i].cpu().numpy()
+            assert got.shape == want.shape
+            assert np.abs(got - want).max() <= 2.0 * np.spacing(np.abs(want).max()) and np.mean(got == want) > 0.99
+            m_got, m_want = Masks[i].cpu().numpy(), d['Masks%d' % i].astype(np.float32)
+            edge = np.abs(d['Inpts%d' % i] - 0.01) < 1e-12          # a value within one ulp of the threshold may flip
+            assert np.array_equal(m_got[~edge], m_want[~edge])
+            for j, k in enumerate(('lp_times', 'lp_stations', 'lp_phases', 'lp_meta')):
+                assert np.array_equal(lists[j][i], d['%s%d' % (k, i)])
+
+
+def test_legacy_input_features_match_oracle_seeded():
+    """The same at 100 x 2000 with three samples per call, against the pinned oracle (empty S axis: all picks are P)."""
+    from genie_b200 import synth
+    from genie_b200.process_utils import extract_inputs_from_data_fixed_grids_with_phase_type as legacy
+    from oracle import genie_oracle as go
+    dev = _dev()
+    net = synth.Network(100, 2000, seed=2)
+    P = synth.make_picks(net, 0.0, 900.0, seed=3)
+    P = P[np.argsort(P[:, 0])]
+    ind_use = np.arange(100)
+    trv = net.travel_times()
+    ts = np.array([200.0, 260.5, 410.25])
+    for picks in (P, P[P[:, 4] == 0]):
+        want, want_m = go.legacy_input_features(picks, picks[:, 4], ind_use, ts, trv, net.max_moveout(), 10.0, 3.0)
+        [Inpts, Masks], _ = legacy(None, net.sta, ind_use, picks, picks[:, 4], None, ts, net.grid, trv, None, None, None,
+                                   net.max_moveout(), None, [8, 15, 10], [10.0, 3.0], None, None, device=dev)
+        for i in range(len(ts)):
+            got, w = Inpts[i].cpu().numpy(), want[i].astype(np.float32)
+            assert np.abs(got - w).max() <= 2.0 * np.spacing(1.0) and np.mean(got == w) > 0.99
+            edge = np.abs(want[i] - 0.01) < 1e-12
+            assert np.array_equal(Masks[i].cpu().numpy()[~edge], want_m[i].astype(np.float32)[~edge])
+
+
 @pytest.mark.parametrize('name', ['c1_10x100_edges', 'mid_36of40x300_edges'])
 def test_updated_model_definition_matches_reference(name):
     """a2': `use_updated_model_definition: True` (DataAggregationEdges, module.py:102-174, 1024-1186) through the

@@ -82,6 +82,22 @@ def test_edge_feature_model_matches_reference(name):
     assert rel_err(x.numpy(), d['x']) < 2e-6
 
 
+@pytest.mark.parametrize('name', ['legacy_12of14x60', 'legacy_8x30_short'])
+def test_legacy_input_features_match_reference(name):
+    """a1': extract_inputs_from_data_fixed_grids_with_phase_type run unmodified (oracle/gen_golden.py legacy_input)."""
+    d, _ = load_golden(name)
+    P = d['picks']
+    Inpts, Masks, parts = go.legacy_input_features(P, P[:, 4], d['ind_use'], d['time_samples'], d['trv_times'],
+                                                    float(d['max_t']), float(d['t_win']), float(d['kernel_sig_t']),
+                                                    return_parts=True)
+    lists = go.legacy_pick_lists(P, P[:, 4], d['ind_use'], d['time_samples'], parts['lp'], d['sta'].shape[0])
+    for i in range(len(d['time_samples'])):
+        assert np.array_equal(Inpts[i], d['Inpts%d' % i])          # same numpy expressions -> identical bits
+        assert np.array_equal(Masks[i], d['Masks%d' % i])
+        assert np.array_equal(lists[0][i], d['lp_times%d' % i]) and np.array_equal(lists[1][i], d['lp_stations%d' % i])
+        assert np.array_equal(lists[2][i], d['lp_phases%d' % i]) and np.array_equal(lists[3][i], d['lp_meta%d' % i])
+
+
 def test_mean_of_empty_neighbourhood_is_zero():
     msg = torch.ones(3, 2)
     out = go.propagate_mean(msg, torch.tensor([0, 0, 2]), 4)
