@@ -91,6 +91,11 @@ SIGNATURES = {
     'genie_plan_set_edge_terms': (ctypes.c_int, [_P, _P, _P]),
     'genie_frontend_packed_floats': (ctypes.c_size_t, []),
     'genie_frontend_pack_weights': (ctypes.c_int, [ctypes.POINTER(FrontendWeights), _P, _P]),
+    'genie_heads_packed_floats': (ctypes.c_size_t, []),
+    'genie_heads_layout': (ctypes.c_int, [_P, ctypes.c_int]),
+    'genie_heads_grid_fwd': (ctypes.c_int, [_P, _P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int, _P, _P]),
+    'genie_heads_query_fwd': (ctypes.c_int, [_P, _P, ctypes.c_int, _P, ctypes.c_int, _P, _P, _P, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_float, _P, _P]),
     'genie_input_nearest_fwd': (ctypes.c_int, [ctypes.POINTER(NearestParams), _P, _P, _P, _P, _P, _P, _P, _P]),
     'genie_input_scatter_fwd': (ctypes.c_int, [_P, ctypes.POINTER(InputParams), _P, ctypes.c_int64, _P, _P, _P, _P, _P,
                                                _P, _P, _P, _P, _P]),

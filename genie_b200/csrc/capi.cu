@@ -33,7 +33,7 @@ const char* const kKernelNames[KID_COUNT] = {"pack_weights_kernel", "input_serie
                                              "da_init_kernel",      "da_layer1_kernel",    "da_layer1_tc_kernel", "da_layer2_readin_kernel",
                                              "readin_finalize_kernel", "sa_pre_kernel",    "sa_main_kernel",
                                              "src_mean32_kernel",   "src_mean16_kernel",   "da_layer1_s_kernel",
-                                             "da_layer2_s_kernel"};
+                                             "da_layer2_s_kernel",  "heads_grid_kernel",   "heads_query_kernel"};
 }  // namespace
 
 TimedLaunch::TimedLaunch(int kid_, cudaStream_t st_) : kid(kid_), st(st_), slot(nullptr) {
@@ -294,6 +294,43 @@ int genie_input_scatter_fwd(const genie_plan_t* plan, const genie_input_params_t
     return launch_input_scatter(plan, prm, picks_dev, n_picks, sta_perm_dev, ind_use_dev, trv_times_dev, node_sta_dev,
                                 node_grid_dev, series_dev, slice_out_dev, mask_out_dev, time_bin_out_dev,
                                 static_cast<cudaStream_t>(stream));
+}
+
+size_t genie_heads_packed_floats(void) { return (size_t)HD_FLOATS; }
+
+int genie_heads_layout(int32_t* offsets_out, int n) {
+    static const int32_t k[] = {HD_SD_W, HD_SD_B, HD_SD_SL, HD_TA_WC1, HD_TA_BC1, HD_TA_WV1, HD_TA_BV1, HD_TA_WV2, HD_TA_BV2,
+                                HD_TA_WP1, HD_TA_BP1, HD_TA_WP2, HD_TA_BP2, HD_TA_SL, HD_SA_WQ, HD_SA_BQ, HD_SA_WC, HD_SA_BC,
+                                HD_SA_WV, HD_SA_BV, HD_SA_WP, HD_SA_BP, HD_SA_SL};
+    const int count = (int)(sizeof(k) / sizeof(k[0]));
+    if (!offsets_out || n < count) {
+        set_error("genie_heads_layout: need room for " + std::to_string(count) + " offsets");
+        return GENIE_ERR_INVALID;
+    }
+    for (int i = 0; i < count; ++i) offsets_out[i] = k[i];
+    return GENIE_OK;
+}
+
+int genie_heads_grid_fwd(const float* heads_packed_dev, const float* fold_dev, int n_t, const float* x_spatial_dev, int ld_x,
+                         int n_grid, float* y_out_dev, void* stream) {
+    if (!heads_packed_dev || !fold_dev || !x_spatial_dev || !y_out_dev || n_t < 0 || n_grid < 0 || ld_x < 30) {
+        set_error("genie_heads_grid_fwd: bad argument");
+        return GENIE_ERR_INVALID;
+    }
+    return launch_heads_grid(heads_packed_dev, fold_dev, n_t, x_spatial_dev, ld_x, n_grid, y_out_dev,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int genie_heads_query_fwd(const float* heads_packed_dev, const float* fold_dev, int n_t, const float* x_spatial_dev, int ld_x,
+                          const float* x_context_dev, const float* x_query_dev, const int64_t* nbr_dev, int k_nbr, int n_query,
+                          float scale_rel, float* x_out_dev, void* stream) {
+    if (!heads_packed_dev || !fold_dev || !x_spatial_dev || !x_context_dev || !x_query_dev || !nbr_dev || !x_out_dev ||
+        n_t < 0 || n_query < 0 || ld_x < 30 || !(scale_rel > 0.f)) {
+        set_error("genie_heads_query_fwd: bad argument");
+        return GENIE_ERR_INVALID;
+    }
+    return launch_heads_query(heads_packed_dev, fold_dev, n_t, x_spatial_dev, ld_x, x_context_dev, x_query_dev, nbr_dev, k_nbr,
+                              n_query, scale_rel, x_out_dev, static_cast<cudaStream_t>(stream));
 }
 
 int genie_input_nearest_fwd(const genie_nearest_params_t* prm, const double* times_all_dev, const double* times_p_dev,

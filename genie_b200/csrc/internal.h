@@ -87,6 +87,8 @@ enum KernelId {
     KID_SRC_MEAN16,
     KID_DA_LAYER1_S,
     KID_DA_LAYER2_S,
+    KID_HEADS_GRID,
+    KID_HEADS_QUERY,
     KID_COUNT
 };
 // Brackets one kernel launch with cudaEvents on its stream when timing is enabled (no-op otherwise).
@@ -148,6 +150,11 @@ int launch_da_layer1_s(const genie_plan* p, const float* packed, const float* pf
 void set_s1_trace(long long* buf, int tiles);
 int launch_da_layer2_s(const genie_plan* p, const float* packed, const float* zc, const float* va, const float* m2,
                        const float* mask, const float* edge_attr, float* latent_out, float* out, int ld_out,
+                       cudaStream_t st);
+int launch_heads_grid(const float* packed, const float* fold, int T, const float* x_spatial, int ld_x, int G, float* y,
+                      cudaStream_t st);
+int launch_heads_query(const float* packed, const float* fold, int T, const float* x_spatial, int ld_x, const float* x_context,
+                       const float* x_query, const int64_t* nbr, int k_nbr, int Q, float scale_rel, float* x_out,
                        cudaStream_t st);
 int launch_input_nearest(const genie_nearest_params_t* prm, const double* t_all, const double* t_p, const double* t_s,
                          const int32_t* ind_use, const float* trv_times, float* slice_out, float* mask_out, cudaStream_t st);

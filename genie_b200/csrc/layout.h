@@ -103,6 +103,34 @@ static_assert(DA_W11 % 4 == 0 && DA_END % 4 == 0 && RI_END % 4 == 0 && SA_SIZE %
                   T2_FLOATS % 4 == 0,
               "16-byte alignment");
 
+// ---- read-out heads (heads_kernels.cu; module.py:251-331) ---------------------------------------------------------------
+// Every matrix K-major [n_in][ld]; packed on the host (genie_b200/ops.py HeadsWeights) at the offsets genie_heads_layout reports.
+constexpr int HD_SD_W = 0;                          // SpatialDirect.f_direct                  [30][32]
+constexpr int HD_SD_B = HD_SD_W + 30 * 32;          //                                         [32]
+constexpr int HD_SD_SL = HD_SD_B + 32;              // [4]: activate
+constexpr int HD_TA_WC1 = HD_SD_SL + 4;             // TemporalAttention.f_context_1           [30][32]
+constexpr int HD_TA_BC1 = HD_TA_WC1 + 30 * 32;
+constexpr int HD_TA_WV1 = HD_TA_BC1 + 32;           // f_values_1                              [30][32]
+constexpr int HD_TA_BV1 = HD_TA_WV1 + 30 * 32;
+constexpr int HD_TA_WV2 = HD_TA_BV1 + 32;           // f_values_2                              [30][76]
+constexpr int HD_TA_BV2 = HD_TA_WV2 + 30 * 76;      //                                         [76]
+constexpr int HD_TA_WP1 = HD_TA_BV2 + 76;           // proj_1                                  [15][32]
+constexpr int HD_TA_BP1 = HD_TA_WP1 + 15 * 32;
+constexpr int HD_TA_WP2 = HD_TA_BP1 + 32;           // proj_2 (30 -> 1)                        [32]
+constexpr int HD_TA_BP2 = HD_TA_WP2 + 32;           //                                         [4]
+constexpr int HD_TA_SL = HD_TA_BP2 + 4;             // [4]: activate1, activate2, activate4, activate5
+constexpr int HD_SA_WQ = HD_TA_SL + 4;              // SpatialAttention.f_queries              [3][76]
+constexpr int HD_SA_BQ = HD_SA_WQ + 3 * 76;
+constexpr int HD_SA_WC = HD_SA_BQ + 76;             // f_context  rows 0-29 x_j, 30-32 edge attr [33][76]
+constexpr int HD_SA_BC = HD_SA_WC + 33 * 76;
+constexpr int HD_SA_WV = HD_SA_BC + 76;             // f_values                                [33][76]
+constexpr int HD_SA_BV = HD_SA_WV + 33 * 76;
+constexpr int HD_SA_WP = HD_SA_BV + 76;             // proj                                    [15][32]
+constexpr int HD_SA_BP = HD_SA_WP + 15 * 32;
+constexpr int HD_SA_SL = HD_SA_BP + 32;             // [4]: activate1, activate2
+constexpr int HD_FLOATS = HD_SA_SL + 4;
+static_assert(HD_FLOATS % 4 == 0 && HD_TA_WV2 % 4 == 0 && HD_SA_WC % 4 == 0 && HD_SA_WP % 4 == 0, "16-byte alignment");
+
 // ---- node-feature row strides in the workspace (floats) -------------------------------------------------------------
 constexpr int LD_TR0 = 32;   // tr0 rows padded to 128 B: one L2 line per gathered neighbour row
 constexpr int LD_ZC = 32;    // [ca(15) 0 | cb(15) 0]

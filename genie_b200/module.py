@@ -163,8 +163,15 @@ class SpatialAttention(nn.Module):
         key = (x_query.data_ptr(), x_query._version, tuple(x_query.shape), x_context.data_ptr(), x_context._version,
                tuple(x_context.shape), k)
         if self._edge_cache is None or self._edge_cache[0] != key:
-            self._edge_cache = (key, knn_query_edges(x_context, x_query, k), x_query, x_context)
+            self._edge_cache = (key, knn_query_edges(x_context, x_query, k), x_query, x_context, None)
         return self._edge_cache[1]
+
+    def _nbr_table(self, edge_index, Q):
+        """[Q, k] context node of every query edge (the k consecutive edges of a query), cached with the edges."""
+        c = self._edge_cache
+        if len(c) < 5 or c[4] is None or c[4].shape[0] != Q:
+            self._edge_cache = c[:4] + (edge_index[0].view(Q, -1).contiguous(),)
+        return self._edge_cache[4]
 
     def forward(self, inpts, x_query, x_context, k=10):
         edge_index = self._edges(x_query, x_context, k)
@@ -347,6 +354,7 @@ class GCN_Detection_Network_extended(nn.Module):
         self._plan_key = None
         self._packed = None
         self._read_in_attr = None
+        self._heads = None
         self._edge_means = None       # updated model: (means_sta(scale), means_src(scale)) of the current plan
         self._edge_terms = None       # (key, t_sta, t_src, re-laid weight tensors)
 
@@ -464,6 +472,15 @@ class GCN_Detection_Network_extended(nn.Module):
         """module.py:999-1020 -> (y [G,T,1], x [Q,T,1])."""
         with torch.no_grad():
             x_spatial = self.front_end(Slice, Mask, x_temp_cuda_cart)[0]
+            if ops.HeadsWeights.supported(self) and x_query_cart.shape[0] > 0:
+                # read-out heads in libgenie_b200 (two kernels); the torch restatement below is kept for other head shapes
+                if self._heads is None or self._heads.device != x_spatial.device:
+                    self._heads = ops.HeadsWeights(x_spatial.device)
+                hp, fold, T = self._heads.update(self, t_query)
+                edges = self.SpatialAttention._edges(x_query_cart, x_temp_cuda_cart, 10)
+                nbr = self.SpatialAttention._nbr_table(edges, x_query_cart.shape[0])
+                return ops.heads_fwd(self._heads, hp, fold, T, x_spatial, x_temp_cuda_cart, x_query_cart, nbr,
+                                     float(self.SpatialAttention.scale_rel))
             y_latent = self.SpatialDirect(x_spatial)
             y = self.TemporalAttention(y_latent, t_query)
             x = self.SpatialAttention(x_spatial, x_query_cart, x_temp_cuda_cart)

@@ -83,6 +83,99 @@ class PackedWeights(object):
         return self.buf
 
 
+class HeadsWeights(object):
+    """Kernel-layout copy of the read-out head parameters (SpatialDirect, TemporalAttention, SpatialAttention) and the
+    t_query branch of TemporalAttention folded into f_context_2 (include/genie_b200.h, genie_heads_*).  Re-packed whenever
+    a parameter changes; the fold is cached per t_query tensor."""
+    NAMES = ('SD_W', 'SD_B', 'SD_SL', 'TA_WC1', 'TA_BC1', 'TA_WV1', 'TA_BV1', 'TA_WV2', 'TA_BV2', 'TA_WP1', 'TA_BP1',
+             'TA_WP2', 'TA_BP2', 'TA_SL', 'SA_WQ', 'SA_BQ', 'SA_WC', 'SA_BC', 'SA_WV', 'SA_BV', 'SA_WP', 'SA_BP', 'SA_SL')
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        lib = capi.load()
+        off = (ctypes.c_int32 * len(self.NAMES))()
+        capi.check(lib.genie_heads_layout(off, len(self.NAMES)))
+        self.off = dict(zip(self.NAMES, [int(o) for o in off]))
+        self.buf = torch.zeros(int(lib.genie_heads_packed_floats()), dtype=F32, device=self.device)
+        self._key, self._fold = None, None
+
+    @staticmethod
+    def supported(model):
+        sd, ta, sa = model.SpatialDirect, model.TemporalAttention, model.SpatialAttention
+        return (tuple(sd.f_direct.weight.shape) == (30, 30) and tuple(ta.f_context_1.weight.shape) == (30, 30) and
+                tuple(ta.f_context_2.weight.shape) == (75, 30) and tuple(ta.proj_2.weight.shape) == (1, 30) and
+                ta.n_heads == 5 and ta.n_latent == 15 and tuple(sa.f_context.weight.shape) == (75, 33) and
+                tuple(sa.proj.weight.shape) == (30, 15) and sa.n_heads == 5 and sa.n_latent == 15)
+
+    def _mat(self, name, lin_w, ld):
+        w = lin_w.detach().t().contiguous()                         # [n_in, n_out]
+        n_in, n_out = w.shape
+        o = self.off[name]
+        self.buf[o:o + n_in * ld].view(n_in, ld)[:, :n_out] = w
+
+    def _vec(self, name, v):
+        v = v.detach().reshape(-1)
+        self.buf[self.off[name]:self.off[name] + v.numel()] = v
+
+    def update(self, model, t_query):
+        sd, ta, sa = model.SpatialDirect, model.TemporalAttention, model.SpatialAttention
+        mods = (sd, ta, sa)
+        key = tuple((p.data_ptr(), p._version) for m in mods for p in m.parameters())
+        if key != self._key:
+            with torch.no_grad():
+                self.buf.zero_()
+                self._mat('SD_W', sd.f_direct.weight, 32); self._vec('SD_B', sd.f_direct.bias)
+                self._vec('SD_SL', sd.activate.weight)
+                self._mat('TA_WC1', ta.f_context_1.weight, 32); self._vec('TA_BC1', ta.f_context_1.bias)
+                self._mat('TA_WV1', ta.f_values_1.weight, 32); self._vec('TA_BV1', ta.f_values_1.bias)
+                self._mat('TA_WV2', ta.f_values_2.weight, 76); self._vec('TA_BV2', ta.f_values_2.bias)
+                self._mat('TA_WP1', ta.proj_1.weight, 32); self._vec('TA_BP1', ta.proj_1.bias)
+                self._vec('TA_WP2', ta.proj_2.weight); self._vec('TA_BP2', ta.proj_2.bias)
+                self._vec('TA_SL', torch.cat([a.weight.detach().reshape(1) for a in
+                                              (ta.activate1, ta.activate2, ta.activate4, ta.activate5)]))
+                self._mat('SA_WQ', sa.f_queries.weight, 76); self._vec('SA_BQ', sa.f_queries.bias)
+                self._mat('SA_WC', sa.f_context.weight, 76); self._vec('SA_BC', sa.f_context.bias)
+                self._mat('SA_WV', sa.f_values.weight, 76); self._vec('SA_BV', sa.f_values.bias)
+                self._mat('SA_WP', sa.proj.weight, 32); self._vec('SA_BP', sa.proj.bias)
+                self._vec('SA_SL', torch.cat([sa.activate1.weight.detach().reshape(1), sa.activate2.weight.detach().reshape(1)]))
+            self._key, self._fold = key, None
+        fkey = (t_query.data_ptr(), t_query._version, tuple(t_query.shape), float(ta.scale_t))
+        if self._fold is None or self._fold[0] != fkey:
+            with torch.no_grad():
+                T = t_query.shape[0]
+                q = ta.temporal_query_2(ta.activate3(ta.temporal_query_1(t_query.reshape(-1, 1).float() / ta.scale_t)))
+                q = q.view(T, 5, 15)
+                w2 = ta.f_context_2.weight.detach().view(5, 15, 30)
+                b2 = ta.f_context_2.bias.detach().view(5, 15)
+                A = torch.einsum('thl,hlk->thk', q, w2) / ta.scale                  # [T, 5, 30]
+                a0 = torch.einsum('thl,hl->th', q, b2) / ta.scale                   # [T, 5]
+                fold = torch.zeros(T * 5 * 32 + T * 5, dtype=F32, device=self.device)
+                fold[:T * 5 * 32].view(T * 5, 32)[:, :30] = A.reshape(T * 5, 30)
+                fold[T * 5 * 32:] = a0.reshape(-1)
+            self._fold = (fkey, fold, T, t_query)
+        return self.buf, self._fold[1], self._fold[2]
+
+
+def heads_fwd(hw, packed, fold, T, x_spatial, x_context, x_query, nbr, scale_rel):
+    """y [G,T,1], x [Q,T,1] of forward_fixed_source (module.py:1015-1020) in two kernels."""
+    dev = x_spatial.device
+    x_spatial = _f32c(x_spatial, 'x_spatial')
+    G, Q = x_spatial.shape[0], x_query.shape[0]
+    y = torch.empty((G, T, 1), dtype=F32, device=dev)
+    x = torch.empty((Q, T, 1), dtype=F32, device=dev)
+    lib = capi.load()
+    with torch.cuda.device(dev):
+        capi.check(lib.genie_heads_grid_fwd(capi.dptr(packed, F32), capi.dptr(fold, F32), int(T), capi.dptr(x_spatial, F32),
+                                            int(x_spatial.stride(0)), int(G), capi.dptr(y), capi.stream_ptr(dev)))
+        if Q > 0:
+            capi.check(lib.genie_heads_query_fwd(
+                capi.dptr(packed, F32), capi.dptr(fold, F32), int(T), capi.dptr(x_spatial, F32), int(x_spatial.stride(0)),
+                capi.dptr(_f32c(x_context, 'x_context'), F32), capi.dptr(_f32c(x_query, 'x_query'), F32),
+                capi.dptr(nbr, torch.int64), int(nbr.shape[1]), int(Q), float(scale_rel), capi.dptr(x),
+                capi.stream_ptr(dev)))
+    return y, x
+
+
 def _f32c(t, name):
     if t.dtype != F32:
         t = t.float()

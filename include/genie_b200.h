@@ -184,6 +184,27 @@ GENIE_API int genie_input_scatter_fwd(const genie_plan_t* plan, const genie_inpu
                             float* series_dev, float* slice_out_dev, float* mask_out_dev, int64_t* time_bin_out_dev,
                             void* stream);
 
+/* ---- read-out heads (the step right after the front end) ---------------------------------------------
+ * y = TemporalAttention(SpatialDirect(x_spatial), t_query)                         (module.py:251-260, 299-331, 1015-1016)
+ * x = TemporalAttention(SpatialAttention(x_spatial, x_query, x_context), t_query)  (module.py:262-297, 1018-1020)
+ *   heads_packed_dev  fp32 [genie_heads_packed_floats()]: every nn.Linear of the three modules K-major [n_in][ld] at the
+ *                     offsets genie_heads_layout reports (order: SpatialDirect W, b, slope; TemporalAttention f_context_1 W, b,
+ *                     f_values_1 W, b, f_values_2 W, b, proj_1 W, b, proj_2 W, b, slopes {1,2,4,5}; SpatialAttention f_queries
+ *                     W, b, f_context W, b, f_values W, b, proj W, b, slopes {1,2}); ld = 32 / 76 for 30 / 75 outputs.
+ *   fold_dev          fp32 [n_t*5*32 + n_t*5]: the t_query branch folded into f_context_2 — row (t*5+h) of A (32 floats, 30
+ *                     used) = q[t,h,:] . f_context_2.weight[h*15:(h+1)*15, :] / sqrt(15), then a0[t*5+h] = q[t,h,:] .
+ *                     f_context_2.bias[h*15:(h+1)*15] / sqrt(15), q = temporal_query_2(activate3(temporal_query_1(t/scale_t))).
+ *   nbr_dev           int64 [n_query][k_nbr] context node of every query edge, nearest first (knn(...).flip(0), module.py:282).
+ *   y_out_dev [n_grid][n_t], x_out_dev [n_query][n_t].
+ */
+GENIE_API size_t genie_heads_packed_floats(void);
+GENIE_API int genie_heads_layout(int32_t* offsets_out, int n);
+GENIE_API int genie_heads_grid_fwd(const float* heads_packed_dev, const float* fold_dev, int n_t, const float* x_spatial_dev,
+                                   int ld_x, int n_grid, float* y_out_dev, void* stream);
+GENIE_API int genie_heads_query_fwd(const float* heads_packed_dev, const float* fold_dev, int n_t, const float* x_spatial_dev,
+                                    int ld_x, const float* x_context_dev, const float* x_query_dev, const int64_t* nbr_dev,
+                                    int k_nbr, int n_query, float scale_rel, float* x_out_dev, void* stream);
+
 /* ---- a1': nearest-pick input features -----------------------------------------------------------------------------------
  * Replaces the device-sized part of process_utils.extract_inputs_from_data_fixed_grids_with_phase_type
  * (process_utils.py:194-268; the input features used when `use_updated_input: False` and in training): per sample b, product
