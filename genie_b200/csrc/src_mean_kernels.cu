@@ -4,15 +4,15 @@
 //
 // The product edge (g,s) <- (g',s) keeps the station, so for a slab of stations the pass is a sparse G x G matrix applied
 // to dense rows.  The kernel walks compact groups of grid nodes (genie_graph_desc_t.grid_grp_*, built by recursive
-// bisection of the grid graph): the source-neighbour sets of the ~64 nodes of a group overlap heavily (union ~200 rows
-// instead of 64 x 15), and ONE 1024-thread CTA per SM works on one (group, station slab) tile at a time, so the union of
-// neighbour rows (<= 265 x 512 B) sits in that SM's L1 while the group's nodes re-read it: L2 sees every row ~3 times
-// instead of 15, DRAM once (tiles are visited slab-major: all groups of one slab, G x 512 B = 26 MB, stay L2 resident).
+// bisection of the grid graph): the source-neighbour sets of the <= 256 nodes of a group overlap heavily (union ~600 rows
+// instead of 256 x 15), and ONE 1024-thread CTA per SM works on one (group, 8-station slab) tile at a time, so the union
+// of neighbour rows is re-read through that SM's L1 / the L2 while the group's nodes are summed: DRAM sees every row once
+// (tiles are visited slab-major: all groups of one slab, G x 1 KB = 51 MB at C4, stay L2 resident).  Group size and slab
+// width were swept on the GPU; the L1 data pipe is 88 % / 95 % busy (profiles/r1zl_ncu_full_summary.md).
 // Lanes map to 16-byte chunks of a row (8 lanes per 128-byte row), so every request is a fully used 128-byte line; there
 // is no shared memory, no barrier and no atomics: warps drift apart freely, and the leaders pull the next tile's rows
 // into L1 while the stragglers finish.
 #include "common.cuh"
-#include <cstdlib>
 
 using namespace gl;
 
@@ -21,7 +21,7 @@ namespace {
 constexpr int SM_THREADS = 1024;
 
 // W = floats per row (32: layer-0 features p, 16: layer-2 messages v_b); SB = stations per slab (even)
-template <int W, int SB, bool PREFETCH>
+template <int W, int SB>
 __global__ void __launch_bounds__(SM_THREADS, 1)
     src_mean_kernel(const float* __restrict__ X, float* __restrict__ out, int S, const int64_t* __restrict__ rowptr,
                     const int32_t* __restrict__ col, const int32_t* __restrict__ grp_ptr,
@@ -40,34 +40,6 @@ __global__ void __launch_bounds__(SM_THREADS, 1)
         const int gcnt = __ldg(grp_ptr + grp + 1) - gbeg;
         const int s0 = slab * SB;
         const int items = gcnt * PAIRS * LPR;
-        if (PREFETCH) {     // measured on B200 (r1r): 5.1 -> 8.5 ms, the extra L1 requests cost more than the misses: kept off
-            // Pull the neighbour rows of this CTA's NEXT tile into L1 while this tile is summed (the union of a group's rows
-            // then hits instead of stalling the warps on its first touch).  The PAIRS * LPR threads of a grid node share its
-            // deg x (slab bytes / 128) lines.
-            const int64_t tn = t + gridDim.x;
-            if (tn < n_tiles) {
-                const int slab_n = (int)(tn / n_groups);
-                const int grp_n = (int)(tn - (int64_t)slab_n * n_groups);
-                const int gbeg_n = __ldg(grp_ptr + grp_n);
-                const int gcnt_n = __ldg(grp_ptr + grp_n + 1) - gbeg_n;
-                constexpr int LINES = SB * W * 4 / 128;          // 128-byte lines of one neighbour row inside the slab
-                constexpr int TPN = PAIRS * LPR;                 // threads per grid node
-                const int i = threadIdx.x;
-                if (i < gcnt_n * TPN) {
-                    const int gl = i / TPN, sub = i - gl * TPN;
-                    const int g = __ldg(grp_nodes + gbeg_n + gl);
-                    const int beg = (int)__ldg(rowptr + g);
-                    const int deg = (int)__ldg(rowptr + g + 1) - beg;
-                    const char* base = reinterpret_cast<const char*>(X) + (size_t)slab_n * SB * W * 4;
-                    for (int n = sub; n < deg * LINES; n += TPN) {
-                        const int j = n / LINES, line = n - j * LINES;
-                        if (slab_n * SB + line * (128 / (W * 4)) >= S) continue;     // ragged last slab
-                        const uint32_t nb = (uint32_t)__ldg(col + beg + j);
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (size_t)nb * gstride * 16 + line * 128));
-                    }
-                }
-            }
-        }
         for (int i = threadIdx.x; i < items; i += SM_THREADS) {
             const int c = i % LPR;
             const int pr = (i / LPR) % PAIRS;
@@ -126,7 +98,7 @@ static void launch_src_mean_t(const genie_plan* p, const float* X, float* out, c
     const int n_slabs = (g.n_sta + SB - 1) / SB;
     const int64_t n_tiles = (int64_t)g.n_grid_groups * n_slabs;
     const unsigned grid = (unsigned)(n_tiles < p->sm_count ? n_tiles : p->sm_count);
-    src_mean_kernel<W, SB, false><<<grid, SM_THREADS, 0, st>>>(X, out, g.n_sta, g.src_rowptr, g.src_col, g.grid_grp_ptr,
+    src_mean_kernel<W, SB><<<grid, SM_THREADS, 0, st>>>(X, out, g.n_sta, g.src_rowptr, g.src_col, g.grid_grp_ptr,
                                                         g.grid_grp_nodes, g.n_grid_groups, n_slabs, gate);
 }
 
@@ -134,25 +106,14 @@ int launch_src_mean(const genie_plan* p, int width, const float* X, float* out, 
     // one slab = 512 bytes of every neighbour row: 4 stations of 128-byte rows, 8 stations of 64-byte rows
     // (64 grid nodes x 2 station pairs x 8 lanes = 1024 items: one item per thread of the CTA)
     // One slab = 8 stations of every neighbour row (1024 B of 128-byte rows, 512 B of 64-byte rows): measured best on B200
-    // together with groups of 256 grid nodes (r1zd / r1ze sweeps: 5.2 -> 3.9 ms and 3.6 -> 3.3 ms at C4).
-    static int slab32 = 0, slab16 = 0;             // development knobs: bytes of every neighbour row one tile covers
-    if (slab32 == 0) {
-        const char* e = getenv("GENIE_SRC_SLAB32");
-        slab32 = e ? atoi(e) : 1024;
-        e = getenv("GENIE_SRC_SLAB16");
-        slab16 = e ? atoi(e) : 512;
-    }
+    // together with groups of 256 grid nodes (sweeps of 64..4096 nodes x 256..2048 bytes, gpurun r1zd-r1zf: 5.2 -> 3.9 ms and
+    // 3.6 -> 3.3 ms at C4).
     if (width == 32) {
         TimedLaunch tl(KID_SRC_MEAN32, st);
-        if (slab32 == 256) launch_src_mean_t<32, 2>(p, X, out, gate, st);
-        else if (slab32 == 512) launch_src_mean_t<32, 4>(p, X, out, gate, st);
-        else if (slab32 == 2048) launch_src_mean_t<32, 16>(p, X, out, gate, st);
-        else launch_src_mean_t<32, 8>(p, X, out, gate, st);
+        launch_src_mean_t<32, 8>(p, X, out, gate, st);
     } else if (width == 16) {
         TimedLaunch tl(KID_SRC_MEAN16, st);
-        if (slab16 == 256) launch_src_mean_t<16, 4>(p, X, out, gate, st);
-        else if (slab16 == 1024) launch_src_mean_t<16, 16>(p, X, out, gate, st);
-        else launch_src_mean_t<16, 8>(p, X, out, gate, st);
+        launch_src_mean_t<16, 8>(p, X, out, gate, st);
     } else {
         set_error("launch_src_mean: unsupported row width");
         return GENIE_ERR_INVALID;

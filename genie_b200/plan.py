@@ -48,7 +48,7 @@ def locality_order(rowptr, col, n):
 # ---- on-chip tiling tables of the split (source pass / station pass) kernels ----------------------------------------------
 TILE_M = 128        # product-node rows of one station tile (= MMA M)
 ROWS_MAX = 288      # station rows (tile + halo) staged in shared memory per tile; row ROWS_MAX is an all-zero row
-GROUP_SIZE = int(os.environ.get('GENIE_GROUP_SIZE', 256))    # grid nodes per source-pass group (measured best on B200)
+GROUP_SIZE = 256    # grid nodes per source-pass group (measured best on B200 together with 8-station slabs)
 
 
 def bisection_groups(rowptr, col, n, size):
