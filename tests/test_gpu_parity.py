@@ -135,6 +135,38 @@ def _random_case(S, G, k_s, k_g, seed, dev):
     return net, A_sta, A_src, torch.from_numpy(Slice), torch.from_numpy(Mask), torch.from_numpy(attr)
 
 
+@pytest.mark.parametrize('G,Q,T', [(7, 5, 3), (300, 77, 5), (1000, 130, 12)])
+def test_head_kernels_match_the_torch_restatement(G, Q, T):
+    """genie_heads_grid_fwd / genie_heads_query_fwd against the torch restatement of SpatialDirect, SpatialAttention and
+    TemporalAttention (module.py:251-331; itself checked against the reference's y, x in the golden tests): ragged sizes,
+    fewer context nodes than k = 10, other numbers of query times."""
+    from genie_b200 import ops
+    from genie_b200.module import GCN_Detection_Network_extended
+    dev = _dev()
+    torch.manual_seed(G)
+    m = GCN_Detection_Network_extended(None, None, device=dev).eval()
+    for mod in (m.SpatialDirect, m.SpatialAttention, m.TemporalAttention):
+        for name, prm in mod.named_parameters():
+            if name.endswith('weight') and prm.numel() == 1:
+                prm.data.fill_(0.1 + 0.5 * float(torch.rand(1)))            # distinct PReLU slopes
+    x_spatial = torch.randn((G, 30), device=dev)
+    ctx = torch.rand((G, 3), device=dev) * 50000.0
+    xq = torch.rand((Q, 3), device=dev) * 50000.0
+    tq = torch.linspace(-4.0, 4.0, T, device=dev).reshape(-1, 1)
+    with torch.no_grad():
+        want_y = m.TemporalAttention(m.SpatialDirect(x_spatial), tq)
+        want_x = m.TemporalAttention(m.SpatialAttention(x_spatial, xq, ctx), tq)
+        hw = ops.HeadsWeights(dev)
+        hp, fold, Tn = hw.update(m, tq)
+        edges = m.SpatialAttention._edges(xq, ctx, 10)
+        nbr = m.SpatialAttention._nbr_table(edges, Q)
+        assert nbr.shape == (Q, min(10, G))
+        y, x = ops.heads_fwd(hw, hp, fold, Tn, x_spatial, ctx, xq, nbr, float(m.SpatialAttention.scale_rel))
+    assert y.shape == want_y.shape and x.shape == want_x.shape
+    assert rel_err(y.cpu().numpy(), want_y.cpu().numpy()) < 2e-5
+    assert rel_err(x.cpu().numpy(), want_x.cpu().numpy()) < 2e-5
+
+
 @pytest.mark.parametrize('name', ['legacy_12of14x60', 'legacy_8x30_short'])
 def test_legacy_input_features_match_reference(name):
     """a1': extract_inputs_from_data_fixed_grids_with_phase_type (process_utils.py:102-308) through the reference's own
