@@ -123,8 +123,36 @@ def station_tiles(rowptr, col, n_sta, tile_m=TILE_M, rows_max=ROWS_MAX):
             rows[i, :len(lst)] = lst
             meta[i] = (len(own), len(lst))
         if ok:
+            _pair_neighbour_order(nbr, rows_max)
             return dict(rows=rows, meta=meta, nbr=nbr, invdeg=invdeg, tile=t)
     return None
+
+
+def _pair_neighbour_order(nbr, pad):
+    """Orders every row's neighbour list so that the layer-2 gather of 64-byte rows is (mostly) free of shared-memory bank
+    conflicts.  A 64-byte staged row covers half of the 32 banks — which half is the parity of its staged index — and the lanes
+    r and r + 4 of a quarter-warp read the same 16-byte chunk position at every step (da_s2_kernel.cu), so they collide exactly
+    when their step-j neighbours have the same parity.  For every such pair the two lists are re-ordered (a sum does not care)
+    so that at as many steps as possible one lane reads an even and the other an odd staged row; padding goes last."""
+    nt, tm, k = nbr.shape
+    for t in range(nt):
+        for r in range(tm):
+            if r & 4:
+                continue
+            s = r + 4
+            a = [int(x) for x in nbr[t, r] if x != pad]
+            b = [int(x) for x in nbr[t, s] if x != pad] if s < tm else []
+            ea, oa = [x for x in a if x % 2 == 0], [x for x in a if x % 2]
+            eb, ob = [x for x in b if x % 2 == 0], [x for x in b if x % 2]
+            n1 = min(len(ea), len(ob))                      # steps with (even, odd)
+            n2 = min(len(oa), len(eb))                      # steps with (odd, even)
+            new_a = ea[:n1] + oa[:n2] + ea[n1:] + oa[n2:]
+            new_b = ob[:n1] + eb[:n2] + ob[n1:] + eb[n2:]
+            nbr[t, r, :] = pad
+            nbr[t, r, :len(new_a)] = new_a
+            if s < tm:
+                nbr[t, s, :] = pad
+                nbr[t, s, :len(new_b)] = new_b
 
 
 def _is_cartesian(A_in_sta, A_in_src, prod_target, S, G):
