@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1)
                     const int32_t* __restrict__ grp_nodes, int n_groups, int n_slabs, const float* __restrict__ gate) {
     if (gate != nullptr && *gate == 0.f) return;     // the one-pass kernels run instead (layout.h TCS_OK)
     constexpr int LPR = W / 4;                       // lanes (16-byte chunks) per row
-    constexpr int PAIRS = SB / 2;                    // every lane sums the same chunk of TWO consecutive stations
+    constexpr int PAIRS = SB / 2;                    // every lane sums the same chunk of TWO stations (s and s + PAIRS)
     const float4* __restrict__ X4 = reinterpret_cast<const float4*>(X);
     float4* __restrict__ O4 = reinterpret_cast<float4*>(out);
     const uint32_t gstride = (uint32_t)S * LPR;      // float4 units between consecutive grid nodes (P * LPR < 2^32 checked)
@@ -44,14 +44,14 @@ __global__ void __launch_bounds__(SM_THREADS, 1)
             const int c = i % LPR;
             const int pr = (i / LPR) % PAIRS;
             const int gl = i / (LPR * PAIRS);
-            const int s = s0 + 2 * pr;
+            const int s = s0 + pr;                 // the lanes of one load cover CONSECUTIVE stations: 128-byte lines fully used
             if (s >= S) continue;
-            const bool two = s + 1 < S;
+            const bool two = s + PAIRS < S;        // second station of this lane: PAIRS further on
             const int g = __ldg(grp_nodes + gbeg + gl);
             const int beg = (int)__ldg(rowptr + g);
             const int deg = (int)__ldg(rowptr + g + 1) - beg;
             const uint32_t off = (uint32_t)s * LPR + c;                   // chunk c of station s inside a grid node's block
-            const uint32_t off2 = two ? off + LPR : off;                  // same chunk of station s + 1 (clamped at the edge)
+            const uint32_t off2 = two ? off + PAIRS * LPR : off;          // same chunk of station s + PAIRS (clamped at the edge)
             const int32_t* __restrict__ cp = col + beg;
             float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
             int j = 0;
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1)
             const float inv = deg > 0 ? 1.f / (float)deg : 0.f;
             const uint32_t o = (uint32_t)g * gstride + off;
             __stcs(O4 + o, make_float4(a0.x * inv, a0.y * inv, a0.z * inv, a0.w * inv));
-            if (two) __stcs(O4 + (o + LPR), make_float4(a1.x * inv, a1.y * inv, a1.z * inv, a1.w * inv));
+            if (two) __stcs(O4 + (o + PAIRS * LPR), make_float4(a1.x * inv, a1.y * inv, a1.z * inv, a1.w * inv));
         }
     }
 }
