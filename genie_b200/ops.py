@@ -43,7 +43,9 @@ class PackedWeights(object):
         """`relaid`: updated model definition only — (l1_t1_2, l1_t2_2, l2_t1_2, l2_t2_2) weights without their four
         edge-feature columns ([30,64] / [15,94]); those columns live in the plan's edge-term tables."""
         da, ri, sas, mods = self._sources(model)
-        key = tuple((p.data_ptr(), p._version) for m in mods for p in m.parameters())
+        if getattr(self, '_plist_for', None) is not model:           # nn.Module.parameters() walks the tree: ~70 us per call
+            self._plist, self._plist_for = [p for m in mods for p in m.parameters()], model
+        key = tuple((p.data_ptr(), p._version) for p in self._plist)
         if relaid is not None:
             key = key + tuple(t.data_ptr() for t in relaid)
         if key == self._key:
@@ -120,7 +122,9 @@ class HeadsWeights(object):
     def update(self, model, t_query):
         sd, ta, sa = model.SpatialDirect, model.TemporalAttention, model.SpatialAttention
         mods = (sd, ta, sa)
-        key = tuple((p.data_ptr(), p._version) for m in mods for p in m.parameters())
+        if getattr(self, '_plist_for', None) is not model:
+            self._plist, self._plist_for = [p for m in mods for p in m.parameters()], model
+        key = tuple((p.data_ptr(), p._version) for p in self._plist)
         if key != self._key:
             with torch.no_grad():
                 self.buf.zero_()
