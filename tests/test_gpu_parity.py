@@ -441,6 +441,46 @@ def test_station_permutation_invariance_large():
     assert rel_err(xs2.cpu().numpy(), xs.cpu().numpy()) < 1e-5
 
 
+def test_full_size_c4_split_equals_one_pass():
+    """BASELINE.json's headline size (1000 stations x 50000 grid nodes, P = 5e7) cannot be checked against the CPU oracle;
+    instead the two independent kernel families are compared on it — the split source-pass / two-pipeline tcgen05 station
+    pass (tiling tables) and the one-pass kernels (no tables: L2 gathers, FFMA read-in with atomics) — plus run-to-run bit
+    equality of the atomic-free split path.  Inputs are generated on the device."""
+    from genie_b200 import ops, synth
+    from genie_b200.plan import GraphPlan
+    from genie_b200.module import GCN_Detection_Network_extended
+    from genie_b200.process_utils import extract_inputs_adjacencies_cartesian
+    from oracle import genie_oracle as go
+    dev = _dev()
+    if torch.cuda.get_device_properties(dev).total_memory < 100e9:
+        pytest.skip('needs ~60 GB of device memory')
+    S, G = 1000, 50000
+    net = synth.Network(S, G, seed=0)
+    A_sta, A_src = extract_inputs_adjacencies_cartesian(net.sta, net.grid, 15, 15)
+    gen = torch.Generator(device=dev).manual_seed(5)
+    P = S * G
+    Slice = torch.rand((P, 4), device=dev, generator=gen) * (torch.rand((P, 4), device=dev, generator=gen) < 0.3)
+    Mask = (Slice.abs() > 0.01).float()
+    attr = torch.rand((P, 3), device=dev, generator=gen) - 0.5
+    grid = torch.from_numpy(net.grid).float().to(dev)
+    m = GCN_Detection_Network_extended(None, None, device=dev)
+    m.load_state_dict(go.init_state(seed=6), strict=False)
+    packed = m._packed_weights(dev)
+    outs = []
+    for tiling in (True, False):
+        plan = GraphPlan.cartesian(A_sta, A_src, S, G, device=dev, tiling=tiling)
+        xs, _, r = ops.frontend_fwd(plan, packed, Slice, Mask, attr, grid, 30000.0, want_readin=True)
+        if tiling:
+            xs2, _, r2 = ops.frontend_fwd(plan, packed, Slice, Mask, attr, grid, 30000.0, want_readin=True)
+            assert torch.equal(xs, xs2) and torch.equal(r, r2)
+        outs.append((xs.cpu().numpy(), r.cpu().numpy()))
+        del plan
+        torch.cuda.empty_cache()
+    assert np.isfinite(outs[0][0]).all() and np.abs(outs[0][0]).max() > 0
+    assert rel_err(outs[0][1], outs[1][1]) < 2e-5
+    assert rel_err(outs[0][0], outs[1][0]) < 2e-5
+
+
 def test_config2_against_oracle():
     """BASELINE.json configs[1]: 100 stations x 5000 grid nodes, k = 15 / 15 (P = 500 000), full front end vs oracle."""
     from genie_b200 import ops
