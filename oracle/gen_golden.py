@@ -3,6 +3,7 @@
     python oracle/gen_golden.py synthetic      # seeded synthetic networks, reference default-initialised weights
     python oracle/gen_golden.py synthetic_edges  # same, `use_updated_model_definition: True` (DataAggregationEdges)
     python oracle/gen_golden.py legacy_input     # a1': extract_inputs_from_data_fixed_grids_with_phase_type
+    python oracle/gen_golden.py association      # forward_fixed incl. the association branch
     python oracle/gen_golden.py ferndale       # Examples/Ferndale.zip: real stations/grids/picks + trained checkpoint
 
 The reference classes (`/root/reference/Code/module.py`, `process_utils.py`) are imported as they are, with
@@ -194,6 +195,130 @@ def legacy_input():
               [int((np.asarray(x) > 0).sum()) for x in Inpts], Inpts[0].dtype, Inpts[0].shape)
 
 
+def association():
+    """§8f rank 2: `forward_fixed` (module.py:963-997) of the UNMODIFIED reference — front end + heads + association branch
+    (BipartiteGraphReadOutOperator, DataAggregationAssociationPhase, LocalSliceLgCollapse{P,S}, Arrivals).  Set-up as in
+    process_continuous_days.py:627-634; the time-pointer tables through the reference's own
+    compute_time_embedding_vectors (process_utils.py:851-877)."""
+    work = tempfile.mkdtemp(prefix='genie_golden_')
+    for f in ('config.yaml', 'train_config.yaml'):
+        shutil.copy(os.path.join(REF, 'Code', f), work)
+    torch, module, pu, Data = _import_reference(os.path.join(REF, 'Code'), work)
+    from genie_b200 import synth
+
+    def identity(x):
+        return x
+
+    for name, S_all, n_use, G, k_sta, k_spc, Q, n_src, seed in (('assoc_10x100', 10, 10, 100, 8, 15, 32, 3, 0),
+                                                                ('assoc_18of20x160', 20, 18, 160, 8, 15, 48, 2, 9)):
+        net = synth.Network(S_all, G, seed=seed, width_km=60.0 if S_all <= 10 else 90.0)
+        rng = np.random.default_rng(300 + seed)
+        ind_use = np.sort(rng.choice(S_all, size=n_use, replace=False))
+        S = n_use
+        max_t = net.max_moveout()
+        sig, dt = 3.0, float(np.round(3.0 / 10.0, 2))
+        P = synth.make_picks(net, 0.0, 600.0, seed=seed + 1, events_per_3h=400.0, false_per_sta_min=2.0)
+        t0 = 200.0 + 3.0 * seed
+        trv_times = net.travel_times()
+        locs, grid = net.sta, net.grid
+        torch.manual_seed(seed)
+        mz = module.GCN_Detection_Network_extended(identity, identity, device='cpu')
+        mz.eval()
+        graph_params = [k_sta, k_spc, 1]
+        dummy_ptr = np.zeros(S_all, dtype='int')
+        out = pu.extract_inputs_adjacencies(None, locs, ind_use, grid, None, np.zeros(1), dummy_ptr, dummy_ptr,
+                                            identity, graph_params, device='cpu')
+        A_sta_sta, A_src_src, A_prod_sta, A_prod_src, A_src_in_prod = out[0:5]
+        A_src_in_sta = torch.Tensor(np.concatenate((np.tile(np.arange(S), G).reshape(1, -1),
+                                                    np.arange(G).repeat(S, axis=0).reshape(1, -1)), axis=0)).long()
+        attr_scale = np.array([net.width, net.width, 42000.0]).reshape(1, -1)
+        spatial_vals = torch.Tensor(((np.repeat(np.expand_dims(grid, axis=1), S, axis=1)
+                                      - np.repeat(np.expand_dims(locs[ind_use], axis=0), G, axis=0)).reshape(-1, 3))
+                                    / attr_scale)
+        A_src_in_edges = Data(x=spatial_vals, edge_index=A_src_in_prod)
+        A_Lg_in_src = Data(x=spatial_vals, edge_index=torch.Tensor(
+            np.ascontiguousarray(np.flip(A_src_in_prod.numpy(), axis=0))).long())     # process_continuous_days.py:632
+        tt_use = torch.Tensor(trv_times[:, ind_use, :])                              # [G, S, 2]
+
+        def trv_pairwise(sta_rows, src_rows):
+            # synthetic travel times of the (station, source) pairs; rows are in product-node order here
+            assert sta_rows.shape[0] == G * S
+            return tt_use.reshape(-1, 2)
+
+        A_edges_p, A_edges_s, dt_partition = pu.compute_time_embedding_vectors(
+            trv_pairwise, locs[ind_use], grid, A_src_in_sta, max_t, dt_res=sig / 5.0, t_win=sig * 2.0, device='cpu')
+        tlatent = tt_use.reshape(-1, 2)
+        locs_cart = torch.Tensor(locs[ind_use])
+        grid_cart = torch.Tensor(grid)
+        mz.set_adjacencies(A_prod_sta, A_prod_src, A_src_in_edges, A_Lg_in_src, A_src_in_sta, A_src_src,
+                           torch.Tensor(A_edges_p).long(), torch.Tensor(A_edges_s).long(), torch.Tensor(dt_partition),
+                           tlatent, locs_cart, grid_cart)
+        [Inpts, Masks], [lp_t, lp_s, lp_p, _] = pu.extract_input_from_data(
+            None, P, np.array([t0]), ind_use, locs, grid, A_src_in_sta.numpy(), trv_times=trv_times, max_t=max_t,
+            kernel_sig_t=sig, dt=dt, device='cpu')
+        Slice, Mask = Inpts[0], Masks[0]
+        x_query = np.stack((rng.uniform(0, net.width, Q), rng.uniform(0, net.width, Q),
+                            rng.uniform(-40000.0, 0.0, Q)), axis=1)
+        t_query = np.arange(-3.0, 3.0 + 0.75, 0.75)
+        # with the default nn.Linear init y is negative everywhere: shift the bias of the last projection so that the
+        # source mask (y.max > 0.01, module.py:983) is a genuine mixture of zeros and ones (weights only, code untouched)
+        y0, _ = mz.forward_fixed_source(Slice, Mask, torch.Tensor(lp_t[0]), torch.Tensor(lp_s[0]).long(),
+                                        torch.Tensor(lp_p[0].reshape(-1, 1)).float(), locs_cart, grid_cart,
+                                        torch.Tensor(x_query), torch.Tensor(t_query.reshape(-1, 1)))
+        sd0 = mz.state_dict()
+        gain = float(0.05 / y0[:, :, 0].max(1)[0].std())       # spread the per-node maxima to a standard deviation of 0.05
+        sd0['TemporalAttention.proj_2.weight'] *= gain
+        mz.load_state_dict(sd0)
+        y0, _ = mz.forward_fixed_source(Slice, Mask, torch.Tensor(lp_t[0]), torch.Tensor(lp_s[0]).long(),
+                                        torch.Tensor(lp_p[0].reshape(-1, 1)).float(), locs_cart, grid_cart,
+                                        torch.Tensor(x_query), torch.Tensor(t_query.reshape(-1, 1)))
+        ym = np.sort(y0[:, :, 0].max(1)[0].numpy())
+        lo, hi = int(0.3 * len(ym)), int(0.7 * len(ym))
+        j = lo + int(np.argmax(np.diff(ym[lo:hi])))           # widest gap near the median: the threshold goes in its middle
+        sd0['TemporalAttention.proj_2.bias'] += float(0.01 - 0.5 * (ym[j] + ym[j + 1]))
+        mz.load_state_dict(sd0)
+        # association queries: n_src sources at grid nodes (so their travel times are rows of trv_times), origin times
+        # relative to t0 inside and outside the 2*eps keep window of the null arrival (module.py:723-727)
+        isrc = rng.choice(G, size=n_src, replace=False)
+        x_query_src = grid[isrc]
+        tq_sample = np.linspace(0.0, 2.5 * module.eps, n_src)
+        trv_out_q = trv_times[isrc][:, ind_use, :]
+        store = _hook_outputs(mz)
+        extra = {}
+        for nm in ('BipartiteGraphReadOutOperator', 'DataAggregationAssociationPhase', 'LocalSliceLgCollapseP',
+                   'LocalSliceLgCollapseS', 'Arrivals'):
+            getattr(mz, nm).register_forward_hook(
+                (lambda key: (lambda _m, _i, o: extra.setdefault(key, o)))(nm))
+        y, x, arv_p, arv_s = mz.forward_fixed(
+            Slice, Mask, torch.Tensor(lp_t[0]), torch.Tensor(lp_s[0]).long(), torch.Tensor(lp_p[0].reshape(-1, 1)).long(),
+            locs_cart, grid_cart, torch.Tensor(x_query), torch.Tensor(x_query_src), torch.Tensor(t_query.reshape(-1, 1)),
+            torch.Tensor(tq_sample), torch.Tensor(trv_out_q))
+        res = dict(
+            A_sta_sta=A_sta_sta.numpy(), A_src_src=A_src_src.numpy(), read_in_attr=spatial_vals.numpy(),
+            Slice=Slice.numpy(), Mask=Mask.numpy(), A_edges_p=np.asarray(A_edges_p).astype('int64'),
+            A_edges_s=np.asarray(A_edges_s).astype('int64'), dt_partition=np.asarray(dt_partition, dtype='float64'),
+            tlatent=tlatent.numpy(), tpick=np.asarray(lp_t[0]), ipick=np.asarray(lp_s[0]).astype('int64'),
+            phase_label=np.asarray(lp_p[0]).astype('int64'), x_query=x_query, x_query_src=x_query_src,
+            t_query=t_query, tq_sample=tq_sample, trv_out_q=trv_out_q,
+            x_latent=store['DataAggregation'][0].numpy(), x_spatial=store['SpatialAggregation3'][0].numpy(),
+            y_latent=store['SpatialDirect'][0].numpy(), x_src=store['SpatialAttention'][1].numpy(),
+            assoc_s0=extra['BipartiteGraphReadOutOperator'][0].numpy(),
+            mask_out_1=extra['BipartiteGraphReadOutOperator'][1].numpy(),
+            assoc_s=extra['DataAggregationAssociationPhase'].numpy(),
+            arv_p_embed=extra['LocalSliceLgCollapseP'].numpy(), arv_s_embed=extra['LocalSliceLgCollapseS'].numpy(),
+            y=y.numpy(), x=x.numpy(), arv_p=arv_p.numpy(), arv_s=arv_s.numpy())
+        res.update(_pack(mz.state_dict()))
+        res.update(sta=locs, grid=grid, ind_use=ind_use, trv_times=trv_times, picks=P, t0=np.float64(t0),
+                   max_t=np.float64(max_t), kernel_sig_t=np.float64(sig), dt=np.float64(dt), k_sta=np.int64(k_sta),
+                   k_spc=np.int64(k_spc), scale_rel=np.float64(module.scale_rel), scale_t=np.float64(module.scale_t),
+                   eps=np.float64(module.eps), attr_scale=attr_scale)
+        np.savez_compressed(os.path.join(GOLD, name + '.npz'), **res)
+        print(name, 'P=%d picks=%d mask_out.mean=%.3f margin=%.2e s.abs=%.6f arv_p.abs=%.6f arv_s.abs=%.6f y.max=%.6f' % (
+            Slice.shape[0], len(lp_t[0]), float(res['mask_out_1'].mean()),
+            float(np.abs(res['y'][:, :, 0].max(1) - 0.01).min()), np.abs(res['assoc_s']).sum(),
+            np.abs(res['arv_p']).sum(), np.abs(res['arv_s']).sum(), res['y'].max()))
+
+
 if __name__ == '__main__':
     mode = sys.argv[1] if len(sys.argv) > 1 else 'synthetic'
     if mode == 'synthetic':
@@ -202,6 +327,8 @@ if __name__ == '__main__':
         synthetic(edges=True)
     elif mode == 'legacy_input':
         legacy_input()
+    elif mode == 'association':
+        association()
     elif mode == 'ferndale':
         from gen_golden_ferndale import ferndale
         ferndale()

@@ -455,3 +455,194 @@ def init_state(seed=2, scale=1.0, edges=False):
     for a in ('activate1', 'activate2', 'activate3', 'activate4', 'activate5'):
         prelu(p + a)
     return sd
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# association branch: module.py:333-352, 356-403, 604-653, 656-781, 963-997
+# --------------------------------------------------------------------------------------------------------------------
+
+
+def bipartite_read_out(sd, pre, y_latent, edge_attr, edge_index, mask_out):
+    """BipartiteGraphReadOutOperator, module.py:333-352: messages grid node -> product node (`A_Lg_in_src`, edge_index =
+    [g(i); i], process_continuous_days.py:632), aggr='add', mask_j = source-prediction mask of the grid node.  Returns
+    (s [P,15], mask_out_1 [E,1] = mask_out[edge_index[0]])."""
+    M = int(edge_index[1].max()) + 1
+    xj = y_latent.index_select(0, edge_index[0])
+    mj = mask_out.index_select(0, edge_index[0])
+    msg = mj * _prelu(sd, pre + 'activate1', _lin(sd, pre + 'fc1', torch.cat((xj, edge_attr), dim=-1)))
+    out = _prelu(sd, pre + 'activate2', _lin(sd, pre + 'fc2', propagate_sum(msg, edge_index[1], M)))
+    return out, mj
+
+
+def data_aggregation_association(sd, pre, s, x_latent, mask1, mask2, A_in_sta, A_in_src, return_parts=False):
+    """DataAggregationAssociationPhase.forward, module.py:387-403 (`use_updated_model_definition: False`).  Unlike
+    DataAggregation, the layer-1 messages pass through l1_t*_1 first and the mask has five channels."""
+    n = s.shape[0]
+    mask = torch.cat((mask1, mask2), dim=-1)
+    tr = _prelu(sd, pre + 'activate', _lin(sd, pre + 'init_trns', torch.cat((s, x_latent, mask), dim=-1)))
+
+    def agg(x, A):
+        return propagate_mean(x.index_select(0, A[0]), A[1], n)
+
+    a1 = _prelu(sd, pre + 'activate11', _lin(sd, pre + 'l1_t1_1', tr))
+    a2 = _prelu(sd, pre + 'activate12', _lin(sd, pre + 'l1_t2_1', tr))
+    tr1 = _lin(sd, pre + 'l1_t1_2', torch.cat((tr, agg(a1, A_in_sta), mask), dim=1))
+    tr2 = _lin(sd, pre + 'l1_t2_2', torch.cat((tr, agg(a2, A_in_src), mask), dim=1))
+    trb = _prelu(sd, pre + 'activate1', torch.cat((tr1, tr2), dim=1))
+    b1 = _prelu(sd, pre + 'activate21', _lin(sd, pre + 'l2_t1_1', trb))
+    b2 = _prelu(sd, pre + 'activate22', _lin(sd, pre + 'l2_t2_1', trb))
+    o1 = _lin(sd, pre + 'l2_t1_2', torch.cat((trb, agg(b1, A_in_sta), mask), dim=1))
+    o2 = _lin(sd, pre + 'l2_t2_2', torch.cat((trb, agg(b2, A_in_src), mask), dim=1))
+    out = _prelu(sd, pre + 'activate2', torch.cat((o1, o2), dim=1))
+    if return_parts:
+        return out, dict(assoc_tr0=tr, assoc_tr1=trb)
+    return out
+
+
+def local_slice_collapse(sd, pre, A_edges, dt_partition, tpick, ipick, phase_label, inpt, tlatent, eps,
+                         use_phase_types=True, k_infer=10):
+    """LocalSliceLgCollapse.forward/message, module.py:617-653: every pick selects the k_infer product nodes its
+    (station, time bin) row of the pointer table names, keeps those whose theoretical time is within 2*eps, and averages
+    PReLU(fc1([s_j ‖ (t_pick - t_j)/eps ‖ phase])) over them."""
+    n_arv, l_dt = tpick.shape[0], dt_partition.shape[0]
+    dt = dt_partition[1] - dt_partition[0]
+    ph = phase_label.float() if use_phase_types else phase_label.float() * 0.0
+    t_index = torch.floor((tpick - dt_partition[0]) / dt).long()                                              # :630
+    t_index = ((ipick * l_dt * k_infer + t_index * k_infer).view(-1, 1) + torch.arange(k_infer).view(1, -1)).reshape(-1)
+    src_index = torch.arange(n_arv).view(-1, 1).repeat(1, k_infer).view(-1)
+    e0 = A_edges[t_index].long()
+    t_rel = tpick[src_index] - tlatent[e0, 0]                                                                 # :637
+    keep = torch.where(t_rel.abs() < 2.0 * eps)[0]
+    e0, e1 = e0[keep], src_index[keep]
+    msg = torch.cat((inpt.index_select(0, e0), (tpick.view(-1, 1)[e1] - tlatent[e0]) / eps, ph[e1]), dim=-1)
+    msg = _prelu(sd, pre + 'activate1', _lin(sd, pre + 'fc1', msg))
+    return _prelu(sd, pre + 'activate2', _lin(sd, pre + 'fc2', propagate_mean(msg, e1, n_arv)))
+
+
+def arrival_edges(ipick, n_arv):
+    """module.py:714: for every pick a (target) all picks b on the same station plus the null arrival n_arv (sources),
+    in the reference's order (stations ascending; itertools.product(list, list + [null])).  Returns [2,E]: row 0 = b, row 1 = a.
+    The per-station lists come from cKDTree.query_ball_point(r=0) in the reference; SORTED here — the edge order only
+    permutes the terms of the per-target sums."""
+    ip = ipick.numpy()
+    src, dst = [], []
+    for u in np.unique(ip):
+        lst = np.where(ip == u)[0]
+        ext = np.concatenate((lst, np.array([n_arv])))
+        dst.append(np.repeat(lst, len(ext)))
+        src.append(np.tile(ext, len(lst)))
+    if not src:
+        return torch.zeros(2, 0, dtype=torch.long)
+    return torch.from_numpy(np.stack((np.concatenate(src), np.concatenate(dst)))).long()
+
+
+def station_source_attention(sd, pre, stime, src_embed, trv_src, arrival_p, arrival_s, tpick, ipick, phase_label, eps,
+                             use_phase_types=True, n_heads=3, n_latent=15):
+    """StationSourceAttentionMergedPhases.forward/message, module.py:698-781 (use_neighbor_assoc_edges False)."""
+    n_src, n_sta, n_arv = trv_src.shape[0], trv_src.shape[1], tpick.shape[0]
+    ph = phase_label.float() if use_phase_types else phase_label.float() * 0.0
+    arrival = torch.cat((torch.cat((arrival_p, torch.zeros(1, arrival_p.shape[1])), dim=0),
+                         torch.cat((arrival_s, torch.zeros(1, arrival_s.shape[1])), dim=0)), dim=1)           # :709-711
+    edges = arrival_edges(ipick, n_arv)
+    n_edge = edges.shape[1]
+    e0 = edges[0].repeat(n_src)                                                                               # :718
+    e1 = edges[1].repeat(n_src) + (torch.arange(n_src) * n_arv).repeat_interleave(n_edge)
+    sindex = torch.arange(n_src).repeat_interleave(n_edge)
+    atime = torch.cat((tpick, torch.tensor([-eps], dtype=tpick.dtype)))
+    stindex = torch.cat((ipick, torch.tensor([n_sta], dtype=torch.long)))
+    tsrc_p = torch.cat((trv_src[:, :, 0], -eps * torch.ones(n_src, 1)), dim=1)
+    tsrc_s = torch.cat((trv_src[:, :, 1], -eps * torch.ones(n_src, 1)), dim=1)
+    phase = torch.cat((ph, torch.tensor([[-1.0]])), dim=0)
+    t_kernel_sq = torch.tensor([eps], dtype=torch.float32) ** 2
+    rel_p = (atime[e0] - (tsrc_p[sindex, stindex[e0]] + stime[sindex])).reshape(-1, 1)
+    rel_s = (atime[e0] - (tsrc_s[sindex, stindex[e0]] + stime[sindex])).reshape(-1, 1)
+    thr = 2.0 * torch.sqrt(t_kernel_sq)
+    keep = torch.where((((rel_p.abs() < thr) + (rel_s.abs() < thr)).reshape(-1)) > 0)[0]                      # :727
+    e0, e1, sindex, rel_p, rel_s = e0[keep], e1[keep], sindex[keep], rel_p[keep], rel_s[keep]
+    M = n_arv * n_src
+    if e0.numel() > 0:
+        # message (:746-781); `edge_index[0].max()` is taken over the KEPT edges, as in the reference
+        e0max = int(e0.max())
+        f_p = torch.cat((torch.exp(-0.5 * (rel_p ** 2) / t_kernel_sq), torch.sign(rel_p), phase[e0]), dim=1)
+        f_s = torch.cat((torch.exp(-0.5 * (rel_s ** 2) / t_kernel_sq), torch.sign(rel_s), phase[e0]), dim=1)
+        self_link = (e0 == torch.remainder(e1, e0max)).reshape(-1, 1).float()                                # :762
+        null_link = (e0 == e0max).reshape(-1, 1).float()
+        xj = arrival.index_select(0, e0)
+        ctx = _lin(sd, pre + 'f_src_context_2', _prelu(sd, pre + 'activate1', _lin(sd, pre + 'f_src_context_1', torch.cat(
+            (src_embed[sindex], stime[sindex].reshape(-1, 1), self_link, null_link), dim=1)))).view(-1, n_heads, n_latent)
+        qry = _lin(sd, pre + 'f_arrival_query_2', _prelu(sd, pre + 'activate2', _lin(sd, pre + 'f_arrival_query_1', torch.cat(
+            (xj, f_p, f_s), dim=1)))).view(-1, n_heads, n_latent)
+        val = _lin(sd, pre + 'f_values_2', _prelu(sd, pre + 'activate3', _lin(sd, pre + 'f_values_1', torch.cat(
+            (xj, f_p, f_s, self_link, null_link), dim=1)))).view(-1, n_heads, n_latent)
+        scores = (qry * ctx).sum(-1) / math.sqrt(n_latent)
+        alpha = segment_softmax(scores, e1, M)
+        agg = propagate_sum(alpha.unsqueeze(-1) * val, e1, M)
+    else:
+        agg = torch.zeros(M, n_heads, n_latent)
+    out = _lin(sd, pre + 'proj_2', _prelu(sd, pre + 'activate4', _lin(sd, pre + 'proj_1', agg.mean(1))))     # :742
+    return out.view(n_src, n_arv, -1)
+
+
+def forward_fixed(sd, Slice, Mask, A_in_sta, A_in_src, read_in_attr, read_in_index, A_src, grid_cart, A_edges_p,
+                  A_edges_s, dt_partition, tlatent, tpick, ipick, phase_label, x_query_cart, x_query_src_cart, t_query,
+                  tq_sample, trv_out_q, scale_rel, scale_t, eps, return_parts=False, query_edges=None,
+                  query_src_edges=None):
+    """module.py:963-997 (= forward, :908-939, with the adjacencies passed per call): returns y, x, arv_p, arv_s."""
+    x_spatial, parts = front_end(sd, Slice, Mask, A_in_sta, A_in_src, read_in_attr, read_in_index, A_src, grid_cart,
+                                 scale_rel, return_parts=True)
+    x_latent = parts['x_latent']
+    y_latent = spatial_direct(sd, 'SpatialDirect.', x_spatial)
+    y = temporal_attention(sd, 'TemporalAttention.', y_latent, t_query, scale_t)
+    xq = spatial_attention(sd, 'SpatialAttention.', x_spatial, x_query_cart, grid_cart, scale_rel, edge_index=query_edges)
+    x_src = spatial_attention(sd, 'SpatialAttention.', x_spatial, x_query_src_cart, grid_cart, scale_rel,
+                              edge_index=query_src_edges)
+    x = temporal_attention(sd, 'TemporalAttention.', xq, t_query, scale_t)
+    mask_out = 1.0 * (y[:, :, 0].max(1, keepdim=True)[0] > 0.01)                                              # :983
+    A_Lg = torch.stack((read_in_index[1], read_in_index[0]))                     # process_continuous_days.py:632
+    s0, mask_out_1 = bipartite_read_out(sd, 'BipartiteGraphReadOutOperator.', y_latent, read_in_attr, A_Lg, mask_out)
+    s = data_aggregation_association(sd, 'DataAggregationAssociationPhase.', s0, x_latent, mask_out_1, Mask, A_in_sta,
+                                     A_in_src)
+    arv_p = local_slice_collapse(sd, 'LocalSliceLgCollapseP.', A_edges_p, dt_partition, tpick, ipick, phase_label, s,
+                                 tlatent[:, 0].reshape(-1, 1), eps)
+    arv_s = local_slice_collapse(sd, 'LocalSliceLgCollapseS.', A_edges_s, dt_partition, tpick, ipick, phase_label, s,
+                                 tlatent[:, 1].reshape(-1, 1), eps)
+    arv = station_source_attention(sd, 'Arrivals.', tq_sample, x_src, trv_out_q, arv_p, arv_s, tpick, ipick,
+                                   phase_label, eps)
+    out = (y, x, arv[:, :, 0].unsqueeze(-1), arv[:, :, 1].unsqueeze(-1))
+    if return_parts:
+        parts.update(x_spatial=x_spatial, y_latent=y_latent, x_src=x_src, mask_out=mask_out, assoc_s0=s0, assoc_s=s,
+                     arv_p_embed=arv_p, arv_s_embed=arv_s)
+        return out + (parts,)
+    return out
+
+
+def init_state_association(sd, seed=7, scale=1.0):
+    """Adds seeded weights for the association modules (module.py:900-904) to a state made by init_state."""
+    g = torch.Generator().manual_seed(seed)
+
+    def lin(name, n_in, n_out):
+        bound = scale / math.sqrt(n_in)
+        sd[name + '.weight'] = (torch.rand(n_out, n_in, generator=g) * 2 - 1) * bound
+        sd[name + '.bias'] = (torch.rand(n_out, generator=g) * 2 - 1) * bound
+
+    def prelu(name):
+        sd[name + '.weight'] = torch.full((1,), 0.25) + 0.1 * (torch.rand(1, generator=g) - 0.5)
+
+    p = 'BipartiteGraphReadOutOperator.'
+    lin(p + 'fc1', 33, 30); lin(p + 'fc2', 30, 15); prelu(p + 'activate1'); prelu(p + 'activate2')
+    p = 'DataAggregationAssociationPhase.'
+    lin(p + 'init_trns', 50, 30); lin(p + 'l1_t1_1', 30, 30); lin(p + 'l1_t1_2', 65, 30)
+    lin(p + 'l1_t2_1', 30, 30); lin(p + 'l1_t2_2', 65, 30); lin(p + 'l2_t1_1', 60, 30); lin(p + 'l2_t1_2', 95, 15)
+    lin(p + 'l2_t2_1', 60, 30); lin(p + 'l2_t2_2', 95, 15)
+    for a in ('activate', 'activate11', 'activate12', 'activate1', 'activate21', 'activate22', 'activate2'):
+        prelu(p + a)
+    for p in ('LocalSliceLgCollapseP.', 'LocalSliceLgCollapseS.'):
+        lin(p + 'fc1', 32, 30); lin(p + 'fc2', 30, 15); prelu(p + 'activate1'); prelu(p + 'activate2')
+    p = 'Arrivals.'
+    lin(p + 'f_arrival_query_1', 36, 30); lin(p + 'f_arrival_query_2', 30, 45)
+    lin(p + 'f_src_context_1', 33, 30); lin(p + 'f_src_context_2', 30, 45)
+    lin(p + 'f_values_1', 38, 30); lin(p + 'f_values_2', 30, 45)
+    lin(p + 'proj_1', 15, 30); lin(p + 'proj_2', 30, 2)
+    for a in ('activate1', 'activate2', 'activate3', 'activate4'):
+        prelu(p + a)
+    return sd

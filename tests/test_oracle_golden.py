@@ -121,3 +121,37 @@ def test_ferndale_known_answers():
     assert abs(float(d['read_in'].astype(np.float64).sum()) - 901.758727) < 1e-2
     assert abs(float(d['x_spatial'].max()) - 7.177079) < 1e-5
     assert abs(float(d['y'].max()) - 0.946654) < 1e-5
+
+
+ASSOC = ['assoc_10x100', 'assoc_18of20x160']
+
+
+def assoc_inputs(d):
+    """Tensors of an association fixture in the order oracle.forward_fixed takes them (after the graphs)."""
+    t = torch.from_numpy
+    return dict(A_edges_p=t(d['A_edges_p']), A_edges_s=t(d['A_edges_s']), dt_partition=t(d['dt_partition']).float(),
+                tlatent=t(d['tlatent']).float(), tpick=t(d['tpick']).float(), ipick=t(d['ipick']).long(),
+                phase_label=t(d['phase_label']).long().reshape(-1, 1), x_query_cart=t(d['x_query']).float(),
+                x_query_src_cart=t(d['x_query_src']).float(), t_query=t(d['t_query']).float().reshape(-1, 1),
+                tq_sample=t(d['tq_sample']).float(), trv_out_q=t(d['trv_out_q']).float())
+
+
+@pytest.mark.parametrize('name', ASSOC)
+def test_association_branch_matches_reference(name):
+    """forward_fixed (module.py:963-997) incl. BipartiteGraphReadOutOperator, DataAggregationAssociationPhase,
+    LocalSliceLgCollapse{P,S} and Arrivals against the unmodified reference."""
+    d, sd = load_golden(name)
+    S, G, A_sta, A_src, A_ps, A_pg, A_sip, A_sis = _graphs(d)
+    Slice, Mask = torch.from_numpy(d['Slice']), torch.from_numpy(d['Mask'])
+    kw = assoc_inputs(d)
+    y, x, arv_p, arv_s, parts = go.forward_fixed(
+        sd, Slice, Mask, A_ps, A_pg, torch.from_numpy(d['read_in_attr']), A_sip, A_src,
+        torch.from_numpy(d['grid']).float(), scale_rel=float(d['scale_rel']), scale_t=float(d['scale_t']),
+        eps=float(d['eps']), return_parts=True, **kw)
+    assert np.array_equal(parts['mask_out'].numpy()[A_sip[1].numpy()], d['mask_out_1'])
+    assert 0.2 < d['mask_out_1'].mean() < 0.8            # the fixture exercises both mask values
+    for key in ('x_latent', 'x_spatial', 'y_latent', 'x_src', 'assoc_s0', 'assoc_s', 'arv_p_embed', 'arv_s_embed'):
+        assert rel_err(parts[key].numpy(), d[key]) < 5e-6, key
+    assert rel_err(y.numpy(), d['y']) < 5e-6 and rel_err(x.numpy(), d['x']) < 5e-6
+    assert rel_err(arv_p.numpy(), d['arv_p']) < 5e-6 and rel_err(arv_s.numpy(), d['arv_s']) < 5e-6
+    assert arv_p.shape == (len(d['tq_sample']), len(d['tpick']), 1)
