@@ -17,7 +17,7 @@ _LIB_PATH = os.path.join(_HERE, 'libgenie_b200.so')
 _lib = None
 
 GRAPH_CARTESIAN, GRAPH_EXPLICIT = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 EDGE_TERM_LD = 48           # GENIE_EDGE_TERM_LD
 
 c_f32p = ctypes.c_void_p   # device pointers are passed as opaque addresses
@@ -96,6 +96,14 @@ SIGNATURES = {
     'genie_heads_grid_fwd': (ctypes.c_int, [_P, _P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int, _P, _P]),
     'genie_heads_query_fwd': (ctypes.c_int, [_P, _P, ctypes.c_int, _P, ctypes.c_int, _P, _P, _P, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_float, _P, _P]),
+    'genie_assoc_packed_floats': (ctypes.c_size_t, []),
+    'genie_assoc_layout': (ctypes.c_int, [_P, ctypes.c_int]),
+    'genie_assoc_workspace_bytes': (ctypes.c_size_t, [_P]),
+    'genie_assoc_product_fwd': (ctypes.c_int, [_P, _P, _P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_float, _P, _P, _P, _P,
+                                               _P, _P, ctypes.POINTER(ctypes.c_void_p), _P]),
+    'genie_assoc_collapse_fwd': (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, _P, ctypes.c_int64, _P, _P, _P, _P,
+                                                ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                                ctypes.c_float, ctypes.c_float, _P, _P]),
     'genie_input_nearest_fwd': (ctypes.c_int, [ctypes.POINTER(NearestParams), _P, _P, _P, _P, _P, _P, _P, _P]),
     'genie_input_scatter_fwd': (ctypes.c_int, [_P, ctypes.POINTER(InputParams), _P, ctypes.c_int64, _P, _P, _P, _P, _P,
                                                _P, _P, _P, _P, _P]),

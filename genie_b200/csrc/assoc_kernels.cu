@@ -1,0 +1,496 @@
+// Association branch of forward / forward_fixed (module.py:983-991): the product-node-sized part.
+//
+//   mask_out = (max_t y[g,t] > 0.01)                                                            module.py:983
+//   s0  = BipartiteGraphReadOutOperator(SpatialDirect(x_spatial), A_Lg_in_src, mask_out)        module.py:333-352
+//   s   = DataAggregationAssociationPhase(s0, x_latent, mask_out[g(i)], Mask, A_in_sta, A_in_src)   module.py:356-403
+//   arv = LocalSliceLgCollapse{P,S}(A_edges_{p,s}, dt_partition, tpick, ipick, phase, s, tlatent)   module.py:604-653
+//
+// Five kernels, split at the global dependencies:
+//   assoc_grid_pre_kernel   per grid node: y_latent = SpatialDirect(x_spatial), the y_latent half of the read-out fc1
+//                           (every product node of a grid node shares it) and the source mask
+//   assoc_init_kernel       per product node (thread per node, weights broadcast from shared memory): read-out MLP ->
+//                           init_trns (50 -> 30) -> the two layer-1 message maps l1_t1_1 / l1_t2_1 (unlike DataAggregation,
+//                           the association phase DOES use them, module.py:394-395)
+//   assoc_layer1_kernel     gather the two means -> l1_t*_2 -> l2_t*_1 -> the layer-2 linear maps split by linearity exactly as
+//                           in da_kernels.cu (15-wide messages va / vb, node-local part zc)
+//   assoc_layer2_kernel     gather va / vb means, add zc, PReLU -> s rows [o1(15) 0 | o2(15) 0]
+//   assoc_collapse_kernel   one warp per (pick, phase): the k_infer = 10 product nodes the pointer table names, kept when their
+//                           theoretical time is within 2 eps, PReLU(fc1 [s_j | dt/eps | phase]) averaged, fc2 -> arrival rows
+// Layout of the packed weights: AS_* below, reported to the host by genie_assoc_layout (packed in genie_b200/ops.py).
+#include "common.cuh"
+#include "gather.cuh"
+
+using namespace gl;
+
+namespace as {
+// every matrix K-major [n_in][ld]
+constexpr int SD_W = 0;                        // SpatialDirect.f_direct                         [30][32]
+constexpr int SD_B = SD_W + 30 * 32;           //                                                [32]
+constexpr int RO_WY = SD_B + 32;               // read-out fc1[:, 0:30]  (y_latent)              [30][32]
+constexpr int RO_B1 = RO_WY + 30 * 32;         //                                                [32]
+constexpr int RO_WA = RO_B1 + 32;              // read-out fc1[:, 30:33] (edge attr)             [4][32] (3 used)
+constexpr int RO_W2 = RO_WA + 4 * 32;          // read-out fc2                                   [30][16]
+constexpr int RO_B2 = RO_W2 + 30 * 16;         //                                                [16]
+constexpr int AI_W = RO_B2 + 16;               // init_trns: rows 0-14 s0, 15-44 x_latent, 45 mask_out, 46-49 Mask   [52][32] (50 used)
+constexpr int AI_B = AI_W + 52 * 32;
+constexpr int M11_W = AI_B + 32;               // l1_t1_1                                        [30][32]
+constexpr int M11_B = M11_W + 30 * 32;
+constexpr int M12_W = M11_B + 32;              // l1_t2_1                                        [30][32]
+constexpr int M12_B = M12_W + 30 * 32;
+constexpr int INIT_END = M12_B + 32;
+// ---- layer-1 block (copied to shared memory as one piece) ----
+constexpr int W11 = INIT_END;                  // l1_t1_2: rows 0-29 tr, 30-59 mean_sta, 60-64 mask5   [68][32] (65 used)
+constexpr int W12 = W11 + 68 * 32;             // l1_t2_2
+constexpr int B11 = W12 + 68 * 32;
+constexpr int B12 = B11 + 32;
+constexpr int W21A = B12 + 32;                 // l2_t1_1                                        [60][32]
+constexpr int W22A = W21A + 60 * 32;           // l2_t2_1
+constexpr int B21A = W22A + 60 * 32;
+constexpr int B22A = B21A + 32;
+constexpr int WVA = B22A + 32;                 // l2_t1_2[:, 60:90]                              [30][16]
+constexpr int WVB = WVA + 30 * 16;             // l2_t2_2[:, 60:90]
+constexpr int WCA = WVB + 30 * 16;             // l2_t1_2[:, 0:60 | 90:95]: rows 0-59 tr, 60-64 mask5   [68][16] (65 used)
+constexpr int WCB = WCA + 68 * 16;
+constexpr int BCA = WCB + 68 * 16;
+constexpr int BCB = BCA + 16;
+constexpr int L1_END = BCB + 16;
+// ---- LocalSliceLgCollapse P / S ----
+constexpr int CP_W1 = L1_END;                  // fc1: rows 0-29 s_j, 30 (t_pick - t_j)/eps, 31 phase  [32][32]
+constexpr int CP_B1 = CP_W1 + 32 * 32;
+constexpr int CP_W2 = CP_B1 + 32;              // fc2                                            [30][16]
+constexpr int CP_B2 = CP_W2 + 30 * 16;
+constexpr int CS_W1 = CP_B2 + 16;
+constexpr int CS_B1 = CS_W1 + 32 * 32;
+constexpr int CS_W2 = CS_B1 + 32;
+constexpr int CS_B2 = CS_W2 + 30 * 16;
+constexpr int C_SIZE = CS_W1 - CP_W1;
+constexpr int SL = CS_B2 + 16;                 // slopes [16], see enum
+constexpr int FLOATS = SL + 16;
+enum { SL_SD = 0, SL_RO1, SL_RO2, SL_A, SL_A11, SL_A12, SL_A1, SL_A21, SL_A22, SL_A2, SL_CP1, SL_CP2, SL_CS1, SL_CS2 };
+static_assert(W11 % 4 == 0 && WVA % 4 == 0 && WCA % 4 == 0 && CP_W1 % 4 == 0 && SL % 4 == 0 && RO_W2 % 4 == 0, "alignment");
+
+constexpr int LD_S = 32;                       // s rows: [o1(15) 0 | o2(15) 0]
+}  // namespace as
+
+namespace {
+
+constexpr int TM = 128;
+constexpr int LDF = TM + 1;
+
+// --------------------------------------------------------------------------------------------------------------------
+// per grid node
+// --------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) assoc_grid_pre_kernel(const float* __restrict__ packed, const float* __restrict__ x_spatial,
+                                                             int ld_x, const float* __restrict__ y, int T, int G,
+                                                             float thresh, float* __restrict__ yfc1,
+                                                             float* __restrict__ mask_out) {
+    __shared__ __align__(16) float sW[as::RO_WA];    // SD_W .. RO_B1
+    for (int i = threadIdx.x; i < as::RO_WA; i += 128) sW[i] = packed[i];
+    const float a_sd = packed[as::SL + as::SL_SD];
+    __syncthreads();
+    const int g = blockIdx.x * 128 + threadIdx.x;
+    if (g >= G) return;
+    float yl[30];
+#pragma unroll
+    for (int o = 0; o < 30; ++o) yl[o] = sW[as::SD_B + o];
+    for (int k = 0; k < 30; ++k) fma_row30(yl, x_spatial[(int64_t)g * ld_x + k], sW + as::SD_W + k * 32);
+    float acc[30];
+#pragma unroll
+    for (int o = 0; o < 30; ++o) acc[o] = sW[as::RO_B1 + o];
+#pragma unroll
+    for (int k = 0; k < 30; ++k) fma_row30(acc, prelu(yl[k], a_sd), sW + as::RO_WY + k * 32);
+#pragma unroll
+    for (int o = 0; o < 30; ++o) yfc1[(int64_t)g * 32 + o] = acc[o];
+    yfc1[(int64_t)g * 32 + 30] = 0.f;
+    yfc1[(int64_t)g * 32 + 31] = 0.f;
+    float m = -INFINITY;
+    for (int t = 0; t < T; ++t) m = fmaxf(m, y[(int64_t)g * T + t]);
+    mask_out[g] = (T > 0 && m > thresh) ? 1.f : 0.f;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// per product node: read-out MLP -> init_trns -> layer-1 message maps
+// --------------------------------------------------------------------------------------------------------------------
+constexpr int K0_THREADS = 128;
+constexpr int K0_W0 = as::RO_WA;                       // first packed float staged in shared memory
+constexpr int K0_W_FLOATS = as::INIT_END - K0_W0;
+constexpr size_t K0_SMEM = (size_t)K0_W_FLOATS * sizeof(float);
+
+__device__ __forceinline__ void store_row32(float* __restrict__ dst, const float (&v)[30]) {
+    float4* d = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int c = 0; c < 7; ++c) d[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    d[7] = make_float4(v[28], v[29], 0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(K0_THREADS)
+    assoc_init_kernel(const GraphView gv, const float* __restrict__ packed, const float* __restrict__ yfc1,
+                      const float* __restrict__ mask_out, const float* __restrict__ edge_attr,
+                      const float* __restrict__ x_latent, const float* __restrict__ mask, float* __restrict__ s0_out,
+                      float* __restrict__ tr_out, float* __restrict__ a1_out, float* __restrict__ a2_out) {
+    extern __shared__ __align__(16) float sW0[];
+    for (int i = threadIdx.x; i < K0_W_FLOATS; i += K0_THREADS) sW0[i] = packed[K0_W0 + i];
+    const float a_ro1 = packed[as::SL + as::SL_RO1], a_ro2 = packed[as::SL + as::SL_RO2];
+    const float a_in = packed[as::SL + as::SL_A], a11 = packed[as::SL + as::SL_A11], a12 = packed[as::SL + as::SL_A12];
+    __syncthreads();
+    const float* sW = sW0 - K0_W0;                     // index with the packed offsets
+    const int64_t i = (int64_t)blockIdx.x * K0_THREADS + threadIdx.x;
+    if (i >= gv.P) return;
+    const int g = node_grid(gv, i);
+    const float mo = mask_out[g];
+    float tr[30];
+    {
+        // read-out: s0 = PReLU(fc2(mask_j * PReLU(fc1 [y_latent_g | attr_i])))       (module.py:346, 350-352)
+        float h[30];
+        const float4* yr = reinterpret_cast<const float4*>(yfc1 + (int64_t)g * 32);
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            const float4 v = __ldg(yr + c);
+            h[4 * c] = v.x; h[4 * c + 1] = v.y; h[4 * c + 2] = v.z; h[4 * c + 3] = v.w;
+        }
+        {
+            const float4 v = __ldg(yr + 7);
+            h[28] = v.x; h[29] = v.y;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) fma_row30(h, edge_attr[i * 3 + k], sW + as::RO_WA + k * 32);
+        float s[16];
+#pragma unroll
+        for (int o = 0; o < 16; ++o) s[o] = sW[as::RO_B2 + o];
+#pragma unroll
+        for (int k = 0; k < 30; ++k) fma_row16(s, mo * prelu(h[k], a_ro1), sW + as::RO_W2 + k * 16);
+#pragma unroll
+        for (int o = 0; o < 15; ++o) s[o] = prelu(s[o], a_ro2);
+        if (s0_out != nullptr) {
+#pragma unroll
+            for (int o = 0; o < 15; ++o) s0_out[i * 15 + o] = s[o];
+        }
+        // init_trns [s0 | x_latent | mask_out | Mask]                                (module.py:389-391)
+#pragma unroll
+        for (int o = 0; o < 30; ++o) tr[o] = sW[as::AI_B + o];
+#pragma unroll
+        for (int k = 0; k < 15; ++k) fma_row30(tr, s[k], sW + as::AI_W + k * 32);
+        const float2* xl = reinterpret_cast<const float2*>(x_latent + i * 30);
+#pragma unroll 5
+        for (int k = 0; k < 15; ++k) {
+            const float2 v = __ldg(xl + k);
+            fma_row30(tr, v.x, sW + as::AI_W + (15 + 2 * k) * 32);
+            fma_row30(tr, v.y, sW + as::AI_W + (16 + 2 * k) * 32);
+        }
+        fma_row30(tr, mo, sW + as::AI_W + 45 * 32);
+        const float4 mv = __ldg(reinterpret_cast<const float4*>(mask) + i);
+        fma_row30(tr, mv.x, sW + as::AI_W + 46 * 32);
+        fma_row30(tr, mv.y, sW + as::AI_W + 47 * 32);
+        fma_row30(tr, mv.z, sW + as::AI_W + 48 * 32);
+        fma_row30(tr, mv.w, sW + as::AI_W + 49 * 32);
+#pragma unroll
+        for (int o = 0; o < 30; ++o) tr[o] = prelu(tr[o], a_in);
+    }
+    store_row32(tr_out + i * 32, tr);
+    {
+        float m[30];
+#pragma unroll
+        for (int o = 0; o < 30; ++o) m[o] = sW[as::M11_B + o];
+#pragma unroll
+        for (int k = 0; k < 30; ++k) fma_row30(m, tr[k], sW + as::M11_W + k * 32);
+#pragma unroll
+        for (int o = 0; o < 30; ++o) m[o] = prelu(m[o], a11);
+        store_row32(a1_out + i * 32, m);
+    }
+    {
+        float m[30];
+#pragma unroll
+        for (int o = 0; o < 30; ++o) m[o] = sW[as::M12_B + o];
+#pragma unroll
+        for (int k = 0; k < 30; ++k) fma_row30(m, tr[k], sW + as::M12_W + k * 32);
+#pragma unroll
+        for (int o = 0; o < 30; ++o) m[o] = prelu(m[o], a12);
+        store_row32(a2_out + i * 32, m);
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// layer 1 (+ the node-local part of layer 2); the structure of da_layer1_kernel with five mask channels
+// --------------------------------------------------------------------------------------------------------------------
+constexpr int K2_THREADS = 256;
+constexpr int K2_W_FLOATS = as::L1_END - as::W11;
+constexpr int K2_F_ROWS = 95;   // 0-29 tr | 30-59 mean_sta | 60-89 mean_src | 90-94 mask5 ; rows 0-59 later hold the new tr
+constexpr size_t K2_SMEM = (size_t)(K2_W_FLOATS + K2_F_ROWS * LDF) * sizeof(float);
+
+__global__ void __launch_bounds__(K2_THREADS, 2)
+    assoc_layer1_kernel(const GraphView gv, const float* __restrict__ packed, const float* __restrict__ tr_in,
+                        const float* __restrict__ a1, const float* __restrict__ a2, const float* __restrict__ mask_out,
+                        const float* __restrict__ mask, float* __restrict__ zc, float* __restrict__ va,
+                        float* __restrict__ vb, int64_t n_tiles) {
+    extern __shared__ __align__(16) float smem[];
+    float* sW0 = smem;
+    float* F = smem + K2_W_FLOATS;
+    {
+        const float4* src = reinterpret_cast<const float4*>(packed + as::W11);
+        float4* dst = reinterpret_cast<float4*>(sW0);
+        for (int i = threadIdx.x; i < K2_W_FLOATS / 4; i += K2_THREADS) dst[i] = src[i];
+    }
+    const float s_a1 = packed[as::SL + as::SL_A1], s_a21 = packed[as::SL + as::SL_A21], s_a22 = packed[as::SL + as::SL_A22];
+    __syncthreads();
+    const float* sW = sW0 - as::W11;                   // index with the packed offsets
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = threadIdx.x & (TM - 1);
+    const int br = threadIdx.x >> 7;   // 0: station-edge branch (l*_t1_*), 1: source-edge branch (l*_t2_*)
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t i0 = tile * TM;
+        // ---- stage A: gather ------------------------------------------------------------------------------------------
+        for (int m = warp; m < TM; m += K2_THREADS / 32) {
+            const int64_t i = i0 + m;
+            float own = 0.f, m1 = 0.f, m2 = 0.f, mk = 0.f;
+            if (i < gv.P) {
+                NbrRange rs, rg;
+                node_ranges(gv, i, rs, rg);
+                own = tr_in[i * 32 + lane];
+                m1 = gather_mean32(a1, rs, gv.sta_col, 1.f, lane);
+                m2 = gather_mean32(a2, rg, gv.src_col, 1.f, lane);
+                if (lane == 0) mk = mask_out[node_grid(gv, i)];
+                else if (lane < 5) mk = mask[i * 4 + lane - 1];
+            }
+            if (lane < 30) {
+                F[lane * LDF + m] = own;
+                F[(30 + lane) * LDF + m] = m1;
+                F[(60 + lane) * LDF + m] = m2;
+            }
+            if (lane < 5) F[(90 + lane) * LDF + m] = mk;
+        }
+        __syncthreads();
+        // ---- stage B: tr = PReLU1([l1_t1_2(..) | l1_t2_2(..)]) --------------------------------------------------------
+        {
+            const float* W = sW + (br ? as::W12 : as::W11);
+            const float* B = sW + (br ? as::B12 : as::B11);
+            float acc[30];
+#pragma unroll
+            for (int o = 0; o < 30; ++o) acc[o] = B[o];
+#pragma unroll 2
+            for (int k = 0; k < 30; ++k) fma_row30(acc, F[k * LDF + n], W + k * 32);
+            const float* Fm = F + (30 + 30 * br) * LDF;
+#pragma unroll 2
+            for (int k = 0; k < 30; ++k) fma_row30(acc, Fm[k * LDF + n], W + (30 + k) * 32);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) fma_row30(acc, F[(90 + k) * LDF + n], W + (60 + k) * 32);
+            __syncthreads();   // every thread has finished reading rows 0-89
+#pragma unroll
+            for (int o = 0; o < 30; ++o) F[(br * 30 + o) * LDF + n] = prelu(acc[o], s_a1);
+        }
+        __syncthreads();
+        // ---- stage C: h = PReLU(l2_t*_1 tr);  v = W_agg h;  c = W_tr tr + W_m mask + b ---------------------------------
+        {
+            const float* Wa = sW + (br ? as::W22A : as::W21A);
+            const float* Ba = sW + (br ? as::B22A : as::B21A);
+            const float ah = br ? s_a22 : s_a21;
+            float h[30];
+#pragma unroll
+            for (int o = 0; o < 30; ++o) h[o] = Ba[o];
+#pragma unroll 2
+            for (int k = 0; k < 60; ++k) fma_row30(h, F[k * LDF + n], Wa + k * 32);
+            float v[16];
+#pragma unroll
+            for (int o = 0; o < 16; ++o) v[o] = 0.f;
+            const float* Wv = sW + (br ? as::WVB : as::WVA);
+#pragma unroll
+            for (int k = 0; k < 30; ++k) fma_row16(v, prelu(h[k], ah), Wv + k * 16);
+            const float* Wc = sW + (br ? as::WCB : as::WCA);
+            const float* Bc = sW + (br ? as::BCB : as::BCA);
+            float c[16];
+#pragma unroll
+            for (int o = 0; o < 16; ++o) c[o] = Bc[o];
+#pragma unroll 2
+            for (int k = 0; k < 60; ++k) fma_row16(c, F[k * LDF + n], Wc + k * 16);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) fma_row16(c, F[(90 + k) * LDF + n], Wc + (60 + k) * 16);
+            const int64_t i = i0 + n;
+            if (i < gv.P) {
+                float4* zp = reinterpret_cast<float4*>(zc + i * LD_ZC + br * 16);
+                float4* vp = reinterpret_cast<float4*>((br ? vb : va) + i * LD_V);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    zp[q] = make_float4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
+                    vp[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                }
+            }
+        }
+        __syncthreads();   // F is rewritten by the next tile's gather
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// layer 2: s = PReLU2(zc + [mean_sta va | mean_src vb]); one warp per product node
+// --------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) assoc_layer2_kernel(const GraphView gv, const float* __restrict__ packed,
+                                                           const float* __restrict__ zc, const float* __restrict__ va,
+                                                           const float* __restrict__ vb, float* __restrict__ s_out) {
+    const float a2 = packed[as::SL + as::SL_A2];
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < gv.P; i += warps) {
+        NbrRange rs, rg;
+        node_ranges(gv, i, rs, rg);
+        const float own = zc[i * LD_ZC + lane];
+        const float mean = gather_mean16x2(va, vb, rs, rg, gv.sta_col, gv.src_col, lane);
+        s_out[i * as::LD_S + lane] = (lane & 15) < 15 ? prelu(own + mean, a2) : 0.f;
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// LocalSliceLgCollapse P and S: one warp per (pick, phase); lanes = hidden channels
+// --------------------------------------------------------------------------------------------------------------------
+constexpr int KC_WARPS = 4;
+
+__global__ void __launch_bounds__(KC_WARPS * 32)
+    assoc_collapse_kernel(const float* __restrict__ packed, const float* __restrict__ s_rows, int64_t P,
+                          const int64_t* __restrict__ edges_p, const int64_t* __restrict__ edges_s,
+                          const float* __restrict__ tlatent, const float* __restrict__ tpick,
+                          const int64_t* __restrict__ ipick, const float* __restrict__ phase_label, int n_arv,
+                          int l_dt, int k_infer, float dt0, float dt_step, float eps, float* __restrict__ arrival) {
+    __shared__ __align__(16) float sW[2 * as::C_SIZE];
+    for (int i = threadIdx.x; i < 2 * as::C_SIZE; i += KC_WARPS * 32) sW[i] = packed[as::CP_W1 + i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int a = blockIdx.x * KC_WARPS + (threadIdx.x >> 5);
+    const int ph = blockIdx.y;                         // 0: P (LocalSliceLgCollapseP), 1: S
+    if (a > n_arv) return;
+    float* out = arrival + (int64_t)a * 30 + ph * 15;
+    if (a == n_arv) {                                  // the null arrival of module.py:709-710
+        if (lane < 15) out[lane] = 0.f;
+        return;
+    }
+    const float* W1 = sW + ph * as::C_SIZE;
+    const float* B1 = W1 + (as::CP_B1 - as::CP_W1);
+    const float* W2 = W1 + (as::CP_W2 - as::CP_W1);
+    const float* B2 = W1 + (as::CP_B2 - as::CP_W1);
+    const float s1 = packed[as::SL + (ph ? as::SL_CS1 : as::SL_CP1)], s2 = packed[as::SL + (ph ? as::SL_CS2 : as::SL_CP2)];
+    const int64_t* __restrict__ edges = ph ? edges_s : edges_p;
+    const float tp = tpick[a];
+    const float phl = phase_label[a];
+    // t_index = floor((tpick - dt_partition[0]) / dt) in fp32, as torch evaluates it (module.py:630)
+    const float tq = floorf(__fdiv_rn(__fsub_rn(tp, dt0), dt_step));
+    const int64_t base = (ipick[a] * (int64_t)l_dt + (int64_t)tq) * k_infer;
+    const bool in_table = tq >= 0.f && tq < (float)l_dt;
+    float acc = 0.f;
+    int cnt = 0;
+    for (int e = 0; e < k_infer && in_table; ++e) {
+        const int64_t j = edges[base + e];
+        if (j < 0 || j >= P) continue;
+        const float t_rel = __fsub_rn(tp, tlatent[j * 2 + ph]);                      // module.py:637
+        if (!(fabsf(t_rel) < 2.0f * eps)) continue;
+        ++cnt;
+        const float row = s_rows[j * as::LD_S + lane];
+        float h = B1[lane];
+#pragma unroll
+        for (int k = 0; k < 30; ++k) h = fmaf(__shfl_sync(FULL_MASK, row, k < 15 ? k : k + 1), W1[k * 32 + lane], h);
+        h = fmaf(__fdiv_rn(t_rel, eps), W1[30 * 32 + lane], h);
+        h = fmaf(phl, W1[31 * 32 + lane], h);
+        acc += prelu(h, s1);
+    }
+    const float mean = cnt > 0 ? acc / (float)cnt : 0.f;
+    float o = lane < 15 ? B2[lane] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 30; ++k) {
+        const float mk = __shfl_sync(FULL_MASK, mean, k);
+        if (lane < 15) o = fmaf(mk, W2[k * 16 + lane], o);
+    }
+    if (lane < 15) out[lane] = prelu(o, s2);
+}
+
+}  // namespace
+
+// --------------------------------------------------------------------------------------------------------------------
+// launchers
+// --------------------------------------------------------------------------------------------------------------------
+size_t assoc_packed_floats() { return (size_t)as::FLOATS; }
+
+int assoc_layout(int32_t* out, int n) {
+    static const int32_t k[] = {as::SD_W, as::SD_B, as::RO_WY, as::RO_B1, as::RO_WA, as::RO_W2, as::RO_B2, as::AI_W, as::AI_B,
+                                as::M11_W, as::M11_B, as::M12_W, as::M12_B, as::W11, as::W12, as::B11, as::B12, as::W21A,
+                                as::W22A, as::B21A, as::B22A, as::WVA, as::WVB, as::WCA, as::WCB, as::BCA, as::BCB,
+                                as::CP_W1, as::CP_B1, as::CP_W2, as::CP_B2, as::CS_W1, as::CS_B1, as::CS_W2, as::CS_B2, as::SL};
+    const int count = (int)(sizeof(k) / sizeof(k[0]));
+    if (!out || n < count) {
+        set_error("genie_assoc_layout: need room for " + std::to_string(count) + " offsets");
+        return GENIE_ERR_INVALID;
+    }
+    for (int i = 0; i < count; ++i) out[i] = k[i];
+    return GENIE_OK;
+}
+
+AssocWorkspace carve_assoc_workspace(const genie_plan* p, void* base) {
+    AssocWorkspace w;
+    const size_t P = (size_t)p->g.n_prod, G = (size_t)p->g.n_grid;
+    size_t off = 0;
+    auto take = [&](size_t floats) {
+        float* ptr = base ? reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off) : nullptr;
+        off += (floats * sizeof(float) + 255) / 256 * 256;
+        return ptr;
+    };
+    w.tr = take(P * 32);
+    w.a1 = take(P * 32);
+    w.a2 = take(P * 32);
+    w.zc = take(P * 32);
+    w.va = take(P * 16);
+    w.vb = take(P * 16);
+    w.yfc1 = take(G * 32);
+    w.mask_out = take(G);
+    w.bytes = off;
+    return w;
+}
+
+int launch_assoc_product(const genie_plan* p, const float* packed, const float* x_spatial, int ld_x, const float* y, int T,
+                         float thresh, const float* edge_attr, const float* x_latent, const float* mask,
+                         const AssocWorkspace& w, float* s0_out, float* mask_out_copy, cudaStream_t st) {
+    const int64_t P = p->g.n_prod;
+    const int G = p->g.n_grid;
+    if (P == 0 || G == 0) return GENIE_OK;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GENIE_CUDA_CHECK(cudaFuncSetAttribute(assoc_layer1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM));
+        GENIE_CUDA_CHECK(cudaFuncSetAttribute(assoc_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K0_SMEM));
+        attr_set = true;
+    }
+    const GraphView gv = make_view(p);
+    {
+        TimedLaunch tl(KID_ASSOC_GRID_PRE, st);
+        assoc_grid_pre_kernel<<<(G + 127) / 128, 128, 0, st>>>(packed, x_spatial, ld_x, y, T, G, thresh, w.yfc1, w.mask_out);
+        GENIE_LAUNCH_CHECK();
+    }
+    if (mask_out_copy != nullptr)
+        GENIE_CUDA_CHECK(cudaMemcpyAsync(mask_out_copy, w.mask_out, sizeof(float) * (size_t)G, cudaMemcpyDeviceToDevice, st));
+    {
+        TimedLaunch tl(KID_ASSOC_INIT, st);
+        assoc_init_kernel<<<(unsigned)((P + K0_THREADS - 1) / K0_THREADS), K0_THREADS, K0_SMEM, st>>>(
+            gv, packed, w.yfc1, w.mask_out, edge_attr, x_latent, mask, s0_out, w.tr, w.a1, w.a2);
+        GENIE_LAUNCH_CHECK();
+    }
+    {
+        const int64_t n_tiles = (P + TM - 1) / TM;
+        const int64_t grid = n_tiles < (int64_t)p->sm_count * 2 ? n_tiles : (int64_t)p->sm_count * 2;
+        TimedLaunch tl(KID_ASSOC_LAYER1, st);
+        assoc_layer1_kernel<<<(unsigned)grid, K2_THREADS, K2_SMEM, st>>>(gv, packed, w.tr, w.a1, w.a2, w.mask_out, mask, w.zc,
+                                                                        w.va, w.vb, n_tiles);
+        GENIE_LAUNCH_CHECK();
+    }
+    {
+        const int64_t blocks = (P + 7) / 8;
+        const int64_t cap = (int64_t)p->sm_count * 16;
+        TimedLaunch tl(KID_ASSOC_LAYER2, st);
+        assoc_layer2_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(gv, packed, w.zc, w.va, w.vb, w.tr);
+        GENIE_LAUNCH_CHECK();
+    }
+    return GENIE_OK;
+}
+
+int launch_assoc_collapse(const float* packed, const float* s_rows, int64_t P, const int64_t* edges_p, const int64_t* edges_s,
+                          const float* tlatent, const float* tpick, const int64_t* ipick, const float* phase_label, int n_arv,
+                          int l_dt, int k_infer, float dt0, float dt_step, float eps, float* arrival, cudaStream_t st) {
+    const dim3 grid((unsigned)((n_arv + 1 + KC_WARPS - 1) / KC_WARPS), 2);
+    TimedLaunch tl(KID_ASSOC_COLLAPSE, st);
+    assoc_collapse_kernel<<<grid, KC_WARPS * 32, 0, st>>>(packed, s_rows, P, edges_p, edges_s, tlatent, tpick, ipick,
+                                                         phase_label, n_arv, l_dt, k_infer, dt0, dt_step, eps, arrival);
+    GENIE_LAUNCH_CHECK();
+    return GENIE_OK;
+}

@@ -33,7 +33,9 @@ const char* const kKernelNames[KID_COUNT] = {"pack_weights_kernel", "input_serie
                                              "da_init_kernel",      "da_layer1_kernel",    "da_layer1_tc_kernel", "da_layer2_readin_kernel",
                                              "readin_finalize_kernel", "sa_pre_kernel",    "sa_main_kernel",
                                              "src_mean32_kernel",   "src_mean16_kernel",   "da_layer1_s_kernel",
-                                             "da_layer2_s_kernel",  "heads_grid_kernel",   "heads_query_kernel"};
+                                             "da_layer2_s_kernel",  "heads_grid_kernel",   "heads_query_kernel",
+                                             "assoc_grid_pre_kernel", "assoc_init_kernel", "assoc_layer1_kernel",
+                                             "assoc_layer2_kernel", "assoc_collapse_kernel"};
 }  // namespace
 
 TimedLaunch::TimedLaunch(int kid_, cudaStream_t st_) : kid(kid_), st(st_), slot(nullptr) {
@@ -348,6 +350,47 @@ int genie_input_nearest_fwd(const genie_nearest_params_t* prm, const double* tim
     }
     return launch_input_nearest(prm, times_all_dev, times_p_dev, times_s_dev, ind_use_dev, trv_times_dev, slice_out_dev,
                                 mask_out_dev, static_cast<cudaStream_t>(stream));
+}
+
+// ---- association branch ---------------------------------------------------------------------------
+size_t genie_assoc_packed_floats(void) { return assoc_packed_floats(); }
+
+int genie_assoc_layout(int32_t* offsets_out, int n) { return assoc_layout(offsets_out, n); }
+
+size_t genie_assoc_workspace_bytes(const genie_plan_t* plan) {
+    if (!plan) return 0;
+    return carve_assoc_workspace(plan, nullptr).bytes;
+}
+
+int genie_assoc_product_fwd(const genie_plan_t* plan, const float* assoc_packed_dev, const float* x_spatial_dev, int ld_x,
+                            const float* y_dev, int n_t, float mask_thresh, const float* edge_attr_dev,
+                            const float* x_latent_dev, const float* mask_dev, void* assoc_workspace_dev,
+                            float* s0_out_dev, float* mask_out_dev, float** s_rows_out, void* stream) {
+    if (!plan || !assoc_packed_dev || !x_spatial_dev || !y_dev || !edge_attr_dev || !x_latent_dev || !mask_dev ||
+        !assoc_workspace_dev || ld_x < 30 || n_t < 0) {
+        set_error("genie_assoc_product_fwd: bad argument");
+        return GENIE_ERR_INVALID;
+    }
+    const AssocWorkspace w = carve_assoc_workspace(plan, assoc_workspace_dev);
+    if (s_rows_out) *s_rows_out = w.tr;
+    return launch_assoc_product(plan, assoc_packed_dev, x_spatial_dev, ld_x, y_dev, n_t, mask_thresh, edge_attr_dev,
+                                x_latent_dev, mask_dev, w, s0_out_dev, mask_out_dev, static_cast<cudaStream_t>(stream));
+}
+
+int genie_assoc_collapse_fwd(const float* assoc_packed_dev, const float* s_rows_dev, int64_t n_prod, const int64_t* edges_p_dev,
+                             const int64_t* edges_s_dev, int64_t n_edges, const float* tlatent_dev, const float* tpick_dev,
+                             const int64_t* ipick_dev, const float* phase_dev, int n_arv, int n_sta, int l_dt, int k_infer,
+                             float dt0, float dt_step, float eps, float* arrival_out_dev, void* stream) {
+    if (!assoc_packed_dev || !s_rows_dev || !edges_p_dev || !edges_s_dev || !tlatent_dev || !arrival_out_dev || n_arv < 0 ||
+        (n_arv > 0 && (!tpick_dev || !ipick_dev || !phase_dev)) || l_dt < 2 || k_infer < 1 || !(dt_step > 0.f) ||
+        !(eps > 0.f) || n_edges != (int64_t)n_sta * l_dt * k_infer) {
+        set_error("genie_assoc_collapse_fwd: bad argument (the pointer tables must hold n_sta * len(dt_partition) * k_infer "
+                  "entries, module.py:624)");
+        return GENIE_ERR_INVALID;
+    }
+    return launch_assoc_collapse(assoc_packed_dev, s_rows_dev, n_prod, edges_p_dev, edges_s_dev, tlatent_dev, tpick_dev,
+                                 ipick_dev, phase_dev, n_arv, l_dt, k_infer, dt0, dt_step, eps, arrival_out_dev,
+                                 static_cast<cudaStream_t>(stream));
 }
 
 int genie_data_aggregation_fwd(const genie_plan_t* plan, const float* packed_dev, const float* slice_dev,

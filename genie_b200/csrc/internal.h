@@ -89,6 +89,11 @@ enum KernelId {
     KID_DA_LAYER2_S,
     KID_HEADS_GRID,
     KID_HEADS_QUERY,
+    KID_ASSOC_GRID_PRE,
+    KID_ASSOC_INIT,
+    KID_ASSOC_LAYER1,
+    KID_ASSOC_LAYER2,
+    KID_ASSOC_COLLAPSE,
     KID_COUNT
 };
 // Brackets one kernel launch with cudaEvents on its stream when timing is enabled (no-op otherwise).
@@ -156,6 +161,27 @@ int launch_heads_grid(const float* packed, const float* fold, int T, const float
 int launch_heads_query(const float* packed, const float* fold, int T, const float* x_spatial, int ld_x, const float* x_context,
                        const float* x_query, const int64_t* nbr, int k_nbr, int Q, float scale_rel, float* x_out,
                        cudaStream_t st);
+// association branch (assoc_kernels.cu)
+struct AssocWorkspace {
+    float* tr;        // [P][32]   init_trns output; re-used for the branch output s [P][32] = [o1(15) 0 | o2(15) 0]
+    float* a1;        // [P][32]   PReLU11(l1_t1_1 tr)
+    float* a2;        // [P][32]   PReLU12(l1_t2_1 tr)
+    float* zc;        // [P][32]
+    float* va;        // [P][16]
+    float* vb;        // [P][16]
+    float* yfc1;      // [G][32]   read-out fc1, y_latent half
+    float* mask_out;  // [G]
+    size_t bytes;
+};
+AssocWorkspace carve_assoc_workspace(const genie_plan* p, void* base);
+size_t assoc_packed_floats();
+int assoc_layout(int32_t* out, int n);
+int launch_assoc_product(const genie_plan* p, const float* packed, const float* x_spatial, int ld_x, const float* y, int T,
+                         float thresh, const float* edge_attr, const float* x_latent, const float* mask,
+                         const AssocWorkspace& w, float* s0_out, float* mask_out_copy, cudaStream_t st);
+int launch_assoc_collapse(const float* packed, const float* s_rows, int64_t P, const int64_t* edges_p, const int64_t* edges_s,
+                          const float* tlatent, const float* tpick, const int64_t* ipick, const float* phase_label, int n_arv,
+                          int l_dt, int k_infer, float dt0, float dt_step, float eps, float* arrival, cudaStream_t st);
 int launch_input_nearest(const genie_nearest_params_t* prm, const double* t_all, const double* t_p, const double* t_s,
                          const int32_t* ind_use, const float* trv_times, float* slice_out, float* mask_out, cudaStream_t st);
 int launch_input_scatter(const genie_plan* p, const genie_input_params_t* prm, const double* picks, int64_t n_picks,

@@ -173,8 +173,10 @@ class SpatialAttention(nn.Module):
             self._edge_cache = c[:4] + (edge_index[0].view(Q, -1).contiguous(),)
         return self._edge_cache[4]
 
-    def forward(self, inpts, x_query, x_context, k=10):
-        edge_index = self._edges(x_query, x_context, k)
+    def forward(self, inpts, x_query, x_context, k=10, cache=True):
+        """cache=False: one-off query sets (the association sources x_query_src_cart) do not evict the cached kNN edges of
+        the fixed query grid."""
+        edge_index = self._edges(x_query, x_context, k) if cache else knn_query_edges(x_context, x_query, k)
         Q = x_query.shape[0]
         kk = edge_index.shape[1] // max(Q, 1)
         edge_attr = (x_query[edge_index[1]] - x_context[edge_index[0]]) / self.scale_rel
@@ -266,7 +268,7 @@ class DataAggregationAssociationPhaseEdges(DataAggregationAssociationPhase):
 
 
 class LocalSliceLgCollapse(nn.Module):
-    """Parameters of module.py:610-622."""
+    """Parameters of module.py:610-622.  Forward: libgenie_b200 (genie_assoc_collapse_fwd, P and S in one launch)."""
 
     def __init__(self, ndim_in, ndim_out, n_edge=2, n_hidden=30, eps=eps, use_phase_types=use_phase_types,
                  device='cuda'):
@@ -300,6 +302,77 @@ class StationSourceAttentionMergedPhases(nn.Module):
         self.activate3 = nn.PReLU()
         self.activate4 = nn.PReLU()
         self.n_heads, self.n_latent, self.eps = n_heads, n_latent, eps
+        self.scale = np.sqrt(n_latent)
+        self.use_phase_types = use_phase_types
+        self.use_neighbor_assoc_edges = use_neighbor_assoc_edges
+        if use_neighbor_assoc_edges:
+            raise NotImplementedError('genie_b200: use_neighbor_assoc_edges=True is not supported')
+
+    def forward(self, src, stime, src_embed, trv_src, locs_cart, arrival_p, arrival_s, tpick, ipick, phase_label):
+        """module.py:698-744 with the reference's signature (`src`, `locs_cart` are unused there as well)."""
+        z = arrival_p.new_zeros((1, arrival_p.shape[1]))
+        arrival = torch.cat((torch.cat((arrival_p, z), dim=0), torch.cat((arrival_s, z), dim=0)), dim=1)     # :709-711
+        return self.forward_merged(stime, src_embed, trv_src, arrival, tpick, ipick, phase_label)
+
+    def forward_merged(self, stime, src_embed, trv_src, arrival, tpick, ipick, phase_label):
+        """Source-arrival attention (module.py:698-781) on `arrival` [n_arv + 1, 2 * ndim_arv_in] = [P embedding | S embedding]
+        with the null arrival as last row (what genie_assoc_collapse_fwd writes).  Pick-sized work (n_src x sum over
+        stations of n_s (n_s + 1) edges): plain torch on the tensors' device, no torch_geometric / cKDTree / Python loop —
+        the same-station pairs come from one comparison matrix, the segment softmax from scatter-amax / index_add."""
+        dev = arrival.device
+        n_src, n_sta, n_arv = int(trv_src.shape[0]), int(trv_src.shape[1]), int(tpick.shape[0])
+        eps = float(self.eps)
+        tpick = tpick.reshape(-1).float()
+        ipick = ipick.reshape(-1).long()
+        stime = stime.reshape(-1).float()
+        ph = phase_label.reshape(-1, 1).float()
+        if not self.use_phase_types:
+            ph = ph * 0.0
+        # edges of one source: every pick a (target) <- every pick b of the same station, and <- the null arrival (:714)
+        tgt, srcn = torch.nonzero(ipick.view(-1, 1) == ipick.view(1, -1), as_tuple=True)
+        ar = torch.arange(n_arv, device=dev)
+        e0 = torch.cat((srcn, torch.full((n_arv,), n_arv, dtype=torch.long, device=dev)))
+        e1 = torch.cat((tgt, ar))
+        n_edge = e0.numel()
+        sindex = torch.arange(n_src, device=dev).repeat_interleave(n_edge)                                   # :719
+        e0 = e0.repeat(n_src)
+        e1 = e1.repeat(n_src) + sindex * n_arv
+        atime = torch.cat((tpick, tpick.new_full((1,), -eps)))
+        stindex = torch.cat((ipick, ipick.new_full((1,), n_sta)))
+        pad = trv_src.new_full((n_src, 1), -eps)
+        tsrc_p = torch.cat((trv_src[:, :, 0], pad), dim=1)
+        tsrc_s = torch.cat((trv_src[:, :, 1], pad), dim=1)
+        phase = torch.cat((ph, ph.new_full((1, 1), -1.0)), dim=0)
+        t_kernel_sq = torch.tensor([eps], dtype=torch.float32, device=dev) ** 2
+        rel_p = (atime[e0] - (tsrc_p[sindex, stindex[e0]] + stime[sindex])).reshape(-1, 1)
+        rel_s = (atime[e0] - (tsrc_s[sindex, stindex[e0]] + stime[sindex])).reshape(-1, 1)
+        thr = 2.0 * torch.sqrt(t_kernel_sq)
+        keep = torch.nonzero(((rel_p.abs() < thr) | (rel_s.abs() < thr)).reshape(-1), as_tuple=True)[0]      # :727
+        e0, e1, sindex, rel_p, rel_s = e0[keep], e1[keep], sindex[keep], rel_p[keep], rel_s[keep]
+        M, H, L = n_arv * n_src, self.n_heads, self.n_latent
+        if e0.numel() > 0:
+            e0max = int(e0.max())           # taken over the kept edges, as the reference's message() does (:762-763)
+            f_p = torch.cat((torch.exp(-0.5 * (rel_p ** 2) / t_kernel_sq), torch.sign(rel_p), phase[e0]), dim=1)
+            f_s = torch.cat((torch.exp(-0.5 * (rel_s ** 2) / t_kernel_sq), torch.sign(rel_s), phase[e0]), dim=1)
+            self_link = (e0 == torch.remainder(e1, e0max)).reshape(-1, 1).float()
+            null_link = (e0 == e0max).reshape(-1, 1).float()
+            xj = arrival[e0]
+            ctx = self.f_src_context_2(self.activate1(self.f_src_context_1(torch.cat(
+                (src_embed[sindex], stime[sindex].reshape(-1, 1), self_link, null_link), dim=1)))).view(-1, H, L)
+            qry = self.f_arrival_query_2(self.activate2(self.f_arrival_query_1(torch.cat((xj, f_p, f_s), dim=1)))).view(-1, H, L)
+            val = self.f_values_2(self.activate3(self.f_values_1(torch.cat(
+                (xj, f_p, f_s, self_link, null_link), dim=1)))).view(-1, H, L)
+            scores = (qry * ctx).sum(-1) / self.scale
+            idx = e1.view(-1, 1).expand(-1, H)
+            mx = scores.new_full((M, H), float('-inf')).scatter_reduce(0, idx, scores, reduce='amax', include_self=True)
+            ex = (scores - mx.gather(0, idx)).exp()
+            den = scores.new_zeros((M, H)).scatter_add_(0, idx, ex)
+            alpha = ex / (den.gather(0, idx) + 1e-16)
+            agg = val.new_zeros((M, H, L)).index_add_(0, e1, alpha.unsqueeze(-1) * val)
+        else:
+            agg = arrival.new_zeros((M, H, L))
+        out = self.proj_2(self.activate4(self.proj_1(agg.mean(1))))                                          # :742
+        return out.view(n_src, n_arv, out.shape[-1])
 
 
 # ---- the model ----------------------------------------------------------------------------------------------------------
@@ -354,7 +427,9 @@ class GCN_Detection_Network_extended(nn.Module):
         self._plan_key = None
         self._packed = None
         self._read_in_attr = None
-        self._heads = None
+        self._heads_w = None
+        self._assoc_w = None
+        self._read_out_key, self._read_out_attr = None, None
         self._edge_means = None       # updated model: (means_sta(scale), means_src(scale)) of the current plan
         self._edge_terms = None       # (key, t_sta, t_src, re-laid weight tensors)
 
@@ -467,32 +542,97 @@ class GCN_Detection_Network_extended(nn.Module):
         return ops.frontend_fwd(self._plan, packed, Slice, Mask, self._read_in_attr, x_temp_cuda_cart,
                                 float(self.scale_rel), want_latent=want_latent, want_readin=want_readin)
 
+    def _heads(self, x_spatial, x_temp_cuda_cart, x_query_cart, t_query):
+        """SpatialDirect -> TemporalAttention and SpatialAttention -> TemporalAttention (module.py:1015-1020)."""
+        if ops.HeadsWeights.supported(self) and x_query_cart.shape[0] > 0:
+            # read-out heads in libgenie_b200 (two kernels); the torch restatement below is kept for other head shapes
+            if self._heads_w is None or self._heads_w.device != x_spatial.device:
+                self._heads_w = ops.HeadsWeights(x_spatial.device)
+            hp, fold, T = self._heads_w.update(self, t_query)
+            edges = self.SpatialAttention._edges(x_query_cart, x_temp_cuda_cart, 10)
+            nbr = self.SpatialAttention._nbr_table(edges, x_query_cart.shape[0])
+            return ops.heads_fwd(self._heads_w, hp, fold, T, x_spatial, x_temp_cuda_cart, x_query_cart, nbr,
+                                 float(self.SpatialAttention.scale_rel))
+        y_latent = self.SpatialDirect(x_spatial)
+        y = self.TemporalAttention(y_latent, t_query)
+        x = self.SpatialAttention(x_spatial, x_query_cart, x_temp_cuda_cart)
+        x = self.TemporalAttention(x, t_query)
+        return y, x
+
     def forward_fixed_source(self, Slice, Mask, tpick, ipick, phase_label, locs_use_cart, x_temp_cuda_cart,
                              x_query_cart, t_query):
         """module.py:999-1020 -> (y [G,T,1], x [Q,T,1])."""
         with torch.no_grad():
             x_spatial = self.front_end(Slice, Mask, x_temp_cuda_cart)[0]
-            if ops.HeadsWeights.supported(self) and x_query_cart.shape[0] > 0:
-                # read-out heads in libgenie_b200 (two kernels); the torch restatement below is kept for other head shapes
-                if self._heads is None or self._heads.device != x_spatial.device:
-                    self._heads = ops.HeadsWeights(x_spatial.device)
-                hp, fold, T = self._heads.update(self, t_query)
-                edges = self.SpatialAttention._edges(x_query_cart, x_temp_cuda_cart, 10)
-                nbr = self.SpatialAttention._nbr_table(edges, x_query_cart.shape[0])
-                return ops.heads_fwd(self._heads, hp, fold, T, x_spatial, x_temp_cuda_cart, x_query_cart, nbr,
-                                     float(self.SpatialAttention.scale_rel))
-            y_latent = self.SpatialDirect(x_spatial)
-            y = self.TemporalAttention(y_latent, t_query)
-            x = self.SpatialAttention(x_spatial, x_query_cart, x_temp_cuda_cart)
-            x = self.TemporalAttention(x, t_query)
-        return y, x
+            return self._heads(x_spatial, x_temp_cuda_cart, x_query_cart, t_query)
 
-    def forward_fixed(self, *args, **kwargs):
-        raise NotImplementedError('genie_b200: the association branch (forward_fixed, module.py:963) is outside the '
-                                  'hot path built so far (SURVEY.md §8f rank 2)')
+    # -- association branch (SURVEY.md §8f rank 2) -----------------------------------------------------------------------
+    def _check_read_out_graph(self, A_Lg_in_src):
+        """The read-out kernel assumes edge e of A_Lg_in_src runs from grid node g(e) to product node e — the flipped read-in
+        list of process_continuous_days.py:632 / :645.  Checked once per tensor."""
+        ei = A_Lg_in_src.edge_index
+        key = (ei.data_ptr(), ei._version, tuple(ei.shape))
+        if self._read_out_key != key:
+            plan = self._plan
+            ei = ei.to(plan.device)
+            ok = ei.shape[1] == plan.n_prod and bool((ei[1] == torch.arange(plan.n_prod, device=plan.device)).all())
+            if ok:
+                ok = bool((ei[0] == plan.node_grid_index()).all())
+            if not ok:
+                raise capi.GenieError('A_Lg_in_src.edge_index must be the flipped A_src_in_edges.edge_index '
+                                      '([g(i); i], process_continuous_days.py:632)')
+            self._read_out_key = key
+            self._read_out_attr = A_Lg_in_src.x.to(plan.device).float().contiguous()
+        return self._read_out_attr
+
+    def _association(self, Slice, Mask, A_Lg_in_src, A_edges_p, A_edges_s, dt_partition, tlatent, tpick, ipick, phase_label,
+                     locs_use_cart, x_temp_cuda_cart, x_query_cart, x_query_src_cart, t_query, tq_sample, trv_out_q):
+        """module.py:974-997: front end + heads + association branch -> (y, x, arv_p, arv_s)."""
+        if self.updated_model:
+            raise NotImplementedError('genie_b200: the association branch of the updated model definition '
+                                      '(DataAggregationAssociationPhaseEdges, module.py:406) is not built')
+        if not ops.AssocWeights.supported(self):
+            raise NotImplementedError('genie_b200: the association kernels are built for the reference\'s module shapes')
+        with torch.no_grad():
+            x_spatial, x_latent, _ = self.front_end(Slice, Mask, x_temp_cuda_cart, want_latent=True)
+            y, x = self._heads(x_spatial, x_temp_cuda_cart, x_query_cart, t_query)
+            x_src = self.SpatialAttention(x_spatial, x_query_src_cart, x_temp_cuda_cart, cache=False)         # :980
+            attr = self._check_read_out_graph(A_Lg_in_src)
+            dev = x_spatial.device
+            if self._assoc_w is None or self._assoc_w.device != dev:
+                self._assoc_w = ops.AssocWeights(dev)
+            packed = self._assoc_w.update(self)
+            s_rows = ops.assoc_product_fwd(self._plan, packed, x_spatial, y.reshape(y.shape[0], -1), attr, x_latent, Mask,
+                                           mask_thresh=0.01)                                                   # :983-987
+            cp = self.LocalSliceLgCollapseP
+            ph = phase_label.reshape(-1).float()
+            if not cp.use_phase_types:
+                ph = ph * 0.0
+            arrival = ops.assoc_collapse_fwd(packed, s_rows, A_edges_p, A_edges_s, dt_partition, tlatent, tpick, ipick, ph,
+                                             int(locs_use_cart.shape[0]), float(cp.eps))                       # :988-989
+            arv = self.Arrivals.forward_merged(tq_sample, x_src, trv_out_q, arrival, tpick, ipick, phase_label)  # :990
+        return y, x, arv[:, :, 0].unsqueeze(-1), arv[:, :, 1].unsqueeze(-1)
+
+    def forward_fixed(self, Slice, Mask, tpick, ipick, phase_label, locs_use_cart, x_temp_cuda_cart, x_query_cart,
+                      x_query_src_cart, t_query, tq_sample, trv_out_q):
+        """module.py:963-997 -> (y [G,T,1], x [Q,T,1], arv_p [n_src,n_arv,1], arv_s [n_src,n_arv,1])."""
+        if self._plan is None:
+            raise RuntimeError('set_adjacencies must be called before forward_fixed*')
+        return self._association(Slice, Mask, self.A_Lg_in_src, self.A_edges_p, self.A_edges_s, self.dt_partition,
+                                 self.tlatent, tpick, ipick, phase_label, locs_use_cart, x_temp_cuda_cart, x_query_cart,
+                                 x_query_src_cart, t_query, tq_sample, trv_out_q)
 
     def forward(self, Slice, Mask, A_in_sta, A_in_src, A_src_in_edges, A_Lg_in_src, A_src_in_sta, A_src, A_edges_p,
                 A_edges_s, dt_partition, tlatent, tpick, ipick, phase_label, locs_use_cart, x_temp_cuda_cart,
                 x_query_cart, x_query_src_cart, t_query, tq_sample, trv_out_q):
-        raise NotImplementedError('genie_b200: the full training forward (module.py:908, association outputs) is '
-                                  'outside the hot path built so far (SURVEY.md §8f rank 2)')
+        """module.py:908-939: forward_fixed with the adjacencies passed on every call (plans are cached on tensor identity).
+        Inference only: the backward kernels (training, BASELINE.json configs[2]) are not built, so a call that would
+        need gradients raises instead of silently returning detached outputs."""
+        if torch.is_grad_enabled() and self.training:
+            raise NotImplementedError('genie_b200: backward of the CUDA front end is not implemented yet; '
+                                      'call under torch.no_grad() / model.eval()')
+        n_sta, n_grid = int(locs_use_cart.shape[0]), int(x_temp_cuda_cart.shape[0])
+        self._plan_for(A_in_sta, A_in_src, A_src_in_edges, A_src, n_sta, n_grid, Slice.device)
+        return self._association(Slice, Mask, A_Lg_in_src, A_edges_p, A_edges_s, dt_partition, tlatent, tpick, ipick,
+                                 phase_label, locs_use_cart, x_temp_cuda_cart, x_query_cart, x_query_src_cart, t_query,
+                                 tq_sample, trv_out_q)

@@ -180,6 +180,147 @@ def heads_fwd(hw, packed, fold, T, x_spatial, x_context, x_query, nbr, scale_rel
     return y, x
 
 
+class AssocWeights(object):
+    """Kernel-layout copy of the association-branch parameters (BipartiteGraphReadOutOperator,
+    DataAggregationAssociationPhase, LocalSliceLgCollapse{P,S}, + SpatialDirect for y_latent); see include/genie_b200.h,
+    genie_assoc_*.  Re-packed whenever a parameter changes."""
+    NAMES = ('SD_W', 'SD_B', 'RO_WY', 'RO_B1', 'RO_WA', 'RO_W2', 'RO_B2', 'AI_W', 'AI_B', 'M11_W', 'M11_B', 'M12_W', 'M12_B',
+             'W11', 'W12', 'B11', 'B12', 'W21A', 'W22A', 'B21A', 'B22A', 'WVA', 'WVB', 'WCA', 'WCB', 'BCA', 'BCB',
+             'CP_W1', 'CP_B1', 'CP_W2', 'CP_B2', 'CS_W1', 'CS_B1', 'CS_W2', 'CS_B2', 'SL')
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        lib = capi.load()
+        off = (ctypes.c_int32 * len(self.NAMES))()
+        capi.check(lib.genie_assoc_layout(off, len(self.NAMES)))
+        self.off = dict(zip(self.NAMES, [int(o) for o in off]))
+        self.buf = torch.zeros(int(lib.genie_assoc_packed_floats()), dtype=F32, device=self.device)
+        self._key = None
+
+    @staticmethod
+    def supported(model):
+        ro, da = model.BipartiteGraphReadOutOperator, model.DataAggregationAssociationPhase
+        cp, cs = model.LocalSliceLgCollapseP, model.LocalSliceLgCollapseS
+        return (tuple(model.SpatialDirect.f_direct.weight.shape) == (30, 30) and tuple(ro.fc1.weight.shape) == (30, 33) and
+                tuple(ro.fc2.weight.shape) == (15, 30) and tuple(da.init_trns.weight.shape) == (30, 50) and
+                tuple(da.l1_t1_2.weight.shape) == (30, 65) and tuple(da.l2_t1_2.weight.shape) == (15, 95) and
+                tuple(cp.fc1.weight.shape) == (30, 32) and tuple(cs.fc2.weight.shape) == (15, 30))
+
+    def _mat(self, name, w, ld):
+        """w: [n_out, n_in] slice of an nn.Linear weight -> K-major rows of `ld` floats."""
+        w = w.detach().t().contiguous()
+        n_in, n_out = w.shape
+        o = self.off[name]
+        self.buf[o:o + n_in * ld].view(n_in, ld)[:, :n_out] = w
+
+    def _vec(self, name, v):
+        v = v.detach().reshape(-1)
+        self.buf[self.off[name]:self.off[name] + v.numel()] = v
+
+    def update(self, model):
+        sd, ro, da = model.SpatialDirect, model.BipartiteGraphReadOutOperator, model.DataAggregationAssociationPhase
+        cp, cs = model.LocalSliceLgCollapseP, model.LocalSliceLgCollapseS
+        mods = (sd, ro, da, cp, cs)
+        if getattr(self, '_plist_for', None) is not model:
+            self._plist, self._plist_for = [p for m in mods for p in m.parameters()], model
+        key = tuple((p.data_ptr(), p._version) for p in self._plist)
+        if key == self._key:
+            return self.buf
+        for p in self._plist:
+            if p.device != self.device or p.dtype != F32:
+                raise capi.GenieError('association parameters must be fp32 tensors on %s' % self.device)
+        with torch.no_grad():
+            self.buf.zero_()
+            self._mat('SD_W', sd.f_direct.weight, 32); self._vec('SD_B', sd.f_direct.bias)
+            self._mat('RO_WY', ro.fc1.weight[:, 0:30], 32); self._vec('RO_B1', ro.fc1.bias)
+            self._mat('RO_WA', ro.fc1.weight[:, 30:33], 32)
+            self._mat('RO_W2', ro.fc2.weight, 16); self._vec('RO_B2', ro.fc2.bias)
+            self._mat('AI_W', da.init_trns.weight, 32); self._vec('AI_B', da.init_trns.bias)
+            self._mat('M11_W', da.l1_t1_1.weight, 32); self._vec('M11_B', da.l1_t1_1.bias)
+            self._mat('M12_W', da.l1_t2_1.weight, 32); self._vec('M12_B', da.l1_t2_1.bias)
+            self._mat('W11', da.l1_t1_2.weight, 32); self._vec('B11', da.l1_t1_2.bias)
+            self._mat('W12', da.l1_t2_2.weight, 32); self._vec('B12', da.l1_t2_2.bias)
+            self._mat('W21A', da.l2_t1_1.weight, 32); self._vec('B21A', da.l2_t1_1.bias)
+            self._mat('W22A', da.l2_t2_1.weight, 32); self._vec('B22A', da.l2_t2_1.bias)
+            for wv, wc, bc, lin in (('WVA', 'WCA', 'BCA', da.l2_t1_2), ('WVB', 'WCB', 'BCB', da.l2_t2_2)):
+                self._mat(wv, lin.weight[:, 60:90], 16)
+                self._mat(wc, torch.cat((lin.weight[:, 0:60], lin.weight[:, 90:95]), dim=1), 16)
+                self._vec(bc, lin.bias)
+            for pre, m in (('CP', cp), ('CS', cs)):
+                self._mat(pre + '_W1', m.fc1.weight, 32); self._vec(pre + '_B1', m.fc1.bias)
+                self._mat(pre + '_W2', m.fc2.weight, 16); self._vec(pre + '_B2', m.fc2.bias)
+            self._vec('SL', torch.cat([a.weight.detach().reshape(1) for a in (
+                sd.activate, ro.activate1, ro.activate2, da.activate, da.activate11, da.activate12, da.activate1,
+                da.activate21, da.activate22, da.activate2, cp.activate1, cp.activate2, cs.activate1, cs.activate2)]))
+        self._key = key
+        return self.buf
+
+
+def assoc_workspace(plan):
+    ws = getattr(plan, '_assoc_workspace', None)
+    if ws is None:
+        n = int(capi.load().genie_assoc_workspace_bytes(plan.handle))
+        ws = torch.empty(max(n, 256), dtype=torch.uint8, device=plan.device)
+        plan._assoc_workspace = ws
+    return ws
+
+
+def assoc_product_fwd(plan, packed, x_spatial, y, edge_attr, x_latent, Mask, mask_thresh=0.01, want_parts=False):
+    """mask_out, BipartiteGraphReadOutOperator and DataAggregationAssociationPhase (module.py:983-987).  Returns the branch
+    output s as a [P,32] view into the association workspace (columns 0-14 and 16-30 hold s[:, :15] and s[:, 15:]; valid
+    until the next call on this plan), and with want_parts also s0 [P,15] and mask_out [G]."""
+    dev = plan.device
+    x_spatial, y = _f32c(x_spatial, 'x_spatial'), _f32c(y, 'y')
+    edge_attr, x_latent, Mask = _f32c(edge_attr, 'attr'), _f32c(x_latent, 'x_latent'), _f32c(Mask, 'Mask')
+    G, P = plan.n_grid, plan.n_prod
+    if x_spatial.shape[0] != G or y.shape[0] != G or x_latent.shape != (P, 30) or Mask.shape != (P, 4) or \
+            edge_attr.shape != (P, 3):
+        raise capi.GenieError('association: x_spatial/y must have G = %d rows, x_latent [P,30], Mask [P,4], attr [P,3]' % G)
+    T = int(y.numel() // max(G, 1))
+    ws = assoc_workspace(plan)
+    s0 = torch.empty((P, 15), dtype=F32, device=dev) if want_parts else None
+    mask_out = torch.empty((G,), dtype=F32, device=dev) if want_parts else None
+    ptr = ctypes.c_void_p()
+    with torch.cuda.device(dev):
+        capi.check(capi.load().genie_assoc_product_fwd(
+            plan.handle, capi.dptr(packed, F32), capi.dptr(x_spatial, F32), int(x_spatial.stride(0)), capi.dptr(y, F32), T,
+            ctypes.c_float(mask_thresh), capi.dptr(edge_attr, F32), capi.dptr(x_latent, F32), capi.dptr(Mask, F32),
+            capi.dptr(ws), capi.dptr(s0), capi.dptr(mask_out), ctypes.byref(ptr), capi.stream_ptr(dev)))
+    off = ptr.value - ws.data_ptr()
+    s_rows = ws[off:off + P * 32 * 4].view(F32).view(P, 32)
+    return (s_rows, s0, mask_out) if want_parts else s_rows
+
+
+def assoc_collapse_fwd(packed, s_rows, A_edges_p, A_edges_s, dt_partition, tlatent, tpick, ipick, phase_label, n_sta, eps,
+                       k_infer=10):
+    """LocalSliceLgCollapseP / S (module.py:624-653) for every pick -> arrival [n_arv + 1, 30] (last row: the null arrival)."""
+    dev = s_rows.device
+    n_arv = int(tpick.shape[0])
+    if dt_partition.numel() < 2:
+        raise capi.GenieError('dt_partition needs at least two entries')
+    dtp = dt_partition.to(dev, F32)
+    dt0, dt_step = float(dtp[0]), float(dtp[1] - dtp[0])          # fp32 difference, as module.py:626 forms it
+    A_edges_p = A_edges_p.to(dev, torch.int64).contiguous()
+    A_edges_s = A_edges_s.to(dev, torch.int64).contiguous()
+    if A_edges_p.numel() != A_edges_s.numel():
+        raise capi.GenieError('A_edges_p and A_edges_s must have the same length')
+    tlatent = _f32c(tlatent.to(dev), 'tlatent')
+    if tlatent.shape != (s_rows.shape[0], 2):
+        raise capi.GenieError('tlatent must be [P,2]')
+    tpick = _f32c(tpick.to(dev).reshape(-1), 'tpick')
+    ipick = ipick.to(dev, torch.int64).reshape(-1).contiguous()
+    phase = _f32c(phase_label.to(dev).reshape(-1), 'phase_label')
+    arrival = torch.empty((n_arv + 1, 30), dtype=F32, device=dev)
+    with torch.cuda.device(dev):
+        capi.check(capi.load().genie_assoc_collapse_fwd(
+            capi.dptr(packed, F32), capi.dptr(s_rows, F32), int(s_rows.shape[0]), capi.dptr(A_edges_p, torch.int64),
+            capi.dptr(A_edges_s, torch.int64), int(A_edges_p.numel()), capi.dptr(tlatent, F32),
+            capi.dptr(tpick, F32) if n_arv else None, capi.dptr(ipick, torch.int64) if n_arv else None,
+            capi.dptr(phase, F32) if n_arv else None, n_arv, int(n_sta), int(dtp.numel()), int(k_infer),
+            ctypes.c_float(dt0), ctypes.c_float(dt_step), ctypes.c_float(eps), capi.dptr(arrival), capi.stream_ptr(dev)))
+    return arrival
+
+
 def _f32c(t, name):
     if t.dtype != F32:
         t = t.float()

@@ -285,6 +285,12 @@ class GraphPlan(object):
                                                              capi.dptr(t_src, torch.float32, 'edge_src')))
         self._edge_terms = (t_sta, t_src)              # keep the tensors alive
 
+    def node_grid_index(self):
+        """int64 [P]: grid node of every product node (CARTESIAN: i // n_sta; EXPLICIT: the read-in target list)."""
+        if self.prod_grid is not None:
+            return self.prod_grid.long()
+        return torch.arange(self.n_prod, device=self.device) // self.n_sta
+
     def workspace(self):
         if self._workspace is None:
             self._workspace = torch.empty(max(self.workspace_bytes, 256), dtype=torch.uint8, device=self.device)

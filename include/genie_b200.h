@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GENIE_B200_ABI_VERSION 3
+#define GENIE_B200_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define GENIE_API __attribute__((visibility("default")))
@@ -204,6 +204,40 @@ GENIE_API int genie_heads_grid_fwd(const float* heads_packed_dev, const float* f
 GENIE_API int genie_heads_query_fwd(const float* heads_packed_dev, const float* fold_dev, int n_t, const float* x_spatial_dev,
                                     int ld_x, const float* x_context_dev, const float* x_query_dev, const int64_t* nbr_dev,
                                     int k_nbr, int n_query, float scale_rel, float* x_out_dev, void* stream);
+
+/* ---- association branch (forward / forward_fixed, module.py:983-991) -------------------------------
+ * The product-node-sized part of the association branch:
+ *   mask_out = max_t y[g,t] > mask_thresh                                                              (module.py:983)
+ *   s0 = BipartiteGraphReadOutOperator(SpatialDirect(x_spatial), A_Lg_in_src, mask_out)                (module.py:333-352)
+ *   s  = DataAggregationAssociationPhase(s0, x_latent, mask_out[g(i)], Mask, A_in_sta, A_in_src)       (module.py:356-403)
+ *   arrival[a] = [LocalSliceLgCollapseP(...)[a] | LocalSliceLgCollapseS(...)[a]], a null row appended  (module.py:604-653, 709-711)
+ * A_Lg_in_src must be the flipped read-in edge list (edge e: grid node g(e) -> product node e, process_continuous_days.py:632)
+ * and carry the same [P,3] edge features as A_src_in_edges; the graphs are the plan's.
+ *   assoc_packed_dev   fp32 [genie_assoc_packed_floats()], every nn.Linear K-major [n_in][ld] at the offsets genie_assoc_layout
+ *                      reports (order: SpatialDirect W, b; read-out fc1[:, :30], fc1.bias, fc1[:, 30:33], fc2 W, b; init_trns W,
+ *                      b; l1_t1_1 W, b; l1_t2_1 W, b; l1_t1_2, l1_t2_2 W, their biases; l2_t1_1, l2_t2_1 W, their biases;
+ *                      l2_t1_2[:, 60:90], l2_t2_2[:, 60:90]; l2_t1_2[:, 0:60 | 90:95], l2_t2_2[...], their biases; collapse P
+ *                      fc1 W, b, fc2 W, b; collapse S the same; 16 slopes {SpatialDirect, read-out 1, 2, association activate,
+ *                      11, 12, 1, 21, 22, 2, collapse P 1, 2, collapse S 1, 2}); ld = 32 / 16 for 30 / 15 outputs.
+ *   x_spatial_dev [n_grid][ld_x]; y_dev [n_grid][n_t] (the grid prediction of the heads); x_latent_dev [P][30] (DataAggregation
+ *   output, genie_frontend_fwd's x_latent_out_dev); s0_out_dev [P][15] or NULL; mask_out_dev [n_grid] or NULL;
+ *   *s_rows_out (optional) receives the address, inside the workspace, of s as [P][32] rows = [s[0:15] 0 | s[15:30] 0].
+ *   genie_assoc_collapse_fwd: edges_{p,s}_dev int64 [n_sta * l_dt * k_infer] product-node pointers (A_edges_p / A_edges_s);
+ *   tlatent_dev [P][2]; tpick fp32, ipick int64, phase fp32 [n_arv]; dt0 = dt_partition[0], dt_step = dt_partition[1] -
+ *   dt_partition[0] (fp32 difference, as torch forms it); arrival_out_dev [n_arv + 1][30].
+ */
+GENIE_API size_t genie_assoc_packed_floats(void);
+GENIE_API int genie_assoc_layout(int32_t* offsets_out, int n);
+GENIE_API size_t genie_assoc_workspace_bytes(const genie_plan_t* plan);
+GENIE_API int genie_assoc_product_fwd(const genie_plan_t* plan, const float* assoc_packed_dev, const float* x_spatial_dev,
+                                      int ld_x, const float* y_dev, int n_t, float mask_thresh, const float* edge_attr_dev,
+                                      const float* x_latent_dev, const float* mask_dev, void* assoc_workspace_dev,
+                                      float* s0_out_dev, float* mask_out_dev, float** s_rows_out, void* stream);
+GENIE_API int genie_assoc_collapse_fwd(const float* assoc_packed_dev, const float* s_rows_dev, int64_t n_prod,
+                                       const int64_t* edges_p_dev, const int64_t* edges_s_dev, int64_t n_edges,
+                                       const float* tlatent_dev, const float* tpick_dev, const int64_t* ipick_dev,
+                                       const float* phase_dev, int n_arv, int n_sta, int l_dt, int k_infer, float dt0,
+                                       float dt_step, float eps, float* arrival_out_dev, void* stream);
 
 /* ---- a1': nearest-pick input features -----------------------------------------------------------------------------------
  * Replaces the device-sized part of process_utils.extract_inputs_from_data_fixed_grids_with_phase_type

@@ -218,7 +218,6 @@ def association():
         max_t = net.max_moveout()
         sig, dt = 3.0, float(np.round(3.0 / 10.0, 2))
         P = synth.make_picks(net, 0.0, 600.0, seed=seed + 1, events_per_3h=400.0, false_per_sta_min=2.0)
-        t0 = 200.0 + 3.0 * seed
         trv_times = net.travel_times()
         locs, grid = net.sta, net.grid
         torch.manual_seed(seed)
@@ -253,30 +252,33 @@ def association():
         mz.set_adjacencies(A_prod_sta, A_prod_src, A_src_in_edges, A_Lg_in_src, A_src_in_sta, A_src_src,
                            torch.Tensor(A_edges_p).long(), torch.Tensor(A_edges_s).long(), torch.Tensor(dt_partition),
                            tlatent, locs_cart, grid_cart)
-        [Inpts, Masks], [lp_t, lp_s, lp_p, _] = pu.extract_input_from_data(
-            None, P, np.array([t0]), ind_use, locs, grid, A_src_in_sta.numpy(), trv_times=trv_times, max_t=max_t,
-            kernel_sig_t=sig, dt=dt, device='cpu')
-        Slice, Mask = Inpts[0], Masks[0]
         x_query = np.stack((rng.uniform(0, net.width, Q), rng.uniform(0, net.width, Q),
                             rng.uniform(-40000.0, 0.0, Q)), axis=1)
         t_query = np.arange(-3.0, 3.0 + 0.75, 0.75)
-        # with the default nn.Linear init y is negative everywhere: shift the bias of the last projection so that the
-        # source mask (y.max > 0.01, module.py:983) is a genuine mixture of zeros and ones (weights only, code untouched)
-        y0, _ = mz.forward_fixed_source(Slice, Mask, torch.Tensor(lp_t[0]), torch.Tensor(lp_s[0]).long(),
-                                        torch.Tensor(lp_p[0].reshape(-1, 1)).float(), locs_cart, grid_cart,
-                                        torch.Tensor(x_query), torch.Tensor(t_query.reshape(-1, 1)))
-        sd0 = mz.state_dict()
-        gain = float(0.05 / y0[:, :, 0].max(1)[0].std())       # spread the per-node maxima to a standard deviation of 0.05
-        sd0['TemporalAttention.proj_2.weight'] *= gain
-        mz.load_state_dict(sd0)
-        y0, _ = mz.forward_fixed_source(Slice, Mask, torch.Tensor(lp_t[0]), torch.Tensor(lp_s[0]).long(),
-                                        torch.Tensor(lp_p[0].reshape(-1, 1)).float(), locs_cart, grid_cart,
-                                        torch.Tensor(x_query), torch.Tensor(t_query.reshape(-1, 1)))
-        ym = np.sort(y0[:, :, 0].max(1)[0].numpy())
-        lo, hi = int(0.3 * len(ym)), int(0.7 * len(ym))
-        j = lo + int(np.argmax(np.diff(ym[lo:hi])))           # widest gap near the median: the threshold goes in its middle
-        sd0['TemporalAttention.proj_2.bias'] += float(0.01 - 0.5 * (ym[j] + ym[j + 1]))
-        mz.load_state_dict(sd0)
+        # weights: the trained Ferndale checkpoint (Examples/Ferndale.zip), so that y genuinely varies over the grid and the
+        # source mask (y.max > 0.01, module.py:983) is a mixture of zeros and ones decided by O(0.1) margins, not by rounding
+        with zipfile.ZipFile(os.path.join(REF, 'Examples', 'Ferndale.zip')) as z:
+            ck_name = [n for n in z.namelist() if n.endswith('trained_gnn_model_step_20000_ver_1.h5')][0]
+            z.extract(ck_name, work)
+        ck = torch.load(os.path.join(work, ck_name), map_location='cpu')
+        missing = mz.load_state_dict(ck, strict=False)
+        assert not missing.unexpected_keys and all(k.startswith('SpatialAttention.f_queries') for k in missing.missing_keys)
+        # window: the first origin time (3 s steps) whose source mask is a clear mixture — at least 8 % of either value and
+        # every grid node's y.max at least 2e-3 * max|y| away from the 0.01 threshold
+        for t0 in 200.0 + 3.0 * seed + 3.0 * np.arange(120):
+            [Inpts, Masks], [lp_t, lp_s, lp_p, _] = pu.extract_input_from_data(
+                None, P, np.array([t0]), ind_use, locs, grid, A_src_in_sta.numpy(), trv_times=trv_times, max_t=max_t,
+                kernel_sig_t=sig, dt=dt, device='cpu')
+            Slice, Mask = Inpts[0], Masks[0]
+            y0, _ = mz.forward_fixed_source(Slice, Mask, torch.Tensor(lp_t[0]), torch.Tensor(lp_s[0]).long(),
+                                            torch.Tensor(lp_p[0].reshape(-1, 1)).float(), locs_cart, grid_cart,
+                                            torch.Tensor(x_query), torch.Tensor(t_query.reshape(-1, 1)))
+            ym = y0[:, :, 0].max(1)[0].numpy()
+            frac = float((ym > 0.01).mean())
+            if 0.08 < frac < 0.92 and np.abs(ym - 0.01).min() > 2e-3 * np.abs(y0.numpy()).max() and len(lp_t[0]) >= 12:
+                break
+        else:
+            raise SystemExit('no window with a mixed source mask')
         # association queries: n_src sources at grid nodes (so their travel times are rows of trv_times), origin times
         # relative to t0 inside and outside the 2*eps keep window of the null arrival (module.py:723-727)
         isrc = rng.choice(G, size=n_src, replace=False)

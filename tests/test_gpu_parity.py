@@ -548,3 +548,143 @@ def test_sharded_front_end_single_process():
     assert rel_err(read_in.cpu().numpy(), want_r.cpu().numpy()) < 1e-5
     xs = bes[0].spatial(read_in, grid, 30000.0)
     assert rel_err(xs.cpu().numpy(), want_xs.cpu().numpy()) < 1e-5
+
+
+# ---- association branch: forward_fixed / forward ------------------------------------------------------
+
+ASSOC = ['assoc_10x100', 'assoc_18of20x160']
+
+
+def _assoc_setup(d, sd, dev):
+    from oracle.refshim.torch_geometric.data import Data
+    A_sta, A_src, A_ps, A_pg, A_sip, A_sis = _graphs(d)
+    m = _model(sd, dev, float(d['scale_rel']), float(d['scale_t']))
+    t = lambda k: torch.from_numpy(d[k]).to(dev)
+    locs = torch.from_numpy(d['sta'][d['ind_use']]).float().to(dev)
+    grid = torch.from_numpy(d['grid']).float().to(dev)
+    A_edges = Data(x=t('read_in_attr'), edge_index=A_sip.to(dev))
+    A_Lg = Data(x=t('read_in_attr'), edge_index=A_sip.flip(0).contiguous().to(dev))
+    graphs = (A_ps.to(dev), A_pg.to(dev), A_edges, A_Lg, A_sis.to(dev), A_src.to(dev), t('A_edges_p'), t('A_edges_s'),
+              t('dt_partition').float(), t('tlatent').float())
+    window = (t('tpick').float(), t('ipick').long(), t('phase_label').long().reshape(-1, 1), locs, grid,
+              t('x_query').float(), t('x_query_src').float(), t('t_query').float().reshape(-1, 1), t('tq_sample').float(),
+              t('trv_out_q').float())
+    return m, graphs, window, locs, grid
+
+
+@pytest.mark.parametrize('name', ASSOC)
+def test_forward_fixed_matches_reference(name):
+    """forward_fixed (module.py:963-997) through the nn.Module surface against the unmodified reference, plus the
+    intermediate tensors of the association kernels through the operator-level C-ABI wrappers."""
+    from genie_b200 import capi, ops
+    dev = _dev()
+    d, sd = load_golden(name)
+    m, graphs, window, locs, grid = _assoc_setup(d, sd, dev)
+    m.set_adjacencies(*graphs, locs, grid)
+    t = lambda k: torch.from_numpy(d[k]).to(dev)
+    n0 = capi.launch_count()
+    y, x, arv_p, arv_s = m.forward_fixed(t('Slice'), t('Mask'), *window)
+    assert capi.launch_count() - n0 >= 15
+    assert rel_err(y.cpu().numpy(), d['y']) < TOL and rel_err(x.cpu().numpy(), d['x']) < TOL
+    assert arv_p.shape == d['arv_p'].shape and arv_s.shape == d['arv_s'].shape
+    assert rel_err(arv_p.cpu().numpy(), d['arv_p']) < TOL
+    assert rel_err(arv_s.cpu().numpy(), d['arv_s']) < TOL
+    # operator level
+    packed = m._assoc_w.update(m)
+    s_rows, s0, mask_out = ops.assoc_product_fwd(m._plan, packed, t('x_spatial'), t('y').reshape(len(d['grid']), -1),
+                                                 t('read_in_attr'), t('x_latent'), t('Mask'), want_parts=True)
+    S = len(d['ind_use'])
+    assert np.array_equal(mask_out.cpu().numpy()[np.arange(S * len(d['grid'])) // S][:, None], d['mask_out_1'])
+    assert rel_err(s0.cpu().numpy(), d['assoc_s0']) < TOL
+    s = torch.cat((s_rows[:, 0:15], s_rows[:, 16:31]), dim=1)
+    assert rel_err(s.cpu().numpy(), d['assoc_s']) < TOL
+    assert not s_rows[:, 15].any() and not s_rows[:, 31].any()
+    arrival = ops.assoc_collapse_fwd(packed, s_rows, t('A_edges_p'), t('A_edges_s'), t('dt_partition').float(),
+                                     t('tlatent').float(), t('tpick').float(), t('ipick').long(), t('phase_label').float(), S,
+                                     float(d['eps']))
+    assert arrival.shape == (len(d['tpick']) + 1, 30) and not arrival[-1].any()
+    assert rel_err(arrival[:-1, :15].cpu().numpy(), d['arv_p_embed']) < TOL
+    assert rel_err(arrival[:-1, 15:].cpu().numpy(), d['arv_s_embed']) < TOL
+
+
+def test_forward_equals_forward_fixed_and_refuses_training():
+    """`forward` (module.py:908-939) takes the adjacencies per call; same numbers, and no silent no-grad result in training."""
+    dev = _dev()
+    d, sd = load_golden(ASSOC[0])
+    m, graphs, window, locs, grid = _assoc_setup(d, sd, dev)
+    t = lambda k: torch.from_numpy(d[k]).to(dev)
+    with torch.no_grad():
+        out = m.forward(t('Slice'), t('Mask'), *graphs, *window)
+    for a, key in zip(out, ('y', 'x', 'arv_p', 'arv_s')):
+        assert rel_err(a.cpu().numpy(), d[key]) < TOL, key
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m.forward(t('Slice'), t('Mask'), *graphs, *window)
+
+
+@pytest.mark.parametrize('explicit', [False, True])
+def test_association_matches_oracle_seeded(explicit):
+    """Seeded 60 x 400 network (split tcgen05 front end feeding the association kernels) and the same network as an EXPLICIT
+    product graph (generic kernels, prod_grid look-ups), against the oracle; ragged picks: stations without picks, a pick
+    whose time bin is the last of the table, picks outside every 2 eps window."""
+    from genie_b200 import ops, synth
+    from genie_b200.plan import GraphPlan
+    from genie_b200.process_utils import extract_inputs_adjacencies_cartesian
+    from oracle import genie_oracle as go
+    dev = _dev()
+    S, G, n_src, Q = 60, 400, 4, 50
+    net, A_sta, A_src, Slice, Mask, attr = _random_case(S, G, 8, 15, 21, dev)
+    rng = np.random.default_rng(77)
+    sd = load_golden(ASSOC[0])[1]                                        # the trained Ferndale weights the fixtures carry
+    A_sta, A_src, A_ps, A_pg, A_sip = go.build_adjacencies_dense(net.sta, net.grid, 8, 15)[:5]
+    P = S * G
+    trv = torch.from_numpy(net.travel_times()).float()                  # [G, S, 2]
+    tlatent = trv.reshape(-1, 2)
+    max_t = float(tlatent.max())
+    eps, k_inf = 15.0, 10
+    dt_partition = torch.arange(-6.0, max_t + 6.0 + 0.6, 0.6)
+    l_dt = dt_partition.numel()
+    A_edges_p = torch.from_numpy(rng.integers(0, P, S * l_dt * k_inf)).long()
+    A_edges_s = torch.from_numpy(rng.integers(0, P, S * l_dt * k_inf)).long()
+    n_arv = 70
+    tpick = torch.from_numpy(rng.uniform(-5.9, max_t + 5.9, n_arv)).float()
+    tpick[0] = float(dt_partition[-1]) + 0.1                             # last bin of the table
+    tpick[1] = -5.999
+    ipick = torch.from_numpy(rng.integers(0, S // 2, n_arv)).long()      # half of the stations have no picks
+    phase = torch.from_numpy(rng.integers(0, 2, n_arv)).long().reshape(-1, 1)
+    grid_cart = torch.from_numpy(net.grid).float()
+    x_query = torch.from_numpy(np.stack((rng.uniform(0, net.width, Q), rng.uniform(0, net.width, Q),
+                                         rng.uniform(-40000.0, 0.0, Q)), axis=1)).float()
+    isrc = rng.choice(G, n_src, replace=False)
+    x_query_src = grid_cart[isrc]
+    t_query = torch.arange(-3.0, 3.75, 0.75).reshape(-1, 1)
+    tq_sample = torch.tensor([0.0, 10.0, 29.0, 200.0])
+    trv_out_q = trv[isrc]
+    want = go.forward_fixed(sd, Slice, Mask, A_ps, A_pg, attr, A_sip, A_src, grid_cart, A_edges_p, A_edges_s, dt_partition,
+                            tlatent, tpick, ipick, phase, x_query, x_query_src, t_query, tq_sample, trv_out_q, 30000.0, 9.0,
+                            eps, return_parts=True)
+    parts = want[4]
+    ym = want[0][:, :, 0].max(1)[0]
+    assert 0.05 < float(parts['mask_out'].mean()) < 0.95 and float((ym - 0.01).abs().min()) > 1e-3 * float(want[0].abs().max())
+    m = _model(sd, dev, 30000.0, 9.0)
+    from oracle.refshim.torch_geometric.data import Data
+    mv = lambda a: a.to(dev)
+    if explicit:
+        m._plan = GraphPlan.from_edge_lists(mv(A_ps[:, torch.randperm(A_ps.shape[1])]), mv(A_pg), mv(A_sip), mv(A_src), 1, G,
+                                            device=dev)
+        # from_edge_lists recognises the Cartesian pattern only for the reference's edge order; the shuffled list is EXPLICIT
+        assert m._plan.mode == 1
+        m._read_in_attr = mv(attr)
+        m.A_Lg_in_src, m.A_edges_p, m.A_edges_s = Data(x=mv(attr), edge_index=mv(A_sip.flip(0).contiguous())), mv(A_edges_p), mv(A_edges_s)
+        m.dt_partition, m.tlatent = mv(dt_partition), mv(tlatent)
+    else:
+        m.set_adjacencies(mv(A_ps), mv(A_pg), Data(x=mv(attr), edge_index=mv(A_sip)),
+                          Data(x=mv(attr), edge_index=mv(A_sip.flip(0).contiguous())), None, mv(A_src), mv(A_edges_p),
+                          mv(A_edges_s), mv(dt_partition), mv(tlatent), mv(torch.from_numpy(net.sta).float()), mv(grid_cart))
+        assert m._plan.mode == 0
+    y, x, arv_p, arv_s = m.forward_fixed(mv(Slice), mv(Mask), mv(tpick), mv(ipick), mv(phase),
+                                         mv(torch.from_numpy(net.sta).float()), mv(grid_cart), mv(x_query), mv(x_query_src),
+                                         mv(t_query), mv(tq_sample), mv(trv_out_q))
+    assert rel_err(y.cpu().numpy(), want[0].numpy()) < TOL and rel_err(x.cpu().numpy(), want[1].numpy()) < TOL
+    assert rel_err(arv_p.cpu().numpy(), want[2].numpy()) < TOL
+    assert rel_err(arv_s.cpu().numpy(), want[3].numpy()) < TOL
