@@ -89,6 +89,7 @@ SIGNATURES = {
     'genie_plan_destroy': (None, [_P]),
     'genie_plan_workspace_bytes': (ctypes.c_size_t, [_P]),
     'genie_plan_set_edge_terms': (ctypes.c_int, [_P, _P, _P]),
+    'genie_plan_set_init_terms': (ctypes.c_int, [_P, _P, _P]),
     'genie_frontend_packed_floats': (ctypes.c_size_t, []),
     'genie_frontend_pack_weights': (ctypes.c_int, [ctypes.POINTER(FrontendWeights), _P, _P]),
     'genie_heads_packed_floats': (ctypes.c_size_t, []),

@@ -74,6 +74,37 @@ constexpr int LD_S = 32;                       // s rows: [o1(15) 0 | o2(15) 0]
 
 namespace {
 
+// Two-wide accumulators (Blackwell FFMA2, common.cuh): acc[o] holds outputs 2o, 2o+1.  acc += a * wrow[0..29]; wrow is a
+// 16-byte aligned shared-memory row read with the same address by all lanes (broadcast).  Same rounding as scalar FMAs.
+__device__ __forceinline__ void fma2_row30(f32x2_t (&acc)[15], float a, const float* __restrict__ wrow) {
+    const float4* w4 = reinterpret_cast<const float4*>(wrow);
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+        const float4 w = w4[c];
+        ffma2(acc[2 * c], a, w.x, w.y);
+        ffma2(acc[2 * c + 1], a, w.z, w.w);
+    }
+    const float2 w = *reinterpret_cast<const float2*>(wrow + 28);
+    ffma2(acc[14], a, w.x, w.y);
+}
+__device__ __forceinline__ void fma2_row16(f32x2_t (&acc)[8], float a, const float* __restrict__ wrow) {
+    const float4* w4 = reinterpret_cast<const float4*>(wrow);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float4 w = w4[c];
+        ffma2(acc[2 * c], a, w.x, w.y);
+        ffma2(acc[2 * c + 1], a, w.z, w.w);
+    }
+}
+__device__ __forceinline__ void init2_30(f32x2_t (&acc)[15], const float* __restrict__ b) {
+#pragma unroll
+    for (int o = 0; o < 15; ++o) acc[o] = pack2(b[2 * o], b[2 * o + 1]);
+}
+__device__ __forceinline__ void init2_16(f32x2_t (&acc)[8], const float* __restrict__ b) {
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = pack2(b[2 * o], b[2 * o + 1]);
+}
+
 constexpr int TM = 128;
 constexpr int LDF = TM + 1;
 
@@ -219,9 +250,9 @@ constexpr size_t K2_SMEM = (size_t)(K2_W_FLOATS + K2_F_ROWS * LDF) * sizeof(floa
 
 __global__ void __launch_bounds__(K2_THREADS, 2)
     assoc_layer1_kernel(const GraphView gv, const float* __restrict__ packed, const float* __restrict__ tr_in,
-                        const float* __restrict__ a1, const float* __restrict__ a2, const float* __restrict__ mask_out,
-                        const float* __restrict__ mask, float* __restrict__ zc, float* __restrict__ va,
-                        float* __restrict__ vb, int64_t n_tiles) {
+                        const float* __restrict__ a1, const float* __restrict__ a2, const float* __restrict__ msrc,
+                        const float* __restrict__ mask_out, const float* __restrict__ mask, float* __restrict__ zc,
+                        float* __restrict__ va, float* __restrict__ vb, int64_t n_tiles) {
     extern __shared__ __align__(16) float smem[];
     float* sW0 = smem;
     float* F = smem + K2_W_FLOATS;
@@ -248,7 +279,8 @@ __global__ void __launch_bounds__(K2_THREADS, 2)
                 node_ranges(gv, i, rs, rg);
                 own = tr_in[i * 32 + lane];
                 m1 = gather_mean32(a1, rs, gv.sta_col, 1.f, lane);
-                m2 = gather_mean32(a2, rg, gv.src_col, 1.f, lane);
+                // source neighbours: pre-averaged by the source pass (src_mean_kernels.cu) on plans with tiling tables
+                m2 = msrc != nullptr ? msrc[i * 32 + lane] : gather_mean32(a2, rg, gv.src_col, 1.f, lane);
                 if (lane == 0) mk = mask_out[node_grid(gv, i)];
                 else if (lane < 5) mk = mask[i * 4 + lane - 1];
             }
@@ -263,55 +295,66 @@ __global__ void __launch_bounds__(K2_THREADS, 2)
         // ---- stage B: tr = PReLU1([l1_t1_2(..) | l1_t2_2(..)]) --------------------------------------------------------
         {
             const float* W = sW + (br ? as::W12 : as::W11);
-            const float* B = sW + (br ? as::B12 : as::B11);
-            float acc[30];
-#pragma unroll
-            for (int o = 0; o < 30; ++o) acc[o] = B[o];
+            f32x2_t acc[15];
+            init2_30(acc, sW + (br ? as::B12 : as::B11));
 #pragma unroll 2
-            for (int k = 0; k < 30; ++k) fma_row30(acc, F[k * LDF + n], W + k * 32);
+            for (int k = 0; k < 30; ++k) fma2_row30(acc, F[k * LDF + n], W + k * 32);
             const float* Fm = F + (30 + 30 * br) * LDF;
 #pragma unroll 2
-            for (int k = 0; k < 30; ++k) fma_row30(acc, Fm[k * LDF + n], W + (30 + k) * 32);
+            for (int k = 0; k < 30; ++k) fma2_row30(acc, Fm[k * LDF + n], W + (30 + k) * 32);
 #pragma unroll
-            for (int k = 0; k < 5; ++k) fma_row30(acc, F[(90 + k) * LDF + n], W + (60 + k) * 32);
+            for (int k = 0; k < 5; ++k) fma2_row30(acc, F[(90 + k) * LDF + n], W + (60 + k) * 32);
             __syncthreads();   // every thread has finished reading rows 0-89
 #pragma unroll
-            for (int o = 0; o < 30; ++o) F[(br * 30 + o) * LDF + n] = prelu(acc[o], s_a1);
+            for (int o = 0; o < 15; ++o) {
+                float lo, hi;
+                unpack2(acc[o], lo, hi);
+                F[(br * 30 + 2 * o) * LDF + n] = prelu(lo, s_a1);
+                F[(br * 30 + 2 * o + 1) * LDF + n] = prelu(hi, s_a1);
+            }
         }
         __syncthreads();
         // ---- stage C: h = PReLU(l2_t*_1 tr);  v = W_agg h;  c = W_tr tr + W_m mask + b ---------------------------------
         {
             const float* Wa = sW + (br ? as::W22A : as::W21A);
-            const float* Ba = sW + (br ? as::B22A : as::B21A);
             const float ah = br ? s_a22 : s_a21;
-            float h[30];
-#pragma unroll
-            for (int o = 0; o < 30; ++o) h[o] = Ba[o];
+            f32x2_t h[15];
+            init2_30(h, sW + (br ? as::B22A : as::B21A));
+            const float* Wc = sW + (br ? as::WCB : as::WCA);
+            f32x2_t c[8];
+            init2_16(c, sW + (br ? as::BCB : as::BCA));
 #pragma unroll 2
-            for (int k = 0; k < 60; ++k) fma_row30(h, F[k * LDF + n], Wa + k * 32);
-            float v[16];
+            for (int k = 0; k < 60; ++k) {
+                const float x = F[k * LDF + n];
+                fma2_row30(h, x, Wa + k * 32);
+                fma2_row16(c, x, Wc + k * 16);
+            }
 #pragma unroll
-            for (int o = 0; o < 16; ++o) v[o] = 0.f;
+            for (int k = 0; k < 5; ++k) fma2_row16(c, F[(90 + k) * LDF + n], Wc + (60 + k) * 16);
+            f32x2_t v[8];
+#pragma unroll
+            for (int o = 0; o < 8; ++o) v[o] = pack2(0.f, 0.f);
             const float* Wv = sW + (br ? as::WVB : as::WVA);
 #pragma unroll
-            for (int k = 0; k < 30; ++k) fma_row16(v, prelu(h[k], ah), Wv + k * 16);
-            const float* Wc = sW + (br ? as::WCB : as::WCA);
-            const float* Bc = sW + (br ? as::BCB : as::BCA);
-            float c[16];
-#pragma unroll
-            for (int o = 0; o < 16; ++o) c[o] = Bc[o];
-#pragma unroll 2
-            for (int k = 0; k < 60; ++k) fma_row16(c, F[k * LDF + n], Wc + k * 16);
-#pragma unroll
-            for (int k = 0; k < 5; ++k) fma_row16(c, F[(90 + k) * LDF + n], Wc + (60 + k) * 16);
+            for (int k = 0; k < 15; ++k) {
+                float lo, hi;
+                unpack2(h[k], lo, hi);
+                fma2_row16(v, prelu(lo, ah), Wv + (2 * k) * 16);
+                fma2_row16(v, prelu(hi, ah), Wv + (2 * k + 1) * 16);
+            }
             const int64_t i = i0 + n;
             if (i < gv.P) {
                 float4* zp = reinterpret_cast<float4*>(zc + i * LD_ZC + br * 16);
                 float4* vp = reinterpret_cast<float4*>((br ? vb : va) + i * LD_V);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    zp[q] = make_float4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
-                    vp[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    float4 cz, vz;
+                    unpack2(c[2 * q], cz.x, cz.y);
+                    unpack2(c[2 * q + 1], cz.z, cz.w);
+                    unpack2(v[2 * q], vz.x, vz.y);
+                    unpack2(v[2 * q + 1], vz.z, vz.w);
+                    zp[q] = cz;
+                    vp[q] = vz;
                 }
             }
         }
@@ -334,6 +377,31 @@ __global__ void __launch_bounds__(256) assoc_layer2_kernel(const GraphView gv, c
         const float own = zc[i * LD_ZC + lane];
         const float mean = gather_mean16x2(va, vb, rs, rg, gv.sta_col, gv.src_col, lane);
         s_out[i * as::LD_S + lane] = (lane & 15) < 15 ? prelu(own + mean, a2) : 0.f;
+    }
+}
+
+// Same, on plans with tiling tables: the source half was pre-averaged by the source pass (m2src [P][16]), so only the
+// station half is gathered — by half-warps, two product nodes per warp pass.
+__global__ void __launch_bounds__(256) assoc_layer2_pre_kernel(const GraphView gv, const float* __restrict__ packed,
+                                                               const float* __restrict__ zc, const float* __restrict__ va,
+                                                               const float* __restrict__ m2src, float* __restrict__ s_out) {
+    const float a2 = packed[as::SL + as::SL_A2];
+    const int lane = threadIdx.x & 31, half = lane >> 4, l = lane & 15;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t n_pairs = (gv.P + 1) / 2;
+    for (int64_t pr = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pr < n_pairs; pr += warps) {
+        const int64_t i0 = 2 * pr, i1 = min(2 * pr + 1, gv.P - 1);        // an odd tail pair repeats its last node
+        NbrRange r0, r1, unused;
+        node_ranges(gv, i0, r0, unused);
+        node_ranges(gv, i1, r1, unused);
+        const float mean = gather_mean16x2(va, va, r0, r1, gv.sta_col, gv.sta_col, lane);
+        const int64_t i = half ? i1 : i0;
+        const float o1 = zc[i * LD_ZC + l] + mean;
+        const float o2 = zc[i * LD_ZC + 16 + l] + m2src[i * LD_V + l];
+        if (half == 0 || i1 != i0) {
+            s_out[i * as::LD_S + l] = l < 15 ? prelu(o1, a2) : 0.f;
+            s_out[i * as::LD_S + 16 + l] = l < 15 ? prelu(o2, a2) : 0.f;
+        }
     }
 }
 
@@ -434,6 +502,7 @@ AssocWorkspace carve_assoc_workspace(const genie_plan* p, void* base) {
     w.zc = take(P * 32);
     w.va = take(P * 16);
     w.vb = take(P * 16);
+    w.msrc = take(P * 32);
     w.yfc1 = take(G * 32);
     w.mask_out = take(G);
     w.bytes = off;
@@ -466,19 +535,31 @@ int launch_assoc_product(const genie_plan* p, const float* packed, const float* 
             gv, packed, w.yfc1, w.mask_out, edge_attr, x_latent, mask, s0_out, w.tr, w.a1, w.a2);
         GENIE_LAUNCH_CHECK();
     }
+    // plans with tiling tables: the two means over source neighbours come from the source pass of the front end
+    // (src_mean_kernels.cu: grouped grid nodes, every neighbour row read once from DRAM) instead of per-node L2 gathers
+    const bool split = split_supported(p);
+    int rc;
+    if (split && (rc = launch_src_mean(p, 32, w.a2, w.msrc, nullptr, st))) return rc;
     {
         const int64_t n_tiles = (P + TM - 1) / TM;
         const int64_t grid = n_tiles < (int64_t)p->sm_count * 2 ? n_tiles : (int64_t)p->sm_count * 2;
         TimedLaunch tl(KID_ASSOC_LAYER1, st);
-        assoc_layer1_kernel<<<(unsigned)grid, K2_THREADS, K2_SMEM, st>>>(gv, packed, w.tr, w.a1, w.a2, w.mask_out, mask, w.zc,
+        assoc_layer1_kernel<<<(unsigned)grid, K2_THREADS, K2_SMEM, st>>>(gv, packed, w.tr, w.a1, w.a2,
+                                                                        split ? w.msrc : nullptr, w.mask_out, mask, w.zc,
                                                                         w.va, w.vb, n_tiles);
         GENIE_LAUNCH_CHECK();
     }
+    float* m2src = split ? w.a1 : nullptr;             // a1 is dead after layer 1: [P][16] fits in its [P][32]
+    if (split && (rc = launch_src_mean(p, 16, w.vb, m2src, nullptr, st))) return rc;
     {
-        const int64_t blocks = (P + 7) / 8;
+        const int64_t blocks = split ? (P / 2 + 8) / 8 : (P + 7) / 8;
         const int64_t cap = (int64_t)p->sm_count * 16;
+        const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
         TimedLaunch tl(KID_ASSOC_LAYER2, st);
-        assoc_layer2_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(gv, packed, w.zc, w.va, w.vb, w.tr);
+        if (split)
+            assoc_layer2_pre_kernel<<<grid, 256, 0, st>>>(gv, packed, w.zc, w.va, m2src, w.tr);
+        else
+            assoc_layer2_kernel<<<grid, 256, 0, st>>>(gv, packed, w.zc, w.va, w.vb, w.tr);
         GENIE_LAUNCH_CHECK();
     }
     return GENIE_OK;

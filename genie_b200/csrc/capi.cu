@@ -188,6 +188,17 @@ int genie_plan_set_edge_terms(genie_plan_t* plan, const float* edge_sta_dev, con
     return GENIE_OK;
 }
 
+int genie_plan_set_init_terms(genie_plan_t* plan, const float* init_sta_dev, const float* init_src_dev) {
+    if (!plan || (init_sta_dev == nullptr && init_src_dev != nullptr) ||
+        (init_sta_dev != nullptr && (plan->g.mode == GENIE_GRAPH_CARTESIAN) != (init_src_dev != nullptr))) {
+        set_error("genie_plan_set_init_terms: CARTESIAN plans take a station and a grid table, EXPLICIT plans one per-node table");
+        return GENIE_ERR_INVALID;
+    }
+    plan->init_sta = init_sta_dev;
+    plan->init_src = init_src_dev;
+    return GENIE_OK;
+}
+
 int genie_debug_trace(int64_t* trace_dev, int tiles) {
     set_s1_trace(reinterpret_cast<long long*>(trace_dev), trace_dev ? tiles : 0);
     return GENIE_OK;

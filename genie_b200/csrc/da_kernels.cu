@@ -35,7 +35,8 @@ __constant__ float c_init[8 * LD + LD];
 __global__ void __launch_bounds__(K1_THREADS) da_init_kernel(const float* __restrict__ packed,
                                                              const float* __restrict__ slice,
                                                              const float* __restrict__ mask, float* __restrict__ tr0,
-                                                             int64_t P, int tc_plan) {
+                                                             int64_t P, int tc_plan, const float* __restrict__ init_sta,
+                                                             const float* __restrict__ init_src, int S) {
     __shared__ __align__(16) float sOut[K1_THREADS * LD_TR0];
     const float a0 = packed[DA_SLOPES + SL_A0];
     // tensor-core path (da_tc_kernels.cu): store p = PReLU12(tr0) instead of tr0
@@ -48,6 +49,25 @@ __global__ void __launch_bounds__(K1_THREADS) da_init_kernel(const float* __rest
     f32x2_t acc2[15];
 #pragma unroll
     for (int o = 0; o < 15; ++o) acc2[o] = pack2(c_init[8 * LD + 2 * o], c_init[8 * LD + 2 * o + 1]);
+    if (init_sta != nullptr && i < P) {
+        // use_absolute_pos (module.py:913-914): the six position channels of init_trns, by linearity a per-station plus a
+        // per-grid-node term (CARTESIAN) or one per-node term (EXPLICIT) added before the activation
+        const int64_t g = init_src != nullptr ? i / S : 0;
+        const float2* ts = reinterpret_cast<const float2*>(init_sta + (init_src != nullptr ? i - g * S : i) * 32);
+#pragma unroll
+        for (int o = 0; o < 15; ++o) {
+            const float2 v = __ldg(ts + o);
+            fadd2(acc2[o], pack2(v.x, v.y));
+        }
+        if (init_src != nullptr) {
+            const float2* tg = reinterpret_cast<const float2*>(init_src + g * 32);
+#pragma unroll
+            for (int o = 0; o < 15; ++o) {
+                const float2 v = __ldg(tg + o);
+                fadd2(acc2[o], pack2(v.x, v.y));
+            }
+        }
+    }
     if (i < P) {
         const float4 sv = __ldcs(reinterpret_cast<const float4*>(slice) + i);
         const float4 mv = __ldg(reinterpret_cast<const float4*>(mask) + i);
@@ -349,7 +369,8 @@ int launch_da_init(const genie_plan* p, const float* packed, const float* slice,
     const int64_t blocks = (P + K1_THREADS - 1) / K1_THREADS;
     GENIE_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_init, packed + DA_W0, sizeof(float) * (8 * LD + LD), 0, cudaMemcpyDeviceToDevice, st));
     TimedLaunch tl(KID_DA_INIT, st);
-    da_init_kernel<<<(unsigned)blocks, K1_THREADS, 0, st>>>(packed, slice, mask, tr0, P, tc_plan ? 1 : 0);
+    da_init_kernel<<<(unsigned)blocks, K1_THREADS, 0, st>>>(packed, slice, mask, tr0, P, tc_plan ? 1 : 0, p->init_sta,
+                                                            p->init_src, p->g.n_sta);
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;
 }

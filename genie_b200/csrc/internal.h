@@ -15,6 +15,9 @@ struct genie_plan {
     // Edge-feature model (genie_plan_set_edge_terms): per-node additive terms of layer 1, NULL = off.
     const float* edge_sta;  // [S or P][GENIE_EDGE_TERM_LD]
     const float* edge_src;  // [G or P][GENIE_EDGE_TERM_LD]
+    // use_absolute_pos (genie_plan_set_init_terms): additive terms of init_trns before its activation, NULL = off.
+    const float* init_sta;  // [S][32] (CARTESIAN) or [P][32] (EXPLICIT, init_src NULL)
+    const float* init_src;  // [G][32] or NULL
 };
 
 // Device-side view of the product graph.  CARTESIAN: node i = g*S + s; sta neighbours g*S + col, src neighbours
@@ -169,6 +172,7 @@ struct AssocWorkspace {
     float* zc;        // [P][32]
     float* va;        // [P][16]
     float* vb;        // [P][16]
+    float* msrc;      // [P][32]   mean over source neighbours of a2 (plans with tiling tables)
     float* yfc1;      // [G][32]   read-out fc1, y_latent half
     float* mask_out;  // [G]
     size_t bytes;

@@ -54,10 +54,11 @@ class DataAggregation(nn.Module):
 
     def __init__(self, in_channels, out_channels, n_hidden=30, n_dim_mask=4, use_absolute_pos=use_absolute_pos):
         super().__init__()
-        if use_absolute_pos:
-            raise NotImplementedError('genie_b200: use_absolute_pos=True is not supported yet')
         if (in_channels, out_channels, n_hidden, n_dim_mask) != (4, 15, 30, 4):
             raise NotImplementedError('genie_b200: DataAggregation is built for (4, 15, n_hidden=30, n_dim_mask=4)')
+        self.use_absolute_pos = bool(use_absolute_pos)
+        if use_absolute_pos:
+            in_channels = in_channels + 3 * 2         # module.py:56-57: station and source positions join Slice
         self.in_channels, self.out_channels, self.n_hidden = in_channels, out_channels, n_hidden
         ne = self.n_edge
         self.activate = nn.PReLU()
@@ -241,8 +242,11 @@ class DataAggregationAssociationPhase(nn.Module):
 
     n_edge = 0
 
-    def __init__(self, in_channels, out_channels, n_hidden=30, n_dim_latent=30, n_dim_mask=5):
+    def __init__(self, in_channels, out_channels, n_hidden=30, n_dim_latent=30, n_dim_mask=5,
+                 use_absolute_pos=use_absolute_pos):
         super().__init__()
+        if use_absolute_pos:
+            in_channels = in_channels + 2 * 3          # module.py:361-362
         ne = self.n_edge
         self.activate = nn.PReLU()
         self.init_trns = nn.Linear(in_channels + n_dim_latent + n_dim_mask, n_hidden)
@@ -404,9 +408,8 @@ class GCN_Detection_Network_extended(nn.Module):
                  updated_model=None):
         super().__init__()
         self.updated_model = use_updated_model_definition if updated_model is None else bool(updated_model)
-        if use_absolute_pos:
-            raise NotImplementedError('genie_b200: use_absolute_pos=True is not supported yet')
-        self.DataAggregation = (DataAggregationEdges if self.updated_model else DataAggregation)(4, 15).to(device)
+        self.DataAggregation = (DataAggregationEdges if self.updated_model else DataAggregation)(
+            4, 15, use_absolute_pos=use_absolute_pos).to(device)
         self.Bipartite_ReadIn = BipartiteGraphOperator(30, 15, ndim_edges=3).to(device)
         self.SpatialAggregation1 = SpatialAggregation(15, 30, scale_rel=scale_rel).to(device)
         self.SpatialAggregation2 = SpatialAggregation(30, 30, scale_rel=scale_rel).to(device)
@@ -416,7 +419,8 @@ class GCN_Detection_Network_extended(nn.Module):
         self.TemporalAttention = TemporalAttention(30, 1, 15).to(device)
         self.BipartiteGraphReadOutOperator = BipartiteGraphReadOutOperator(30, 15).to(device)
         self.DataAggregationAssociationPhase = (DataAggregationAssociationPhaseEdges if self.updated_model
-                                                else DataAggregationAssociationPhase)(15, 15).to(device)
+                                                else DataAggregationAssociationPhase)(
+            15, 15, use_absolute_pos=use_absolute_pos).to(device)
         self.LocalSliceLgCollapseP = LocalSliceLgCollapse(30, 15, device=device).to(device)
         self.LocalSliceLgCollapseS = LocalSliceLgCollapse(30, 15, device=device).to(device)
         self.Arrivals = StationSourceAttentionMergedPhases(30, 15, 2, 15, n_heads=3, device=device).to(device)
@@ -432,6 +436,7 @@ class GCN_Detection_Network_extended(nn.Module):
         self._read_out_key, self._read_out_attr = None, None
         self._edge_means = None       # updated model: (means_sta(scale), means_src(scale)) of the current plan
         self._edge_terms = None       # (key, t_sta, t_src, re-laid weight tensors)
+        self._init_terms = None       # use_absolute_pos: (key, re-laid init_trns weight [30,8])
 
     # -- graph plans ---------------------------------------------------------------------------------------------------
     def set_adjacencies(self, A_in_sta, A_in_src, A_src_in_edges, A_Lg_in_src, A_src_in_sta, A_src, A_edges_p, A_edges_s,
@@ -448,15 +453,19 @@ class GCN_Detection_Network_extended(nn.Module):
         self._set_edge_means(pos_loc, pos_src, A_src_in_sta)
 
     def set_adjacencies_cartesian(self, A_sta_sta, A_src_src, read_in_attr, n_sta, n_grid, device=None, pos_loc=None,
-                                  pos_src=None):
+                                  pos_src=None, A_edges_p=None, A_edges_s=None, dt_partition=None, tlatent=None):
         """Dense mode without ever materialising the product edge lists (needed beyond a few 10^7 product nodes):
         the two kNN graphs of process_utils.py:718-719 and the read-in edge features `A_src_in_edges.x` [P,3]
-        (+ the Cartesian station / grid positions for the updated model's edge features)."""
+        (+ the Cartesian station / grid positions for the updated model's edge features, and the time-pointer tables of
+        the association branch when forward_fixed is going to be called)."""
         device = device if device is not None else read_in_attr.device
         self._plan = GraphPlan.cartesian(A_sta_sta, A_src_src, n_sta, n_grid, device=device)
         self._read_in_attr = read_in_attr.to(device).float().contiguous()
         self.A_src = A_src_src
         self._plan_key = None
+        # association inputs (forward_fixed): the read-out graph A_Lg_in_src is the implicit [g(i); i] with the read-in features
+        self.A_Lg_in_src, self.A_edges_p, self.A_edges_s = None, A_edges_p, A_edges_s
+        self.dt_partition, self.tlatent = dt_partition, tlatent
         self._set_edge_means(pos_loc, pos_src, None)
 
     def _set_edge_means(self, pos_loc, pos_src, A_src_in_sta):
@@ -517,7 +526,7 @@ class GCN_Detection_Network_extended(nn.Module):
         return self._plan
 
     # -- CUDA front end ------------------------------------------------------------------------------------------------
-    def _packed_weights(self, dev):
+    def _packed_weights(self, dev, init_relaid=None):
         if self._packed is None or self._packed.device != torch.device(dev):
             self._packed = ops.PackedWeights(dev)
         relaid = None
@@ -525,9 +534,40 @@ class GCN_Detection_Network_extended(nn.Module):
             if self._edge_means is None:
                 raise RuntimeError('set_adjacencies must be called before the weights of the updated model are packed')
             relaid = self._update_edge_terms()[3]
-        return self._packed.update(self, relaid)
+        return self._packed.update(self, relaid, init_relaid)
 
-    def front_end(self, Slice, Mask, x_temp_cuda_cart, want_latent=False, want_readin=False):
+    def _update_init_terms(self, locs_use_cart, x_temp_cuda_cart):
+        """use_absolute_pos (module.py:913-914): tables of genie_plan_set_init_terms + init_trns without its six position
+        columns.  Rebuilt when the weight, the positions, scale_rel or the plan change."""
+        w = self.DataAggregation.init_trns.weight
+        plan = self._plan
+        key = (w.data_ptr(), w._version, locs_use_cart.data_ptr(), locs_use_cart._version, x_temp_cuda_cart.data_ptr(),
+               x_temp_cuda_cart._version, float(self.scale_rel), id(plan))
+        if self._init_terms is not None and self._init_terms[0] == key:
+            return self._init_terms[1]
+        wd = w.detach()
+        sc = 3.0 * float(self.scale_rel)
+
+        def table(pos, cols):
+            t = torch.zeros((pos.shape[0], 32), dtype=torch.float32, device=wd.device)
+            t[:, :30] = (pos.to(wd.device).float() / sc) @ wd[:, cols].t()
+            return t
+        t_sta, t_src = table(locs_use_cart, slice(4, 7)), table(x_temp_cuda_cart, slice(7, 10))
+        if plan.mode == capi.GRAPH_CARTESIAN:
+            if t_sta.shape[0] != plan.n_sta or t_src.shape[0] != plan.n_grid:
+                raise capi.GenieError('use_absolute_pos: locs_use_cart / x_temp_cuda_cart do not match the plan')
+            plan.set_init_terms(t_sta.contiguous(), t_src.contiguous())
+        else:
+            idx = getattr(self, 'A_src_in_sta', None)
+            if idx is None:
+                raise capi.GenieError('use_absolute_pos on an explicit product graph needs A_src_in_sta (set_adjacencies)')
+            idx = idx.to(wd.device).long()
+            plan.set_init_terms((t_sta[idx[0]] + t_src[idx[1]]).contiguous(), None)
+        relaid = torch.cat((wd[:, 0:4], wd[:, 10:14]), dim=1).contiguous()
+        self._init_terms = (key, relaid)
+        return relaid
+
+    def front_end(self, Slice, Mask, x_temp_cuda_cart, want_latent=False, want_readin=False, locs_use_cart=None):
         """DataAggregation -> Bipartite_ReadIn -> SpatialAggregation1..3 in libgenie_b200 (module.py:1010-1014)."""
         if self._plan is None:
             raise RuntimeError('set_adjacencies must be called before forward_fixed*')
@@ -538,7 +578,12 @@ class GCN_Detection_Network_extended(nn.Module):
                 and self.training:
             raise NotImplementedError('genie_b200: backward of the CUDA front end is not implemented yet; '
                                       'call under torch.no_grad() / model.eval()')
-        packed = self._packed_weights(Slice.device)
+        init_relaid = None
+        if self.use_absolute_pos:
+            if locs_use_cart is None:
+                raise capi.GenieError('use_absolute_pos: the front end needs locs_use_cart')
+            init_relaid = self._update_init_terms(locs_use_cart, x_temp_cuda_cart)
+        packed = self._packed_weights(Slice.device, init_relaid)
         return ops.frontend_fwd(self._plan, packed, Slice, Mask, self._read_in_attr, x_temp_cuda_cart,
                                 float(self.scale_rel), want_latent=want_latent, want_readin=want_readin)
 
@@ -563,7 +608,7 @@ class GCN_Detection_Network_extended(nn.Module):
                              x_query_cart, t_query):
         """module.py:999-1020 -> (y [G,T,1], x [Q,T,1])."""
         with torch.no_grad():
-            x_spatial = self.front_end(Slice, Mask, x_temp_cuda_cart)[0]
+            x_spatial = self.front_end(Slice, Mask, x_temp_cuda_cart, locs_use_cart=locs_use_cart)[0]
             return self._heads(x_spatial, x_temp_cuda_cart, x_query_cart, t_query)
 
     # -- association branch (SURVEY.md §8f rank 2) -----------------------------------------------------------------------
@@ -591,13 +636,20 @@ class GCN_Detection_Network_extended(nn.Module):
         if self.updated_model:
             raise NotImplementedError('genie_b200: the association branch of the updated model definition '
                                       '(DataAggregationAssociationPhaseEdges, module.py:406) is not built')
+        if self.use_absolute_pos:
+            raise NotImplementedError('genie_b200: the association branch with use_absolute_pos=True is not built')
         if not ops.AssocWeights.supported(self):
             raise NotImplementedError('genie_b200: the association kernels are built for the reference\'s module shapes')
         with torch.no_grad():
             x_spatial, x_latent, _ = self.front_end(Slice, Mask, x_temp_cuda_cart, want_latent=True)
             y, x = self._heads(x_spatial, x_temp_cuda_cart, x_query_cart, t_query)
             x_src = self.SpatialAttention(x_spatial, x_query_src_cart, x_temp_cuda_cart, cache=False)         # :980
-            attr = self._check_read_out_graph(A_Lg_in_src)
+            if A_Lg_in_src is None and self._plan.mode == capi.GRAPH_CARTESIAN:
+                attr = self._read_in_attr                      # set_adjacencies_cartesian: implicit read-out graph
+            else:
+                attr = self._check_read_out_graph(A_Lg_in_src)
+            if A_edges_p is None or A_edges_s is None or dt_partition is None or tlatent is None:
+                raise RuntimeError('forward_fixed needs A_edges_p, A_edges_s, dt_partition and tlatent (set_adjacencies)')
             dev = x_spatial.device
             if self._assoc_w is None or self._assoc_w.device != dev:
                 self._assoc_w = ops.AssocWeights(dev)

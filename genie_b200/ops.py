@@ -39,7 +39,7 @@ class PackedWeights(object):
             ts += [sa.fc1, sa.fc2, sa.fglobal, sa.activate1, sa.activate2, sa.activate3]
         return da, ri, sas, ts
 
-    def update(self, model, relaid=None):
+    def update(self, model, relaid=None, init_relaid=None):
         """`relaid`: updated model definition only — (l1_t1_2, l1_t2_2, l2_t1_2, l2_t2_2) weights without their four
         edge-feature columns ([30,64] / [15,94]); those columns live in the plan's edge-term tables."""
         da, ri, sas, mods = self._sources(model)
@@ -48,6 +48,8 @@ class PackedWeights(object):
         key = tuple((p.data_ptr(), p._version) for p in self._plist)
         if relaid is not None:
             key = key + tuple(t.data_ptr() for t in relaid)
+        if init_relaid is not None:                 # use_absolute_pos: init_trns without its six position columns [30,8]
+            key = key + (init_relaid.data_ptr(),)
         if key == self._key:
             return self.buf
         for m in mods:
@@ -59,6 +61,11 @@ class PackedWeights(object):
                      ('da_l2_t1_1', da.l2_t1_1), ('da_l2_t2_1', da.l2_t2_1), ('da_l2_t1_2', da.l2_t1_2),
                      ('da_l2_t2_2', da.l2_t2_2), ('ri_fc1', ri.fc1), ('ri_fc2', ri.fc2)):
             _lin(ws, f, m)
+        if init_relaid is not None:
+            ws.da_init_trns.weight = capi.dptr(init_relaid, F32, 'da_init_trns.weight (re-laid)')
+            self._init_relaid = init_relaid         # keep the tensor alive
+        elif da.init_trns.weight.shape[1] != 8:
+            raise capi.GenieError('init_trns of a use_absolute_pos model needs its re-laid copy')
         if relaid is not None:
             for f, t in zip(('da_l1_t1_2', 'da_l1_t2_2', 'da_l2_t1_2', 'da_l2_t2_2'), relaid):
                 getattr(ws, f).weight = capi.dptr(t, F32, f + '.weight (re-laid)')

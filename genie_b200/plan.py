@@ -285,6 +285,17 @@ class GraphPlan(object):
                                                              capi.dptr(t_src, torch.float32, 'edge_src')))
         self._edge_terms = (t_sta, t_src)              # keep the tensors alive
 
+    def set_init_terms(self, t_sta, t_src):
+        """genie_plan_set_init_terms (use_absolute_pos): [S,32] + [G,32] (CARTESIAN) or [P,32] + None (EXPLICIT); None, None = off."""
+        if t_sta is not None:
+            rows = (self.n_sta, self.n_grid) if self.mode == capi.GRAPH_CARTESIAN else (self.n_prod, None)
+            if tuple(t_sta.shape) != (rows[0], 32) or (rows[1] is None) != (t_src is None) or \
+                    (t_src is not None and tuple(t_src.shape) != (rows[1], 32)):
+                raise capi.GenieError('init-term tables must be [%s, 32] and [%s, 32]' % rows)
+        capi.check(capi.load().genie_plan_set_init_terms(self.handle, capi.dptr(t_sta, torch.float32, 'init_sta'),
+                                                         capi.dptr(t_src, torch.float32, 'init_src')))
+        self._init_terms = (t_sta, t_src)              # keep the tensors alive
+
     def node_grid_index(self):
         """int64 [P]: grid node of every product node (CARTESIAN: i // n_sta; EXPLICIT: the read-in target list)."""
         if self.prod_grid is not None:

@@ -115,6 +115,14 @@ GENIE_API void genie_plan_destroy(genie_plan_t* plan);
  * them in set_adjacencies / whenever the weights change. */
 #define GENIE_EDGE_TERM_LD 48
 GENIE_API int genie_plan_set_edge_terms(genie_plan_t* plan, const float* edge_sta_dev, const float* edge_src_dev);
+/* `use_absolute_pos: True` (module.py:913-914, 56-57): Slice gains the six channels [locs_use_cart[s] | x_temp_cuda_cart[g]] /
+ * (3 scale_rel) before init_trns (4+6+4 inputs).  They do not depend on the window, so — exact, by linearity — they reduce to
+ * additive terms of init_trns before its activation:
+ *   CARTESIAN plans: init_sta_dev [S][32] = init_trns.weight[:, 4:7] . locs[s] / (3 scale_rel)   (30 used, padding zero)
+ *                    init_src_dev [G][32] = init_trns.weight[:, 7:10] . x_temp[g] / (3 scale_rel)
+ *   EXPLICIT plans:  init_sta_dev [P][32] = the sum of the two for the node's (station, grid node); init_src_dev NULL.
+ * The weights structure then carries init_trns WITHOUT those six columns ([30][8]).  Tables are the caller's; NULL, NULL = off. */
+GENIE_API int genie_plan_set_init_terms(genie_plan_t* plan, const float* init_sta_dev, const float* init_src_dev);
 /* Bytes of caller-provided scratch the forward entry points need for this plan (intermediate node features). */
 GENIE_API size_t genie_plan_workspace_bytes(const genie_plan_t* plan);
 

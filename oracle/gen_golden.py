@@ -2,6 +2,7 @@
 
     python oracle/gen_golden.py synthetic      # seeded synthetic networks, reference default-initialised weights
     python oracle/gen_golden.py synthetic_edges  # same, `use_updated_model_definition: True` (DataAggregationEdges)
+    python oracle/gen_golden.py synthetic_abspos # same, `use_absolute_pos: True` (station / source positions join Slice)
     python oracle/gen_golden.py legacy_input     # a1': extract_inputs_from_data_fixed_grids_with_phase_type
     python oracle/gen_golden.py association      # forward_fixed incl. the association branch
     python oracle/gen_golden.py ferndale       # Examples/Ferndale.zip: real stations/grids/picks + trained checkpoint
@@ -105,7 +106,7 @@ def _run_reference_window(torch, module, pu, Data, mz, locs, ind_use, grid, trv_
     return res
 
 
-def synthetic(edges=False):
+def synthetic(edges=False, abs_pos=False):
     """edges=True: the reference's `use_updated_model_definition: True` classes (DataAggregationEdges, module.py:102-174,
     1024-1111); the YAML copy in the scratch directory is switched, the reference sources are untouched."""
     work = tempfile.mkdtemp(prefix='genie_golden_')
@@ -117,8 +118,14 @@ def synthetic(edges=False):
         cfg, n = re.subn(r'(?m)^use_updated_model_definition:\s*\w+', 'use_updated_model_definition: True', cfg)
         assert n == 1
         open(os.path.join(work, 'config.yaml'), 'w').write(cfg)
+    if abs_pos:
+        import re
+        cfg = open(os.path.join(work, 'config.yaml')).read()
+        cfg, n = re.subn(r'(?m)^use_absolute_pos:\s*\w+', 'use_absolute_pos: True', cfg)
+        assert n == 1
+        open(os.path.join(work, 'config.yaml'), 'w').write(cfg)
     torch, module, pu, Data = _import_reference(os.path.join(REF, 'Code'), work)
-    assert bool(module.use_updated_model_definition) == edges
+    assert bool(module.use_updated_model_definition) == edges and bool(module.use_absolute_pos) == abs_pos
     from genie_b200 import synth
 
     def identity(x):
@@ -129,6 +136,8 @@ def synthetic(edges=False):
         ('mid_36of40x300', 40, 36, 300, 8, 15, 128, 3),     # station subset (ind_use != arange), k_s < S-2
         ('small_6x40', 6, 6, 40, 8, 15, 16, 5),             # k_sta clipped to S-2 (process_utils.py:712)
     ]
+    if abs_pos:
+        cases = [('c1_10x100_abspos', 10, 10, 100, 8, 15, 64, 0), ('mid_36of40x300_abspos', 40, 36, 300, 8, 15, 128, 3)]
     if edges:
         cases = [('c1_10x100_edges', 10, 10, 100, 8, 15, 64, 0), ('mid_36of40x300_edges', 40, 36, 300, 8, 15, 128, 3)]
     for name, S_all, n_use, G, k_sta, k_spc, Q, seed in cases:
@@ -327,6 +336,8 @@ if __name__ == '__main__':
         synthetic()
     elif mode == 'synthetic_edges':
         synthetic(edges=True)
+    elif mode == 'synthetic_abspos':
+        synthetic(abs_pos=True)
     elif mode == 'legacy_input':
         legacy_input()
     elif mode == 'association':

@@ -381,10 +381,18 @@ def temporal_attention(sd, pre, x, t_query, scale_t, n_heads=5, n_latent=15):
     return _lin(sd, pre + 'proj_2', _prelu(sd, pre + 'activate5', _lin(sd, pre + 'proj_1', z)))
 
 
+def absolute_pos_channels(Slice, locs_cart, grid_cart, A_src_in_sta, scale_rel):
+    """`use_absolute_pos: True`, module.py:913-914: Slice gains [station position | source position] / (3 scale_rel)."""
+    return torch.cat((Slice, locs_cart[A_src_in_sta[0]] / (3.0 * scale_rel), grid_cart[A_src_in_sta[1]] / (3.0 * scale_rel)),
+                     dim=1)
+
+
 def front_end(sd, Slice, Mask, A_in_sta, A_in_src, read_in_attr, read_in_index, A_src, grid_cart, scale_rel,
-              return_parts=False, pos_rel=None):
+              return_parts=False, pos_rel=None, abs_pos=None):
     """a2 -> a3 -> a4 x3: the product-graph front end of module.py:1010-1014.  `pos_rel` = (pos_rel_sta, pos_rel_src) selects
     the `use_updated_model_definition: True` DataAggregationEdges (module.py:1176)."""
+    if abs_pos is not None:              # (locs_cart, A_src_in_sta): the `use_absolute_pos: True` input channels
+        Slice = absolute_pos_channels(Slice, abs_pos[0], grid_cart, abs_pos[1], scale_rel)
     if pos_rel is not None:
         x_latent = data_aggregation_edges(sd, 'DataAggregation.', Slice, Mask, A_in_sta, A_in_src, pos_rel[0], pos_rel[1])
     else:
@@ -399,10 +407,11 @@ def front_end(sd, Slice, Mask, A_in_sta, A_in_src, read_in_attr, read_in_index, 
 
 
 def forward_fixed_source(sd, Slice, Mask, A_in_sta, A_in_src, read_in_attr, read_in_index, A_src, grid_cart,
-                         x_query_cart, t_query, scale_rel, scale_t, return_parts=False, query_edges=None, pos_rel=None):
+                         x_query_cart, t_query, scale_rel, scale_t, return_parts=False, query_edges=None, pos_rel=None,
+                         abs_pos=None):
     """module.py:999-1020 / 1165-1186 (use_absolute_pos False): returns y [G,T,1] and x [Q,T,1]."""
     x_spatial, parts = front_end(sd, Slice, Mask, A_in_sta, A_in_src, read_in_attr, read_in_index, A_src, grid_cart,
-                                 scale_rel, return_parts=True, pos_rel=pos_rel)
+                                 scale_rel, return_parts=True, pos_rel=pos_rel, abs_pos=abs_pos)
     y_latent = spatial_direct(sd, 'SpatialDirect.', x_spatial)
     y = temporal_attention(sd, 'TemporalAttention.', y_latent, t_query, scale_t)
     xq = spatial_attention(sd, 'SpatialAttention.', x_spatial, x_query_cart, grid_cart, scale_rel,

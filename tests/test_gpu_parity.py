@@ -688,3 +688,45 @@ def test_association_matches_oracle_seeded(explicit):
     assert rel_err(y.cpu().numpy(), want[0].numpy()) < TOL and rel_err(x.cpu().numpy(), want[1].numpy()) < TOL
     assert rel_err(arv_p.cpu().numpy(), want[2].numpy()) < TOL
     assert rel_err(arv_s.cpu().numpy(), want[3].numpy()) < TOL
+
+
+# ---- use_absolute_pos: True (module.py:913-914) --------------------------------------------------------------------------
+
+def _abspos_model(sd, dev, d):
+    from genie_b200.module import GCN_Detection_Network_extended
+    m = GCN_Detection_Network_extended(None, None, scale_rel=float(d['scale_rel']), use_absolute_pos=True, device=dev)
+    m.load_state_dict(sd)
+    m.TemporalAttention.scale_t = float(d['scale_t'])
+    return m.eval()
+
+
+@pytest.mark.parametrize('name', ['c1_10x100_abspos', 'mid_36of40x300_abspos'])
+@pytest.mark.parametrize('explicit', [False, True])
+def test_absolute_pos_matches_reference(name, explicit):
+    """The six position channels of init_trns as per-station / per-grid-node additive terms (genie_plan_set_init_terms) on a
+    CARTESIAN plan, and as per-product-node terms on an EXPLICIT plan (shuffled edge list), against the unmodified reference."""
+    from genie_b200 import capi
+    from oracle.refshim.torch_geometric.data import Data
+    dev = _dev()
+    d, sd = load_golden(name)
+    A_sta, A_src, A_ps, A_pg, A_sip, A_sis = _graphs(d)
+    m = _abspos_model(sd, dev, d)
+    t = lambda k: torch.from_numpy(d[k]).to(dev)
+    locs = torch.from_numpy(d['sta'][d['ind_use']]).float().to(dev)
+    grid = torch.from_numpy(d['grid']).float().to(dev)
+    if explicit:
+        A_ps = A_ps[:, torch.randperm(A_ps.shape[1], generator=torch.Generator().manual_seed(1))]
+    m.set_adjacencies(A_ps.to(dev), A_pg.to(dev), Data(x=t('read_in_attr'), edge_index=A_sip.to(dev)), None, A_sis.to(dev),
+                      A_src.to(dev), None, None, None, None, locs, grid)
+    assert m._plan.mode == (capi.GRAPH_EXPLICIT if explicit else capi.GRAPH_CARTESIAN)
+    xs, lat, _ = m.front_end(t('Slice'), t('Mask'), grid, want_latent=True, locs_use_cart=locs)
+    assert rel_err(lat.cpu().numpy(), d['x_latent']) < TOL
+    assert rel_err(xs.cpu().numpy(), d['x_spatial']) < TOL
+    y, x = m.forward_fixed_source(t('Slice'), t('Mask'), None, None, None, locs, grid,
+                                  torch.from_numpy(d['x_query']).float().to(dev),
+                                  torch.from_numpy(d['t_query']).float().reshape(-1, 1).to(dev))
+    assert rel_err(y.cpu().numpy(), d['y']) < TOL and rel_err(x.cpu().numpy(), d['x']) < TOL
+    # a changed scale_rel / weight must refresh the tables (no stale cache)
+    m.scale_rel = 2.0 * float(d['scale_rel'])
+    lat2 = m.front_end(t('Slice'), t('Mask'), grid, want_latent=True, locs_use_cart=locs)[1]
+    assert rel_err(lat2.cpu().numpy(), d['x_latent']) > 1e-3

@@ -155,3 +155,20 @@ def test_association_branch_matches_reference(name):
     assert rel_err(y.numpy(), d['y']) < 5e-6 and rel_err(x.numpy(), d['x']) < 5e-6
     assert rel_err(arv_p.numpy(), d['arv_p']) < 5e-6 and rel_err(arv_s.numpy(), d['arv_s']) < 5e-6
     assert arv_p.shape == (len(d['tq_sample']), len(d['tpick']), 1)
+
+
+@pytest.mark.parametrize('name', ['c1_10x100_abspos', 'mid_36of40x300_abspos'])
+def test_absolute_pos_matches_reference(name):
+    """`use_absolute_pos: True` (module.py:913-914): init_trns takes 14 inputs."""
+    d, sd = load_golden(name)
+    assert tuple(sd['DataAggregation.init_trns.weight'].shape) == (30, 14)
+    S, G, A_sta, A_src, A_ps, A_pg, A_sip, A_sis = _graphs(d)
+    locs = torch.from_numpy(d['sta'][d['ind_use']]).float()
+    y, x, parts = go.forward_fixed_source(
+        sd, torch.from_numpy(d['Slice']), torch.from_numpy(d['Mask']), A_ps, A_pg, torch.from_numpy(d['read_in_attr']), A_sip,
+        A_src, torch.from_numpy(d['grid']).float(), torch.from_numpy(d['x_query']).float(),
+        torch.from_numpy(d['t_query']).float().reshape(-1, 1), float(d['scale_rel']), float(d['scale_t']),
+        return_parts=True, abs_pos=(locs, A_sis))
+    for key in ('x_latent', 'read_in', 'x_spatial'):
+        assert rel_err(parts[key].numpy(), d[key]) < 2e-6, key
+    assert rel_err(y.numpy(), d['y']) < 2e-6 and rel_err(x.numpy(), d['x']) < 2e-6
