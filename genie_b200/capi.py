@@ -17,7 +17,7 @@ _LIB_PATH = os.path.join(_HERE, 'libgenie_b200.so')
 _lib = None
 
 GRAPH_CARTESIAN, GRAPH_EXPLICIT = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 EDGE_TERM_LD = 48           # GENIE_EDGE_TERM_LD
 
 c_f32p = ctypes.c_void_p   # device pointers are passed as opaque addresses
@@ -97,6 +97,7 @@ SIGNATURES = {
     'genie_heads_grid_fwd': (ctypes.c_int, [_P, _P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int, _P, _P]),
     'genie_heads_query_fwd': (ctypes.c_int, [_P, _P, ctypes.c_int, _P, ctypes.c_int, _P, _P, _P, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_float, _P, _P]),
+    'genie_knn_fwd': (ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int, _P, _P]),
     'genie_assoc_packed_floats': (ctypes.c_size_t, []),
     'genie_assoc_layout': (ctypes.c_int, [_P, ctypes.c_int]),
     'genie_assoc_workspace_bytes': (ctypes.c_size_t, [_P]),

@@ -35,7 +35,7 @@ const char* const kKernelNames[KID_COUNT] = {"pack_weights_kernel", "input_serie
                                              "src_mean32_kernel",   "src_mean16_kernel",   "da_layer1_s_kernel",
                                              "da_layer2_s_kernel",  "heads_grid_kernel",   "heads_query_kernel",
                                              "assoc_grid_pre_kernel", "assoc_init_kernel", "assoc_layer1_kernel",
-                                             "assoc_layer2_kernel", "assoc_collapse_kernel"};
+                                             "assoc_layer2_kernel", "assoc_collapse_kernel", "knn_kernel"};
 }  // namespace
 
 TimedLaunch::TimedLaunch(int kid_, cudaStream_t st_) : kid(kid_), st(st_), slot(nullptr) {
@@ -361,6 +361,15 @@ int genie_input_nearest_fwd(const genie_nearest_params_t* prm, const double* tim
     }
     return launch_input_nearest(prm, times_all_dev, times_p_dev, times_s_dev, ind_use_dev, trv_times_dev, slice_out_dev,
                                 mask_out_dev, static_cast<cudaStream_t>(stream));
+}
+
+// ---- device kNN -------------------------------------------------------------------------------------
+int genie_knn_fwd(const float* x_dev, int n_x, const float* y_dev, int n_y, int k, int64_t* idx_out_dev, void* stream) {
+    if (n_x < 0 || n_y < 0 || k < 1 || k > 32 || k > n_x || (n_x > 0 && !x_dev) || (n_y > 0 && (!y_dev || !idx_out_dev))) {
+        set_error("genie_knn_fwd: bad argument (1 <= k <= min(32, n_x))");
+        return GENIE_ERR_INVALID;
+    }
+    return launch_knn(x_dev, n_x, y_dev, n_y, k, idx_out_dev, static_cast<cudaStream_t>(stream));
 }
 
 // ---- association branch ---------------------------------------------------------------------------

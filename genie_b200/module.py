@@ -128,18 +128,13 @@ class SpatialDirect(nn.Module):
         return self.activate(self.f_direct(inpts))
 
 
-def knn_query_edges(x_context, x_query, k, chunk=4096):
-    """`knn(x_context/1000, x_query/1000, k).flip(0)` (module.py:282) without torch_cluster: brute force on the device.
+def knn_query_edges(x_context, x_query, k):
+    """`knn(x_context/1000, x_query/1000, k).flip(0)` (module.py:282) without torch_cluster: libgenie_b200's brute-force
+    kNN kernel (genie_knn_fwd).
 
     Returns int64 [2, Q*k]: row 0 = context (source) index, nearest first, row 1 = query (target) index."""
-    xc, xq = x_context / 1000.0, x_query / 1000.0
-    k = min(k, xc.shape[0])
-    idx = []
-    for q0 in range(0, xq.shape[0], chunk):
-        d = torch.cdist(xq[q0:q0 + chunk].double(), xc.double())
-        idx.append(torch.topk(d, k, dim=1, largest=False, sorted=True)[1])
-    idx = torch.cat(idx, dim=0) if idx else torch.zeros((0, k), dtype=torch.long, device=xc.device)
-    tgt = torch.arange(xq.shape[0], device=xc.device).repeat_interleave(k)
+    idx = ops.knn(x_context / 1000.0, x_query / 1000.0, k)
+    tgt = torch.arange(x_query.shape[0], device=x_context.device).repeat_interleave(idx.shape[1])
     return torch.stack((idx.reshape(-1), tgt), dim=0)
 
 

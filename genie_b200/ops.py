@@ -328,6 +328,21 @@ def assoc_collapse_fwd(packed, s_rows, A_edges_p, A_edges_s, dt_partition, tlate
     return arrival
 
 
+def knn(x, y, k):
+    """torch_cluster.knn(x, y, k) on the device (genie_knn_fwd): int64 [n_y, k], the k rows of x nearest to every row of y,
+    nearest first.  x, y: fp32 CUDA tensors [n, 3] (kilometres, as the reference passes them)."""
+    x, y = _f32c(x, 'x'), _f32c(y, 'y')
+    if x.dim() != 2 or y.dim() != 2 or x.shape[1] != 3 or y.shape[1] != 3:
+        raise capi.GenieError('knn: points must be [n, 3]')
+    k = int(min(k, x.shape[0]))
+    out = torch.empty((y.shape[0], k), dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        capi.check(capi.load().genie_knn_fwd(capi.dptr(x, F32, 'x'), int(x.shape[0]), capi.dptr(y, F32, 'y') if y.shape[0] else None,
+                                             int(y.shape[0]), k, capi.dptr(out) if y.shape[0] else None,
+                                             capi.stream_ptr(x.device)))
+    return out
+
+
 def _f32c(t, name):
     if t.dtype != F32:
         t = t.float()

@@ -3,7 +3,7 @@
 * `extract_input_from_data`  — same signature and return structure as process_utils.py:460, but the per-station series,
   the travel-time-shifted gather and Slice/Mask live on the GPU (libgenie_b200 `genie_input_scatter_fwd`).
 * `extract_inputs_adjacencies` — the dense-mode graph builder of process_utils.py:701-742.  kNN graphs are static per
-  station set and are built on the host with a k-d tree (acceptable until the device kNN lands).
+  station set; `device=` runs the searches in libgenie_b200's kNN kernel (genie_knn_fwd), otherwise a host k-d tree is used.
 * `InputExtractor` — the streaming form used by bench.py: travel times, station tables and (optionally) a whole day of
   picks stay resident in HBM; one call per window.
 """
@@ -29,9 +29,24 @@ def knn_graph(pos_km, k):
     return torch.from_numpy(np.stack((src[keep], tgt[keep]), axis=0)).long()
 
 
-def extract_inputs_adjacencies_cartesian(locs_cart, grid_cart, k_sta_edges, k_spc_edges):
-    """The two small graphs of process_utils.py:712-719 for Cartesian coordinates in metres."""
+def knn_graph_device(pos_km, k):
+    """knn_graph on the device (genie_knn_fwd): pos_km fp32 CUDA tensor [n,3] -> int64 [2,E] on the same device, edges
+    grouped by target, nearest source first — the order `knn(x, x, k+1).flip(0)` + remove_self_loops produces."""
+    n = pos_km.shape[0]
+    idx = ops.knn(pos_km, pos_km, min(k + 1, n))                       # [n, k+1]
+    tgt = torch.arange(n, device=pos_km.device).view(-1, 1).expand_as(idx)
+    keep = idx != tgt
+    return torch.stack((idx[keep], tgt[keep]), dim=0)
+
+
+def extract_inputs_adjacencies_cartesian(locs_cart, grid_cart, k_sta_edges, k_spc_edges, device=None):
+    """The two small graphs of process_utils.py:712-719 for Cartesian coordinates in metres.  With `device` (a CUDA device)
+    the searches run in libgenie_b200's kNN kernel and the edge lists stay on the device; otherwise a host k-d tree is used
+    (set-up code, once per station set)."""
     k_sta = int(min(k_sta_edges, locs_cart.shape[0] - 2))
+    if device is not None:
+        km = lambda a: torch.from_numpy((np.asarray(a, dtype=np.float64) / 1000.0).astype(np.float32)).to(device)
+        return knn_graph_device(km(locs_cart), k_sta), knn_graph_device(km(grid_cart), k_spc_edges)
     A_sta_sta = knn_graph((np.asarray(locs_cart, dtype=np.float64) / 1000.0).astype(np.float32), k_sta)
     A_src_src = knn_graph((np.asarray(grid_cart, dtype=np.float64) / 1000.0).astype(np.float32), k_spc_edges)
     return A_sta_sta, A_src_src

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GENIE_B200_ABI_VERSION 4
+#define GENIE_B200_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define GENIE_API __attribute__((visibility("default")))
@@ -212,6 +212,13 @@ GENIE_API int genie_heads_grid_fwd(const float* heads_packed_dev, const float* f
 GENIE_API int genie_heads_query_fwd(const float* heads_packed_dev, const float* fold_dev, int n_t, const float* x_spatial_dev,
                                     int ld_x, const float* x_context_dev, const float* x_query_dev, const int64_t* nbr_dev,
                                     int k_nbr, int n_query, float scale_rel, float* x_out_dev, void* stream);
+
+/* ---- device kNN ---------------------------------------------------------------------------------
+ * Replaces torch_cluster.knn(x, y, k) at process_utils.py:718-719 (station / source graphs) and module.py:282 (query edges):
+ * idx_out_dev int64 [n_y][k] = the k rows of x_dev [n_x][3] nearest to every row of y_dev [n_y][3], nearest first (the
+ * reference's row 1 of knn(x, y, k), whose row 0 is repeat(arange(n_y), k)).  Coordinates fp32 exactly as the reference passes
+ * them (kilometres); distances are evaluated in fp64, ties keep the lower index.  1 <= k <= min(32, n_x). */
+GENIE_API int genie_knn_fwd(const float* x_dev, int n_x, const float* y_dev, int n_y, int k, int64_t* idx_out_dev, void* stream);
 
 /* ---- association branch (forward / forward_fixed, module.py:983-991) -------------------------------
  * The product-node-sized part of the association branch:

@@ -730,3 +730,43 @@ def test_absolute_pos_matches_reference(name, explicit):
     m.scale_rel = 2.0 * float(d['scale_rel'])
     lat2 = m.front_end(t('Slice'), t('Mask'), grid, want_latent=True, locs_use_cart=locs)[1]
     assert rel_err(lat2.cpu().numpy(), d['x_latent']) > 1e-3
+
+
+# ---- device kNN --------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize('n_x,n_y,k', [(3000, 3000, 16), (500, 4100, 10), (9, 40, 9), (20000, 257, 8), (70, 70, 32)])
+def test_device_knn_matches_kdtree(n_x, n_y, k):
+    """genie_knn_fwd against an fp64 k-d tree on the same fp32 points: identical indices, nearest first."""
+    from scipy.spatial import cKDTree
+    from genie_b200 import ops
+    dev = _dev()
+    rng = np.random.default_rng(n_x + k)
+    x = (rng.uniform(0, 300.0, (n_x, 3)) * np.array([1.0, 1.0, 0.15])).astype(np.float32)
+    y = x if n_x == n_y else (rng.uniform(0, 300.0, (n_y, 3)) * np.array([1.0, 1.0, 0.15])).astype(np.float32)
+    got = ops.knn(torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev), k).cpu().numpy()
+    want = cKDTree(x.astype(np.float64)).query(y.astype(np.float64), k=k)[1].reshape(n_y, k)
+    assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_device_knn_graphs_and_query_edges_match_host():
+    """The three call sites: station / source graphs (process_utils.py:718-719) and SpatialAttention's query edges
+    (module.py:282), against the host k-d tree builder / the oracle's knn; empty query set; k clipped to n_x."""
+    from genie_b200 import ops, synth
+    from genie_b200.module import knn_query_edges
+    from genie_b200.process_utils import extract_inputs_adjacencies_cartesian
+    from oracle import genie_oracle as go
+    dev = _dev()
+    net = synth.Network(120, 2500, seed=11)
+    A_sta, A_src = extract_inputs_adjacencies_cartesian(net.sta, net.grid, 8, 15)
+    D_sta, D_src = extract_inputs_adjacencies_cartesian(net.sta, net.grid, 8, 15, device=dev)
+    assert D_sta.is_cuda and torch.equal(D_sta.cpu(), A_sta) and torch.equal(D_src.cpu(), A_src)
+    tiny = synth.Network(6, 40, seed=5)                                  # k_sta clipped to S - 2 (process_utils.py:712)
+    T_sta, _ = extract_inputs_adjacencies_cartesian(tiny.sta, tiny.grid, 8, 15, device=dev)
+    assert torch.equal(T_sta.cpu(), extract_inputs_adjacencies_cartesian(tiny.sta, tiny.grid, 8, 15)[0])
+    rng = np.random.default_rng(2)
+    xq = np.stack((rng.uniform(0, net.width, 333), rng.uniform(0, net.width, 333), rng.uniform(-40000, 0, 333)), 1)
+    grid_t, xq_t = torch.from_numpy(net.grid).float(), torch.from_numpy(xq).float()
+    e = knn_query_edges(grid_t.to(dev), xq_t.to(dev), 10)
+    assert torch.equal(e.cpu(), go.knn(grid_t / 1000.0, xq_t / 1000.0, 10).flip(0))
+    assert ops.knn(grid_t.to(dev), torch.zeros((0, 3), device=dev), 10).shape == (0, 10)
+    assert ops.knn(grid_t[:4].to(dev), xq_t[:5].to(dev), 10).shape == (5, 4)
