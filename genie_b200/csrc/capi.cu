@@ -35,7 +35,7 @@ const char* const kKernelNames[KID_COUNT] = {"pack_weights_kernel", "input_serie
                                              "src_mean32_kernel",   "src_mean16_kernel",   "da_layer1_s_kernel",
                                              "da_layer2_s_kernel",  "heads_grid_kernel",   "heads_query_kernel",
                                              "assoc_grid_pre_kernel", "assoc_init_kernel", "assoc_layer1_kernel",
-                                             "assoc_layer2_kernel", "assoc_collapse_kernel", "knn_kernel"};
+                                             "assoc_layer2_kernel", "assoc_collapse_kernel", "knn_kernel", "stack_output_kernel"};
 }  // namespace
 
 TimedLaunch::TimedLaunch(int kid_, cudaStream_t st_) : kid(kid_), st(st_), slot(nullptr) {
@@ -361,6 +361,17 @@ int genie_input_nearest_fwd(const genie_nearest_params_t* prm, const double* tim
     }
     return launch_input_nearest(prm, times_all_dev, times_p_dev, times_s_dev, ind_use_dev, trv_times_dev, slice_out_dev,
                                 mask_out_dev, static_cast<cudaStream_t>(stream));
+}
+
+// ---- output stacking of the streaming loop ------------------------------------------------------------
+int genie_stack_output_fwd(const float* x_dev, int n_query, int n_t, int n_use, const int32_t* col_dev, float scale,
+                           float* out_dev, int64_t ld_out, void* stream) {
+    if (n_query < 0 || n_t < 0 || n_use < 0 || n_use > n_t || ld_out < 0 ||
+        ((int64_t)n_query * n_use > 0 && (!x_dev || !col_dev || !out_dev))) {
+        set_error("genie_stack_output_fwd: bad argument");
+        return GENIE_ERR_INVALID;
+    }
+    return launch_stack_output(x_dev, n_query, n_t, n_use, col_dev, scale, out_dev, ld_out, static_cast<cudaStream_t>(stream));
 }
 
 // ---- device kNN -------------------------------------------------------------------------------------

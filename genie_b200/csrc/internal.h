@@ -98,6 +98,7 @@ enum KernelId {
     KID_ASSOC_LAYER2,
     KID_ASSOC_COLLAPSE,
     KID_KNN,
+    KID_STACK,
     KID_COUNT
 };
 // Brackets one kernel launch with cudaEvents on its stream when timing is enabled (no-op otherwise).
@@ -187,6 +188,8 @@ int launch_assoc_product(const genie_plan* p, const float* packed, const float* 
 int launch_assoc_collapse(const float* packed, const float* s_rows, int64_t P, const int64_t* edges_p, const int64_t* edges_s,
                           const float* tlatent, const float* tpick, const int64_t* ipick, const float* phase_label, int n_arv,
                           int l_dt, int k_infer, float dt0, float dt_step, float eps, float* arrival, cudaStream_t st);
+int launch_stack_output(const float* x, int Q, int T, int n_use, const int32_t* col, float scale, float* out, int64_t ld_out,
+                        cudaStream_t st);
 int launch_knn(const float* x, int n_x, const float* y, int n_y, int k, int64_t* idx_out, cudaStream_t st);
 int launch_input_nearest(const genie_nearest_params_t* prm, const double* t_all, const double* t_p, const double* t_s,
                          const int32_t* ind_use, const float* trv_times, float* slice_out, float* mask_out, cudaStream_t st);

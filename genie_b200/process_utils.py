@@ -93,6 +93,12 @@ class InputExtractor(object):
         P = np.asarray(P, dtype=np.float64)
         P = P[np.argsort(P[:, 0], kind='stable')]
         self._day = (P[:, 0].copy(), torch.from_numpy(np.ascontiguousarray(P)).to(self.plan.device))
+        used = self.sta_perm.cpu().numpy()[P[:, 1].astype('int')] >= 0
+        self._used_cum = np.concatenate(([0], np.cumsum(used))).astype(np.int64)
+
+    def used_cum(self):
+        """Prefix counts, over the resident (time-sorted) pick table, of the picks on used stations."""
+        return self._used_cum
 
     def window_rows(self, t0):
         """Row range of the resident pick table that can touch window t0 (process_utils.py:476)."""

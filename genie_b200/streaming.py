@@ -1,0 +1,91 @@
+"""The caller-side streaming loop of `process_continuous_days.py:757-813` with everything resident on the device
+(SURVEY.md §8f rank 4).
+
+The reference, per origin-time sample: `extract_input_from_data` on the host, a fresh host->device copy of Slice / Mask
+(:797), `forward_fixed_source`, a device->host copy of the query prediction and `Out_2[:, ip_need] += ...` in numpy (:802-805).
+Here the day's pick table, the travel times and the solution array `Out_2` stay in HBM: per window one input-scatter launch pair
+(genie_input_scatter_fwd), the front end + heads (genie_frontend_fwd, genie_heads_*) and one stacking launch
+(genie_stack_output_fwd); the host only computes the window's row range in the pick table and the nine column indices.
+One copy of `Out_2` [Q, n_steps] comes back at the end of the day.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import capi
+
+N_OVERLAP = {'full': 1.0, 'partial': 3.0, 'half': 2.0}          # process_continuous_days.py:369-379
+
+
+def nearest_index(sorted_vals, t):
+    """Index of the entry of the ascending array `sorted_vals` nearest to every t (cKDTree.query on a 1-D set, :765, :793);
+    the lower index on an exact tie."""
+    sorted_vals = np.asarray(sorted_vals, dtype=np.float64)
+    t = np.asarray(t, dtype=np.float64)
+    hi = np.clip(np.searchsorted(sorted_vals, t, side='left'), 0, len(sorted_vals) - 1)
+    lo = np.clip(hi - 1, 0, len(sorted_vals) - 1)
+    return np.where(np.abs(sorted_vals[lo] - t) <= np.abs(sorted_vals[hi] - t), lo, hi)
+
+
+class DayProcessor(object):
+    """`mz`: a GCN_Detection_Network_extended with its adjacencies set; `extractor`: an InputExtractor with the day's picks
+    resident (`set_day`).  `run(tsteps, tsteps_abs)` returns Out_2 [Q, len(tsteps_abs)] on the device."""
+
+    def __init__(self, mz, extractor, locs_use_cart, x_grid_cart, X_query_cart, t_win=6.0, dt_win=0.75, step_size='half',
+                 n_scale_x_grid=1, pick_t_win=10.0):
+        self.mz, self.ex = mz, extractor
+        self.locs, self.grid, self.xq = locs_use_cart, x_grid_cart, X_query_cart
+        self.t_win, self.dt_win, self.step_size = float(t_win), float(dt_win), step_size
+        self.scale = 1.0 / (N_OVERLAP[step_size] * float(n_scale_x_grid))
+        self.pick_t_win = float(pick_t_win)                       # extract_pick_inputs_from_data's t_win (process_utils.py:644)
+        dev = X_query_cart.device
+        self.t_rel = np.arange(-self.t_win / 2.0, self.t_win / 2.0 + self.dt_win, self.dt_win)       # :534, :793
+        self.tq = torch.from_numpy(self.t_rel).reshape(-1, 1).float().to(dev)
+        self.windows_done, self.windows_skipped = 0, 0
+
+    def window_pick_count(self, t0):
+        """len(lp_times[i0]) of the reference (:787): picks of used stations inside the input window (process_utils.py:476)
+        and inside extract_pick_inputs_from_data's ball (process_utils.py:665)."""
+        ex = self.ex
+        times, cum = ex._day[0], ex.used_cum()
+        sig2, mt = 2.0 * ex.kernel_sig_t, ex.max_t
+        lo = max(np.searchsorted(times, t0 - sig2, side='right'), np.searchsorted(times, t0 - self.pick_t_win, side='left'))
+        hi = min(np.searchsorted(times, t0 + mt + sig2, side='left'),
+                 np.searchsorted(times, t0 + mt + self.pick_t_win, side='right'))
+        return int(cum[hi] - cum[lo]) if hi > lo else 0
+
+    def run(self, tsteps, tsteps_abs, out=None):
+        """tsteps: origin-time samples to process (already thinned by the caller's min-pick rule, :725-748); tsteps_abs: the
+        fixed solution grid (:411).  Windows without picks are skipped as in the reference (:787)."""
+        dev = self.xq.device
+        Q, n_abs = int(self.xq.shape[0]), len(tsteps_abs)
+        tsteps_abs = np.asarray(tsteps_abs, dtype=np.float64)
+        if out is None:
+            out = torch.zeros((Q, n_abs), dtype=torch.float32, device=dev)
+        T = len(self.t_rel)
+        n_use = T - 1 if self.step_size == 'half' else T                                              # :802-805
+        lib = capi.load()
+        centre = nearest_index(tsteps_abs, np.asarray(tsteps, dtype=np.float64))                    # :765
+        cols_all = nearest_index(tsteps_abs, tsteps_abs[centre][:, None] + self.t_rel[None, :])     # :793
+        cols_dev = torch.from_numpy(cols_all.astype(np.int32)).to(dev)
+        for i0, t0 in enumerate(np.asarray(tsteps, dtype=np.float64)):
+            if self.window_pick_count(float(t0)) == 0:
+                self.windows_skipped += 1
+                continue
+            Slice, Mask = self.ex(float(t0))
+            _, x = self.mz.forward_fixed_source(Slice, Mask, None, None, None, self.locs, self.grid, self.xq, self.tq)
+            x = x.reshape(Q, T)
+            with torch.cuda.device(dev):
+                capi.check(lib.genie_stack_output_fwd(capi.dptr(x, torch.float32, 'x'), Q, T, n_use,
+                                                      capi.dptr(cols_dev[i0], torch.int32, 'cols'),
+                                                      ctypes.c_float(self.scale), capi.dptr(out, torch.float32, 'Out_2'),
+                                                      n_abs, capi.stream_ptr(dev)))
+            self.windows_done += 1
+        return out
+
+    @staticmethod
+    def sparse(out, thresh=0.01):
+        """Out_2_sparse of :812-813: rows (query index, time index, value) of the entries above the threshold."""
+        iz = torch.nonzero(out > thresh, as_tuple=False)
+        return torch.cat((iz.double(), out[iz[:, 0], iz[:, 1]].double().view(-1, 1)), dim=1)

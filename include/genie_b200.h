@@ -213,6 +213,15 @@ GENIE_API int genie_heads_query_fwd(const float* heads_packed_dev, const float* 
                                     int ld_x, const float* x_context_dev, const float* x_query_dev, const int64_t* nbr_dev,
                                     int k_nbr, int n_query, float scale_rel, float* x_out_dev, void* stream);
 
+/* ---- output stacking of the streaming loop --------------------------------------------------------
+ * process_continuous_days.py:797-805: Out_2[:, ip_need[t]] += x[:, t, 0] / n_overlap / n_scale_x_grid for the first n_use
+ * (all, or all but the last when step_size == 'half') query times of one window, on the device.
+ *   x_dev [n_query][n_t] (the query prediction of forward_fixed_source); col_dev int32 [n_use] distinct columns of out_dev
+ *   [n_query][ld_out] (the nearest solution-grid step of every query time, the caller's cKDTree look-up at :793);
+ *   scale = 1 / (n_overlap * n_scale_x_grid).  Launch windows in stream order: columns of consecutive windows overlap. */
+GENIE_API int genie_stack_output_fwd(const float* x_dev, int n_query, int n_t, int n_use, const int32_t* col_dev, float scale,
+                                     float* out_dev, int64_t ld_out, void* stream);
+
 /* ---- device kNN ---------------------------------------------------------------------------------
  * Replaces torch_cluster.knn(x, y, k) at process_utils.py:718-719 (station / source graphs) and module.py:282 (query edges):
  * idx_out_dev int64 [n_y][k] = the k rows of x_dev [n_x][3] nearest to every row of y_dev [n_y][3], nearest first (the

@@ -655,3 +655,42 @@ def init_state_association(sd, seed=7, scale=1.0):
     for a in ('activate1', 'activate2', 'activate3', 'activate4'):
         prelu(p + a)
     return sd
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# caller-side streaming loop: process_continuous_days.py:757-813, one source grid,
+# `use_updated_input: True`.  The loop lives in the reference's script body (not importable), so this restatement is
+# checked by reading only: parity UNPINNED for this function (its per-window pieces, input_scatter and
+# forward_fixed_source, are pinned above).
+# --------------------------------------------------------------------------------------------------------------------
+
+
+def continuous_day_stack(sd, P, tsteps, tsteps_abs, ind_use, n_locs, A_src_in_sta, trv_times, max_t, kernel_sig_t, dt,
+                         A_in_sta, A_in_src, read_in_attr, read_in_index, A_src, grid_cart, x_query_cart, scale_rel, scale_t,
+                         t_win=6.0, dt_win=0.75, step_size='half', n_scale_x_grid=1, pick_t_win=10.0):
+    from scipy.spatial import cKDTree
+    n_overlap = {'full': 1.0, 'partial': 3.0, 'half': 2.0}[step_size]                        # :369-379
+    tsteps_abs = np.asarray(tsteps_abs, dtype=np.float64)
+    tree_tsteps = cKDTree(tsteps_abs.reshape(-1, 1))                                          # :412
+    Out_2 = np.zeros((x_query_cart.shape[0], len(tsteps_abs)))                                # :758
+    t_rel = np.arange(-t_win / 2.0, t_win / 2.0 + dt_win, dt_win)
+    tq = torch.from_numpy(t_rel).reshape(-1, 1).float()                                       # :534
+    idx = tree_tsteps.query(np.asarray(tsteps, dtype=np.float64).reshape(-1, 1))[1]           # :765
+    n_done = 0
+    for i0, t0 in enumerate(np.asarray(tsteps, dtype=np.float64)):
+        # pick list of the window (process_utils.py:476-481, 665): only its length matters here (:787)
+        sel = (P[:, 0] > (t0 - 2.0 * kernel_sig_t)) * (P[:, 0] < (t0 + max_t + 2.0 * kernel_sig_t))
+        sel = sel * np.isin(P[:, 1].astype('int'), np.asarray(ind_use))
+        sel = sel * (np.abs(P[:, 0] - (t0 + max_t / 2.0)) <= (pick_t_win + max_t / 2.0))
+        if sel.sum() == 0:
+            continue
+        Slice, Mask = input_scatter(P, t0, ind_use, n_locs, A_src_in_sta, trv_times, max_t, kernel_sig_t, dt)
+        ip_need = tree_tsteps.query(tsteps_abs[idx[i0]] + t_rel.reshape(-1, 1))               # :793
+        _, x = forward_fixed_source(sd, torch.from_numpy(Slice), torch.from_numpy(Mask), A_in_sta, A_in_src, read_in_attr,
+                                    read_in_index, A_src, grid_cart, x_query_cart, tq, scale_rel, scale_t)
+        if step_size == 'half':                                                                # :802-805
+            Out_2[:, ip_need[1][0:-1]] += x[:, 0:-1, 0].numpy() / n_overlap / n_scale_x_grid
+        else:
+            Out_2[:, ip_need[1]] += x[:, :, 0].numpy() / n_overlap / n_scale_x_grid
+        n_done += 1
+    return Out_2, n_done

@@ -770,3 +770,47 @@ def test_device_knn_graphs_and_query_edges_match_host():
     assert torch.equal(e.cpu(), go.knn(grid_t / 1000.0, xq_t / 1000.0, 10).flip(0))
     assert ops.knn(grid_t.to(dev), torch.zeros((0, 3), device=dev), 10).shape == (0, 10)
     assert ops.knn(grid_t[:4].to(dev), xq_t[:5].to(dev), 10).shape == (5, 4)
+
+
+# ---- streaming loop with device-side stacking -------------------------------------------------------
+
+@pytest.mark.parametrize('step_size', ['half', 'full'])
+def test_day_processor_matches_oracle_loop(step_size):
+    """DayProcessor (picks, travel times and Out_2 resident on the device) against the restated loop of
+    process_continuous_days.py:757-813 on the 10 x 100 fixture network with the trained weights: overlapping windows, windows
+    at the edges of the solution grid, windows without picks (skipped)."""
+    from genie_b200.plan import GraphPlan
+    from genie_b200.process_utils import InputExtractor
+    from genie_b200.streaming import DayProcessor, nearest_index
+    from oracle import genie_oracle as go
+    dev = _dev()
+    d, sd = load_golden('assoc_10x100')
+    S, G = len(d['ind_use']), d['grid'].shape[0]
+    A_sta, A_src, A_ps, A_pg, A_sip, A_sis = _graphs(d)
+    step = 3.0 if step_size == 'half' else 6.0
+    tsteps = np.concatenate((np.arange(0.0, 45.0, step), [150.0, 153.0, 5000.0, 5003.0]))
+    tsteps_abs = np.arange(-3.0, 160.0 + 0.75, 0.75)
+    xq = torch.from_numpy(d['x_query']).float()
+    grid = torch.from_numpy(d['grid']).float()
+    attr = torch.from_numpy(d['read_in_attr'])
+    want, n_done = go.continuous_day_stack(
+        sd, d['picks'], tsteps, tsteps_abs, d['ind_use'], d['sta'].shape[0], A_sis.numpy(), d['trv_times'], float(d['max_t']),
+        float(d['kernel_sig_t']), float(d['dt']), A_ps, A_pg, attr, A_sip, A_src, grid, xq, float(d['scale_rel']),
+        float(d['scale_t']), step_size=step_size)
+    m = _model(sd, dev, float(d['scale_rel']), float(d['scale_t']))
+    m.set_adjacencies_cartesian(A_sta, A_src, attr.to(dev), S, G, device=dev)
+    ex = InputExtractor(m._plan, d['trv_times'], d['ind_use'], d['sta'].shape[0], float(d['max_t']), float(d['kernel_sig_t']),
+                        float(d['dt']))
+    ex.set_day(d['picks'])
+    dp = DayProcessor(m, ex, torch.from_numpy(d['sta'][d['ind_use']]).float().to(dev), grid.to(dev), xq.to(dev),
+                      step_size=step_size)
+    out = dp.run(tsteps, tsteps_abs)
+    assert dp.windows_done == n_done and dp.windows_skipped == len(tsteps) - n_done and dp.windows_skipped >= 2
+    assert rel_err(out.cpu().numpy(), want) < TOL
+    sp = DayProcessor.sparse(out, 0.01).cpu().numpy()
+    iz1, iz2 = np.where(out.cpu().numpy() > 0.01)
+    assert np.array_equal(sp[:, 0], iz1) and np.array_equal(sp[:, 1], iz2)
+    # the 1-D nearest look-up against the k-d tree it replaces
+    from scipy.spatial import cKDTree
+    t = np.random.default_rng(0).uniform(-10.0, 170.0, 500)
+    assert np.array_equal(nearest_index(tsteps_abs, t), cKDTree(tsteps_abs.reshape(-1, 1)).query(t.reshape(-1, 1))[1])
