@@ -103,6 +103,7 @@ SIGNATURES = {
     'genie_assoc_packed_floats': (ctypes.c_size_t, []),
     'genie_assoc_layout': (ctypes.c_int, [_P, ctypes.c_int]),
     'genie_assoc_workspace_bytes': (ctypes.c_size_t, [_P]),
+    'genie_assoc_set_terms': (ctypes.c_int, [_P, _P, _P, _P, _P]),
     'genie_assoc_product_fwd': (ctypes.c_int, [_P, _P, _P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_float, _P, _P, _P, _P,
                                                _P, _P, ctypes.POINTER(ctypes.c_void_p), _P]),
     'genie_assoc_collapse_fwd': (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, _P, ctypes.c_int64, _P, _P, _P, _P,

@@ -157,8 +157,9 @@ __device__ __forceinline__ void store_row32(float* __restrict__ dst, const float
 __global__ void __launch_bounds__(K0_THREADS)
     assoc_init_kernel(const GraphView gv, const float* __restrict__ packed, const float* __restrict__ yfc1,
                       const float* __restrict__ mask_out, const float* __restrict__ edge_attr,
-                      const float* __restrict__ x_latent, const float* __restrict__ mask, float* __restrict__ s0_out,
-                      float* __restrict__ tr_out, float* __restrict__ a1_out, float* __restrict__ a2_out) {
+                      const float* __restrict__ x_latent, const float* __restrict__ mask, const float* __restrict__ init_sta,
+                      const float* __restrict__ init_src, float* __restrict__ s0_out, float* __restrict__ tr_out,
+                      float* __restrict__ a1_out, float* __restrict__ a2_out) {
     extern __shared__ __align__(16) float sW0[];
     for (int i = threadIdx.x; i < K0_W_FLOATS; i += K0_THREADS) sW0[i] = packed[K0_W0 + i];
     const float a_ro1 = packed[as::SL + as::SL_RO1], a_ro2 = packed[as::SL + as::SL_RO2];
@@ -199,6 +200,17 @@ __global__ void __launch_bounds__(K0_THREADS)
         // init_trns [s0 | x_latent | mask_out | Mask]                                (module.py:389-391)
 #pragma unroll
         for (int o = 0; o < 30; ++o) tr[o] = sW[as::AI_B + o];
+        if (init_sta != nullptr) {
+            // use_absolute_pos (module.py:987-988): the six position channels of init_trns as additive terms
+            const float* ts = init_sta + (init_src != nullptr ? i - (int64_t)g * gv.S : i) * 32;
+#pragma unroll
+            for (int o = 0; o < 30; ++o) tr[o] += __ldg(ts + o);
+            if (init_src != nullptr) {
+                const float* tg = init_src + (int64_t)g * 32;
+#pragma unroll
+                for (int o = 0; o < 30; ++o) tr[o] += __ldg(tg + o);
+            }
+        }
 #pragma unroll
         for (int k = 0; k < 15; ++k) fma_row30(tr, s[k], sW + as::AI_W + k * 32);
         const float2* xl = reinterpret_cast<const float2*>(x_latent + i * 30);
@@ -251,8 +263,9 @@ constexpr size_t K2_SMEM = (size_t)(K2_W_FLOATS + K2_F_ROWS * LDF) * sizeof(floa
 __global__ void __launch_bounds__(K2_THREADS, 2)
     assoc_layer1_kernel(const GraphView gv, const float* __restrict__ packed, const float* __restrict__ tr_in,
                         const float* __restrict__ a1, const float* __restrict__ a2, const float* __restrict__ msrc,
-                        const float* __restrict__ mask_out, const float* __restrict__ mask, float* __restrict__ zc,
-                        float* __restrict__ va, float* __restrict__ vb, int64_t n_tiles) {
+                        const float* __restrict__ mask_out, const float* __restrict__ mask, const float* __restrict__ edge_sta,
+                        const float* __restrict__ edge_src, float* __restrict__ zc, float* __restrict__ va,
+                        float* __restrict__ vb, int64_t n_tiles) {
     extern __shared__ __align__(16) float smem[];
     float* sW0 = smem;
     float* F = smem + K2_W_FLOATS;
@@ -292,11 +305,25 @@ __global__ void __launch_bounds__(K2_THREADS, 2)
             if (lane < 5) F[(90 + lane) * LDF + m] = mk;
         }
         __syncthreads();
+        // edge-feature model (genie_assoc_set_terms): per-node additive terms of this thread's branch, or NULL
+        const float* et = nullptr;
+        if (edge_sta != nullptr && i0 + n < gv.P) {
+            int64_t idx = i0 + n;
+            if (gv.mode == GENIE_GRAPH_CARTESIAN) {
+                const int64_t g = idx / gv.S;
+                idx = br ? g : idx - g * gv.S;
+            }
+            et = (br ? edge_src : edge_sta) + idx * GENIE_EDGE_TERM_LD;
+        }
         // ---- stage B: tr = PReLU1([l1_t1_2(..) | l1_t2_2(..)]) --------------------------------------------------------
         {
             const float* W = sW + (br ? as::W12 : as::W11);
             f32x2_t acc[15];
             init2_30(acc, sW + (br ? as::B12 : as::B11));
+            if (et != nullptr) {
+#pragma unroll
+                for (int o = 0; o < 15; ++o) fadd2(acc[o], pack2(__ldg(et + 2 * o), __ldg(et + 2 * o + 1)));
+            }
 #pragma unroll 2
             for (int k = 0; k < 30; ++k) fma2_row30(acc, F[k * LDF + n], W + k * 32);
             const float* Fm = F + (30 + 30 * br) * LDF;
@@ -323,6 +350,10 @@ __global__ void __launch_bounds__(K2_THREADS, 2)
             const float* Wc = sW + (br ? as::WCB : as::WCA);
             f32x2_t c[8];
             init2_16(c, sW + (br ? as::BCB : as::BCA));
+            if (et != nullptr) {
+#pragma unroll
+                for (int o = 0; o < 8; ++o) fadd2(c[o], pack2(__ldg(et + 32 + 2 * o), __ldg(et + 32 + 2 * o + 1)));
+            }
 #pragma unroll 2
             for (int k = 0; k < 60; ++k) {
                 const float x = F[k * LDF + n];
@@ -532,7 +563,8 @@ int launch_assoc_product(const genie_plan* p, const float* packed, const float* 
     {
         TimedLaunch tl(KID_ASSOC_INIT, st);
         assoc_init_kernel<<<(unsigned)((P + K0_THREADS - 1) / K0_THREADS), K0_THREADS, K0_SMEM, st>>>(
-            gv, packed, w.yfc1, w.mask_out, edge_attr, x_latent, mask, s0_out, w.tr, w.a1, w.a2);
+            gv, packed, w.yfc1, w.mask_out, edge_attr, x_latent, mask, p->assoc_init_sta, p->assoc_init_src, s0_out, w.tr,
+            w.a1, w.a2);
         GENIE_LAUNCH_CHECK();
     }
     // plans with tiling tables: the two means over source neighbours come from the source pass of the front end
@@ -545,8 +577,9 @@ int launch_assoc_product(const genie_plan* p, const float* packed, const float* 
         const int64_t grid = n_tiles < (int64_t)p->sm_count * 2 ? n_tiles : (int64_t)p->sm_count * 2;
         TimedLaunch tl(KID_ASSOC_LAYER1, st);
         assoc_layer1_kernel<<<(unsigned)grid, K2_THREADS, K2_SMEM, st>>>(gv, packed, w.tr, w.a1, w.a2,
-                                                                        split ? w.msrc : nullptr, w.mask_out, mask, w.zc,
-                                                                        w.va, w.vb, n_tiles);
+                                                                        split ? w.msrc : nullptr, w.mask_out, mask,
+                                                                        p->assoc_edge_sta, p->assoc_edge_src, w.zc, w.va,
+                                                                        w.vb, n_tiles);
         GENIE_LAUNCH_CHECK();
     }
     float* m2src = split ? w.a1 : nullptr;             // a1 is dead after layer 1: [P][16] fits in its [P][32]

@@ -388,6 +388,22 @@ size_t genie_assoc_packed_floats(void) { return assoc_packed_floats(); }
 
 int genie_assoc_layout(int32_t* offsets_out, int n) { return assoc_layout(offsets_out, n); }
 
+int genie_assoc_set_terms(genie_plan_t* plan, const float* init_sta_dev, const float* init_src_dev, const float* edge_sta_dev,
+                          const float* edge_src_dev) {
+    if (!plan || (init_sta_dev == nullptr && init_src_dev != nullptr) ||
+        (init_sta_dev != nullptr && (plan->g.mode == GENIE_GRAPH_CARTESIAN) != (init_src_dev != nullptr)) ||
+        ((edge_sta_dev == nullptr) != (edge_src_dev == nullptr))) {
+        set_error("genie_assoc_set_terms: table combination does not match the plan (see genie_plan_set_init_terms / "
+                  "genie_plan_set_edge_terms)");
+        return GENIE_ERR_INVALID;
+    }
+    plan->assoc_init_sta = init_sta_dev;
+    plan->assoc_init_src = init_src_dev;
+    plan->assoc_edge_sta = edge_sta_dev;
+    plan->assoc_edge_src = edge_src_dev;
+    return GENIE_OK;
+}
+
 size_t genie_assoc_workspace_bytes(const genie_plan_t* plan) {
     if (!plan) return 0;
     return carve_assoc_workspace(plan, nullptr).bytes;

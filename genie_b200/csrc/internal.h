@@ -18,6 +18,11 @@ struct genie_plan {
     // use_absolute_pos (genie_plan_set_init_terms): additive terms of init_trns before its activation, NULL = off.
     const float* init_sta;  // [S][32] (CARTESIAN) or [P][32] (EXPLICIT, init_src NULL)
     const float* init_src;  // [G][32] or NULL
+    // the same two kinds of tables for the association branch (genie_assoc_set_terms), NULL = off
+    const float* assoc_init_sta;
+    const float* assoc_init_src;
+    const float* assoc_edge_sta;
+    const float* assoc_edge_src;
 };
 
 // Device-side view of the product graph.  CARTESIAN: node i = g*S + s; sta neighbours g*S + col, src neighbours

@@ -432,6 +432,7 @@ class GCN_Detection_Network_extended(nn.Module):
         self._edge_means = None       # updated model: (means_sta(scale), means_src(scale)) of the current plan
         self._edge_terms = None       # (key, t_sta, t_src, re-laid weight tensors)
         self._init_terms = None       # use_absolute_pos: (key, re-laid init_trns weight [30,8])
+        self._assoc_terms = None      # association branch of the model variants: (key, re-laid weights)
 
     # -- graph plans ---------------------------------------------------------------------------------------------------
     def set_adjacencies(self, A_in_sta, A_in_src, A_src_in_edges, A_Lg_in_src, A_src_in_sta, A_src, A_edges_p, A_edges_s,
@@ -625,18 +626,63 @@ class GCN_Detection_Network_extended(nn.Module):
             self._read_out_attr = A_Lg_in_src.x.to(plan.device).float().contiguous()
         return self._read_out_attr
 
+    def _update_assoc_terms(self, locs_use_cart, x_temp_cuda_cart):
+        """Model variants of the association branch (genie_assoc_set_terms): tables + re-laid weights, rebuilt when a weight,
+        the positions, scale_rel or the plan change.  Returns the dict AssocWeights.update takes (empty for the default model)."""
+        if not (self.updated_model or self.use_absolute_pos):
+            return None
+        da, plan = self.DataAggregationAssociationPhase, self._plan
+        ws = (da.init_trns.weight, da.l1_t1_2.weight, da.l1_t2_2.weight, da.l2_t1_2.weight, da.l2_t2_2.weight)
+        key = tuple((w.data_ptr(), w._version) for w in ws) + (
+            locs_use_cart.data_ptr(), locs_use_cart._version, x_temp_cuda_cart.data_ptr(), x_temp_cuda_cart._version,
+            float(self.scale_rel), id(plan), id(self._edge_means))
+        if self._assoc_terms is not None and self._assoc_terms[0] == key:
+            return self._assoc_terms[1]
+        w0, w11, w12, w21, w22 = (w.detach() for w in ws)
+        dev = w0.device
+        relaid, init_sta, init_src, edge_sta, edge_src = {}, None, None, None, None
+        if self.use_absolute_pos:                     # init_trns input order: [s0 (15) | locs (3) | x_temp (3) | x_latent | mask5]
+            sc = 3.0 * float(self.scale_rel)
+
+            def table(pos, cols):
+                t = torch.zeros((pos.shape[0], 32), dtype=torch.float32, device=dev)
+                t[:, :30] = (pos.to(dev).float() / sc) @ w0[:, cols].t()
+                return t
+            t_sta, t_src = table(locs_use_cart, slice(15, 18)), table(x_temp_cuda_cart, slice(18, 21))
+            if plan.mode == capi.GRAPH_CARTESIAN:
+                init_sta, init_src = t_sta.contiguous(), t_src.contiguous()
+            else:
+                idx = getattr(self, 'A_src_in_sta', None)
+                if idx is None:
+                    raise capi.GenieError('use_absolute_pos on an explicit product graph needs A_src_in_sta (set_adjacencies)')
+                idx = idx.to(dev).long()
+                init_sta = (t_sta[idx[0]] + t_src[idx[1]]).contiguous()
+            relaid['init_trns'] = torch.cat((w0[:, 0:15], w0[:, 21:56]), dim=1).contiguous()
+        if self.updated_model:                        # l1_t*_2: [tr | mean x_j | mean pos_rel (4) | mask5]; l2_t*_2 likewise
+            if self._edge_means is None:
+                raise RuntimeError('set_adjacencies must be called before forward_fixed of the updated model')
+            m_sta, m_src = self._edge_means[0](float(self.scale_rel)), self._edge_means[1](float(self.scale_rel))
+
+            def etable(m, wa, wb):
+                t = torch.zeros((m.shape[0], capi.EDGE_TERM_LD), dtype=torch.float32, device=dev)
+                t[:, 0:30] = m @ wa[:, 60:64].t()
+                t[:, 32:47] = m @ wb[:, 90:94].t()
+                return t.contiguous()
+            edge_sta, edge_src = etable(m_sta, w11, w21), etable(m_src, w12, w22)
+            cut = lambda w, a: torch.cat((w[:, :a], w[:, a + 4:]), dim=1).contiguous()
+            relaid.update(l1_t1_2=cut(w11, 60), l1_t2_2=cut(w12, 60), l2_t1_2=cut(w21, 90), l2_t2_2=cut(w22, 90))
+        plan.set_assoc_terms(init_sta, init_src, edge_sta, edge_src)
+        self._assoc_terms = (key, relaid)
+        return relaid
+
     def _association(self, Slice, Mask, A_Lg_in_src, A_edges_p, A_edges_s, dt_partition, tlatent, tpick, ipick, phase_label,
                      locs_use_cart, x_temp_cuda_cart, x_query_cart, x_query_src_cart, t_query, tq_sample, trv_out_q):
         """module.py:974-997: front end + heads + association branch -> (y, x, arv_p, arv_s)."""
-        if self.updated_model:
-            raise NotImplementedError('genie_b200: the association branch of the updated model definition '
-                                      '(DataAggregationAssociationPhaseEdges, module.py:406) is not built')
-        if self.use_absolute_pos:
-            raise NotImplementedError('genie_b200: the association branch with use_absolute_pos=True is not built')
         if not ops.AssocWeights.supported(self):
             raise NotImplementedError('genie_b200: the association kernels are built for the reference\'s module shapes')
         with torch.no_grad():
-            x_spatial, x_latent, _ = self.front_end(Slice, Mask, x_temp_cuda_cart, want_latent=True)
+            x_spatial, x_latent, _ = self.front_end(Slice, Mask, x_temp_cuda_cart, want_latent=True,
+                                                    locs_use_cart=locs_use_cart)
             y, x = self._heads(x_spatial, x_temp_cuda_cart, x_query_cart, t_query)
             x_src = self.SpatialAttention(x_spatial, x_query_src_cart, x_temp_cuda_cart, cache=False)         # :980
             if A_Lg_in_src is None and self._plan.mode == capi.GRAPH_CARTESIAN:
@@ -648,7 +694,7 @@ class GCN_Detection_Network_extended(nn.Module):
             dev = x_spatial.device
             if self._assoc_w is None or self._assoc_w.device != dev:
                 self._assoc_w = ops.AssocWeights(dev)
-            packed = self._assoc_w.update(self)
+            packed = self._assoc_w.update(self, self._update_assoc_terms(locs_use_cart, x_temp_cuda_cart))
             s_rows = ops.assoc_product_fwd(self._plan, packed, x_spatial, y.reshape(y.shape[0], -1), attr, x_latent, Mask,
                                            mask_thresh=0.01)                                                   # :983-987
             cp = self.LocalSliceLgCollapseP

@@ -209,8 +209,9 @@ class AssocWeights(object):
         ro, da = model.BipartiteGraphReadOutOperator, model.DataAggregationAssociationPhase
         cp, cs = model.LocalSliceLgCollapseP, model.LocalSliceLgCollapseS
         return (tuple(model.SpatialDirect.f_direct.weight.shape) == (30, 30) and tuple(ro.fc1.weight.shape) == (30, 33) and
-                tuple(ro.fc2.weight.shape) == (15, 30) and tuple(da.init_trns.weight.shape) == (30, 50) and
-                tuple(da.l1_t1_2.weight.shape) == (30, 65) and tuple(da.l2_t1_2.weight.shape) == (15, 95) and
+                tuple(ro.fc2.weight.shape) == (15, 30) and tuple(da.init_trns.weight.shape) in ((30, 50), (30, 56)) and
+                tuple(da.l1_t1_2.weight.shape) in ((30, 65), (30, 69)) and
+                tuple(da.l2_t1_2.weight.shape) in ((15, 95), (15, 99)) and
                 tuple(cp.fc1.weight.shape) == (30, 32) and tuple(cs.fc2.weight.shape) == (15, 30))
 
     def _mat(self, name, w, ld):
@@ -224,35 +225,44 @@ class AssocWeights(object):
         v = v.detach().reshape(-1)
         self.buf[self.off[name]:self.off[name] + v.numel()] = v
 
-    def update(self, model):
+    def update(self, model, relaid=None):
+        """`relaid`: model variants only — dict of re-laid weight copies (`init_trns` [30,50] without the six position columns of
+        use_absolute_pos; `l1_t1_2`, `l1_t2_2` [30,65] and `l2_t1_2`, `l2_t2_2` [15,95] without the four edge-feature columns
+        of the updated model definition); those columns live in the tables of genie_assoc_set_terms."""
+        relaid = relaid or {}
         sd, ro, da = model.SpatialDirect, model.BipartiteGraphReadOutOperator, model.DataAggregationAssociationPhase
         cp, cs = model.LocalSliceLgCollapseP, model.LocalSliceLgCollapseS
         mods = (sd, ro, da, cp, cs)
         if getattr(self, '_plist_for', None) is not model:
             self._plist, self._plist_for = [p for m in mods for p in m.parameters()], model
-        key = tuple((p.data_ptr(), p._version) for p in self._plist)
+        key = tuple((p.data_ptr(), p._version) for p in self._plist) + tuple((k, relaid[k].data_ptr()) for k in sorted(relaid))
         if key == self._key:
             return self.buf
         for p in self._plist:
             if p.device != self.device or p.dtype != F32:
                 raise capi.GenieError('association parameters must be fp32 tensors on %s' % self.device)
+        w = lambda name: relaid[name] if name in relaid else getattr(da, name).weight
+        for name, n_in in (('init_trns', 50), ('l1_t1_2', 65), ('l1_t2_2', 65), ('l2_t1_2', 95), ('l2_t2_2', 95)):
+            if w(name).shape[1] != n_in:
+                raise capi.GenieError('association weights of a model variant need their re-laid copies (%s)' % name)
+        self._relaid = relaid                                  # keep the tensors alive
         with torch.no_grad():
             self.buf.zero_()
             self._mat('SD_W', sd.f_direct.weight, 32); self._vec('SD_B', sd.f_direct.bias)
             self._mat('RO_WY', ro.fc1.weight[:, 0:30], 32); self._vec('RO_B1', ro.fc1.bias)
             self._mat('RO_WA', ro.fc1.weight[:, 30:33], 32)
             self._mat('RO_W2', ro.fc2.weight, 16); self._vec('RO_B2', ro.fc2.bias)
-            self._mat('AI_W', da.init_trns.weight, 32); self._vec('AI_B', da.init_trns.bias)
+            self._mat('AI_W', w('init_trns'), 32); self._vec('AI_B', da.init_trns.bias)
             self._mat('M11_W', da.l1_t1_1.weight, 32); self._vec('M11_B', da.l1_t1_1.bias)
             self._mat('M12_W', da.l1_t2_1.weight, 32); self._vec('M12_B', da.l1_t2_1.bias)
-            self._mat('W11', da.l1_t1_2.weight, 32); self._vec('B11', da.l1_t1_2.bias)
-            self._mat('W12', da.l1_t2_2.weight, 32); self._vec('B12', da.l1_t2_2.bias)
+            self._mat('W11', w('l1_t1_2'), 32); self._vec('B11', da.l1_t1_2.bias)
+            self._mat('W12', w('l1_t2_2'), 32); self._vec('B12', da.l1_t2_2.bias)
             self._mat('W21A', da.l2_t1_1.weight, 32); self._vec('B21A', da.l2_t1_1.bias)
             self._mat('W22A', da.l2_t2_1.weight, 32); self._vec('B22A', da.l2_t2_1.bias)
-            for wv, wc, bc, lin in (('WVA', 'WCA', 'BCA', da.l2_t1_2), ('WVB', 'WCB', 'BCB', da.l2_t2_2)):
-                self._mat(wv, lin.weight[:, 60:90], 16)
-                self._mat(wc, torch.cat((lin.weight[:, 0:60], lin.weight[:, 90:95]), dim=1), 16)
-                self._vec(bc, lin.bias)
+            for wv, wc, bc, nm in (('WVA', 'WCA', 'BCA', 'l2_t1_2'), ('WVB', 'WCB', 'BCB', 'l2_t2_2')):
+                self._mat(wv, w(nm)[:, 60:90], 16)
+                self._mat(wc, torch.cat((w(nm)[:, 0:60], w(nm)[:, 90:95]), dim=1), 16)
+                self._vec(bc, getattr(da, nm).bias)
             for pre, m in (('CP', cp), ('CS', cs)):
                 self._mat(pre + '_W1', m.fc1.weight, 32); self._vec(pre + '_B1', m.fc1.bias)
                 self._mat(pre + '_W2', m.fc2.weight, 16); self._vec(pre + '_B2', m.fc2.bias)

@@ -296,6 +296,13 @@ class GraphPlan(object):
                                                          capi.dptr(t_src, torch.float32, 'init_src')))
         self._init_terms = (t_sta, t_src)              # keep the tensors alive
 
+    def set_assoc_terms(self, init_sta, init_src, edge_sta, edge_src):
+        """genie_assoc_set_terms: the init / edge-term tables of the association branch's model variants (None = off)."""
+        capi.check(capi.load().genie_assoc_set_terms(
+            self.handle, capi.dptr(init_sta, torch.float32, 'assoc init_sta'), capi.dptr(init_src, torch.float32, 'assoc init_src'),
+            capi.dptr(edge_sta, torch.float32, 'assoc edge_sta'), capi.dptr(edge_src, torch.float32, 'assoc edge_src')))
+        self._assoc_terms = (init_sta, init_src, edge_sta, edge_src)       # keep the tensors alive
+
     def node_grid_index(self):
         """int64 [P]: grid node of every product node (CARTESIAN: i // n_sta; EXPLICIT: the read-in target list)."""
         if self.prod_grid is not None:

@@ -253,6 +253,16 @@ GENIE_API int genie_knn_fwd(const float* x_dev, int n_x, const float* y_dev, int
 GENIE_API size_t genie_assoc_packed_floats(void);
 GENIE_API int genie_assoc_layout(int32_t* offsets_out, int n);
 GENIE_API size_t genie_assoc_workspace_bytes(const genie_plan_t* plan);
+/* Model variants of the association branch, by the same linearity arguments as genie_plan_set_init_terms /
+ * genie_plan_set_edge_terms (all tables the caller's, window-independent; NULL = off):
+ *   `use_absolute_pos: True` (module.py:987-988): init_sta_dev / init_src_dev [S][32] / [G][32] (CARTESIAN) or [P][32] / NULL
+ *       = DataAggregationAssociationPhase.init_trns.weight[:, 15:18] . locs / (3 scale_rel) and [:, 18:21] . x_temp / (3 scale_rel);
+ *       the packed init_trns then has its six position columns removed ([30][50]).
+ *   `use_updated_model_definition: True` (DataAggregationAssociationPhaseEdges, module.py:406-481): edge_sta_dev / edge_src_dev
+ *       [S or P][GENIE_EDGE_TERM_LD] / [G or P][GENIE_EDGE_TERM_LD] with [0,30) = l1_t*_2.weight[:, 60:64] . mean pos_rel and
+ *       [32,47) = l2_t*_2.weight[:, 90:94] . mean pos_rel; the packed l1_t*_2 / l2_t*_2 then lack those four columns. */
+GENIE_API int genie_assoc_set_terms(genie_plan_t* plan, const float* init_sta_dev, const float* init_src_dev,
+                                    const float* edge_sta_dev, const float* edge_src_dev);
 GENIE_API int genie_assoc_product_fwd(const genie_plan_t* plan, const float* assoc_packed_dev, const float* x_spatial_dev,
                                       int ld_x, const float* y_dev, int n_t, float mask_thresh, const float* edge_attr_dev,
                                       const float* x_latent_dev, const float* mask_dev, void* assoc_workspace_dev,

@@ -204,7 +204,7 @@ def legacy_input():
               [int((np.asarray(x) > 0).sum()) for x in Inpts], Inpts[0].dtype, Inpts[0].shape)
 
 
-def association():
+def association(edges=False, abs_pos=False):
     """§8f rank 2: `forward_fixed` (module.py:963-997) of the UNMODIFIED reference — front end + heads + association branch
     (BipartiteGraphReadOutOperator, DataAggregationAssociationPhase, LocalSliceLgCollapse{P,S}, Arrivals).  Set-up as in
     process_continuous_days.py:627-634; the time-pointer tables through the reference's own
@@ -212,14 +212,26 @@ def association():
     work = tempfile.mkdtemp(prefix='genie_golden_')
     for f in ('config.yaml', 'train_config.yaml'):
         shutil.copy(os.path.join(REF, 'Code', f), work)
+    if edges or abs_pos:
+        import re
+        cfg = open(os.path.join(work, 'config.yaml')).read()
+        for on, key in ((edges, 'use_updated_model_definition'), (abs_pos, 'use_absolute_pos')):
+            if on:
+                cfg, n = re.subn(r'(?m)^%s:\s*\w+' % key, '%s: True' % key, cfg)
+                assert n == 1
+        open(os.path.join(work, 'config.yaml'), 'w').write(cfg)
     torch, module, pu, Data = _import_reference(os.path.join(REF, 'Code'), work)
+    assert bool(module.use_updated_model_definition) == edges and bool(module.use_absolute_pos) == abs_pos
     from genie_b200 import synth
 
     def identity(x):
         return x
 
-    for name, S_all, n_use, G, k_sta, k_spc, Q, n_src, seed in (('assoc_10x100', 10, 10, 100, 8, 15, 32, 3, 0),
-                                                                ('assoc_18of20x160', 20, 18, 160, 8, 15, 48, 2, 9)):
+    cases = (('assoc_10x100', 10, 10, 100, 8, 15, 32, 3, 0), ('assoc_18of20x160', 20, 18, 160, 8, 15, 48, 2, 9))
+    if edges or abs_pos:      # one case per variant: station subset, 14 x 120
+        cases = (('assoc_14of16x120' + ('_edges' if edges else '') + ('_abspos' if abs_pos else ''), 16, 14, 120, 8, 15, 32, 3,
+                  4 + int(edges) + 2 * int(abs_pos)),)
+    for name, S_all, n_use, G, k_sta, k_spc, Q, n_src, seed in cases:
         net = synth.Network(S_all, G, seed=seed, width_km=60.0 if S_all <= 10 else 90.0)
         rng = np.random.default_rng(300 + seed)
         ind_use = np.sort(rng.choice(S_all, size=n_use, replace=False))
@@ -270,8 +282,12 @@ def association():
             ck_name = [n for n in z.namelist() if n.endswith('trained_gnn_model_step_20000_ver_1.h5')][0]
             z.extract(ck_name, work)
         ck = torch.load(os.path.join(work, ck_name), map_location='cpu')
+        own = mz.state_dict()
+        if edges or abs_pos:   # the variants widen some Linear layers: those keep their default initialisation
+            ck = {k: v for k, v in ck.items() if k in own and tuple(own[k].shape) == tuple(v.shape)}
         missing = mz.load_state_dict(ck, strict=False)
-        assert not missing.unexpected_keys and all(k.startswith('SpatialAttention.f_queries') for k in missing.missing_keys)
+        assert not missing.unexpected_keys
+        assert edges or abs_pos or all(k.startswith('SpatialAttention.f_queries') for k in missing.missing_keys)
         # window: the first origin time (3 s steps) whose source mask is a clear mixture — at least 8 % of either value and
         # every grid node's y.max at least 2e-3 * max|y| away from the 0.01 threshold
         for t0 in 200.0 + 3.0 * seed + 3.0 * np.arange(120):
@@ -342,6 +358,10 @@ if __name__ == '__main__':
         legacy_input()
     elif mode == 'association':
         association()
+    elif mode == 'association_edges':
+        association(edges=True)
+    elif mode == 'association_abspos':
+        association(abs_pos=True)
     elif mode == 'ferndale':
         from gen_golden_ferndale import ferndale
         ferndale()

@@ -483,15 +483,20 @@ def bipartite_read_out(sd, pre, y_latent, edge_attr, edge_index, mask_out):
     return out, mj
 
 
-def data_aggregation_association(sd, pre, s, x_latent, mask1, mask2, A_in_sta, A_in_src, return_parts=False):
+def data_aggregation_association(sd, pre, s, x_latent, mask1, mask2, A_in_sta, A_in_src, return_parts=False, pos_rel=None):
     """DataAggregationAssociationPhase.forward, module.py:387-403 (`use_updated_model_definition: False`).  Unlike
-    DataAggregation, the layer-1 messages pass through l1_t*_1 first and the mask has five channels."""
+    DataAggregation, the layer-1 messages pass through l1_t*_1 first and the mask has five channels.
+    `pos_rel` = (pos_rel_sta, pos_rel_src): DataAggregationAssociationPhaseEdges, module.py:442-481 — every message is
+    [x_j | pos_rel(edge)] (message_type 1 / 2)."""
     n = s.shape[0]
     mask = torch.cat((mask1, mask2), dim=-1)
     tr = _prelu(sd, pre + 'activate', _lin(sd, pre + 'init_trns', torch.cat((s, x_latent, mask), dim=-1)))
 
     def agg(x, A):
-        return propagate_mean(x.index_select(0, A[0]), A[1], n)
+        msg = x.index_select(0, A[0])
+        if pos_rel is not None:
+            msg = torch.cat((msg, pos_rel[0] if A is A_in_sta else pos_rel[1]), dim=1)
+        return propagate_mean(msg, A[1], n)
 
     a1 = _prelu(sd, pre + 'activate11', _lin(sd, pre + 'l1_t1_1', tr))
     a2 = _prelu(sd, pre + 'activate12', _lin(sd, pre + 'l1_t2_1', tr))
@@ -595,10 +600,10 @@ def station_source_attention(sd, pre, stime, src_embed, trv_src, arrival_p, arri
 def forward_fixed(sd, Slice, Mask, A_in_sta, A_in_src, read_in_attr, read_in_index, A_src, grid_cart, A_edges_p,
                   A_edges_s, dt_partition, tlatent, tpick, ipick, phase_label, x_query_cart, x_query_src_cart, t_query,
                   tq_sample, trv_out_q, scale_rel, scale_t, eps, return_parts=False, query_edges=None,
-                  query_src_edges=None):
+                  query_src_edges=None, pos_rel=None, abs_pos=None):
     """module.py:963-997 (= forward, :908-939, with the adjacencies passed per call): returns y, x, arv_p, arv_s."""
     x_spatial, parts = front_end(sd, Slice, Mask, A_in_sta, A_in_src, read_in_attr, read_in_index, A_src, grid_cart,
-                                 scale_rel, return_parts=True)
+                                 scale_rel, return_parts=True, pos_rel=pos_rel, abs_pos=abs_pos)
     x_latent = parts['x_latent']
     y_latent = spatial_direct(sd, 'SpatialDirect.', x_spatial)
     y = temporal_attention(sd, 'TemporalAttention.', y_latent, t_query, scale_t)
@@ -609,8 +614,11 @@ def forward_fixed(sd, Slice, Mask, A_in_sta, A_in_src, read_in_attr, read_in_ind
     mask_out = 1.0 * (y[:, :, 0].max(1, keepdim=True)[0] > 0.01)                                              # :983
     A_Lg = torch.stack((read_in_index[1], read_in_index[0]))                     # process_continuous_days.py:632
     s0, mask_out_1 = bipartite_read_out(sd, 'BipartiteGraphReadOutOperator.', y_latent, read_in_attr, A_Lg, mask_out)
-    s = data_aggregation_association(sd, 'DataAggregationAssociationPhase.', s0, x_latent, mask_out_1, Mask, A_in_sta,
-                                     A_in_src)
+    s_in = s0
+    if abs_pos is not None:                                                                                   # :987-988
+        s_in = absolute_pos_channels(s0, abs_pos[0], grid_cart, abs_pos[1], scale_rel)
+    s = data_aggregation_association(sd, 'DataAggregationAssociationPhase.', s_in, x_latent, mask_out_1, Mask, A_in_sta,
+                                     A_in_src, pos_rel=pos_rel)
     arv_p = local_slice_collapse(sd, 'LocalSliceLgCollapseP.', A_edges_p, dt_partition, tpick, ipick, phase_label, s,
                                  tlatent[:, 0].reshape(-1, 1), eps)
     arv_s = local_slice_collapse(sd, 'LocalSliceLgCollapseS.', A_edges_s, dt_partition, tpick, ipick, phase_label, s,

@@ -21,9 +21,10 @@ def _dev():
     return torch.device('cuda:0')
 
 
-def _model(sd, dev, scale_rel, scale_t, updated_model=False):
+def _model(sd, dev, scale_rel, scale_t, updated_model=False, use_absolute_pos=False):
     from genie_b200.module import GCN_Detection_Network_extended
-    m = GCN_Detection_Network_extended(None, None, scale_rel=scale_rel, device=dev, updated_model=updated_model)
+    m = GCN_Detection_Network_extended(None, None, scale_rel=scale_rel, device=dev, updated_model=updated_model,
+                                       use_absolute_pos=use_absolute_pos)
     m.load_state_dict(sd)
     m.TemporalAttention.scale_t = scale_t
     m.eval()
@@ -553,12 +554,14 @@ def test_sharded_front_end_single_process():
 # ---- association branch: forward_fixed / forward ------------------------------------------------------
 
 ASSOC = ['assoc_10x100', 'assoc_18of20x160']
+ASSOC_VARIANTS = ['assoc_14of16x120_edges', 'assoc_14of16x120_abspos']       # use_updated_model_definition / use_absolute_pos
 
 
-def _assoc_setup(d, sd, dev):
+def _assoc_setup(d, sd, dev, name=''):
     from oracle.refshim.torch_geometric.data import Data
     A_sta, A_src, A_ps, A_pg, A_sip, A_sis = _graphs(d)
-    m = _model(sd, dev, float(d['scale_rel']), float(d['scale_t']))
+    m = _model(sd, dev, float(d['scale_rel']), float(d['scale_t']), updated_model=name.endswith('_edges'),
+               use_absolute_pos=name.endswith('_abspos'))
     t = lambda k: torch.from_numpy(d[k]).to(dev)
     locs = torch.from_numpy(d['sta'][d['ind_use']]).float().to(dev)
     grid = torch.from_numpy(d['grid']).float().to(dev)
@@ -572,14 +575,14 @@ def _assoc_setup(d, sd, dev):
     return m, graphs, window, locs, grid
 
 
-@pytest.mark.parametrize('name', ASSOC)
+@pytest.mark.parametrize('name', ASSOC + ASSOC_VARIANTS)
 def test_forward_fixed_matches_reference(name):
     """forward_fixed (module.py:963-997) through the nn.Module surface against the unmodified reference, plus the
     intermediate tensors of the association kernels through the operator-level C-ABI wrappers."""
     from genie_b200 import capi, ops
     dev = _dev()
     d, sd = load_golden(name)
-    m, graphs, window, locs, grid = _assoc_setup(d, sd, dev)
+    m, graphs, window, locs, grid = _assoc_setup(d, sd, dev, name)
     m.set_adjacencies(*graphs, locs, grid)
     t = lambda k: torch.from_numpy(d[k]).to(dev)
     n0 = capi.launch_count()
@@ -590,7 +593,7 @@ def test_forward_fixed_matches_reference(name):
     assert rel_err(arv_p.cpu().numpy(), d['arv_p']) < TOL
     assert rel_err(arv_s.cpu().numpy(), d['arv_s']) < TOL
     # operator level
-    packed = m._assoc_w.update(m)
+    packed = m._assoc_w.update(m, m._update_assoc_terms(locs, grid))
     s_rows, s0, mask_out = ops.assoc_product_fwd(m._plan, packed, t('x_spatial'), t('y').reshape(len(d['grid']), -1),
                                                  t('read_in_attr'), t('x_latent'), t('Mask'), want_parts=True)
     S = len(d['ind_use'])
