@@ -97,6 +97,8 @@ SIGNATURES = {
     'genie_heads_grid_fwd': (ctypes.c_int, [_P, _P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int, _P, _P]),
     'genie_heads_query_fwd': (ctypes.c_int, [_P, _P, ctypes.c_int, _P, ctypes.c_int, _P, _P, _P, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_float, _P, _P]),
+    'genie_kron_spmm_fwd': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, _P, _P, _P, _P, ctypes.c_int,
+                                           ctypes.c_int, _P, ctypes.c_int, _P]),
     'genie_stack_output_fwd': (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, ctypes.c_float, _P, ctypes.c_int64,
                                               _P]),
     'genie_knn_fwd': (ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int, _P, _P]),

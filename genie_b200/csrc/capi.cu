@@ -35,7 +35,7 @@ const char* const kKernelNames[KID_COUNT] = {"pack_weights_kernel", "input_serie
                                              "src_mean32_kernel",   "src_mean16_kernel",   "da_layer1_s_kernel",
                                              "da_layer2_s_kernel",  "heads_grid_kernel",   "heads_query_kernel",
                                              "assoc_grid_pre_kernel", "assoc_init_kernel", "assoc_layer1_kernel",
-                                             "assoc_layer2_kernel", "assoc_collapse_kernel", "knn_kernel", "stack_output_kernel"};
+                                             "assoc_layer2_kernel", "assoc_collapse_kernel", "knn_kernel", "stack_output_kernel", "kron_spmm_kernel"};
 }  // namespace
 
 TimedLaunch::TimedLaunch(int kid_, cudaStream_t st_) : kid(kid_), st(st_), slot(nullptr) {
@@ -361,6 +361,21 @@ int genie_input_nearest_fwd(const genie_nearest_params_t* prm, const double* tim
     }
     return launch_input_nearest(prm, times_all_dev, times_p_dev, times_s_dev, ind_use_dev, trv_times_dev, slice_out_dev,
                                 mask_out_dev, static_cast<cudaStream_t>(stream));
+}
+
+// ---- product-graph message passing of the training path -----------------------------------------------------------------------
+int genie_kron_spmm_fwd(int mode, int n_sta, int n_grid, int64_t n_prod, const int64_t* rowptr_dev, const int32_t* col_dev,
+                        const float* val_dev, const float* x_dev, int ld_x, int n_ch, float* out_dev, int ld_out, void* stream) {
+    if (mode < 0 || mode > 2 || n_prod < 0 || n_ch < 0 || ld_x < n_ch || ld_out < n_ch || !rowptr_dev ||
+        (mode != 2 && (n_sta <= 0 || n_grid <= 0 || n_prod != (int64_t)n_sta * n_grid)) ||
+        (n_prod > 0 && n_ch > 0 && (!x_dev || !out_dev))) {
+        set_error("genie_kron_spmm_fwd: bad argument");
+        return GENIE_ERR_INVALID;
+    }
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return launch_kron_spmm(mode, n_sta, n_prod, rowptr_dev, col_dev, val_dev, x_dev, ld_x, n_ch, out_dev, ld_out, sms,
+                            static_cast<cudaStream_t>(stream));
 }
 
 // ---- output stacking of the streaming loop ------------------------------------------------------------

@@ -104,6 +104,7 @@ enum KernelId {
     KID_ASSOC_COLLAPSE,
     KID_KNN,
     KID_STACK,
+    KID_KRON_SPMM,
     KID_COUNT
 };
 // Brackets one kernel launch with cudaEvents on its stream when timing is enabled (no-op otherwise).
@@ -195,6 +196,8 @@ int launch_assoc_collapse(const float* packed, const float* s_rows, int64_t P, c
                           int l_dt, int k_infer, float dt0, float dt_step, float eps, float* arrival, cudaStream_t st);
 int launch_stack_output(const float* x, int Q, int T, int n_use, const int32_t* col, float scale, float* out, int64_t ld_out,
                         cudaStream_t st);
+int launch_kron_spmm(int mode, int S, int64_t P, const int64_t* rowptr, const int32_t* col, const float* val, const float* X,
+                     int ld_x, int C, float* out, int ld_o, int sm_count, cudaStream_t st);
 int launch_knn(const float* x, int n_x, const float* y, int n_y, int k, int64_t* idx_out, cudaStream_t st);
 int launch_input_nearest(const genie_nearest_params_t* prm, const double* t_all, const double* t_p, const double* t_s,
                          const int32_t* ind_use, const float* trv_times, float* slice_out, float* mask_out, cudaStream_t st);

@@ -508,7 +508,7 @@ class GCN_Detection_Network_extended(nn.Module):
         self._plan.set_edge_terms(t_sta, t_src)
         return self._edge_terms
 
-    def _plan_for(self, A_in_sta, A_in_src, A_src_in_edges, A_src, n_sta, n_grid, dev):
+    def _plan_for(self, A_in_sta, A_in_src, A_src_in_edges, A_src, n_sta, n_grid, dev, pos=None, A_src_in_sta=None):
         """`forward` receives the graphs on every call (module.py:908): plans are cached on tensor identity."""
         key = (A_in_sta.data_ptr(), A_in_src.data_ptr(), A_src_in_edges.edge_index.data_ptr(), A_src.data_ptr(),
                A_in_sta.shape[1], A_in_src.shape[1], n_sta, n_grid)
@@ -517,8 +517,10 @@ class GCN_Detection_Network_extended(nn.Module):
                                                    device=dev)
             self._read_in_attr = A_src_in_edges.x.to(dev).float().contiguous()
             self._plan_key = key
-            if self.updated_model:
-                raise NotImplementedError('genie_b200: the updated model needs set_adjacencies (positions) first')
+            if self.updated_model:        # module.py:1059-1072: the edge features come from the positions of the call
+                if pos is None:
+                    raise RuntimeError('the updated model needs the station / grid positions to build its edge features')
+                self._set_edge_means(pos[0], pos[1], A_src_in_sta)
         return self._plan
 
     # -- CUDA front end ------------------------------------------------------------------------------------------------
@@ -572,8 +574,8 @@ class GCN_Detection_Network_extended(nn.Module):
         if torch.is_grad_enabled() and (Slice.requires_grad or any(p.requires_grad for p in
                                                                    self.DataAggregation.parameters())) \
                 and self.training:
-            raise NotImplementedError('genie_b200: backward of the CUDA front end is not implemented yet; '
-                                      'call under torch.no_grad() / model.eval()')
+            raise NotImplementedError('genie_b200: the fused inference kernels keep no activations; for gradients call '
+                                      'forward(...) (the differentiable path), else use torch.no_grad() / model.eval()')
         init_relaid = None
         if self.use_absolute_pos:
             if locs_use_cart is None:
@@ -719,13 +721,19 @@ class GCN_Detection_Network_extended(nn.Module):
                 A_edges_s, dt_partition, tlatent, tpick, ipick, phase_label, locs_use_cart, x_temp_cuda_cart,
                 x_query_cart, x_query_src_cart, t_query, tq_sample, trv_out_q):
         """module.py:908-939: forward_fixed with the adjacencies passed on every call (plans are cached on tensor identity).
-        Inference only: the backward kernels (training, BASELINE.json configs[2]) are not built, so a call that would
-        need gradients raises instead of silently returning detached outputs."""
-        if torch.is_grad_enabled() and self.training:
-            raise NotImplementedError('genie_b200: backward of the CUDA front end is not implemented yet; '
-                                      'call under torch.no_grad() / model.eval()')
+        Under torch.no_grad() the fused inference kernels run; with gradients enabled (training) the differentiable path of
+        genie_b200/training.py does."""
         n_sta, n_grid = int(locs_use_cart.shape[0]), int(x_temp_cuda_cart.shape[0])
-        self._plan_for(A_in_sta, A_in_src, A_src_in_edges, A_src, n_sta, n_grid, Slice.device)
+        self._plan_for(A_in_sta, A_in_src, A_src_in_edges, A_src, n_sta, n_grid, Slice.device,
+                       pos=(locs_use_cart, x_temp_cuda_cart), A_src_in_sta=A_src_in_sta)
+        self.A_src_in_sta = A_src_in_sta
+        if torch.is_grad_enabled():
+            # training (train_GENIE_model.py:1786): the differentiable path — the reference's operator graph with the
+            # product-graph message passing (forward and backward) on libgenie_b200's gather kernel (genie_b200/training.py)
+            from . import training
+            return training.forward_train(self, Slice, Mask, A_Lg_in_src, A_src, A_edges_p, A_edges_s, dt_partition, tlatent,
+                                          tpick, ipick, phase_label, locs_use_cart, x_temp_cuda_cart, x_query_cart,
+                                          x_query_src_cart, t_query, tq_sample, trv_out_q)
         return self._association(Slice, Mask, A_Lg_in_src, A_edges_p, A_edges_s, dt_partition, tlatent, tpick, ipick,
                                  phase_label, locs_use_cart, x_temp_cuda_cart, x_query_cart, x_query_src_cart, t_query,
                                  tq_sample, trv_out_q)

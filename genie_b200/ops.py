@@ -338,6 +338,24 @@ def assoc_collapse_fwd(packed, s_rows, A_edges_p, A_edges_s, dt_partition, tlate
     return arrival
 
 
+def kron_spmm(kg, csr, x):
+    """out[i] = sum_e val[e] * x[nbr(i, e)] over one edge type of the product graph (genie_kron_spmm_fwd): the mean
+    aggregation of `propagate` (csr = kg.fwd) or its gradient (csr = kg.rev).  x: fp32 CUDA [P, C]."""
+    if x.dtype != F32:
+        x = x.float()
+    x = x.contiguous()
+    if x.dim() != 2 or x.shape[0] != kg.n_prod:
+        raise capi.GenieError('kron_spmm: x must be [P, C] with P = %d' % kg.n_prod)
+    rowptr, col, val = csr
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        capi.check(capi.load().genie_kron_spmm_fwd(
+            int(kg.mode), int(kg.n_sta), int(kg.n_grid), int(kg.n_prod), capi.dptr(rowptr, torch.int64, 'rowptr'),
+            capi.dptr(col, torch.int32, 'col'), capi.dptr(val, F32, 'val'), capi.dptr(x, F32, 'x'), int(x.shape[1]),
+            int(x.shape[1]), capi.dptr(out), int(x.shape[1]), capi.stream_ptr(x.device)))
+    return out
+
+
 def knn(x, y, k):
     """torch_cluster.knn(x, y, k) on the device (genie_knn_fwd): int64 [n_y, k], the k rows of x nearest to every row of y,
     nearest first.  x, y: fp32 CUDA tensors [n, 3] (kilometres, as the reference passes them)."""

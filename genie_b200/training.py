@@ -1,0 +1,202 @@
+"""Differentiable forward of `GCN_Detection_Network_extended` for training (module.py:908-939, `mz(*input_tensors)` at
+train_GENIE_model.py:1786; BASELINE.json configs[2]).
+
+The inference path (`forward_fixed_source`, `forward_fixed`) runs fused kernels that keep no activations.  Training needs
+gradients with respect to every parameter, so this path keeps the reference's operator graph — and replaces the part of it
+that costs the reference >= 85 % of its time: `MessagePassing.propagate` over the product graph, i.e. an
+`index_select` that materialises an [E, 30] tensor (E = 15 P) followed by `scatter_add_`, in the forward AND in the backward
+pass.  Here that pair is ONE gather kernel per direction (`genie_kron_spmm_fwd`: the product graph as the Kronecker product of
+a small CSR matrix with an identity, forward by target, backward by source, no atomics), wrapped in `MeanAggregate`.  The dense
+per-node Linear / PReLU layers stay torch ops (plain library GEMMs with autograd); the grid-sized SpatialAggregation layers and
+the pick-sized heads / association modules are index ops on small tensors.
+
+Nothing here touches the CPU: `ops.kron_spmm` raises on host tensors.
+"""
+import numpy as np
+import torch
+
+from . import capi, ops
+
+
+class KronGraph(object):
+    """One edge type of the product graph: forward CSR (by target, val = 1/in-degree) and its transpose (by source)."""
+
+    def __init__(self, mode, n_sta, n_grid, n_prod, rowptr, col, device):
+        self.mode, self.n_sta, self.n_grid, self.n_prod = int(mode), int(n_sta), int(n_grid), int(n_prod)
+        rowptr = rowptr.to(device).long().contiguous()
+        col = col.to(device).to(torch.int32).contiguous()
+        n = rowptr.numel() - 1
+        deg = rowptr[1:] - rowptr[:-1]
+        tgt = torch.repeat_interleave(torch.arange(n, device=device), deg)
+        w = 1.0 / deg.clamp(min=1).float()
+        self.fwd = (rowptr, col, w[tgt].contiguous())
+        order = torch.sort(col.long(), stable=True)[1]                  # edges grouped by source
+        rrow = torch.zeros(n + 1, dtype=torch.long, device=device)
+        rrow[1:] = torch.cumsum(torch.bincount(col.long(), minlength=n), 0)
+        self.rev = (rrow.contiguous(), tgt[order].to(torch.int32).contiguous(), w[tgt][order].contiguous())
+
+
+def build_kron_graphs(plan):
+    """(station-edge graph, source-edge graph) of a GraphPlan: the small kNN graphs for CARTESIAN plans, the explicit
+    product-level CSR otherwise."""
+    dev = plan.device
+    if plan.mode == capi.GRAPH_CARTESIAN:
+        return (KronGraph(0, plan.n_sta, plan.n_grid, plan.n_prod, plan.sta_rowptr, plan.sta_col, dev),
+                KronGraph(1, plan.n_sta, plan.n_grid, plan.n_prod, plan.src_rowptr, plan.src_col, dev))
+    return (KronGraph(2, 0, 0, plan.n_prod, plan.sta_rowptr, plan.sta_col, dev),
+            KronGraph(2, 0, 0, plan.n_prod, plan.src_rowptr, plan.src_col, dev))
+
+
+class MeanAggregate(torch.autograd.Function):
+    """`propagate(A, x=x)` with aggr='mean' and message = x_j (module.py:90-95), forward and backward on libgenie_b200."""
+
+    @staticmethod
+    def forward(ctx, x, kg):
+        ctx.kg = kg
+        return ops.kron_spmm(kg, kg.fwd, x)
+
+    @staticmethod
+    def backward(ctx, grad):
+        return ops.kron_spmm(ctx.kg, ctx.kg.rev, grad), None
+
+
+def mean_aggregate(x, kg):
+    return MeanAggregate.apply(x.contiguous(), kg)
+
+
+# ---- the modules of module.py as differentiable functions of the parameter holders ----------------------------------------
+
+def _expand_edge_means(model, kg_sta):
+    """Updated model: mean over in-edges of pos_rel for every product node ([P,4] each), from the per-station / per-grid-node
+    (CARTESIAN) or per-node (EXPLICIT) tables of `model._edge_means`."""
+    m_sta, m_src = model._edge_means[0](float(model.scale_rel)), model._edge_means[1](float(model.scale_rel))
+    if kg_sta.mode == 2:
+        return m_sta, m_src
+    return m_sta.repeat(kg_sta.n_grid, 1), m_src.repeat_interleave(kg_sta.n_sta, dim=0)
+
+
+def data_aggregation(da, Slice, Mask, kg_sta, kg_src, edge_means=None):
+    """DataAggregation.forward (module.py:85-98) / DataAggregationEdges.forward (:143-157)."""
+    tr = da.activate(da.init_trns(torch.cat((Slice, Mask), dim=-1)))
+    cat = (lambda a, m, e: torch.cat((a, m, e, Mask), dim=1)) if edge_means is not None else \
+        (lambda a, m, e: torch.cat((a, m, Mask), dim=1))
+    e_sta, e_src = edge_means if edge_means is not None else (None, None)
+    tr1 = da.l1_t1_2(cat(tr, mean_aggregate(da.activate11(tr), kg_sta), e_sta))
+    tr2 = da.l1_t2_2(cat(tr, mean_aggregate(da.activate12(tr), kg_src), e_src))
+    tr = da.activate1(torch.cat((tr1, tr2), dim=1))
+    tr1 = da.l2_t1_2(cat(tr, mean_aggregate(da.activate21(da.l2_t1_1(tr)), kg_sta), e_sta))
+    tr2 = da.l2_t2_2(cat(tr, mean_aggregate(da.activate22(da.l2_t2_1(tr)), kg_src), e_src))
+    return da.activate2(torch.cat((tr1, tr2), dim=1))
+
+
+def data_aggregation_association(da, s, latent, mask1, mask2, kg_sta, kg_src, edge_means=None):
+    """DataAggregationAssociationPhase.forward (module.py:387-403) / ...Edges.forward (:442-467)."""
+    mask = torch.cat((mask1, mask2), dim=-1)
+    tr = da.activate(da.init_trns(torch.cat((s, latent, mask), dim=-1)))
+    cat = (lambda a, m, e: torch.cat((a, m, e, mask), dim=1)) if edge_means is not None else \
+        (lambda a, m, e: torch.cat((a, m, mask), dim=1))
+    e_sta, e_src = edge_means if edge_means is not None else (None, None)
+    tr1 = da.l1_t1_2(cat(tr, mean_aggregate(da.activate11(da.l1_t1_1(tr)), kg_sta), e_sta))
+    tr2 = da.l1_t2_2(cat(tr, mean_aggregate(da.activate12(da.l1_t2_1(tr)), kg_src), e_src))
+    tr = da.activate1(torch.cat((tr1, tr2), dim=1))
+    tr1 = da.l2_t1_2(cat(tr, mean_aggregate(da.activate21(da.l2_t1_1(tr)), kg_sta), e_sta))
+    tr2 = da.l2_t2_2(cat(tr, mean_aggregate(da.activate22(da.l2_t2_1(tr)), kg_src), e_src))
+    return da.activate2(torch.cat((tr1, tr2), dim=1))
+
+
+def bipartite_read_in(ri, x_latent, attr, node_grid, n_grid, Mask):
+    """BipartiteGraphOperator.forward (module.py:224-229): masked per-node MLP summed onto the node's grid node."""
+    h = Mask.max(1, keepdim=True)[0] * ri.activate1(ri.fc1(torch.cat((x_latent, attr), dim=-1)))
+    xg = h.new_zeros((n_grid, h.shape[1])).index_add_(0, node_grid, h)
+    return ri.activate2(ri.fc2(xg))
+
+
+def spatial_aggregation(sa, x, A_src, pos, scale_rel):
+    """SpatialAggregation.forward / message (module.py:243-249); the global feature is a mean over EDGES (:249)."""
+    n = x.shape[0]
+    p = pos / scale_rel
+    src, tgt = A_src[0], A_src[1]
+    xj = x[src]
+    glob = sa.activate3(sa.fglobal(xj)).mean(0, keepdim=True)
+    msg = sa.activate1(sa.fc1(torch.cat((xj, p[tgt] - p[src], glob.expand(xj.shape[0], -1)), dim=-1)))
+    cnt = torch.bincount(tgt, minlength=n).clamp(min=1).to(msg.dtype).unsqueeze(1)
+    agg = msg.new_zeros((n, msg.shape[1])).index_add_(0, tgt, msg) / cnt
+    return sa.activate2(sa.fc2(torch.cat((x, agg), dim=-1)))
+
+
+def bipartite_read_out(ro, y_latent, attr, node_grid, mask_out):
+    """BipartiteGraphReadOutOperator.forward (module.py:344-352) for the read-out graph [g(i); i]."""
+    mj = mask_out[node_grid]
+    h = mj * ro.activate1(ro.fc1(torch.cat((y_latent[node_grid], attr), dim=-1)))
+    return ro.activate2(ro.fc2(h)), mj
+
+
+def local_slice_collapse(cm, A_edges, dt_partition, tpick, ipick, phase_label, s, tlatent, k_infer=10):
+    """LocalSliceLgCollapse.forward / message (module.py:624-653)."""
+    n_arv, l_dt = tpick.shape[0], dt_partition.shape[0]
+    dev = s.device
+    dt = dt_partition[1] - dt_partition[0]
+    ph = phase_label.reshape(-1, 1).float()
+    if not cm.use_phase_types:
+        ph = ph * 0.0
+    t_index = torch.floor((tpick - dt_partition[0]) / dt).long()
+    t_index = ((ipick * l_dt * k_infer + t_index * k_infer).view(-1, 1) + torch.arange(k_infer, device=dev).view(1, -1)).reshape(-1)
+    e1 = torch.arange(n_arv, device=dev).repeat_interleave(k_infer)
+    e0 = A_edges[t_index].long()
+    keep = torch.nonzero((tpick[e1] - tlatent[e0, 0]).abs() < 2.0 * cm.eps, as_tuple=True)[0]
+    e0, e1 = e0[keep], e1[keep]
+    msg = cm.activate1(cm.fc1(torch.cat((s[e0], (tpick.view(-1, 1)[e1] - tlatent[e0]) / cm.eps, ph[e1]), dim=-1)))
+    cnt = torch.bincount(e1, minlength=n_arv).clamp(min=1).to(msg.dtype).unsqueeze(1)
+    agg = msg.new_zeros((n_arv, msg.shape[1])).index_add_(0, e1, msg) / cnt
+    return cm.activate2(cm.fc2(agg))
+
+
+def forward_train(model, Slice, Mask, A_Lg_in_src, A_src, A_edges_p, A_edges_s, dt_partition, tlatent, tpick, ipick,
+                  phase_label, locs_use_cart, x_temp_cuda_cart, x_query_cart, x_query_src_cart, t_query, tq_sample, trv_out_q):
+    """module.py:908-939 with autograd: returns (y, x, arv_p, arv_s).  `model._plan` must be the plan of the call's graphs."""
+    plan = model._plan
+    if not Slice.is_cuda:
+        raise capi.GenieError('genie_b200 has no CPU path: inputs must be CUDA tensors')
+    key = id(plan)
+    if getattr(model, '_kron', None) is None or model._kron[0] != key:
+        model._kron = (key,) + build_kron_graphs(plan)
+    kg_sta, kg_src = model._kron[1], model._kron[2]
+    node_grid = plan.node_grid_index()
+    Slice, Mask = Slice.float(), Mask.float()
+    scale = float(model.scale_rel)
+    edge_means = _expand_edge_means(model, kg_sta) if model.updated_model else None
+    abs_ch = None
+    if model.use_absolute_pos:                                                                               # :913-914
+        if plan.mode == capi.GRAPH_CARTESIAN:
+            abs_ch = torch.cat((locs_use_cart.repeat(plan.n_grid, 1), x_temp_cuda_cart.repeat_interleave(plan.n_sta, dim=0)),
+                               dim=1) / (3.0 * scale)
+        else:
+            idx = model.A_src_in_sta.to(Slice.device).long()
+            abs_ch = torch.cat((locs_use_cart[idx[0]], x_temp_cuda_cart[idx[1]]), dim=1) / (3.0 * scale)
+        Slice = torch.cat((Slice, abs_ch), dim=1)
+    attr = model._read_in_attr
+    x_latent = data_aggregation(model.DataAggregation, Slice, Mask, kg_sta, kg_src, edge_means)
+    x = bipartite_read_in(model.Bipartite_ReadIn, x_latent, attr, node_grid, plan.n_grid, Mask)
+    A_src = A_src.to(x.device).long()
+    x = spatial_aggregation(model.SpatialAggregation1, x, A_src, x_temp_cuda_cart, scale)
+    x = spatial_aggregation(model.SpatialAggregation2, x, A_src, x_temp_cuda_cart, scale)
+    x_spatial = spatial_aggregation(model.SpatialAggregation3, x, A_src, x_temp_cuda_cart, scale)
+    y_latent = model.SpatialDirect(x_spatial)
+    y = model.TemporalAttention(y_latent, t_query)
+    x = model.SpatialAttention(x_spatial, x_query_cart, x_temp_cuda_cart)
+    x_src = model.SpatialAttention(x_spatial, x_query_src_cart, x_temp_cuda_cart, cache=False)
+    x = model.TemporalAttention(x, t_query)
+    mask_out = 1.0 * (y[:, :, 0].detach().max(1, keepdim=True)[0] > 0.01).detach()                           # :926
+    ro_attr = attr if A_Lg_in_src is None else model._check_read_out_graph(A_Lg_in_src)
+    s, mask_out_1 = bipartite_read_out(model.BipartiteGraphReadOutOperator, y_latent, ro_attr, node_grid, mask_out)
+    if abs_ch is not None:
+        s = torch.cat((s, abs_ch), dim=1)                                                                    # :930-931
+    s = data_aggregation_association(model.DataAggregationAssociationPhase, s, x_latent.detach(), mask_out_1, Mask, kg_sta,
+                                     kg_src, edge_means)                                                     # :932
+    dtp, tl = dt_partition.to(s.device).float(), tlatent.to(s.device).float()
+    arv_p = local_slice_collapse(model.LocalSliceLgCollapseP, A_edges_p.to(s.device), dtp, tpick, ipick, phase_label, s,
+                                 tl[:, 0].reshape(-1, 1))
+    arv_s = local_slice_collapse(model.LocalSliceLgCollapseS, A_edges_s.to(s.device), dtp, tpick, ipick, phase_label, s,
+                                 tl[:, 1].reshape(-1, 1))
+    arv = model.Arrivals(x_query_src_cart, tq_sample, x_src, trv_out_q, locs_use_cart, arv_p, arv_s, tpick, ipick, phase_label)
+    return y, x, arv[:, :, 0].unsqueeze(-1), arv[:, :, 1].unsqueeze(-1)

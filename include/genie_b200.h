@@ -213,6 +213,20 @@ GENIE_API int genie_heads_query_fwd(const float* heads_packed_dev, const float* 
                                     int ld_x, const float* x_context_dev, const float* x_query_dev, const int64_t* nbr_dev,
                                     int k_nbr, int n_query, float scale_rel, float* x_out_dev, void* stream);
 
+/* ---- product-graph message passing of the training path (BASELINE.json configs[2]) -----------------------------------------
+ * Replaces `MessagePassing.propagate(A_in_sta / A_in_src, x=...)` with aggr='mean' (module.py:90-95, 394-400) AND its
+ * gradient, i.e. the reference's index_select + scatter_add_ pair in both directions:
+ *     out[i, 0:n_ch] = sum_{e in row(i)} val[e] * x[nbr(i, e), 0:n_ch]
+ * with a small CSR matrix (rowptr int64, col int32, val fp32, all device pointers) applied as a Kronecker product:
+ *   mode 0: node i = g*n_sta + s, row(i) = row s of an [n_sta x n_sta] matrix, nbr = g*n_sta + col   (station edges, :720)
+ *   mode 1: node i = g*n_sta + s, row(i) = row g of an [n_grid x n_grid] matrix, nbr = col*n_sta + s (source edges, :721)
+ *   mode 2: explicit [n_prod x n_prod] matrix (sub-graph mode).
+ * Forward: CSR by target, val = 1/in-degree(target).  Backward of the same op: CSR by source, val = 1/in-degree(edge target).
+ * Both are gathers: no atomics, bit-reproducible.  x_dev [n_prod][ld_x], out_dev [n_prod][ld_out]. */
+GENIE_API int genie_kron_spmm_fwd(int mode, int n_sta, int n_grid, int64_t n_prod, const int64_t* rowptr_dev,
+                                  const int32_t* col_dev, const float* val_dev, const float* x_dev, int ld_x, int n_ch,
+                                  float* out_dev, int ld_out, void* stream);
+
 /* ---- output stacking of the streaming loop --------------------------------------------------------
  * process_continuous_days.py:797-805: Out_2[:, ip_need[t]] += x[:, t, 0] / n_overlap / n_scale_x_grid for the first n_use
  * (all, or all but the last when step_size == 'half') query times of one window, on the device.

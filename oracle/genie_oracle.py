@@ -617,7 +617,8 @@ def forward_fixed(sd, Slice, Mask, A_in_sta, A_in_src, read_in_attr, read_in_ind
     s_in = s0
     if abs_pos is not None:                                                                                   # :987-988
         s_in = absolute_pos_channels(s0, abs_pos[0], grid_cart, abs_pos[1], scale_rel)
-    s = data_aggregation_association(sd, 'DataAggregationAssociationPhase.', s_in, x_latent, mask_out_1, Mask, A_in_sta,
+    # x_latent enters detached, as in the reference (`x_latent.detach()`, :932): no gradient reaches DataAggregation this way
+    s = data_aggregation_association(sd, 'DataAggregationAssociationPhase.', s_in, x_latent.detach(), mask_out_1, Mask, A_in_sta,
                                      A_in_src, pos_rel=pos_rel)
     arv_p = local_slice_collapse(sd, 'LocalSliceLgCollapseP.', A_edges_p, dt_partition, tpick, ipick, phase_label, s,
                                  tlatent[:, 0].reshape(-1, 1), eps)

@@ -610,7 +610,7 @@ def test_forward_fixed_matches_reference(name):
     assert rel_err(arrival[:-1, 15:].cpu().numpy(), d['arv_s_embed']) < TOL
 
 
-def test_forward_equals_forward_fixed_and_refuses_training():
+def test_forward_equals_forward_fixed_with_and_without_gradients():
     """`forward` (module.py:908-939) takes the adjacencies per call; same numbers, and no silent no-grad result in training."""
     dev = _dev()
     d, sd = load_golden(ASSOC[0])
@@ -620,9 +620,12 @@ def test_forward_equals_forward_fixed_and_refuses_training():
         out = m.forward(t('Slice'), t('Mask'), *graphs, *window)
     for a, key in zip(out, ('y', 'x', 'arv_p', 'arv_s')):
         assert rel_err(a.cpu().numpy(), d[key]) < TOL, key
+    # with gradients enabled the differentiable path runs instead (test_training_steps_match_oracle)
     m.train()
-    with pytest.raises(NotImplementedError):
-        m.forward(t('Slice'), t('Mask'), *graphs, *window)
+    out = m.forward(t('Slice'), t('Mask'), *graphs, *window)
+    assert out[0].requires_grad and out[2].requires_grad
+    for a, key in zip(out, ('y', 'x', 'arv_p', 'arv_s')):
+        assert rel_err(a.detach().cpu().numpy(), d[key]) < TOL, key
 
 
 @pytest.mark.parametrize('explicit', [False, True])
@@ -817,3 +820,109 @@ def test_day_processor_matches_oracle_loop(step_size):
     from scipy.spatial import cKDTree
     t = np.random.default_rng(0).uniform(-10.0, 170.0, 500)
     assert np.array_equal(nearest_index(tsteps_abs, t), cKDTree(tsteps_abs.reshape(-1, 1)).query(t.reshape(-1, 1))[1])
+
+
+# ---- training path (BASELINE.json configs[2]): forward with gradients, loss and Adam steps against the oracle ------------------
+
+@pytest.mark.parametrize('mode,C', [(0, 30), (1, 30), (1, 15), (2, 34), (0, 1)])
+def test_kron_spmm_forward_and_transpose(mode, C):
+    """genie_kron_spmm_fwd on the forward (by target) and the transposed (by source) CSR of one edge type against a dense
+    product; together they are the mean aggregation of `propagate` and its gradient."""
+    from genie_b200 import ops
+    from genie_b200.plan import csr_by_destination
+    from genie_b200.training import KronGraph
+    from oracle import genie_oracle as go
+    dev = _dev()
+    S, G = 23, 41
+    rng = np.random.default_rng(mode * 10 + C)
+    if mode == 2:
+        n = 777
+        E = 5 * n
+        A = torch.from_numpy(np.stack((rng.integers(0, n, E), rng.integers(0, n - 30, E)), 0)).long()      # 30 isolated targets
+        rowptr, col = csr_by_destination(A, n)
+        kg = KronGraph(2, 0, 0, n, rowptr, col, dev)
+        P = n
+    else:
+        pts = rng.uniform(0, 100.0, ((S if mode == 0 else G), 3)).astype(np.float32)
+        A = go.knn_graph_no_self(pts, 6)
+        n = S if mode == 0 else G
+        rowptr, col = csr_by_destination(A, n)
+        kg = KronGraph(mode, S, G, S * G, rowptr, col, dev)
+        P = S * G
+    x = torch.from_numpy(rng.normal(size=(P, C)).astype(np.float32))
+    dense = torch.zeros((n, n), dtype=torch.float64)
+    deg = torch.bincount(A[1], minlength=n).clamp(min=1).double()
+    dense.index_put_((A[1], A[0]), 1.0 / deg[A[1]], accumulate=True)
+
+    def apply(M):
+        if mode == 0:
+            return torch.einsum('st,gtc->gsc', M, x.double().view(G, S, C)).reshape(P, C)
+        if mode == 1:
+            return torch.einsum('gh,hsc->gsc', M, x.double().view(G, S, C)).reshape(P, C)
+        return M @ x.double()
+    got_f = ops.kron_spmm(kg, kg.fwd, x.to(dev)).cpu().double()
+    got_r = ops.kron_spmm(kg, kg.rev, x.to(dev)).cpu().double()
+    assert rel_err(got_f.numpy(), apply(dense).numpy()) < 1e-6
+    assert rel_err(got_r.numpy(), apply(dense.t()).numpy()) < 1e-6
+    # the forward mean equals the oracle's propagate_mean over the explicit product edge list
+    if mode == 0:
+        A_prod = (A.repeat(1, G) + S * torch.arange(G).repeat_interleave(A.shape[1]).view(1, -1))
+        want = go.propagate_mean(x.index_select(0, A_prod[0]), A_prod[1], P)
+        assert rel_err(got_f.numpy(), want.numpy()) < 1e-6
+
+
+@pytest.mark.parametrize('name', ['assoc_10x100', 'assoc_14of16x120_edges', 'assoc_14of16x120_abspos'])
+def test_training_steps_match_oracle(name):
+    """`mz(*input_tensors)` with gradients (train_GENIE_model.py:1786) + Adam (lr 1e-3) for three steps on the device against
+    the oracle's autograd on the CPU: outputs, the weighted MSE loss of :1384, :1789 on synthetic labels, every parameter gradient
+    of the first step, and the loss trajectory."""
+    from genie_b200 import capi
+    from test_oracle_golden import assoc_inputs, assoc_variant
+    from oracle import genie_oracle as go
+    dev = _dev()
+    d, sd = load_golden(name)
+    m, graphs, window, locs, grid = _assoc_setup(d, sd, dev, name)
+    m.train()
+    A_sta, A_src, A_ps, A_pg, A_sip, A_sis = _graphs(d)
+    kw = assoc_inputs(d)
+    pos_rel, abs_pos = assoc_variant(d, name, A_ps, A_pg, A_sis)
+    t = lambda k: torch.from_numpy(d[k]).to(dev)
+    rng = np.random.default_rng(5)
+    lbl = [torch.from_numpy(rng.uniform(0, 1, d[k].shape[:2]).astype(np.float32)) for k in ('y', 'x', 'arv_p', 'arv_s')]
+    wts = (0.1, 0.4, 0.25, 0.25)
+    loss_fn = torch.nn.MSELoss()                     # train_GENIE_model.py:1384
+
+    def loss_of(out, to=lambda a: a):
+        return sum(w * loss_fn(o[:, :, 0], to(l)) for w, o, l in zip(wts, out, lbl))
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    opt_o = torch.optim.Adam(list(sdo.values()), lr=1e-3)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    n0 = capi.launch_count()
+    for step in range(3):
+        opt_o.zero_grad()
+        want = go.forward_fixed(sdo, torch.from_numpy(d['Slice']), torch.from_numpy(d['Mask']), A_ps, A_pg,
+                                torch.from_numpy(d['read_in_attr']), A_sip, A_src, torch.from_numpy(d['grid']).float(),
+                                scale_rel=float(d['scale_rel']), scale_t=float(d['scale_t']), eps=float(d['eps']),
+                                pos_rel=pos_rel, abs_pos=abs_pos, **kw)
+        loss_o = loss_of(want)
+        loss_o.backward()
+        opt.zero_grad()
+        out = m(t('Slice'), t('Mask'), *graphs, *window)
+        loss = loss_of(out, lambda a: a.to(dev))
+        loss.backward()
+        assert abs(float(loss.detach()) - float(loss_o.detach())) < 1e-4 * abs(float(loss_o.detach())), step
+        if step == 0:
+            for a, b, key in zip(out, want, ('y', 'x', 'arv_p', 'arv_s')):
+                assert rel_err(a.detach().cpu().numpy(), b.detach().numpy()) < TOL, key
+            checked = 0
+            for k, p in m.named_parameters():
+                g_o = sdo[k].grad
+                if g_o is None or p.grad is None:
+                    assert (g_o is None or not g_o.any()) and (p.grad is None or not p.grad.any()), k
+                    continue
+                assert rel_err(p.grad.cpu().numpy(), g_o.numpy()) < 1e-3, k
+                checked += 1
+            assert checked > 100
+        opt_o.step()
+        opt.step()
+    assert capi.launch_count() - n0 >= 3 * 16           # 8 aggregations forward + 8 backward per step ran on our kernel
