@@ -52,6 +52,78 @@ def extract_inputs_adjacencies_cartesian(locs_cart, grid_cart, k_sta_edges, k_sp
     return A_sta_sta, A_src_src
 
 
+def extract_inputs_adjacencies_subgraph(locs, x_grid, ftrns1, ftrns2=None, max_deg_offset=5.0, k_nearest_pairs=30,
+                                        k_sta_edges=10, k_spc_edges=15, verbose=False,
+                                        scale_pairwise_sta_in_src_distances=100e3, scale_deg=110e3, device=None):
+    """Sub-graph mode of the reference (process_utils.py:744-849), same signature and return list
+    [A_sta_sta, A_src_src, A_prod_sta_sta, A_prod_src_src, A_src_in_prod, A_src_in_sta]: the product graph only over the
+    (station, source) pairs that are within `scale_deg * max_deg_offset` metres or among the source's `k_nearest_pairs`
+    nearest stations.  The reference loops over all grid nodes and all stations in Python (:798-841); here the pair set is
+    one sorted key list, membership a dense [G*S] index table, and the two product edge lists are expansions of the small
+    graphs' CSR rows — torch ops on `device` (CUDA: kNN through genie_knn_fwd), no Python loop.  Edge order as the reference's."""
+    dev = torch.device('cpu') if device is None else torch.device(device)
+    on_gpu = dev.type == 'cuda'
+    sta_m = np.asarray(ftrns1(locs), dtype=np.float64)
+    grid_m = np.asarray(ftrns1(x_grid), dtype=np.float64)
+    S, G = sta_m.shape[0], grid_m.shape[0]
+    k_sta = int(min(k_sta_edges, S - 2))                                                              # :764
+    km = lambda a: torch.from_numpy((a / 1000.0).astype(np.float32))
+    if on_gpu:
+        A_sta_sta, A_src_src = knn_graph_device(km(sta_m).to(dev), k_sta), knn_graph_device(km(grid_m).to(dev), k_spc_edges)
+        nn_idx = ops.knn(km(sta_m).to(dev), km(grid_m).to(dev), int(k_nearest_pairs))             # [G, k]  (:784)
+    else:
+        A_sta_sta, A_src_src = knn_graph(km(sta_m).numpy(), k_sta), knn_graph(km(grid_m).numpy(), k_spc_edges)
+        kk = int(min(k_nearest_pairs, S))
+        nn_idx = torch.from_numpy(cKDTree(km(sta_m).numpy().astype(np.float64)).query(
+            km(grid_m).numpy().astype(np.float64), k=kk)[1].reshape(G, kk)).long()
+    # pair set as sorted keys g*S + s  (:776-794: epsilon pairs + kNN pairs, unique, ordered by source then station)
+    g_t, s_t = torch.from_numpy(grid_m).to(dev), torch.from_numpy(sta_m).to(dev)
+    keys = [(torch.arange(G, device=dev).view(-1, 1) * S + nn_idx.long()).reshape(-1)]
+    thr = float(scale_deg) * float(max_deg_offset)
+    for g0 in range(0, G, 4096):                                    # fp64 distances as numpy's in the reference (:777-779)
+        d = torch.linalg.norm(g_t[g0:g0 + 4096, None, :] - s_t[None, :, :], dim=2)
+        gi, si = torch.nonzero(d < thr, as_tuple=True)
+        keys.append((gi + g0) * S + si)
+    keys = torch.unique(torch.cat(keys))                             # sorted
+    n_prod = keys.numel()
+    node_grid, node_sta = keys // S, keys % S
+    A_src_in_sta = torch.stack((node_sta, node_grid), dim=0)
+    A_src_in_prod = torch.stack((torch.arange(n_prod, device=dev), node_grid), dim=0)
+    table = torch.full((G * S,), -1, dtype=torch.long, device=dev)
+    table[keys] = torch.arange(n_prod, device=dev)
+
+    def expand(A_small, n_small, node_row):
+        """For every product node, the in-edges of its row in the small graph (CSR by target, the small graph's own order)."""
+        rowptr, col = csr_by_destination_stable(A_small, n_small)
+        deg = (rowptr[1:] - rowptr[:-1])[node_row]
+        tgt = torch.repeat_interleave(torch.arange(n_prod, device=dev), deg)
+        start = torch.repeat_interleave(rowptr[:-1][node_row], deg)
+        off = torch.arange(tgt.numel(), device=dev) - torch.repeat_interleave(torch.cumsum(deg, 0) - deg, deg)
+        return col[start + off], tgt
+
+    # station edges (:823-826): per source, the station graph restricted to the source's station list, in A_sta_sta's order
+    sj, tgt = expand(A_sta_sta.to(dev), S, node_sta)
+    src = table[node_grid[tgt] * S + sj]
+    keep = src >= 0
+    A_prod_sta_sta = torch.stack((src[keep], tgt[keep]), dim=0)
+    # source edges (:828-846): per station, the source graph restricted to the sources linked to it; sorted by (target, source)
+    gj, tgt = expand(A_src_src.to(dev), G, node_grid)
+    src = table[gj * S + node_sta[tgt]]
+    keep = src >= 0
+    src, tgt = src[keep], tgt[keep]
+    order = torch.sort(tgt * n_prod + src)[1]
+    A_prod_src_src = torch.stack((src[order], tgt[order]), dim=0)
+    return [A_sta_sta.to(dev), A_src_src.to(dev), A_prod_sta_sta, A_prod_src_src, A_src_in_prod, A_src_in_sta]
+
+
+def csr_by_destination_stable(A, n):
+    """CSR by target node of an int64 [2,E] edge list, keeping the list's order inside every row: (rowptr [n+1], source [E])."""
+    order = torch.sort(A[1], stable=True)[1]
+    rowptr = torch.zeros(n + 1, dtype=torch.long, device=A.device)
+    rowptr[1:] = torch.cumsum(torch.bincount(A[1], minlength=n), 0)
+    return rowptr, A[0][order]
+
+
 def product_edge_lists(A_sta_sta, A_src_src, n_sta, n_grid):
     """A_prod_sta_sta, A_prod_src_src, A_src_in_prod, A_src_in_sta of process_utils.py:720-722 /
     process_continuous_days.py:629 (small networks only: these lists are what the CARTESIAN plan avoids)."""

@@ -5,6 +5,7 @@
     python oracle/gen_golden.py synthetic_abspos # same, `use_absolute_pos: True` (station / source positions join Slice)
     python oracle/gen_golden.py legacy_input     # a1': extract_inputs_from_data_fixed_grids_with_phase_type
     python oracle/gen_golden.py association      # forward_fixed incl. the association branch
+    python oracle/gen_golden.py subgraph         # sub-graph mode builder (process_utils.py:744-849) + one window on it
     python oracle/gen_golden.py ferndale       # Examples/Ferndale.zip: real stations/grids/picks + trained checkpoint
 
 The reference classes (`/root/reference/Code/module.py`, `process_utils.py`) are imported as they are, with
@@ -346,6 +347,65 @@ def association(edges=False, abs_pos=False):
             np.abs(res['arv_p']).sum(), np.abs(res['arv_s']).sum(), res['y'].max()))
 
 
+def subgraph():
+    """extract_inputs_adjacencies_subgraph (process_utils.py:744-849) of the unmodified reference on two synthetic networks
+    (Cartesian metres, ftrns1 = identity) + one window of inputs and the front end on the resulting explicit product graph."""
+    work = tempfile.mkdtemp(prefix='genie_golden_')
+    for f in ('config.yaml', 'train_config.yaml'):
+        shutil.copy(os.path.join(REF, 'Code', f), work)
+    torch, module, pu, Data = _import_reference(os.path.join(REF, 'Code'), work)
+    from genie_b200 import synth
+
+    def identity(x):
+        return x
+
+    for name, S, G, k_sta, k_spc, k_pairs, max_deg, seed in (('subgraph_14x60', 14, 60, 8, 15, 5, 0.2, 2),
+                                                           ('subgraph_30x200', 30, 200, 10, 15, 8, 0.25, 6)):
+        net = synth.Network(S, G, seed=seed, width_km=60.0 if S < 20 else 100.0)
+        out = pu.extract_inputs_adjacencies_subgraph(net.sta, net.grid, identity, identity, max_deg_offset=max_deg,
+                                                     k_nearest_pairs=k_pairs, k_sta_edges=k_sta, k_spc_edges=k_spc, device='cpu')
+        A_sta_sta, A_src_src, A_prod_sta, A_prod_src, A_src_in_prod, A_src_in_sta = out
+        P = A_src_in_sta.shape[1]
+        assert P < S * G
+        # one window through the reference on this explicit graph (process_continuous_days.py:640-648, 776-797)
+        torch.manual_seed(seed)
+        mz = module.GCN_Detection_Network_extended(identity, identity, device='cpu')
+        mz.eval()
+        attr_scale = np.array([net.width, net.width, 42000.0]).reshape(1, -1)
+        spatial_vals = torch.Tensor((net.grid[A_src_in_prod[1].numpy()] - net.sta[A_src_in_sta[0][A_src_in_prod[0]].numpy()])
+                                    / attr_scale)                                                   # :642
+        mz.set_adjacencies(A_prod_sta, A_prod_src, Data(x=spatial_vals, edge_index=A_src_in_prod), None, A_src_in_sta,
+                           A_src_src, None, None, None, None, torch.Tensor(net.sta), torch.Tensor(net.grid))
+        Pk = synth.make_picks(net, 0.0, 600.0, seed=seed + 1, events_per_3h=400.0, false_per_sta_min=2.0)
+        t0, sig, dt = 210.0, 3.0, 0.3
+        max_t = net.max_moveout()
+        trv_times = net.travel_times()
+        [Inpts, Masks], [lp_t, lp_s, lp_p, _] = pu.extract_input_from_data(
+            None, Pk, np.array([t0]), np.arange(S), net.sta, net.grid, A_src_in_sta.numpy(), trv_times=trv_times, max_t=max_t,
+            kernel_sig_t=sig, dt=dt, device='cpu')
+        rng = np.random.default_rng(seed)
+        Q = 40
+        x_query = np.stack((rng.uniform(0, net.width, Q), rng.uniform(0, net.width, Q), rng.uniform(-40000.0, 0.0, Q)), axis=1)
+        t_query = np.arange(-3.0, 3.0 + 0.75, 0.75)
+        store = _hook_outputs(mz)
+        y, x = mz.forward_fixed_source(Inpts[0], Masks[0], torch.Tensor(lp_t[0]), torch.Tensor(lp_s[0]).long(),
+                                       torch.Tensor(lp_p[0].reshape(-1, 1)).float(), torch.Tensor(net.sta), torch.Tensor(net.grid),
+                                       torch.Tensor(x_query), torch.Tensor(t_query.reshape(-1, 1)))
+        res = dict(sta=net.sta, grid=net.grid, ind_use=np.arange(S), k_sta=np.int64(k_sta), k_spc=np.int64(k_spc),
+                   k_nearest_pairs=np.int64(k_pairs), max_deg_offset=np.float64(max_deg), A_sta_sta=A_sta_sta.numpy(),
+                   A_src_src=A_src_src.numpy(), A_prod_sta_sta=A_prod_sta.numpy(), A_prod_src_src=A_prod_src.numpy(),
+                   A_src_in_prod=A_src_in_prod.numpy(), A_src_in_sta=A_src_in_sta.numpy(), read_in_attr=spatial_vals.numpy(),
+                   picks=Pk, t0=np.float64(t0), max_t=np.float64(max_t), kernel_sig_t=np.float64(sig), dt=np.float64(dt),
+                   trv_times=trv_times, Slice=Inpts[0].numpy(), Mask=Masks[0].numpy(), x_query=x_query, t_query=t_query,
+                   x_latent=store['DataAggregation'][0].numpy(), read_in=store['Bipartite_ReadIn'][0].numpy(),
+                   x_spatial=store['SpatialAggregation3'][0].numpy(), y=y.numpy(), x=x.numpy(),
+                   scale_rel=np.float64(module.scale_rel), scale_t=np.float64(module.scale_t))
+        res.update(_pack(mz.state_dict()))
+        np.savez_compressed(os.path.join(GOLD, name + '.npz'), **res)
+        print(name, 'P=%d of %d, sta edges %d, src edges %d, Slice nnz %d, x_latent.abs %.4f' % (
+            P, S * G, A_prod_sta.shape[1], A_prod_src.shape[1], int((Inpts[0] != 0).sum()), float(np.abs(res['x_latent']).sum())))
+
+
 if __name__ == '__main__':
     mode = sys.argv[1] if len(sys.argv) > 1 else 'synthetic'
     if mode == 'synthetic':
@@ -362,6 +422,8 @@ if __name__ == '__main__':
         association(edges=True)
     elif mode == 'association_abspos':
         association(abs_pos=True)
+    elif mode == 'subgraph':
+        subgraph()
     elif mode == 'ferndale':
         from gen_golden_ferndale import ferndale
         ferndale()

@@ -926,3 +926,38 @@ def test_training_steps_match_oracle(name):
         opt_o.step()
         opt.step()
     assert capi.launch_count() - n0 >= 3 * 16           # 8 aggregations forward + 8 backward per step ran on our kernel
+
+
+# ---- sub-graph mode (process_utils.py:744-849; SURVEY.md §8d "C4 subgraph variant") -------------------------------------------
+
+@pytest.mark.parametrize('name', ['subgraph_14x60', 'subgraph_30x200'])
+def test_subgraph_mode_matches_reference(name):
+    """The sub-graph builder on the device (kNN through genie_knn_fwd), then inputs (a1 over the pair list) and
+    forward_fixed_source on the EXPLICIT plan, against the unmodified reference."""
+    from genie_b200 import capi
+    from genie_b200.process_utils import extract_inputs_adjacencies_subgraph, InputExtractor
+    from oracle.refshim.torch_geometric.data import Data
+    dev = _dev()
+    d, sd = load_golden(name)
+    out = extract_inputs_adjacencies_subgraph(d['sta'], d['grid'], lambda x: x, None, max_deg_offset=float(d['max_deg_offset']),
+                                              k_nearest_pairs=int(d['k_nearest_pairs']), k_sta_edges=int(d['k_sta']),
+                                              k_spc_edges=int(d['k_spc']), device=dev)
+    for got, key in zip(out, ('A_sta_sta', 'A_src_src', 'A_prod_sta_sta', 'A_prod_src_src', 'A_src_in_prod', 'A_src_in_sta')):
+        assert got.is_cuda and np.array_equal(got.cpu().numpy(), d[key]), key
+    A_sta, A_src, A_ps, A_pg, A_sip, A_sis = out
+    m = _model(sd, dev, float(d['scale_rel']), float(d['scale_t']))
+    t = lambda k: torch.from_numpy(d[k]).to(dev)
+    locs, grid = t('sta').float(), t('grid').float()
+    m.set_adjacencies(A_ps, A_pg, Data(x=t('read_in_attr'), edge_index=A_sip), None, A_sis, A_src, None, None, None, None,
+                      locs, grid)
+    assert m._plan.mode == capi.GRAPH_EXPLICIT and m._plan.n_prod == d['Slice'].shape[0]
+    ex = InputExtractor(m._plan, d['trv_times'], d['ind_use'], d['sta'].shape[0], float(d['max_t']), float(d['kernel_sig_t']),
+                        float(d['dt']), node_sta=A_sis[0], node_grid=A_sis[1])
+    ex.set_day(d['picks'])
+    Slice, Mask = ex(float(d['t0']))
+    assert np.array_equal(Slice.cpu().numpy(), d['Slice']) and np.array_equal(Mask.cpu().numpy(), d['Mask'])
+    xs, lat, _ = m.front_end(Slice, Mask, grid, want_latent=True)
+    assert rel_err(lat.cpu().numpy(), d['x_latent']) < TOL and rel_err(xs.cpu().numpy(), d['x_spatial']) < TOL
+    y, x = m.forward_fixed_source(Slice, Mask, None, None, None, locs, grid, t('x_query').float(),
+                                  t('t_query').float().reshape(-1, 1))
+    assert rel_err(y.cpu().numpy(), d['y']) < TOL and rel_err(x.cpu().numpy(), d['x']) < TOL

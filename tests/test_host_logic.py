@@ -200,3 +200,18 @@ def test_bisection_groups_partition_and_compactness():
     union = [len(set(np.concatenate([cl[rp[g]:rp[g + 1]] for g in nodes[ptr[i]:ptr[i + 1]]]).tolist()))
              for i in range(len(sizes))]
     assert np.sum(sizes) * 15 / np.sum(union) > 3.0             # neighbour rows are re-used > 3x inside a group
+
+
+@pytest.mark.parametrize('name', ['subgraph_14x60', 'subgraph_30x200'])
+def test_subgraph_builder_matches_reference(name):
+    """extract_inputs_adjacencies_subgraph (process_utils.py:744-849): all six edge lists identical to the unmodified
+    reference's, including the edge order."""
+    from conftest import load_golden
+    from genie_b200.process_utils import extract_inputs_adjacencies_subgraph
+    d, _ = load_golden(name)
+    out = extract_inputs_adjacencies_subgraph(d['sta'], d['grid'], lambda x: x, None, max_deg_offset=float(d['max_deg_offset']),
+                                              k_nearest_pairs=int(d['k_nearest_pairs']), k_sta_edges=int(d['k_sta']),
+                                              k_spc_edges=int(d['k_spc']))
+    for got, key in zip(out, ('A_sta_sta', 'A_src_src', 'A_prod_sta_sta', 'A_prod_src_src', 'A_src_in_prod', 'A_src_in_sta')):
+        assert got.dtype == torch.int64 and np.array_equal(got.numpy(), d[key]), key
+    assert out[5].shape[1] < d['sta'].shape[0] * d['grid'].shape[0]

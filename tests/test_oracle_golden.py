@@ -182,3 +182,20 @@ def test_absolute_pos_matches_reference(name):
     for key in ('x_latent', 'read_in', 'x_spatial'):
         assert rel_err(parts[key].numpy(), d[key]) < 2e-6, key
     assert rel_err(y.numpy(), d['y']) < 2e-6 and rel_err(x.numpy(), d['x']) < 2e-6
+
+
+@pytest.mark.parametrize('name', ['subgraph_14x60', 'subgraph_30x200'])
+def test_subgraph_window_matches_reference(name):
+    """Sub-graph mode: inputs (a1 with the pair list as A_src_in_sta) and the front end + heads on the explicit product graph."""
+    d, sd = load_golden(name)
+    t = torch.from_numpy
+    Slice, Mask = go.input_scatter(d['picks'], float(d['t0']), d['ind_use'], d['sta'].shape[0], d['A_src_in_sta'],
+                                   d['trv_times'], float(d['max_t']), float(d['kernel_sig_t']), float(d['dt']))
+    assert np.array_equal(Slice, d['Slice']) and np.array_equal(Mask, d['Mask'])
+    y, x, parts = go.forward_fixed_source(
+        sd, t(d['Slice']), t(d['Mask']), t(d['A_prod_sta_sta']), t(d['A_prod_src_src']), t(d['read_in_attr']),
+        t(d['A_src_in_prod']), t(d['A_src_src']), t(d['grid']).float(), t(d['x_query']).float(),
+        t(d['t_query']).float().reshape(-1, 1), float(d['scale_rel']), float(d['scale_t']), return_parts=True)
+    for key in ('x_latent', 'read_in', 'x_spatial'):
+        assert rel_err(parts[key].numpy(), d[key]) < 2e-6, key
+    assert rel_err(y.numpy(), d['y']) < 2e-6 and rel_err(x.numpy(), d['x']) < 2e-6
