@@ -70,5 +70,7 @@ if __name__ == '__main__':
     which = sys.argv[1:] or ['c2', 'c4']
     if 'c2' in which:
         run(100, 5000, 'C2')
+    if 'c4s' in which:
+        run(1000, 5000, 'C4/10')
     if 'c4' in which:
         run(1000, 50000, 'C4')
