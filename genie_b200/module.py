@@ -1,11 +1,16 @@
 """Drop-in replacement for the hot-path classes of the reference's `Code/module.py`.
 
 `from genie_b200.module import *` gives `GCN_Detection_Network_extended` with the reference's constructor, method
-signatures and state_dict key names (module.py:882-1020), so `train_GENIE_model.py:1382` / `process_continuous_days.py:
-335-337, 634, 797` work against it unchanged.  The product-graph front end (DataAggregation -> Bipartite_ReadIn ->
-SpatialAggregation1..3, >= 97 % of the reference's forward time) runs in libgenie_b200.so; the sub-modules of the same
-names only hold the parameters.  The small per-grid-node read-out heads (SpatialDirect, TemporalAttention,
-SpatialAttention) are restated in plain torch without torch_geometric.
+signatures and state_dict key names (module.py:882-1020), so `train_GENIE_model.py:1382, 1786` / `process_continuous_days.py:
+335-337, 634, 797, 1062` work against it unchanged.  Everything that scales with the product graph runs in libgenie_b200.so
+(the sub-modules of the reference's names only hold the parameters):
+  forward_fixed_source  front end (DataAggregation -> Bipartite_ReadIn -> SpatialAggregation1..3, >= 97 % of the reference's
+                        forward time) + read-out heads (SpatialDirect, TemporalAttention, SpatialAttention)
+  forward_fixed         the same + the association branch (BipartiteGraphReadOutOperator, DataAggregationAssociationPhase,
+                        LocalSliceLgCollapse{P,S}); only the pick-sized source-arrival attention (Arrivals) is plain torch
+  forward               under torch.no_grad() = forward_fixed with the graphs of the call; with gradients the differentiable
+                        path of genie_b200/training.py (message passing and its gradient on genie_kron_spmm_fwd)
+The torch `forward` methods of the head modules below are kept for head shapes the kernels are not built for and for training.
 
 Like the reference (module.py:27-46) the module reads `config.yaml` / `train_config.yaml` from the working directory at
 import time when they exist; otherwise the reference's shipped defaults are used.
