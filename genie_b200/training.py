@@ -64,6 +64,47 @@ def mean_aggregate(x, kg):
     return MeanAggregate.apply(x.contiguous(), kg)
 
 
+class _SplitKLinear(torch.autograd.Function):
+    """nn.Linear on a product-node-sized input [P, n_in] with a weight gradient the GPU can parallelise.  The gradient
+    dW = dY^T X is a [n_out x n_in] (at most 30 x 95) result reduced over P = 10^5..10^7 rows: as ONE GEMM the library
+    maps it to a single output tile, i.e. one SM walks all P rows (measured: 409 us per layer at P = 5 * 10^5, 27 % of a training
+    sample, profiles/r3j_train_profile.log).  Here the rows are cut into SPLIT slabs, the slabs' partial products run as one
+    batched GEMM over all SMs and are summed (a fixed order: bit-reproducible)."""
+    SPLIT = 256
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return torch.addmm(bias, x, weight.t())
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        gy = gy.contiguous()
+        n = x.shape[0]
+        c = n // _SplitKLinear.SPLIT
+        main = c * _SplitKLinear.SPLIT
+        gw = None
+        if ctx.needs_input_grad[1]:
+            gw = torch.bmm(gy[:main].view(_SplitKLinear.SPLIT, c, -1).transpose(1, 2),
+                           x[:main].view(_SplitKLinear.SPLIT, c, -1)).sum(0)
+            if main < n:
+                gw = gw + gy[main:].t() @ x[main:]
+        gx = gy @ weight if ctx.needs_input_grad[0] else None
+        gb = gy.sum(0) if ctx.needs_input_grad[2] else None
+        return gx, gw, gb
+
+
+LIN_SPLIT_MIN_ROWS = 16384
+
+
+def lin(layer, x):
+    """`layer(x)` for an nn.Linear; product-node-sized inputs take the split-K weight gradient."""
+    if x.dim() == 2 and x.shape[0] >= LIN_SPLIT_MIN_ROWS:
+        return _SplitKLinear.apply(x.contiguous(), layer.weight, layer.bias)
+    return layer(x)
+
+
 # ---- the modules of module.py as differentiable functions of the parameter holders ----------------------------------------
 
 def _expand_edge_means(model, kg_sta):
@@ -77,36 +118,36 @@ def _expand_edge_means(model, kg_sta):
 
 def data_aggregation(da, Slice, Mask, kg_sta, kg_src, edge_means=None):
     """DataAggregation.forward (module.py:85-98) / DataAggregationEdges.forward (:143-157)."""
-    tr = da.activate(da.init_trns(torch.cat((Slice, Mask), dim=-1)))
+    tr = da.activate(lin(da.init_trns, torch.cat((Slice, Mask), dim=-1)))
     cat = (lambda a, m, e: torch.cat((a, m, e, Mask), dim=1)) if edge_means is not None else \
         (lambda a, m, e: torch.cat((a, m, Mask), dim=1))
     e_sta, e_src = edge_means if edge_means is not None else (None, None)
-    tr1 = da.l1_t1_2(cat(tr, mean_aggregate(da.activate11(tr), kg_sta), e_sta))
-    tr2 = da.l1_t2_2(cat(tr, mean_aggregate(da.activate12(tr), kg_src), e_src))
+    tr1 = lin(da.l1_t1_2, cat(tr, mean_aggregate(da.activate11(tr), kg_sta), e_sta))
+    tr2 = lin(da.l1_t2_2, cat(tr, mean_aggregate(da.activate12(tr), kg_src), e_src))
     tr = da.activate1(torch.cat((tr1, tr2), dim=1))
-    tr1 = da.l2_t1_2(cat(tr, mean_aggregate(da.activate21(da.l2_t1_1(tr)), kg_sta), e_sta))
-    tr2 = da.l2_t2_2(cat(tr, mean_aggregate(da.activate22(da.l2_t2_1(tr)), kg_src), e_src))
+    tr1 = lin(da.l2_t1_2, cat(tr, mean_aggregate(da.activate21(lin(da.l2_t1_1, tr)), kg_sta), e_sta))
+    tr2 = lin(da.l2_t2_2, cat(tr, mean_aggregate(da.activate22(lin(da.l2_t2_1, tr)), kg_src), e_src))
     return da.activate2(torch.cat((tr1, tr2), dim=1))
 
 
 def data_aggregation_association(da, s, latent, mask1, mask2, kg_sta, kg_src, edge_means=None):
     """DataAggregationAssociationPhase.forward (module.py:387-403) / ...Edges.forward (:442-467)."""
     mask = torch.cat((mask1, mask2), dim=-1)
-    tr = da.activate(da.init_trns(torch.cat((s, latent, mask), dim=-1)))
+    tr = da.activate(lin(da.init_trns, torch.cat((s, latent, mask), dim=-1)))
     cat = (lambda a, m, e: torch.cat((a, m, e, mask), dim=1)) if edge_means is not None else \
         (lambda a, m, e: torch.cat((a, m, mask), dim=1))
     e_sta, e_src = edge_means if edge_means is not None else (None, None)
-    tr1 = da.l1_t1_2(cat(tr, mean_aggregate(da.activate11(da.l1_t1_1(tr)), kg_sta), e_sta))
-    tr2 = da.l1_t2_2(cat(tr, mean_aggregate(da.activate12(da.l1_t2_1(tr)), kg_src), e_src))
+    tr1 = lin(da.l1_t1_2, cat(tr, mean_aggregate(da.activate11(lin(da.l1_t1_1, tr)), kg_sta), e_sta))
+    tr2 = lin(da.l1_t2_2, cat(tr, mean_aggregate(da.activate12(lin(da.l1_t2_1, tr)), kg_src), e_src))
     tr = da.activate1(torch.cat((tr1, tr2), dim=1))
-    tr1 = da.l2_t1_2(cat(tr, mean_aggregate(da.activate21(da.l2_t1_1(tr)), kg_sta), e_sta))
-    tr2 = da.l2_t2_2(cat(tr, mean_aggregate(da.activate22(da.l2_t2_1(tr)), kg_src), e_src))
+    tr1 = lin(da.l2_t1_2, cat(tr, mean_aggregate(da.activate21(lin(da.l2_t1_1, tr)), kg_sta), e_sta))
+    tr2 = lin(da.l2_t2_2, cat(tr, mean_aggregate(da.activate22(lin(da.l2_t2_1, tr)), kg_src), e_src))
     return da.activate2(torch.cat((tr1, tr2), dim=1))
 
 
 def bipartite_read_in(ri, x_latent, attr, node_grid, n_grid, Mask):
     """BipartiteGraphOperator.forward (module.py:224-229): masked per-node MLP summed onto the node's grid node."""
-    h = Mask.max(1, keepdim=True)[0] * ri.activate1(ri.fc1(torch.cat((x_latent, attr), dim=-1)))
+    h = Mask.max(1, keepdim=True)[0] * ri.activate1(lin(ri.fc1, torch.cat((x_latent, attr), dim=-1)))
     xg = h.new_zeros((n_grid, h.shape[1])).index_add_(0, node_grid, h)
     return ri.activate2(ri.fc2(xg))
 
@@ -127,8 +168,8 @@ def spatial_aggregation(sa, x, A_src, pos, scale_rel):
 def bipartite_read_out(ro, y_latent, attr, node_grid, mask_out):
     """BipartiteGraphReadOutOperator.forward (module.py:344-352) for the read-out graph [g(i); i]."""
     mj = mask_out[node_grid]
-    h = mj * ro.activate1(ro.fc1(torch.cat((y_latent[node_grid], attr), dim=-1)))
-    return ro.activate2(ro.fc2(h)), mj
+    h = mj * ro.activate1(lin(ro.fc1, torch.cat((y_latent[node_grid], attr), dim=-1)))
+    return ro.activate2(lin(ro.fc2, h)), mj
 
 
 def local_slice_collapse(cm, A_edges, dt_partition, tpick, ipick, phase_label, s, tlatent, k_infer=10):

@@ -81,6 +81,13 @@ def run(S, G, label, n_arv=400, n_src=8, Q=2500, batch=32):
         if n:
             print('    %-24s %8.3f ms total in %d launches per sample' % (k, ms, n), flush=True)
     capi.timing_enable(False)
+    if '--profile' in sys.argv:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for _ in range(3):
+                sample()
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=28, max_name_column_width=60), flush=True)
     with torch.no_grad():
         m.eval()
         medi, _ = timed(lambda: m(Slice, Mask, *graphs, *window), n=10, warm=3)

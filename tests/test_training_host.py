@@ -58,6 +58,7 @@ def test_training_forward_and_gradients_match_oracle(name, monkeypatch):
     loss_o.backward()
     # product: training path with the CUDA call replaced by its dense restatement
     monkeypatch.setattr(ops, 'kron_spmm', _dense_kron_spmm)
+    monkeypatch.setattr(training, 'LIN_SPLIT_MIN_ROWS', 300)        # the fixtures' P ~ 10^3: take the split-K weight gradient
     monkeypatch.setattr(gm, 'knn_query_edges', lambda xc, xq, k: go.knn(xc / 1000.0, xq / 1000.0, k).flip(0))
     m = gm.GCN_Detection_Network_extended(None, None, scale_rel=float(d['scale_rel']), device='cpu',
                                           updated_model=name.endswith('_edges'), use_absolute_pos=name.endswith('_abspos'))
