@@ -359,8 +359,12 @@ def subgraph():
     def identity(x):
         return x
 
+    # the third case is ragged: two nearest stations per source and a 3 km radius leave stations with a single source or
+    # none at all (the reference's empty-slice branch, process_utils.py:832-834) and sources whose station list has no
+    # station-graph edge inside it
     for name, S, G, k_sta, k_spc, k_pairs, max_deg, seed in (('subgraph_14x60', 14, 60, 8, 15, 5, 0.2, 2),
-                                                           ('subgraph_30x200', 30, 200, 10, 15, 8, 0.25, 6)):
+                                                           ('subgraph_30x200', 30, 200, 10, 15, 8, 0.25, 6),
+                                                           ('subgraph_12x40_ragged', 12, 40, 8, 15, 2, 0.03, 8)):
         net = synth.Network(S, G, seed=seed, width_km=60.0 if S < 20 else 100.0)
         out = pu.extract_inputs_adjacencies_subgraph(net.sta, net.grid, identity, identity, max_deg_offset=max_deg,
                                                      k_nearest_pairs=k_pairs, k_sta_edges=k_sta, k_spc_edges=k_spc, device='cpu')

@@ -930,7 +930,7 @@ def test_training_steps_match_oracle(name):
 
 # ---- sub-graph mode (process_utils.py:744-849; SURVEY.md §8d "C4 subgraph variant") -------------------------------------------
 
-@pytest.mark.parametrize('name', ['subgraph_14x60', 'subgraph_30x200'])
+@pytest.mark.parametrize('name', ['subgraph_14x60', 'subgraph_30x200', 'subgraph_12x40_ragged'])
 def test_subgraph_mode_matches_reference(name):
     """The sub-graph builder on the device (kNN through genie_knn_fwd), then inputs (a1 over the pair list) and
     forward_fixed_source on the EXPLICIT plan, against the unmodified reference."""

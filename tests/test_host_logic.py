@@ -202,7 +202,7 @@ def test_bisection_groups_partition_and_compactness():
     assert np.sum(sizes) * 15 / np.sum(union) > 3.0             # neighbour rows are re-used > 3x inside a group
 
 
-@pytest.mark.parametrize('name', ['subgraph_14x60', 'subgraph_30x200'])
+@pytest.mark.parametrize('name', ['subgraph_14x60', 'subgraph_30x200', 'subgraph_12x40_ragged'])
 def test_subgraph_builder_matches_reference(name):
     """extract_inputs_adjacencies_subgraph (process_utils.py:744-849): all six edge lists identical to the unmodified
     reference's, including the edge order."""

@@ -184,7 +184,7 @@ def test_absolute_pos_matches_reference(name):
     assert rel_err(y.numpy(), d['y']) < 2e-6 and rel_err(x.numpy(), d['x']) < 2e-6
 
 
-@pytest.mark.parametrize('name', ['subgraph_14x60', 'subgraph_30x200'])
+@pytest.mark.parametrize('name', ['subgraph_14x60', 'subgraph_30x200', 'subgraph_12x40_ragged'])
 def test_subgraph_window_matches_reference(name):
     """Sub-graph mode: inputs (a1 with the pair list as A_src_in_sta) and the front end + heads on the explicit product graph."""
     d, sd = load_golden(name)
