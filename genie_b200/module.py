@@ -49,6 +49,13 @@ use_absolute_pos = bool(_cfg.get('use_absolute_pos', False))
 
 device = torch.device('cuda')
 
+# `from genie_b200.module import *` placed after the reference's `from module import *` overrides exactly these names
+__all__ = ['DataAggregation', 'DataAggregationEdges', 'BipartiteGraphOperator', 'SpatialAggregation', 'SpatialDirect',
+           'SpatialAttention', 'TemporalAttention', 'BipartiteGraphReadOutOperator', 'DataAggregationAssociationPhase',
+           'DataAggregationAssociationPhaseEdges', 'LocalSliceLgCollapse', 'StationSourceAttentionMergedPhases',
+           'GCN_Detection_Network_extended', 'knn_query_edges', 'use_updated_model_definition', 'scale_rel', 'k_sta_edges',
+           'scale_t', 'eps', 'use_phase_types', 'use_absolute_pos', 'device']
+
 
 # ---- parameter holders of the CUDA front end -------------------------------------------------------------------------
 
