@@ -15,6 +15,11 @@ from . import capi, ops
 from .plan import GraphPlan
 
 
+# `from genie_b200.process_utils import *` after the reference's `from process_utils import *` overrides exactly these names
+__all__ = ['extract_input_from_data', 'extract_inputs_from_data_fixed_grids_with_phase_type', 'extract_pick_inputs_from_data',
+           'extract_inputs_adjacencies', 'extract_inputs_adjacencies_subgraph', 'extract_inputs_adjacencies_cartesian',
+           'product_edge_lists', 'knn_graph', 'knn_graph_device', 'InputExtractor']
+
 # ---- graphs -------------------------------------------------------------------------------------------------------------
 
 def knn_graph(pos_km, k):
@@ -50,6 +55,34 @@ def extract_inputs_adjacencies_cartesian(locs_cart, grid_cart, k_sta_edges, k_sp
     A_sta_sta = knn_graph((np.asarray(locs_cart, dtype=np.float64) / 1000.0).astype(np.float32), k_sta)
     A_src_src = knn_graph((np.asarray(grid_cart, dtype=np.float64) / 1000.0).astype(np.float32), k_spc_edges)
     return A_sta_sta, A_src_src
+
+
+def extract_inputs_adjacencies(trv, locs, ind_use, x_grid, x_grid_trv, x_grid_trv_ref, x_grid_trv_pointers_p,
+                               x_grid_trv_pointers_s, ftrns1, graph_params, device=None, verbose=False):
+    """Dense-mode graph builder with the reference's signature and return list (process_utils.py:701-742):
+    [A_sta_sta, A_src_src, A_prod_sta_sta, A_prod_src_src, A_src_in_prod, A_edges_time_p, A_edges_time_s, A_edges_ref].
+    kNN through genie_knn_fwd when `device` is a CUDA device.  The explicit product lists are returned because the reference's
+    callers expect them (`set_adjacencies` recognises their pattern and keeps only the two small graphs); beyond a few 10^7
+    product nodes use extract_inputs_adjacencies_cartesian + set_adjacencies_cartesian instead."""
+    k_sta_edges, k_spc_edges, k_time_edges = graph_params
+    ind_use = np.asarray(ind_use).astype('int')
+    n_sta, n_spc, n_sta_slice = locs.shape[0], x_grid.shape[0], len(ind_use)
+    A_sta_sta, A_src_src = extract_inputs_adjacencies_cartesian(ftrns1(locs[ind_use]), ftrns1(x_grid), k_sta_edges,
+                                                                k_spc_edges, device=device)
+    dev = A_sta_sta.device
+    A_prod_sta, A_prod_src, A_src_in_prod, _ = (a.to(dev) for a in product_edge_lists(A_sta_sta.cpu(), A_src_src.cpu(),
+                                                                                       n_sta_slice, n_spc))
+    # time-pointer tables of the used stations, re-indexed to the station subset (:723-734, the reference's expressions)
+    perm_vec = -1 * np.ones(n_sta)
+    perm_vec[ind_use] = np.arange(n_sta_slice)
+    len_dt = len(x_grid_trv_ref)
+    rows = np.tile(np.arange(k_time_edges * len_dt), n_sta_slice) + (len_dt * k_time_edges) * ind_use.repeat(k_time_edges * len_dt)
+    one_vec = np.repeat(ind_use * np.ones(n_sta_slice), k_time_edges * len_dt).astype('int')
+    A_edges_time_p = (n_sta_slice * (np.asarray(x_grid_trv_pointers_p)[rows] - one_vec) / n_sta) + perm_vec[one_vec]
+    A_edges_time_s = (n_sta_slice * (np.asarray(x_grid_trv_pointers_s)[rows] - one_vec) / n_sta) + perm_vec[one_vec]
+    A_edges_ref = np.asarray(x_grid_trv_ref) * 1 + 0
+    assert A_edges_time_p.max() < n_spc * n_sta_slice and A_edges_time_s.max() < n_spc * n_sta_slice
+    return [A_sta_sta, A_src_src, A_prod_sta, A_prod_src, A_src_in_prod, A_edges_time_p, A_edges_time_s, A_edges_ref]
 
 
 def extract_inputs_adjacencies_subgraph(locs, x_grid, ftrns1, ftrns2=None, max_deg_offset=5.0, k_nearest_pairs=30,

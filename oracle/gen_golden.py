@@ -5,6 +5,7 @@
     python oracle/gen_golden.py synthetic_abspos # same, `use_absolute_pos: True` (station / source positions join Slice)
     python oracle/gen_golden.py legacy_input     # a1': extract_inputs_from_data_fixed_grids_with_phase_type
     python oracle/gen_golden.py association      # forward_fixed incl. the association branch
+    python oracle/gen_golden.py dense_adjacencies # the dense graph builder incl. the time-pointer re-indexing (process_utils.py:701-742)
     python oracle/gen_golden.py subgraph         # sub-graph mode builder (process_utils.py:744-849) + one window on it
     python oracle/gen_golden.py ferndale       # Examples/Ferndale.zip: real stations/grids/picks + trained checkpoint
 
@@ -410,6 +411,38 @@ def subgraph():
             P, S * G, A_prod_sta.shape[1], A_prod_src.shape[1], int((Inpts[0] != 0).sum()), float(np.abs(res['x_latent']).sum())))
 
 
+def dense_adjacencies():
+    """extract_inputs_adjacencies (process_utils.py:701-742) of the unmodified reference incl. the time-pointer re-indexing of a
+    station subset (:723-734): all eight returned objects."""
+    work = tempfile.mkdtemp(prefix='genie_golden_')
+    for f in ('config.yaml', 'train_config.yaml'):
+        shutil.copy(os.path.join(REF, 'Code', f), work)
+    torch, module, pu, Data = _import_reference(os.path.join(REF, 'Code'), work)
+    from genie_b200 import synth
+
+    def identity(x):
+        return x
+
+    S_all, n_use, G, k_sta, k_spc, k_time, len_dt, seed = 12, 9, 30, 8, 15, 3, 7, 12
+    net = synth.Network(S_all, G, seed=seed, width_km=60.0)
+    rng = np.random.default_rng(seed)
+    ind_use = np.sort(rng.choice(S_all, size=n_use, replace=False))
+    # pointer tables over ALL stations: row (station, time bin, k) names a product node g*S_all + station (utils.py:976)
+    sta_of = np.repeat(np.arange(S_all), len_dt * k_time)
+    ptr_p = rng.integers(0, G, S_all * len_dt * k_time) * S_all + sta_of
+    ptr_s = rng.integers(0, G, S_all * len_dt * k_time) * S_all + sta_of
+    ref_t = np.linspace(-6.0, 12.0, len_dt)
+    out = pu.extract_inputs_adjacencies(None, net.sta, ind_use, net.grid, None, ref_t, ptr_p, ptr_s, identity,
+                                        [k_sta, k_spc, k_time], device='cpu')
+    names = ('A_sta_sta', 'A_src_src', 'A_prod_sta_sta', 'A_prod_src_src', 'A_src_in_prod', 'A_edges_time_p', 'A_edges_time_s',
+             'A_edges_ref')
+    res = {k: (v.numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in zip(names, out)}
+    res.update(sta=net.sta, grid=net.grid, ind_use=ind_use, ptr_p=ptr_p, ptr_s=ptr_s, ref_t=ref_t, k_sta=np.int64(k_sta),
+               k_spc=np.int64(k_spc), k_time=np.int64(k_time))
+    np.savez_compressed(os.path.join(GOLD, 'dense_adjacencies_9of12x30.npz'), **res)
+    print('dense_adjacencies', {k: (res[k].shape, res[k].dtype) for k in names})
+
+
 if __name__ == '__main__':
     mode = sys.argv[1] if len(sys.argv) > 1 else 'synthetic'
     if mode == 'synthetic':
@@ -428,6 +461,8 @@ if __name__ == '__main__':
         association(abs_pos=True)
     elif mode == 'subgraph':
         subgraph()
+    elif mode == 'dense_adjacencies':
+        dense_adjacencies()
     elif mode == 'ferndale':
         from gen_golden_ferndale import ferndale
         ferndale()

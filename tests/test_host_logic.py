@@ -215,3 +215,18 @@ def test_subgraph_builder_matches_reference(name):
     for got, key in zip(out, ('A_sta_sta', 'A_src_src', 'A_prod_sta_sta', 'A_prod_src_src', 'A_src_in_prod', 'A_src_in_sta')):
         assert got.dtype == torch.int64 and np.array_equal(got.numpy(), d[key]), key
     assert out[5].shape[1] < d['sta'].shape[0] * d['grid'].shape[0]
+
+
+def test_dense_adjacency_builder_matches_reference():
+    """extract_inputs_adjacencies (process_utils.py:701-742) with a station subset: the eight returned objects identical to the
+    unmodified reference's, and the product lists are recognised as the Cartesian pattern."""
+    from conftest import load_golden
+    from genie_b200.process_utils import extract_inputs_adjacencies
+    d, _ = load_golden('dense_adjacencies_9of12x30')
+    out = extract_inputs_adjacencies(None, d['sta'], d['ind_use'], d['grid'], None, d['ref_t'], d['ptr_p'], d['ptr_s'],
+                                     lambda x: x, [int(d['k_sta']), int(d['k_spc']), int(d['k_time'])])
+    names = ('A_sta_sta', 'A_src_src', 'A_prod_sta_sta', 'A_prod_src_src', 'A_src_in_prod', 'A_edges_time_p', 'A_edges_time_s',
+             'A_edges_ref')
+    for got, key in zip(out, names):
+        got = got.numpy() if torch.is_tensor(got) else np.asarray(got)
+        assert got.dtype == d[key].dtype and np.array_equal(got, d[key]), key
