@@ -17,7 +17,7 @@ from .plan import GraphPlan
 
 # `from genie_b200.process_utils import *` after the reference's `from process_utils import *` overrides exactly these names
 __all__ = ['extract_input_from_data', 'extract_inputs_from_data_fixed_grids_with_phase_type', 'extract_pick_inputs_from_data',
-           'extract_inputs_adjacencies', 'extract_inputs_adjacencies_subgraph', 'extract_inputs_adjacencies_cartesian',
+           'extract_inputs_adjacencies', 'extract_inputs_adjacencies_subgraph', 'compute_time_embedding_vectors', 'extract_inputs_adjacencies_cartesian',
            'product_edge_lists', 'knn_graph', 'knn_graph_device', 'InputExtractor']
 
 # ---- graphs -------------------------------------------------------------------------------------------------------------
@@ -147,6 +147,49 @@ def extract_inputs_adjacencies_subgraph(locs, x_grid, ftrns1, ftrns2=None, max_d
     order = torch.sort(tgt * n_prod + src)[1]
     A_prod_src_src = torch.stack((src[order], tgt[order]), dim=0)
     return [A_sta_sta.to(dev), A_src_src.to(dev), A_prod_sta_sta, A_prod_src_src, A_src_in_prod, A_src_in_sta]
+
+
+def compute_time_embedding_vectors(trv_pairwise, locs, x_grid, A_src_in_sta, max_t, dt_res=1.0, k_times=10, t_win=10,
+                                   device=None, trv_out=None):
+    """Time-pointer tables of the association branch with the reference's signature (process_utils.py:851-877): for every
+    station and every step of `dt_partition = arange(-t_win, max_t + t_win + dt_res, dt_res)`, the `k_times` product nodes of
+    that station whose P (resp. S) travel time is nearest to the step, nearest first.  The reference queries two 2-D k-d
+    trees whose first coordinate (station index x 2 (max_t + t_win + dt_res)) only separates the stations; here every
+    station's travel times are sorted once and the 2 k_times candidates around each step's insertion point are ranked —
+    torch ops on `device`, no tree.  `trv_out` [P,2] may be given instead of calling `trv_pairwise`.
+    Returns (edges_time_p, edges_time_s, dt_partition) as the reference does (int64 arrays, float64 array)."""
+    dev = torch.device('cpu') if device is None else torch.device(device)
+    A = torch.as_tensor(A_src_in_sta).to(dev).long()
+    if trv_out is None:
+        trv_out = trv_pairwise(torch.Tensor(locs).to(dev)[A[0]], torch.Tensor(x_grid).to(dev)[A[1]])
+    trv_out = torch.as_tensor(trv_out).to(dev).double()
+    n_sta, n_prod, k = int(len(locs)), int(A.shape[1]), int(k_times)
+    dt_partition = np.arange(-t_win, max_t + t_win + dt_res, dt_res)
+    q = torch.from_numpy(dt_partition).to(dev)                                        # [L]
+    L = q.numel()
+    sta = A[0]
+    cnt = torch.bincount(sta, minlength=n_sta)
+    if int(cnt.min()) < k:
+        raise capi.GenieError('compute_time_embedding_vectors: every station needs at least k_times product nodes')
+    start = torch.cumsum(cnt, 0) - cnt
+    big = 4.0 * float(max_t + t_win + dt_res) + 1.0        # separates the stations inside one global sort key
+    out = []
+    for ph in (0, 1):
+        t = trv_out[:, ph]
+        order = torch.sort(sta.double() * big + t)[1]                                 # nodes grouped by station, by time
+        ts = t[order]
+        # insertion point of every (station, step) in that station's sorted times
+        keys = (torch.arange(n_sta, device=dev).double() * big).view(-1, 1) + q.view(1, -1)      # [S, L]
+        pos = torch.searchsorted((sta[order].double() * big + ts).contiguous(), keys.reshape(-1).contiguous()).view(n_sta, L)
+        cand = pos.unsqueeze(-1) + torch.arange(-k, k, device=dev).view(1, 1, -1)                # [S, L, 2k] global positions
+        lo, hi = start.view(-1, 1, 1), (start + cnt).view(-1, 1, 1)
+        valid = (cand >= lo) & (cand < hi)
+        candc = cand.clamp(0, n_prod - 1)
+        dist = (ts[candc] - q.view(1, -1, 1)).abs()
+        dist = torch.where(valid, dist, torch.full_like(dist, float('inf')))
+        sel = torch.topk(dist, k, dim=-1, largest=False, sorted=True)[1]
+        out.append(order[torch.gather(candc, -1, sel)].reshape(-1).cpu().numpy())
+    return out[0], out[1], dt_partition
 
 
 def csr_by_destination_stable(A, n):

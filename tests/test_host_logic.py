@@ -230,3 +230,19 @@ def test_dense_adjacency_builder_matches_reference():
     for got, key in zip(out, names):
         got = got.numpy() if torch.is_tensor(got) else np.asarray(got)
         assert got.dtype == d[key].dtype and np.array_equal(got, d[key]), key
+
+
+@pytest.mark.parametrize('name', ['assoc_10x100', 'assoc_18of20x160', 'assoc_14of16x120_edges'])
+def test_time_embedding_vectors_match_reference(name):
+    """compute_time_embedding_vectors (process_utils.py:851-877) without k-d trees: the pointer tables the unmodified reference
+    built for the association fixtures, entry for entry."""
+    from conftest import load_golden
+    from genie_b200.process_utils import compute_time_embedding_vectors
+    d, _ = load_golden(name)
+    S, G = len(d['ind_use']), d['grid'].shape[0]
+    A_sis = np.stack((np.tile(np.arange(S), G), np.repeat(np.arange(G), S)))
+    sig = float(d['kernel_sig_t'])
+    ep, es, dtp = compute_time_embedding_vectors(None, d['sta'][d['ind_use']], d['grid'], A_sis, float(d['max_t']),
+                                                 dt_res=sig / 5.0, t_win=sig * 2.0, trv_out=d['tlatent'])
+    assert np.array_equal(dtp, d['dt_partition'])
+    assert ep.dtype == np.int64 and np.array_equal(ep, d['A_edges_p']) and np.array_equal(es, d['A_edges_s'])
