@@ -961,3 +961,26 @@ def test_subgraph_mode_matches_reference(name):
     y, x = m.forward_fixed_source(Slice, Mask, None, None, None, locs, grid, t('x_query').float(),
                                   t('t_query').float().reshape(-1, 1))
     assert rel_err(y.cpu().numpy(), d['y']) < TOL and rel_err(x.cpu().numpy(), d['x']) < TOL
+
+
+def test_setup_builders_on_the_device_match_reference():
+    """extract_inputs_adjacencies and compute_time_embedding_vectors with device= (kNN through genie_knn_fwd, index arithmetic
+    in torch on the GPU) against the fixtures of the unmodified reference."""
+    from genie_b200.process_utils import extract_inputs_adjacencies, compute_time_embedding_vectors
+    dev = _dev()
+    d, _ = load_golden('dense_adjacencies_9of12x30')
+    out = extract_inputs_adjacencies(None, d['sta'], d['ind_use'], d['grid'], None, d['ref_t'], d['ptr_p'], d['ptr_s'],
+                                     lambda x: x, [int(d['k_sta']), int(d['k_spc']), int(d['k_time'])], device=dev)
+    for got, key in zip(out, ('A_sta_sta', 'A_src_src', 'A_prod_sta_sta', 'A_prod_src_src', 'A_src_in_prod', 'A_edges_time_p',
+                              'A_edges_time_s', 'A_edges_ref')):
+        if torch.is_tensor(got):
+            assert got.is_cuda
+            got = got.cpu().numpy()
+        assert np.array_equal(np.asarray(got), d[key]), key
+    d, _ = load_golden('assoc_18of20x160')
+    S, G = len(d['ind_use']), d['grid'].shape[0]
+    A_sis = np.stack((np.tile(np.arange(S), G), np.repeat(np.arange(G), S)))
+    sig = float(d['kernel_sig_t'])
+    ep, es, dtp = compute_time_embedding_vectors(None, d['sta'][d['ind_use']], d['grid'], A_sis, float(d['max_t']),
+                                                 dt_res=sig / 5.0, t_win=sig * 2.0, trv_out=d['tlatent'], device=dev)
+    assert np.array_equal(ep, d['A_edges_p']) and np.array_equal(es, d['A_edges_s']) and np.array_equal(dtp, d['dt_partition'])
