@@ -84,6 +84,17 @@ class DayProcessor(object):
             self.windows_done += 1
         return out
 
+    def run_distributed(self, tsteps, tsteps_abs, group=None):
+        """One day over the ranks of a torch.distributed group (one process per GPU): windows are independent, so rank r
+        takes the origin times r, r + R, ... (no data-path exchange while processing), and the ranks' partial stacks are
+        summed by ONE all-reduce at the end of the day (NCCL over NVLink on a multi-GPU box; Q x n_steps floats).  Every
+        rank returns the full Out_2.  The sum order differs from the sequential loop's: equal within fp32 rounding."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        out = self.run(np.asarray(tsteps)[rank::world], tsteps_abs)
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+        return out
+
     @staticmethod
     def sparse(out, thresh=0.01):
         """Out_2_sparse of :812-813: rows (query index, time index, value) of the entries above the threshold."""
