@@ -984,3 +984,35 @@ def test_setup_builders_on_the_device_match_reference():
     ep, es, dtp = compute_time_embedding_vectors(None, d['sta'][d['ind_use']], d['grid'], A_sis, float(d['max_t']),
                                                  dt_res=sig / 5.0, t_win=sig * 2.0, trv_out=d['tlatent'], device=dev)
     assert np.array_equal(ep, d['A_edges_p']) and np.array_equal(es, d['A_edges_s']) and np.array_equal(dtp, d['dt_partition'])
+
+
+def test_forward_fixed_edge_cases():
+    """Association branch with no picks at all, and with a source mask that is zero everywhere (y below the threshold):
+    shapes as the reference's, values against the oracle."""
+    from test_oracle_golden import assoc_inputs
+    from oracle import genie_oracle as go
+    dev = _dev()
+    d, sd = load_golden('assoc_10x100')
+    sd = {k: v.clone() for k, v in sd.items()}
+    m, graphs, window, locs, grid = _assoc_setup(d, sd, dev)
+    m.set_adjacencies(*graphs, locs, grid)
+    t = lambda k: torch.from_numpy(d[k]).to(dev)
+    # no picks: arv_p / arv_s are [n_src, 0, 1]
+    w = list(window)
+    w[0], w[1], w[2] = torch.zeros(0, device=dev), torch.zeros(0, dtype=torch.long, device=dev), torch.zeros((0, 1), dtype=torch.long, device=dev)
+    y, x, arv_p, arv_s = m.forward_fixed(t('Slice'), t('Mask'), *w)
+    n_src = len(d['tq_sample'])
+    assert arv_p.shape == (n_src, 0, 1) and arv_s.shape == (n_src, 0, 1)
+    assert rel_err(y.cpu().numpy(), d['y']) < TOL
+    # source mask zero everywhere: shift the last bias so that max y < 0.01 on every grid node
+    sd['TemporalAttention.proj_2.bias'] = sd['TemporalAttention.proj_2.bias'] - 5.0
+    m.load_state_dict(sd)
+    A_sta, A_src, A_ps, A_pg, A_sip, A_sis = _graphs(d)
+    want = go.forward_fixed(sd, torch.from_numpy(d['Slice']), torch.from_numpy(d['Mask']), A_ps, A_pg,
+                            torch.from_numpy(d['read_in_attr']), A_sip, A_src, torch.from_numpy(d['grid']).float(),
+                            scale_rel=float(d['scale_rel']), scale_t=float(d['scale_t']), eps=float(d['eps']),
+                            return_parts=True, **assoc_inputs(d))
+    assert not want[4]['mask_out'].any()
+    out = m.forward_fixed(t('Slice'), t('Mask'), *window)
+    for a, b, key in zip(out, want[:4], ('y', 'x', 'arv_p', 'arv_s')):
+        assert rel_err(a.cpu().numpy(), b.numpy()) < TOL, key
