@@ -17,7 +17,7 @@ _LIB_PATH = os.path.join(_HERE, 'libgenie_b200.so')
 _lib = None
 
 GRAPH_CARTESIAN, GRAPH_EXPLICIT = 0, 1
-ABI_VERSION = 5
+ABI_VERSION = 6
 EDGE_TERM_LD = 48           # GENIE_EDGE_TERM_LD
 
 c_f32p = ctypes.c_void_p   # device pointers are passed as opaque addresses

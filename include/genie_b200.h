@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GENIE_B200_ABI_VERSION 5
+#define GENIE_B200_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define GENIE_API __attribute__((visibility("default")))
