@@ -246,3 +246,34 @@ def test_time_embedding_vectors_match_reference(name):
                                                  dt_res=sig / 5.0, t_win=sig * 2.0, trv_out=d['tlatent'])
     assert np.array_equal(dtp, d['dt_partition'])
     assert ep.dtype == np.int64 and np.array_equal(ep, d['A_edges_p']) and np.array_equal(es, d['A_edges_s'])
+
+
+def test_day_processor_window_pick_count_matches_reference_rule():
+    """DayProcessor.window_pick_count (prefix sums over the resident pick table) against the reference's rule for skipping a
+    window (process_continuous_days.py:787 via process_utils.py:476-481, 665), on a station subset, incl. empty windows and
+    windows at the ends of the pick table."""
+    from conftest import load_golden
+    from genie_b200.process_utils import InputExtractor
+    from genie_b200.streaming import DayProcessor
+
+    class _Plan(object):
+        device = torch.device('cpu')
+
+    d, _ = load_golden('mid_36of40x300')
+    P = d['picks']
+    max_t, sig = float(d['max_t']), float(d['kernel_sig_t'])
+    ex = InputExtractor(_Plan(), np.zeros((2, d['sta'].shape[0], 2), dtype=np.float32), d['ind_use'], d['sta'].shape[0], max_t,
+                        sig, float(d['dt']))
+    ex.set_day(P)
+    dp = DayProcessor(None, ex, None, None, torch.zeros(1, 3))
+    rng = np.random.default_rng(0)
+    t0s = np.concatenate((rng.uniform(P[:, 0].min() - 2 * max_t, P[:, 0].max() + 2 * max_t, 300), P[:40, 0] - 2.0 * sig,
+                          P[-40:, 0] - max_t - 2.0 * sig, [-1e6, 1e6]))
+    n_zero = 0
+    for t0 in t0s:
+        sel = (P[:, 0] > (t0 - 2.0 * sig)) * (P[:, 0] < (t0 + max_t + 2.0 * sig))
+        sel = sel * np.isin(P[:, 1].astype('int'), d['ind_use'])
+        sel = sel * (np.abs(P[:, 0] - (t0 + max_t / 2.0)) <= (10.0 + max_t / 2.0))
+        assert dp.window_pick_count(float(t0)) == int(sel.sum()), t0
+        n_zero += int(sel.sum() == 0)
+    assert 0 < n_zero < len(t0s)
