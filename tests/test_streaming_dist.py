@@ -53,7 +53,11 @@ def test_day_processor_two_ranks_allreduce_equals_single_process():
     ctx = mp.get_context('spawn')
     with ctx.Manager() as mgr:
         ret = mgr.dict()
-        procs = [ctx.Process(target=_worker, args=(r, 2, 29533, tsteps, tsteps_abs, ret)) for r in range(2)]
+        import socket
+        with socket.socket() as sk:                      # a free rendezvous port on the loopback interface
+            sk.bind(('127.0.0.1', 0))
+            port = sk.getsockname()[1]
+        procs = [ctx.Process(target=_worker, args=(r, 2, port, tsteps, tsteps_abs, ret)) for r in range(2)]
         for p in procs:
             p.start()
         for p in procs:
