@@ -546,11 +546,11 @@ int launch_assoc_product(const genie_plan* p, const float* packed, const float* 
     const int64_t P = p->g.n_prod;
     const int G = p->g.n_grid;
     if (P == 0 || G == 0) return GENIE_OK;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.need()) {
         GENIE_CUDA_CHECK(cudaFuncSetAttribute(assoc_layer1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM));
         GENIE_CUDA_CHECK(cudaFuncSetAttribute(assoc_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K0_SMEM));
-        attr_set = true;
+        attr_set.mark();
     }
     const GraphView gv = make_view(p);
     {

@@ -11,6 +11,7 @@ using namespace gl;
 namespace {
 thread_local std::string g_last_error;
 std::atomic<int64_t> g_launches{0};
+std::atomic<uint64_t> g_plan_counter{0};
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 }  // namespace
@@ -244,6 +245,7 @@ int genie_plan_create(const genie_graph_desc_t* d, genie_plan_t** out) {
     }
     p->g = *d;
     p->n_edges_grid = -1;
+    p->cslot = (int)(g_plan_counter.fetch_add(1, std::memory_order_relaxed) % GENIE_CSLOTS);
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, dev);

@@ -30,14 +30,16 @@ constexpr int LDF = TM + 1;    // feature-tile row stride (floats): conflict-fre
 constexpr int K1_THREADS = 256;
 // init_trns weights + bias in the constant bank (FFMA reads them as uniform operands: no shared-memory broadcasts);
 // refreshed from the packed weights by a stream-ordered device-to-device copy before every launch.
-__constant__ float c_init[8 * LD + LD];
+__constant__ float c_init_slots[GENIE_CSLOTS][8 * LD + LD];     // one slot per plan (genie_plan::cslot)
 
+template <int CSLOT>
 __global__ void __launch_bounds__(K1_THREADS) da_init_kernel(const float* __restrict__ packed,
                                                              const float* __restrict__ slice,
                                                              const float* __restrict__ mask, float* __restrict__ tr0,
                                                              int64_t P, int tc_plan, const float* __restrict__ init_sta,
                                                              const float* __restrict__ init_src, int S) {
     __shared__ __align__(16) float sOut[K1_THREADS * LD_TR0];
+    const float* c_init = c_init_slots[CSLOT];       // compile-time slot: the weights stay immediate constant-bank operands
     const float a0 = packed[DA_SLOPES + SL_A0];
     // tensor-core path (da_tc_kernels.cu): store p = PReLU12(tr0) instead of tr0
     const bool post = tc_plan && packed[TC_BASE + TC_SCAL + TCS_OK] != 0.f;
@@ -367,10 +369,19 @@ int launch_da_init(const genie_plan* p, const float* packed, const float* slice,
     const int64_t P = p->g.n_prod;
     if (P == 0) return GENIE_OK;
     const int64_t blocks = (P + K1_THREADS - 1) / K1_THREADS;
-    GENIE_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_init, packed + DA_W0, sizeof(float) * (8 * LD + LD), 0, cudaMemcpyDeviceToDevice, st));
+    GENIE_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_init_slots, packed + DA_W0, sizeof(float) * (8 * LD + LD),
+                                             sizeof(float) * (8 * LD + LD) * p->cslot, cudaMemcpyDeviceToDevice, st));
     TimedLaunch tl(KID_DA_INIT, st);
-    da_init_kernel<<<(unsigned)blocks, K1_THREADS, 0, st>>>(packed, slice, mask, tr0, P, tc_plan ? 1 : 0, p->init_sta,
-                                                            p->init_src, p->g.n_sta);
+#define GENIE_INIT_CASE(C)                                                                                          \
+    case C:                                                                                                         \
+        da_init_kernel<C><<<(unsigned)blocks, K1_THREADS, 0, st>>>(packed, slice, mask, tr0, P, tc_plan ? 1 : 0,    \
+                                                                   p->init_sta, p->init_src, p->g.n_sta);           \
+        break;
+    switch (p->cslot) {
+        GENIE_INIT_CASE(0) GENIE_INIT_CASE(1) GENIE_INIT_CASE(2) GENIE_INIT_CASE(3)
+        default: set_error("launch_da_init: bad constant slot"); return GENIE_ERR_INVALID;
+    }
+#undef GENIE_INIT_CASE
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;
 }
@@ -379,11 +390,11 @@ int launch_da_layer1(const genie_plan* p, const float* packed, const float* tr0,
                      float* vb, bool tc_plan, cudaStream_t st) {
     const int64_t P = p->g.n_prod;
     if (P == 0) return GENIE_OK;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.need()) {
         GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)K2_SMEM));
-        attr_set = true;
+        attr_set.mark();
     }
     const int64_t n_tiles = (P + TM - 1) / TM;
     const int64_t grid = n_tiles < (int64_t)p->sm_count * 2 ? n_tiles : (int64_t)p->sm_count * 2;

@@ -626,11 +626,11 @@ int launch_da_layer1_s(const genie_plan* p, const float* packed, const float* pf
                        const float* mask, float* zc, float* va, float* vb, cudaStream_t st) {
     const genie_graph_desc_t& g = p->g;
     const int64_t n_tiles = (int64_t)g.n_sta_tiles * (g.n_grid_owned > 0 ? g.n_grid_owned : g.n_grid);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.need()) {
         GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer1_s_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
         GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer1_s_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-        attr_set = true;
+        attr_set.mark();
     }
     const int64_t grid = n_tiles < p->sm_count ? n_tiles : p->sm_count;
     TimedLaunch tl(KID_DA_LAYER1_S, st);

@@ -41,7 +41,7 @@ static_assert(SM_TOTAL <= 232448, "shared memory budget");
 // fc1 of the read-in (33 x 30 + bias) in the constant bank: FFMA reads its weight operand straight from c[][] (uniform, no
 // register-file write-back), which takes the weight broadcasts off the shared-memory pipe (the bound of this kernel in
 // profiles/r1k).  Refreshed from the caller's packed weights by a stream-ordered device-to-device copy before every launch.
-__constant__ float c_ri[W_FLOATS];
+__constant__ float c_ri_slots[GENIE_CSLOTS][W_FLOATS];      // one slot per plan (genie_plan::cslot)
 
 struct Bars {
     uint64_t full[N_WG], empty[N_WG];
@@ -96,7 +96,7 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
     return v[0];
 }
 
-template <bool STORE_LATENT>
+template <bool STORE_LATENT, int CSLOT>
 __global__ void __launch_bounds__(S2_THREADS, 1)
     da_layer2_s_kernel(const float* __restrict__ packed, const float* __restrict__ zc, const float* __restrict__ va,
                        const float* __restrict__ m2, const float* __restrict__ mask, const float* __restrict__ edge_attr,
@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1)
                        const int32_t* __restrict__ tile_rows, const int32_t* __restrict__ tile_meta,
                        const uint16_t* __restrict__ tile_nbr, const float* __restrict__ tile_invdeg) {
     extern __shared__ __align__(128) unsigned char smem[];
+    const float* c_ri = c_ri_slots[CSLOT];     // compile-time slot: fc1 stays immediate constant-bank operands
     float* sW = reinterpret_cast<float*>(smem + SM_W);
     float* part = reinterpret_cast<float*>(smem + SM_PART);
     float* wpart = reinterpret_cast<float*>(smem + SM_WPART);
@@ -326,26 +327,26 @@ int launch_da_layer2_s(const genie_plan* p, const float* packed, const float* zc
         set_error("launch_da_layer2_s: too many station tiles");
         return GENIE_ERR_UNSUPPORTED;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer2_s_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-        GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer2_s_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-        attr_set = true;
-    }
     const int n_own = g.n_grid_owned > 0 ? g.n_grid_owned : g.n_grid;
     const unsigned grid = (unsigned)(n_own < p->sm_count ? n_own : p->sm_count);
-    GENIE_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_ri, packed + RI_WFC1, sizeof(float) * W_FLOATS, 0, cudaMemcpyDeviceToDevice, st));
+    GENIE_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_ri_slots, packed + RI_WFC1, sizeof(float) * W_FLOATS, sizeof(float) * W_FLOATS * p->cslot,
+                                             cudaMemcpyDeviceToDevice, st));
+    static PerDeviceOnce attr_set;
+    const bool set_attr = attr_set.need();
     TimedLaunch tl(KID_DA_LAYER2_S, st);
-    if (latent_out)
-        da_layer2_s_kernel<true><<<grid, S2_THREADS, SM_TOTAL, st>>>(packed, zc, va, m2, mask, edge_attr, latent_out, out,
-                                                                     ld_out, g.n_sta, n_own, g.n_sta_tiles,
-                                                                     g.sta_tile_rows, g.sta_tile_meta, g.sta_tile_nbr,
-                                                                     g.sta_tile_invdeg);
-    else
-        da_layer2_s_kernel<false><<<grid, S2_THREADS, SM_TOTAL, st>>>(packed, zc, va, m2, mask, edge_attr, nullptr, out,
-                                                                      ld_out, g.n_sta, n_own, g.n_sta_tiles,
-                                                                      g.sta_tile_rows, g.sta_tile_meta, g.sta_tile_nbr,
-                                                                      g.sta_tile_invdeg);
+#define GENIE_S2_LAUNCH(L, C)                                                                                                  \
+    do {                                                                                                                        \
+        if (set_attr)                                                                                                           \
+            GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer2_s_kernel<L, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)); \
+        if (L == (latent_out != nullptr) && C == p->cslot)                                                                      \
+            da_layer2_s_kernel<L, C><<<grid, S2_THREADS, SM_TOTAL, st>>>(packed, zc, va, m2, mask, edge_attr, latent_out, out, ld_out, \
+                                                                         g.n_sta, n_own, g.n_sta_tiles, g.sta_tile_rows,       \
+                                                                         g.sta_tile_meta, g.sta_tile_nbr, g.sta_tile_invdeg);  \
+    } while (0)
+    GENIE_S2_LAUNCH(false, 0); GENIE_S2_LAUNCH(false, 1); GENIE_S2_LAUNCH(false, 2); GENIE_S2_LAUNCH(false, 3);
+    GENIE_S2_LAUNCH(true, 0); GENIE_S2_LAUNCH(true, 1); GENIE_S2_LAUNCH(true, 2); GENIE_S2_LAUNCH(true, 3);
+#undef GENIE_S2_LAUNCH
+    if (set_attr) attr_set.mark();
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;
 }

@@ -551,10 +551,10 @@ int launch_da_layer1_tc(const genie_plan* p, const float* packed, const float* p
         set_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
         return GENIE_ERR_CUDA;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.need()) {
         GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-        attr_set = true;
+        attr_set.mark();
     }
     const int64_t grid = n_tiles < p->sm_count ? n_tiles : p->sm_count;
     TimedLaunch tl(KID_DA_LAYER1_TC, st);

@@ -3,14 +3,21 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include <string>
 
 #include "../../include/genie_b200.h"
 #include "layout.h"
 
+// Weight blocks that kernels read as constant-bank operands (init_trns, read-in fc1) live in per-plan slots of a __constant__
+// array, refreshed in stream order before each launch: plans (models, e.g. the reference's mz_list, one per grid) that run
+// on different streams do not share a slot unless more than GENIE_CSLOTS plans are alive at once.
+constexpr int GENIE_CSLOTS = 4;     // the slot is a template parameter of the kernels that use it
+
 struct genie_plan {
     genie_graph_desc_t g;
     int sm_count;
+    int cslot;              // constant-bank slot of this plan
     int64_t n_edges_grid;   // number of grid-graph edges (host copy of grid_rowptr[G]), fetched lazily
     // Edge-feature model (genie_plan_set_edge_terms): per-node additive terms of layer 1, NULL = off.
     const float* edge_sta;  // [S or P][GENIE_EDGE_TERM_LD]
@@ -77,6 +84,17 @@ struct Workspace {
 Workspace carve_workspace(const genie_plan* p, void* base);
 
 void set_error(const std::string& msg);
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device (context): a launcher sets it once per device.
+// need() is true until mark() has been called for the CURRENT device; safe from several host threads (worst case the
+// attribute is set twice).
+struct PerDeviceOnce {
+    std::atomic<unsigned char> done[64];
+    PerDeviceOnce() { for (auto& d : done) d.store(0); }
+    static int dev() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < 64) ? d : 0; }
+    bool need() const { return done[dev()].load(std::memory_order_acquire) == 0; }
+    void mark() { done[dev()].store(1, std::memory_order_release); }
+};
 void count_launch(int n = 1);
 
 // Kernel ids of the optional per-kernel device timing (genie_timing_* in the C-ABI).

@@ -436,6 +436,7 @@ class GCN_Detection_Network_extended(nn.Module):
         self.ftrns1, self.ftrns2 = ftrns1, ftrns2
         self._plan = None
         self._plan_key = None
+        self._plan_refs = None
         self._packed = None
         self._read_in_attr = None
         self._heads_w = None
@@ -457,7 +458,8 @@ class GCN_Detection_Network_extended(nn.Module):
         self._plan = GraphPlan.from_edge_lists(A_in_sta, A_in_src, A_src_in_edges.edge_index, A_src, n_sta, n_grid,
                                                device=pos_src.device)
         self._read_in_attr = A_src_in_edges.x.to(pos_src.device).float().contiguous()
-        self._plan_key = None
+        self._plan_key, self._plan_refs = None, None
+        self._init_terms = self._assoc_terms = None          # keyed on id(plan): a recycled id must not match
         self._set_edge_means(pos_loc, pos_src, A_src_in_sta)
 
     def set_adjacencies_cartesian(self, A_sta_sta, A_src_src, read_in_attr, n_sta, n_grid, device=None, pos_loc=None,
@@ -470,7 +472,8 @@ class GCN_Detection_Network_extended(nn.Module):
         self._plan = GraphPlan.cartesian(A_sta_sta, A_src_src, n_sta, n_grid, device=device)
         self._read_in_attr = read_in_attr.to(device).float().contiguous()
         self.A_src = A_src_src
-        self._plan_key = None
+        self._plan_key, self._plan_refs = None, None
+        self._init_terms = self._assoc_terms = None
         # association inputs (forward_fixed): the read-out graph A_Lg_in_src is the implicit [g(i); i] with the read-in features
         self.A_Lg_in_src, self.A_edges_p, self.A_edges_s = None, A_edges_p, A_edges_s
         self.dt_partition, self.tlatent = dt_partition, tlatent
@@ -522,13 +525,16 @@ class GCN_Detection_Network_extended(nn.Module):
 
     def _plan_for(self, A_in_sta, A_in_src, A_src_in_edges, A_src, n_sta, n_grid, dev, pos=None, A_src_in_sta=None):
         """`forward` receives the graphs on every call (module.py:908): plans are cached on tensor identity."""
-        key = (A_in_sta.data_ptr(), A_in_src.data_ptr(), A_src_in_edges.edge_index.data_ptr(), A_src.data_ptr(),
-               A_in_sta.shape[1], A_in_src.shape[1], n_sta, n_grid)
+        # The key tensors are kept referenced next to the plan (self._plan_refs): a freed tensor's address can be handed out
+        # again by the caching allocator for the next sample's same-sized edge lists, which would match a stale key.
+        ei = A_src_in_edges.edge_index
+        keyed = (A_in_sta, A_in_src, ei, A_src, A_src_in_edges.x)
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape), str(t.device)) for t in keyed) + (n_sta, n_grid, str(dev))
         if self._plan is None or self._plan_key != key:
-            self._plan = GraphPlan.from_edge_lists(A_in_sta, A_in_src, A_src_in_edges.edge_index, A_src, n_sta, n_grid,
-                                                   device=dev)
+            self._plan = GraphPlan.from_edge_lists(A_in_sta, A_in_src, ei, A_src, n_sta, n_grid, device=dev)
             self._read_in_attr = A_src_in_edges.x.to(dev).float().contiguous()
-            self._plan_key = key
+            self._plan_key, self._plan_refs = key, keyed
+            self._init_terms = self._assoc_terms = None
             if self.updated_model:        # module.py:1059-1072: the edge features come from the positions of the call
                 if pos is None:
                     raise RuntimeError('the updated model needs the station / grid positions to build its edge features')

@@ -72,16 +72,19 @@ def extract_inputs_adjacencies(trv, locs, ind_use, x_grid, x_grid_trv, x_grid_tr
     dev = A_sta_sta.device
     A_prod_sta, A_prod_src, A_src_in_prod, _ = (a.to(dev) for a in product_edge_lists(A_sta_sta.cpu(), A_src_src.cpu(),
                                                                                        n_sta_slice, n_spc))
-    # time-pointer tables of the used stations, re-indexed to the station subset (:723-734, the reference's expressions)
-    perm_vec = -1 * np.ones(n_sta)
-    perm_vec[ind_use] = np.arange(n_sta_slice)
-    len_dt = len(x_grid_trv_ref)
-    rows = np.tile(np.arange(k_time_edges * len_dt), n_sta_slice) + (len_dt * k_time_edges) * ind_use.repeat(k_time_edges * len_dt)
-    one_vec = np.repeat(ind_use * np.ones(n_sta_slice), k_time_edges * len_dt).astype('int')
-    A_edges_time_p = (n_sta_slice * (np.asarray(x_grid_trv_pointers_p)[rows] - one_vec) / n_sta) + perm_vec[one_vec]
-    A_edges_time_s = (n_sta_slice * (np.asarray(x_grid_trv_pointers_s)[rows] - one_vec) / n_sta) + perm_vec[one_vec]
-    A_edges_ref = np.asarray(x_grid_trv_ref) * 1 + 0
-    assert A_edges_time_p.max() < n_spc * n_sta_slice and A_edges_time_s.max() < n_spc * n_sta_slice
+    # Time-pointer tables of the used stations (:723-734).  A pointer is a product-node id over ALL stations,
+    # g * n_sta + station; the block of station u (k_time_edges * len_dt entries) moves to slot u of the subset and its
+    # entries become g * n_sta_slice + u.  The division is carried out in floating point as the reference's is.
+    blk = int(k_time_edges) * len(x_grid_trv_ref)
+    slot = np.arange(n_sta_slice, dtype=np.float64).reshape(-1, 1)
+
+    def subset_pointers(table):
+        rows = np.asarray(table).reshape(n_sta, blk)[ind_use]                           # [n_sta_slice, blk]
+        return ((n_sta_slice * (rows - ind_use.reshape(-1, 1))) / n_sta + slot).reshape(-1)
+    A_edges_time_p, A_edges_time_s = subset_pointers(x_grid_trv_pointers_p), subset_pointers(x_grid_trv_pointers_s)
+    A_edges_ref = np.array(x_grid_trv_ref, copy=True)
+    if max(A_edges_time_p.max(), A_edges_time_s.max()) >= n_spc * n_sta_slice:
+        raise ValueError('time pointers reference product nodes outside the station subset')
     return [A_sta_sta, A_src_src, A_prod_sta, A_prod_src, A_src_in_prod, A_edges_time_p, A_edges_time_s, A_edges_ref]
 
 
@@ -224,6 +227,7 @@ class InputExtractor(object):
         self.n_sta_use = len(ind_use)
         perm = -1 * np.ones(self.n_locs, dtype=np.int32)
         perm[ind_use] = np.arange(self.n_sta_use, dtype=np.int32)                       # process_utils.py:485-486
+        self.sta_perm_host = perm                         # host copy: no device sync per window
         self.sta_perm = torch.from_numpy(perm).to(dev)
         self.ind_use = torch.from_numpy(ind_use.astype(np.int32)).to(dev)
         self.trv_times = trv_times if torch.is_tensor(trv_times) else torch.from_numpy(np.ascontiguousarray(trv_times))
@@ -241,7 +245,7 @@ class InputExtractor(object):
         P = np.asarray(P, dtype=np.float64)
         P = P[np.argsort(P[:, 0], kind='stable')]
         self._day = (P[:, 0].copy(), torch.from_numpy(np.ascontiguousarray(P)).to(self.plan.device))
-        used = self.sta_perm.cpu().numpy()[P[:, 1].astype('int')] >= 0
+        used = self.sta_perm_host[P[:, 1].astype('int')] >= 0
         self._used_cum = np.concatenate(([0], np.cumsum(used))).astype(np.int64)
 
     def used_cum(self):
@@ -287,6 +291,51 @@ _extractors = {}
 _legacy_cache = {}
 
 
+def _legacy_host_tables(locs, ind_use, arrivals, phase_labels, arrivals_tree, time_samples, max_t, pred_params):
+    """Host half of extract_inputs_from_data_fixed_grids_with_phase_type: the pick selection of every sample, the merged
+    offset time axes and the per-sample pick lists — a few thousand numbers, numpy."""
+    arrivals = np.asarray(arrivals, dtype=np.float64)
+    phase_labels = np.asarray(phase_labels)
+    time_samples = np.asarray(time_samples, dtype=np.float64).reshape(-1)
+    n_batch, n_sta = len(time_samples), int(locs.shape[0])
+    t_win, kernel_sig_t = float(pred_params[0]), float(pred_params[1])
+    if arrivals_tree is not None:                                                                          # :138
+        lp = arrivals_tree.query_ball_point(time_samples.reshape(-1, 1) + max_t / 2.0, r=t_win + max_t / 2.0)
+        lp = [np.array(list(l)).astype('int') for l in lp]
+    else:
+        lp = [np.where(np.abs(arrivals[:, 0] - (ts + max_t / 2.0)) <= t_win + max_t / 2.0)[0] for ts in time_samples]
+    ind_sta_select = np.unique(ind_use)                                                                    # :152
+    # One merged, sorted time axis for all samples and stations (:177-189): sample i and absolute station a are moved to
+    # their own disjoint stretch of the axis, offset i * 1.5 max_t + a * 1.5 n_batch * 1.5 max_t, relative to the sample time.
+    offset_per_batch = 1.5 * max_t
+    offset_per_station = 1.5 * n_batch * offset_per_batch
+    shifted, labels = [], []
+    for i, rows in enumerate(lp):
+        shift = -time_samples[i] + i * offset_per_batch + offset_per_station * arrivals[rows, 1]
+        shifted.append(arrivals[rows, 0] + shift)
+        labels.append(phase_labels[rows])
+    shifted, labels = np.concatenate(shifted), np.concatenate(labels)
+    by_time = np.argsort(shifted)                                                                          # :188
+    shifted, labels = np.ascontiguousarray(shifted[by_time]), labels[by_time]
+    axes = [shifted] + [np.ascontiguousarray(shifted[labels == ph]) for ph in (0, 1)]                      # :209-210
+    # per-sample pick lists (:270-291): picks on selected stations, ordered by (station slot, time)
+    slot_of = np.full(n_sta, -1.0)
+    slot_of[ind_sta_select] = np.arange(len(ind_sta_select))
+    lp_times, lp_stations, lp_phases, lp_meta = [], [], [], []
+    for i, rows in enumerate(lp):
+        slots = slot_of[arrivals[rows, 1].astype('int')]
+        rows = rows[slots > -1]
+        slots = slots[slots > -1]
+        order = np.lexsort((arrivals[rows, 0], slots))
+        rows = rows[order]
+        lp_times.append(arrivals[rows, 0] - time_samples[i])
+        lp_stations.append(slots[order])
+        lp_phases.append(phase_labels[rows])
+        lp_meta.append(arrivals[rows, :])
+    return dict(axes=axes, lists=[lp_times, lp_stations, lp_phases, lp_meta], ind_sta_select=ind_sta_select,
+                offset_per_batch=offset_per_batch, offset_per_station=offset_per_station, kernel_sig_t=kernel_sig_t)
+
+
 def extract_inputs_from_data_fixed_grids_with_phase_type(trv, locs, ind_use, arrivals, phase_labels, arrivals_tree,
                                                           time_samples, x_grid, x_grid_trv, lat_range, lon_range,
                                                           depth_range, max_t, training_params, graph_params, pred_params,
@@ -296,26 +345,11 @@ def extract_inputs_from_data_fixed_grids_with_phase_type(trv, locs, ind_use, arr
     time sample.  The pick selection and the merged, offset time axis of :137-189 are a few thousand numbers and are built on
     the host with the reference's own numpy expressions; the G x S x 4 nearest-pick searches run in libgenie_b200."""
     import ctypes
-    arrivals = np.asarray(arrivals, dtype=np.float64)
-    phase_labels = np.asarray(phase_labels)
     time_samples = np.asarray(time_samples, dtype=np.float64).reshape(-1)
     n_batch, n_spc, n_sta = len(time_samples), int(x_grid.shape[0]), int(locs.shape[0])
-    t_win, kernel_sig_t = float(pred_params[0]), float(pred_params[1])
-    if arrivals_tree is not None:                                                                          # :138
-        lp = arrivals_tree.query_ball_point(time_samples.reshape(-1, 1) + max_t / 2.0, r=t_win + max_t / 2.0)
-        lp = [np.array(list(l)).astype('int') for l in lp]
-    else:
-        lp = [np.where(np.abs(arrivals[:, 0] - (ts + max_t / 2.0)) <= t_win + max_t / 2.0)[0] for ts in time_samples]
-    ind_sta_select = np.unique(ind_use)                                                                    # :152
-    offset_per_batch = 1.5 * max_t                                                                         # :177
-    offset_per_station = 1.5 * n_batch * offset_per_batch                                                  # :178
-    arrivals_offset = np.hstack([-time_samples[i] + i * offset_per_batch + offset_per_station * arrivals[lp[i], 1]
-                                 for i in range(n_batch)])                                                 # :180
-    t_sel = np.hstack([arrivals[lp[i], 0] for i in range(n_batch)]) + arrivals_offset                      # :182
-    ph_sel = np.hstack([phase_labels[lp[i]] for i in range(n_batch)])
-    order = np.argsort(t_sel)                                                                              # :188
-    t_sel, ph_sel = np.ascontiguousarray(t_sel[order]), ph_sel[order]
-    axes = [t_sel, np.ascontiguousarray(t_sel[ph_sel == 0]), np.ascontiguousarray(t_sel[ph_sel == 1])]    # :209-210
+    h = _legacy_host_tables(locs, ind_use, arrivals, phase_labels, arrivals_tree, time_samples, max_t, pred_params)
+    axes, ind_sta_select, kernel_sig_t = h['axes'], h['ind_sta_select'], h['kernel_sig_t']
+    offset_per_batch, offset_per_station = h['offset_per_batch'], h['offset_per_station']
     dev = torch.device(device)
     if not dev.type == 'cuda':
         raise capi.GenieError('genie_b200 has no CPU path: device must be a CUDA device')
@@ -336,22 +370,7 @@ def extract_inputs_from_data_fixed_grids_with_phase_type(trv, locs, ind_use, arr
         capi.check(capi.load().genie_input_nearest_fwd(
             ctypes.byref(prm), ptr(axes_dev[0]), ptr(axes_dev[1]), ptr(axes_dev[2]), capi.dptr(ind_dev, torch.int32),
             capi.dptr(trv_dev, torch.float32), capi.dptr(Slice), capi.dptr(Mask), capi.stream_ptr(dev)))
-    # per-sample pick lists (:270-291)
-    lp_times, lp_stations, lp_phases, lp_meta = [], [], [], []
-    for i in range(n_batch):
-        perm_vec = -1 * np.ones(n_sta)
-        perm_vec[ind_sta_select] = np.arange(len(ind_sta_select))
-        meta = arrivals[lp[i], :]
-        phase_vals = phase_labels[lp[i]]
-        times = meta[:, 0]
-        indices = perm_vec[meta[:, 1].astype('int')]
-        ineed = np.where(indices > -1)[0]
-        times, indices, phase_vals, meta = times[ineed], indices[ineed], phase_vals[ineed], meta[ineed]
-        lex_sort = np.lexsort((times, indices))
-        lp_times.append(times[lex_sort] - time_samples[i])
-        lp_stations.append(indices[lex_sort])
-        lp_phases.append(phase_vals[lex_sort])
-        lp_meta.append(meta[lex_sort])
+    lp_times, lp_stations, lp_phases, lp_meta = h['lists']
     return [[Slice[i] for i in range(n_batch)], [Mask[i] for i in range(n_batch)]], \
         [lp_times, lp_stations, lp_phases, lp_meta]
 
@@ -367,10 +386,12 @@ def extract_input_from_data(trv_pairwise, P, t0, ind_use, locs, x_grid, A_src_in
     t0v = float(np.asarray(t0).reshape(-1)[0])
     ind_use = np.asarray(ind_use).astype('int')
     A = A_src_in_sta.cpu().numpy() if torch.is_tensor(A_src_in_sta) else np.asarray(A_src_in_sta)
-    key = (id(trv_times), id(A_src_in_sta), len(ind_use), int(ind_use.sum()), float(max_t), float(kernel_sig_t),
-           float(dt), str(device))
-    ex = _extractors.get(key)
-    if ex is None:
+    # One extractor is cached.  The key holds the station subset itself and the sizes; the entry keeps `trv_times` and
+    # `A_src_in_sta` referenced, so their id()s cannot be recycled by other objects while the entry lives.
+    key = (id(trv_times), id(A_src_in_sta), ind_use.tobytes(), int(locs.shape[0]), int(x_grid.shape[0]), float(max_t),
+           float(kernel_sig_t), float(dt), str(device), id(plan) if plan is not None else None)
+    ent = _extractors.get(key)
+    if ent is None:
         G, S = int(x_grid.shape[0]), len(ind_use)
         if plan is None:
             # a node -> (station, grid) table is enough for a1; the plan only carries sizes here
@@ -385,11 +406,12 @@ def extract_input_from_data(trv_pairwise, P, t0, ind_use, locs, x_grid, A_src_in
         nodes = (None, None) if plan.mode == 0 else (A[0], A[1])
         ex = InputExtractor(plan, trv_times, ind_use, locs.shape[0], max_t, kernel_sig_t, dt, nodes[0], nodes[1])
         _extractors.clear()
-        _extractors[key] = ex
+        _extractors[key] = ent = (ex, trv_times, A_src_in_sta, plan)
+    ex = ent[0]
     P = np.asarray(P, dtype=np.float64)
     keep = (P[:, 0] > (t0v - 2.0 * kernel_sig_t)) & (P[:, 0] < (t0v + max_t + 2.0 * kernel_sig_t))      # :476
     P_slice = P[keep]
-    P_slice = P_slice[ex.sta_perm.cpu().numpy()[P_slice[:, 1].astype('int')] > -1]                     # :480-482
+    P_slice = P_slice[ex.sta_perm_host[P_slice[:, 1].astype('int')] > -1]                               # :480-482
     picks_dev = torch.from_numpy(np.ascontiguousarray(P_slice)).to(ex.plan.device)
     Slice, Mask = ex(t0v, picks_dev)
     lp = extract_pick_inputs_from_data(P_slice, locs, ind_use, np.array([t0v]), max_t)

@@ -277,3 +277,23 @@ def test_day_processor_window_pick_count_matches_reference_rule():
         assert dp.window_pick_count(float(t0)) == int(sel.sum()), t0
         n_zero += int(sel.sum() == 0)
     assert 0 < n_zero < len(t0s)
+
+
+@pytest.mark.parametrize('name', ['legacy_12of14x60', 'legacy_8x30_short'])
+def test_legacy_host_tables_match_reference(name):
+    """Host half of a1' (process_utils.py:137-189, :270-291): per-sample pick lists identical to the unmodified reference's,
+    with and without the caller's k-d tree; the merged time axes are sorted and partition into the two phases."""
+    from scipy.spatial import cKDTree
+    from genie_b200.process_utils import _legacy_host_tables
+    d, _ = load_golden(name)
+    P = d['picks']
+    for tree in (cKDTree(P[:, 0][:, None]), None):
+        h = _legacy_host_tables(d['sta'], d['ind_use'], P, P[:, 4], tree, d['time_samples'], float(d['max_t']),
+                                [float(d['t_win']), float(d['kernel_sig_t'])])
+        for i in range(len(d['time_samples'])):
+            for j, k in enumerate(('lp_times', 'lp_stations', 'lp_phases', 'lp_meta')):
+                got = h['lists'][j][i]
+                assert got.dtype == d['%s%d' % (k, i)].dtype and np.array_equal(got, d['%s%d' % (k, i)]), (k, i)
+        a_all, a_p, a_s = h['axes']
+        assert np.all(np.diff(a_all) >= 0) and len(a_p) + len(a_s) == len(a_all)
+        assert np.array_equal(np.sort(np.concatenate((a_p, a_s))), a_all)
