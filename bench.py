@@ -120,20 +120,25 @@ class ClockSampler(object):
 
 # ---- the reference algorithm on the host cores (oracle port) ------------------------------------------------------------
 
-def cpu_reference(workload, steps, warmup, grid_sample=None):
-    """Times oracle.forward_fixed_source + oracle.input_scatter (torch-CPU fp32, all host threads) on a bounded sample:
-    all stations, the first `grid_sample` grid nodes (Morton order => a compact sub-volume) with their own kNN graph.
-    Cost is linear in the number of product nodes, so windows/s at full size = sample rate * Gs/G."""
+def cpu_reference(workload, steps, warmup, sample_nodes=5.0e6):
+    """Times oracle.input_scatter + oracle.forward_fixed_source (torch-CPU fp32, all host threads) on a bounded sample:
+    all stations, the first Gs grid nodes (Morton order => a compact sub-volume) with their own kNN graph, Gs chosen so that
+    the sample has about `sample_nodes` product nodes (P = 5e6 for the dense C4 / C5 sizes) — fewer when the
+    host has little free memory (the oracle's message tensors take ~6 kB per product node).  Cost is linear in the number of
+    product nodes, so windows/s at full size = sample rate x Gs/G, labelled extrapolated.  Median over the
+    timed windows."""
     import torch
     from genie_b200 import synth
     from oracle import genie_oracle as go
     S, G, k_s, k_g = WORKLOADS[workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    if grid_sample is None:
-        per_step_nodes = 5.0e5 * min(1.0, 30.0 / max(steps + warmup, 1))     # ~2 s per 5e5 nodes on 8-16 cores
-        grid_sample = int(max(20, min(G, per_step_nodes // S)))
-    Gs = min(G, grid_sample)
+    try:
+        import psutil
+        sample_nodes = min(sample_nodes, 0.5 * psutil.virtual_memory().available / 6000.0)
+    except ImportError:
+        pass
+    Gs = int(max(20, min(G, sample_nodes // S)))
     net = synth.Network(S, G, seed=0)
     grid = net.grid[:Gs]
     A = go.build_adjacencies_dense(net.sta, grid, k_s, k_g)
@@ -147,7 +152,6 @@ def cpu_reference(workload, steps, warmup, grid_sample=None):
     tq = torch.arange(-3.0, 3.01, 0.75).reshape(-1, 1)
     gridt = torch.from_numpy(grid).float()
     ind_use = np.arange(S)
-    qe = None
     times = []
     with torch.no_grad():
         for i in range(n_win):
@@ -161,14 +165,15 @@ def cpu_reference(workload, steps, warmup, grid_sample=None):
             t_b = time.perf_counter()
             if i >= warmup:
                 times.append(t_b - t_a)
-    total = float(np.sum(times))
-    wps_sample = len(times) / total
-    value = wps_sample * Gs / G
-    sample = ('oracle (torch-CPU fp32 port of module.py:999-1020 + process_utils.py:460-629) on all %d stations x the '
-              'first %d of %d grid nodes (P=%d), %d windows after %d warm-up; %.3f s/window on the sample; value = '
-              'sample windows/s x %d/%d (cost linear in P, extrapolated)' % (S, Gs, G, S * Gs, len(times), warmup,
-                                                                             total / len(times), Gs, G))
-    return dict(value=value, unit=UNIT, cores=cores, kind='port', sample=sample), total / len(times)
+    med = float(np.median(times))
+    value = (1.0 / med) * Gs / G
+    sample = ('oracle (torch-CPU fp32 port of module.py:999-1020 + process_utils.py:460-629), %d host threads, on all %d '
+              'stations x the first %d of %d grid nodes (P=%d), %d windows after %d warm-up, median %.3f s/window on the '
+              'sample; %s' % (cores, S, Gs, G, S * Gs, len(times), warmup, med,
+                              'value = sample windows/s x %d/%d (cost linear in P: EXTRAPOLATED to the full size)' % (Gs, G)
+                              if Gs < G else 'full size, not extrapolated'))
+    return dict(value=value, unit=UNIT, cores=cores, kind='port', sample=sample, sample_product_nodes=S * Gs,
+                windows_timed=len(times), extrapolated=bool(Gs < G)), med
 
 
 def run_reference(args):
@@ -176,7 +181,9 @@ def run_reference(args):
     if rank != 0:
         return
     S, G, k_s, k_g = WORKLOADS[args.workload]
-    cb, s_per_step = cpu_reference(args.workload, args.steps, args.warmup)
+    # P = 5e6 per step when the whole run stays within a few minutes (~10 s per step at that size on 16 cores), else smaller
+    n_win = max(args.steps + args.warmup, 1)
+    cb, s_per_step = cpu_reference(args.workload, args.steps, args.warmup, sample_nodes=min(5.0e6, 1.25e8 / n_win))
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 / cb['value'], 'higher_is_better': True,
@@ -205,6 +212,7 @@ class Workload(object):
         net = synth.Network(S, G, seed=0)
         self.net = net
         A_sta, A_src = extract_inputs_adjacencies_cartesian(net.sta, net.grid, k_s, k_g)
+        self.A_sta, self.A_src = A_sta, A_src
         sta_d = torch.from_numpy(net.sta).to(dev)
         grid_d = torch.from_numpy(net.grid).to(dev)
         trv = torch.empty((G, S, 2), dtype=torch.float32, device=dev)
@@ -326,6 +334,40 @@ class ShardedWorkload(object):
             d2h = (y.numel() + x.numel()) * 4
         torch.cuda.current_stream().synchronize()
         return (hi - lo) * 5 * 8, d2h
+
+
+def closure_parity(wl, w, n_clusters=5, cluster=4):
+    """Oracle check of one of the timed windows at FULL size (outside every timed region): the window's a1 inputs, x_latent
+    and Bipartite_ReadIn rows of >= 16 sampled grid nodes against the CPU oracle run on their 2-hop source-graph closure
+    (oracle/closure_check.py), and y / x of the timed call against the oracle's SpatialAggregation + heads on the full grid.
+    Element-wise (row-scaled) relative metric; the integer time-bin map must be equal."""
+    import torch
+    from oracle import closure_check as cc
+    m, ex, S, G = wl.model, wl.ex, wl.S, wl.G
+    t0 = w * STEP_S
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    targets = cc.sample_targets(G, n_clusters, cluster)
+    lo, hi = ex.window_rows(t0)
+    picks = ex._day[1][lo:hi].cpu().numpy()
+    trv_of = lambda nodes: ex.trv_times[torch.from_numpy(nodes).to(wl.dev)].cpu().numpy()
+    attr_of = lambda nodes: m._read_in_attr.view(G, S, 3)[torch.from_numpy(nodes).to(wl.dev)].reshape(-1, 3).cpu().numpy()
+    t_a = time.time()
+    want = cc.oracle_on_closure(sd, wl.A_sta, wl.A_src, S, G, targets, picks, t0, trv_of, attr_of, wl.max_t, KERNEL_SIG_T, DT)
+    Slice, Mask, tb = ex(t0, want_time_bin=True)
+    rows = torch.from_numpy(want['nodes']).to(wl.dev)
+    _, latent, readin = m.front_end(Slice, Mask, wl.grid, want_latent=True, want_readin=True, locs_use_cart=wl.locs)
+    y, x = m.forward_fixed_source(Slice, Mask, None, None, None, wl.locs, wl.grid, wl.xq, wl.tq)       # the timed call
+    rep = cc.compare(want, tb[rows].cpu().numpy(), Slice[rows].cpu().numpy(), Mask[rows].cpu().numpy(),
+                     latent[rows].cpu().numpy(), readin[torch.from_numpy(targets).to(wl.dev)].cpu().numpy())
+    del latent, tb
+    y_o, x_o = cc.oracle_tail(sd, readin.cpu(), wl.A_src, wl.grid.cpu(), wl.xq.cpu(), wl.tq.cpu(), SCALE_REL,
+                              float(m.TemporalAttention.scale_t))
+    rep['y_rel'], rep['x_rel'] = cc.global_rel(y.cpu().numpy(), y_o), cc.global_rel(x.cpu().numpy(), x_o)
+    rep['window'], rep['picks_in_window'], rep['seconds'] = int(w), int(hi - lo), round(time.time() - t_a, 1)
+    rep['tolerance'] = 1e-4
+    rep['ok'] = bool(rep.get('time_bin_equal') and rep.get('mask_equal') and rep['max_rel'] < 1e-4 and
+                     rep['y_rel'] < 1e-4 and rep['x_rel'] < 1e-4)
+    return rep
 
 
 def run_genie(args):
@@ -452,8 +494,10 @@ def run_genie(args):
                          'library_kernels_share_of_step': kernel_total / ms},
             'clocks': clocks,
         }
+        if not sharded and not args.no_parity_check:
+            line['parity_check'] = closure_parity(wl, windows[W])          # the first timed window, against the CPU oracle
         if world == 1 and not args.no_cpu_baseline:
-            line['cpu_baseline'] = cpu_reference(args.workload, 3, 1)[0]
+            line['cpu_baseline'] = cpu_reference(args.workload, 5, 1, sample_nodes=2.0e6)[0]   # ~25 s of CPU work
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -469,6 +513,7 @@ def main():
     ap.add_argument('--workload', default='c4_1000x50000_dense', choices=sorted(WORKLOADS))
     ap.add_argument('--day-seconds', type=float, default=DAY_S)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-parity-check', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'genie' else args.warmup
     if args.impl == 'reference':

@@ -1,18 +1,23 @@
 #!/bin/bash
 # One GPU-box visit: parity tests, timing probe, bench line, ncu launch list + full capture of the top kernels.
-# usage: scripts/gpu_round.sh <tag> [skip-ncu]
+# usage: scripts/gpu_round.sh <tag> [skip-ncu|skip-tests]
 tag=${1:-r1}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${tag}_pytest.log
+if [ "$2" != "skip-tests" ]; then
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${tag}_pytest.log
 tail -5 gpurun_out/${tag}_pytest.log
+fi
 timeout 600 python scripts/probe_perf.py c2 c4 > gpurun_out/${tag}_probe.log 2>&1
 cat gpurun_out/${tag}_probe.log
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
 tail -3 gpurun_out/${tag}_bench.err; cat gpurun_out/${tag}_bench.json
 if [ "$2" != "skip-ncu" ]; then
 GENIE_BENCH_PROFILE=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 300 --csv \
-  --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --day-seconds 2000 > gpurun_out/${tag}_ncu_bench.log 2>&1
-GENIE_BENCH_PROFILE=1 timeout 1200 ncu --profile-from-start off --set full --clock-control none --import-source on \
-  -k regex:'da_init|src_mean|da_layer1_s|da_layer2_s' -c 5 -o gpurun_out/${tag}_prof -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --day-seconds 2000 > gpurun_out/${tag}_ncu_full.log 2>&1
+  --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-parity-check --day-seconds 2000 > gpurun_out/${tag}_ncu_bench.log 2>&1
+# --set full + the tensor-pipe counters BASELINE.json's north star names
+GENIE_BENCH_PROFILE=1 timeout 1200 ncu --profile-from-start off --set full \
+  --metrics sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum,sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_uniform.sum \
+  --clock-control none --import-source on \
+  -k regex:'input_gather|da_init|src_mean|da_layer1_s|da_layer2_s|window_' -c 7 -o gpurun_out/${tag}_prof -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity-check --day-seconds 2000 > gpurun_out/${tag}_ncu_full.log 2>&1
 tail -3 gpurun_out/${tag}_ncu_full.log
 fi

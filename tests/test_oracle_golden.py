@@ -199,3 +199,44 @@ def test_subgraph_window_matches_reference(name):
     for key in ('x_latent', 'read_in', 'x_spatial'):
         assert rel_err(parts[key].numpy(), d[key]) < 2e-6, key
     assert rel_err(y.numpy(), d['y']) < 2e-6 and rel_err(x.numpy(), d['x']) < 2e-6
+
+
+def test_closure_check_reproduces_the_full_oracle():
+    """oracle/closure_check.py (the full-size parity anchor of the GPU tests and of bench.py): on a network small enough for
+    the whole oracle, the rows of sampled grid nodes computed on their 2-hop closure equal the full computation."""
+    from genie_b200 import synth
+    from oracle import closure_check as cc
+    S, G = 12, 600
+    net = synth.Network(S, G, seed=4)
+    A = go.build_adjacencies_dense(net.sta, net.grid, 8, 15)
+    trv = net.travel_times()
+    attr = net.read_in_offsets(30000.0)
+    max_t = net.max_moveout()
+    P = synth.make_picks(net, 0.0, 400.0, seed=5, false_per_sta_min=6.0)
+    sd = go.init_state(seed=2)
+    t0 = 100.0
+    Sl, Mk, parts = go.input_scatter(P, t0, np.arange(S), S, A[5].numpy(), trv, max_t, 3.0, 0.3, return_parts=True)
+    with torch.no_grad():
+        x_lat = go.data_aggregation(sd, 'DataAggregation.', torch.from_numpy(Sl), torch.from_numpy(Mk), A[2], A[3])
+        r = go.bipartite_read_in(sd, 'Bipartite_ReadIn.', x_lat, torch.from_numpy(attr), A[4], torch.from_numpy(Mk))
+    targets = cc.sample_targets(G, 5, 4)
+    assert len(targets) >= 16
+    want = cc.oracle_on_closure(sd, A[0], A[1], S, G, targets, P, t0, lambda n: trv[n],
+                                lambda n: attr.reshape(G, S, 3)[n].reshape(-1, 3), max_t, 3.0, 0.3)
+    assert want['n_closure'] < G                       # a real sub-network, not the whole grid
+    rep = cc.compare(want, parts['time_bin'][want['nodes']], Sl[want['nodes']], Mk[want['nodes']],
+                     x_lat.numpy()[want['nodes']], r.numpy()[targets])
+    assert rep['time_bin_equal'] and rep['mask_equal'] and rep['slice_max_abs'] == 0.0
+    assert rep['max_rel'] < 1e-6, rep
+    # the cheap tail on the full grid from the full read-in table reproduces forward_fixed_source
+    xq = torch.from_numpy(np.random.default_rng(0).uniform(0, net.width, (50, 3))).float()
+    xq[:, 2] = -xq[:, 2] / net.width * 40000.0
+    tq = torch.arange(-3.0, 3.01, 0.75).reshape(-1, 1)
+    grid = torch.from_numpy(net.grid).float()
+    y0, x0 = go.forward_fixed_source(sd, torch.from_numpy(Sl), torch.from_numpy(Mk), A[2], A[3], torch.from_numpy(attr), A[4],
+                                     A[1], grid, xq, tq, 30000.0, 9.0)
+    y1, x1 = cc.oracle_tail(sd, r, A[1], grid, xq, tq, 30000.0, 9.0)
+    assert np.array_equal(y0.numpy(), y1) and np.array_equal(x0.numpy(), x1)
+    # the row-wise metric is the stricter one
+    a = np.array([[1.0, 1e-3], [1e-3, 1e-3]]); b = a.copy(); b[1, 1] += 1e-6
+    assert cc.rowwise_rel(b, a) > 100 * cc.global_rel(b, a)
