@@ -17,7 +17,7 @@ _LIB_PATH = os.path.join(_HERE, 'libgenie_b200.so')
 _lib = None
 
 GRAPH_CARTESIAN, GRAPH_EXPLICIT = 0, 1
-ABI_VERSION = 6
+ABI_VERSION = 7
 EDGE_TERM_LD = 48           # GENIE_EDGE_TERM_LD
 
 c_f32p = ctypes.c_void_p   # device pointers are passed as opaque addresses
@@ -70,7 +70,12 @@ class InputParams(ctypes.Structure):
     _fields_ = [('t0', ctypes.c_double), ('max_t', ctypes.c_double), ('kernel_sig_t', ctypes.c_double),
                 ('dt', ctypes.c_double), ('ref0', ctypes.c_double), ('ref_step', ctypes.c_double),
                 ('n_ts', ctypes.c_int32), ('n_extra', ctypes.c_int32), ('n_locs', ctypes.c_int32),
-                ('n_sta_use', ctypes.c_int32)]
+                ('n_sta_use', ctypes.c_int32), ('use_sign_input', ctypes.c_int32), ('reserved_', ctypes.c_int32)]
+
+
+class WindowParams(ctypes.Structure):
+    """genie_window_params_t: the device-resident per-window block of genie_window_fwd."""
+    _fields_ = [('prm', InputParams), ('pick_lo', ctypes.c_int64), ('pick_hi', ctypes.c_int64)]
 
 
 # name -> (restype, argtypes); every symbol include/genie_b200.h declares
@@ -122,6 +127,8 @@ SIGNATURES = {
                                               ctypes.POINTER(ctypes.c_size_t)]),
     'genie_da_layer2_readin_fwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     'genie_frontend_fwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _P, ctypes.c_float, _P, _P, _P, _P, _P]),
+    'genie_window_fwd': (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, ctypes.c_int32, _P, _P, _P, _P, _P, ctypes.c_int32, _P, _P, ctypes.c_float,
+                                        _P, _P, _P, _P, _P, _P, _P]),
 }
 
 

@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "internal.h"
+#include "input.cuh"
 
 using namespace gl;
 
@@ -115,6 +116,18 @@ static int launch_da_layers01(const genie_plan* plan, const float* packed, const
         if ((rc = launch_da_layer1_tc(plan, packed, w.tr0, mask, w.zc, w.va, w.vb, st))) return rc;
     }
     return launch_da_layer1(plan, packed, w.tr0, mask, w.zc, w.va, w.vb, tc, st);
+}
+
+// The same with a1 folded into layer 0 (genie_window_fwd): split plans only; the mask travels inside the feature rows.
+static int launch_da_layers01_window(const genie_plan* plan, const float* packed, const WindowParamSrc& ws,
+                                     const int32_t* ind_use, const float* trv, const float* series, float* slice_out,
+                                     float* mask_out, const Workspace& w, cudaStream_t st) {
+    int rc;
+    if ((rc = launch_da_init_fused(plan, packed, ws, ind_use, trv, series, slice_out, mask_out, w.tr0, true, st))) return rc;
+    const float* gate = packed + TC_BASE + TC_SCAL + TCS_OK;
+    if ((rc = launch_src_mean(plan, 32, w.tr0, w.msrc, gate, st))) return rc;
+    if ((rc = launch_da_layer1_s(plan, packed, w.tr0, w.msrc, nullptr, w.zc, w.va, w.vb, st))) return rc;
+    return launch_da_layer1(plan, packed, w.tr0, nullptr, w.zc, w.va, w.vb, true, st);
 }
 
 // Layer 2 of DataAggregation (+ Bipartite_ReadIn when `readin_out` is given) from zc / va / vb.
@@ -531,6 +544,46 @@ int genie_spatial_aggregation_fwd(const genie_plan_t* plan, const float* packed_
     Workspace w = carve_workspace(plan, workspace_dev);
     return launch_spatial_aggregation(plan, packed_dev, layer, x_dev, layer == 0 ? 15 : 30, pos_dev, scale_rel, w.px,
                                       w.partial, out_dev, 30, static_cast<cudaStream_t>(stream));
+}
+
+int genie_window_fwd(const genie_plan_t* plan, const float* packed_dev, const genie_window_params_t* wp_dev,
+                     int64_t max_window_picks, int32_t n_extra, const double* picks_dev, const int32_t* sta_perm_dev,
+                     const int32_t* ind_use_dev, const float* trv_times_dev, float* series_dev, int32_t n_ts_max,
+                     const float* edge_attr_dev, const float* pos_dev, float scale_rel, float* slice_out_dev,
+                     float* mask_out_dev, float* x_latent_out_dev, float* readin_out_dev, float* x_spatial_out_dev,
+                     void* workspace_dev, void* stream) {
+    if (!plan || !packed_dev || !wp_dev || !sta_perm_dev || !ind_use_dev || !trv_times_dev || !series_dev || !edge_attr_dev ||
+        !pos_dev || !x_spatial_out_dev || !workspace_dev || (max_window_picks > 0 && !picks_dev) || max_window_picks < 0 ||
+        n_extra < 0 || n_ts_max < 2 || ((slice_out_dev == nullptr) != (mask_out_dev == nullptr))) {
+        set_error("genie_window_fwd: bad argument");
+        return GENIE_ERR_INVALID;
+    }
+    if (!split_supported(plan) || plan->g.n_sta_tiles > 32 || plan->g.n_prod >= (int64_t)0x7fffffff) {
+        set_error("genie_window_fwd: needs a CARTESIAN plan with tiling tables (use genie_input_scatter_fwd + genie_frontend_fwd)");
+        return GENIE_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Workspace w = carve_workspace(plan, workspace_dev);
+    WindowParamSrc ws;
+    ws.host = genie_input_params_t();
+    ws.dev = wp_dev;
+    ws.n_picks = 0;
+    int rc;
+    if ((rc = launch_input_series(ws, max_window_picks, picks_dev, sta_perm_dev, series_dev,
+                                  (size_t)2 * plan->g.n_sta * n_ts_max * sizeof(float), n_extra, st)))
+        return rc;
+    if ((rc = launch_da_layers01_window(plan, packed_dev, ws, ind_use_dev, trv_times_dev, series_dev, slice_out_dev,
+                                        mask_out_dev, w, st)))
+        return rc;
+    float* r = readin_out_dev ? readin_out_dev : w.r;
+    const int ld_r = readin_out_dev ? 15 : 16;
+    if ((rc = launch_da_layer2(plan, packed_dev, w, nullptr, edge_attr_dev, x_latent_out_dev, r, ld_r, st))) return rc;
+    if ((rc = launch_spatial_aggregation(plan, packed_dev, 0, r, ld_r, pos_dev, scale_rel, w.px, w.partial, w.sa_a, 32, st)))
+        return rc;
+    if ((rc = launch_spatial_aggregation(plan, packed_dev, 1, w.sa_a, 32, pos_dev, scale_rel, w.px, w.partial, w.sa_b, 32, st)))
+        return rc;
+    return launch_spatial_aggregation(plan, packed_dev, 2, w.sa_b, 32, pos_dev, scale_rel, w.px, w.partial, x_spatial_out_dev,
+                                      30, st);
 }
 
 int genie_frontend_fwd(const genie_plan_t* plan, const float* packed_dev, const float* slice_dev,

@@ -16,6 +16,7 @@
 // broadcast from shared memory.
 #include "common.cuh"
 #include "gather.cuh"
+#include "input.cuh"
 
 using namespace gl;
 
@@ -32,11 +33,25 @@ constexpr int K1_THREADS = 256;
 // refreshed from the packed weights by a stream-ordered device-to-device copy before every launch.
 __constant__ float c_init_slots[GENIE_CSLOTS][8 * LD + LD];     // one slot per plan (genie_plan::cslot)
 
-template <int CSLOT>
-__global__ void __launch_bounds__(K1_THREADS) da_init_kernel(const float* __restrict__ packed,
-                                                             const float* __restrict__ slice,
-                                                             const float* __restrict__ mask, float* __restrict__ tr0,
-                                                             int64_t P, int tc_plan, const float* __restrict__ init_sta,
+// FUSED: a1 is folded in (genie_window_fwd) — the thread computes its node's Slice / Mask row from the per-station series and
+// the travel-time table (input.cuh, the arithmetic of input_gather_kernel) instead of loading it; the rows reach HBM only
+// when the caller asks for copies.  The four mask values ride in padding channel 30 of the stored row (pack_mask): the
+// station-pass kernels take the mask from the rows they stage anyway.
+struct InitInputs {
+    const float* slice;          // !FUSED: [P,4]
+    const float* mask;           // !FUSED: [P,4]
+    WindowParamSrc ws;           // FUSED
+    const int32_t* ind_use;      // FUSED: used station -> absolute station
+    const float* trv;            // FUSED: [G, n_locs, 2]
+    const float* series;         // FUSED: [S][n_ts][2]
+    float* slice_out;            // FUSED, optional
+    float* mask_out;             // FUSED, optional
+};
+
+template <int CSLOT, bool FUSED>
+__global__ void __launch_bounds__(K1_THREADS) da_init_kernel(const float* __restrict__ packed, const InitInputs in,
+                                                             float* __restrict__ tr0, int64_t P, int tc_plan,
+                                                             const float* __restrict__ init_sta,
                                                              const float* __restrict__ init_src, int S) {
     __shared__ __align__(16) float sOut[K1_THREADS * LD_TR0];
     const float* c_init = c_init_slots[CSLOT];       // compile-time slot: the weights stay immediate constant-bank operands
@@ -51,18 +66,22 @@ __global__ void __launch_bounds__(K1_THREADS) da_init_kernel(const float* __rest
     f32x2_t acc2[15];
 #pragma unroll
     for (int o = 0; o < 15; ++o) acc2[o] = pack2(c_init[8 * LD + 2 * o], c_init[8 * LD + 2 * o + 1]);
+    uint32_t g32 = 0, s32 = 0;
+    if ((FUSED || init_src != nullptr) && i < P) {           // 32-bit division (P < 2^31 is checked by the launcher)
+        g32 = (uint32_t)i / (uint32_t)S;
+        s32 = (uint32_t)i - g32 * (uint32_t)S;
+    }
     if (init_sta != nullptr && i < P) {
         // use_absolute_pos (module.py:913-914): the six position channels of init_trns, by linearity a per-station plus a
         // per-grid-node term (CARTESIAN) or one per-node term (EXPLICIT) added before the activation
-        const int64_t g = init_src != nullptr ? i / S : 0;
-        const float2* ts = reinterpret_cast<const float2*>(init_sta + (init_src != nullptr ? i - g * S : i) * 32);
+        const float2* ts = reinterpret_cast<const float2*>(init_sta + (init_src != nullptr ? (int64_t)s32 : i) * 32);
 #pragma unroll
         for (int o = 0; o < 15; ++o) {
             const float2 v = __ldg(ts + o);
             fadd2(acc2[o], pack2(v.x, v.y));
         }
         if (init_src != nullptr) {
-            const float2* tg = reinterpret_cast<const float2*>(init_src + g * 32);
+            const float2* tg = reinterpret_cast<const float2*>(init_src + (int64_t)g32 * 32);
 #pragma unroll
             for (int o = 0; o < 15; ++o) {
                 const float2 v = __ldg(tg + o);
@@ -70,14 +89,32 @@ __global__ void __launch_bounds__(K1_THREADS) da_init_kernel(const float* __rest
             }
         }
     }
+    float mpack = 0.f;
     if (i < P) {
-        const float4 sv = __ldcs(reinterpret_cast<const float4*>(slice) + i);
-        const float4 mv = __ldg(reinterpret_cast<const float4*>(mask) + i);
-        const float in[8] = {sv.x, sv.y, sv.z, sv.w, mv.x, mv.y, mv.z, mv.w};
+        float4 sv, mv;
+        if (FUSED) {
+            int64_t lo, hi;
+            const genie_input_params_t prm = load_params(in.ws, lo, hi);
+            const int sta_abs = __ldg(in.ind_use + s32);
+            const float2 tt = __ldg(reinterpret_cast<const float2*>(in.trv + ((int64_t)g32 * prm.n_locs + sta_abs) * 2));
+            long long bp, bs;
+            sv = input_slice_row(prm, (int)s32, tt, in.series, bp, bs);
+            mv = input_mask_row(sv);
+            if (in.slice_out != nullptr) {
+                __stcs(reinterpret_cast<float4*>(in.slice_out) + i, sv);
+                __stcs(reinterpret_cast<float4*>(in.mask_out) + i, mv);
+            }
+        } else {
+            sv = __ldcs(reinterpret_cast<const float4*>(in.slice) + i);
+            mv = __ldg(reinterpret_cast<const float4*>(in.mask) + i);
+        }
+        mpack = pack_mask(make_float4(mv.x != 0.f ? 1.f : 0.f, mv.y != 0.f ? 1.f : 0.f, mv.z != 0.f ? 1.f : 0.f,
+                                      mv.w != 0.f ? 1.f : 0.f));
+        const float inp[8] = {sv.x, sv.y, sv.z, sv.w, mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
 #pragma unroll
-            for (int o = 0; o < 15; ++o) ffma2(acc2[o], in[k], c_init[k * LD + 2 * o], c_init[k * LD + 2 * o + 1]);
+            for (int o = 0; o < 15; ++o) ffma2(acc2[o], inp[k], c_init[k * LD + 2 * o], c_init[k * LD + 2 * o + 1]);
         }
     }
     float acc[30];
@@ -91,7 +128,7 @@ __global__ void __launch_bounds__(K1_THREADS) da_init_kernel(const float* __rest
         float4 v;
         v.x = prelu(prelu(acc[(4 * c + 0) < 30 ? (4 * c + 0) : 0], a0), a12);
         v.y = prelu(prelu(acc[(4 * c + 1) < 30 ? (4 * c + 1) : 0], a0), a12);
-        v.z = (4 * c + 2) < 30 ? prelu(prelu(acc[(4 * c + 2) < 30 ? (4 * c + 2) : 0], a0), a12) : 0.f;
+        v.z = (4 * c + 2) < 30 ? prelu(prelu(acc[(4 * c + 2) < 30 ? (4 * c + 2) : 0], a0), a12) : mpack;   // channel 30
         v.w = (4 * c + 3) < 30 ? prelu(prelu(acc[(4 * c + 3) < 30 ? (4 * c + 3) : 0], a0), a12) : 0.f;
         srow[c ^ (n & 7)] = v;
     }
@@ -145,7 +182,8 @@ __global__ void __launch_bounds__(K2_THREADS, 2)
                 own = tr0[i * LD_TR0 + lane];
                 m1 = gather_mean32(tr0, rs, gv.sta_col, a11, lane);
                 m2 = gather_mean32(tr0, rg, gv.src_col, a12, lane);
-                if (lane < 4) mk = mask[i * 4 + lane];
+                if (lane < 4)     // mask == NULL (a1 fused into layer 0): the four values ride bit-packed in channel 30 of the row
+                    mk = mask != nullptr ? mask[i * 4 + lane] : (float)(((int)tr0[i * LD_TR0 + 30] >> lane) & 1);
             }
             if (lane < 30) {
                 F[lane * LDF + m] = own;
@@ -217,6 +255,9 @@ __global__ void __launch_bounds__(K2_THREADS, 2)
             for (int k = 0; k < 60; ++k) fma_row16(c, F[k * LDF + n], Wc + k * LD16);
 #pragma unroll
             for (int k = 0; k < 4; ++k) fma_row16(c, F[(90 + k) * LDF + n], Wc + (60 + k) * LD16);
+            // padding channel 15 of zc carries max_c(mask) for the read-in of the split layer-2 kernel (da_s2_kernel.cu)
+            if (br == 0)
+                c[15] = fmaxf(fmaxf(F[90 * LDF + n], F[91 * LDF + n]), fmaxf(F[92 * LDF + n], F[93 * LDF + n]));
             const int64_t i = i0 + n;
             if (i < gv.P) {
                 float4* zp = reinterpret_cast<float4*>(zc + i * LD_ZC + br * 16);
@@ -364,8 +405,9 @@ __global__ void __launch_bounds__(128) readin_finalize_kernel(const float* __res
 // --------------------------------------------------------------------------------------------------------------------
 // launchers
 // --------------------------------------------------------------------------------------------------------------------
-int launch_da_init(const genie_plan* p, const float* packed, const float* slice, const float* mask, float* tr0,
-                   bool tc_plan, cudaStream_t st) {
+template <bool FUSED>
+static int launch_da_init_t(const genie_plan* p, const float* packed, const InitInputs& in, float* tr0, bool tc_plan,
+                            cudaStream_t st) {
     const int64_t P = p->g.n_prod;
     if (P == 0) return GENIE_OK;
     const int64_t blocks = (P + K1_THREADS - 1) / K1_THREADS;
@@ -374,8 +416,8 @@ int launch_da_init(const genie_plan* p, const float* packed, const float* slice,
     TimedLaunch tl(KID_DA_INIT, st);
 #define GENIE_INIT_CASE(C)                                                                                          \
     case C:                                                                                                         \
-        da_init_kernel<C><<<(unsigned)blocks, K1_THREADS, 0, st>>>(packed, slice, mask, tr0, P, tc_plan ? 1 : 0,    \
-                                                                   p->init_sta, p->init_src, p->g.n_sta);           \
+        da_init_kernel<C, FUSED><<<(unsigned)blocks, K1_THREADS, 0, st>>>(packed, in, tr0, P, tc_plan ? 1 : 0,      \
+                                                                          p->init_sta, p->init_src, p->g.n_sta);    \
         break;
     switch (p->cslot) {
         GENIE_INIT_CASE(0) GENIE_INIT_CASE(1) GENIE_INIT_CASE(2) GENIE_INIT_CASE(3)
@@ -384,6 +426,32 @@ int launch_da_init(const genie_plan* p, const float* packed, const float* slice,
 #undef GENIE_INIT_CASE
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;
+}
+
+int launch_da_init(const genie_plan* p, const float* packed, const float* slice, const float* mask, float* tr0,
+                   bool tc_plan, cudaStream_t st) {
+    InitInputs in = {};
+    in.slice = slice;
+    in.mask = mask;
+    return launch_da_init_t<false>(p, packed, in, tr0, tc_plan, st);
+}
+
+// a1 fused into layer 0 (genie_window_fwd): CARTESIAN plans with P < 2^31.
+int launch_da_init_fused(const genie_plan* p, const float* packed, const WindowParamSrc& ws, const int32_t* ind_use,
+                         const float* trv, const float* series, float* slice_out, float* mask_out, float* tr0,
+                         bool tc_plan, cudaStream_t st) {
+    if (p->g.mode != GENIE_GRAPH_CARTESIAN || p->g.n_prod >= (int64_t)0x7fffffff) {
+        set_error("launch_da_init_fused: needs a CARTESIAN plan with fewer than 2^31 product nodes");
+        return GENIE_ERR_UNSUPPORTED;
+    }
+    InitInputs in = {};
+    in.ws = ws;
+    in.ind_use = ind_use;
+    in.trv = trv;
+    in.series = series;
+    in.slice_out = slice_out;
+    in.mask_out = slice_out ? mask_out : nullptr;
+    return launch_da_init_t<true>(p, packed, in, tr0, tc_plan, st);
 }
 
 int launch_da_layer1(const genie_plan* p, const float* packed, const float* tr0, const float* mask, float* zc, float* va,

@@ -7,9 +7,11 @@
 // The CTA runs TWO tile pipelines (even / odd tiles) that share the producers and the weights in shared memory; a pipeline
 // owns one shared-memory buffer, 256 tensor-memory columns, a gather warpgroup, an epilogue warpgroup and an MMA-issuing
 // warp, so the gather of one tile, the tensor-core chain of another and the epilogues overlap:
-//     * producer warps stage, with cp.async, the p rows of the tile's stations AND of the halo of their station-graph
-//       in-neighbours (<= 288 rows x 128 B, table genie_graph_desc_t.sta_tile_rows), the tile's msrc rows and its mask
-//       rows, and convert the staged p rows in place to PReLU11(tr0) (each thread converts the chunks it copied itself);
+//     * producer warps stage the p rows of the tile's stations AND of the halo of their station-graph in-neighbours
+//       (<= 288 rows x 128 B, table genie_graph_desc_t.sta_tile_rows) as PReLU11(tr0): the rows pass through registers
+//       (LDG -> convert -> STS; per 512 bytes the same LSU work as a cp.async, and the conversion no longer is a serial
+//       phase between fill and gather), the tile's msrc rows and its mask rows go by cp.async.  `mask` == NULL: the four
+//       mask values ride bit-packed in channel 30 of the p rows (a1 fused into layer 0, genie_window_fwd);
 //     * the gather warpgroup (thread per row) sums the <= 16 neighbour rows of its station out of shared memory (16-byte
 //       chunks are visited in a per-lane rotated order, so arbitrary rows are bank-conflict free), recovers tr0 of its
 //       own row, and writes the three 32-column A operands  [tr0 | mask0,1], [mean_sta | mask2,3], [mean_src | mask2,3]
@@ -25,6 +27,7 @@
 // DRAM sees p, msrc and mask once (the tiles of one grid node are consecutive, its 128 KB block stays in L2); nothing is
 // gathered from L2.  All hand-offs are mbarriers with bounded spins (a protocol bug traps, it never hangs).
 #include "common.cuh"
+#include "input.cuh"
 #include "tc_common.cuh"
 #include <cstdlib>
 
@@ -39,6 +42,7 @@ constexpr int WG_G0 = 4, WG_E0 = 12, WG_P0 = 20;     // gather (2 x 4 warps) / e
 constexpr int ROWS = GENIE_TILE_ROWS_MAX;            // staged p rows per tile; row ROWS is the zero row
 constexpr int NPIPE = 2;
 constexpr int P_THREADS = 64;                        // producer threads per pipeline (two warps)
+constexpr int S1_STAGGER_DEFAULT = 0;
 
 // shared memory map (bytes)
 constexpr int SB_P = 0;                              // [ROWS + 1][128 B]   staged rows (tile stations first, then halo)
@@ -68,7 +72,6 @@ struct Bars {
     uint64_t full[NPIPE], empty[NPIPE];
     uint64_t opA_full[NPIPE], opA_free[NPIPE];
     uint64_t d_full[NPIPE], aE_full[NPIPE], d_free[NPIPE];
-    uint64_t raw[NPIPE];           // copies landed (producers -> gather warpgroup, which converts the rows in place)
     uint32_t tmem_base;
 };
 static_assert(sizeof(Bars) <= 256, "barrier block");
@@ -147,10 +150,18 @@ __device__ __forceinline__ void store16_rows(const float (&v)[16], unsigned char
 
 // Epilogue-warpgroup half of the stage-B operands of one tile: [tr0 | mask0,1] (tr0 recovered from the staged PReLU11(tr0)
 // of the thread's own row) and [mean_src | mask2,3] (the thread's msrc row) -> tensor memory.  Returns the row's mask.
-__device__ __forceinline__ float4 s1_own_operands(const unsigned char* sb, int r, bool valid, int key, float inv11,
-                                                  uint32_t lane_base) {
+__device__ __forceinline__ float4 s1_load_mask(const unsigned char* sb, int r, bool valid, bool packed) {
     float4 mk = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) mk = *reinterpret_cast<const float4*>(sb + SB_MK + r * 16);
+    if (valid) {
+        if (packed) mk = unpack_mask(*reinterpret_cast<const float*>(sb + SB_MK + r * 4));
+        else mk = *reinterpret_cast<const float4*>(sb + SB_MK + r * 16);
+    }
+    return mk;
+}
+
+__device__ __forceinline__ float4 s1_own_operands(const unsigned char* sb, int r, bool valid, int key, float inv11,
+                                                  uint32_t lane_base, bool packed) {
+    const float4 mk = s1_load_mask(sb, r, valid, packed);
     float a[16];
     {
         float4 own[8];
@@ -204,8 +215,10 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                        float* __restrict__ vb, int S, int NT, const int32_t* __restrict__ tile_rows,
                        const int32_t* __restrict__ tile_meta, const uint16_t* __restrict__ tile_nbr,
                        const float* __restrict__ tile_invdeg, int64_t n_tiles, const float* __restrict__ edge_sta,
-                       const float* __restrict__ edge_src, long long* __restrict__ trace, int trace_tiles, int trace_start) {
+                       const float* __restrict__ edge_src, long long* __restrict__ trace, int trace_tiles, int trace_start,
+                       int stagger) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    const bool packed_mask = mask == nullptr;
     const float* tcw = packed + T2_BASE;
     if (tcw[T2_SCAL + TCS_OK] == 0.f) return;   // slopes not eligible: the generic kernels run instead (uniform exit)
 
@@ -227,14 +240,13 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
     }
     if (threadIdx.x == 0) {
         for (int b = 0; b < NPIPE; ++b) {
-            mbar_init(&bars->full[b], 128);           // gather warpgroup, after the in-place conversion
+            mbar_init(&bars->full[b], P_THREADS);     // producers: rows staged (and converted)
             mbar_init(&bars->empty[b], 256);          // gather + epilogue warpgroups
             mbar_init(&bars->opA_full[b], 256);
             mbar_init(&bars->opA_free[b], 1);
             mbar_init(&bars->d_full[b], 1);
             mbar_init(&bars->aE_full[b], 128);
             mbar_init(&bars->d_free[b], 128);
-            mbar_init(&bars->raw[b], P_THREADS);
         }
         fence_barrier_init();
     }
@@ -250,41 +262,64 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
     const float* sc = sW + T2_SCAL;
 
     if (warp >= WG_P0) {
-        // ================================ producers of pipeline q: cp.async row gather =================================
-        // Thread `tid` owns the 16-byte chunk c = tid & 7 of the staged rows rr + 8 j (rr = tid >> 3).  The staged p rows
-        // are only ever read as PReLU11(tr0): the (otherwise waiting) gather warpgroup converts them in place once the
-        // copies have landed.
+        // ================================ producers of pipeline q: row gather ==========================================
+        // Thread `tid` owns the 16-byte chunk c = tid & 7 of the staged rows rr + 8 j (rr = tid >> 3).  msrc / mask rows go by
+        // cp.async; the p rows pass through registers and are stored as PReLU11(tr0) (they are only ever read in that form).
         const int q = (warp - WG_P0) >> 1;
         const int tid = threadIdx.x - (WG_P0 + 2 * q) * 32;
         const int rr = tid >> 3, c = tid & 7;
         constexpr int JMAX = (ROWS + 7) / 8;
+        constexpr int PB = 12;                         // p chunks in flight per thread
+        static_assert(JMAX % PB == 0, "p-row batches");
+        const float r11 = sc[TCS_R11];
         unsigned char* sbp = smem + SM_BUF + q * SB_SIZE;
         const uint32_t sb = smem_u32(sbp);
+        if (q == 1 && stagger > 0) {                   // start the second pipeline out of phase with the first
+            const long long t_go = clock64() + stagger;
+            while (clock64() < t_go) {}
+        }
         int64_t k = 0;
         for (int64_t t = blockIdx.x + (int64_t)q * gridDim.x; t < n_tiles; t += 2 * (int64_t)gridDim.x, ++k) {
             const int g = (int)(t / NT), T = (int)(t - (int64_t)g * NT);
             const int n_own = __ldg(tile_meta + 2 * T), n_rows = __ldg(tile_meta + 2 * T + 1);
             const int32_t* rows = tile_rows + (int64_t)T * ROWS;
-            int ids[JMAX];
-#pragma unroll
-            for (int j = 0; j < JMAX; ++j) ids[j] = (rr + 8 * j) < n_rows ? __ldg(rows + rr + 8 * j) : -1;
-            const int id_m0 = tid < n_own ? __ldg(rows + tid) : -1;
-            const int id_m1 = tid + 64 < n_own ? __ldg(rows + tid + 64) : -1;
+            // (the station-id table of the 8 tile types is a few KB and L1-resident: ids are fetched batch by batch)
             if (k > 0) mbar_wait(&bars->empty[q], (uint32_t)((k - 1) & 1));
             if (tid == 0) S1_TRACE(17);
-            const int64_t node0 = (int64_t)g * S;
-#pragma unroll
-            for (int j = 0; j < JMAX; ++j)
-                if (ids[j] >= 0) cp_async16(sb + SB_P + (rr + 8 * j) * 128 + c * 16, p + (node0 + ids[j]) * 32 + c * 4);
+            const float4* pg = reinterpret_cast<const float4*>(p + (int64_t)g * S * 32);
+            const float4* mg = reinterpret_cast<const float4*>(msrc + (int64_t)g * S * 32);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int r = rr + 8 * j;
-                if (r < n_own) cp_async16(sb + SB_MS + r * 128 + ((c ^ (r & 7)) << 4), msrc + (node0 + ids[j]) * 32 + c * 4);
+                if (r < n_own) cp_async16(sb + SB_MS + r * 128 + ((c ^ (r & 7)) << 4), mg + (__ldg(rows + r) * 8 + c));
             }
-            if (id_m0 >= 0) cp_async16(sb + SB_MK + tid * 16, mask + (node0 + id_m0) * 4);
-            if (id_m1 >= 0) cp_async16(sb + SB_MK + (tid + 64) * 16, mask + (node0 + id_m1) * 4);
+            if (!packed_mask) {
+                const float4* kg = reinterpret_cast<const float4*>(mask + (int64_t)g * S * 4);
+                if (tid < n_own) cp_async16(sb + SB_MK + tid * 16, kg + __ldg(rows + tid));
+                if (tid + 64 < n_own) cp_async16(sb + SB_MK + (tid + 64) * 16, kg + __ldg(rows + tid + 64));
+            }
+#pragma unroll 1
+            for (int j0 = 0; j0 < JMAX; j0 += PB) {
+                if (rr + 8 * j0 >= n_rows) break;
+                float4 v[PB];
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    const int r = rr + 8 * (j0 + u);
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < n_rows) v[u] = __ldcg(pg + (__ldg(rows + r) * 8 + c));
+                }
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    const int r = rr + 8 * (j0 + u);
+                    if (r < n_rows) {
+                        if (packed_mask && c == 7 && r < n_own) *reinterpret_cast<float*>(sbp + SB_MK + r * 4) = v[u].z;
+                        *reinterpret_cast<float4*>(sbp + SB_P + r * 128 + c * 16) = make_float4(
+                            prelu_f(v[u].x, r11), prelu_f(v[u].y, r11), prelu_f(v[u].z, r11), prelu_f(v[u].w, r11));
+                    }
+                }
+            }
             asm volatile("cp.async.wait_all;" ::: "memory");
-            mbar_arrive(&bars->raw[q]);
+            mbar_arrive(&bars->full[q]);
             if (tid == 0) S1_TRACE(18);
         }
     } else if (warp < NPIPE) {
@@ -373,7 +408,6 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
         const int r = ((warp - WG_G0) & 3) * 32 + lane;
         const uint32_t lane_base = tm + q * TM_PIPE + ((uint32_t)((warp & 3) * 32) << 16);
         const int key = lane & 7;
-        const float r11 = sc[TCS_R11];
         unsigned char* sb = smem + SM_BUF + q * SB_SIZE;
         int64_t k = 0;
         for (int64_t t = blockIdx.x + (int64_t)q * gridDim.x; t < n_tiles; t += 2 * (int64_t)gridDim.x, ++k) {
@@ -383,28 +417,6 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
             const uint4* nb = reinterpret_cast<const uint4*>(tile_nbr + ((int64_t)T * 128 + r) * 16);
             const uint4 n0 = __ldg(nb), n1 = __ldg(nb + 1);
             const float invdeg = __ldg(tile_invdeg + T * 128 + r);
-            // ---- staged p rows -> PReLU11(tr0), in place: 16-byte chunk r & 7 of the rows (r >> 3) + 16 j, in batches whose
-            //      loads are all in flight before the first store ----------------------------------------------------------
-            mbar_wait(&bars->raw[q], (uint32_t)(k & 1));
-            {
-                const int n_rows = __ldg(tile_meta + 2 * T + 1);
-                unsigned char* cb = sb + SB_P + (r >> 3) * 128 + (r & 7) * 16;
-                constexpr int CB = 9;
-                static_assert((ROWS + 15) / 16 == 2 * CB, "conversion batches");
-#pragma unroll
-                for (int j0 = 0; j0 < 2 * CB; j0 += CB) {
-                    if ((r >> 3) + 16 * j0 >= n_rows) break;
-                    float4 v[CB];
-#pragma unroll
-                    for (int u = 0; u < CB; ++u) v[u] = *reinterpret_cast<const float4*>(cb + (j0 + u) * 16 * 128);
-#pragma unroll
-                    for (int u = 0; u < CB; ++u)
-                        if ((r >> 3) + 16 * (j0 + u) < n_rows)
-                            *reinterpret_cast<float4*>(cb + (j0 + u) * 16 * 128) = make_float4(
-                                prelu_f(v[u].x, r11), prelu_f(v[u].y, r11), prelu_f(v[u].z, r11), prelu_f(v[u].w, r11));
-                }
-            }
-            mbar_arrive(&bars->full[q]);
             mbar_wait(&bars->full[q], (uint32_t)(k & 1));
             if (r == 0) S1_TRACE(12);
             // ---- sum of the station neighbours' rows (16-byte chunk k ^ key of every row: conflict free) ------------------
@@ -426,8 +438,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
             }
             unrotate8(acc, key);
             const bool valid = r < n_own;
-            float4 mk = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) mk = *reinterpret_cast<const float4*>(sb + SB_MK + r * 16);
+            const float4 mk = s1_load_mask(sb, r, valid, packed_mask);
             mbar_arrive(&bars->empty[q]);            // release (gather half): every shared-memory read of this tile is done
             // ---- A operand -> tensor memory (free once stage D of the pipeline's previous tile has completed) ---------------
             if (r == 0) S1_TRACE(14);
@@ -478,7 +489,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                 const int g = (int)(t / NT), T = (int)(t - (int64_t)g * NT);
                 valid = r < __ldg(tile_meta + 2 * T);
                 mbar_wait(&bars->full[q], 0u);
-                mk = s1_own_operands(sb, r, valid, key, inv11, lane_base);
+                mk = s1_own_operands(sb, r, valid, key, inv11, lane_base, packed_mask);
                 mbar_arrive(&bars->empty[q]);
                 tmem_st_wait();
                 tc_fence_before_sync();
@@ -569,6 +580,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                         v[4 * u] += e.x; v[4 * u + 1] += e.y; v[4 * u + 2] += e.z; v[4 * u + 3] += e.w;
                     }
                 }
+                if (c == 0) v[15] = fmaxf(fmaxf(mk.x, mk.y), fmaxf(mk.z, mk.w));     // padding channel 15: max_c(mask) for layer 2's read-in
                 store16_rows(v, scr, lane, sid, zc + c, node0, LD_ZC);
             }
             tmem_st_wait();
@@ -596,7 +608,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                 const int g2 = (int)(t2 / NT), T2 = (int)(t2 - (int64_t)g2 * NT);
                 valid = r < __ldg(tile_meta + 2 * T2);
                 mbar_wait(&bars->full[q], (uint32_t)((k + 1) & 1));
-                mk = s1_own_operands(sb, r, valid, key, inv11, lane_base);
+                mk = s1_own_operands(sb, r, valid, key, inv11, lane_base, packed_mask);
                 mbar_arrive(&bars->empty[q]);
                 tmem_st_wait();
                 tc_fence_before_sync();
@@ -633,15 +645,17 @@ int launch_da_layer1_s(const genie_plan* p, const float* packed, const float* pf
         attr_set.mark();
     }
     const int64_t grid = n_tiles < p->sm_count ? n_tiles : p->sm_count;
+    // initial phase offset (cycles) of the second tile pipeline; GENIE_S1_STAGGER overrides (development sweeps)
+    static const int stagger = [] { const char* e = getenv("GENIE_S1_STAGGER"); return e ? atoi(e) : S1_STAGGER_DEFAULT; }();
     TimedLaunch tl(KID_DA_LAYER1_S, st);
     if (p->edge_sta != nullptr)
         da_layer1_s_kernel<true><<<(unsigned)grid, S1_THREADS, SM_TOTAL, st>>>(
             packed, pfeat, msrc, mask, zc, va, vb, g.n_sta, g.n_sta_tiles, g.sta_tile_rows, g.sta_tile_meta, g.sta_tile_nbr,
-            g.sta_tile_invdeg, n_tiles, p->edge_sta, p->edge_src, g_s1_trace, g_s1_trace_tiles, g_s1_trace_start);
+            g.sta_tile_invdeg, n_tiles, p->edge_sta, p->edge_src, g_s1_trace, g_s1_trace_tiles, g_s1_trace_start, stagger);
     else
         da_layer1_s_kernel<false><<<(unsigned)grid, S1_THREADS, SM_TOTAL, st>>>(
             packed, pfeat, msrc, mask, zc, va, vb, g.n_sta, g.n_sta_tiles, g.sta_tile_rows, g.sta_tile_meta, g.sta_tile_nbr,
-            g.sta_tile_invdeg, n_tiles, nullptr, nullptr, g_s1_trace, g_s1_trace_tiles, g_s1_trace_start);
+            g.sta_tile_invdeg, n_tiles, nullptr, nullptr, g_s1_trace, g_s1_trace_tiles, g_s1_trace_start, stagger);
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;
 }

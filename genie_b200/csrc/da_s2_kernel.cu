@@ -3,7 +3,8 @@
 // Reference: module.py:94-98 (second aggregation of DataAggregation) and module.py:224-229 (Bipartite_ReadIn):
 //   x_latent = PReLU2([c_a + mean_sta v_a | c_b + mean_src v_b])            (the 15-wide halves of l2_t*_2, split by linearity
 //                                                                           in layer 1: zc = [c_a 0 | c_b 0], va, vb)
-//   h        = max_c(mask) * PReLU(fc1 [x_latent | edge attr])              33 -> 30, per product node
+//   h        = max_c(mask) * PReLU(fc1 [x_latent | edge attr])              33 -> 30, per product node (max_c(mask) was
+//                                                                           left in padding channel 15 of zc by layer 1)
 //   out[g]   = PReLU(fc2 sum_{s} h[g,s])                                    sum over the stations of grid node g, 30 -> 15
 // mean_src v_b comes from the source pass (src_mean_kernels.cu, 16-float rows).  One tile = (grid node g, compact set of
 // <= 128 stations): producer warps stage the v_a rows of the tile and of its station halo (64 B each), the tile's zc rows
@@ -188,10 +189,8 @@ __global__ void __launch_bounds__(S2_THREADS, 1)
             const uint4* nb = reinterpret_cast<const uint4*>(tile_nbr + ((int64_t)T * 128 + r) * 16);
             const uint4 n0 = __ldg(nb), n1 = __ldg(nb + 1);
             const float invdeg = __ldg(tile_invdeg + T * 128 + r);
-            float4 mk = make_float4(0.f, 0.f, 0.f, 0.f);
             float e0 = 0.f, e1 = 0.f, e2 = 0.f;
             if (valid) {
-                mk = __ldg(reinterpret_cast<const float4*>(mask) + node);
                 e0 = __ldg(edge_attr + node * 3);
                 e1 = __ldg(edge_attr + node * 3 + 1);
                 e2 = __ldg(edge_attr + node * 3 + 2);
@@ -223,10 +222,12 @@ __global__ void __launch_bounds__(S2_THREADS, 1)
             }
             // ---- x_latent ----------------------------------------------------------------------------------------------------
             float x[32];
+            float zmask = 0.f;       // max_c(mask) of the node: layer 1 left it in padding channel 15 of the zc row
             if (valid) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const float4 za = *reinterpret_cast<const float4*>(sb + SB_ZC + r * 128 + ((c ^ (r & 7)) << 4));
+                    if (c == 3) zmask = za.w;
                     const float4 zb = *reinterpret_cast<const float4*>(sb + SB_ZC + r * 128 + (((c + 4) ^ (r & 7)) << 4));
                     const float4 mb = *reinterpret_cast<const float4*>(sb + SB_M2 + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
                     x[4 * c + 0] = prelu(za.x + acc[c].x * invdeg, a2);
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1)
                 float acc30[30];
 #pragma unroll
                 for (int o = 0; o < 15; ++o) unpack2(acc2[o], acc30[2 * o], acc30[2 * o + 1]);
-                const float mmax = valid ? fmaxf(fmaxf(mk.x, mk.y), fmaxf(mk.z, mk.w)) : 0.f;
+                const float mmax = valid ? zmask : 0.f;
 #pragma unroll
                 for (int o = 0; o < 30; ++o) h[o] = valid ? mmax * prelu(acc30[o], ri_a1) : 0.f;
                 h[30] = 0.f;

@@ -10,16 +10,21 @@
 //   promoted to fp64), reads {max(P,S) series at the P bin, max(P,S) at the S bin, P series at the P bin, S series at the
 //   S bin} (:605-608); first and last bin of every series read as zero (:565-568); Mask = |Slice| > 0.01 (:629).
 #include "common.cuh"
+#include "input.cuh"
 
 namespace {
 
-__global__ void input_series_kernel(const genie_input_params_t prm, const double* __restrict__ picks, int64_t n_picks,
+// One thread per (pick row of the window's range, bin offset).  The parameters and the pick range come by value or — for
+// a window captured in a CUDA graph — from the device block `ws.dev`; the grid is then sized for the largest window.
+__global__ void input_series_kernel(const WindowParamSrc ws, const double* __restrict__ picks,
                                     const int32_t* __restrict__ sta_perm, float* __restrict__ series) {
+    int64_t lo, hi;
+    const genie_input_params_t prm = load_params(ws, lo, hi);
     const int n_off = 2 * prm.n_extra + 1;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t p = tid / n_off;
-    if (p >= n_picks) return;
-    const int off = (int)(tid - p * n_off) - prm.n_extra;
+    const int64_t p = lo + tid / n_off;
+    if (p >= hi) return;
+    const int off = (int)(tid % n_off) - prm.n_extra;
     const double t = picks[p * 5 + 0];
     if (!((t > (prm.t0 - 2.0 * prm.kernel_sig_t)) && (t < (prm.t0 + prm.max_t + 2.0 * prm.kernel_sig_t)))) return;
     const long long sta_abs = (long long)picks[p * 5 + 1];
@@ -65,29 +70,10 @@ __global__ void input_gather_kernel(const genie_input_params_t prm, int mode, in
     }
     const int sta_abs = ind_use[s];
     const float2 tt = *reinterpret_cast<const float2*>(trv + ((int64_t)g * prm.n_locs + sta_abs) * 2);
-    const long long bp = (long long)__ddiv_rn(__dsub_rn(__dadd_rn((double)tt.x, prm.t0), prm.ref0), prm.dt);
-    const long long bs = (long long)__ddiv_rn(__dsub_rn(__dadd_rn((double)tt.y, prm.t0), prm.ref0), prm.dt);
-    const float2* sr = reinterpret_cast<const float2*>(series) + (int64_t)s * prm.n_ts;      // [bin] = (P series, S series)
-    const bool okp = bp > 0 && bp < (long long)prm.n_ts - 1;
-    const bool oks = bs > 0 && bs < (long long)prm.n_ts - 1;
-    const float2 at_p = okp ? __ldg(sr + bp) : make_float2(0.f, 0.f);
-    const float2 at_s = oks ? __ldg(sr + bs) : make_float2(0.f, 0.f);
-    const float pp = at_p.x;   // P series at the P bin
-    const float sp_ = at_p.y;  // S series at the P bin
-    const float ps = at_s.x;   // P series at the S bin
-    const float ss_ = at_s.y;  // S series at the S bin
-    float4 o;
-    o.x = fmaxf(pp, sp_);
-    o.y = fmaxf(ps, ss_);
-    o.z = pp;
-    o.w = ss_;
-    float4 m;
-    m.x = fabsf(o.x) > 0.01f ? 1.f : 0.f;
-    m.y = fabsf(o.y) > 0.01f ? 1.f : 0.f;
-    m.z = fabsf(o.z) > 0.01f ? 1.f : 0.f;
-    m.w = fabsf(o.w) > 0.01f ? 1.f : 0.f;
+    long long bp, bs;
+    const float4 o = input_slice_row(prm, s, tt, series, bp, bs);
     __stcs(reinterpret_cast<float4*>(slice_out) + i, o);     // read once, by the next kernel
-    reinterpret_cast<float4*>(mask_out)[i] = m;
+    reinterpret_cast<float4*>(mask_out)[i] = input_mask_row(o);
     if (time_bin_out != nullptr) {
         time_bin_out[i * 2 + 0] = bp;
         time_bin_out[i * 2 + 1] = bs;
@@ -154,20 +140,31 @@ int launch_input_nearest(const genie_nearest_params_t* prm, const double* t_all,
     return GENIE_OK;
 }
 
+int launch_input_series(const WindowParamSrc& ws, int64_t max_picks, const double* picks, const int32_t* sta_perm, float* series,
+                        size_t series_bytes, int n_extra, cudaStream_t st) {
+    GENIE_CUDA_CHECK(cudaMemsetAsync(series, 0, series_bytes, st));
+    if (max_picks > 0) {
+        const int64_t total = max_picks * (2 * (int64_t)n_extra + 1);
+        const int64_t blocks = (total + 255) / 256;
+        TimedLaunch tl(KID_INPUT_SERIES, st);
+        input_series_kernel<<<(unsigned)blocks, 256, 0, st>>>(ws, picks, sta_perm, series);
+        GENIE_LAUNCH_CHECK();
+    }
+    return GENIE_OK;
+}
+
 int launch_input_scatter(const genie_plan* p, const genie_input_params_t* prm, const double* picks, int64_t n_picks,
                          const int32_t* sta_perm, const int32_t* ind_use, const float* trv_times,
                          const int32_t* node_sta, const int32_t* node_grid, float* series, float* slice_out,
                          float* mask_out, int64_t* time_bin_out, cudaStream_t st) {
     const int64_t P = p->g.n_prod;
-    const size_t series_bytes = (size_t)2 * prm->n_sta_use * prm->n_ts * sizeof(float);
-    GENIE_CUDA_CHECK(cudaMemsetAsync(series, 0, series_bytes, st));
-    if (n_picks > 0) {
-        const int64_t total = n_picks * (2 * (int64_t)prm->n_extra + 1);
-        const int64_t blocks = (total + 255) / 256;
-        TimedLaunch tl(KID_INPUT_SERIES, st);
-        input_series_kernel<<<(unsigned)blocks, 256, 0, st>>>(*prm, picks, n_picks, sta_perm, series);
-        GENIE_LAUNCH_CHECK();
-    }
+    WindowParamSrc ws;
+    ws.host = *prm;
+    ws.dev = nullptr;
+    ws.n_picks = n_picks;
+    int rc = launch_input_series(ws, n_picks, picks, sta_perm, series, (size_t)2 * prm->n_sta_use * prm->n_ts * sizeof(float),
+                                 prm->n_extra, st);
+    if (rc) return rc;
     if (P > 0) {
         const int64_t blocks = (P + 255) / 256;
         TimedLaunch tl(KID_INPUT_GATHER, st);

@@ -161,6 +161,12 @@ int launch_pack_weights(const genie_frontend_weights_t* w, float* packed, cudaSt
 bool da_tc_supported(const genie_plan* p);
 int launch_da_init(const genie_plan* p, const float* packed, const float* slice, const float* mask, float* tr0,
                    bool tc_plan, cudaStream_t st);
+struct WindowParamSrc;
+int launch_da_init_fused(const genie_plan* p, const float* packed, const WindowParamSrc& ws, const int32_t* ind_use,
+                         const float* trv, const float* series, float* slice_out, float* mask_out, float* tr0,
+                         bool tc_plan, cudaStream_t st);
+int launch_input_series(const WindowParamSrc& ws, int64_t max_picks, const double* picks, const int32_t* sta_perm, float* series,
+                        size_t series_bytes, int n_extra, cudaStream_t st);
 int launch_da_layer1(const genie_plan* p, const float* packed, const float* tr0, const float* mask, float* zc, float* va,
                      float* vb, bool tc_plan, cudaStream_t st);
 int launch_da_layer1_tc(const genie_plan* p, const float* packed, const float* pfeat, const float* mask, float* zc,

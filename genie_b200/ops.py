@@ -468,7 +468,7 @@ def da_layer2_readin_fwd(plan, packed, Mask, edge_attr, want_latent=False):
 
 # ---- a1 ----------------------------------------------------------------------------------------------------------------
 
-def input_params(t0, max_t, kernel_sig_t, dt, n_locs, n_sta_use):
+def input_params(t0, max_t, kernel_sig_t, dt, n_locs, n_sta_use, use_sign_input=False):
     """The fp64 scalars the reference derives with numpy (process_utils.py:500-502, 520), by the same expressions."""
     t0, max_t, kernel_sig_t, dt = float(t0), float(max_t), float(kernel_sig_t), float(dt)
     t_offset = 3.0 * kernel_sig_t
@@ -481,6 +481,7 @@ def input_params(t0, max_t, kernel_sig_t, dt, n_locs, n_sta_use):
     prm.n_ts = int(math.ceil((stop - start) / dt))      # len(numpy.arange(start, stop, dt))
     prm.n_extra = int(np.ceil(3 * kernel_sig_t / dt))
     prm.n_locs, prm.n_sta_use = int(n_locs), int(n_sta_use)
+    prm.use_sign_input = 1 if use_sign_input else 0
     return prm
 
 
@@ -506,3 +507,25 @@ def input_scatter_fwd(plan, prm, picks, sta_perm, ind_use, trv_times, node_sta=N
             capi.dptr(node_grid, torch.int32, 'node_grid'), capi.dptr(series, F32), capi.dptr(Slice), capi.dptr(Mask),
             capi.dptr(tb), capi.stream_ptr(dev)))
     return Slice, Mask, tb, series
+
+
+def window_fwd(plan, packed, wp_dev, max_window_picks, n_extra, picks, sta_perm, ind_use, trv_times, series, n_ts_max,
+               edge_attr, pos, scale_rel, want_inputs=False, want_latent=False, want_readin=False, out=None):
+    """genie_window_fwd: a1 fused into the front end for one window whose parameters sit in the device block `wp_dev`
+    (uint8 CUDA tensor holding a capi.WindowParams).  Returns (x_spatial, latent, readin, Slice, Mask)."""
+    dev = plan.device
+    x_spatial = out if out is not None else torch.empty((plan.n_grid, 30), dtype=F32, device=dev)
+    latent = torch.empty((plan.n_prod, 30), dtype=F32, device=dev) if want_latent else None
+    readin = torch.empty((plan.n_grid, 15), dtype=F32, device=dev) if want_readin else None
+    Slice = torch.empty((plan.n_prod, 4), dtype=F32, device=dev) if want_inputs else None
+    Mask = torch.empty((plan.n_prod, 4), dtype=F32, device=dev) if want_inputs else None
+    with torch.cuda.device(dev):
+        capi.check(capi.load().genie_window_fwd(
+            plan.handle, capi.dptr(packed, F32), capi.dptr(wp_dev, torch.uint8, 'window params'), int(max_window_picks),
+            int(n_extra), capi.dptr(picks, torch.float64, 'picks') if max_window_picks else None,
+            capi.dptr(sta_perm, torch.int32, 'sta_perm'), capi.dptr(ind_use, torch.int32, 'ind_use'),
+            capi.dptr(trv_times, F32, 'trv_times'), capi.dptr(series, F32, 'series'), int(n_ts_max),
+            capi.dptr(edge_attr, F32, 'attr'), capi.dptr(pos, F32, 'pos'), ctypes.c_float(scale_rel), capi.dptr(Slice),
+            capi.dptr(Mask), capi.dptr(latent), capi.dptr(readin), capi.dptr(x_spatial), capi.dptr(plan.workspace()),
+            capi.stream_ptr(dev)))
+    return x_spatial, latent, readin, Slice, Mask

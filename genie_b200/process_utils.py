@@ -219,8 +219,10 @@ def product_edge_lists(A_sta_sta, A_src_src, n_sta, n_grid):
 class InputExtractor(object):
     """Device-resident state of `extract_input_from_data` for one (station set, source grid)."""
 
-    def __init__(self, plan, trv_times, ind_use, n_locs, max_t, kernel_sig_t, dt, node_sta=None, node_grid=None):
+    def __init__(self, plan, trv_times, ind_use, n_locs, max_t, kernel_sig_t, dt, node_sta=None, node_grid=None,
+                 use_sign_input=False):
         dev = plan.device
+        self.use_sign_input = bool(use_sign_input)
         self.plan, self.max_t, self.kernel_sig_t, self.dt = plan, float(max_t), float(kernel_sig_t), float(dt)
         self.n_locs = int(n_locs)
         ind_use = np.asarray(ind_use).astype('int')
@@ -238,7 +240,7 @@ class InputExtractor(object):
         self._day = None
 
     def params(self, t0):
-        return ops.input_params(t0, self.max_t, self.kernel_sig_t, self.dt, self.n_locs, self.n_sta_use)
+        return ops.input_params(t0, self.max_t, self.kernel_sig_t, self.dt, self.n_locs, self.n_sta_use, self.use_sign_input)
 
     def set_day(self, P):
         """Keep a whole pick table [n,5] (sorted by time here) resident on the device."""
@@ -379,17 +381,21 @@ def extract_input_from_data(trv_pairwise, P, t0, ind_use, locs, x_grid, A_src_in
                             kernel_sig_t=5.0, dt=0.2, batch_grids=False, use_asserts=True, verbose=False,
                             use_sign_input=False, return_embedding=False, device='cuda', plan=None):
     """Same call as process_utils.py:460; returns `[Inpts, Masks], [lp_times, lp_stations, lp_phases, lp_meta]` with
-    Inpts/Masks CUDA tensors.  `trv_times` ([G, n_locs, 2]) is required; per-(grid, station set) state is cached."""
-    if trv_times is None or use_sign_input or batch_grids or return_embedding:
-        raise NotImplementedError('genie_b200.extract_input_from_data: needs trv_times; use_sign_input, batch_grids '
-                                  'and return_embedding are not supported')
+    Inpts/Masks CUDA tensors.  `trv_times` is the [G, n_locs, 2] travel-time table; without it (:594-596) the table is
+    filled once from `trv_pairwise` for the pairs of `A_src_in_sta`.  `use_sign_input` (:610-614; the flag the
+    day-processing script passes, process_continuous_days.py:776) and `return_embedding` (:571-572) behave as in the
+    reference; `batch_grids` is 'Not implemented' there as well (:574-576).  Per-(grid, station set) state is cached."""
+    if batch_grids:
+        raise NotImplementedError('extract_input_from_data: batch_grids is not implemented (neither is it in the reference, '
+                                  'process_utils.py:574-576)')
     t0v = float(np.asarray(t0).reshape(-1)[0])
     ind_use = np.asarray(ind_use).astype('int')
     A = A_src_in_sta.cpu().numpy() if torch.is_tensor(A_src_in_sta) else np.asarray(A_src_in_sta)
     # One extractor is cached.  The key holds the station subset itself and the sizes; the entry keeps `trv_times` and
-    # `A_src_in_sta` referenced, so their id()s cannot be recycled by other objects while the entry lives.
-    key = (id(trv_times), id(A_src_in_sta), ind_use.tobytes(), int(locs.shape[0]), int(x_grid.shape[0]), float(max_t),
-           float(kernel_sig_t), float(dt), str(device), id(plan) if plan is not None else None)
+    # `A_src_in_sta` (and `trv_pairwise`) referenced, so their id()s cannot be recycled by other objects while the entry lives.
+    key = (id(trv_times) if trv_times is not None else ('pairwise', id(trv_pairwise)), id(A_src_in_sta), ind_use.tobytes(),
+           int(locs.shape[0]), int(x_grid.shape[0]), float(max_t), float(kernel_sig_t), float(dt), str(device),
+           id(plan) if plan is not None else None, bool(use_sign_input))
     ent = _extractors.get(key)
     if ent is None:
         G, S = int(x_grid.shape[0]), len(ind_use)
@@ -404,9 +410,18 @@ def extract_input_from_data(trv_pairwise, P, t0, ind_use, locs, x_grid, A_src_in
                 plan = GraphPlan.explicit(empty, empty, torch.from_numpy(A[1].astype(np.int64)), empty, A.shape[1], G,
                                           device=device)
         nodes = (None, None) if plan.mode == 0 else (A[0], A[1])
-        ex = InputExtractor(plan, trv_times, ind_use, locs.shape[0], max_t, kernel_sig_t, dt, nodes[0], nodes[1])
+        table = trv_times
+        if table is None:
+            # :594-596: travel times of exactly the (station, source) pairs of A_src_in_sta from the caller's calculator
+            dev = torch.device(device)
+            tt = trv_pairwise(torch.Tensor(locs[ind_use]).to(dev)[torch.from_numpy(A[0]).to(dev)],
+                              torch.Tensor(x_grid).to(dev)[torch.from_numpy(A[1]).to(dev)]).detach().float()
+            table = torch.zeros((G, int(locs.shape[0]), 2), dtype=torch.float32, device=tt.device)
+            table[torch.from_numpy(A[1]).to(tt.device), torch.from_numpy(ind_use[A[0]]).to(tt.device)] = tt
+        ex = InputExtractor(plan, table, ind_use, locs.shape[0], max_t, kernel_sig_t, dt, nodes[0], nodes[1],
+                            use_sign_input=use_sign_input)
         _extractors.clear()
-        _extractors[key] = ent = (ex, trv_times, A_src_in_sta, plan)
+        _extractors[key] = ent = (ex, trv_times, A_src_in_sta, plan, trv_pairwise)
     ex = ent[0]
     P = np.asarray(P, dtype=np.float64)
     keep = (P[:, 0] > (t0v - 2.0 * kernel_sig_t)) & (P[:, 0] < (t0v + max_t + 2.0 * kernel_sig_t))      # :476
@@ -414,5 +429,14 @@ def extract_input_from_data(trv_pairwise, P, t0, ind_use, locs, x_grid, A_src_in
     P_slice = P_slice[ex.sta_perm_host[P_slice[:, 1].astype('int')] > -1]                               # :480-482
     picks_dev = torch.from_numpy(np.ascontiguousarray(P_slice)).to(ex.plan.device)
     Slice, Mask = ex(t0v, picks_dev)
+    if return_embedding:
+        # :571-572: per-phase series of the stations that have a pick in the window, flattened [station][bin]
+        ind_unique = np.sort(np.unique(P_slice[:, 1]).astype('int'))
+        prm = ex.params(t0v)
+        ser = ex._series.view(ex.n_sta_use, prm.n_ts, 2)[torch.from_numpy(ex.sta_perm_host[ind_unique].astype(np.int64)).to(Slice.device)]
+        t_offset = 3.0 * kernel_sig_t
+        abs_time_ref = np.arange(t0v - t_offset, t0v + max_t + t_offset + dt, dt)
+        return (ser[:, :, 0].reshape(-1).clone(), ser[:, :, 1].reshape(-1).clone(), ind_unique, abs_time_ref, int(prm.n_ts),
+                len(ind_unique))
     lp = extract_pick_inputs_from_data(P_slice, locs, ind_use, np.array([t0v]), max_t)
     return [[Slice], [Mask]], lp

@@ -28,6 +28,123 @@ def nearest_index(sorted_vals, t):
     return np.where(np.abs(sorted_vals[lo] - t) <= np.abs(sorted_vals[hi] - t), lo, hi)
 
 
+class WindowRunner(object):
+    """One window of the streaming loop (process_continuous_days.py:776-805: extract_input_from_data + forward_fixed_source) as
+    ONE device-side unit: genie_window_fwd (a1 fused into the front end, Slice / Mask never reach HBM) + the read-out heads,
+    captured once in a CUDA graph and replayed per window.  Everything that changes between windows is the 96-byte parameter
+    block (capi.WindowParams: t0, the time axis, the window's row range in the resident pick table); the host writes it into
+    a ring of pinned slots and one stream-ordered copy per window moves it to the device block the graph reads.
+
+    mz: GCN_Detection_Network_extended with a CARTESIAN plan that has tiling tables; extractor: the plan's InputExtractor.
+    source='resident': the picks come from the extractor's resident day table (`set_day`);
+    source='staged':   the window's picks are copied per window from pinned host memory (`run(t0, picks_host=...)`) into a
+                       device staging area of `max_window_picks` rows — the end-to-end path with host buffers.
+    run() returns (y [G,T,1], x [Q,T,1]); with use_graph=True these are the graph's static output tensors (overwritten by the
+    next run).  Call refresh() after changing model weights or query points."""
+
+    RING = 64
+
+    def __init__(self, mz, extractor, locs_use_cart, x_grid_cart, x_query_cart, t_query, use_graph=True, source='resident',
+                 max_window_picks=None):
+        from . import ops
+        self.mz, self.ex, self.ops = mz, extractor, ops
+        self.locs, self.grid, self.xq, self.tq = locs_use_cart, x_grid_cart, x_query_cart, t_query
+        self.use_graph, self.source = bool(use_graph), source
+        plan = mz._plan
+        if plan is None or plan is not extractor.plan:
+            raise capi.GenieError('WindowRunner: the model and the extractor must share one GraphPlan')
+        if plan.mode != capi.GRAPH_CARTESIAN or plan.tiles is None or extractor.node_sta is not None:
+            raise capi.GenieError('WindowRunner needs a CARTESIAN plan with tiling tables (dense mode)')
+        if mz.use_absolute_pos and locs_use_cart is None:
+            raise capi.GenieError('use_absolute_pos: WindowRunner needs locs_use_cart')
+        self.dev = dev = plan.device
+        self.sz = ctypes.sizeof(capi.WindowParams)
+        self.wp_host = torch.zeros((self.RING, self.sz), dtype=torch.uint8).pin_memory()
+        self.wp_dev = torch.zeros(self.sz, dtype=torch.uint8, device=dev)
+        self._slot, self._ring_events = 0, [None] * self.RING
+        prm = extractor.params(0.0)
+        self.n_extra = int(prm.n_extra)
+        self.n_ts_max = int(prm.n_ts) + 2                    # len(arange) can differ by one between windows (fp64 rounding)
+        self.series = torch.empty((2 * extractor.n_sta_use * self.n_ts_max,), dtype=torch.float32, device=dev)
+        if source == 'resident':
+            if extractor._day is None:
+                raise capi.GenieError("WindowRunner(source='resident') needs extractor.set_day(picks)")
+            times = extractor._day[0]
+            if max_window_picks is None:                      # the busiest window of the day, from the sorted pick times
+                span = extractor.max_t + 4.0 * extractor.kernel_sig_t
+                hi = np.searchsorted(times, times + span, side='right')
+                max_window_picks = int((hi - np.arange(len(times))).max()) if len(times) else 0
+            self.picks = extractor._day[1]
+        elif source == 'staged':
+            if not max_window_picks:
+                raise capi.GenieError("WindowRunner(source='staged') needs max_window_picks")
+            self.picks = torch.zeros((int(max_window_picks), 5), dtype=torch.float64, device=dev)
+        else:
+            raise ValueError(source)
+        self.max_window_picks = int(max_window_picks)
+        self._graph, self._out = None, None
+        self.windows = 0
+
+    def refresh(self):
+        """Drop the captured graph (weights, query points or t_query changed)."""
+        self._graph, self._out = None, None
+
+    def _device_work(self):
+        mz, ex, ops = self.mz, self.ex, self.ops
+        init_relaid = mz._update_init_terms(self.locs, self.grid) if mz.use_absolute_pos else None
+        packed = mz._packed_weights(self.dev, init_relaid)
+        x_spatial = ops.window_fwd(mz._plan, packed, self.wp_dev, self.max_window_picks, self.n_extra, self.picks, ex.sta_perm,
+                                   ex.ind_use, ex.trv_times, self.series, self.n_ts_max, mz._read_in_attr, self.grid,
+                                   float(mz.scale_rel))[0]
+        return mz._heads(x_spatial, self.grid, self.xq, self.tq)
+
+    def _post_params(self, t0, lo, hi):
+        """Window parameters -> next pinned ring slot -> (stream-ordered) device block."""
+        wp = capi.WindowParams()
+        wp.prm = self.ex.params(t0)
+        if wp.prm.n_ts > self.n_ts_max or wp.prm.n_extra != self.n_extra:
+            raise capi.GenieError('WindowRunner: the window time axis does not fit the series scratch')
+        if hi - lo > self.max_window_picks:
+            raise capi.GenieError('WindowRunner: %d picks in the window, max_window_picks = %d' % (hi - lo, self.max_window_picks))
+        wp.pick_lo, wp.pick_hi = int(lo), int(hi)
+        slot = self._slot
+        ev = self._ring_events[slot]
+        if ev is not None:
+            ev.synchronize()                                  # the copy that last read this slot has executed
+        ctypes.memmove(self.wp_host[slot].data_ptr(), ctypes.addressof(wp), self.sz)
+        self.wp_dev.copy_(self.wp_host[slot], non_blocking=True)
+        if self._ring_events[slot] is None:
+            self._ring_events[slot] = torch.cuda.Event()
+        self._ring_events[slot].record()
+        self._slot = (slot + 1) % self.RING
+
+    def run(self, t0, picks_host=None):
+        t0 = float(t0)
+        with torch.no_grad():
+            if self.source == 'resident':
+                lo, hi = self.ex.window_rows(t0)
+            else:
+                n = int(picks_host.shape[0])
+                if n > self.max_window_picks:
+                    raise capi.GenieError('WindowRunner: %d picks in the window, max_window_picks = %d' % (n, self.max_window_picks))
+                if n:
+                    self.picks[:n].copy_(picks_host, non_blocking=True)
+                lo, hi = 0, n
+            self._post_params(t0, lo, hi)
+            self.windows += 1
+            if not self.use_graph:
+                return self._device_work()
+            if self._graph is None:
+                self._device_work()                           # warm-up: packs weights, builds caches, sets kernel attributes
+                torch.cuda.current_stream(self.dev).synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._out = self._device_work()
+                self._graph = g
+            self._graph.replay()
+            return self._out
+
+
 class DayProcessor(object):
     """`mz`: a GCN_Detection_Network_extended with its adjacencies set; `extractor`: an InputExtractor with the day's picks
     resident (`set_day`).  `run(tsteps, tsteps_abs)` returns Out_2 [Q, len(tsteps_abs)] on the device."""

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GENIE_B200_ABI_VERSION 6
+#define GENIE_B200_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define GENIE_API __attribute__((visibility("default")))
@@ -160,7 +160,8 @@ GENIE_API size_t genie_frontend_packed_floats(void);
 GENIE_API int genie_frontend_pack_weights(const genie_frontend_weights_t* w, float* packed_dev, void* stream);
 
 /* ---- a1: pick window -> Slice / Mask ---------------------------------------------------------------------------------
- * Replaces process_utils.extract_input_from_data (process_utils.py:460-629; use_sign_input False, trv_times given).
+ * Replaces process_utils.extract_input_from_data (process_utils.py:460-629; trv_times given — the host mirror builds the
+ * table from `trv_pairwise` when the caller passes none, :594-596).
  * The fp64 quantities that the reference derives on the host with numpy (`abs_time_ref[0]`, the arange step
  * `(start+dt)-start`, `len(abs_time_ref)`, `ceil(3*sigma/dt)`) are computed by the caller with the same expressions and
  * passed in, so the integer pick->bin and node->bin maps are bit-identical to numpy's.
@@ -176,6 +177,8 @@ typedef struct genie_input_params {
     int32_t n_extra;        /* ceil(3*sigma/dt)                           (process_utils.py:520) */
     int32_t n_locs;         /* number of stations of the absolute station table */
     int32_t n_sta_use;      /* number of used stations (len(ind_use)) */
+    int32_t use_sign_input; /* process_utils.py:610-614: features times sign(-diff) of the series they were read from */
+    int32_t reserved_;
 } genie_input_params_t;
 
 /* picks_dev      fp64 [n_picks,5] (time, absolute station, amp, prob, phase 0/1), any order.
@@ -338,6 +341,35 @@ GENIE_API int genie_frontend_fwd(const genie_plan_t* plan, const float* packed_d
                        const float* mask_dev, const float* edge_attr_dev, const float* pos_dev, float scale_rel,
                        float* x_latent_out_dev, float* readin_out_dev, float* x_spatial_out_dev,
                        void* workspace_dev, void* stream);
+
+/* ---- a1 fused into the front end: one window of the streaming loop — process_continuous_days.py:776-797 -------------
+ * extract_input_from_data + forward_fixed_source's front end for CARTESIAN plans whose pick table, travel times and graphs
+ * are resident on the device.  Slice / Mask never reach HBM: the per-station series is built as in genie_input_scatter_fwd,
+ * and the layer-0 kernel computes every node's Slice / Mask row in registers (same fp64 bin arithmetic) right before
+ * init_trns.  Everything that changes from window to window sits in ONE device-resident block, so that the whole window
+ * can be captured in a CUDA graph once and replayed (the caller refreshes the block, e.g. by a captured copy from pinned
+ * host memory):
+ *   wp_dev            DEVICE pointer to the window's parameters and the row range [pick_lo, pick_hi) of its picks inside
+ *                     picks_dev (the reference's selection P[:,0] in (t0 - 2 sigma, t0 + max_t + 2 sigma), :476, is applied
+ *                     per pick again, so any superset range is fine)
+ *   max_window_picks  launch bound of the series kernel (a frozen graph cannot resize its grids): pick_hi - pick_lo must not
+ *                     exceed it — rows beyond it are NOT processed; n_extra = the host's copy of prm.n_extra (a constant
+ *                     of sigma and dt), which sizes that grid as well
+ *   series_dev        fp32 scratch for 2 * n_sta_use * n_ts_max floats; n_ts_max >= every window's prm.n_ts
+ *   slice_out_dev / mask_out_dev   optional [P,4] copies of the inputs (NULL = not materialised)
+ * Other arguments as genie_frontend_fwd.  Plans without tiling tables and EXPLICIT plans: GENIE_ERR_UNSUPPORTED
+ * (use genie_input_scatter_fwd + genie_frontend_fwd). */
+typedef struct genie_window_params {
+    genie_input_params_t prm;
+    int64_t pick_lo, pick_hi;
+} genie_window_params_t;
+
+GENIE_API int genie_window_fwd(const genie_plan_t* plan, const float* packed_dev, const genie_window_params_t* wp_dev,
+                               int64_t max_window_picks, int32_t n_extra, const double* picks_dev, const int32_t* sta_perm_dev,
+                               const int32_t* ind_use_dev, const float* trv_times_dev, float* series_dev, int32_t n_ts_max,
+                               const float* edge_attr_dev, const float* pos_dev, float scale_rel, float* slice_out_dev,
+                               float* mask_out_dev, float* x_latent_out_dev, float* readin_out_dev,
+                               float* x_spatial_out_dev, void* workspace_dev, void* stream);
 
 /* ---- the same front end in two halves, for grid-sharded plans (genie_b200/sharded.py) ----------------------------------
  * genie_da_layer1_fwd runs DataAggregation up to the layer-2 messages (module.py:88-93) and leaves them in the workspace;

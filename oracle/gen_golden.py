@@ -6,6 +6,7 @@
     python oracle/gen_golden.py legacy_input     # a1': extract_inputs_from_data_fixed_grids_with_phase_type
     python oracle/gen_golden.py association      # forward_fixed incl. the association branch
     python oracle/gen_golden.py dense_adjacencies # the dense graph builder incl. the time-pointer re-indexing (process_utils.py:701-742)
+    python oracle/gen_golden.py input_variants   # a1 with use_sign_input / trv_times=None (process_utils.py:594-614)
     python oracle/gen_golden.py subgraph         # sub-graph mode builder (process_utils.py:744-849) + one window on it
     python oracle/gen_golden.py ferndale       # Examples/Ferndale.zip: real stations/grids/picks + trained checkpoint
 
@@ -443,6 +444,47 @@ def dense_adjacencies():
     print('dense_adjacencies', {k: (res[k].shape, res[k].dtype) for k in names})
 
 
+def input_variants():
+    """a1 with the switches of extract_input_from_data (process_utils.py:460) the day-processing script uses:
+    `use_sign_input=True` (process_continuous_days.py:776 passes the flag; :610-614) and `trv_times=None` (travel times from
+    the `trv_pairwise` callable, :594-596), on a station subset — through the unmodified reference."""
+    work = tempfile.mkdtemp(prefix='genie_golden_')
+    for f in ('config.yaml', 'train_config.yaml'):
+        shutil.copy(os.path.join(REF, 'Code', f), work)
+    torch, module, pu, Data = _import_reference(os.path.join(REF, 'Code'), work)
+    from genie_b200 import synth
+    S_all, n_use, G, seed = 14, 12, 60, 11
+    net = synth.Network(S_all, G, seed=seed, width_km=120.0)
+    rng = np.random.default_rng(100 + seed)
+    ind_use = np.sort(rng.choice(S_all, size=n_use, replace=False))
+    max_t = net.max_moveout()
+    sig, dt = 3.0, float(np.round(3.0 / 10.0, 2))
+    P = synth.make_picks(net, 0.0, 600.0, seed=seed + 1, events_per_3h=400.0, false_per_sta_min=3.0)
+    t0 = 233.0
+    trv_times = net.travel_times()
+    A_src_in_sta = np.concatenate((np.tile(np.arange(n_use), G).reshape(1, -1),
+                                   np.arange(G).repeat(n_use, axis=0).reshape(1, -1)), axis=0)
+
+    def trv_pairwise(sta, src):                        # homogeneous half-space in fp32 torch, as a travel-time net would return
+        d = torch.norm(sta - src, dim=1, keepdim=True)
+        return torch.cat((d / 6000.0, d / 3464.0), dim=1)
+
+    res = dict(sta=net.sta, grid=net.grid, ind_use=ind_use, trv_times=trv_times, picks=P, t0=np.float64(t0),
+               max_t=np.float64(max_t), kernel_sig_t=np.float64(sig), dt=np.float64(dt))
+    for tag, kw in (('sign', dict(trv_times=trv_times, use_sign_input=True)),
+                    ('plain', dict(trv_times=trv_times)),
+                    ('pairwise', dict(trv_times=None)),
+                    ('pairwise_sign', dict(trv_times=None, use_sign_input=True))):
+        [Inpts, Masks], _ = pu.extract_input_from_data(trv_pairwise, P, np.array([t0]), ind_use, net.sta, net.grid,
+                                                       A_src_in_sta, max_t=max_t, kernel_sig_t=sig, dt=dt, device='cpu', **kw)
+        res['Slice_' + tag], res['Mask_' + tag] = Inpts[0].numpy(), Masks[0].numpy()
+    sta_t, grid_t = torch.Tensor(net.sta[ind_use]), torch.Tensor(net.grid)
+    res['trv_pairwise'] = trv_pairwise(sta_t[A_src_in_sta[0]], grid_t[A_src_in_sta[1]]).numpy()       # [P,2] fp32
+    np.savez_compressed(os.path.join(GOLD, 'input_variants_12of14x60.npz'), **res)
+    print('input_variants', {k: (float(res[k].sum()), int((res[k] != 0).sum())) for k in res if k.startswith('Slice_')},
+          'negatives with sign input:', int((res['Slice_sign'] < 0).sum()))
+
+
 if __name__ == '__main__':
     mode = sys.argv[1] if len(sys.argv) > 1 else 'synthetic'
     if mode == 'synthetic':
@@ -463,6 +505,8 @@ if __name__ == '__main__':
         subgraph()
     elif mode == 'dense_adjacencies':
         dense_adjacencies()
+    elif mode == 'input_variants':
+        input_variants()
     elif mode == 'ferndale':
         from gen_golden_ferndale import ferndale
         ferndale()

@@ -118,7 +118,8 @@ def input_time_axis(t0, max_t, kernel_sig_t, dt):
     return ref, int(len(ref))
 
 
-def input_scatter(P, t0, ind_use, n_locs, A_src_in_sta, trv_times, max_t, kernel_sig_t, dt, return_parts=False):
+def input_scatter(P, t0, ind_use, n_locs, A_src_in_sta, trv_times, max_t, kernel_sig_t, dt, return_parts=False,
+                  use_sign_input=False, trv_node=None):
     """Restates extract_input_from_data (process_utils.py:460-629).
 
     P [n,5] float64 (time, station, amp, prob, phase 0/1); ind_use int array of used (absolute) station ids;
@@ -134,6 +135,8 @@ def input_scatter(P, t0, ind_use, n_locs, A_src_in_sta, trv_times, max_t, kernel
     A = np.asarray(A_src_in_sta).astype('int')
     S_use = len(ind_use)
     ref, n_ts = input_time_axis(t0, max_t, kernel_sig_t, dt)
+    # use_sign_input (:610-614): every feature times sign(-diff) of the flattened [station][bin] series it is read from.
+    # trv_node [P,2]: per-node travel times as `trv_pairwise` returns them when trv_times is None (:594-596).
 
     keep = (P[:, 0] > (t0 - 2.0 * kernel_sig_t)) & (P[:, 0] < (t0 + max_t + 2.0 * kernel_sig_t))   # :476
     Pw = P[keep]
@@ -161,7 +164,8 @@ def input_scatter(P, t0, ind_use, n_locs, A_src_in_sta, trv_times, max_t, kernel
     either = series.max(axis=0)                                                                    # :569
 
     # :599  fp32 travel time + fp64 t0 - fp64 ref[0], divided by fp64 dt, truncated toward zero
-    tb = ((trv_times[A[1], ind_use[A[0]], :] + np.array([t0]) - ref[0]) / dt).astype('int')
+    tt = trv_times[A[1], ind_use[A[0]], :] if trv_node is None else np.asarray(trv_node)
+    tb = ((tt + np.array([t0]) - ref[0]) / dt).astype('int')
     inb = (tb >= 0) & (tb < n_ts)
     tbc = np.clip(tb, 0, n_ts - 1)
     s = A[0]
@@ -169,6 +173,16 @@ def input_scatter(P, t0, ind_use, n_locs, A_src_in_sta, trv_times, max_t, kernel
     f1 = np.where(inb[:, 1], either[s, tbc[:, 1]], 0.0)                                            # :606
     f2 = np.where(inb[:, 0], series[0, s, tbc[:, 0]], 0.0)                                         # :607
     f3 = np.where(inb[:, 1], series[1, s, tbc[:, 1]], 0.0)                                         # :608
+    if use_sign_input:
+        def slope_sign(e):                           # torch.sign(-diff(e, append = e[-1] + (e[-1] - e[-2]))) on the flat array
+            flat = e.reshape(-1)
+            d = np.diff(flat, append=flat[-1:] + (flat[-1:] - flat[-2:-1]))
+            return np.sign(-1.0 * d).reshape(e.shape)
+        sg_e, sg_p, sg_s = slope_sign(either), slope_sign(series[0]), slope_sign(series[1])
+        f0 = f0 * np.where(inb[:, 0], sg_e[s, tbc[:, 0]], 0.0)                                     # :611
+        f1 = f1 * np.where(inb[:, 1], sg_e[s, tbc[:, 1]], 0.0)                                     # :612
+        f2 = f2 * np.where(inb[:, 0], sg_p[s, tbc[:, 0]], 0.0)                                     # :613
+        f3 = f3 * np.where(inb[:, 1], sg_s[s, tbc[:, 1]], 0.0)                                     # :614
     Slice = np.stack((f0, f1, f2, f3), axis=1).astype(np.float32)                                  # :627-628
     Mask = (np.abs(Slice) > 0.01).astype(np.float32)                                               # :629
     if return_parts:

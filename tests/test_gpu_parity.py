@@ -65,6 +65,115 @@ def test_input_scatter_matches_reference(name):
     assert torch.equal(S2, Slice) and torch.equal(M2, Mask)
 
 
+def test_input_switches_match_reference():
+    """extract_input_from_data with the switches of the reference's signature (process_utils.py:460): use_sign_input
+    (:610-614, the flag process_continuous_days.py:776 passes), trv_times=None with a `trv_pairwise` calculator (:594-596)
+    and return_embedding (:571-572), against the unmodified reference on a station subset."""
+    from genie_b200.process_utils import extract_input_from_data
+    dev = _dev()
+    d, _ = load_golden('input_variants_12of14x60')
+    S, G = len(d['ind_use']), d['grid'].shape[0]
+    A = np.stack((np.tile(np.arange(S), G), np.repeat(np.arange(G), S)), axis=0)
+
+    def trv_pairwise(sta, src):                       # evaluated on the host in fp32, exactly as the fixture's calculator
+        dd = torch.norm(sta.cpu() - src.cpu(), dim=1, keepdim=True)
+        return torch.cat((dd / 6000.0, dd / 3464.0), dim=1).to(sta.device)
+
+    for tag, kw in (('plain', dict(trv_times=d['trv_times'])), ('sign', dict(trv_times=d['trv_times'], use_sign_input=True)),
+                    ('pairwise', dict(trv_times=None)), ('pairwise_sign', dict(trv_times=None, use_sign_input=True))):
+        [Inpts, Masks], _ = extract_input_from_data(trv_pairwise, d['picks'], np.array([float(d['t0'])]), d['ind_use'], d['sta'],
+                                                    d['grid'], A, max_t=float(d['max_t']), kernel_sig_t=float(d['kernel_sig_t']),
+                                                    dt=float(d['dt']), device=dev, **kw)
+        got = Inpts[0].cpu().numpy()
+        assert np.abs(got - d['Slice_' + tag]).max() <= 1e-6, tag
+        assert np.array_equal(np.sign(got), np.sign(d['Slice_' + tag])), tag
+        assert np.array_equal(Masks[0].cpu().numpy(), d['Mask_' + tag]), tag
+    # the per-station series of return_embedding against the oracle's (pinned by the fixtures of test_oracle_golden.py)
+    from oracle import genie_oracle as go
+    emb = extract_input_from_data(None, d['picks'], np.array([float(d['t0'])]), d['ind_use'], d['sta'], d['grid'], A,
+                                  trv_times=d['trv_times'], max_t=float(d['max_t']), kernel_sig_t=float(d['kernel_sig_t']),
+                                  dt=float(d['dt']), return_embedding=True, device=dev)
+    _, _, parts = go.input_scatter(d['picks'], float(d['t0']), d['ind_use'], d['sta'].shape[0], A, d['trv_times'],
+                                   float(d['max_t']), float(d['kernel_sig_t']), float(d['dt']), return_parts=True)
+    perm = -np.ones(d['sta'].shape[0], dtype=int)
+    perm[d['ind_use']] = np.arange(S)
+    assert emb[4] == parts['n_ts'] and emb[5] == len(emb[2]) and abs(emb[3][0] - parts['ref0']) == 0.0
+    for ph in (0, 1):
+        want = parts['series'][ph][perm[emb[2]]].reshape(-1)
+        assert np.abs(emb[ph].cpu().numpy() - want).max() <= 1e-6
+
+
+def test_window_runner_equals_the_two_step_path():
+    """genie_window_fwd (a1 fused into layer 0: Slice / Mask never reach HBM, the mask rides bit-packed in the feature rows)
+    behind streaming.WindowRunner — eager, captured in a CUDA graph, and with the window's picks staged from pinned host
+    memory — against extract_input + forward_fixed_source on the same windows: y and x bit for bit, and the optional
+    Slice / Mask copies equal the two-step inputs."""
+    from genie_b200 import ops, synth
+    from genie_b200.module import GCN_Detection_Network_extended
+    from genie_b200.process_utils import InputExtractor, extract_inputs_adjacencies_cartesian
+    from genie_b200.streaming import WindowRunner
+    from oracle import genie_oracle as go
+    dev = _dev()
+    S, G = 100, 1500
+    net = synth.Network(S, G, seed=3)
+    A_sta, A_src = extract_inputs_adjacencies_cartesian(net.sta, net.grid, 15, 15)
+    attr = torch.from_numpy(net.read_in_offsets(30000.0)).to(dev)
+    m = GCN_Detection_Network_extended(None, None, scale_rel=30000.0, device=dev).eval()
+    m.load_state_dict(go.init_state(seed=9), strict=False)
+    m.set_adjacencies_cartesian(A_sta, A_src, attr, S, G, device=dev)
+    max_t = net.max_moveout()
+    for sign in (False, True):
+        ex = InputExtractor(m._plan, net.travel_times(), np.arange(S), S, max_t, 3.0, 0.3, use_sign_input=sign)
+        P = synth.make_picks(net, 0.0, 600.0, seed=4, false_per_sta_min=4.0)
+        ex.set_day(P)
+        locs = torch.from_numpy(net.sta).float().to(dev)
+        grid = torch.from_numpy(net.grid).float().to(dev)
+        xq = torch.from_numpy(np.random.default_rng(1).uniform(0, net.width, (300, 3))).float().to(dev)
+        xq[:, 2] = -xq[:, 2] / net.width * 40000.0
+        tq = torch.arange(-3.0, 3.01, 0.75, device=dev).reshape(-1, 1)
+        runners = [WindowRunner(m, ex, locs, grid, xq, tq, use_graph=False),
+                   WindowRunner(m, ex, locs, grid, xq, tq, use_graph=True),
+                   WindowRunner(m, ex, locs, grid, xq, tq, use_graph=True, source='staged', max_window_picks=4096)]
+        host = torch.from_numpy(ex._day[1].cpu().numpy()).pin_memory()
+        for t0 in (12.0, 15.0, 18.0, 250.5, 251.25, 400.0):
+            Slice, Mask = ex(t0)
+            y0, x0 = m.forward_fixed_source(Slice, Mask, None, None, None, locs, grid, xq, tq)
+            if sign:
+                assert bool((Slice < 0).any())
+            for r in runners:
+                if r.source == 'staged':
+                    lo, hi = ex.window_rows(t0)
+                    y, x = r.run(t0, host[lo:hi])
+                else:
+                    y, x = r.run(t0)
+                assert torch.equal(y, y0) and torch.equal(x, x0), (t0, r.use_graph, r.source)
+        # the optional copies of the inputs
+        wp = capi_window_block(ex, 250.5, dev)
+        packed = m._packed_weights(dev)
+        lo, hi = ex.window_rows(250.5)
+        out = ops.window_fwd(m._plan, packed, wp(lo, hi), hi - lo, ex.params(0.0).n_extra, ex._day[1], ex.sta_perm, ex.ind_use,
+                             ex.trv_times, torch.empty(2 * S * (ex.params(0.0).n_ts + 2), device=dev), ex.params(0.0).n_ts + 2,
+                             attr, grid, 30000.0, want_inputs=True, want_latent=True, want_readin=True)
+        Slice, Mask = ex(250.5)
+        _, lat, rin = m.front_end(Slice, Mask, grid, want_latent=True, want_readin=True)
+        assert torch.equal(out[3], Slice) and torch.equal(out[4], Mask)
+        assert torch.equal(out[1], lat) and torch.equal(out[2], rin)
+
+
+def capi_window_block(ex, t0, dev):
+    """Device copy of a capi.WindowParams for window t0 (test helper)."""
+    import ctypes
+    from genie_b200 import capi
+
+    def make(lo, hi):
+        wp = capi.WindowParams()
+        wp.prm = ex.params(t0)
+        wp.pick_lo, wp.pick_hi = int(lo), int(hi)
+        raw = np.frombuffer(ctypes.string_at(ctypes.addressof(wp), ctypes.sizeof(wp)), dtype=np.uint8).copy()
+        return torch.from_numpy(raw).to(dev)
+    return make
+
+
 @pytest.mark.parametrize('name', GOLD)
 def test_operators_match_reference(name):
     """a2, a3, a4 one by one, each fed the reference's own input for that stage."""
@@ -495,11 +604,13 @@ def test_window_against_oracle_on_sampled_closure(workload, window):
     if workload.startswith('c4') and torch.cuda.get_device_properties(dev).total_memory < 100e9:
         pytest.skip('needs ~60 GB of device memory')
     wl = bench.Workload(workload, dev, day_s=1500.0)
+    wl.runners(use_graph=workload.startswith('c2'))         # C2 through the CUDA-graph replay, C4 eager (as bench.py runs them)
     rep = bench.closure_parity(wl, window)
     assert rep['nodes'] >= 16 and rep['picks_in_window'] > 0
     assert rep['time_bin_equal'] and rep['mask_equal'] and rep['slice_max_abs'] <= 1e-6, rep
     assert rep['x_latent_rowwise_rel'] < 1e-4 and rep['read_in_rowwise_rel'] < 1e-4, rep
     assert rep['y_rel'] < 1e-4 and rep['x_rel'] < 1e-4, rep
+    assert rep['fused_equals_two_step'], rep
     assert rep['ok']
     del wl
     torch.cuda.empty_cache()

@@ -240,3 +240,19 @@ def test_closure_check_reproduces_the_full_oracle():
     # the row-wise metric is the stricter one
     a = np.array([[1.0, 1e-3], [1e-3, 1e-3]]); b = a.copy(); b[1, 1] += 1e-6
     assert cc.rowwise_rel(b, a) > 100 * cc.global_rel(b, a)
+
+
+def test_input_variants_match_reference():
+    """a1 with use_sign_input (process_utils.py:610-614) and with per-pair travel times from `trv_pairwise` (:594-596):
+    the oracle against the unmodified reference (oracle/gen_golden.py input_variants)."""
+    d, _ = load_golden('input_variants_12of14x60')
+    S, G = len(d['ind_use']), d['grid'].shape[0]
+    A = np.stack((np.tile(np.arange(S), G), np.repeat(np.arange(G), S)), axis=0)
+    args = (d['picks'], float(d['t0']), d['ind_use'], d['sta'].shape[0], A, d['trv_times'], float(d['max_t']),
+            float(d['kernel_sig_t']), float(d['dt']))
+    for tag, kw in (('plain', {}), ('sign', dict(use_sign_input=True)), ('pairwise', dict(trv_node=d['trv_pairwise'])),
+                    ('pairwise_sign', dict(trv_node=d['trv_pairwise'], use_sign_input=True))):
+        Sl, Mk = go.input_scatter(*args, **kw)
+        assert np.array_equal(Sl, d['Slice_' + tag]), tag
+        assert np.array_equal(Mk, d['Mask_' + tag]), tag
+    assert (d['Slice_sign'] < 0).sum() > 100 and np.array_equal(np.abs(d['Slice_sign']) > 0.01, d['Mask_sign'] > 0)
