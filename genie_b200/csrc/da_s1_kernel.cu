@@ -7,14 +7,16 @@
 // The CTA runs TWO tile pipelines (even / odd tiles) that share the producers and the weights in shared memory; a pipeline
 // owns one shared-memory buffer, 256 tensor-memory columns, a gather warpgroup, an epilogue warpgroup and an MMA-issuing
 // warp, so the gather of one tile, the tensor-core chain of another and the epilogues overlap:
-//     * producer warps stage the p rows of the tile's stations AND of the halo of their station-graph in-neighbours
-//       (<= 288 rows x 128 B, table genie_graph_desc_t.sta_tile_rows) as PReLU11(tr0): the rows pass through registers
-//       (LDG -> convert -> STS; per 512 bytes the same LSU work as a cp.async, and the conversion no longer is a serial
-//       phase between fill and gather), the tile's msrc rows and its mask rows go by cp.async.  `mask` == NULL: the four
-//       mask values ride bit-packed in channel 30 of the p rows (a1 fused into layer 0, genie_window_fwd);
-//     * the gather warpgroup (thread per row) sums the <= 16 neighbour rows of its station out of shared memory (16-byte
-//       chunks are visited in a per-lane rotated order, so arbitrary rows are bank-conflict free), recovers tr0 of its
-//       own row, and writes the three 32-column A operands  [tr0 | mask0,1], [mean_sta | mask2,3], [mean_src | mask2,3]
+//     * producer warps stage, with cp.async, the p rows of the tile's stations AND of the halo of their station-graph
+//       in-neighbours (<= 288 rows x 128 B, table genie_graph_desc_t.sta_tile_rows), the tile's msrc rows and its mask
+//       rows (`mask` == NULL: the four mask values ride bit-packed in channel 30 of the p rows — a1 fused into layer 0,
+//       genie_window_fwd — and a compact copy of that chunk is staged instead);
+//     * the gather warpgroup (thread per row) sums PReLU11(tr0) over the <= 16 neighbour rows of its station out of shared
+//       memory: the staged value is p = PReLU12(tr0), and PReLU11(tr0) = max(p, r p) (min for r > 1), r = slope11 / slope12,
+//       evaluated on the fly (an earlier version converted the staged rows in place first: a serial 2.5 k-cycle phase
+//       between fill and gather and 14 % of the kernel's shared-memory wavefronts, profiles/r4b); 16-byte chunks are
+//       visited in a per-lane rotated order, so arbitrary rows are bank-conflict free.  The warpgroups write the three
+//       32-column A operands  [tr0 | mask0,1], [mean_sta | mask2,3], [mean_src | mask2,3]
 //       as 3xTF32 hi/lo parts straight into tensor memory;
 //     * the MMA warp runs  stage B [.. ] -> tr (60),  stage C tr -> [h_a | h_b | c_a | c_b] (90),  stage D PReLU(h) ->
 //       [v_a | v_b] (30)  as tcgen05.mma kind::tf32 (hi*hi + lo*hi + hi*lo), weights resident in shared memory in the
@@ -148,13 +150,13 @@ __device__ __forceinline__ void store16_rows(const float (&v)[16], unsigned char
     __syncwarp();
 }
 
-// Epilogue-warpgroup half of the stage-B operands of one tile: [tr0 | mask0,1] (tr0 recovered from the staged PReLU11(tr0)
+// Epilogue-warpgroup half of the stage-B operands of one tile: [tr0 | mask0,1] (tr0 recovered from the staged PReLU12(tr0)
 // of the thread's own row) and [mean_src | mask2,3] (the thread's msrc row) -> tensor memory.  Returns the row's mask.
 __device__ __forceinline__ float4 s1_load_mask(const unsigned char* sb, int r, bool valid, bool packed) {
     float4 mk = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) {
-        if (packed) mk = unpack_mask(*reinterpret_cast<const float*>(sb + SB_MK + r * 4));
-        else mk = *reinterpret_cast<const float4*>(sb + SB_MK + r * 16);
+        mk = *reinterpret_cast<const float4*>(sb + SB_MK + r * 16);
+        if (packed) mk = unpack_mask(mk.z);       // chunk 7 of the own p row: channel 30 = the four mask bits
     }
     return mk;
 }
@@ -269,9 +271,6 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
         const int tid = threadIdx.x - (WG_P0 + 2 * q) * 32;
         const int rr = tid >> 3, c = tid & 7;
         constexpr int JMAX = (ROWS + 7) / 8;
-        constexpr int PB = 12;                         // p chunks in flight per thread
-        static_assert(JMAX % PB == 0, "p-row batches");
-        const float r11 = sc[TCS_R11];
         unsigned char* sbp = smem + SM_BUF + q * SB_SIZE;
         const uint32_t sb = smem_u32(sbp);
         if (q == 1 && stagger > 0) {                   // start the second pipeline out of phase with the first
@@ -283,40 +282,30 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
             const int g = (int)(t / NT), T = (int)(t - (int64_t)g * NT);
             const int n_own = __ldg(tile_meta + 2 * T), n_rows = __ldg(tile_meta + 2 * T + 1);
             const int32_t* rows = tile_rows + (int64_t)T * ROWS;
-            // (the station-id table of the 8 tile types is a few KB and L1-resident: ids are fetched batch by batch)
+            int ids[JMAX];
+#pragma unroll
+            for (int j = 0; j < JMAX; ++j) ids[j] = (rr + 8 * j) < n_rows ? __ldg(rows + rr + 8 * j) : -1;
+            const int id_m0 = tid < n_own ? __ldg(rows + tid) : -1;
+            const int id_m1 = tid + 64 < n_own ? __ldg(rows + tid + 64) : -1;
             if (k > 0) mbar_wait(&bars->empty[q], (uint32_t)((k - 1) & 1));
             if (tid == 0) S1_TRACE(17);
-            const float4* pg = reinterpret_cast<const float4*>(p + (int64_t)g * S * 32);
-            const float4* mg = reinterpret_cast<const float4*>(msrc + (int64_t)g * S * 32);
+            const int64_t node0 = (int64_t)g * S;
+#pragma unroll
+            for (int j = 0; j < JMAX; ++j)
+                if (ids[j] >= 0) cp_async16(sb + SB_P + (rr + 8 * j) * 128 + c * 16, p + (node0 + ids[j]) * 32 + c * 4);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int r = rr + 8 * j;
-                if (r < n_own) cp_async16(sb + SB_MS + r * 128 + ((c ^ (r & 7)) << 4), mg + (__ldg(rows + r) * 8 + c));
+                if (r < n_own) cp_async16(sb + SB_MS + r * 128 + ((c ^ (r & 7)) << 4), msrc + (node0 + ids[j]) * 32 + c * 4);
             }
-            if (!packed_mask) {
-                const float4* kg = reinterpret_cast<const float4*>(mask + (int64_t)g * S * 4);
-                if (tid < n_own) cp_async16(sb + SB_MK + tid * 16, kg + __ldg(rows + tid));
-                if (tid + 64 < n_own) cp_async16(sb + SB_MK + (tid + 64) * 16, kg + __ldg(rows + tid + 64));
-            }
-#pragma unroll 1
-            for (int j0 = 0; j0 < JMAX; j0 += PB) {
-                if (rr + 8 * j0 >= n_rows) break;
-                float4 v[PB];
-#pragma unroll
-                for (int u = 0; u < PB; ++u) {
-                    const int r = rr + 8 * (j0 + u);
-                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (r < n_rows) v[u] = __ldcg(pg + (__ldg(rows + r) * 8 + c));
-                }
-#pragma unroll
-                for (int u = 0; u < PB; ++u) {
-                    const int r = rr + 8 * (j0 + u);
-                    if (r < n_rows) {
-                        if (packed_mask && c == 7 && r < n_own) *reinterpret_cast<float*>(sbp + SB_MK + r * 4) = v[u].z;
-                        *reinterpret_cast<float4*>(sbp + SB_P + r * 128 + c * 16) = make_float4(
-                            prelu_f(v[u].x, r11), prelu_f(v[u].y, r11), prelu_f(v[u].z, r11), prelu_f(v[u].w, r11));
-                    }
-                }
+            // mask rows: from the caller's Mask [P,4], or (packed) a compact copy of chunk 7 of the own p rows, whose
+            // channel 30 carries the four mask bits — thread-per-row readers get it without bank conflicts
+            if (packed_mask) {
+                if (id_m0 >= 0) cp_async16(sb + SB_MK + tid * 16, p + (node0 + id_m0) * 32 + 28);
+                if (id_m1 >= 0) cp_async16(sb + SB_MK + (tid + 64) * 16, p + (node0 + id_m1) * 32 + 28);
+            } else {
+                if (id_m0 >= 0) cp_async16(sb + SB_MK + tid * 16, mask + (node0 + id_m0) * 4);
+                if (id_m1 >= 0) cp_async16(sb + SB_MK + (tid + 64) * 16, mask + (node0 + id_m1) * 4);
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
             mbar_arrive(&bars->full[q]);
@@ -408,6 +397,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
         const int r = ((warp - WG_G0) & 3) * 32 + lane;
         const uint32_t lane_base = tm + q * TM_PIPE + ((uint32_t)((warp & 3) * 32) << 16);
         const int key = lane & 7;
+        const float r11 = sc[TCS_R11];
         unsigned char* sb = smem + SM_BUF + q * SB_SIZE;
         int64_t k = 0;
         for (int64_t t = blockIdx.x + (int64_t)q * gridDim.x; t < n_tiles; t += 2 * (int64_t)gridDim.x, ++k) {
@@ -426,13 +416,23 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
 #pragma unroll
                 for (int c = 0; c < 8; ++c) a2[c].lo = a2[c].hi = 0ull;
                 const uint32_t w[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const uint32_t idx = (j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xffffu);
-                    const unsigned char* ra = sb + SB_P + idx * 128;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) fadd4(a2[c], *reinterpret_cast<const float4*>(ra + ((c ^ key) << 4)));
+                // PReLU11(tr0) from the staged p = PReLU12(tr0): max(p, r p) for r <= 1, min(p, r p) for r > 1 (both slopes are
+                // positive on this path, layout.h TCS_OK) — the values the in-place conversion used to produce, bit for bit
+#define S1_GATHER(OP)                                                                                           \
+    _Pragma("unroll") for (int j = 0; j < 16; ++j) {                                                            \
+        const uint32_t idx = (j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xffffu);                               \
+        const unsigned char* ra = sb + SB_P + idx * 128;                                                        \
+        _Pragma("unroll") for (int c = 0; c < 8; ++c) {                                                         \
+            const float4 v = *reinterpret_cast<const float4*>(ra + ((c ^ key) << 4));                           \
+            fadd4(a2[c], make_float4(OP(v.x, v.x * r11), OP(v.y, v.y * r11), OP(v.z, v.z * r11), OP(v.w, v.w * r11))); \
+        }                                                                                                       \
+    }
+                if (r11 <= 1.f) {
+                    S1_GATHER(fmaxf)
+                } else {
+                    S1_GATHER(fminf)
                 }
+#undef S1_GATHER
 #pragma unroll
                 for (int c = 0; c < 8; ++c) acc[c] = to_float4(a2[c]);
             }
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
         const int q = (warp - WG_E0) >> 2;
         const int r = ((warp - WG_E0) & 3) * 32 + lane;
         const uint32_t lane_base = tm + q * TM_PIPE + ((uint32_t)((warp & 3) * 32) << 16);
-        const float a1 = sc[TCS_A1], a21 = sc[TCS_A21], a22 = sc[TCS_A22], inv11 = sc[TCS_INV11];
+        const float a1 = sc[TCS_A1], a21 = sc[TCS_A21], a22 = sc[TCS_A22], inv11 = sc[TCS_INV12];   // staged rows are PReLU12(tr0)
         const int key = lane & 7;
         const unsigned char* sb = smem + SM_BUF + q * SB_SIZE;
         unsigned char* scr = smem + SM_SCR + (warp - WG_E0) * 2048;
