@@ -11,12 +11,13 @@
 //       in-neighbours (<= 288 rows x 128 B, table genie_graph_desc_t.sta_tile_rows), the tile's msrc rows and its mask
 //       rows (`mask` == NULL: the four mask values ride bit-packed in channel 30 of the p rows — a1 fused into layer 0,
 //       genie_window_fwd — and a compact copy of that chunk is staged instead);
-//     * the gather warpgroup (thread per row) sums PReLU11(tr0) over the <= 16 neighbour rows of its station out of shared
-//       memory: the staged value is p = PReLU12(tr0), and PReLU11(tr0) = max(p, r p) (min for r > 1), r = slope11 / slope12,
-//       evaluated on the fly (an earlier version converted the staged rows in place first: a serial 2.5 k-cycle phase
-//       between fill and gather and 14 % of the kernel's shared-memory wavefronts, profiles/r4b); 16-byte chunks are
-//       visited in a per-lane rotated order, so arbitrary rows are bank-conflict free.  The warpgroups write the three
-//       32-column A operands  [tr0 | mask0,1], [mean_sta | mask2,3], [mean_src | mask2,3]
+//       the (otherwise waiting) gather warpgroup converts the staged p rows in place to PReLU11(tr0), the only form they
+//       are read in.  (Measured and rejected in round 2, profiles/r4_s1_experiments.md: the conversion folded into the
+//       gather as max(p, r p), the rows passed through the producers' registers, conversion by the producers per commit
+//       group, conversion by the gather warpgroup per commit group, and a start-up phase offset between the pipelines.)
+//     * the gather warpgroup (thread per row) sums the <= 16 neighbour rows of its station out of shared memory (16-byte
+//       chunks are visited in a per-lane rotated order, so arbitrary rows are bank-conflict free), recovers tr0 of its
+//       own row, and writes the three 32-column A operands  [tr0 | mask0,1], [mean_sta | mask2,3], [mean_src | mask2,3]
 //       as 3xTF32 hi/lo parts straight into tensor memory;
 //     * the MMA warp runs  stage B [.. ] -> tr (60),  stage C tr -> [h_a | h_b | c_a | c_b] (90),  stage D PReLU(h) ->
 //       [v_a | v_b] (30)  as tcgen05.mma kind::tf32 (hi*hi + lo*hi + hi*lo), weights resident in shared memory in the
@@ -44,7 +45,6 @@ constexpr int WG_G0 = 4, WG_E0 = 12, WG_P0 = 20;     // gather (2 x 4 warps) / e
 constexpr int ROWS = GENIE_TILE_ROWS_MAX;            // staged p rows per tile; row ROWS is the zero row
 constexpr int NPIPE = 2;
 constexpr int P_THREADS = 64;                        // producer threads per pipeline (two warps)
-constexpr int S1_STAGGER_DEFAULT = 0;
 
 // shared memory map (bytes)
 constexpr int SB_P = 0;                              // [ROWS + 1][128 B]   staged rows (tile stations first, then halo)
@@ -74,6 +74,7 @@ struct Bars {
     uint64_t full[NPIPE], empty[NPIPE];
     uint64_t opA_full[NPIPE], opA_free[NPIPE];
     uint64_t d_full[NPIPE], aE_full[NPIPE], d_free[NPIPE];
+    uint64_t raw[NPIPE];           // copies landed (producers -> gather warpgroup, which converts the rows in place)
     uint32_t tmem_base;
 };
 static_assert(sizeof(Bars) <= 256, "barrier block");
@@ -150,7 +151,7 @@ __device__ __forceinline__ void store16_rows(const float (&v)[16], unsigned char
     __syncwarp();
 }
 
-// Epilogue-warpgroup half of the stage-B operands of one tile: [tr0 | mask0,1] (tr0 recovered from the staged PReLU12(tr0)
+// Epilogue-warpgroup half of the stage-B operands of one tile: [tr0 | mask0,1] (tr0 recovered from the staged PReLU11(tr0)
 // of the thread's own row) and [mean_src | mask2,3] (the thread's msrc row) -> tensor memory.  Returns the row's mask.
 __device__ __forceinline__ float4 s1_load_mask(const unsigned char* sb, int r, bool valid, bool packed) {
     float4 mk = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -217,8 +218,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                        float* __restrict__ vb, int S, int NT, const int32_t* __restrict__ tile_rows,
                        const int32_t* __restrict__ tile_meta, const uint16_t* __restrict__ tile_nbr,
                        const float* __restrict__ tile_invdeg, int64_t n_tiles, const float* __restrict__ edge_sta,
-                       const float* __restrict__ edge_src, long long* __restrict__ trace, int trace_tiles, int trace_start,
-                       int stagger) {
+                       const float* __restrict__ edge_src, long long* __restrict__ trace, int trace_tiles, int trace_start) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const bool packed_mask = mask == nullptr;
     const float* tcw = packed + T2_BASE;
@@ -242,7 +242,8 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
     }
     if (threadIdx.x == 0) {
         for (int b = 0; b < NPIPE; ++b) {
-            mbar_init(&bars->full[b], P_THREADS);     // producers: rows staged (and converted)
+            mbar_init(&bars->full[b], 128);           // gather warpgroup, after the in-place conversion
+            mbar_init(&bars->raw[b], P_THREADS);
             mbar_init(&bars->empty[b], 256);          // gather + epilogue warpgroups
             mbar_init(&bars->opA_full[b], 256);
             mbar_init(&bars->opA_free[b], 1);
@@ -273,10 +274,6 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
         constexpr int JMAX = (ROWS + 7) / 8;
         unsigned char* sbp = smem + SM_BUF + q * SB_SIZE;
         const uint32_t sb = smem_u32(sbp);
-        if (q == 1 && stagger > 0) {                   // start the second pipeline out of phase with the first
-            const long long t_go = clock64() + stagger;
-            while (clock64() < t_go) {}
-        }
         int64_t k = 0;
         for (int64_t t = blockIdx.x + (int64_t)q * gridDim.x; t < n_tiles; t += 2 * (int64_t)gridDim.x, ++k) {
             const int g = (int)(t / NT), T = (int)(t - (int64_t)g * NT);
@@ -298,18 +295,17 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                 const int r = rr + 8 * j;
                 if (r < n_own) cp_async16(sb + SB_MS + r * 128 + ((c ^ (r & 7)) << 4), msrc + (node0 + ids[j]) * 32 + c * 4);
             }
-            // mask rows: from the caller's Mask [P,4], or (packed) a compact copy of chunk 7 of the own p rows, whose
-            // channel 30 carries the four mask bits — thread-per-row readers get it without bank conflicts
-            if (packed_mask) {
-                if (id_m0 >= 0) cp_async16(sb + SB_MK + tid * 16, p + (node0 + id_m0) * 32 + 28);
-                if (id_m1 >= 0) cp_async16(sb + SB_MK + (tid + 64) * 16, p + (node0 + id_m1) * 32 + 28);
-            } else {
-                if (id_m0 >= 0) cp_async16(sb + SB_MK + tid * 16, mask + (node0 + id_m0) * 4);
-                if (id_m1 >= 0) cp_async16(sb + SB_MK + (tid + 64) * 16, mask + (node0 + id_m1) * 4);
+            {   // mask rows: from the caller's Mask [P,4], or (packed) a compact copy of chunk 7 of the own p rows, whose
+                // channel 30 carries the four mask bits — thread-per-row readers get it without bank conflicts
+                const float* mrow = packed_mask ? p + 28 : mask;
+                const int mld = packed_mask ? 32 : 4;
+                if (id_m0 >= 0) cp_async16(sb + SB_MK + tid * 16, mrow + (node0 + id_m0) * mld);
+                if (id_m1 >= 0) cp_async16(sb + SB_MK + (tid + 64) * 16, mrow + (node0 + id_m1) * mld);
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
-            mbar_arrive(&bars->full[q]);
+            mbar_arrive(&bars->raw[q]);
             if (tid == 0) S1_TRACE(18);
+
         }
     } else if (warp < NPIPE) {
         // ================================ MMA issuer of pipeline q ====================================================
@@ -407,6 +403,28 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
             const uint4* nb = reinterpret_cast<const uint4*>(tile_nbr + ((int64_t)T * 128 + r) * 16);
             const uint4 n0 = __ldg(nb), n1 = __ldg(nb + 1);
             const float invdeg = __ldg(tile_invdeg + T * 128 + r);
+            // ---- staged p rows -> PReLU11(tr0), in place: 16-byte chunk r & 7 of the rows (r >> 3) + 16 j, in batches whose
+            //      loads are all in flight before the first store ----------------------------------------------------------
+            mbar_wait(&bars->raw[q], (uint32_t)(k & 1));
+            {
+                const int n_rows = __ldg(tile_meta + 2 * T + 1);
+                unsigned char* cb = sb + SB_P + (r >> 3) * 128 + (r & 7) * 16;
+                constexpr int CB = 9;
+                static_assert((ROWS + 15) / 16 == 2 * CB, "conversion batches");
+#pragma unroll
+                for (int j0 = 0; j0 < 2 * CB; j0 += CB) {
+                    if ((r >> 3) + 16 * j0 >= n_rows) break;
+                    float4 v[CB];
+#pragma unroll
+                    for (int u = 0; u < CB; ++u) v[u] = *reinterpret_cast<const float4*>(cb + (j0 + u) * 16 * 128);
+#pragma unroll
+                    for (int u = 0; u < CB; ++u)
+                        if ((r >> 3) + 16 * (j0 + u) < n_rows)
+                            *reinterpret_cast<float4*>(cb + (j0 + u) * 16 * 128) = make_float4(
+                                prelu_f(v[u].x, r11), prelu_f(v[u].y, r11), prelu_f(v[u].z, r11), prelu_f(v[u].w, r11));
+                }
+            }
+            mbar_arrive(&bars->full[q]);
             mbar_wait(&bars->full[q], (uint32_t)(k & 1));
             if (r == 0) S1_TRACE(12);
             // ---- sum of the station neighbours' rows (16-byte chunk k ^ key of every row: conflict free) ------------------
@@ -416,23 +434,13 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
 #pragma unroll
                 for (int c = 0; c < 8; ++c) a2[c].lo = a2[c].hi = 0ull;
                 const uint32_t w[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
-                // PReLU11(tr0) from the staged p = PReLU12(tr0): max(p, r p) for r <= 1, min(p, r p) for r > 1 (both slopes are
-                // positive on this path, layout.h TCS_OK) — the values the in-place conversion used to produce, bit for bit
-#define S1_GATHER(OP)                                                                                           \
-    _Pragma("unroll") for (int j = 0; j < 16; ++j) {                                                            \
-        const uint32_t idx = (j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xffffu);                               \
-        const unsigned char* ra = sb + SB_P + idx * 128;                                                        \
-        _Pragma("unroll") for (int c = 0; c < 8; ++c) {                                                         \
-            const float4 v = *reinterpret_cast<const float4*>(ra + ((c ^ key) << 4));                           \
-            fadd4(a2[c], make_float4(OP(v.x, v.x * r11), OP(v.y, v.y * r11), OP(v.z, v.z * r11), OP(v.w, v.w * r11))); \
-        }                                                                                                       \
-    }
-                if (r11 <= 1.f) {
-                    S1_GATHER(fmaxf)
-                } else {
-                    S1_GATHER(fminf)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t idx = (j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xffffu);
+                    const unsigned char* ra = sb + SB_P + idx * 128;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) fadd4(a2[c], *reinterpret_cast<const float4*>(ra + ((c ^ key) << 4)));
                 }
-#undef S1_GATHER
 #pragma unroll
                 for (int c = 0; c < 8; ++c) acc[c] = to_float4(a2[c]);
             }
@@ -472,7 +480,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
         const int q = (warp - WG_E0) >> 2;
         const int r = ((warp - WG_E0) & 3) * 32 + lane;
         const uint32_t lane_base = tm + q * TM_PIPE + ((uint32_t)((warp & 3) * 32) << 16);
-        const float a1 = sc[TCS_A1], a21 = sc[TCS_A21], a22 = sc[TCS_A22], inv11 = sc[TCS_INV12];   // staged rows are PReLU12(tr0)
+        const float a1 = sc[TCS_A1], a21 = sc[TCS_A21], a22 = sc[TCS_A22], inv11 = sc[TCS_INV11];
         const int key = lane & 7;
         const unsigned char* sb = smem + SM_BUF + q * SB_SIZE;
         unsigned char* scr = smem + SM_SCR + (warp - WG_E0) * 2048;
@@ -645,17 +653,15 @@ int launch_da_layer1_s(const genie_plan* p, const float* packed, const float* pf
         attr_set.mark();
     }
     const int64_t grid = n_tiles < p->sm_count ? n_tiles : p->sm_count;
-    // initial phase offset (cycles) of the second tile pipeline; GENIE_S1_STAGGER overrides (development sweeps)
-    static const int stagger = [] { const char* e = getenv("GENIE_S1_STAGGER"); return e ? atoi(e) : S1_STAGGER_DEFAULT; }();
     TimedLaunch tl(KID_DA_LAYER1_S, st);
     if (p->edge_sta != nullptr)
         da_layer1_s_kernel<true><<<(unsigned)grid, S1_THREADS, SM_TOTAL, st>>>(
             packed, pfeat, msrc, mask, zc, va, vb, g.n_sta, g.n_sta_tiles, g.sta_tile_rows, g.sta_tile_meta, g.sta_tile_nbr,
-            g.sta_tile_invdeg, n_tiles, p->edge_sta, p->edge_src, g_s1_trace, g_s1_trace_tiles, g_s1_trace_start, stagger);
+            g.sta_tile_invdeg, n_tiles, p->edge_sta, p->edge_src, g_s1_trace, g_s1_trace_tiles, g_s1_trace_start);
     else
         da_layer1_s_kernel<false><<<(unsigned)grid, S1_THREADS, SM_TOTAL, st>>>(
             packed, pfeat, msrc, mask, zc, va, vb, g.n_sta, g.n_sta_tiles, g.sta_tile_rows, g.sta_tile_meta, g.sta_tile_nbr,
-            g.sta_tile_invdeg, n_tiles, nullptr, nullptr, g_s1_trace, g_s1_trace_tiles, g_s1_trace_start, stagger);
+            g.sta_tile_invdeg, n_tiles, nullptr, nullptr, g_s1_trace, g_s1_trace_tiles, g_s1_trace_start);
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;
 }
