@@ -347,7 +347,7 @@ class ShardedWorkload(object):
         return (hi - lo) * 5 * 8, d2h
 
 
-def closure_parity(wl, w, n_clusters=5, cluster=4):
+def closure_parity(wl, w, n_clusters=5, cluster=4, tol=1e-4):
     """Oracle check of one of the timed windows at FULL size (outside every timed region): the window's a1 inputs, x_latent
     and Bipartite_ReadIn rows of >= 16 sampled grid nodes against the CPU oracle run on their 2-hop source-graph closure
     (oracle/closure_check.py), and y / x of the timed call against the oracle's SpatialAggregation + heads on the full grid.
@@ -385,11 +385,54 @@ def closure_parity(wl, w, n_clusters=5, cluster=4):
                               float(m.TemporalAttention.scale_t))
     rep['y_rel'], rep['x_rel'] = cc.global_rel(y.cpu().numpy(), y_o), cc.global_rel(x.cpu().numpy(), x_o)
     rep['window'], rep['picks_in_window'], rep['seconds'] = int(w), int(hi - lo), round(time.time() - t_a, 1)
-    rep['tolerance'] = 1e-4
+    rep['tolerance'] = tol
     rep['fused_equals_two_step'] = fused_same      # genie_window_fwd vs extract_input + forward_fixed_source, bit for bit
-    rep['ok'] = bool(rep.get('time_bin_equal') and rep.get('mask_equal') and rep['max_rel'] < 1e-4 and
-                     rep['y_rel'] < 1e-4 and rep['x_rel'] < 1e-4 and fused_same)
+    rep['ok'] = bool(rep.get('time_bin_equal') and rep.get('mask_equal') and rep['max_rel'] < tol and
+                     rep['y_rel'] < tol and rep['x_rel'] < tol and fused_same)
     return rep
+
+
+def bf16_mode(wl, windows, W, K, use_graph, args):
+    """The SECOND mode (BASELINE.json configs[1]: bf16 inference): GENIE_STORAGE_BF16 keeps the gathered intermediate rows as
+    bf16 (fp32 arithmetic).  Timed like `value` (same windows, resident inputs); its error against the oracle (sampled
+    closure) and against the fp32 mode is reported beside it.  It does not satisfy, and is never used for, the 1e-4 parity
+    bar."""
+    import torch
+    from genie_b200 import capi
+    m = wl.model
+    y32, x32 = wl.runner.run(windows[W] * STEP_S)
+    y32, x32 = y32.clone(), x32.clone()
+    m.set_storage('bf16')
+    wl.runners(use_graph)
+    for w in windows[:W]:
+        wl.window_resident(w)
+    torch.cuda.synchronize()
+    capi.timing_enable(True)
+    capi.timing_collect(reset=True)
+    beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    beg.record()
+    for w in windows[W:W + K]:
+        wl.window_resident(w)
+    end.record()
+    torch.cuda.synchronize()
+    ms = beg.elapsed_time(end)
+    kt = capi.timing_collect(reset=True)
+    capi.timing_enable(False)
+    y16, x16 = wl.runner.run(windows[W] * STEP_S)
+    from oracle import closure_check as cc
+    out = {'value': K / (ms * 1e-3), 'ms_per_step': ms / K, 'unit': UNIT,
+           'algorithmic_bytes_per_node': 404.0,
+           'window_roofline_frac': 404.0 * wl.P / (ms / K * 1e-3) / 1e9 / _peaks()[0],
+           'kernels_ms_per_step': {k: round(v[0] / K, 4) for k, v in sorted(kt.items()) if v[1] > 0},
+           'y_rel_vs_fp32': cc.global_rel(y16.cpu().numpy(), y32.cpu().numpy()),
+           'x_rel_vs_fp32': cc.global_rel(x16.cpu().numpy(), x32.cpu().numpy())}
+    if not args.no_parity_check:
+        rep = closure_parity(wl, windows[W], tol=2e-2)
+        out['max_rel_vs_oracle'] = max(rep['max_rel'], rep['y_rel'], rep['x_rel'])
+        out['parity_check'] = rep
+    m.set_storage('fp32')
+    wl.runners(use_graph)
+    return out
 
 
 def run_genie(args):
@@ -561,6 +604,10 @@ def run_genie(args):
         }
         if not sharded and not args.no_parity_check:
             line['parity_check'] = closure_parity(wl, windows[W])          # the first timed window, against the CPU oracle
+        if not sharded and not args.no_bf16:
+            line['modes'] = {'fp32_parity': {'value': line['value'], 'ms_per_step': line['ms_per_step'],
+                                             'max_rel_vs_oracle': (line.get('parity_check') or {}).get('max_rel')},
+                             'bf16_storage': bf16_mode(wl, windows, W, K, use_graph, args)}
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_reference(args.workload, 5, 1, sample_nodes=2.0e6)[0]   # ~25 s of CPU work
         print(json.dumps(line), flush=True)
@@ -579,6 +626,7 @@ def main():
     ap.add_argument('--day-seconds', type=float, default=DAY_S)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-parity-check', action='store_true')
+    ap.add_argument('--no-bf16', action='store_true', help='skip the bf16-storage second mode')
     ap.add_argument('--graph', default='auto', choices=['auto', 'on', 'off'], help='replay each window as one CUDA graph')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'genie' else args.warmup

@@ -19,6 +19,7 @@ _lib = None
 GRAPH_CARTESIAN, GRAPH_EXPLICIT = 0, 1
 ABI_VERSION = 7
 EDGE_TERM_LD = 48           # GENIE_EDGE_TERM_LD
+STORAGE_FP32, STORAGE_BF16 = 0, 1
 
 c_f32p = ctypes.c_void_p   # device pointers are passed as opaque addresses
 
@@ -93,6 +94,7 @@ SIGNATURES = {
     'genie_plan_create': (ctypes.c_int, [ctypes.POINTER(GraphDesc), ctypes.POINTER(_P)]),
     'genie_plan_destroy': (None, [_P]),
     'genie_plan_workspace_bytes': (ctypes.c_size_t, [_P]),
+    'genie_plan_set_storage': (ctypes.c_int, [_P, ctypes.c_int32]),
     'genie_plan_set_edge_terms': (ctypes.c_int, [_P, _P, _P]),
     'genie_plan_set_init_terms': (ctypes.c_int, [_P, _P, _P]),
     'genie_frontend_packed_floats': (ctypes.c_size_t, []),

@@ -81,11 +81,13 @@ Workspace carve_workspace(const genie_plan* p, void* base) {
         off += align_up(n_floats * sizeof(float), 256);
         return ptr;
     };
-    w.tr0 = take(P * LD_TR0);
-    w.msrc = split_supported(p) ? take(P * LD_TR0) : nullptr;
+    // bf16 storage (genie_plan_set_storage): tr0 / msrc / vb (and mean_src(vb), which re-uses tr0) hold bf16 rows
+    const size_t half = p->storage == GENIE_STORAGE_BF16 ? 2 : 1;
+    w.tr0 = take(P * LD_TR0 / half);
+    w.msrc = split_supported(p) ? take(P * LD_TR0 / half) : nullptr;
     w.zc = take(P * LD_ZC);
     w.va = take(P * LD_V);
-    w.vb = take(P * LD_V);
+    w.vb = take(P * LD_V / half);
     w.xg = take(G * 32);
     w.r = take(G * 16);
     w.px = take(G * 32);
@@ -104,13 +106,20 @@ Workspace carve_workspace(const genie_plan* p, void* base) {
 static int launch_da_layers01(const genie_plan* plan, const float* packed, const float* slice, const float* mask,
                               const Workspace& w, cudaStream_t st) {
     const bool split = split_supported(plan);
+    if (plan->storage == GENIE_STORAGE_BF16) {
+        // bf16 rows exist only on the split tensor-core path (the caller checked the PReLU slopes, layout.h TCS_OK)
+        int rc;
+        if ((rc = launch_da_init(plan, packed, slice, mask, w.tr0, true, st))) return rc;
+        if ((rc = launch_src_mean(plan, 32, w.tr0, w.msrc, nullptr, st, plan->storage))) return rc;
+        return launch_da_layer1_s(plan, packed, w.tr0, w.msrc, mask, w.zc, w.va, w.vb, st);
+    }
     // the edge-feature terms are implemented in the split and the generic kernels, not in the one-pass tensor-core kernel
     const bool tc = split || (da_tc_supported(plan) && plan->edge_sta == nullptr);
     int rc;
     if ((rc = launch_da_init(plan, packed, slice, mask, w.tr0, tc, st))) return rc;
     if (split) {
         const float* gate = packed + TC_BASE + TC_SCAL + TCS_OK;
-        if ((rc = launch_src_mean(plan, 32, w.tr0, w.msrc, gate, st))) return rc;
+        if ((rc = launch_src_mean(plan, 32, w.tr0, w.msrc, gate, st, plan->storage))) return rc;
         if ((rc = launch_da_layer1_s(plan, packed, w.tr0, w.msrc, mask, w.zc, w.va, w.vb, st))) return rc;
     } else if (tc) {
         if ((rc = launch_da_layer1_tc(plan, packed, w.tr0, mask, w.zc, w.va, w.vb, st))) return rc;
@@ -125,8 +134,9 @@ static int launch_da_layers01_window(const genie_plan* plan, const float* packed
     int rc;
     if ((rc = launch_da_init_fused(plan, packed, ws, ind_use, trv, series, slice_out, mask_out, w.tr0, true, st))) return rc;
     const float* gate = packed + TC_BASE + TC_SCAL + TCS_OK;
-    if ((rc = launch_src_mean(plan, 32, w.tr0, w.msrc, gate, st))) return rc;
+    if ((rc = launch_src_mean(plan, 32, w.tr0, w.msrc, gate, st, plan->storage))) return rc;
     if ((rc = launch_da_layer1_s(plan, packed, w.tr0, w.msrc, nullptr, w.zc, w.va, w.vb, st))) return rc;
+    if (plan->storage == GENIE_STORAGE_BF16) return GENIE_OK;       // no generic fallback on bf16 rows
     return launch_da_layer1(plan, packed, w.tr0, nullptr, w.zc, w.va, w.vb, true, st);
 }
 
@@ -136,9 +146,14 @@ static int launch_da_layer2(const genie_plan* plan, const float* packed, const W
     int rc;
     if (split_supported(plan) && plan->g.n_sta_tiles <= 32 && edge_attr != nullptr) {
         float* m2 = w.tr0;                                 // layer-0 features are dead: re-use their buffer
-        if ((rc = launch_src_mean(plan, 16, w.vb, m2, nullptr, st))) return rc;
+        if ((rc = launch_src_mean(plan, 16, w.vb, m2, nullptr, st, plan->storage))) return rc;
         return launch_da_layer2_s(plan, packed, w.zc, w.va, m2, mask, edge_attr, latent_out, readin_out ? readin_out : w.r,
                                   readin_out ? ld_r : 16, st);
+    }
+    if (plan->storage == GENIE_STORAGE_BF16) {
+        set_error("bf16 storage: layer 2 runs only fused with the read-in on a plan with tiling tables (genie_frontend_fwd / "
+                  "genie_window_fwd)");
+        return GENIE_ERR_UNSUPPORTED;
     }
     if (readin_out) {
         GENIE_CUDA_CHECK(cudaMemsetAsync(w.xg, 0, (size_t)plan->g.n_grid * 32 * sizeof(float), st));
@@ -213,6 +228,19 @@ int genie_plan_set_init_terms(genie_plan_t* plan, const float* init_sta_dev, con
     return GENIE_OK;
 }
 
+int genie_plan_set_storage(genie_plan_t* plan, int32_t storage) {
+    if (!plan || (storage != GENIE_STORAGE_FP32 && storage != GENIE_STORAGE_BF16)) {
+        set_error("genie_plan_set_storage: bad argument");
+        return GENIE_ERR_INVALID;
+    }
+    if (storage == GENIE_STORAGE_BF16 && (!split_supported(plan) || plan->g.n_sta_tiles > 32)) {
+        set_error("genie_plan_set_storage: bf16 storage needs a CARTESIAN plan with tiling tables");
+        return GENIE_ERR_UNSUPPORTED;
+    }
+    plan->storage = storage;
+    return GENIE_OK;
+}
+
 int genie_debug_trace(int64_t* trace_dev, int tiles) {
     set_s1_trace(reinterpret_cast<long long*>(trace_dev), trace_dev ? tiles : 0);
     return GENIE_OK;
@@ -258,6 +286,7 @@ int genie_plan_create(const genie_graph_desc_t* d, genie_plan_t** out) {
     }
     p->g = *d;
     p->n_edges_grid = -1;
+    p->storage = GENIE_STORAGE_FP32;
     p->cslot = (int)(g_plan_counter.fetch_add(1, std::memory_order_relaxed) % GENIE_CSLOTS);
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -518,7 +547,7 @@ int genie_workspace_region(const genie_plan_t* plan, void* workspace_dev, int32_
     }
     Workspace w = carve_workspace(plan, workspace_dev);
     *ptr_out = w.vb;
-    *bytes_out = (size_t)plan->g.n_prod * LD_V * sizeof(float);
+    *bytes_out = (size_t)plan->g.n_prod * LD_V * (plan->storage == GENIE_STORAGE_BF16 ? 2 : sizeof(float));
     return GENIE_OK;
 }
 

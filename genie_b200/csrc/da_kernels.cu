@@ -16,6 +16,7 @@
 // broadcast from shared memory.
 #include "common.cuh"
 #include "gather.cuh"
+#include "bf16.cuh"
 #include "input.cuh"
 
 using namespace gl;
@@ -48,7 +49,8 @@ struct InitInputs {
     float* mask_out;             // FUSED, optional
 };
 
-template <int CSLOT, bool FUSED>
+// BF16: the row is stored as 32 bf16 (64 bytes; genie_plan_set_storage) instead of 32 floats.
+template <int CSLOT, bool FUSED, bool BF16>
 __global__ void __launch_bounds__(K1_THREADS) da_init_kernel(const float* __restrict__ packed, const InitInputs in,
                                                              float* __restrict__ tr0, int64_t P, int tc_plan,
                                                              const float* __restrict__ init_sta,
@@ -122,23 +124,39 @@ __global__ void __launch_bounds__(K1_THREADS) da_init_kernel(const float* __rest
     for (int o = 0; o < 15; ++o) unpack2(acc2[o], acc[2 * o], acc[2 * o + 1]);
     // stage the row in shared memory (16-byte chunks XOR-swizzled by the row index: conflict-free), then write the
     // tile out as one contiguous, fully coalesced block.
-    float4* srow = reinterpret_cast<float4*>(sOut + n * LD_TR0);
+    float row[32];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        float4 v;
-        v.x = prelu(prelu(acc[(4 * c + 0) < 30 ? (4 * c + 0) : 0], a0), a12);
-        v.y = prelu(prelu(acc[(4 * c + 1) < 30 ? (4 * c + 1) : 0], a0), a12);
-        v.z = (4 * c + 2) < 30 ? prelu(prelu(acc[(4 * c + 2) < 30 ? (4 * c + 2) : 0], a0), a12) : mpack;   // channel 30
-        v.w = (4 * c + 3) < 30 ? prelu(prelu(acc[(4 * c + 3) < 30 ? (4 * c + 3) : 0], a0), a12) : 0.f;
-        srow[c ^ (n & 7)] = v;
-    }
-    __syncthreads();
-    float4* dst = reinterpret_cast<float4*>(tr0 + i0 * LD_TR0);
+    for (int o = 0; o < 30; ++o) row[o] = prelu(prelu(acc[o], a0), a12);
+    row[30] = mpack;                                                                                   // channel 30
+    row[31] = 0.f;
+    if (BF16) {
+        uint4* srow = reinterpret_cast<uint4*>(sOut) + n * 4;
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        const int f = it * K1_THREADS + threadIdx.x;   // float4 index inside the tile
-        const int row = f >> 3, pos = f & 7;
-        if (i0 + row < P) dst[row * 8 + (pos ^ (row & 7))] = reinterpret_cast<const float4*>(sOut)[f];
+        for (int c = 0; c < 4; ++c) {
+            const float v8[8] = {row[8 * c], row[8 * c + 1], row[8 * c + 2], row[8 * c + 3],
+                                 row[8 * c + 4], row[8 * c + 5], row[8 * c + 6], row[8 * c + 7]};
+            srow[c ^ ((n >> 1) & 3)] = bf16_pack8(v8);
+        }
+        __syncthreads();
+        uint4* dst = reinterpret_cast<uint4*>(tr0) + i0 * 4;          // bf16 rows: 4 chunks of 16 bytes
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int f = it * K1_THREADS + threadIdx.x;
+            const int r = f >> 2, pos = f & 3;
+            if (i0 + r < P) dst[r * 4 + (pos ^ ((r >> 1) & 3))] = reinterpret_cast<const uint4*>(sOut)[f];
+        }
+    } else {
+        float4* srow = reinterpret_cast<float4*>(sOut + n * LD_TR0);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) srow[c ^ (n & 7)] = make_float4(row[4 * c], row[4 * c + 1], row[4 * c + 2], row[4 * c + 3]);
+        __syncthreads();
+        float4* dst = reinterpret_cast<float4*>(tr0 + i0 * LD_TR0);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int f = it * K1_THREADS + threadIdx.x;   // float4 index inside the tile
+            const int r = f >> 3, pos = f & 7;
+            if (i0 + r < P) dst[r * 8 + (pos ^ (r & 7))] = reinterpret_cast<const float4*>(sOut)[f];
+        }
     }
 }
 
@@ -405,7 +423,7 @@ __global__ void __launch_bounds__(128) readin_finalize_kernel(const float* __res
 // --------------------------------------------------------------------------------------------------------------------
 // launchers
 // --------------------------------------------------------------------------------------------------------------------
-template <bool FUSED>
+template <bool FUSED, bool BF16>
 static int launch_da_init_t(const genie_plan* p, const float* packed, const InitInputs& in, float* tr0, bool tc_plan,
                             cudaStream_t st) {
     const int64_t P = p->g.n_prod;
@@ -416,8 +434,8 @@ static int launch_da_init_t(const genie_plan* p, const float* packed, const Init
     TimedLaunch tl(KID_DA_INIT, st);
 #define GENIE_INIT_CASE(C)                                                                                          \
     case C:                                                                                                         \
-        da_init_kernel<C, FUSED><<<(unsigned)blocks, K1_THREADS, 0, st>>>(packed, in, tr0, P, tc_plan ? 1 : 0,      \
-                                                                          p->init_sta, p->init_src, p->g.n_sta);    \
+        da_init_kernel<C, FUSED, BF16><<<(unsigned)blocks, K1_THREADS, 0, st>>>(packed, in, tr0, P, tc_plan ? 1 : 0, \
+                                                                                p->init_sta, p->init_src, p->g.n_sta); \
         break;
     switch (p->cslot) {
         GENIE_INIT_CASE(0) GENIE_INIT_CASE(1) GENIE_INIT_CASE(2) GENIE_INIT_CASE(3)
@@ -433,7 +451,8 @@ int launch_da_init(const genie_plan* p, const float* packed, const float* slice,
     InitInputs in = {};
     in.slice = slice;
     in.mask = mask;
-    return launch_da_init_t<false>(p, packed, in, tr0, tc_plan, st);
+    return p->storage == GENIE_STORAGE_BF16 ? launch_da_init_t<false, true>(p, packed, in, tr0, tc_plan, st)
+                                            : launch_da_init_t<false, false>(p, packed, in, tr0, tc_plan, st);
 }
 
 // a1 fused into layer 0 (genie_window_fwd): CARTESIAN plans with P < 2^31.
@@ -451,7 +470,8 @@ int launch_da_init_fused(const genie_plan* p, const float* packed, const WindowP
     in.series = series;
     in.slice_out = slice_out;
     in.mask_out = slice_out ? mask_out : nullptr;
-    return launch_da_init_t<true>(p, packed, in, tr0, tc_plan, st);
+    return p->storage == GENIE_STORAGE_BF16 ? launch_da_init_t<true, true>(p, packed, in, tr0, tc_plan, st)
+                                            : launch_da_init_t<true, false>(p, packed, in, tr0, tc_plan, st);
 }
 
 int launch_da_layer1(const genie_plan* p, const float* packed, const float* tr0, const float* mask, float* zc, float* va,

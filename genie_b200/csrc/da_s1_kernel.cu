@@ -29,6 +29,7 @@
 //     * the epilogue warpgroup applies the activations between the stages and stores c (zc) and v_a / v_b.
 // DRAM sees p, msrc and mask once (the tiles of one grid node are consecutive, its 128 KB block stays in L2); nothing is
 // gathered from L2.  All hand-offs are mbarriers with bounded spins (a protocol bug traps, it never hangs).
+#include "bf16.cuh"
 #include "common.cuh"
 #include "input.cuh"
 #include "tc_common.cuh"
@@ -46,18 +47,27 @@ constexpr int ROWS = GENIE_TILE_ROWS_MAX;            // staged p rows per tile; 
 constexpr int NPIPE = 2;
 constexpr int P_THREADS = 64;                        // producer threads per pipeline (two warps)
 
-// shared memory map (bytes)
-constexpr int SB_P = 0;                              // [ROWS + 1][128 B]   staged rows (tile stations first, then halo)
-constexpr int SB_MS = SB_P + (ROWS + 1) * 128;       // [128][128 B]        msrc rows, 16-byte chunks XOR-swizzled by row
-constexpr int SB_MK = SB_MS + 128 * 128;             // [128][16 B]         mask rows
-constexpr int SB_SIZE = SB_MK + 128 * 16;
+// shared memory map (bytes).  Row format of the staged tensors: fp32 rows (128 B; ONE staging buffer per pipeline, shared
+// memory is full) or the bf16 rows of the fast storage mode (genie_plan_set_storage; 64 B, TWO staging buffers per pipeline:
+// the fill of a pipeline's next tile overlaps the gather of its current one — the producer -> convert -> gather -> release
+// loop of a single buffer is what bounds the fp32 kernel, profiles/r4_s1_experiments.md).
 constexpr int SM_W = 0;                              // tensor-core weight blob (layout.h T2_*)
 constexpr int SM_BUF = (T2_FLOATS * 4 + 1023) / 1024 * 1024;
-constexpr int SM_BAR = SM_BUF + NPIPE * SB_SIZE;
-constexpr int SM_SCR = SM_BAR + 256;                 // [8 epilogue warps][32 rows][64 B] store-transposition scratch
-constexpr int SM_TOTAL = SM_SCR + 8 * 2048;
-static_assert(SB_SIZE % 16 == 0 && SM_BUF % 1024 == 0 && SM_BAR % 8 == 0, "alignment");
-static_assert(SM_TOTAL <= 232448, "shared memory budget");
+template <bool BF16>
+struct Fmt {
+    static constexpr int RB = BF16 ? 64 : 128;       // bytes of a staged feature row
+    static constexpr int CPR = RB / 16;              // 16-byte chunks per row
+    static constexpr int NBUF = BF16 ? 2 : 1;        // staging buffers per pipeline
+    static constexpr int SB_P = 0;                   // [ROWS + 1][RB]   staged rows (tile stations first, then halo)
+    static constexpr int SB_MS = SB_P + (ROWS + 1) * RB;   // [128][RB]    msrc rows, 16-byte chunks XOR-swizzled by row
+    static constexpr int SB_MK = SB_MS + 128 * RB;   // [128][16 B]      mask rows
+    static constexpr int SB_SIZE = SB_MK + 128 * 16;
+    static constexpr int SM_BAR = SM_BUF + NPIPE * NBUF * SB_SIZE;
+    static constexpr int SM_SCR = SM_BAR + 256;      // [8 epilogue warps][32 rows][64 B] store-transposition scratch
+    static constexpr int SM_TOTAL = SM_SCR + 8 * 2048;
+    static_assert(SB_SIZE % 16 == 0 && SM_BUF % 1024 == 0 && SM_BAR % 8 == 0, "alignment");
+    static_assert(SM_TOTAL <= 232448, "shared memory budget");
+};
 
 // tensor memory map (columns, relative to the pipeline's 256-column block)
 constexpr int TM_OWN_HI = 0, TM_OWN_LO = 32;         // [tr0(30) | mask0 mask1], lo part [.. | 1 1] (bias of stage B)
@@ -71,10 +81,10 @@ constexpr int TM_PIPE = 256;
 constexpr int TM_COLS = 512;
 
 struct Bars {
-    uint64_t full[NPIPE], empty[NPIPE];
+    uint64_t full[NPIPE][2], empty[NPIPE][2];      // per staging buffer
     uint64_t opA_full[NPIPE], opA_free[NPIPE];
     uint64_t d_full[NPIPE], aE_full[NPIPE], d_free[NPIPE];
-    uint64_t raw[NPIPE];           // copies landed (producers -> gather warpgroup, which converts the rows in place)
+    uint64_t raw[NPIPE][2];        // copies landed (producers -> gather warpgroup, which converts the rows in place)
     uint32_t tmem_base;
 };
 static_assert(sizeof(Bars) <= 256, "barrier block");
@@ -151,27 +161,113 @@ __device__ __forceinline__ void store16_rows(const float (&v)[16], unsigned char
     __syncwarp();
 }
 
-// Epilogue-warpgroup half of the stage-B operands of one tile: [tr0 | mask0,1] (tr0 recovered from the staged PReLU11(tr0)
-// of the thread's own row) and [mean_src | mask2,3] (the thread's msrc row) -> tensor memory.  Returns the row's mask.
+// bf16 variant: 16 floats -> 32-byte row pieces of [P][16] bf16 rows, two lanes per row, 16 rows per store instruction.
+//   sid2[j] = station id of row (lane >> 1) + 16 j of the warp's block, or -1.
+__device__ __forceinline__ void store16_rows_bf16(const float (&v)[16], unsigned char* scr, int lane, const int (&sid2)[2],
+                                                  float* __restrict__ dst, int64_t node0) {
+    const float lo8[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
+    const float hi8[8] = {v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]};
+    const int sw = (lane >> 2) & 1;
+    *reinterpret_cast<uint4*>(scr + lane * 32 + ((0 ^ sw) << 4)) = bf16_pack8(lo8);
+    *reinterpret_cast<uint4*>(scr + lane * 32 + ((1 ^ sw) << 4)) = bf16_pack8(hi8);
+    __syncwarp();
+    const int chunk = lane & 1;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int row = (lane >> 1) + 16 * j;
+        const uint4 x = *reinterpret_cast<const uint4*>(scr + row * 32 + ((chunk ^ ((row >> 2) & 1)) << 4));
+        if (sid2[j] >= 0) __stcs(reinterpret_cast<uint4*>(dst) + (node0 + sid2[j]) * 2 + chunk, x);
+    }
+    __syncwarp();
+}
+
+// v[k][0..7] holds the 8 channels of 16-byte chunk (k ^ key) of a bf16 row; afterwards v[k] holds chunk k.
+__device__ __forceinline__ void unrotate4x8(float (&v)[4][8], int key) {
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        const bool sw = (key >> b) & 1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if ((k >> b) & 1) continue;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float a = v[k][e], c = v[k | (1 << b)][e];
+                v[k][e] = sw ? c : a;
+                v[k | (1 << b)][e] = sw ? a : c;
+            }
+        }
+    }
+}
+
+// The row's four mask values: the caller's Mask row, or (packed) channel 30 of the own p row, of which the producers stage a
+// compact copy of the last 16-byte chunk (fp32: channels 28-31, bf16: channels 24-31).
+template <bool BF16>
 __device__ __forceinline__ float4 s1_load_mask(const unsigned char* sb, int r, bool valid, bool packed) {
     float4 mk = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) {
-        mk = *reinterpret_cast<const float4*>(sb + SB_MK + r * 16);
-        if (packed) mk = unpack_mask(mk.z);       // chunk 7 of the own p row: channel 30 = the four mask bits
+        mk = *reinterpret_cast<const float4*>(sb + Fmt<BF16>::SB_MK + r * 16);
+        if (packed) mk = unpack_mask(BF16 ? bf16_lo(__float_as_uint(mk.w)) : mk.z);
     }
     return mk;
 }
 
+// Epilogue-warpgroup half of the stage-B operands of one tile: [tr0 | mask0,1] (tr0 recovered from the staged PReLU11(tr0)
+// of the thread's own row) and [mean_src | mask2,3] (the thread's msrc row) -> tensor memory.  Returns the row's mask.
+
+template <bool BF16>
 __device__ __forceinline__ float4 s1_own_operands(const unsigned char* sb, int r, bool valid, int key, float inv11,
                                                   uint32_t lane_base, bool packed) {
-    const float4 mk = s1_load_mask(sb, r, valid, packed);
+    using F = Fmt<BF16>;
+    const float4 mk = s1_load_mask<BF16>(sb, r, valid, packed);
     float a[16];
+    if (BF16) {
+        // 64-byte rows: four chunks of 8 channels; own row in the per-lane rotated order (key = lane & 3), msrc row swizzled
+        // by (row >> 1) & 3 — conflict free, static registers
+        float own[4][8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint4 u = make_uint4(0u, 0u, 0u, 0u);
+            if (valid) u = *reinterpret_cast<const uint4*>(sb + F::SB_P + r * 64 + ((c ^ key) << 4));
+            bf16_unpack8(u, own[c]);
+        }
+        unrotate4x8(own, key);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = prelu_f(own[2 * half + (i >> 3)][i & 7], inv11);
+            if (half) {
+                a[14] = mk.x;
+                a[15] = mk.y;
+                st_split16_bias(lane_base + TM_OWN_HI + 16, lane_base + TM_OWN_LO + 16, a);      // bias of stage B
+            } else {
+                st_split16(lane_base + TM_OWN_HI, lane_base + TM_OWN_LO, a);
+            }
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int u2 = 0; u2 < 2; ++u2) {
+                uint4 u = make_uint4(0u, 0u, 0u, 0u);
+                if (valid) u = *reinterpret_cast<const uint4*>(sb + F::SB_MS + r * 64 + (((2 * half + u2) ^ ((r >> 1) & 3)) << 4));
+                float f[8];
+                bf16_unpack8(u, f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a[8 * u2 + e] = f[e];
+            }
+            if (half) {
+                a[14] = mk.z;
+                a[15] = mk.w;
+            }
+            st_split16(lane_base + TM_SRC_HI + 16 * half, lane_base + TM_SRC_LO + 16 * half, a);
+        }
+        return mk;
+    }
     {
         float4 own[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) own[c] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid) {
-            const unsigned char* ra = sb + SB_P + r * 128;
+            const unsigned char* ra = sb + F::SB_P + r * 128;
 #pragma unroll
             for (int c = 0; c < 8; ++c) own[c] = *reinterpret_cast<const float4*>(ra + ((c ^ key) << 4));
         }
@@ -199,7 +295,7 @@ __device__ __forceinline__ float4 s1_own_operands(const unsigned char* sb, int r
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) v = *reinterpret_cast<const float4*>(sb + SB_MS + r * 128 + (((4 * half + u) ^ (r & 7)) << 4));
+            if (valid) v = *reinterpret_cast<const float4*>(sb + F::SB_MS + r * 128 + (((4 * half + u) ^ (r & 7)) << 4));
             a[4 * u] = v.x; a[4 * u + 1] = v.y; a[4 * u + 2] = v.z; a[4 * u + 3] = v.w;
         }
         if (half) {
@@ -211,7 +307,7 @@ __device__ __forceinline__ float4 s1_own_operands(const unsigned char* sb, int r
     return mk;
 }
 
-template <bool EDGE>
+template <bool EDGE, bool BF16>
 __global__ void __launch_bounds__(S1_THREADS, 1)
     da_layer1_s_kernel(const float* __restrict__ packed, const float* __restrict__ p, const float* __restrict__ msrc,
                        const float* __restrict__ mask, float* __restrict__ zc, float* __restrict__ va,
@@ -220,12 +316,14 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                        const float* __restrict__ tile_invdeg, int64_t n_tiles, const float* __restrict__ edge_sta,
                        const float* __restrict__ edge_src, long long* __restrict__ trace, int trace_tiles, int trace_start) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    using F = Fmt<BF16>;
+    constexpr int NBUF = F::NBUF;
     const bool packed_mask = mask == nullptr;
     const float* tcw = packed + T2_BASE;
     if (tcw[T2_SCAL + TCS_OK] == 0.f) return;   // slopes not eligible: the generic kernels run instead (uniform exit)
 
     float* sW = reinterpret_cast<float*>(smem + SM_W);
-    Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
+    Bars* bars = reinterpret_cast<Bars*>(smem + F::SM_BAR);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // ---- one-time set-up ------------------------------------------------------------------------------------------------
@@ -233,18 +331,20 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
         const float4* src = reinterpret_cast<const float4*>(tcw);
         float4* dst = reinterpret_cast<float4*>(sW);
         for (int i = threadIdx.x; i < T2_FLOATS / 4; i += S1_THREADS) dst[i] = src[i];
-        // the zero row of both buffers (padding target of the neighbour table)
-        if (threadIdx.x < NPIPE * 8) {
-            const int b = threadIdx.x >> 3, c = threadIdx.x & 7;
-            *reinterpret_cast<float4*>(smem + SM_BUF + b * SB_SIZE + SB_P + ROWS * 128 + c * 16) =
+        // the zero row of every staging buffer (padding target of the neighbour table)
+        if (threadIdx.x < NPIPE * NBUF * F::CPR) {
+            const int b = threadIdx.x / F::CPR, c = threadIdx.x % F::CPR;
+            *reinterpret_cast<float4*>(smem + SM_BUF + b * F::SB_SIZE + F::SB_P + ROWS * F::RB + c * 16) =
                 make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
     if (threadIdx.x == 0) {
         for (int b = 0; b < NPIPE; ++b) {
-            mbar_init(&bars->full[b], 128);           // gather warpgroup, after the in-place conversion
-            mbar_init(&bars->raw[b], P_THREADS);
-            mbar_init(&bars->empty[b], 256);          // gather + epilogue warpgroups
+            for (int u = 0; u < 2; ++u) {
+                mbar_init(&bars->full[b][u], 128);    // gather warpgroup, after the in-place conversion
+                mbar_init(&bars->raw[b][u], P_THREADS);
+                mbar_init(&bars->empty[b][u], 256);   // gather + epilogue warpgroups
+            }
             mbar_init(&bars->opA_full[b], 256);
             mbar_init(&bars->opA_free[b], 1);
             mbar_init(&bars->d_full[b], 1);
@@ -266,44 +366,49 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
 
     if (warp >= WG_P0) {
         // ================================ producers of pipeline q: row gather ==========================================
-        // Thread `tid` owns the 16-byte chunk c = tid & 7 of the staged rows rr + 8 j (rr = tid >> 3).  msrc / mask rows go by
-        // cp.async; the p rows pass through registers and are stored as PReLU11(tr0) (they are only ever read in that form).
+        // Thread `tid` owns the 16-byte chunk c of the staged rows rr + RPP j (fp32 rows: c = tid & 7, rr = tid >> 3; bf16
+        // rows: c = tid & 3, rr = tid >> 2); everything goes by cp.async.
         const int q = (warp - WG_P0) >> 1;
         const int tid = threadIdx.x - (WG_P0 + 2 * q) * 32;
-        const int rr = tid >> 3, c = tid & 7;
-        constexpr int JMAX = (ROWS + 7) / 8;
-        unsigned char* sbp = smem + SM_BUF + q * SB_SIZE;
-        const uint32_t sb = smem_u32(sbp);
+        constexpr int CPR = F::CPR, RPP = P_THREADS / CPR;         // chunks per row; rows per pass of the 64 threads (8 / 16)
+        const int rr = tid / CPR, c = tid % CPR;
+        constexpr int JMAX = (ROWS + RPP - 1) / RPP, JOWN = 128 / RPP;
+        const unsigned char* pb = reinterpret_cast<const unsigned char*>(p);
+        const unsigned char* mb = reinterpret_cast<const unsigned char*>(msrc);
         int64_t k = 0;
         for (int64_t t = blockIdx.x + (int64_t)q * gridDim.x; t < n_tiles; t += 2 * (int64_t)gridDim.x, ++k) {
+            const int bi = (int)(k % NBUF);
+            const uint32_t n = (uint32_t)(k / NBUF);
+            const uint32_t sb = smem_u32(smem + SM_BUF + (q * NBUF + bi) * F::SB_SIZE);
             const int g = (int)(t / NT), T = (int)(t - (int64_t)g * NT);
             const int n_own = __ldg(tile_meta + 2 * T), n_rows = __ldg(tile_meta + 2 * T + 1);
             const int32_t* rows = tile_rows + (int64_t)T * ROWS;
             int ids[JMAX];
 #pragma unroll
-            for (int j = 0; j < JMAX; ++j) ids[j] = (rr + 8 * j) < n_rows ? __ldg(rows + rr + 8 * j) : -1;
+            for (int j = 0; j < JMAX; ++j) ids[j] = (rr + RPP * j) < n_rows ? __ldg(rows + rr + RPP * j) : -1;
             const int id_m0 = tid < n_own ? __ldg(rows + tid) : -1;
             const int id_m1 = tid + 64 < n_own ? __ldg(rows + tid + 64) : -1;
-            if (k > 0) mbar_wait(&bars->empty[q], (uint32_t)((k - 1) & 1));
+            if (n > 0) mbar_wait(&bars->empty[q][bi], (n - 1) & 1);
             if (tid == 0) S1_TRACE(17);
             const int64_t node0 = (int64_t)g * S;
 #pragma unroll
             for (int j = 0; j < JMAX; ++j)
-                if (ids[j] >= 0) cp_async16(sb + SB_P + (rr + 8 * j) * 128 + c * 16, p + (node0 + ids[j]) * 32 + c * 4);
+                if (ids[j] >= 0) cp_async16(sb + F::SB_P + (rr + RPP * j) * F::RB + c * 16, pb + (node0 + ids[j]) * F::RB + c * 16);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int r = rr + 8 * j;
-                if (r < n_own) cp_async16(sb + SB_MS + r * 128 + ((c ^ (r & 7)) << 4), msrc + (node0 + ids[j]) * 32 + c * 4);
+            for (int j = 0; j < JOWN; ++j) {
+                const int r = rr + RPP * j;
+                const int sw = BF16 ? ((r >> 1) & 3) : (r & 7);
+                if (r < n_own) cp_async16(sb + F::SB_MS + r * F::RB + ((c ^ sw) << 4), mb + (node0 + ids[j]) * F::RB + c * 16);
             }
-            {   // mask rows: from the caller's Mask [P,4], or (packed) a compact copy of chunk 7 of the own p rows, whose
+            {   // mask rows: from the caller's Mask [P,4], or (packed) a compact copy of the last chunk of the own p rows, whose
                 // channel 30 carries the four mask bits — thread-per-row readers get it without bank conflicts
-                const float* mrow = packed_mask ? p + 28 : mask;
-                const int mld = packed_mask ? 32 : 4;
-                if (id_m0 >= 0) cp_async16(sb + SB_MK + tid * 16, mrow + (node0 + id_m0) * mld);
-                if (id_m1 >= 0) cp_async16(sb + SB_MK + (tid + 64) * 16, mrow + (node0 + id_m1) * mld);
+                const unsigned char* mrow = packed_mask ? pb + (F::RB - 16) : reinterpret_cast<const unsigned char*>(mask);
+                const int mld = packed_mask ? F::RB : 16;
+                if (id_m0 >= 0) cp_async16(sb + F::SB_MK + tid * 16, mrow + (node0 + id_m0) * mld);
+                if (id_m1 >= 0) cp_async16(sb + F::SB_MK + (tid + 64) * 16, mrow + (node0 + id_m1) * mld);
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
-            mbar_arrive(&bars->raw[q]);
+            mbar_arrive(&bars->raw[q][bi]);
             if (tid == 0) S1_TRACE(18);
 
         }
@@ -392,11 +497,13 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
         const int q = (warp - WG_G0) >> 2;
         const int r = ((warp - WG_G0) & 3) * 32 + lane;
         const uint32_t lane_base = tm + q * TM_PIPE + ((uint32_t)((warp & 3) * 32) << 16);
-        const int key = lane & 7;
+        const int key = lane & (F::CPR - 1);
         const float r11 = sc[TCS_R11];
-        unsigned char* sb = smem + SM_BUF + q * SB_SIZE;
         int64_t k = 0;
         for (int64_t t = blockIdx.x + (int64_t)q * gridDim.x; t < n_tiles; t += 2 * (int64_t)gridDim.x, ++k) {
+            const int bi = (int)(k % NBUF);
+            const uint32_t n = (uint32_t)(k / NBUF);
+            unsigned char* sb = smem + SM_BUF + (q * NBUF + bi) * F::SB_SIZE;
             const int T = (int)(t % NT);
             const int n_own = __ldg(tile_meta + 2 * T);
             // neighbour table of this row (staged-row indices; padding = the zero row) and 1 / degree
@@ -405,10 +512,26 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
             const float invdeg = __ldg(tile_invdeg + T * 128 + r);
             // ---- staged p rows -> PReLU11(tr0), in place: 16-byte chunk r & 7 of the rows (r >> 3) + 16 j, in batches whose
             //      loads are all in flight before the first store ----------------------------------------------------------
-            mbar_wait(&bars->raw[q], (uint32_t)(k & 1));
-            {
-                const int n_rows = __ldg(tile_meta + 2 * T + 1);
-                unsigned char* cb = sb + SB_P + (r >> 3) * 128 + (r & 7) * 16;
+            mbar_wait(&bars->raw[q][bi], n & 1);
+            const int n_rows = __ldg(tile_meta + 2 * T + 1);
+            if (BF16) {
+                // 64-byte rows: chunk r & 3 of the rows (r >> 2) + 32 u
+                unsigned char* cb = sb + F::SB_P + (r >> 2) * 64 + (r & 3) * 16;
+                constexpr int CB = (ROWS + 31) / 32;
+                uint4 v[CB];
+#pragma unroll
+                for (int u = 0; u < CB; ++u) v[u] = *reinterpret_cast<const uint4*>(cb + u * 32 * 64);
+#pragma unroll
+                for (int u = 0; u < CB; ++u)
+                    if ((r >> 2) + 32 * u < n_rows) {
+                        float f[8];
+                        bf16_unpack8(v[u], f);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] = prelu_f(f[e], r11);
+                        *reinterpret_cast<uint4*>(cb + u * 32 * 64) = bf16_pack8(f);
+                    }
+            } else {
+                unsigned char* cb = sb + F::SB_P + (r >> 3) * 128 + (r & 7) * 16;
                 constexpr int CB = 9;
                 static_assert((ROWS + 15) / 16 == 2 * CB, "conversion batches");
 #pragma unroll
@@ -424,30 +547,67 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                                 prelu_f(v[u].x, r11), prelu_f(v[u].y, r11), prelu_f(v[u].z, r11), prelu_f(v[u].w, r11));
                 }
             }
-            mbar_arrive(&bars->full[q]);
-            mbar_wait(&bars->full[q], (uint32_t)(k & 1));
+            mbar_arrive(&bars->full[q][bi]);
+            mbar_wait(&bars->full[q][bi], n & 1);
             if (r == 0) S1_TRACE(12);
             // ---- sum of the station neighbours' rows (16-byte chunk k ^ key of every row: conflict free) ------------------
-            float4 acc[8];
-            {
-                f32x4_t a2[8];
+            float mean_sta[32];                      // channels 0-31 of the neighbour SUM (scaled by 1 / degree below)
+            const uint32_t w[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+            if (BF16) {
+                // (64-byte rows cover half of the banks: lanes l and l + 4 read the same chunk position and collide when their
+                // rows have the same parity — plan._pair_neighbour_order orders the neighbour lists against that)
+                f32x2_t a2[4][4];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) a2[c].lo = a2[c].hi = 0ull;
-                const uint32_t w[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) a2[c][e] = 0ull;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const uint32_t idx = (j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xffffu);
-                    const unsigned char* ra = sb + SB_P + idx * 128;
+                    const unsigned char* ra = sb + F::SB_P + idx * 64;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) fadd4(a2[c], *reinterpret_cast<const float4*>(ra + ((c ^ key) << 4)));
+                    for (int c = 0; c < 4; ++c) {
+                        const uint4 u = *reinterpret_cast<const uint4*>(ra + ((c ^ key) << 4));
+                        fadd2(a2[c][0], pack2(bf16_lo(u.x), bf16_hi(u.x)));
+                        fadd2(a2[c][1], pack2(bf16_lo(u.y), bf16_hi(u.y)));
+                        fadd2(a2[c][2], pack2(bf16_lo(u.z), bf16_hi(u.z)));
+                        fadd2(a2[c][3], pack2(bf16_lo(u.w), bf16_hi(u.w)));
+                    }
                 }
+                float acc8[4][8];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) acc[c] = to_float4(a2[c]);
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) unpack2(a2[c][e], acc8[c][2 * e], acc8[c][2 * e + 1]);
+                unrotate4x8(acc8, key);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mean_sta[i] = acc8[i >> 3][i & 7];
+            } else {
+                float4 acc[8];
+                {
+                    f32x4_t a2[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) a2[c].lo = a2[c].hi = 0ull;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const uint32_t idx = (j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xffffu);
+                        const unsigned char* ra = sb + F::SB_P + idx * 128;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) fadd4(a2[c], *reinterpret_cast<const float4*>(ra + ((c ^ key) << 4)));
+                    }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[c] = to_float4(a2[c]);
+                }
+                unrotate8(acc, key);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    mean_sta[4 * c] = acc[c].x; mean_sta[4 * c + 1] = acc[c].y;
+                    mean_sta[4 * c + 2] = acc[c].z; mean_sta[4 * c + 3] = acc[c].w;
+                }
             }
-            unrotate8(acc, key);
             const bool valid = r < n_own;
-            const float4 mk = s1_load_mask(sb, r, valid, packed_mask);
-            mbar_arrive(&bars->empty[q]);            // release (gather half): every shared-memory read of this tile is done
+            const float4 mk = s1_load_mask<BF16>(sb, r, valid, packed_mask);
+            mbar_arrive(&bars->empty[q][bi]);        // release (gather half): every shared-memory read of this tile is done
             // ---- A operand -> tensor memory (free once stage D of the pipeline's previous tile has completed) ---------------
             if (r == 0) S1_TRACE(14);
             if (k > 0) mbar_wait(&bars->opA_free[q], (uint32_t)((k - 1) & 1));
@@ -458,11 +618,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float4 v = acc[4 * half + u];
-                        a[4 * u] = v.x * invdeg; a[4 * u + 1] = v.y * invdeg; a[4 * u + 2] = v.z * invdeg;
-                        a[4 * u + 3] = v.w * invdeg;
-                    }
+                    for (int i = 0; i < 16; ++i) a[i] = mean_sta[16 * half + i] * invdeg;
                     if (half) {
                         a[14] = mk.z;       // channels 30, 31 of a feature row are padding: the mask rides there
                         a[15] = mk.w;
@@ -481,9 +637,8 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
         const int r = ((warp - WG_E0) & 3) * 32 + lane;
         const uint32_t lane_base = tm + q * TM_PIPE + ((uint32_t)((warp & 3) * 32) << 16);
         const float a1 = sc[TCS_A1], a21 = sc[TCS_A21], a22 = sc[TCS_A22], inv11 = sc[TCS_INV11];
-        const int key = lane & 7;
-        const unsigned char* sb = smem + SM_BUF + q * SB_SIZE;
-        unsigned char* scr = smem + SM_SCR + (warp - WG_E0) * 2048;
+        const int key = lane & (F::CPR - 1);
+        unsigned char* scr = smem + F::SM_SCR + (warp - WG_E0) * 2048;
         const int row0 = ((warp - WG_E0) & 3) * 32;                 // first tile row of this warp
         uint32_t ph_d = 0;
         int64_t k = 0;
@@ -496,9 +651,9 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
             if (t < n_tiles) {
                 const int g = (int)(t / NT), T = (int)(t - (int64_t)g * NT);
                 valid = r < __ldg(tile_meta + 2 * T);
-                mbar_wait(&bars->full[q], 0u);
-                mk = s1_own_operands(sb, r, valid, key, inv11, lane_base, packed_mask);
-                mbar_arrive(&bars->empty[q]);
+                mbar_wait(&bars->full[q][0], 0u);
+                mk = s1_own_operands<BF16>(smem + SM_BUF + (q * NBUF) * F::SB_SIZE, r, valid, key, inv11, lane_base, packed_mask);
+                mbar_arrive(&bars->empty[q][0]);
                 tmem_st_wait();
                 tc_fence_before_sync();
                 mbar_arrive(&bars->opA_full[q]);
@@ -507,13 +662,18 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
         for (int64_t t = blockIdx.x + (int64_t)q * gridDim.x; t < n_tiles; t += 2 * (int64_t)gridDim.x, ++k) {
             const int g = (int)(t / NT), T = (int)(t - (int64_t)g * NT);
             const int64_t node0 = (int64_t)g * S;
-            int sid[4];
+            int sid[4], sid2[2];
             {
                 const int n_own = __ldg(tile_meta + 2 * T);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int rw = row0 + (lane >> 2) + 8 * j;
                     sid[j] = rw < n_own ? __ldg(tile_rows + (int64_t)T * ROWS + rw) : -1;
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int rw = row0 + (lane >> 1) + 16 * j;
+                    sid2[j] = (BF16 && rw < n_own) ? __ldg(tile_rows + (int64_t)T * ROWS + rw) : -1;
                 }
             }
             // edge-feature model (genie_plan_set_edge_terms): rows of the additive terms of this thread's station / grid node
@@ -605,7 +765,8 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                 float v[16];
                 tmem_ld16(lane_base + TM_DD + c, v);
                 tmem_ld_wait();
-                store16_rows(v, scr, lane, sid, c ? vb : va, node0, LD_V);
+                if (BF16 && c) store16_rows_bf16(v, scr, lane, sid2, vb, node0);      // v_b is a gathered tensor: bf16 rows
+                else store16_rows(v, scr, lane, sid, c ? vb : va, node0, LD_V);
             }
             tc_fence_before_sync();
             mbar_arrive(&bars->d_free[q]);
@@ -615,9 +776,10 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
             if (t2 < n_tiles) {
                 const int g2 = (int)(t2 / NT), T2 = (int)(t2 - (int64_t)g2 * NT);
                 valid = r < __ldg(tile_meta + 2 * T2);
-                mbar_wait(&bars->full[q], (uint32_t)((k + 1) & 1));
-                mk = s1_own_operands(sb, r, valid, key, inv11, lane_base, packed_mask);
-                mbar_arrive(&bars->empty[q]);
+                const int b2 = (int)((k + 1) % NBUF);
+                mbar_wait(&bars->full[q][b2], (uint32_t)(((k + 1) / NBUF) & 1));
+                mk = s1_own_operands<BF16>(smem + SM_BUF + (q * NBUF + b2) * F::SB_SIZE, r, valid, key, inv11, lane_base, packed_mask);
+                mbar_arrive(&bars->empty[q][b2]);
                 tmem_st_wait();
                 tc_fence_before_sync();
                 mbar_arrive(&bars->opA_full[q]);
@@ -648,20 +810,22 @@ int launch_da_layer1_s(const genie_plan* p, const float* packed, const float* pf
     const int64_t n_tiles = (int64_t)g.n_sta_tiles * (g.n_grid_owned > 0 ? g.n_grid_owned : g.n_grid);
     static PerDeviceOnce attr_set;
     if (attr_set.need()) {
-        GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer1_s_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-        GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer1_s_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer1_s_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fmt<false>::SM_TOTAL));
+        GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer1_s_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fmt<false>::SM_TOTAL));
+        GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer1_s_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fmt<true>::SM_TOTAL));
+        GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer1_s_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fmt<true>::SM_TOTAL));
         attr_set.mark();
     }
     const int64_t grid = n_tiles < p->sm_count ? n_tiles : p->sm_count;
+    const bool edge = p->edge_sta != nullptr, bf = p->storage == GENIE_STORAGE_BF16;
     TimedLaunch tl(KID_DA_LAYER1_S, st);
-    if (p->edge_sta != nullptr)
-        da_layer1_s_kernel<true><<<(unsigned)grid, S1_THREADS, SM_TOTAL, st>>>(
-            packed, pfeat, msrc, mask, zc, va, vb, g.n_sta, g.n_sta_tiles, g.sta_tile_rows, g.sta_tile_meta, g.sta_tile_nbr,
+#define GENIE_S1_LAUNCH(E, B)                                                                                                  \
+    if (edge == E && bf == B)                                                                                                   \
+        da_layer1_s_kernel<E, B><<<(unsigned)grid, S1_THREADS, Fmt<B>::SM_TOTAL, st>>>(                                         \
+            packed, pfeat, msrc, mask, zc, va, vb, g.n_sta, g.n_sta_tiles, g.sta_tile_rows, g.sta_tile_meta, g.sta_tile_nbr,    \
             g.sta_tile_invdeg, n_tiles, p->edge_sta, p->edge_src, g_s1_trace, g_s1_trace_tiles, g_s1_trace_start);
-    else
-        da_layer1_s_kernel<false><<<(unsigned)grid, S1_THREADS, SM_TOTAL, st>>>(
-            packed, pfeat, msrc, mask, zc, va, vb, g.n_sta, g.n_sta_tiles, g.sta_tile_rows, g.sta_tile_meta, g.sta_tile_nbr,
-            g.sta_tile_invdeg, n_tiles, nullptr, nullptr, g_s1_trace, g_s1_trace_tiles, g_s1_trace_start);
+    GENIE_S1_LAUNCH(false, false) GENIE_S1_LAUNCH(true, false) GENIE_S1_LAUNCH(false, true) GENIE_S1_LAUNCH(true, true)
+#undef GENIE_S1_LAUNCH
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;
 }

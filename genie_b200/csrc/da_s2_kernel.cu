@@ -13,6 +13,7 @@
 // weights broadcast from shared memory, and reduce over the tile's rows with a register-transposing butterfly.  A CTA owns
 // whole grid nodes: the per-tile sums of one grid node meet in shared memory in a fixed order (no atomics: results are
 // bit-reproducible), and the last tile to finish applies fc2 and writes the read-in row.
+#include "bf16.cuh"
 #include "common.cuh"
 
 using namespace gl;
@@ -97,7 +98,8 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
     return v[0];
 }
 
-template <bool STORE_LATENT, int CSLOT>
+// BF16: the mean_src(v_b) rows `m2` are bf16 (32 bytes; genie_plan_set_storage), staged as they are and widened on read.
+template <bool STORE_LATENT, int CSLOT, bool BF16>
 __global__ void __launch_bounds__(S2_THREADS, 1)
     da_layer2_s_kernel(const float* __restrict__ packed, const float* __restrict__ zc, const float* __restrict__ va,
                        const float* __restrict__ m2, const float* __restrict__ mask, const float* __restrict__ edge_attr,
@@ -164,11 +166,22 @@ __global__ void __launch_bounds__(S2_THREADS, 1)
                 if (id8[j] >= 0)
                     cp_async16(sb + SB_ZC + r * 128 + ((c8 ^ (r & 7)) << 4), zc + (node0 + id8[j]) * LD_ZC + c8 * 4);
             }
+            if (BF16) {      // 32-byte rows: chunk c2 = tid & 1 of rows (tid >> 1) + 64 j, swizzled by (row >> 2) & 1
+                const int c2 = tid & 1;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int r = r4 + 32 * j;
-                if (r < n_own)
-                    cp_async16(sb + SB_M2 + r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4), m2 + (node0 + id4[j]) * LD_V + c4 * 4);
+                for (int j = 0; j < 2; ++j) {
+                    const int r = (tid >> 1) + 64 * j;
+                    if (r < n_own)
+                        cp_async16(sb + SB_M2 + r * 32 + ((c2 ^ ((r >> 2) & 1)) << 4),
+                                   reinterpret_cast<const unsigned char*>(m2) + (node0 + __ldg(rows + r)) * 32 + c2 * 16);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r = r4 + 32 * j;
+                    if (r < n_own)
+                        cp_async16(sb + SB_M2 + r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4), m2 + (node0 + id4[j]) * LD_V + c4 * 4);
+                }
             }
             cp_async_arrive_noinc(&bars->full[b]);
         }
@@ -224,12 +237,28 @@ __global__ void __launch_bounds__(S2_THREADS, 1)
             float x[32];
             float zmask = 0.f;       // max_c(mask) of the node: layer 1 left it in padding channel 15 of the zc row
             if (valid) {
+                float m2v[16];
+                if (BF16) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        float f[8];
+                        bf16_unpack8(*reinterpret_cast<const uint4*>(sb + SB_M2 + r * 32 + ((c ^ ((r >> 2) & 1)) << 4)), f);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) m2v[8 * c + e] = f[e];
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float4 t4 = *reinterpret_cast<const float4*>(sb + SB_M2 + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+                        m2v[4 * c] = t4.x; m2v[4 * c + 1] = t4.y; m2v[4 * c + 2] = t4.z; m2v[4 * c + 3] = t4.w;
+                    }
+                }
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const float4 za = *reinterpret_cast<const float4*>(sb + SB_ZC + r * 128 + ((c ^ (r & 7)) << 4));
                     if (c == 3) zmask = za.w;
                     const float4 zb = *reinterpret_cast<const float4*>(sb + SB_ZC + r * 128 + (((c + 4) ^ (r & 7)) << 4));
-                    const float4 mb = *reinterpret_cast<const float4*>(sb + SB_M2 + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+                    const float4 mb = make_float4(m2v[4 * c], m2v[4 * c + 1], m2v[4 * c + 2], m2v[4 * c + 3]);
                     x[4 * c + 0] = prelu(za.x + acc[c].x * invdeg, a2);
                     x[4 * c + 1] = prelu(za.y + acc[c].y * invdeg, a2);
                     x[4 * c + 2] = prelu(za.z + acc[c].z * invdeg, a2);
@@ -335,18 +364,21 @@ int launch_da_layer2_s(const genie_plan* p, const float* packed, const float* zc
     static PerDeviceOnce attr_set;
     const bool set_attr = attr_set.need();
     TimedLaunch tl(KID_DA_LAYER2_S, st);
-#define GENIE_S2_LAUNCH(L, C)                                                                                                  \
+    const bool bf = p->storage == GENIE_STORAGE_BF16;
+#define GENIE_S2_LAUNCH_B(L, C, B)                                                                                             \
     do {                                                                                                                        \
         if (set_attr)                                                                                                           \
-            GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer2_s_kernel<L, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)); \
-        if (L == (latent_out != nullptr) && C == p->cslot)                                                                      \
-            da_layer2_s_kernel<L, C><<<grid, S2_THREADS, SM_TOTAL, st>>>(packed, zc, va, m2, mask, edge_attr, latent_out, out, ld_out, \
-                                                                         g.n_sta, n_own, g.n_sta_tiles, g.sta_tile_rows,       \
-                                                                         g.sta_tile_meta, g.sta_tile_nbr, g.sta_tile_invdeg);  \
+            GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer2_s_kernel<L, C, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)); \
+        if (L == (latent_out != nullptr) && C == p->cslot && B == bf)                                                           \
+            da_layer2_s_kernel<L, C, B><<<grid, S2_THREADS, SM_TOTAL, st>>>(packed, zc, va, m2, mask, edge_attr, latent_out, out, ld_out, \
+                                                                            g.n_sta, n_own, g.n_sta_tiles, g.sta_tile_rows,    \
+                                                                            g.sta_tile_meta, g.sta_tile_nbr, g.sta_tile_invdeg); \
     } while (0)
+#define GENIE_S2_LAUNCH(L, C) GENIE_S2_LAUNCH_B(L, C, false); GENIE_S2_LAUNCH_B(L, C, true)
     GENIE_S2_LAUNCH(false, 0); GENIE_S2_LAUNCH(false, 1); GENIE_S2_LAUNCH(false, 2); GENIE_S2_LAUNCH(false, 3);
     GENIE_S2_LAUNCH(true, 0); GENIE_S2_LAUNCH(true, 1); GENIE_S2_LAUNCH(true, 2); GENIE_S2_LAUNCH(true, 3);
 #undef GENIE_S2_LAUNCH
+#undef GENIE_S2_LAUNCH_B
     if (set_attr) attr_set.mark();
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;

@@ -18,6 +18,7 @@ struct genie_plan {
     genie_graph_desc_t g;
     int sm_count;
     int cslot;              // constant-bank slot of this plan
+    int storage;            // GENIE_STORAGE_* of the gathered intermediate rows
     int64_t n_edges_grid;   // number of grid-graph edges (host copy of grid_rowptr[G]), fetched lazily
     // Edge-feature model (genie_plan_set_edge_terms): per-node additive terms of layer 1, NULL = off.
     const float* edge_sta;  // [S or P][GENIE_EDGE_TERM_LD]
@@ -184,7 +185,8 @@ int launch_spatial_aggregation(const genie_plan* p, const float* packed, int lay
 // split source-pass / station-pass kernels (plans with tiling tables; src_mean_kernels.cu, da_s1_kernel.cu, da_s2_kernel.cu)
 bool split_supported(const genie_plan* p);
 // out[g,s,:] = mean_{g' in N_src(g)} X[g',s,:], rows of `width` floats (32 or 16); gate: optional device flag, 0 = skip
-int launch_src_mean(const genie_plan* p, int width, const float* X, float* out, const float* gate, cudaStream_t st);
+int launch_src_mean(const genie_plan* p, int width, const float* X, float* out, const float* gate, cudaStream_t st,
+                    int storage = GENIE_STORAGE_FP32);
 int launch_da_layer1_s(const genie_plan* p, const float* packed, const float* pfeat, const float* msrc,
                        const float* mask, float* zc, float* va, float* vb, cudaStream_t st);
 void set_s1_trace(long long* buf, int tiles);

@@ -12,6 +12,7 @@
 // Lanes map to 16-byte chunks of a row (8 lanes per 128-byte row), so every request is a fully used 128-byte line; there
 // is no shared memory, no barrier and no atomics: warps drift apart freely, and the leaders pull the next tile's rows
 // into L1 while the stragglers finish.
+#include "bf16.cuh"
 #include "common.cuh"
 
 using namespace gl;
@@ -83,6 +84,84 @@ __global__ void __launch_bounds__(SM_THREADS, 1)
     }
 }
 
+// The same pass over bf16 rows (genie_plan_set_storage, GENIE_STORAGE_BF16): W channels = W / 8 chunks of 16 bytes per row,
+// fp32 accumulation, bf16 result.  Half the bytes through the L1 data pipe that bounds the fp32 kernel.
+template <int W, int SB>
+__global__ void __launch_bounds__(SM_THREADS, 1)
+    src_mean_bf16_kernel(const uint4* __restrict__ X4, uint4* __restrict__ O4, int S, const int64_t* __restrict__ rowptr,
+                         const int32_t* __restrict__ col, const int32_t* __restrict__ grp_ptr,
+                         const int32_t* __restrict__ grp_nodes, int n_groups, int n_slabs, const float* __restrict__ gate) {
+    if (gate != nullptr && *gate == 0.f) return;
+    constexpr int LPR = W / 8;                       // lanes (16-byte chunks) per row
+    constexpr int PAIRS = SB / 2;
+    const uint32_t gstride = (uint32_t)S * LPR;      // uint4 units between consecutive grid nodes
+    const int64_t n_tiles = (int64_t)n_groups * n_slabs;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int slab = (int)(t / n_groups);
+        const int grp = (int)(t - (int64_t)slab * n_groups);
+        const int gbeg = __ldg(grp_ptr + grp);
+        const int gcnt = __ldg(grp_ptr + grp + 1) - gbeg;
+        const int s0 = slab * SB;
+        const int items = gcnt * PAIRS * LPR;
+        for (int i = threadIdx.x; i < items; i += SM_THREADS) {
+            const int c = i % LPR;
+            const int pr = (i / LPR) % PAIRS;
+            const int gl = i / (LPR * PAIRS);
+            const int s = s0 + pr;
+            if (s >= S) continue;
+            const bool two = s + PAIRS < S;
+            const int g = __ldg(grp_nodes + gbeg + gl);
+            const int beg = (int)__ldg(rowptr + g);
+            const int deg = (int)__ldg(rowptr + g + 1) - beg;
+            const uint32_t off = (uint32_t)s * LPR + c;
+            const uint32_t off2 = two ? off + PAIRS * LPR : off;
+            const int32_t* __restrict__ cp = col + beg;
+            float a0[8], a1[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a0[e] = a1[e] = 0.f;
+            int j = 0;
+            for (; j + 3 <= deg; j += 3) {                                // k = 15 in-edges: five unmasked batches of three
+                uint4 v0[3], v1[3];
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const uint32_t base = (uint32_t)__ldg(cp + j + u) * gstride;
+                    v0[u] = __ldg(X4 + (base + off));
+                    v1[u] = __ldg(X4 + (base + off2));
+                }
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    float f[8];
+                    bf16_unpack8(v0[u], f);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) a0[e] += f[e];
+                    bf16_unpack8(v1[u], f);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) a1[e] += f[e];
+                }
+            }
+            for (; j < deg; ++j) {
+                const uint32_t base = (uint32_t)__ldg(cp + j) * gstride;
+                float f[8];
+                bf16_unpack8(__ldg(X4 + (base + off)), f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a0[e] += f[e];
+                bf16_unpack8(__ldg(X4 + (base + off2)), f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a1[e] += f[e];
+            }
+            const float inv = deg > 0 ? 1.f / (float)deg : 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                a0[e] *= inv;
+                a1[e] *= inv;
+            }
+            const uint32_t o = (uint32_t)g * gstride + off;
+            __stcs(O4 + o, bf16_pack8(a0));
+            if (two) __stcs(O4 + (o + PAIRS * LPR), bf16_pack8(a1));
+        }
+    }
+}
+
 }  // namespace
 
 bool split_supported(const genie_plan* p) {
@@ -102,18 +181,32 @@ static void launch_src_mean_t(const genie_plan* p, const float* X, float* out, c
                                                         g.grid_grp_nodes, g.n_grid_groups, n_slabs, gate);
 }
 
-int launch_src_mean(const genie_plan* p, int width, const float* X, float* out, const float* gate, cudaStream_t st) {
-    // one slab = 512 bytes of every neighbour row: 4 stations of 128-byte rows, 8 stations of 64-byte rows
-    // (64 grid nodes x 2 station pairs x 8 lanes = 1024 items: one item per thread of the CTA)
+template <int W, int SB>
+static void launch_src_mean_bf16_t(const genie_plan* p, const float* X, float* out, const float* gate, cudaStream_t st) {
+    const genie_graph_desc_t& g = p->g;
+    const int n_slabs = (g.n_sta + SB - 1) / SB;
+    const int64_t n_tiles = (int64_t)g.n_grid_groups * n_slabs;
+    const unsigned grid = (unsigned)(n_tiles < p->sm_count ? n_tiles : p->sm_count);
+    src_mean_bf16_kernel<W, SB><<<grid, SM_THREADS, 0, st>>>(reinterpret_cast<const uint4*>(X), reinterpret_cast<uint4*>(out),
+                                                             g.n_sta, g.src_rowptr, g.src_col, g.grid_grp_ptr, g.grid_grp_nodes,
+                                                             g.n_grid_groups, n_slabs, gate);
+}
+
+// X / out: fp32 rows, or (storage == GENIE_STORAGE_BF16) bf16 rows of the same channel count
+int launch_src_mean(const genie_plan* p, int width, const float* X, float* out, const float* gate, cudaStream_t st,
+                    int storage) {
     // One slab = 8 stations of every neighbour row (1024 B of 128-byte rows, 512 B of 64-byte rows): measured best on B200
     // together with groups of 256 grid nodes (sweeps of 64..4096 nodes x 256..2048 bytes, gpurun r1zd-r1zf: 5.2 -> 3.9 ms and
-    // 3.6 -> 3.3 ms at C4).
+    // 3.6 -> 3.3 ms at C4).  bf16 rows: 16 / 32 stations, the same bytes per slab.
+    const bool bf = storage == GENIE_STORAGE_BF16;
     if (width == 32) {
         TimedLaunch tl(KID_SRC_MEAN32, st);
-        launch_src_mean_t<32, 8>(p, X, out, gate, st);
+        if (bf) launch_src_mean_bf16_t<32, 16>(p, X, out, gate, st);
+        else launch_src_mean_t<32, 8>(p, X, out, gate, st);
     } else if (width == 16) {
         TimedLaunch tl(KID_SRC_MEAN16, st);
-        launch_src_mean_t<16, 8>(p, X, out, gate, st);
+        if (bf) launch_src_mean_bf16_t<16, 16>(p, X, out, gate, st);
+        else launch_src_mean_t<16, 8>(p, X, out, gate, st);
     } else {
         set_error("launch_src_mean: unsupported row width");
         return GENIE_ERR_INVALID;

@@ -541,6 +541,20 @@ class GCN_Detection_Network_extended(nn.Module):
                 self._set_edge_means(pos[0], pos[1], A_src_in_sta)
         return self._plan
 
+    def set_storage(self, storage):
+        """'fp32' (default) or 'bf16': storage of the gathered intermediate rows of the current plan (GraphPlan.set_storage).
+        bf16 is the fast inference mode (BASELINE.json configs[1]: ~1e-3 relative to the fp32 reference, NOT within the 1e-4
+        parity bar); it runs only on the tensor-core kernel family, which needs PReLU slopes of activate11 / activate12 in
+        (1e-3, 1e3) — checked here."""
+        if self._plan is None:
+            raise RuntimeError('set_adjacencies must be called before set_storage')
+        if storage == 'bf16':
+            da = self.DataAggregation
+            a11, a12 = float(da.activate11.weight.reshape(-1)[0]), float(da.activate12.weight.reshape(-1)[0])
+            if not (1e-3 < a11 < 1e3 and 1e-3 < a12 < 1e3):
+                raise capi.GenieError('bf16 storage needs activate11 / activate12 slopes in (1e-3, 1e3)')
+        self._plan.set_storage(storage)
+
     # -- CUDA front end ------------------------------------------------------------------------------------------------
     def _packed_weights(self, dev, init_relaid=None):
         if self._packed is None or self._packed.device != torch.device(dev):

@@ -445,12 +445,16 @@ def da_layer1_fwd(plan, packed, Slice, Mask):
 
 
 def message_rows(plan):
-    """View [n_grid, n_sta * 16] of the layer-2 source messages v_b inside the workspace (one row per grid node)."""
+    """View [n_grid, row] of the layer-2 source messages v_b inside the workspace, one row per grid node (n_sta x 16
+    channels: fp32, or bf16 carried as uint8 in the bf16 storage mode — the halo exchange only moves the bytes)."""
     ws = plan.workspace()
     ptr, nbytes = ctypes.c_void_p(), ctypes.c_size_t()
     capi.check(capi.load().genie_workspace_region(plan.handle, capi.dptr(ws), 0, ctypes.byref(ptr), ctypes.byref(nbytes)))
     off = ptr.value - ws.data_ptr()
-    return ws[off:off + nbytes.value].view(F32).view(plan.n_grid, plan.n_sta * 16)
+    raw = ws[off:off + nbytes.value]
+    if plan.storage == 'bf16':
+        return raw.view(plan.n_grid, plan.n_sta * 32)
+    return raw.view(F32).view(plan.n_grid, plan.n_sta * 16)
 
 
 def da_layer2_readin_fwd(plan, packed, Mask, edge_attr, want_latent=False):

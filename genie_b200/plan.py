@@ -262,6 +262,7 @@ class GraphPlan(object):
         self.handle = handle
         self.workspace_bytes = int(lib.genie_plan_workspace_bytes(handle))
         self._workspace = None
+        self.storage = 'fp32'
 
     def __del__(self):
         h = getattr(self, 'handle', None)
@@ -271,6 +272,16 @@ class GraphPlan(object):
             except Exception:
                 pass
             self.handle = None
+
+    def set_storage(self, storage):
+        """genie_plan_set_storage: 'fp32' (default; within 1e-4 of the reference) or 'bf16' (the gathered intermediate rows
+        kept as bf16: the fast inference mode of BASELINE.json configs[1], ~1e-3 relative).  Re-sizes the workspace."""
+        code = {'fp32': capi.STORAGE_FP32, 'bf16': capi.STORAGE_BF16}[storage]
+        capi.check(capi.load().genie_plan_set_storage(self.handle, code))
+        if storage != self.storage:
+            self.storage = storage
+            self.workspace_bytes = int(capi.load().genie_plan_workspace_bytes(self.handle))
+            self._workspace = None
 
     def set_edge_terms(self, t_sta, t_src):
         """genie_plan_set_edge_terms: per-node additive terms of the edge-feature model ([n, 48] fp32 each), or None, None."""

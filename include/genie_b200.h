@@ -154,6 +154,17 @@ typedef struct genie_frontend_weights {
     } sa[3];
 } genie_frontend_weights_t;
 
+/* ---- storage mode of the intermediate node-feature rows -----------------------------------------------------------------
+ * GENIE_STORAGE_FP32 (default): every intermediate is fp32; results match the reference's fp32 path within 1e-4.
+ * GENIE_STORAGE_BF16: the GATHERED rows — layer-0 features, their source-neighbour mean, the layer-2 source messages and
+ *   their mean — are kept as bf16 in HBM and in shared memory (half the bytes on the gather paths that bound the kernels);
+ *   all arithmetic stays fp32 (sums, means, 3xTF32 tensor-core stages).  A fast inference mode (BASELINE.json configs[1]),
+ *   NOT within the 1e-4 bar (~1e-3 relative).  Needs a CARTESIAN plan with tiling tables and PReLU slopes eligible for the
+ *   tensor-core path (layout.h TCS_OK); changes genie_plan_workspace_bytes — set it before sizing the workspace. */
+#define GENIE_STORAGE_FP32 0
+#define GENIE_STORAGE_BF16 1
+GENIE_API int genie_plan_set_storage(genie_plan_t* plan, int32_t storage);
+
 /* Number of floats of the packed (kernel-layout) weight buffer. */
 GENIE_API size_t genie_frontend_packed_floats(void);
 /* Re-lays the reference-layout weights into `packed_dev` (one small kernel; call again whenever weights change). */

@@ -160,6 +160,59 @@ def test_window_runner_equals_the_two_step_path():
         assert torch.equal(out[1], lat) and torch.equal(out[2], rin)
 
 
+def test_bf16_storage_mode_tracks_the_fp32_path():
+    """GENIE_STORAGE_BF16 (BASELINE.json configs[1]: bf16 inference): the gathered intermediate rows kept as bf16, fp32
+    arithmetic.  A SECOND mode — it never stands in for the 1e-4 parity tests: here it is held to 2e-2 of the fp32 path and
+    of the oracle, must differ from fp32 (it really stores bf16), must agree bit for bit between the fused window call and
+    the two-step call, and switching back to fp32 must restore the fp32 results exactly."""
+    from genie_b200 import synth
+    from genie_b200.module import GCN_Detection_Network_extended
+    from genie_b200.process_utils import InputExtractor, extract_inputs_adjacencies_cartesian, product_edge_lists
+    from genie_b200.streaming import WindowRunner
+    from oracle import genie_oracle as go
+    dev = _dev()
+    S, G = 100, 1500
+    net = synth.Network(S, G, seed=3)
+    A_sta, A_src = extract_inputs_adjacencies_cartesian(net.sta, net.grid, 15, 15)
+    attr = torch.from_numpy(net.read_in_offsets(30000.0)).to(dev)
+    sd = go.init_state(seed=9)
+    m = GCN_Detection_Network_extended(None, None, scale_rel=30000.0, device=dev).eval()
+    m.load_state_dict(sd, strict=False)
+    m.set_adjacencies_cartesian(A_sta, A_src, attr, S, G, device=dev)
+    ex = InputExtractor(m._plan, net.travel_times(), np.arange(S), S, net.max_moveout(), 3.0, 0.3)
+    ex.set_day(synth.make_picks(net, 0.0, 600.0, seed=4, false_per_sta_min=4.0))
+    locs = torch.from_numpy(net.sta).float().to(dev)
+    grid = torch.from_numpy(net.grid).float().to(dev)
+    xq = torch.from_numpy(np.random.default_rng(1).uniform(0, net.width, (300, 3))).float().to(dev)
+    xq[:, 2] = -xq[:, 2] / net.width * 40000.0
+    tq = torch.arange(-3.0, 3.01, 0.75, device=dev).reshape(-1, 1)
+    t0 = 250.5
+    Slice, Mask = ex(t0)
+    y32, x32 = m.forward_fixed_source(Slice, Mask, None, None, None, locs, grid, xq, tq)
+    xs32, _, r32 = m.front_end(Slice, Mask, grid, want_readin=True)
+    ws32 = m._plan.workspace_bytes
+    m.set_storage('bf16')
+    assert m._plan.workspace_bytes < 0.8 * ws32
+    y16, x16 = m.forward_fixed_source(Slice, Mask, None, None, None, locs, grid, xq, tq)
+    xs16, _, r16 = m.front_end(Slice, Mask, grid, want_readin=True)
+    assert not torch.equal(r16, r32)
+    for a, b in ((r16, r32), (xs16, xs32), (y16, y32), (x16, x32)):
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 2e-2
+    assert rel_err(r16.cpu().numpy(), r32.cpu().numpy()) > 1e-6
+    # against the oracle
+    A_ps, A_pg, A_sip, _ = product_edge_lists(A_sta, A_src, S, G)
+    want = go.front_end(sd, Slice.cpu(), Mask.cpu(), A_ps, A_pg, attr.cpu(), A_sip, A_src, grid.cpu(), 30000.0)
+    assert rel_err(xs16.cpu().numpy(), want.numpy()) < 2e-2
+    assert rel_err(xs32.cpu().numpy(), want.numpy()) < 1e-4
+    # fused window call == two-step call in this mode as well (eager and graph)
+    for use_graph in (False, True):
+        y, x = WindowRunner(m, ex, locs, grid, xq, tq, use_graph=use_graph).run(t0)
+        assert torch.equal(y, y16) and torch.equal(x, x16)
+    m.set_storage('fp32')
+    y, x = m.forward_fixed_source(Slice, Mask, None, None, None, locs, grid, xq, tq)
+    assert torch.equal(y, y32) and torch.equal(x, x32)
+
+
 def capi_window_block(ex, t0, dev):
     """Device copy of a capi.WindowParams for window t0 (test helper)."""
     import ctypes
