@@ -102,8 +102,15 @@ __device__ __forceinline__ float prelu_f(float x, float a) { return x >= 0.f ? x
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-// 16 consecutive fp32 values -> 3xTF32 parts -> TMEM columns [hi, hi+16) and [lo, lo+16)
+// 16 consecutive fp32 values -> 3xTF32 parts -> TMEM columns [hi, hi+16) and [lo, lo+16).
+// FAST (the bf16-storage mode): the tensor-core stages run single-pass TF32 — the operand goes in as it is (the tensor core
+// reads the top 19 bits) and no lo part is written; the one lo block a bias needs is written by st_split16_bias.
+template <bool FAST>
 __device__ __forceinline__ void st_split16(uint32_t taddr_hi, uint32_t taddr_lo, const float (&v)[16]) {
+    if (FAST) {
+        tmem_st16(taddr_hi, v);
+        return;
+    }
     float h[16], l[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -114,7 +121,14 @@ __device__ __forceinline__ void st_split16(uint32_t taddr_hi, uint32_t taddr_lo,
     tmem_st16(taddr_lo, l);
 }
 // as st_split16, with lo columns 14 and 15 forced to 1 (the bias rows of the lo pass, layout.h T2_*_BIAS)
+template <bool FAST>
 __device__ __forceinline__ void st_split16_bias(uint32_t taddr_hi, uint32_t taddr_lo, const float (&v)[16]) {
+    if (FAST) {      // lo columns 8-15 of this half = k 24-31 of the operand: zeros, and ones in the two bias columns
+        tmem_st16(taddr_hi, v);
+        const float ones[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 1.f};
+        tmem_st8(taddr_lo + 8, ones);
+        return;
+    }
     float h[16], l[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -238,9 +252,9 @@ __device__ __forceinline__ float4 s1_own_operands(const unsigned char* sb, int r
             if (half) {
                 a[14] = mk.x;
                 a[15] = mk.y;
-                st_split16_bias(lane_base + TM_OWN_HI + 16, lane_base + TM_OWN_LO + 16, a);      // bias of stage B
+                st_split16_bias<BF16>(lane_base + TM_OWN_HI + 16, lane_base + TM_OWN_LO + 16, a);      // bias of stage B
             } else {
-                st_split16(lane_base + TM_OWN_HI, lane_base + TM_OWN_LO, a);
+                st_split16<BF16>(lane_base + TM_OWN_HI, lane_base + TM_OWN_LO, a);
             }
         }
 #pragma unroll
@@ -258,7 +272,7 @@ __device__ __forceinline__ float4 s1_own_operands(const unsigned char* sb, int r
                 a[14] = mk.z;
                 a[15] = mk.w;
             }
-            st_split16(lane_base + TM_SRC_HI + 16 * half, lane_base + TM_SRC_LO + 16 * half, a);
+            st_split16<BF16>(lane_base + TM_SRC_HI + 16 * half, lane_base + TM_SRC_LO + 16 * half, a);
         }
         return mk;
     }
@@ -283,9 +297,9 @@ __device__ __forceinline__ float4 s1_own_operands(const unsigned char* sb, int r
             if (half) {
                 a[14] = mk.x;       // channels 30, 31 of a feature row are padding: the mask rides there
                 a[15] = mk.y;
-                st_split16_bias(lane_base + TM_OWN_HI + 16, lane_base + TM_OWN_LO + 16, a);      // bias of stage B
+                st_split16_bias<BF16>(lane_base + TM_OWN_HI + 16, lane_base + TM_OWN_LO + 16, a);      // bias of stage B
             } else {
-                st_split16(lane_base + TM_OWN_HI, lane_base + TM_OWN_LO, a);
+                st_split16<BF16>(lane_base + TM_OWN_HI, lane_base + TM_OWN_LO, a);
             }
         }
     }
@@ -302,7 +316,7 @@ __device__ __forceinline__ float4 s1_own_operands(const unsigned char* sb, int r
             a[14] = mk.z;
             a[15] = mk.w;
         }
-        st_split16(lane_base + TM_SRC_HI + 16 * half, lane_base + TM_SRC_LO + 16 * half, a);
+        st_split16<BF16>(lane_base + TM_SRC_HI + 16 * half, lane_base + TM_SRC_LO + 16 * half, a);
     }
     return mk;
 }
@@ -428,8 +442,23 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                 tc_fence_after_sync();
                 S1_TRACE(0);
                 // ---- stage B: X[0,64) = [tr1 | tr2] pre-activation (bias on the lo pass) ------------------------------
+                if (BF16) {      // fast mode: single-pass TF32 + the one lo k-step that carries the bias
 #pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_tf32_ts(base + TM_X, base + TM_OWN_HI + ks * 8,
+                                     umma_desc_kmajor(wbase + 4 * T2_S1A_HI + ks * 2 * 64 * 16, 64 * 16, 128), i64, ks ? 1u : 0u);
+                    umma_tf32_ts(base + TM_X, base + TM_OWN_LO + 3 * 8, umma_desc_kmajor(wbase + 4 * T2_S1A_BIAS, 64 * 16, 128), i64, 1u);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_tf32_ts(base + TM_X, base + TM_STA_HI + ks * 8,
+                                     umma_desc_kmajor(wbase + 4 * T2_S1B_HI + ks * 2 * 32 * 16, 32 * 16, 128), i32, 1u);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_tf32_ts(base + TM_X + 32, base + TM_SRC_HI + ks * 8,
+                                     umma_desc_kmajor(wbase + 4 * T2_S1C_HI + ks * 2 * 32 * 16, 32 * 16, 128), i32, 1u);
+                }
+#pragma unroll
+                for (int pass = 0; pass < (BF16 ? 0 : 3); ++pass) {
                     const bool a_lo = pass == 1;                // A operand: lo part on pass 1
                     const bool b_lo = pass == 2;                // B operand: lo part on pass 2
                     const uint32_t s1a = wbase + 4 * (b_lo ? T2_S1A_LO : T2_S1A_HI);
@@ -457,8 +486,15 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                 ph_a ^= 1;
                 tc_fence_after_sync();
                 S1_TRACE(2);
+                if (BF16) {
 #pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_tf32_ts(base + TM_DC, base + TM_R2_HI + ks * 8,
+                                     umma_desc_kmajor(wbase + 4 * T2_S2_HI + ks * 2 * 96 * 16, 96 * 16, 128), i96, ks ? 1u : 0u);
+                    umma_tf32_ts(base + TM_DC, base + TM_R2_LO + 3 * 8, umma_desc_kmajor(wbase + 4 * T2_S2_BIAS, 96 * 16, 128), i96, 1u);
+                }
+#pragma unroll
+                for (int pass = 0; pass < (BF16 ? 0 : 3); ++pass) {
                     const uint32_t s2 = wbase + 4 * (pass == 2 ? T2_S2_LO : T2_S2_HI);
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {
@@ -475,7 +511,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                 tc_fence_after_sync();
                 S1_TRACE(4);
 #pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
+                for (int pass = 0; pass < (BF16 ? 1 : 3); ++pass) {
                     const uint32_t s3a = wbase + 4 * (pass == 2 ? T2_S3A_LO : T2_S3A_HI);
                     const uint32_t s3b = wbase + 4 * (pass == 2 ? T2_S3B_LO : T2_S3B_HI);
                     const uint32_t a = base + (pass == 1 ? TM_R2_LO : TM_R2_HI);
@@ -623,7 +659,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                         a[14] = mk.z;       // channels 30, 31 of a feature row are padding: the mask rides there
                         a[15] = mk.w;
                     }
-                    st_split16(lane_base + TM_STA_HI + 16 * half, lane_base + TM_STA_LO + 16 * half, a);
+                    st_split16<BF16>(lane_base + TM_STA_HI + 16 * half, lane_base + TM_STA_LO + 16 * half, a);
                 }
             }
             tmem_st_wait();
@@ -707,13 +743,13 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                 if (c == 16) {
                     v[14] = mk.x;
                     v[15] = mk.y;
-                    st_split16_bias(lane_base + TM_R2_HI + c, lane_base + TM_R2_LO + c, v);     // bias of stage C
+                    st_split16_bias<BF16>(lane_base + TM_R2_HI + c, lane_base + TM_R2_LO + c, v);     // bias of stage C
                 } else {
                     if (c == 48) {
                         v[14] = mk.z;
                         v[15] = mk.w;
                     }
-                    st_split16(lane_base + TM_R2_HI + c, lane_base + TM_R2_LO + c, v);
+                    st_split16<BF16>(lane_base + TM_R2_HI + c, lane_base + TM_R2_LO + c, v);
                 }
             }
             tmem_st_wait();
@@ -733,7 +769,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                 const float a = c < 32 ? a21 : a22;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = prelu_f(v[i], a);
-                st_split16(lane_base + TM_R2_HI + c, lane_base + TM_R2_LO + c, v);
+                st_split16<BF16>(lane_base + TM_R2_HI + c, lane_base + TM_R2_LO + c, v);
             }
 #pragma unroll
             for (int c = 0; c < 32; c += 16) {

@@ -151,6 +151,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+
 // ---- 3xTF32 split ------------------------------------------------------------------------------------------------------
 // hi keeps the 10 explicit mantissa bits a tf32 operand has (low 13 bits cleared, so the tensor core reads it exactly
 // whether it truncates or rounds); lo = x - hi is exact in fp32 and carries the next >= 10 bits.

@@ -16,6 +16,8 @@ S, G = 1000, int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 net = synth.Network(S, G, seed=0)
 A_sta, A_src = extract_inputs_adjacencies_cartesian(net.sta, net.grid, 15, 15)
 plan = GraphPlan.cartesian(A_sta, A_src, S, G, device=dev)
+if len(sys.argv) > 2:
+    plan.set_storage(sys.argv[2])          # 'bf16': the fast storage mode
 P = S * G
 g = torch.Generator(device=dev).manual_seed(1)
 Slice = torch.rand((P, 4), device=dev, generator=g) * (torch.rand((P, 4), device=dev, generator=g) < 0.3)
