@@ -305,6 +305,7 @@ class ShardedWorkload(object):
         be = CudaBackend(self.model, A_sta, part.local_graph(rank), S, self.n_local, self.n_owned, attr, A_src, G, dev)
         self.fe = ShardedFrontEnd(part, rank, be, dev)
         self.halo_rows = [len(h) for h in part.halo]
+        self.exchange_events = None
         self.max_t = net.max_moveout()
         self.ex = InputExtractor(be.plan, trv, np.arange(S), S, self.max_t, KERNEL_SIG_T, DT)
         self.picks = synth.make_picks(net, 0.0, day_s, seed=1)
@@ -321,12 +322,10 @@ class ShardedWorkload(object):
         import torch
         m = self.model
         with torch.no_grad():
-            x_spatial, _ = self.fe.forward(Slice, Mask, self.grid, SCALE_REL)
+            x_spatial, _ = self.fe.forward(Slice, Mask, self.grid, SCALE_REL, events=self.exchange_events)
             if self.rank != 0:                      # the read-out heads are per grid node / query point: rank 0 emits them
                 return None, None
-            y = m.TemporalAttention(m.SpatialDirect(x_spatial), self.tq)
-            x = m.TemporalAttention(m.SpatialAttention(x_spatial, self.xq, self.grid), self.tq)
-        return y, x
+            return m._heads(x_spatial, self.grid, self.xq, self.tq)         # genie_heads_grid_fwd / genie_heads_query_fwd
 
     def window_resident(self, w):
         Slice, Mask = self.ex(w * STEP_S)
@@ -433,6 +432,61 @@ def bf16_mode(wl, windows, W, K, use_graph, args):
     m.set_storage('fp32')
     wl.runners(use_graph)
     return out
+
+
+def sharded_leg(args, dev, rank, world, dist, name='c5_2000x200000_sharded'):
+    """One network too large for one GPU (C5: 2000 stations x 200000 grid nodes, P = 4e8) sharded by grid nodes over all
+    ranks (genie_b200/sharded.py): every rank works on the SAME window, one halo exchange (all-to-all of the layer-2 message
+    rows, NCCL over NVLink) + one all-gather of read-in rows per window.  Timed on the device, max over ranks."""
+    import torch
+    from genie_b200 import capi
+    S, G, k_s, k_g = WORKLOADS[name]
+    t_a = time.time()
+    wl = ShardedWorkload(name, dev, rank, world, day_s=min(args.day_seconds, 3600.0))
+    if args.sharded_storage == 'bf16':
+        wl.model._plan = wl.fe.backend.plan
+        wl.model.set_storage('bf16')
+    torch.cuda.synchronize()
+    setup = time.time() - t_a
+    K, W = max(2, min(args.steps, 6)), 3
+    for w in range(W):
+        wl.window_resident(w)
+    dist.barrier()
+    torch.cuda.synchronize()
+    wl.exchange_events = []
+    capi.timing_enable(True)
+    capi.timing_collect(reset=True)
+    beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    beg.record()
+    for w in range(W, W + K):
+        wl.window_resident(w)
+    end.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = beg.elapsed_time(end)
+    kt = capi.timing_collect(reset=True)
+    capi.timing_enable(False)
+    ex_ms = sum(a.elapsed_time(b) for a, b in wl.exchange_events)
+    kern_ms = sum(v[0] for v in kt.values())
+    t = torch.tensor([ms, ex_ms, kern_ms, float(wl.fe.exchange_bytes), float(wl.n_local), float(wl.n_owned)],
+                     dtype=torch.float64, device=dev)
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    ms = float(tmax[0])
+    peak = _peaks()[0]
+    rep = {'workload': name, 'stations': S, 'grid_nodes': G, 'product_nodes': S * G, 'n_gpus': world, 'steps': K, 'warmup': W,
+           'storage': args.sharded_storage, 'value': K / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms / K, 'scaling': 'strong',
+           'halo_grid_nodes_per_rank': wl.halo_rows, 'owned_grid_nodes_max': int(tmax[5]), 'local_grid_nodes_max': int(tmax[4]),
+           'exchange_bytes_per_step_sum': float(t[3]), 'exchange_ms_per_step_max': float(tmax[1]) / K,
+           'exchange_share_of_step': float(tmax[1]) / ms, 'library_kernels_share_of_step_rank_max': float(tmax[2]) / ms,
+           'product_nodes_per_s': S * G * K / (ms * 1e-3),
+           'window_roofline_frac': BYTES_PER_NODE_WINDOW * S * G / (ms / K * 1e-3) / 1e9 / (peak * world),
+           'collectives': 'all_to_all_single (v_b halo rows) + all_gather_into_tensor (read-in rows) per window, NCCL',
+           'setup_s': round(setup, 1)}
+    del wl
+    torch.cuda.empty_cache()
+    return rep
 
 
 def run_genie(args):
@@ -610,6 +664,14 @@ def run_genie(args):
                              'bf16_storage': bf16_mode(wl, windows, W, K, use_graph, args)}
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_reference(args.workload, 5, 1, sample_nodes=2.0e6)[0]   # ~25 s of CPU work
+    if world > 1 and not sharded and not args.no_sharded_leg:
+        # BASELINE.json configs[4]: the C5 network sharded by grid nodes over the same ranks, after the replica legs
+        del wl
+        torch.cuda.empty_cache()
+        rep = sharded_leg(args, dev, rank, world, dist)
+        if rank == 0:
+            line['sharded'] = rep
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -627,6 +689,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-parity-check', action='store_true')
     ap.add_argument('--no-bf16', action='store_true', help='skip the bf16-storage second mode')
+    ap.add_argument('--no-sharded-leg', action='store_true', help='N > 1: skip the grid-sharded C5 leg after the replica legs')
+    ap.add_argument('--sharded-storage', default='fp32', choices=['fp32', 'bf16'])
     ap.add_argument('--graph', default='auto', choices=['auto', 'on', 'off'], help='replay each window as one CUDA graph')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'genie' else args.warmup

@@ -126,29 +126,37 @@ class ShardedFrontEnd(object):
         inv = np.empty(partition.n_grid, dtype=np.int64)
         inv[order[keep]] = np.nonzero(keep)[0]
         self.gather_index = torch.from_numpy(inv).to(self.device)          # global node -> row of the padded all-gather
+        self._pad, self._allr, self.exchange_bytes = None, None, 0
 
     def exchange(self, rows):
-        """rows [n_local, W]: fills the halo part (rows >= n_owned) from the owners' copies."""
-        send = rows.index_select(0, self.send_rows).contiguous()
+        """rows [n_local, W]: fills the halo part (rows >= n_owned) from the owners' copies.  The halo rows of a rank are
+        ordered by owner, so the all-to-all receives straight into the workspace; only the send side needs a gather (a
+        boundary row can be wanted by several peers)."""
+        send = rows.index_select(0, self.send_rows)
         recv = rows[self.n_owned:]
         if recv.shape[0] != sum(self.recv_counts):
             raise RuntimeError('halo size mismatch')
-        W = rows.shape[1]
-        out = torch.empty((sum(self.recv_counts), W), dtype=rows.dtype, device=rows.device)
-        dist.all_to_all_single(out, send, output_split_sizes=self.recv_counts, input_split_sizes=self.send_counts,
+        dist.all_to_all_single(recv, send, output_split_sizes=self.recv_counts, input_split_sizes=self.send_counts,
                                group=self.group)
-        recv.copy_(out)
         return send.numel() * send.element_size()
 
-    def forward(self, Slice_local, Mask_local, pos_grid, scale_rel):
-        """Slice/Mask of the LOCAL product nodes ([n_local * S, 4], owned grid nodes first) -> x_spatial [G,30] (replicated)."""
+    def forward(self, Slice_local, Mask_local, pos_grid, scale_rel, events=None):
+        """Slice/Mask of the LOCAL product nodes ([n_local * S, 4], owned grid nodes first) -> x_spatial [G,30] (replicated).
+        `events`: optional list that receives (begin, end) CUDA events bracketing the halo exchange."""
         be = self.backend
         be.layer1(Slice_local, Mask_local)
-        self.exchange(be.message_rows())
+        if events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        self.exchange_bytes = self.exchange(be.message_rows())
+        if events is not None:
+            e1.record()
+            events.append((e0, e1))
         r_own = be.layer2_readin()                                           # [n_owned, 15]
-        pad = torch.zeros((self.max_owned, r_own.shape[1]), dtype=r_own.dtype, device=r_own.device)
-        pad[:self.n_owned] = r_own
-        allr = torch.empty((self.part.world * self.max_owned, r_own.shape[1]), dtype=r_own.dtype, device=r_own.device)
-        dist.all_gather_into_tensor(allr, pad, group=self.group)
-        read_in = allr.index_select(0, self.gather_index)                    # [G,15] in global node order
+        if self._pad is None or self._pad.device != r_own.device:
+            self._pad = torch.zeros((self.max_owned, r_own.shape[1]), dtype=r_own.dtype, device=r_own.device)
+            self._allr = torch.empty((self.part.world * self.max_owned, r_own.shape[1]), dtype=r_own.dtype, device=r_own.device)
+        self._pad[:self.n_owned] = r_own
+        dist.all_gather_into_tensor(self._allr, self._pad, group=self.group)
+        read_in = self._allr.index_select(0, self.gather_index)              # [G,15] in global node order
         return be.spatial(read_in, pos_grid, scale_rel), read_in
