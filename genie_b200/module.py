@@ -550,7 +550,7 @@ class GCN_Detection_Network_extended(nn.Module):
             raise RuntimeError('set_adjacencies must be called before set_storage')
         if storage == 'bf16':
             da = self.DataAggregation
-            a11, a12 = float(da.activate11.weight.reshape(-1)[0]), float(da.activate12.weight.reshape(-1)[0])
+            a11, a12 = float(da.activate11.weight.detach().reshape(-1)[0]), float(da.activate12.weight.detach().reshape(-1)[0])
             if not (1e-3 < a11 < 1e3 and 1e-3 < a12 < 1e3):
                 raise capi.GenieError('bf16 storage needs activate11 / activate12 slopes in (1e-3, 1e3)')
         self._plan.set_storage(storage)

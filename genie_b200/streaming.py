@@ -150,7 +150,7 @@ class DayProcessor(object):
     resident (`set_day`).  `run(tsteps, tsteps_abs)` returns Out_2 [Q, len(tsteps_abs)] on the device."""
 
     def __init__(self, mz, extractor, locs_use_cart, x_grid_cart, X_query_cart, t_win=6.0, dt_win=0.75, step_size='half',
-                 n_scale_x_grid=1, pick_t_win=10.0):
+                 n_scale_x_grid=1, pick_t_win=10.0, use_runner=True, use_graph=True):
         self.mz, self.ex = mz, extractor
         self.locs, self.grid, self.xq = locs_use_cart, x_grid_cart, X_query_cart
         self.t_win, self.dt_win, self.step_size = float(t_win), float(dt_win), step_size
@@ -160,6 +160,19 @@ class DayProcessor(object):
         self.t_rel = np.arange(-self.t_win / 2.0, self.t_win / 2.0 + self.dt_win, self.dt_win)       # :534, :793
         self.tq = torch.from_numpy(self.t_rel).reshape(-1, 1).float().to(dev)
         self.windows_done, self.windows_skipped = 0, 0
+        self.use_runner, self.use_graph, self._run = use_runner, use_graph, None
+
+    def _runner(self):
+        """WindowRunner for dense plans with tiling tables (>= 32 stations); None -> the two-step path."""
+        if self.use_runner is False:
+            return None
+        plan = self.mz._plan
+        if plan is None or plan is not self.ex.plan or plan.mode != capi.GRAPH_CARTESIAN or plan.tiles is None or \
+                self.ex.node_sta is not None or self.ex._day is None:
+            return None
+        if self._run is None:
+            self._run = WindowRunner(self.mz, self.ex, self.locs, self.grid, self.xq, self.tq, use_graph=self.use_graph)
+        return self._run
 
     def window_pick_count(self, t0):
         """len(lp_times[i0]) of the reference (:787): picks of used stations inside the input window (process_utils.py:476)
@@ -186,12 +199,16 @@ class DayProcessor(object):
         centre = nearest_index(tsteps_abs, np.asarray(tsteps, dtype=np.float64))                    # :765
         cols_all = nearest_index(tsteps_abs, tsteps_abs[centre][:, None] + self.t_rel[None, :])     # :793
         cols_dev = torch.from_numpy(cols_all.astype(np.int32)).to(dev)
+        runner = self._runner()
         for i0, t0 in enumerate(np.asarray(tsteps, dtype=np.float64)):
             if self.window_pick_count(float(t0)) == 0:
                 self.windows_skipped += 1
                 continue
-            Slice, Mask = self.ex(float(t0))
-            _, x = self.mz.forward_fixed_source(Slice, Mask, None, None, None, self.locs, self.grid, self.xq, self.tq)
+            if runner is not None:                 # a1 fused into the front end, the window replayed as one CUDA graph
+                _, x = runner.run(float(t0))
+            else:
+                Slice, Mask = self.ex(float(t0))
+                _, x = self.mz.forward_fixed_source(Slice, Mask, None, None, None, self.locs, self.grid, self.xq, self.tq)
             x = x.reshape(Q, T)
             with torch.cuda.device(dev):
                 capi.check(lib.genie_stack_output_fwd(capi.dptr(x, torch.float32, 'x'), Q, T, n_use,

@@ -6,6 +6,7 @@
     python oracle/gen_golden.py legacy_input     # a1': extract_inputs_from_data_fixed_grids_with_phase_type
     python oracle/gen_golden.py association      # forward_fixed incl. the association branch
     python oracle/gen_golden.py dense_adjacencies # the dense graph builder incl. the time-pointer re-indexing (process_utils.py:701-742)
+    python oracle/gen_golden.py streaming        # the script-body loop of process_continuous_days.py:757-813, executed verbatim
     python oracle/gen_golden.py input_variants   # a1 with use_sign_input / trv_times=None (process_utils.py:594-614)
     python oracle/gen_golden.py subgraph         # sub-graph mode builder (process_utils.py:744-849) + one window on it
     python oracle/gen_golden.py ferndale       # Examples/Ferndale.zip: real stations/grids/picks + trained checkpoint
@@ -485,6 +486,84 @@ def input_variants():
           'negatives with sign input:', int((res['Slice_sign'] < 0).sum()))
 
 
+def streaming():
+    """The caller-side streaming loop (process_continuous_days.py:757-813: per origin-time sample extract_input_from_data ->
+    forward_fixed_source -> `Out_2[:, ip_need] += ...`).  The loop lives in the reference's SCRIPT BODY and cannot be imported;
+    its source lines are read from the reference file at generation time and executed verbatim (one tab of indentation
+    removed) in a namespace holding the same variable names the script defines, with the unmodified reference module /
+    process_utils behind them.  Result: Out_2 for a short synthetic pick stream, step_size 'half' and 'full'."""
+    work = tempfile.mkdtemp(prefix='genie_golden_')
+    for f in ('config.yaml', 'train_config.yaml'):
+        shutil.copy(os.path.join(REF, 'Code', f), work)
+    torch, module, pu, Data = _import_reference(os.path.join(REF, 'Code'), work)
+    from scipy.spatial import cKDTree
+    from genie_b200 import synth
+    lines = open(os.path.join(REF, 'Code', 'process_continuous_days.py')).read().split('\n')
+    beg = [i for i, l in enumerate(lines) if l.strip().startswith('Out_2 = np.zeros((X_query_cart.shape[0], len(tsteps_abs)))')]
+    end = [i for i, l in enumerate(lines) if l.strip().startswith('Out_2_sparse = np.concatenate(')]
+    assert len(beg) == 1 and len(end) == 1 and 750 < beg[0] < end[0] < 830
+    body = '\n'.join(l[1:] if l.startswith('\t') else l for l in lines[beg[0]:end[0] + 1])
+
+    def identity(x):
+        return x
+
+    S_all, n_use, G, k_sta, k_spc, Q, seed = 10, 10, 100, 8, 15, 48, 0
+    net = synth.Network(S_all, G, seed=seed, width_km=60.0)
+    rng = np.random.default_rng(100 + seed)
+    ind_use = np.arange(S_all)
+    max_t = net.max_moveout()
+    sig, dt_embed = 3.0, float(np.round(3.0 / 10.0, 2))
+    P = synth.make_picks(net, 0.0, 240.0, seed=seed + 1, events_per_3h=900.0, false_per_sta_min=1.5)
+    P = P[~((P[:, 0] > 90.0) & (P[:, 0] < 90.0 + max_t + 30.0))]                   # a quiet stretch: windows without picks (:787)
+    trv_times = net.travel_times()
+    torch.manual_seed(seed)
+    mz = module.GCN_Detection_Network_extended(identity, identity, device='cpu')
+    mz.eval()
+    x_query = np.stack((rng.uniform(0, net.width, Q), rng.uniform(0, net.width, Q), rng.uniform(-40000.0, 0.0, Q)), axis=1)
+    attr_scale = np.array([net.width, net.width, 42000.0]).reshape(1, -1)
+    # set-up as process_continuous_days.py:627-634
+    out = pu.extract_inputs_adjacencies(None, net.sta, ind_use, net.grid, None, np.zeros(1), np.zeros(S_all, dtype='int'),
+                                        np.zeros(S_all, dtype='int'), identity, [k_sta, k_spc, 1], device='cpu')
+    A_sta_sta, A_src_src, A_prod_sta, A_prod_src, A_src_in_prod = out[0:5]
+    A_src_in_sta = torch.Tensor(np.concatenate((np.tile(np.arange(n_use), G).reshape(1, -1),
+                                                np.arange(G).repeat(n_use, axis=0).reshape(1, -1)), axis=0)).long()
+    spatial_vals = torch.Tensor(((np.repeat(np.expand_dims(net.grid, axis=1), n_use, axis=1)
+                                  - np.repeat(np.expand_dims(net.sta[ind_use], axis=0), G, axis=0)).reshape(-1, 3)) / attr_scale)
+    mz.set_adjacencies(A_prod_sta, A_prod_src, Data(x=spatial_vals, edge_index=A_src_in_prod), None, A_src_in_sta, A_src_src,
+                       None, None, None, None, torch.Tensor(net.sta[ind_use]), torch.Tensor(net.grid))
+    res = dict(sta=net.sta, grid=net.grid, ind_use=ind_use, trv_times=trv_times, picks=P, max_t=np.float64(max_t),
+               kernel_sig_t=np.float64(sig), dt=np.float64(dt_embed), k_sta=np.int64(k_sta), k_spc=np.int64(k_spc),
+               scale_rel=np.float64(module.scale_rel), scale_t=np.float64(module.scale_t), x_query=x_query,
+               attr_scale=attr_scale, read_in_attr=spatial_vals.numpy(), A_sta_sta=A_sta_sta.numpy(), A_src_src=A_src_src.numpy())
+    res.update(_pack(mz.state_dict()))
+    day_len = 240.0
+    for step_size in ('half', 'full'):
+        # the script's window geometry (:360-379, :411-412, :534, :571) for n_resolution = 9, t_win = 6 s
+        n_resolution, t_win = 9, 6.0
+        dt_win = np.diff(np.linspace(-t_win / 2.0, t_win / 2.0, n_resolution))[0]
+        step = n_resolution * dt_win if step_size == 'full' else int(np.floor(n_resolution / 2)) * dt_win
+        n_overlap = 1.0 if step_size == 'full' else 2.0
+        tsteps = np.arange(np.maximum(0.0, P[:, 0].min() - max_t), np.minimum(day_len, P[:, 0].max()), step)
+        tsteps_abs = np.arange(-t_win / 2.0, day_len + t_win / 2.0 + dt_win, dt_win)
+        ns = dict(np=np, torch=torch, X_query_cart=torch.Tensor(x_query), tsteps_abs=tsteps_abs,
+                  times_need=[tsteps[j:j + 1] for j in range(len(tsteps))], tree_tsteps=cKDTree(tsteps_abs.reshape(-1, 1)),
+                  x_grid_ind_list=[0], use_updated_input=True, extract_input_from_data=pu.extract_input_from_data,
+                  trv_pairwise=None, P=P, ind_use=ind_use, locs=net.sta, x_grids=[net.grid], A_src_in_sta_l=[A_src_in_sta.numpy()],
+                  x_grids_trv=[trv_times], max_t=max_t, pred_params=[t_win, sig, t_win / 2.0, 25e3], dt_embed_discretize=dt_embed,
+                  use_sign_input=False, device='cpu', use_phase_types=True, mz_list=[mz], ftrns1=identity, locs_use=net.sta[ind_use],
+                  x_grids_cart_torch=[torch.Tensor(net.grid)],
+                  tq=torch.arange(-t_win / 2.0, t_win / 2.0 + dt_win, dt_win).reshape(-1, 1).float(), t_win=t_win, dt_win=dt_win,
+                  step_size=step_size, n_overlap=n_overlap, n_scale_x_grid=1)
+        exec(compile(body, 'process_continuous_days.py:%d-%d' % (beg[0] + 1, end[0] + 1), 'exec'), ns)
+        res['Out_2_' + step_size] = ns['Out_2']
+        res['tsteps_' + step_size], res['tsteps_abs_' + step_size] = tsteps, tsteps_abs
+        res['Out_2_sparse_' + step_size] = ns['Out_2_sparse']
+        print('streaming', step_size, 'windows', len(tsteps), 'Out_2 max %.6f sum %.6f nnz(>0.01) %d' % (
+            ns['Out_2'].max(), ns['Out_2'].sum(), len(ns['Out_2_sparse'])))
+    res['t_win'], res['dt_win'], res['loop_lines'] = np.float64(6.0), np.float64(0.75), np.array([beg[0] + 1, end[0] + 1])
+    np.savez_compressed(os.path.join(GOLD, 'streaming_10x100.npz'), **res)
+
+
 if __name__ == '__main__':
     mode = sys.argv[1] if len(sys.argv) > 1 else 'synthetic'
     if mode == 'synthetic':
@@ -507,6 +586,8 @@ if __name__ == '__main__':
         dense_adjacencies()
     elif mode == 'input_variants':
         input_variants()
+    elif mode == 'streaming':
+        streaming()
     elif mode == 'ferndale':
         from gen_golden_ferndale import ferndale
         ferndale()

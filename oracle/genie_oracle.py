@@ -682,9 +682,10 @@ def init_state_association(sd, seed=7, scale=1.0):
 
 # --------------------------------------------------------------------------------------------------------------------
 # caller-side streaming loop: process_continuous_days.py:757-813, one source grid,
-# `use_updated_input: True`.  The loop lives in the reference's script body (not importable), so this restatement is
-# checked by reading only: parity UNPINNED for this function (its per-window pieces, input_scatter and
-# forward_fixed_source, are pinned above).
+# `use_updated_input: True`.  The loop lives in the reference's script body (not importable); it is PINNED by
+# tests/golden/streaming_10x100.npz, which oracle/gen_golden.py `streaming` produced by executing those source lines verbatim
+# (read from the reference file at generation time) over the unmodified reference module / process_utils
+# (tests/test_oracle_golden.py::test_streaming_loop_matches_reference).
 # --------------------------------------------------------------------------------------------------------------------
 
 

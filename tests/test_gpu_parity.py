@@ -1009,6 +1009,57 @@ def test_day_processor_matches_oracle_loop(step_size):
     assert np.array_equal(nearest_index(tsteps_abs, t), cKDTree(tsteps_abs.reshape(-1, 1)).query(t.reshape(-1, 1))[1])
 
 
+@pytest.mark.parametrize('step_size', ['half', 'full'])
+def test_day_processor_matches_reference_loop(step_size):
+    """DayProcessor against Out_2 of the REFERENCE's own loop body (process_continuous_days.py:757-813, executed verbatim by
+    oracle/gen_golden.py `streaming` over the unmodified reference): overlapping windows, skipped windows, both step sizes."""
+    from genie_b200.process_utils import InputExtractor
+    from genie_b200.streaming import DayProcessor
+    dev = _dev()
+    d, sd = load_golden('streaming_10x100')
+    S, G = len(d['ind_use']), d['grid'].shape[0]
+    m = _model(sd, dev, float(d['scale_rel']), float(d['scale_t']))
+    m.set_adjacencies_cartesian(torch.from_numpy(d['A_sta_sta']), torch.from_numpy(d['A_src_src']),
+                                torch.from_numpy(d['read_in_attr']).to(dev), S, G, device=dev)
+    ex = InputExtractor(m._plan, d['trv_times'], d['ind_use'], d['sta'].shape[0], float(d['max_t']), float(d['kernel_sig_t']),
+                        float(d['dt']))
+    ex.set_day(d['picks'])
+    dp = DayProcessor(m, ex, torch.from_numpy(d['sta'][d['ind_use']]).float().to(dev), torch.from_numpy(d['grid']).float().to(dev),
+                      torch.from_numpy(d['x_query']).float().to(dev), t_win=float(d['t_win']), dt_win=float(d['dt_win']),
+                      step_size=step_size)
+    out = dp.run(d['tsteps_' + step_size], d['tsteps_abs_' + step_size]).cpu().numpy()
+    want = d['Out_2_' + step_size]
+    assert dp.windows_skipped > 0 and dp.windows_done > 0
+    assert rel_err(out, want) < TOL
+    assert np.array_equal(np.abs(out).sum(axis=0) > 0, np.abs(want).sum(axis=0) > 0)
+
+
+def test_day_processor_fused_runner_equals_two_step_loop():
+    """The streaming loop on the fused window path (WindowRunner: genie_window_fwd + heads as one CUDA graph per window) and on
+    the reference-shaped two-step path produce the same Out_2, bit for bit (100 stations: a plan with tiling tables)."""
+    from genie_b200 import synth
+    from genie_b200.module import GCN_Detection_Network_extended
+    from genie_b200.process_utils import InputExtractor, extract_inputs_adjacencies_cartesian
+    from genie_b200.streaming import DayProcessor
+    from oracle import genie_oracle as go
+    dev = _dev()
+    S, G = 100, 800
+    net = synth.Network(S, G, seed=5)
+    A_sta, A_src = extract_inputs_adjacencies_cartesian(net.sta, net.grid, 15, 15)
+    m = GCN_Detection_Network_extended(None, None, scale_rel=30000.0, device=dev).eval()
+    m.load_state_dict(go.init_state(seed=4), strict=False)
+    m.set_adjacencies_cartesian(A_sta, A_src, torch.from_numpy(net.read_in_offsets(30000.0)).to(dev), S, G, device=dev)
+    ex = InputExtractor(m._plan, net.travel_times(), np.arange(S), S, net.max_moveout(), 3.0, 0.3)
+    ex.set_day(synth.make_picks(net, 0.0, 300.0, seed=6, false_per_sta_min=3.0))
+    xq = torch.from_numpy(np.random.default_rng(2).uniform(0, net.width, (200, 3))).float().to(dev)
+    xq[:, 2] = -xq[:, 2] / net.width * 40000.0
+    args = (m, ex, torch.from_numpy(net.sta).float().to(dev), torch.from_numpy(net.grid).float().to(dev), xq)
+    tsteps, tsteps_abs = np.arange(0.0, 150.0, 3.0), np.arange(-3.0, 303.0 + 0.75, 0.75)
+    a = DayProcessor(*args, use_runner=True).run(tsteps, tsteps_abs)
+    b = DayProcessor(*args, use_runner=False).run(tsteps, tsteps_abs)
+    assert torch.equal(a, b) and float(a.abs().max()) > 0
+
+
 # ---- training path (BASELINE.json configs[2]): forward with gradients, loss and Adam steps against the oracle ------------------
 
 @pytest.mark.parametrize('mode,C', [(0, 30), (1, 30), (1, 15), (2, 34), (0, 1)])

@@ -256,3 +256,26 @@ def test_input_variants_match_reference():
         assert np.array_equal(Sl, d['Slice_' + tag]), tag
         assert np.array_equal(Mk, d['Mask_' + tag]), tag
     assert (d['Slice_sign'] < 0).sum() > 100 and np.array_equal(np.abs(d['Slice_sign']) > 0.01, d['Mask_sign'] > 0)
+
+
+@pytest.mark.parametrize('step_size', ['half', 'full'])
+def test_streaming_loop_matches_reference(step_size):
+    """The caller-side loop of process_continuous_days.py:757-813 (executed verbatim by oracle/gen_golden.py `streaming`):
+    oracle.continuous_day_stack reproduces the reference's Out_2, including the windows it skips for lack of picks."""
+    d, sd = load_golden('streaming_10x100')
+    S, G = len(d['ind_use']), d['grid'].shape[0]
+    A_sta, A_src = torch.from_numpy(d['A_sta_sta']), torch.from_numpy(d['A_src_src'])
+    A_ps = (A_sta.repeat(1, G) + S * torch.arange(G).repeat_interleave(A_sta.shape[1]).view(1, -1)).contiguous()
+    A_pg = (S * A_src.repeat(1, S) + torch.arange(S).repeat_interleave(A_src.shape[1]).view(1, -1)).contiguous()
+    A_sip = torch.stack((torch.arange(S * G), torch.arange(G).repeat_interleave(S)), dim=0)
+    A_sis = np.stack((np.tile(np.arange(S), G), np.repeat(np.arange(G), S)), axis=0)
+    out, n_done = go.continuous_day_stack(
+        sd, d['picks'], d['tsteps_' + step_size], d['tsteps_abs_' + step_size], d['ind_use'], d['sta'].shape[0], A_sis,
+        d['trv_times'], float(d['max_t']), float(d['kernel_sig_t']), float(d['dt']), A_ps, A_pg, torch.from_numpy(d['read_in_attr']),
+        A_sip, A_src, torch.from_numpy(d['grid']).float(), torch.from_numpy(d['x_query']).float(), float(d['scale_rel']),
+        float(d['scale_t']), t_win=float(d['t_win']), dt_win=float(d['dt_win']), step_size=step_size)
+    want = d['Out_2_' + step_size]
+    assert 0 < n_done < len(d['tsteps_' + step_size])          # some windows were skipped (no picks), some processed
+    assert np.abs(out - want).max() <= 1e-6 * max(np.abs(want).max(), 1e-30)
+    cols = np.abs(want).sum(axis=0) > 0
+    assert np.array_equal(np.abs(out).sum(axis=0) > 0, cols)
