@@ -246,10 +246,10 @@ class Workload(object):
         """The streaming fast path (genie_b200.streaming.WindowRunner): a1 fused into the front end + heads, one parameter
         block per window; `use_graph` replays the whole window as one CUDA graph (launch-bound sizes)."""
         from genie_b200.streaming import WindowRunner
-        self.use_graph = bool(use_graph)
         self.runner = WindowRunner(self.model, self.ex, self.locs, self.grid, self.xq, self.tq, use_graph=use_graph)
         self.runner_e2e = WindowRunner(self.model, self.ex, self.locs, self.grid, self.xq, self.tq, use_graph=use_graph,
                                        source='staged', max_window_picks=self.runner.max_window_picks)
+        self.use_graph = self.runner.use_graph
 
     def window_resident(self, w):
         """Hot path with everything resident in HBM."""
@@ -369,10 +369,13 @@ def closure_parity(wl, w, n_clusters=5, cluster=4, tol=1e-4):
     y, x = y.clone(), x.clone()
     r = wl.runner
     # the same fused kernels once more, this time materialising their inputs and intermediates
-    _, latent, readin, Slice, Mask = ops.window_fwd(m._plan, m._packed_weights(wl.dev), r.wp_dev, r.max_window_picks, r.n_extra,
-                                                    r.picks, ex.sta_perm, ex.ind_use, ex.trv_times, r.series, r.n_ts_max,
-                                                    m._read_in_attr, wl.grid, float(m.scale_rel), want_inputs=True,
-                                                    want_latent=True, want_readin=True)
+    if not r.fused:          # plans without tiling tables (C1): the runner is the two-step sequence itself
+        Slice, Mask = ex(t0)
+        _, latent, readin = m.front_end(Slice, Mask, wl.grid, want_latent=True, want_readin=True, locs_use_cart=wl.locs)
+    else:
+        _, latent, readin, Slice, Mask = ops.window_fwd(m._plan, m._packed_weights(wl.dev), r.wp_dev, r.max_window_picks, r.n_extra,
+            r.picks, ex.sta_perm, ex.ind_use, ex.trv_times, r.series, r.n_ts_max, m._read_in_attr, wl.grid,
+            float(m.scale_rel), want_inputs=True, want_latent=True, want_readin=True)
     S2, M2, tb = ex(t0, want_time_bin=True)                              # the stand-alone a1 kernels (integer time bins)
     y2, x2 = m.forward_fixed_source(S2, M2, None, None, None, wl.locs, wl.grid, wl.xq, wl.tq)
     fused_same = bool(torch.equal(S2, Slice) and torch.equal(M2, Mask) and torch.equal(y2, y) and torch.equal(x2, x))
@@ -658,7 +661,7 @@ def run_genie(args):
         }
         if not sharded and not args.no_parity_check:
             line['parity_check'] = closure_parity(wl, windows[W])          # the first timed window, against the CPU oracle
-        if not sharded and not args.no_bf16:
+        if not sharded and not args.no_bf16 and wl.runner.fused:
             line['modes'] = {'fp32_parity': {'value': line['value'], 'ms_per_step': line['ms_per_step'],
                                              'max_rel_vs_oracle': (line.get('parity_check') or {}).get('max_rel')},
                              'bf16_storage': bf16_mode(wl, windows, W, K, use_graph, args)}

@@ -53,8 +53,11 @@ class WindowRunner(object):
         plan = mz._plan
         if plan is None or plan is not extractor.plan:
             raise capi.GenieError('WindowRunner: the model and the extractor must share one GraphPlan')
-        if plan.mode != capi.GRAPH_CARTESIAN or plan.tiles is None or extractor.node_sta is not None:
-            raise capi.GenieError('WindowRunner needs a CARTESIAN plan with tiling tables (dense mode)')
+        # genie_window_fwd needs a dense plan with tiling tables (>= 32 stations); other plans (tiny networks, sub-graph mode)
+        # run the reference-shaped two-step sequence eagerly: extract_input -> Slice / Mask -> forward_fixed_source
+        self.fused = plan.mode == capi.GRAPH_CARTESIAN and plan.tiles is not None and extractor.node_sta is None
+        if not self.fused:
+            self.use_graph = False
         if mz.use_absolute_pos and locs_use_cart is None:
             raise capi.GenieError('use_absolute_pos: WindowRunner needs locs_use_cart')
         self.dev = dev = plan.device
@@ -120,6 +123,15 @@ class WindowRunner(object):
 
     def run(self, t0, picks_host=None):
         t0 = float(t0)
+        if not self.fused:
+            picks = None
+            if self.source != 'resident':
+                n = int(picks_host.shape[0])
+                self.picks[:n].copy_(picks_host, non_blocking=True)
+                picks = self.picks[:n]
+            self.windows += 1
+            Slice, Mask = self.ex(t0, picks)
+            return self.mz.forward_fixed_source(Slice, Mask, None, None, None, self.locs, self.grid, self.xq, self.tq)
         with torch.no_grad():
             if self.source == 'resident':
                 lo, hi = self.ex.window_rows(t0)
