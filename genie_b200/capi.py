@@ -74,6 +74,13 @@ class InputParams(ctypes.Structure):
                 ('n_sta_use', ctypes.c_int32), ('use_sign_input', ctypes.c_int32), ('reserved_', ctypes.c_int32)]
 
 
+class MlpDesc(ctypes.Structure):
+    """genie_mlp_desc_t."""
+    _fields_ = [('n_rows', ctypes.c_int64), ('n_parts', ctypes.c_int32), ('n_out', ctypes.c_int32),
+                ('width', ctypes.c_int32 * 4), ('ld', ctypes.c_int32 * 4), ('x', ctypes.c_void_p * 4),
+                ('weight', ctypes.c_void_p), ('bias', ctypes.c_void_p), ('slope', ctypes.c_void_p)]
+
+
 class WindowParams(ctypes.Structure):
     """genie_window_params_t: the device-resident per-window block of genie_window_fwd."""
     _fields_ = [('prm', InputParams), ('pick_lo', ctypes.c_int64), ('pick_hi', ctypes.c_int64)]
@@ -106,6 +113,10 @@ SIGNATURES = {
                                             ctypes.c_float, _P, _P]),
     'genie_kron_spmm_fwd': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, _P, _P, _P, _P, ctypes.c_int,
                                            ctypes.c_int, _P, ctypes.c_int, _P]),
+    'genie_node_mlp_partial_rows': (ctypes.c_int, []),
+    'genie_node_mlp_fwd': (ctypes.c_int, [ctypes.POINTER(MlpDesc), _P, ctypes.c_int32, _P]),
+    'genie_node_mlp_bwd': (ctypes.c_int, [ctypes.POINTER(MlpDesc), _P, ctypes.c_int32, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p),
+                                          ctypes.POINTER(ctypes.c_int32), _P, _P]),
     'genie_stack_output_fwd': (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, ctypes.c_float, _P, ctypes.c_int64,
                                               _P]),
     'genie_knn_fwd': (ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int, _P, _P]),

@@ -37,7 +37,8 @@ const char* const kKernelNames[KID_COUNT] = {"pack_weights_kernel", "input_serie
                                              "src_mean32_kernel",   "src_mean16_kernel",   "da_layer1_s_kernel",
                                              "da_layer2_s_kernel",  "heads_grid_kernel",   "heads_query_kernel",
                                              "assoc_grid_pre_kernel", "assoc_init_kernel", "assoc_layer1_kernel",
-                                             "assoc_layer2_kernel", "assoc_collapse_kernel", "knn_kernel", "stack_output_kernel", "kron_spmm_kernel"};
+                                             "assoc_layer2_kernel", "assoc_collapse_kernel", "knn_kernel", "stack_output_kernel", "kron_spmm_kernel",
+                                             "node_mlp_fwd_kernel", "node_mlp_bwd_kernel"};
 }  // namespace
 
 TimedLaunch::TimedLaunch(int kid_, cudaStream_t st_) : kid(kid_), st(st_), slot(nullptr) {
@@ -420,6 +421,22 @@ int genie_kron_spmm_fwd(int mode, int n_sta, int n_grid, int64_t n_prod, const i
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     return launch_kron_spmm(mode, n_sta, n_prod, rowptr_dev, col_dev, val_dev, x_dev, ld_x, n_ch, out_dev, ld_out, sms,
                             static_cast<cudaStream_t>(stream));
+}
+
+// ---- per-node dense layers of the training path ----------------------------------------------------------------------------
+static int current_sm_count() {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+int genie_node_mlp_partial_rows(void) { return mlp_partial_rows(current_sm_count()); }
+int genie_node_mlp_fwd(const genie_mlp_desc_t* desc, float* y_dev, int32_t ld_y, void* stream) {
+    return launch_node_mlp_fwd(desc, y_dev, ld_y, current_sm_count(), static_cast<cudaStream_t>(stream));
+}
+int genie_node_mlp_bwd(const genie_mlp_desc_t* desc, const float* y_dev, int32_t ld_y, const float* gy_dev, int32_t ld_gy,
+                       float* const* gx_dev, const int32_t* ld_gx, float* partial_dev, void* stream) {
+    return launch_node_mlp_bwd(desc, y_dev, ld_y, gy_dev, ld_gy, gx_dev, ld_gx, partial_dev, current_sm_count(),
+                               static_cast<cudaStream_t>(stream));
 }
 
 // ---- output stacking of the streaming loop ------------------------------------------------------------

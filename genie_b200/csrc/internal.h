@@ -124,6 +124,8 @@ enum KernelId {
     KID_KNN,
     KID_STACK,
     KID_KRON_SPMM,
+    KID_NODE_MLP_FWD,
+    KID_NODE_MLP_BWD,
     KID_COUNT
 };
 // Brackets one kernel launch with cudaEvents on its stream when timing is enabled (no-op otherwise).
@@ -224,6 +226,10 @@ int launch_stack_output(const float* x, int Q, int T, int n_use, const int32_t* 
                         cudaStream_t st);
 int launch_kron_spmm(int mode, int S, int64_t P, const int64_t* rowptr, const int32_t* col, const float* val, const float* X,
                      int ld_x, int C, float* out, int ld_o, int sm_count, cudaStream_t st);
+int mlp_partial_rows(int sm_count);
+int launch_node_mlp_fwd(const genie_mlp_desc_t* d, float* y, int ld_y, int sm_count, cudaStream_t st);
+int launch_node_mlp_bwd(const genie_mlp_desc_t* d, const float* y, int ld_y, const float* gy, int ld_gy, float* const* gx,
+                        const int* ld_gx, float* partial, int sm_count, cudaStream_t st);
 int launch_knn(const float* x, int n_x, const float* y, int n_y, int k, int64_t* idx_out, cudaStream_t st);
 int launch_input_nearest(const genie_nearest_params_t* prm, const double* t_all, const double* t_p, const double* t_s,
                          const int32_t* ind_use, const float* trv_times, float* slice_out, float* mask_out, cudaStream_t st);

@@ -533,3 +533,64 @@ def window_fwd(plan, packed, wp_dev, max_window_picks, n_extra, picks, sta_perm,
             capi.dptr(Mask), capi.dptr(latent), capi.dptr(readin), capi.dptr(x_spatial), capi.dptr(plan.workspace()),
             capi.stream_ptr(dev)))
     return x_spatial, latent, readin, Slice, Mask
+
+
+# ---- per-node dense layers of the training path (genie_node_mlp_fwd / genie_node_mlp_bwd) -------------------------------------
+
+def _mlp_desc(parts, weight, bias, slope):
+    n = int(parts[0].shape[0])
+    if not (1 <= len(parts) <= 4):
+        raise capi.GenieError('node_mlp: 1..4 input parts')
+    d = capi.MlpDesc()
+    d.n_rows, d.n_parts, d.n_out = n, len(parts), int(weight.shape[0])
+    n_in = 0
+    for i, x in enumerate(parts):
+        if x.dim() != 2 or x.shape[0] != n or x.dtype != F32 or x.stride(1) != 1:
+            raise capi.GenieError('node_mlp: parts must be fp32 [n, w] tensors with unit column stride')
+        d.width[i], d.ld[i] = int(x.shape[1]), int(x.stride(0)) if n > 1 else int(x.shape[1])
+        d.x[i] = capi.dptr(x, F32, 'part %d' % i) if n else None
+        n_in += int(x.shape[1])
+    if tuple(weight.shape) != (d.n_out, n_in) or not weight.is_contiguous():
+        raise capi.GenieError('node_mlp: weight must be contiguous [n_out, %d]' % n_in)
+    d.weight = capi.dptr(weight, F32, 'weight')
+    d.bias = capi.dptr(bias, F32, 'bias') if bias is not None else None
+    d.slope = capi.dptr(slope, F32, 'slope') if slope is not None else None
+    return d, n_in
+
+
+def node_mlp_supported(parts, weight):
+    return len(parts) <= 4 and weight.shape[0] <= 32 and sum(int(x.shape[1]) for x in parts) <= 104
+
+
+def node_mlp_fwd(parts, weight, bias, slope):
+    """y = PReLU_slope(Linear([parts...])) without materialising the concatenation (slope None: no activation)."""
+    d, _ = _mlp_desc(parts, weight, bias, slope)
+    y = torch.empty((d.n_rows, d.n_out), dtype=F32, device=weight.device)
+    with torch.cuda.device(weight.device):
+        capi.check(capi.load().genie_node_mlp_fwd(ctypes.byref(d), capi.dptr(y), d.n_out, capi.stream_ptr(weight.device)))
+    return y
+
+
+def node_mlp_bwd(parts, weight, bias, slope, y, gy, need_gx):
+    """Gradients of node_mlp_fwd: (gx per part or None, gW, gb, gslope)."""
+    d, n_in = _mlp_desc(parts, weight, bias, slope)
+    dev = weight.device
+    gy = gy.contiguous()
+    lib = capi.load()
+    with torch.cuda.device(dev):
+        rows = int(lib.genie_node_mlp_partial_rows())
+    pld = d.n_out * n_in + d.n_out + 1
+    partial = torch.empty((rows, pld), dtype=F32, device=dev)
+    gx = [torch.empty_like(x, memory_format=torch.contiguous_format) if (need and d.n_rows) else None
+          for x, need in zip(parts, need_gx)]
+    ptrs = (ctypes.c_void_p * 4)(*[(capi.dptr(g) if g is not None else None) for g in gx] + [None] * (4 - len(gx)))
+    lds = (ctypes.c_int32 * 4)(*[(int(g.shape[1]) if g is not None else 0) for g in gx] + [0] * (4 - len(gx)))
+    with torch.cuda.device(dev):
+        capi.check(lib.genie_node_mlp_bwd(ctypes.byref(d), capi.dptr(y, F32) if slope is not None else None, d.n_out,
+                                          capi.dptr(gy, F32, 'gy'), d.n_out, ptrs, lds, capi.dptr(partial), capi.stream_ptr(dev)))
+    tot = partial.sum(0)
+    gW = tot[:d.n_out * n_in].view(d.n_out, n_in)
+    gb = tot[d.n_out * n_in:d.n_out * n_in + d.n_out]
+    ga = tot[d.n_out * n_in + d.n_out:]
+    gx = [g if g is not None else (torch.zeros_like(x) if need else None) for g, x, need in zip(gx, parts, need_gx)]
+    return gx, gW, gb, ga

@@ -105,6 +105,57 @@ def lin(layer, x):
     return layer(x)
 
 
+class NodeMLP(torch.autograd.Function):
+    """`activate(Linear(torch.cat(parts, dim=1)))` over product-node-sized tensors, forward and backward in ONE kernel each
+    (genie_node_mlp_fwd / genie_node_mlp_bwd, csrc/mlp_kernels.cu): no concatenated tensor, no separate addmm / prelu /
+    weight-gradient GEMM.  `slope` is the 1-element nn.PReLU weight, or None for a bare Linear."""
+
+    @staticmethod
+    def forward(ctx, weight, bias, slope, *parts):
+        parts = tuple(p if (p.dtype == torch.float32 and p.stride(1) == 1) else p.float().contiguous() for p in parts)
+        y = ops.node_mlp_fwd(parts, weight, bias, slope)
+        ctx.has_slope = slope is not None
+        ctx.save_for_backward(weight, bias, slope if slope is not None else weight.new_zeros(1), y, *parts)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        weight, bias, slope, y = ctx.saved_tensors[:4]
+        parts = ctx.saved_tensors[4:]
+        need_gx = list(ctx.needs_input_grad[3:])
+        gx, gW, gb, ga = ops.node_mlp_bwd(parts, weight, bias, slope if ctx.has_slope else None, y, gy, need_gx)
+        return (gW, gb, ga.view_as(slope) if ctx.has_slope else None) + tuple(gx)
+
+
+MLP_MIN_ROWS = 4096
+
+
+def mlp(layer, act, *parts):
+    """`act(layer(torch.cat(parts, dim=1)))` (act None: no activation).  Product-node-sized CUDA inputs of the module shapes
+    go through the fused kernels; anything else (tiny inputs, oversize layers, a zero PReLU slope, whose gradient the fused
+    backward cannot recover from the activation's output) through the torch ops."""
+    w = layer.weight
+    n = parts[0].shape[0]
+    if n >= MLP_MIN_ROWS and w.is_cuda and ops.node_mlp_supported(parts, w) and not _ZERO_SLOPE.get(id(act), False):
+        return NodeMLP.apply(w, layer.bias, act.weight if act is not None else None, *parts)
+    x = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+    y = lin(layer, x)
+    return act(y) if act is not None else y
+
+
+_ZERO_SLOPE = {}
+
+
+def note_zero_slopes(model):
+    """One device read per call of forward_train: which nn.PReLU modules currently have slope 0 (fused backward not usable)."""
+    acts = [m for m in model.modules() if isinstance(m, torch.nn.PReLU)]
+    z = (torch.cat([a.weight.detach().reshape(-1)[:1] for a in acts]) == 0).cpu().numpy()
+    _ZERO_SLOPE.clear()
+    for a, f in zip(acts, z):
+        if f:
+            _ZERO_SLOPE[id(a)] = True
+
+
 # ---- the modules of module.py as differentiable functions of the parameter holders ----------------------------------------
 
 def _expand_edge_means(model, kg_sta):
@@ -116,38 +167,44 @@ def _expand_edge_means(model, kg_sta):
     return m_sta.repeat(kg_sta.n_grid, 1), m_src.repeat_interleave(kg_sta.n_sta, dim=0)
 
 
+def _agg_layer(da, l_a, l_b, act, tr, msg_a, msg_b, kg_sta, kg_src, tail_sta, tail_src):
+    """[l_a([tr | mean_sta msg_a | tail]) | l_b([tr | mean_src msg_b | tail])] with `act` applied (one slope: applying it to
+    the halves is applying it to the concatenation, module.py:92, :96)."""
+    t1 = mlp(l_a, act, tr, mean_aggregate(msg_a, kg_sta), tail_sta)
+    t2 = mlp(l_b, act, tr, mean_aggregate(msg_b, kg_src), tail_src)
+    return torch.cat((t1, t2), dim=1)
+
+
 def data_aggregation(da, Slice, Mask, kg_sta, kg_src, edge_means=None):
     """DataAggregation.forward (module.py:85-98) / DataAggregationEdges.forward (:143-157)."""
-    tr = da.activate(lin(da.init_trns, torch.cat((Slice, Mask), dim=-1)))
-    cat = (lambda a, m, e: torch.cat((a, m, e, Mask), dim=1)) if edge_means is not None else \
-        (lambda a, m, e: torch.cat((a, m, Mask), dim=1))
-    e_sta, e_src = edge_means if edge_means is not None else (None, None)
-    tr1 = lin(da.l1_t1_2, cat(tr, mean_aggregate(da.activate11(tr), kg_sta), e_sta))
-    tr2 = lin(da.l1_t2_2, cat(tr, mean_aggregate(da.activate12(tr), kg_src), e_src))
-    tr = da.activate1(torch.cat((tr1, tr2), dim=1))
-    tr1 = lin(da.l2_t1_2, cat(tr, mean_aggregate(da.activate21(lin(da.l2_t1_1, tr)), kg_sta), e_sta))
-    tr2 = lin(da.l2_t2_2, cat(tr, mean_aggregate(da.activate22(lin(da.l2_t2_1, tr)), kg_src), e_src))
-    return da.activate2(torch.cat((tr1, tr2), dim=1))
+    tr = mlp(da.init_trns, da.activate, Slice, Mask)
+    if edge_means is not None:          # the edge-feature channels sit between the aggregate and the mask (:150-156)
+        tail_sta, tail_src = torch.cat((edge_means[0], Mask), dim=1), torch.cat((edge_means[1], Mask), dim=1)
+    else:
+        tail_sta = tail_src = Mask
+    tr = _agg_layer(da, da.l1_t1_2, da.l1_t2_2, da.activate1, tr, da.activate11(tr), da.activate12(tr), kg_sta, kg_src,
+                    tail_sta, tail_src)
+    return _agg_layer(da, da.l2_t1_2, da.l2_t2_2, da.activate2, tr, mlp(da.l2_t1_1, da.activate21, tr),
+                      mlp(da.l2_t2_1, da.activate22, tr), kg_sta, kg_src, tail_sta, tail_src)
 
 
 def data_aggregation_association(da, s, latent, mask1, mask2, kg_sta, kg_src, edge_means=None):
     """DataAggregationAssociationPhase.forward (module.py:387-403) / ...Edges.forward (:442-467)."""
     mask = torch.cat((mask1, mask2), dim=-1)
-    tr = da.activate(lin(da.init_trns, torch.cat((s, latent, mask), dim=-1)))
-    cat = (lambda a, m, e: torch.cat((a, m, e, mask), dim=1)) if edge_means is not None else \
-        (lambda a, m, e: torch.cat((a, m, mask), dim=1))
-    e_sta, e_src = edge_means if edge_means is not None else (None, None)
-    tr1 = lin(da.l1_t1_2, cat(tr, mean_aggregate(da.activate11(lin(da.l1_t1_1, tr)), kg_sta), e_sta))
-    tr2 = lin(da.l1_t2_2, cat(tr, mean_aggregate(da.activate12(lin(da.l1_t2_1, tr)), kg_src), e_src))
-    tr = da.activate1(torch.cat((tr1, tr2), dim=1))
-    tr1 = lin(da.l2_t1_2, cat(tr, mean_aggregate(da.activate21(lin(da.l2_t1_1, tr)), kg_sta), e_sta))
-    tr2 = lin(da.l2_t2_2, cat(tr, mean_aggregate(da.activate22(lin(da.l2_t2_1, tr)), kg_src), e_src))
-    return da.activate2(torch.cat((tr1, tr2), dim=1))
+    tr = mlp(da.init_trns, da.activate, s, latent, mask)
+    if edge_means is not None:
+        tail_sta, tail_src = torch.cat((edge_means[0], mask), dim=1), torch.cat((edge_means[1], mask), dim=1)
+    else:
+        tail_sta = tail_src = mask
+    tr = _agg_layer(da, da.l1_t1_2, da.l1_t2_2, da.activate1, tr, mlp(da.l1_t1_1, da.activate11, tr),
+                    mlp(da.l1_t2_1, da.activate12, tr), kg_sta, kg_src, tail_sta, tail_src)
+    return _agg_layer(da, da.l2_t1_2, da.l2_t2_2, da.activate2, tr, mlp(da.l2_t1_1, da.activate21, tr),
+                      mlp(da.l2_t2_1, da.activate22, tr), kg_sta, kg_src, tail_sta, tail_src)
 
 
 def bipartite_read_in(ri, x_latent, attr, node_grid, n_grid, Mask):
     """BipartiteGraphOperator.forward (module.py:224-229): masked per-node MLP summed onto the node's grid node."""
-    h = Mask.max(1, keepdim=True)[0] * ri.activate1(lin(ri.fc1, torch.cat((x_latent, attr), dim=-1)))
+    h = Mask.max(1, keepdim=True)[0] * mlp(ri.fc1, ri.activate1, x_latent, attr)
     xg = h.new_zeros((n_grid, h.shape[1])).index_add_(0, node_grid, h)
     return ri.activate2(ri.fc2(xg))
 
@@ -168,8 +225,8 @@ def spatial_aggregation(sa, x, A_src, pos, scale_rel):
 def bipartite_read_out(ro, y_latent, attr, node_grid, mask_out):
     """BipartiteGraphReadOutOperator.forward (module.py:344-352) for the read-out graph [g(i); i]."""
     mj = mask_out[node_grid]
-    h = mj * ro.activate1(lin(ro.fc1, torch.cat((y_latent[node_grid], attr), dim=-1)))
-    return ro.activate2(lin(ro.fc2, h)), mj
+    h = mj * mlp(ro.fc1, ro.activate1, y_latent[node_grid], attr)
+    return mlp(ro.fc2, ro.activate2, h), mj
 
 
 def local_slice_collapse(cm, A_edges, dt_partition, tpick, ipick, phase_label, s, tlatent, k_infer=10):
@@ -203,6 +260,7 @@ def forward_train(model, Slice, Mask, A_Lg_in_src, A_src, A_edges_p, A_edges_s, 
         model._kron = (key,) + build_kron_graphs(plan)
     kg_sta, kg_src = model._kron[1], model._kron[2]
     node_grid = plan.node_grid_index()
+    note_zero_slopes(model)
     Slice, Mask = Slice.float(), Mask.float()
     scale = float(model.scale_rel)
     edge_means = _expand_edge_means(model, kg_sta) if model.updated_model else None

@@ -241,6 +241,34 @@ GENIE_API int genie_kron_spmm_fwd(int mode, int n_sta, int n_grid, int64_t n_pro
                                   const int32_t* col_dev, const float* val_dev, const float* x_dev, int ld_x, int n_ch,
                                   float* out_dev, int ld_out, void* stream);
 
+/* ---- per-product-node dense layers of the training path (BASELINE.json configs[2]) -----------------------------------------
+ * Replace `activate(Linear(torch.cat((x_0, x_1, ...), dim=1)))` over product-node-sized tensors — every layer of
+ * DataAggregation (module.py:87-96), DataAggregationAssociationPhase (:387-403), BipartiteGraphOperator.fc1 (:227) and
+ * BipartiteGraphReadOutOperator (:349-351) — and its gradient (train_GENIE_model.py:1786-1861: loss.backward()).
+ *   forward   y = PReLU_a(W [x_0 | x_1 | ...] + b)        the concatenation is never materialised; slope NULL = no activation
+ *   backward  g = gy * PReLU_a'(y);  gx_p = g W[:, columns of part p] (gx_dev[p] NULL = not wanted);
+ *             per-CTA partial sums of  gW = g^T [x_0 | x_1 | ...],  gb = sum g,  ga = sum gy * min(y, 0) / a
+ *             partial_dev: fp32 [genie_node_mlp_partial_rows()][n_out * n_in + n_out + 1] (gW row-major, then gb, then ga); the
+ *             caller sums over the first dimension (fixed order: bit-reproducible, no atomics).
+ * Limits: 1..4 parts, sum of widths <= GENIE_MLP_MAX_IN, n_out <= GENIE_MLP_MAX_OUT, slope != 0 when given. */
+#define GENIE_MLP_MAX_IN 104
+#define GENIE_MLP_MAX_OUT 32
+typedef struct genie_mlp_desc {
+    int64_t n_rows;
+    int32_t n_parts;
+    int32_t n_out;
+    int32_t width[4];       /* columns of every part */
+    int32_t ld[4];          /* row stride (floats) of every part */
+    const float* x[4];      /* device pointers */
+    const float* weight;    /* [n_out][n_in] row-major (nn.Linear.weight), n_in = sum(width) */
+    const float* bias;      /* [n_out] or NULL */
+    const float* slope;     /* 1-element nn.PReLU weight or NULL */
+} genie_mlp_desc_t;
+GENIE_API int genie_node_mlp_partial_rows(void);
+GENIE_API int genie_node_mlp_fwd(const genie_mlp_desc_t* desc, float* y_dev, int32_t ld_y, void* stream);
+GENIE_API int genie_node_mlp_bwd(const genie_mlp_desc_t* desc, const float* y_dev, int32_t ld_y, const float* gy_dev, int32_t ld_gy,
+                                 float* const* gx_dev, const int32_t* ld_gx, float* partial_dev, void* stream);
+
 /* ---- output stacking of the streaming loop --------------------------------------------------------
  * process_continuous_days.py:797-805: Out_2[:, ip_need[t]] += x[:, t, 0] / n_overlap / n_scale_x_grid for the first n_use
  * (all, or all but the last when step_size == 'half') query times of one window, on the device.

@@ -1166,6 +1166,106 @@ def test_training_steps_match_oracle(name):
     assert capi.launch_count() - n0 >= 3 * 16           # 8 aggregations forward + 8 backward per step ran on our kernel
 
 
+@pytest.mark.parametrize('widths,n_out,act,bias', [((4, 4), 30, True, True), ((30, 30, 4), 30, True, True), ((60,), 30, True, True),
+                                                   ((60, 30, 4), 15, True, True), ((15, 30, 1, 4), 30, True, True),
+                                                   ((30, 3), 30, True, True), ((30,), 15, False, True), ((60, 30, 8), 15, True, False),
+                                                   ((104,), 32, True, True)])
+def test_node_mlp_kernels_match_torch(widths, n_out, act, bias):
+    """genie_node_mlp_fwd / genie_node_mlp_bwd — `activate(Linear(cat(parts)))` of the training path, forward and backward in
+    one kernel each — against the torch ops they replace (cat + linear + prelu and autograd): outputs, the gradient of every
+    part, of the weight, the bias and the PReLU slope.  Ragged row count, strided parts."""
+    from genie_b200.training import NodeMLP
+    dev = _dev()
+    n = 5000 + 37
+    g = torch.Generator(device='cpu').manual_seed(sum(widths) * 7 + n_out)
+    parts_cpu = [torch.randn((n, w + 3), generator=g)[:, 1:1 + w] for w in widths]                # column-sliced: row stride w + 3
+    W = torch.randn((n_out, sum(widths)), generator=g) * 0.3
+    b = torch.randn(n_out, generator=g) if bias else None
+    a = torch.tensor([0.2]) if act else None
+    gy = torch.randn((n, n_out), generator=g)
+
+    def run(device, fused):
+        ps = [p.to(device).clone().requires_grad_(True) for p in parts_cpu]
+        Wd = W.to(device).clone().requires_grad_(True)
+        bd = b.to(device).clone().requires_grad_(True) if b is not None else None
+        ad = a.to(device).clone().requires_grad_(True) if a is not None else None
+        if fused:
+            y = NodeMLP.apply(Wd, bd, ad, *[p[:, :] for p in ps])
+        else:
+            y = torch.nn.functional.linear(torch.cat(ps, dim=1).double(), Wd.double(), bd.double() if bd is not None else None)
+            if ad is not None:
+                y = torch.where(y >= 0, y, ad.double() * y)
+        y.backward(gy.to(device).to(y.dtype))
+        return [y] + [p.grad for p in ps] + [Wd.grad] + ([bd.grad] if bd is not None else []) + ([ad.grad] if ad is not None else [])
+    got = run(dev, True)
+    want = run('cpu', False)                    # fp64 on the host
+    for i, (x, w_) in enumerate(zip(got, want)):
+        assert rel_err(x.detach().cpu().numpy(), w_.detach().numpy()) < 2e-5, i
+
+
+def test_training_batch32_trajectory_matches_oracle(monkeypatch):
+    """BASELINE.json configs[2]: batch 32 windows, Adam, loss match.  The step of train_GENIE_model.py:1593, 1786-1789, 1843-1861:
+    optimizer.zero_grad(); for each of the 32 samples loss = weighted MSE / n_batch, loss.backward() (gradients accumulate);
+    optimizer.step() — five steps on the device with the fused per-node layer kernels (genie_node_mlp_*) and the product-graph
+    gather kernel, against the oracle's autograd on the CPU: the summed loss of every step."""
+    import genie_b200.training as training
+    from genie_b200 import capi
+    from test_oracle_golden import assoc_inputs, assoc_variant
+    from oracle import genie_oracle as go
+    monkeypatch.setattr(training, 'MLP_MIN_ROWS', 0)             # the fixture network has 2880 product nodes: use the kernels anyway
+    monkeypatch.setattr(training, 'LIN_SPLIT_MIN_ROWS', 0)
+    dev = _dev()
+    name = 'assoc_18of20x160'
+    d, sd = load_golden(name)
+    m, graphs, window, locs, grid = _assoc_setup(d, sd, dev, name)
+    m.train()
+    A_sta, A_src, A_ps, A_pg, A_sip, A_sis = _graphs(d)
+    kw = assoc_inputs(d)
+    pos_rel, abs_pos = assoc_variant(d, name, A_ps, A_pg, A_sis)
+    n_batch, n_steps = 32, 5
+    rng = np.random.default_rng(11)
+    Sl0, Mk0 = d['Slice'], d['Mask']
+    samples = []
+    for i in range(n_batch):
+        keep = rng.random(Sl0.shape) < 0.8                                       # every sample: its own thinned inputs and labels
+        Sl = (Sl0 * keep * rng.uniform(0.5, 1.0, Sl0.shape)).astype(np.float32)
+        Mk = (np.abs(Sl) > 0.01).astype(np.float32)
+        lbl = [rng.uniform(0, 1, d[k].shape[:2]).astype(np.float32) for k in ('y', 'x', 'arv_p', 'arv_s')]
+        samples.append((Sl, Mk, lbl))
+    wts = (0.1, 0.4, 0.25, 0.25)
+    loss_fn = torch.nn.MSELoss()
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    opt_o = torch.optim.Adam(list(sdo.values()), lr=1e-3)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    n0 = capi.launch_count()
+    for step in range(n_steps):
+        opt_o.zero_grad()
+        opt.zero_grad()
+        tot_o = tot = 0.0
+        for Sl, Mk, lbl in samples:
+            want = go.forward_fixed(sdo, torch.from_numpy(Sl), torch.from_numpy(Mk), A_ps, A_pg, torch.from_numpy(d['read_in_attr']),
+                                    A_sip, A_src, torch.from_numpy(d['grid']).float(), scale_rel=float(d['scale_rel']),
+                                    scale_t=float(d['scale_t']), eps=float(d['eps']), pos_rel=pos_rel, abs_pos=abs_pos, **kw)
+            lo = sum(w * loss_fn(o[:, :, 0], torch.from_numpy(l)) for w, o, l in zip(wts, want, lbl)) / n_batch
+            lo.backward()
+            tot_o += float(lo.detach())
+            out = m(torch.from_numpy(Sl).to(dev), torch.from_numpy(Mk).to(dev), *graphs, *window)
+            ls = sum(w * loss_fn(o[:, :, 0], torch.from_numpy(l).to(dev)) for w, o, l in zip(wts, out, lbl)) / n_batch
+            ls.backward()
+            tot += float(ls.detach())
+        assert abs(tot - tot_o) < 1e-4 * abs(tot_o), (step, tot, tot_o)
+        if step == 0:
+            worst = 0.0
+            for k, p in m.named_parameters():
+                g_o = sdo[k].grad
+                if g_o is not None and p.grad is not None and g_o.any():
+                    worst = max(worst, rel_err(p.grad.cpu().numpy(), g_o.numpy()))
+            assert worst < 1e-3, worst
+        opt_o.step()
+        opt.step()
+    assert capi.launch_count() - n0 >= n_steps * n_batch * 40       # 16 gather + 2 x 16 fused layer launches per sample at least
+
+
 # ---- sub-graph mode (process_utils.py:744-849; SURVEY.md §8d "C4 subgraph variant") -------------------------------------------
 
 @pytest.mark.parametrize('name', ['subgraph_14x60', 'subgraph_30x200', 'subgraph_12x40_ragged'])
