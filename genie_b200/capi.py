@@ -114,8 +114,8 @@ SIGNATURES = {
     'genie_kron_spmm_fwd': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, _P, _P, _P, _P, ctypes.c_int,
                                            ctypes.c_int, _P, ctypes.c_int, _P]),
     'genie_node_mlp_partial_rows': (ctypes.c_int, []),
-    'genie_node_mlp_fwd': (ctypes.c_int, [ctypes.POINTER(MlpDesc), _P, ctypes.c_int32, _P]),
-    'genie_node_mlp_bwd': (ctypes.c_int, [ctypes.POINTER(MlpDesc), _P, ctypes.c_int32, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p),
+    'genie_node_mlp_fwd': (ctypes.c_int, [ctypes.POINTER(MlpDesc), _P, ctypes.c_int32, _P, _P]),
+    'genie_node_mlp_bwd': (ctypes.c_int, [ctypes.POINTER(MlpDesc), _P, ctypes.c_int32, _P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p),
                                           ctypes.POINTER(ctypes.c_int32), _P, _P]),
     'genie_stack_output_fwd': (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, ctypes.c_float, _P, ctypes.c_int64,
                                               _P]),

@@ -430,12 +430,13 @@ static int current_sm_count() {
     return sms;
 }
 int genie_node_mlp_partial_rows(void) { return mlp_partial_rows(current_sm_count()); }
-int genie_node_mlp_fwd(const genie_mlp_desc_t* desc, float* y_dev, int32_t ld_y, void* stream) {
-    return launch_node_mlp_fwd(desc, y_dev, ld_y, current_sm_count(), static_cast<cudaStream_t>(stream));
+int genie_node_mlp_fwd(const genie_mlp_desc_t* desc, float* y_dev, int32_t ld_y, uint32_t* neg_mask_dev, void* stream) {
+    return launch_node_mlp_fwd(desc, y_dev, ld_y, neg_mask_dev, current_sm_count(), static_cast<cudaStream_t>(stream));
 }
-int genie_node_mlp_bwd(const genie_mlp_desc_t* desc, const float* y_dev, int32_t ld_y, const float* gy_dev, int32_t ld_gy,
-                       float* const* gx_dev, const int32_t* ld_gx, float* partial_dev, void* stream) {
-    return launch_node_mlp_bwd(desc, y_dev, ld_y, gy_dev, ld_gy, gx_dev, ld_gx, partial_dev, current_sm_count(),
+int genie_node_mlp_bwd(const genie_mlp_desc_t* desc, const float* y_dev, int32_t ld_y, const uint32_t* neg_mask_dev,
+                       const float* gy_dev, int32_t ld_gy, float* const* gx_dev, const int32_t* ld_gx, float* partial_dev,
+                       void* stream) {
+    return launch_node_mlp_bwd(desc, y_dev, ld_y, neg_mask_dev, gy_dev, ld_gy, gx_dev, ld_gx, partial_dev, current_sm_count(),
                                static_cast<cudaStream_t>(stream));
 }
 

@@ -227,8 +227,9 @@ int launch_stack_output(const float* x, int Q, int T, int n_use, const int32_t* 
 int launch_kron_spmm(int mode, int S, int64_t P, const int64_t* rowptr, const int32_t* col, const float* val, const float* X,
                      int ld_x, int C, float* out, int ld_o, int sm_count, cudaStream_t st);
 int mlp_partial_rows(int sm_count);
-int launch_node_mlp_fwd(const genie_mlp_desc_t* d, float* y, int ld_y, int sm_count, cudaStream_t st);
-int launch_node_mlp_bwd(const genie_mlp_desc_t* d, const float* y, int ld_y, const float* gy, int ld_gy, float* const* gx,
+int launch_node_mlp_fwd(const genie_mlp_desc_t* d, float* y, int ld_y, uint32_t* neg_mask, int sm_count, cudaStream_t st);
+int launch_node_mlp_bwd(const genie_mlp_desc_t* d, const float* y, int ld_y, const uint32_t* neg_mask, const float* gy, int ld_gy,
+                        float* const* gx,
                         const int* ld_gx, float* partial, int sm_count, cudaStream_t st);
 int launch_knn(const float* x, int n_x, const float* y, int n_y, int k, int64_t* idx_out, cudaStream_t st);
 int launch_input_nearest(const genie_nearest_params_t* prm, const double* t_all, const double* t_p, const double* t_s,

@@ -562,16 +562,19 @@ def node_mlp_supported(parts, weight):
     return len(parts) <= 4 and weight.shape[0] <= 32 and sum(int(x.shape[1]) for x in parts) <= 104
 
 
-def node_mlp_fwd(parts, weight, bias, slope):
-    """y = PReLU_slope(Linear([parts...])) without materialising the concatenation (slope None: no activation)."""
+def node_mlp_fwd(parts, weight, bias, slope, want_mask=True):
+    """y = PReLU_slope(Linear([parts...])) without materialising the concatenation (slope None: no activation); also the
+    per-node sign bits of the pre-activation that node_mlp_bwd needs (int32 [n], None without a slope)."""
     d, _ = _mlp_desc(parts, weight, bias, slope)
     y = torch.empty((d.n_rows, d.n_out), dtype=F32, device=weight.device)
+    neg = torch.empty((d.n_rows,), dtype=torch.int32, device=weight.device) if (slope is not None and want_mask) else None
     with torch.cuda.device(weight.device):
-        capi.check(capi.load().genie_node_mlp_fwd(ctypes.byref(d), capi.dptr(y), d.n_out, capi.stream_ptr(weight.device)))
-    return y
+        capi.check(capi.load().genie_node_mlp_fwd(ctypes.byref(d), capi.dptr(y), d.n_out, capi.dptr(neg),
+                                                  capi.stream_ptr(weight.device)))
+    return y, neg
 
 
-def node_mlp_bwd(parts, weight, bias, slope, y, gy, need_gx):
+def node_mlp_bwd(parts, weight, bias, slope, y, neg, gy, need_gx):
     """Gradients of node_mlp_fwd: (gx per part or None, gW, gb, gslope)."""
     d, n_in = _mlp_desc(parts, weight, bias, slope)
     dev = weight.device
@@ -587,6 +590,7 @@ def node_mlp_bwd(parts, weight, bias, slope, y, gy, need_gx):
     lds = (ctypes.c_int32 * 4)(*[(int(g.shape[1]) if g is not None else 0) for g in gx] + [0] * (4 - len(gx)))
     with torch.cuda.device(dev):
         capi.check(lib.genie_node_mlp_bwd(ctypes.byref(d), capi.dptr(y, F32) if slope is not None else None, d.n_out,
+                                          capi.dptr(neg, torch.int32, 'neg_mask') if slope is not None else None,
                                           capi.dptr(gy, F32, 'gy'), d.n_out, ptrs, lds, capi.dptr(partial), capi.stream_ptr(dev)))
     tot = partial.sum(0)
     gW = tot[:d.n_out * n_in].view(d.n_out, n_in)

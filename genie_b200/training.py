@@ -113,18 +113,22 @@ class NodeMLP(torch.autograd.Function):
     @staticmethod
     def forward(ctx, weight, bias, slope, *parts):
         parts = tuple(p if (p.dtype == torch.float32 and p.stride(1) == 1) else p.float().contiguous() for p in parts)
-        y = ops.node_mlp_fwd(parts, weight, bias, slope)
+        y, neg = ops.node_mlp_fwd(parts, weight, bias, slope)
         ctx.has_slope = slope is not None
-        ctx.save_for_backward(weight, bias, slope if slope is not None else weight.new_zeros(1), y, *parts)
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(weight, bias if bias is not None else weight.new_zeros(1),
+                              slope if slope is not None else weight.new_zeros(1), y,
+                              neg if neg is not None else weight.new_zeros(1, dtype=torch.int32), *parts)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        weight, bias, slope, y = ctx.saved_tensors[:4]
-        parts = ctx.saved_tensors[4:]
+        weight, bias, slope, y, neg = ctx.saved_tensors[:5]
+        parts = ctx.saved_tensors[5:]
         need_gx = list(ctx.needs_input_grad[3:])
-        gx, gW, gb, ga = ops.node_mlp_bwd(parts, weight, bias, slope if ctx.has_slope else None, y, gy, need_gx)
-        return (gW, gb, ga.view_as(slope) if ctx.has_slope else None) + tuple(gx)
+        gx, gW, gb, ga = ops.node_mlp_bwd(parts, weight, bias if ctx.has_bias else None, slope if ctx.has_slope else None, y, neg,
+                                          gy, need_gx)
+        return (gW, gb if ctx.has_bias else None, ga.view_as(slope) if ctx.has_slope else None) + tuple(gx)
 
 
 MLP_MIN_ROWS = 4096
@@ -225,7 +229,14 @@ def spatial_aggregation(sa, x, A_src, pos, scale_rel):
 def bipartite_read_out(ro, y_latent, attr, node_grid, mask_out):
     """BipartiteGraphReadOutOperator.forward (module.py:344-352) for the read-out graph [g(i); i]."""
     mj = mask_out[node_grid]
-    h = mj * mlp(ro.fc1, ro.activate1, y_latent[node_grid], attr)
+    G = y_latent.shape[0]
+    if node_grid.numel() % max(G, 1) == 0 and node_grid.numel() and getattr(node_grid, '_genie_regular', False):
+        # dense mode: node_grid = repeat_interleave(arange(G), S) — an expand, whose gradient is a reshape + sum over the stations
+        # (the fancy-index gather's backward is an index_put with accumulation: 1.7 ms per sample at 100 x 5000)
+        yl = y_latent.unsqueeze(1).expand(G, node_grid.numel() // G, y_latent.shape[1]).reshape(-1, y_latent.shape[1])
+    else:
+        yl = y_latent[node_grid]
+    h = mj * mlp(ro.fc1, ro.activate1, yl, attr)
     return mlp(ro.fc2, ro.activate2, h), mj
 
 
@@ -260,6 +271,8 @@ def forward_train(model, Slice, Mask, A_Lg_in_src, A_src, A_edges_p, A_edges_s, 
         model._kron = (key,) + build_kron_graphs(plan)
     kg_sta, kg_src = model._kron[1], model._kron[2]
     node_grid = plan.node_grid_index()
+    if plan.mode == capi.GRAPH_CARTESIAN:
+        node_grid._genie_regular = True
     note_zero_slopes(model)
     Slice, Mask = Slice.float(), Mask.float()
     scale = float(model.scale_rel)

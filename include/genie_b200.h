@@ -247,7 +247,10 @@ GENIE_API int genie_kron_spmm_fwd(int mode, int n_sta, int n_grid, int64_t n_pro
  * BipartiteGraphReadOutOperator (:349-351) — and its gradient (train_GENIE_model.py:1786-1861: loss.backward()).
  *   forward   y = PReLU_a(W [x_0 | x_1 | ...] + b)        the concatenation is never materialised; slope NULL = no activation
  *   backward  g = gy * PReLU_a'(y);  gx_p = g W[:, columns of part p] (gx_dev[p] NULL = not wanted);
- *             per-CTA partial sums of  gW = g^T [x_0 | x_1 | ...],  gb = sum g,  ga = sum gy * min(y, 0) / a
+ *             per-CTA partial sums of  gW = g^T [x_0 | x_1 | ...],  gb = sum g,  ga = sum_{z<0} gy * y / a
+ *             neg_mask_dev: uint32 [n_rows], bit o = the pre-activation z of output o is negative — written by the forward
+ *             call (NULL = not kept), read by the backward call (needed whenever slope is given: a slope may be negative,
+ *             so the sign of y does not tell)
  *             partial_dev: fp32 [genie_node_mlp_partial_rows()][n_out * n_in + n_out + 1] (gW row-major, then gb, then ga); the
  *             caller sums over the first dimension (fixed order: bit-reproducible, no atomics).
  * Limits: 1..4 parts, sum of widths <= GENIE_MLP_MAX_IN, n_out <= GENIE_MLP_MAX_OUT, slope != 0 when given. */
@@ -265,9 +268,10 @@ typedef struct genie_mlp_desc {
     const float* slope;     /* 1-element nn.PReLU weight or NULL */
 } genie_mlp_desc_t;
 GENIE_API int genie_node_mlp_partial_rows(void);
-GENIE_API int genie_node_mlp_fwd(const genie_mlp_desc_t* desc, float* y_dev, int32_t ld_y, void* stream);
-GENIE_API int genie_node_mlp_bwd(const genie_mlp_desc_t* desc, const float* y_dev, int32_t ld_y, const float* gy_dev, int32_t ld_gy,
-                                 float* const* gx_dev, const int32_t* ld_gx, float* partial_dev, void* stream);
+GENIE_API int genie_node_mlp_fwd(const genie_mlp_desc_t* desc, float* y_dev, int32_t ld_y, uint32_t* neg_mask_dev, void* stream);
+GENIE_API int genie_node_mlp_bwd(const genie_mlp_desc_t* desc, const float* y_dev, int32_t ld_y, const uint32_t* neg_mask_dev,
+                                 const float* gy_dev, int32_t ld_gy, float* const* gx_dev, const int32_t* ld_gx,
+                                 float* partial_dev, void* stream);
 
 /* ---- output stacking of the streaming loop --------------------------------------------------------
  * process_continuous_days.py:797-805: Out_2[:, ip_need[t]] += x[:, t, 0] / n_overlap / n_scale_x_grid for the first n_use

@@ -1181,7 +1181,7 @@ def test_node_mlp_kernels_match_torch(widths, n_out, act, bias):
     parts_cpu = [torch.randn((n, w + 3), generator=g)[:, 1:1 + w] for w in widths]                # column-sliced: row stride w + 3
     W = torch.randn((n_out, sum(widths)), generator=g) * 0.3
     b = torch.randn(n_out, generator=g) if bias else None
-    a = torch.tensor([0.2]) if act else None
+    a = torch.tensor([0.2 if n_out != 15 else -0.3]) if act else None      # a PReLU slope may be negative (trained weights are)
     gy = torch.randn((n, n_out), generator=g)
 
     def run(device, fused):
@@ -1255,12 +1255,18 @@ def test_training_batch32_trajectory_matches_oracle(monkeypatch):
             tot += float(ls.detach())
         assert abs(tot - tot_o) < 1e-4 * abs(tot_o), (step, tot, tot_o)
         if step == 0:
-            worst = 0.0
+            # every accumulated parameter gradient: 1e-3 of its own scale (parameters whose gradient is below 1e-4 of the
+            # largest one are held to that floor — their own scale is rounding noise of the 32-sample sum)
+            top = max(float(v.grad.abs().max()) for v in sdo.values() if v.grad is not None)
+            bad = []
             for k, p in m.named_parameters():
                 g_o = sdo[k].grad
                 if g_o is not None and p.grad is not None and g_o.any():
-                    worst = max(worst, rel_err(p.grad.cpu().numpy(), g_o.numpy()))
-            assert worst < 1e-3, worst
+                    err = float((p.grad.cpu() - g_o).abs().max())
+                    scale = max(float(g_o.abs().max()), 1e-4 * top)
+                    if err > 1e-3 * scale:
+                        bad.append((k, err, float(g_o.abs().max())))
+            assert not bad, (top, bad[:8])
         opt_o.step()
         opt.step()
     assert capi.launch_count() - n0 >= n_steps * n_batch * 40       # 16 gather + 2 x 16 fused layer launches per sample at least
