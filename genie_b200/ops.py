@@ -598,3 +598,22 @@ def node_mlp_bwd(parts, weight, bias, slope, y, neg, gy, need_gx):
     ga = tot[d.n_out * n_in + d.n_out:]
     gx = [g if g is not None else (torch.zeros_like(x) if need else None) for g, x, need in zip(gx, parts, need_gx)]
     return gx, gW, gb, ga
+
+
+def csr_apply(csr, x, n_out):
+    """out[i, :] = sum_{e in row i} val[e] * x[col[e], :]  for an explicit CSR (rowptr int64 [n_out+1], col int32, val fp32):
+    genie_kron_spmm_fwd in explicit mode with independent input / output row counts.  Gathers (one entry per row), segment
+    means (val = 1 / row length) and their transposes are all instances; no atomics, bit-reproducible."""
+    rowptr, col, val = csr
+    if x.dtype != F32:
+        x = x.float()
+    x = x.contiguous()
+    out = torch.empty((int(n_out), x.shape[1]), dtype=F32, device=x.device)
+    if n_out == 0 or x.shape[1] == 0:
+        return out
+    with torch.cuda.device(x.device):
+        capi.check(capi.load().genie_kron_spmm_fwd(
+            2, 0, 0, int(n_out), capi.dptr(rowptr, torch.int64, 'rowptr'), capi.dptr(col, torch.int32, 'col'),
+            capi.dptr(val, F32, 'val'), capi.dptr(x, F32, 'x') if x.shape[0] else capi.dptr(out), int(x.shape[1]), int(x.shape[1]),
+            capi.dptr(out), int(x.shape[1]), capi.stream_ptr(x.device)))
+    return out

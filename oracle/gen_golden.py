@@ -6,6 +6,7 @@
     python oracle/gen_golden.py legacy_input     # a1': extract_inputs_from_data_fixed_grids_with_phase_type
     python oracle/gen_golden.py association      # forward_fixed incl. the association branch
     python oracle/gen_golden.py dense_adjacencies # the dense graph builder incl. the time-pointer re-indexing (process_utils.py:701-742)
+    python oracle/gen_golden.py graphdd          # GraphDD's GNN_Location (Relocation/train_double_difference_model.py:333-536)
     python oracle/gen_golden.py streaming        # the script-body loop of process_continuous_days.py:757-813, executed verbatim
     python oracle/gen_golden.py input_variants   # a1 with use_sign_input / trv_times=None (process_utils.py:594-614)
     python oracle/gen_golden.py subgraph         # sub-graph mode builder (process_utils.py:744-849) + one window on it
@@ -564,6 +565,63 @@ def streaming():
     np.savez_compressed(os.path.join(GOLD, 'streaming_10x100.npz'), **res)
 
 
+def graphdd():
+    """GraphDD's location network (Relocation/train_double_difference_model.py:333-536), the second consumer of the
+    DataAggregation kernel family.  The file is a script with top-level code (it cannot be imported): the class definitions
+    are read from it at generation time and executed as they are, with oracle/refshim behind `MessagePassing`."""
+    work = tempfile.mkdtemp(prefix='genie_golden_')
+    for f in ('config.yaml', 'train_config.yaml'):
+        shutil.copy(os.path.join(REF, 'Code', f), work)
+    torch, module, pu, Data = _import_reference(os.path.join(REF, 'Code'), work)
+    from torch import nn
+    from torch_geometric.nn import MessagePassing
+    lines = open(os.path.join(REF, 'Relocation', 'train_double_difference_model.py')).read().split('\n')
+    beg = [i for i, l in enumerate(lines) if l.startswith('class DataAggregation(MessagePassing)')]
+    end = [i for i, l in enumerate(lines) if l.startswith('n_batch = ') and i > beg[0]]
+    assert len(beg) == 1 and len(end) >= 1 and 300 < beg[0] < end[0] < 600
+    ns = dict(torch=torch, nn=nn, np=np, MessagePassing=MessagePassing)
+    exec(compile('\n'.join(lines[beg[0]:end[0]]), 'train_double_difference_model.py:%d-%d' % (beg[0] + 1, end[0]), 'exec'), ns)
+    from genie_b200.process_utils import knn_graph, product_edge_lists
+    rng = np.random.default_rng(21)
+    for name, n_sta, n_src, use_memory in (('graphdd_12x9', 12, 9, False), ('graphdd_10x14_memory', 10, 14, True)):
+        torch.manual_seed(n_sta)
+        locs = np.stack((rng.uniform(0, 80e3, n_sta), rng.uniform(0, 80e3, n_sta), rng.uniform(0, 2e3, n_sta)), 1)
+        srcs = np.stack((rng.uniform(0, 80e3, n_src), rng.uniform(0, 80e3, n_src), rng.uniform(-30e3, 0, n_src)), 1)
+        A_sta, A_src = knn_graph((locs / 1000.0).astype(np.float32), 5), knn_graph((srcs / 1000.0).astype(np.float32), 4)
+        A_in_pick, A_in_src, A_src_in_prod, A_src_in_sta = product_edge_lists(A_sta, A_src, n_sta, n_src)
+        P = n_sta * n_src
+        keep = torch.from_numpy(rng.random(P) < 0.8)                      # picks exist for a subset of (station, source) pairs
+        new_id = torch.cumsum(keep.long(), 0) - 1
+
+        def sub(A):
+            ok = keep[A[0]] & keep[A[1]]
+            return torch.stack((new_id[A[0][ok]], new_id[A[1][ok]]), 0).contiguous()
+        A_in_pick, A_in_src = sub(A_in_pick), sub(A_in_src)
+        A_src_in_sta = A_src_in_sta[:, keep].contiguous()
+        n_prod = int(keep.sum())
+        A_src_in_product = torch.stack((torch.arange(n_prod), A_src_in_sta[1]), 0)
+        A_sta_in_product = torch.stack((torch.arange(n_prod), A_src_in_sta[0]), 0)
+        m = ns['GNN_Location'](None, None, inpt_sources=True, use_sta_corr=True, use_memory=use_memory, use_mask=False,
+                               use_aggregation=False, use_attention=False, device='cpu')
+        m.eval()
+        n_inpt, n_mask = 15 + 3, 15 + 3
+        x = torch.from_numpy(rng.normal(size=(n_prod, n_inpt)).astype(np.float32))
+        mask = torch.from_numpy((rng.random((n_prod, n_mask)) < 0.6).astype(np.float32))
+        memory = torch.from_numpy(rng.normal(size=(n_src, 4)).astype(np.float32)) if use_memory else False
+        lc, sc = torch.Tensor(locs), torch.Tensor(srcs)
+        out = m(x, mask, A_in_pick, A_in_src, A_src_in_product, A_sta_in_product, A_src_in_sta, lc, sc, memory=memory)
+        res = dict(locs=locs, srcs=srcs, x=x.numpy(), mask=mask.numpy(), A_in_pick=A_in_pick.numpy(), A_in_src=A_in_src.numpy(),
+                   A_src_in_product=A_src_in_product.numpy(), A_sta_in_product=A_sta_in_product.numpy(),
+                   A_src_in_sta=A_src_in_sta.numpy(), use_memory=np.int64(use_memory),
+                   out0=out[0].numpy(), out1=out[1].numpy(), out2=out[2].numpy(), out3=out[3].numpy())
+        if use_memory:
+            res['memory'] = memory.numpy()
+        res.update(_pack(m.state_dict()))
+        np.savez_compressed(os.path.join(GOLD, name + '.npz'), **res)
+        print(name, 'P=%d edges %d/%d keys %d' % (n_prod, A_in_pick.shape[1], A_in_src.shape[1], len(m.state_dict())),
+              [float(np.abs(o.numpy()).sum()) for o in out])
+
+
 if __name__ == '__main__':
     mode = sys.argv[1] if len(sys.argv) > 1 else 'synthetic'
     if mode == 'synthetic':
@@ -588,6 +646,8 @@ if __name__ == '__main__':
         input_variants()
     elif mode == 'streaming':
         streaming()
+    elif mode == 'graphdd':
+        graphdd()
     elif mode == 'ferndale':
         from gen_golden_ferndale import ferndale
         ferndale()

@@ -1360,3 +1360,52 @@ def test_forward_fixed_edge_cases():
     out = m.forward_fixed(t('Slice'), t('Mask'), *window)
     for a, b, key in zip(out, want[:4], ('y', 'x', 'arv_p', 'arv_s')):
         assert rel_err(a.cpu().numpy(), b.numpy()) < TOL, key
+
+
+# ---- GraphDD: the second consumer of the kernel family (Relocation/train_double_difference_model.py:333-536) --------------------
+
+@pytest.mark.parametrize('name', ['graphdd_12x9', 'graphdd_10x14_memory'])
+def test_graphdd_location_network_matches_reference(name, monkeypatch):
+    """genie_b200.relocation.GNN_Location (same classes and state_dict keys as the reference's script) with the reference's own
+    weights: the four outputs against the unmodified reference's, and every parameter gradient of a sum-of-outputs loss against
+    the oracle's autograd — with the per-edge layers on genie_node_mlp_* and the gathers / means on genie_kron_spmm_fwd."""
+    import genie_b200.training as training
+    from genie_b200 import capi
+    from genie_b200.relocation import GNN_Location
+    from oracle import graphdd_oracle as gd
+    monkeypatch.setattr(training, 'MLP_MIN_ROWS', 0)            # the fixture graphs have a few hundred edges: use the kernels anyway
+    dev = _dev()
+    d, sd = load_golden(name)
+    use_memory = bool(int(d['use_memory']))
+    m = GNN_Location(None, None, inpt_sources=True, use_memory=use_memory, device=dev)
+    missing = m.load_state_dict({k: v.to(dev) for k, v in sd.items()}, strict=True)
+    t = lambda k: torch.from_numpy(d[k]).to(dev)
+    mem = t('memory') if use_memory else False
+    args = (t('A_in_pick'), t('A_in_src'), t('A_src_in_product'), t('A_sta_in_product'), t('A_src_in_sta'), t('locs').float(),
+            t('srcs').float())
+    n0 = capi.launch_count()
+    out = m(t('x'), t('mask'), *args, memory=mem)
+    assert capi.launch_count() - n0 > 100
+    for i, o in enumerate(out):
+        assert rel_err(o.detach().cpu().numpy(), d['out%d' % i]) < TOL, i
+    m.set_adjacencies(*args)
+    out_fixed = m.forward_fixed(t('x'), t('mask'), memory=mem)
+    assert all(torch.equal(a, b) for a, b in zip(out, out_fixed))
+    # gradients
+    w = [torch.from_numpy(np.random.default_rng(i).normal(size=d['out%d' % i].shape).astype(np.float32)) for i in range(4)]
+    sum(float(1.0) * (o * wi.to(dev)).sum() / (5000.0 if i == 0 else 1.0) for i, (o, wi) in enumerate(zip(out, w))).backward()
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    tc = lambda k: torch.from_numpy(d[k])
+    want = gd.gnn_location(sdo, tc('x'), tc('mask'), tc('A_in_pick'), tc('A_in_src'), tc('A_src_in_product'), tc('A_sta_in_product'),
+                           tc('A_src_in_sta'), tc('locs').float(), tc('srcs').float(), memory=tc('memory') if use_memory else None)
+    sum((o * wi).sum() / (5000.0 if i == 0 else 1.0) for i, (o, wi) in enumerate(zip(want, w))).backward()
+    top = max(float(v.grad.abs().max()) for v in sdo.values() if v.grad is not None)
+    checked = 0
+    for k, p in m.named_parameters():
+        g_o = sdo[k].grad
+        if g_o is None or not g_o.any():
+            continue
+        err = float((p.grad.cpu() - g_o).abs().max())
+        assert err <= 1e-3 * max(float(g_o.abs().max()), 1e-4 * top), (k, err, float(g_o.abs().max()))
+        checked += 1
+    assert checked > 120

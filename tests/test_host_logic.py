@@ -297,3 +297,31 @@ def test_legacy_host_tables_match_reference(name):
         a_all, a_p, a_s = h['axes']
         assert np.all(np.diff(a_all) >= 0) and len(a_p) + len(a_s) == len(a_all)
         assert np.array_equal(np.sort(np.concatenate((a_p, a_s))), a_all)
+
+
+def test_edge_graph_operators_are_the_gather_and_the_mean():
+    """genie_b200.relocation.EdgeGraph (GraphDD consumer): the four CSR matrices it hands to the gather kernel are x[source(e)],
+    its transpose, the mean over a target's in-edges (0 for targets without edges) and its transpose — checked densely."""
+    from genie_b200.relocation import EdgeGraph
+    rng = np.random.default_rng(0)
+    n_src, n_tgt, E = 13, 9, 40
+    ei = torch.from_numpy(np.stack((rng.integers(0, n_src, E), rng.integers(0, n_tgt - 2, E)), 0)).long()      # two empty targets
+    eg = EdgeGraph(ei, n_src, n_tgt)
+
+    def dense(csr, n_rows, n_cols):
+        rowptr, col, val = csr
+        M = torch.zeros((n_rows, n_cols), dtype=torch.float64)
+        for r in range(n_rows):
+            for e in range(int(rowptr[r]), int(rowptr[r + 1])):
+                M[r, int(col[e])] += float(val[e])
+        return M
+    Gm, Gt = dense(eg.g_fwd, E, n_src), dense(eg.g_rev, n_src, E)
+    Mm, Mt = dense(eg.m_fwd, n_tgt, E), dense(eg.m_rev, E, n_tgt)
+    assert torch.equal(Gm.t(), Gt) and torch.allclose(Mm.t(), Mt)
+    x = torch.from_numpy(rng.normal(size=(n_src, 5)))
+    assert torch.equal(Gm @ x, x[eg.src])
+    msg = torch.from_numpy(rng.normal(size=(E, 5)))
+    want = torch.zeros((n_tgt, 5), dtype=torch.float64).index_add_(0, eg.tgt, msg)
+    want = want / torch.bincount(eg.tgt, minlength=n_tgt).clamp(min=1).unsqueeze(1)
+    assert torch.allclose(Mm @ msg, want, atol=1e-6) and float((Mm @ msg)[-1].abs().max()) == 0.0
+    assert torch.equal(torch.sort(eg.order)[0], torch.arange(E)) and torch.equal(ei[1][eg.order], eg.tgt)

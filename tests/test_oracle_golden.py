@@ -279,3 +279,18 @@ def test_streaming_loop_matches_reference(step_size):
     assert np.abs(out - want).max() <= 1e-6 * max(np.abs(want).max(), 1e-30)
     cols = np.abs(want).sum(axis=0) > 0
     assert np.array_equal(np.abs(out).sum(axis=0) > 0, cols)
+
+
+@pytest.mark.parametrize('name', ['graphdd_12x9', 'graphdd_10x14_memory'])
+def test_graphdd_oracle_matches_reference(name):
+    """GraphDD's GNN_Location (Relocation/train_double_difference_model.py:333-536; class definitions executed as they are by
+    oracle/gen_golden.py `graphdd`): the oracle's restatement reproduces all four outputs."""
+    from oracle import graphdd_oracle as gd
+    d, sd = load_golden(name)
+    t = lambda k: torch.from_numpy(d[k])
+    mem = t('memory') if int(d['use_memory']) else None
+    out = gd.gnn_location(sd, t('x'), t('mask'), t('A_in_pick'), t('A_in_src'), t('A_src_in_product'), t('A_sta_in_product'),
+                          t('A_src_in_sta'), t('locs').float(), t('srcs').float(), memory=mem)
+    for i, o in enumerate(out):
+        assert o.shape == d['out%d' % i].shape
+        assert rel_err(o.numpy(), d['out%d' % i]) < 1e-5, i
