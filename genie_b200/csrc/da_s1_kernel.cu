@@ -332,6 +332,11 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
     extern __shared__ __align__(1024) unsigned char smem[];
     using F = Fmt<BF16>;
     constexpr int NBUF = F::NBUF;
+    // Who writes the OWN / SRC stage-B operands: the epilogue warpgroup (after its last epilogue of the previous tile), so that
+    // the gather warpgroup can hand the staging buffer back before it touches tensor memory.  Moving them to the gather
+    // warpgroup in the bf16 kernel (where the epilogue warpgroup's serial chain is the bound, profiles/r5c_trace_bf16.log)
+    // was measured and lost: 8.6 -> 10.0 ms at C4, the extra shared-memory reads land in the gather phase (r9a).
+    constexpr bool OWN_BY_GATHER = false;
     const bool packed_mask = mask == nullptr;
     const float* tcw = packed + T2_BASE;
     if (tcw[T2_SCAL + TCS_OK] == 0.f) return;   // slopes not eligible: the generic kernels run instead (uniform exit)
@@ -359,7 +364,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                 mbar_init(&bars->raw[b][u], P_THREADS);
                 mbar_init(&bars->empty[b][u], 256);   // gather + epilogue warpgroups
             }
-            mbar_init(&bars->opA_full[b], 256);
+            mbar_init(&bars->opA_full[b], OWN_BY_GATHER ? 128 : 256);
             mbar_init(&bars->opA_free[b], 1);
             mbar_init(&bars->d_full[b], 1);
             mbar_init(&bars->aE_full[b], 128);
@@ -643,7 +648,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
             }
             const bool valid = r < n_own;
             const float4 mk = s1_load_mask<BF16>(sb, r, valid, packed_mask);
-            mbar_arrive(&bars->empty[q][bi]);        // release (gather half): every shared-memory read of this tile is done
+            if (!OWN_BY_GATHER) mbar_arrive(&bars->empty[q][bi]);     // release (gather half): every shared-memory read is done
             // ---- A operand -> tensor memory (free once stage D of the pipeline's previous tile has completed) ---------------
             if (r == 0) S1_TRACE(14);
             if (k > 0) mbar_wait(&bars->opA_free[q], (uint32_t)((k - 1) & 1));
@@ -661,6 +666,10 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                     }
                     st_split16<BF16>(lane_base + TM_STA_HI + 16 * half, lane_base + TM_STA_LO + 16 * half, a);
                 }
+            }
+            if (OWN_BY_GATHER) {
+                s1_own_operands<BF16>(sb, r, valid, key, sc[TCS_INV11], lane_base, packed_mask);
+                mbar_arrive(&bars->empty[q][bi]);
             }
             tmem_st_wait();
             tc_fence_before_sync();
@@ -688,11 +697,16 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                 const int g = (int)(t / NT), T = (int)(t - (int64_t)g * NT);
                 valid = r < __ldg(tile_meta + 2 * T);
                 mbar_wait(&bars->full[q][0], 0u);
-                mk = s1_own_operands<BF16>(smem + SM_BUF + (q * NBUF) * F::SB_SIZE, r, valid, key, inv11, lane_base, packed_mask);
-                mbar_arrive(&bars->empty[q][0]);
-                tmem_st_wait();
-                tc_fence_before_sync();
-                mbar_arrive(&bars->opA_full[q]);
+                if (OWN_BY_GATHER) {          // only the row's mask is needed here (for the epilogues)
+                    mk = s1_load_mask<BF16>(smem + SM_BUF + (q * NBUF) * F::SB_SIZE, r, valid, packed_mask);
+                    mbar_arrive(&bars->empty[q][0]);
+                } else {
+                    mk = s1_own_operands<BF16>(smem + SM_BUF + (q * NBUF) * F::SB_SIZE, r, valid, key, inv11, lane_base, packed_mask);
+                    mbar_arrive(&bars->empty[q][0]);
+                    tmem_st_wait();
+                    tc_fence_before_sync();
+                    mbar_arrive(&bars->opA_full[q]);
+                }
             }
         }
         for (int64_t t = blockIdx.x + (int64_t)q * gridDim.x; t < n_tiles; t += 2 * (int64_t)gridDim.x, ++k) {
@@ -814,11 +828,17 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                 valid = r < __ldg(tile_meta + 2 * T2);
                 const int b2 = (int)((k + 1) % NBUF);
                 mbar_wait(&bars->full[q][b2], (uint32_t)(((k + 1) / NBUF) & 1));
-                mk = s1_own_operands<BF16>(smem + SM_BUF + (q * NBUF + b2) * F::SB_SIZE, r, valid, key, inv11, lane_base, packed_mask);
-                mbar_arrive(&bars->empty[q][b2]);
-                tmem_st_wait();
-                tc_fence_before_sync();
-                mbar_arrive(&bars->opA_full[q]);
+                if (OWN_BY_GATHER) {
+                    mk = s1_load_mask<BF16>(smem + SM_BUF + (q * NBUF + b2) * F::SB_SIZE, r, valid, packed_mask);
+                    mbar_arrive(&bars->empty[q][b2]);
+                } else {
+                    mk = s1_own_operands<BF16>(smem + SM_BUF + (q * NBUF + b2) * F::SB_SIZE, r, valid, key, inv11, lane_base,
+                                               packed_mask);
+                    mbar_arrive(&bars->empty[q][b2]);
+                    tmem_st_wait();
+                    tc_fence_before_sync();
+                    mbar_arrive(&bars->opA_full[q]);
+                }
                 if (r == 0) S1_TRACE(19);
             }
         }
