@@ -27,6 +27,12 @@
 //           columns 192-255  stage-B accumulator (tr)
 //           columns 128-223  stage-C accumulator ([h | c]),  224-255 stage-D accumulator ([v_a | v_b])
 //     * the epilogue warpgroup applies the activations between the stages and stores c (zc) and v_a / v_b.
+// ASSOC = true: layer 1 of DataAggregationAssociationPhase (module.py:387-398; assoc_kernels.cu) on the same pipeline.  The
+// association phase differs in three places: its messages are PReLU(l1_t*_1 tr) (two more row tensors, written by
+// assoc_init_kernel: the staged / gathered rows are those, never converted, and the node's own tr row is read from global
+// memory by the epilogue warpgroup after an L2 prefetch by the producers), its mask has a fifth channel — the source mask
+// of the row's grid node, constant over a tile, so its weight columns are added in the epilogues (blob floats
+// T2_FLOATS ..+96) — and its weights (pack.cu assoc_pack_t2_kernel builds the blob in the same T2_* layout).
 // DRAM sees p, msrc and mask once (the tiles of one grid node are consecutive, its 128 KB block stays in L2); nothing is
 // gathered from L2.  All hand-offs are mbarriers with bounded spins (a protocol bug traps, it never hangs).
 #include "bf16.cuh"
@@ -46,6 +52,7 @@ constexpr int WG_G0 = 4, WG_E0 = 12, WG_P0 = 20;     // gather (2 x 4 warps) / e
 constexpr int ROWS = GENIE_TILE_ROWS_MAX;            // staged p rows per tile; row ROWS is the zero row
 constexpr int NPIPE = 2;
 constexpr int P_THREADS = 64;                        // producer threads per pipeline (two warps)
+constexpr int S1_ASSOC_TERMS = 96;                   // association blob: weight columns of the source mask, [tr1 | tr2 | c_a | c_b]
 
 // shared memory map (bytes).  Row format of the staged tensors: fp32 rows (128 B; ONE staging buffer per pipeline, shared
 // memory is full) or the bf16 rows of the fast storage mode (genie_plan_set_storage; 64 B, TWO staging buffers per pipeline:
@@ -228,12 +235,33 @@ __device__ __forceinline__ float4 s1_load_mask(const unsigned char* sb, int r, b
 // Epilogue-warpgroup half of the stage-B operands of one tile: [tr0 | mask0,1] (tr0 recovered from the staged PReLU11(tr0)
 // of the thread's own row) and [mean_src | mask2,3] (the thread's msrc row) -> tensor memory.  Returns the row's mask.
 
-template <bool BF16>
+template <bool BF16, bool ASSOC>
 __device__ __forceinline__ float4 s1_own_operands(const unsigned char* sb, int r, bool valid, int key, float inv11,
-                                                  uint32_t lane_base, bool packed) {
+                                                  uint32_t lane_base, bool packed, const float* __restrict__ own_row) {
     using F = Fmt<BF16>;
     const float4 mk = s1_load_mask<BF16>(sb, r, valid, packed);
     float a[16];
+    if (ASSOC) {
+        // the node's own tr row: 128 contiguous bytes from global memory (L2: prefetched by the producers with the tile)
+        float4 own[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) own[c] = valid ? __ldg(reinterpret_cast<const float4*>(own_row) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 v = own[4 * half + u];
+                a[4 * u] = v.x; a[4 * u + 1] = v.y; a[4 * u + 2] = v.z; a[4 * u + 3] = v.w;
+            }
+            if (half) {
+                a[14] = mk.x;
+                a[15] = mk.y;
+                st_split16_bias<BF16>(lane_base + TM_OWN_HI + 16, lane_base + TM_OWN_LO + 16, a);
+            } else {
+                st_split16<BF16>(lane_base + TM_OWN_HI, lane_base + TM_OWN_LO, a);
+            }
+        }
+    }
     if (BF16) {
         // 64-byte rows: four chunks of 8 channels; own row in the per-lane rotated order (key = lane & 3), msrc row swizzled
         // by (row >> 1) & 3 — conflict free, static registers
@@ -276,7 +304,7 @@ __device__ __forceinline__ float4 s1_own_operands(const unsigned char* sb, int r
         }
         return mk;
     }
-    {
+    if (!ASSOC) {
         float4 own[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) own[c] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -321,14 +349,16 @@ __device__ __forceinline__ float4 s1_own_operands(const unsigned char* sb, int r
     return mk;
 }
 
-template <bool EDGE, bool BF16>
+template <bool EDGE, bool BF16, bool ASSOC>
 __global__ void __launch_bounds__(S1_THREADS, 1)
-    da_layer1_s_kernel(const float* __restrict__ packed, const float* __restrict__ p, const float* __restrict__ msrc,
+    da_layer1_s_kernel(const float* __restrict__ tcw, const float* __restrict__ p, const float* __restrict__ msrc,
                        const float* __restrict__ mask, float* __restrict__ zc, float* __restrict__ va,
                        float* __restrict__ vb, int S, int NT, const int32_t* __restrict__ tile_rows,
                        const int32_t* __restrict__ tile_meta, const uint16_t* __restrict__ tile_nbr,
                        const float* __restrict__ tile_invdeg, int64_t n_tiles, const float* __restrict__ edge_sta,
-                       const float* __restrict__ edge_src, long long* __restrict__ trace, int trace_tiles, int trace_start) {
+                       const float* __restrict__ edge_src, const float* __restrict__ tr_own,
+                       const float* __restrict__ mask_out, long long* __restrict__ trace, int trace_tiles, int trace_start) {
+    static_assert(!(ASSOC && BF16), "the association rows are fp32");
     extern __shared__ __align__(1024) unsigned char smem[];
     using F = Fmt<BF16>;
     constexpr int NBUF = F::NBUF;
@@ -338,7 +368,6 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
     // was measured and lost: 8.6 -> 10.0 ms at C4, the extra shared-memory reads land in the gather phase (r9a).
     constexpr bool OWN_BY_GATHER = false;
     const bool packed_mask = mask == nullptr;
-    const float* tcw = packed + T2_BASE;
     if (tcw[T2_SCAL + TCS_OK] == 0.f) return;   // slopes not eligible: the generic kernels run instead (uniform exit)
 
     float* sW = reinterpret_cast<float*>(smem + SM_W);
@@ -349,7 +378,9 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
     {
         const float4* src = reinterpret_cast<const float4*>(tcw);
         float4* dst = reinterpret_cast<float4*>(sW);
-        for (int i = threadIdx.x; i < T2_FLOATS / 4; i += S1_THREADS) dst[i] = src[i];
+        constexpr int NW4 = (T2_FLOATS + (ASSOC ? S1_ASSOC_TERMS : 0)) / 4;
+        static_assert(NW4 * 16 <= SM_BUF, "weight blob");
+        for (int i = threadIdx.x; i < NW4; i += S1_THREADS) dst[i] = src[i];
         // the zero row of every staging buffer (padding target of the neighbour table)
         if (threadIdx.x < NPIPE * NBUF * F::CPR) {
             const int b = threadIdx.x / F::CPR, c = threadIdx.x % F::CPR;
@@ -413,6 +444,12 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
 #pragma unroll
             for (int j = 0; j < JMAX; ++j)
                 if (ids[j] >= 0) cp_async16(sb + F::SB_P + (rr + RPP * j) * F::RB + c * 16, pb + (node0 + ids[j]) * F::RB + c * 16);
+            if (ASSOC && c == 0) {
+#pragma unroll
+                for (int j = 0; j < JOWN; ++j)
+                    if (rr + RPP * j < n_own)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(tr_own + (node0 + ids[j]) * 32));
+            }
 #pragma unroll
             for (int j = 0; j < JOWN; ++j) {
                 const int r = rr + RPP * j;
@@ -555,7 +592,9 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
             //      loads are all in flight before the first store ----------------------------------------------------------
             mbar_wait(&bars->raw[q][bi], n & 1);
             const int n_rows = __ldg(tile_meta + 2 * T + 1);
-            if (BF16) {
+            if (ASSOC) {
+                // the staged rows are the messages themselves
+            } else if (BF16) {
                 // 64-byte rows: chunk r & 3 of the rows (r >> 2) + 32 u
                 unsigned char* cb = sb + F::SB_P + (r >> 2) * 64 + (r & 3) * 16;
                 constexpr int CB = (ROWS + 31) / 32;
@@ -668,7 +707,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                 }
             }
             if (OWN_BY_GATHER) {
-                s1_own_operands<BF16>(sb, r, valid, key, sc[TCS_INV11], lane_base, packed_mask);
+                s1_own_operands<BF16, false>(sb, r, valid, key, sc[TCS_INV11], lane_base, packed_mask, nullptr);
                 mbar_arrive(&bars->empty[q][bi]);
             }
             tmem_st_wait();
@@ -701,7 +740,9 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                     mk = s1_load_mask<BF16>(smem + SM_BUF + (q * NBUF) * F::SB_SIZE, r, valid, packed_mask);
                     mbar_arrive(&bars->empty[q][0]);
                 } else {
-                    mk = s1_own_operands<BF16>(smem + SM_BUF + (q * NBUF) * F::SB_SIZE, r, valid, key, inv11, lane_base, packed_mask);
+                    const float* own_row = (ASSOC && valid) ? tr_own + ((int64_t)g * S + __ldg(tile_rows + (int64_t)T * ROWS + r)) * 32 : nullptr;
+                    mk = s1_own_operands<BF16, ASSOC>(smem + SM_BUF + (q * NBUF) * F::SB_SIZE, r, valid, key, inv11, lane_base, packed_mask,
+                                                      own_row);
                     mbar_arrive(&bars->empty[q][0]);
                     tmem_st_wait();
                     tc_fence_before_sync();
@@ -734,6 +775,8 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                 et_sta = edge_sta + (int64_t)srow * GENIE_EDGE_TERM_LD;
                 et_src = edge_src + (int64_t)g * GENIE_EDGE_TERM_LD;
             }
+            const float mo = ASSOC ? __ldg(mask_out + g) : 0.f;      // source mask of the tile's grid node (fifth mask channel)
+            const float* term = sW + T2_FLOATS;
             // ---- stage B epilogue: tr = PReLU1(X) -> A operand of stage C (mask in the four spare columns) -----------------
             mbar_wait(&bars->d_full[q], ph_d);
             ph_d ^= 1;
@@ -751,6 +794,10 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                         const float4 e = __ldg(e4 + u);
                         v[4 * u] += e.x; v[4 * u + 1] += e.y; v[4 * u + 2] += e.z; v[4 * u + 3] += e.w;
                     }
+                }
+                if (ASSOC) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = fmaf(mo, term[c + i], v[i]);
                 }
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = prelu_f(v[i], a1);
@@ -798,6 +845,10 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                         v[4 * u] += e.x; v[4 * u + 1] += e.y; v[4 * u + 2] += e.z; v[4 * u + 3] += e.w;
                     }
                 }
+                if (ASSOC) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = fmaf(mo, term[64 + c + i], v[i]);
+                }
                 if (c == 0) v[15] = fmaxf(fmaxf(mk.x, mk.y), fmaxf(mk.z, mk.w));     // padding channel 15: max_c(mask) for layer 2's read-in
                 store16_rows(v, scr, lane, sid, zc + c, node0, LD_ZC);
             }
@@ -832,8 +883,9 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                     mk = s1_load_mask<BF16>(smem + SM_BUF + (q * NBUF + b2) * F::SB_SIZE, r, valid, packed_mask);
                     mbar_arrive(&bars->empty[q][b2]);
                 } else {
-                    mk = s1_own_operands<BF16>(smem + SM_BUF + (q * NBUF + b2) * F::SB_SIZE, r, valid, key, inv11, lane_base,
-                                               packed_mask);
+                    const float* own_row = (ASSOC && valid) ? tr_own + ((int64_t)g2 * S + __ldg(tile_rows + (int64_t)T2 * ROWS + r)) * 32 : nullptr;
+                    mk = s1_own_operands<BF16, ASSOC>(smem + SM_BUF + (q * NBUF + b2) * F::SB_SIZE, r, valid, key, inv11, lane_base,
+                                                      packed_mask, own_row);
                     mbar_arrive(&bars->empty[q][b2]);
                     tmem_st_wait();
                     tc_fence_before_sync();
@@ -860,28 +912,44 @@ void set_s1_trace(long long* buf, int tiles) {
     g_s1_trace_start = e ? atoi(e) : 0;
 }
 
-int launch_da_layer1_s(const genie_plan* p, const float* packed, const float* pfeat, const float* msrc,
-                       const float* mask, float* zc, float* va, float* vb, cudaStream_t st) {
+static int launch_s1(const genie_plan* p, bool assoc, const float* blob, const float* pfeat, const float* msrc, const float* mask,
+                     float* zc, float* va, float* vb, const float* edge_sta, const float* edge_src, const float* tr_own,
+                     const float* mask_out, cudaStream_t st) {
     const genie_graph_desc_t& g = p->g;
     const int64_t n_tiles = (int64_t)g.n_sta_tiles * (g.n_grid_owned > 0 ? g.n_grid_owned : g.n_grid);
     static PerDeviceOnce attr_set;
     if (attr_set.need()) {
-        GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer1_s_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fmt<false>::SM_TOTAL));
-        GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer1_s_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fmt<false>::SM_TOTAL));
-        GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer1_s_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fmt<true>::SM_TOTAL));
-        GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer1_s_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fmt<true>::SM_TOTAL));
+#define GENIE_S1_ATTR(E, B, A)                                                                                    \
+    GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer1_s_kernel<E, B, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          Fmt<B>::SM_TOTAL));
+        GENIE_S1_ATTR(false, false, false) GENIE_S1_ATTR(true, false, false) GENIE_S1_ATTR(false, true, false)
+        GENIE_S1_ATTR(true, true, false) GENIE_S1_ATTR(false, false, true) GENIE_S1_ATTR(true, false, true)
+#undef GENIE_S1_ATTR
         attr_set.mark();
     }
     const int64_t grid = n_tiles < p->sm_count ? n_tiles : p->sm_count;
-    const bool edge = p->edge_sta != nullptr, bf = p->storage == GENIE_STORAGE_BF16;
-    TimedLaunch tl(KID_DA_LAYER1_S, st);
-#define GENIE_S1_LAUNCH(E, B)                                                                                                  \
-    if (edge == E && bf == B)                                                                                                   \
-        da_layer1_s_kernel<E, B><<<(unsigned)grid, S1_THREADS, Fmt<B>::SM_TOTAL, st>>>(                                         \
-            packed, pfeat, msrc, mask, zc, va, vb, g.n_sta, g.n_sta_tiles, g.sta_tile_rows, g.sta_tile_meta, g.sta_tile_nbr,    \
-            g.sta_tile_invdeg, n_tiles, p->edge_sta, p->edge_src, g_s1_trace, g_s1_trace_tiles, g_s1_trace_start);
-    GENIE_S1_LAUNCH(false, false) GENIE_S1_LAUNCH(true, false) GENIE_S1_LAUNCH(false, true) GENIE_S1_LAUNCH(true, true)
+    const bool edge = edge_sta != nullptr, bf = !assoc && p->storage == GENIE_STORAGE_BF16;
+    TimedLaunch tl(assoc ? KID_ASSOC_LAYER1 : KID_DA_LAYER1_S, st);
+#define GENIE_S1_LAUNCH(E, B, A)                                                                                               \
+    if (edge == E && bf == B && assoc == A)                                                                                     \
+        da_layer1_s_kernel<E, B, A><<<(unsigned)grid, S1_THREADS, Fmt<B>::SM_TOTAL, st>>>(                                      \
+            blob, pfeat, msrc, mask, zc, va, vb, g.n_sta, g.n_sta_tiles, g.sta_tile_rows, g.sta_tile_meta, g.sta_tile_nbr,      \
+            g.sta_tile_invdeg, n_tiles, edge_sta, edge_src, tr_own, mask_out, g_s1_trace, g_s1_trace_tiles, g_s1_trace_start);
+    GENIE_S1_LAUNCH(false, false, false) GENIE_S1_LAUNCH(true, false, false) GENIE_S1_LAUNCH(false, true, false)
+    GENIE_S1_LAUNCH(true, true, false) GENIE_S1_LAUNCH(false, false, true) GENIE_S1_LAUNCH(true, false, true)
 #undef GENIE_S1_LAUNCH
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;
+}
+
+int launch_da_layer1_s(const genie_plan* p, const float* packed, const float* pfeat, const float* msrc,
+                       const float* mask, float* zc, float* va, float* vb, cudaStream_t st) {
+    return launch_s1(p, false, packed + T2_BASE, pfeat, msrc, mask, zc, va, vb, p->edge_sta, p->edge_src, nullptr, nullptr, st);
+}
+
+// Layer 1 of the association phase on a plan with tiling tables.  blob: T2_FLOATS + 96 floats built by launch_assoc_pack_t2;
+// a1 = PReLU(l1_t1_1 tr) rows, msrc = mean over source neighbours of PReLU(l1_t2_1 tr), mask [P,4], mask_out [G].
+int launch_assoc_layer1_s(const genie_plan* p, const float* blob, const float* tr, const float* a1, const float* msrc,
+                          const float* mask, const float* mask_out, float* zc, float* va, float* vb, cudaStream_t st) {
+    return launch_s1(p, true, blob, a1, msrc, mask, zc, va, vb, p->assoc_edge_sta, p->assoc_edge_src, tr, mask_out, st);
 }

@@ -211,9 +211,13 @@ struct AssocWorkspace {
     float* msrc;      // [P][32]   mean over source neighbours of a2 (plans with tiling tables)
     float* yfc1;      // [G][32]   read-out fc1, y_latent half
     float* mask_out;  // [G]
+    float* t2;        // tensor-core blob of layer 1 (plans with tiling tables), layout.h T2_FLOATS + 96 floats
     size_t bytes;
 };
 AssocWorkspace carve_assoc_workspace(const genie_plan* p, void* base);
+int launch_assoc_pack_t2(const float* assoc_packed, float* blob, cudaStream_t st);
+int launch_assoc_layer1_s(const genie_plan* p, const float* blob, const float* tr, const float* a1, const float* msrc,
+                          const float* mask, const float* mask_out, float* zc, float* va, float* vb, cudaStream_t st);
 size_t assoc_packed_floats();
 int assoc_layout(int32_t* out, int n);
 int launch_assoc_product(const genie_plan* p, const float* packed, const float* x_spatial, int ld_x, const float* y, int T,

@@ -1,5 +1,6 @@
 // Re-lays the reference's nn.Linear / nn.PReLU parameters (module.py:53-83, 214-222, 231-241) into the packed kernel
 // layout of layout.h.  One CTA; runs once per weight update.
+#include "assoc_layout.h"
 #include "common.cuh"
 
 using namespace gl;
@@ -225,11 +226,90 @@ __global__ void pack_weights_kernel(const genie_frontend_weights_t w, float* __r
     pack_t2(w, p + T2_BASE, p + TC_BASE);
 }
 
+// Tensor-core blob of the association phase's layer 1 (da_s1_kernel.cu, ASSOC = true): the T2_* layout filled from the
+// K-major matrices of the packed association weights (assoc_layout.h), followed by the weight columns of the source mask
+// (mask channel 0 of the phase, module.py:388: mask = [mask_out | Mask]) that the epilogues add: [tr1(32) | tr2(32) | c_a(16) | c_b(16)].
+__global__ void assoc_pack_t2_kernel(const float* __restrict__ ap, float* __restrict__ t) {
+    for (int i = threadIdx.x; i < T2_FLOATS + 96; i += blockDim.x) t[i] = 0.f;
+    __syncthreads();
+    const float *W11 = ap + as::W11, *W12 = ap + as::W12;          // [65 of 68][32]: rows 0-29 tr, 30-59 mean, 60 mask_out, 61-64 Mask
+    const float *W21A = ap + as::W21A, *W22A = ap + as::W22A;      // [60][32]
+    const float *WCA = ap + as::WCA, *WCB = ap + as::WCB;          // [65 of 68][16]: rows 0-59 tr, 60 mask_out, 61-64 Mask
+    const float *WVA = ap + as::WVA, *WVB = ap + as::WVB;          // [30][16]
+    auto s1a = [=](int n, int k) -> float {
+        const int o = n & 31;
+        if (o >= 30) return 0.f;
+        const float* W = n < 32 ? W11 : W12;
+        return k < 30 ? W[k * 32 + o] : W[(61 + (k - 30)) * 32 + o];         // k 30, 31: Mask0, Mask1
+    };
+    pack_umma(t + T2_S1A_HI, t + T2_S1A_LO, 64, 32, s1a);
+    pack_bias_block(t + T2_S1A_BIAS, 64, s1a, [=](int n) -> float {
+        const int o = n & 31;
+        return o < 30 ? ap[(n < 32 ? as::B11 : as::B12) + o] : 0.f;
+    });
+    pack_umma(t + T2_S1B_HI, t + T2_S1B_LO, 32, 32, [=](int n, int k) -> float {
+        if (n >= 30) return 0.f;
+        return k < 30 ? W11[(30 + k) * 32 + n] : W11[(63 + (k - 30)) * 32 + n];      // k 30, 31: Mask2, Mask3
+    });
+    pack_umma(t + T2_S1C_HI, t + T2_S1C_LO, 32, 32, [=](int n, int k) -> float {
+        if (n >= 30) return 0.f;
+        return k < 30 ? W12[(30 + k) * 32 + n] : W12[(63 + (k - 30)) * 32 + n];
+    });
+    auto s2 = [=](int n, int k) -> float {
+        const int kt = k < 30 ? k : (k >= 32 && k < 62) ? k - 2 : -1;
+        const int km = k == 30 ? 0 : k == 31 ? 1 : k == 62 ? 2 : k == 63 ? 3 : -1;
+        if (n < 64) {
+            const int o = n & 31;
+            if (o >= 30 || kt < 0) return 0.f;
+            return (n < 32 ? W21A : W22A)[kt * 32 + o];
+        }
+        const int o = (n - 64) & 15;
+        if (o >= 15) return 0.f;
+        const float* W = n < 80 ? WCA : WCB;
+        if (kt >= 0) return W[kt * 16 + o];
+        if (km >= 0) return W[(61 + km) * 16 + o];
+        return 0.f;
+    };
+    pack_umma(t + T2_S2_HI, t + T2_S2_LO, 96, 64, s2);
+    pack_bias_block(t + T2_S2_BIAS, 96, s2, [=](int n) -> float {
+        if (n < 30) return ap[as::B21A + n];
+        if (n >= 32 && n < 62) return ap[as::B22A + n - 32];
+        if (n >= 64 && n < 79) return ap[as::BCA + n - 64];
+        if (n >= 80 && n < 95) return ap[as::BCB + n - 80];
+        return 0.f;
+    });
+    pack_umma(t + T2_S3A_HI, t + T2_S3A_LO, 16, 32, [=](int n, int k) -> float { return (n < 15 && k < 30) ? WVA[k * 16 + n] : 0.f; });
+    pack_umma(t + T2_S3B_HI, t + T2_S3B_LO, 16, 32, [=](int n, int k) -> float { return (n < 15 && k < 30) ? WVB[k * 16 + n] : 0.f; });
+    if (threadIdx.x == 0) {
+        t[T2_SCAL + TCS_OK] = 1.f;
+        t[T2_SCAL + TCS_A1] = ap[as::SL + as::SL_A1];
+        t[T2_SCAL + TCS_A21] = ap[as::SL + as::SL_A21];
+        t[T2_SCAL + TCS_A22] = ap[as::SL + as::SL_A22];
+    }
+    for (int n = threadIdx.x; n < 96; n += blockDim.x) {
+        float v = 0.f;
+        if (n < 64) {
+            const int o = n & 31;
+            if (o < 30) v = (n < 32 ? W11 : W12)[60 * 32 + o];
+        } else {
+            const int o = (n - 64) & 15;
+            if (o < 15) v = (n < 80 ? WCA : WCB)[60 * 16 + o];
+        }
+        t[T2_FLOATS + n] = v;
+    }
+}
+
 }  // namespace
 
 int launch_pack_weights(const genie_frontend_weights_t* w, float* packed, cudaStream_t st) {
     TimedLaunch tl(KID_PACK, st);
     pack_weights_kernel<<<1, 256, 0, st>>>(*w, packed);
+    GENIE_LAUNCH_CHECK();
+    return GENIE_OK;
+}
+
+int launch_assoc_pack_t2(const float* assoc_packed, float* blob, cudaStream_t st) {
+    assoc_pack_t2_kernel<<<1, 256, 0, st>>>(assoc_packed, blob);
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;
 }
