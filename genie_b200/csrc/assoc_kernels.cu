@@ -542,7 +542,10 @@ int launch_assoc_product(const genie_plan* p, const float* packed, const float* 
     }
     float* m2src = split ? w.a1 : nullptr;             // a1 is dead after layer 1: [P][16] fits in its [P][32]
     if (split && (rc = launch_src_mean(p, 16, w.vb, m2src, nullptr, st))) return rc;
-    {
+    if (split && p->g.n_sta_tiles <= 32) {
+        // the station half on chip as well: the layer-2 station pass of the front end without its read-in (da_s2_kernel.cu, ASSOC)
+        if ((rc = launch_assoc_layer2_s(p, packed + as::SL + as::SL_A2, w.zc, w.va, m2src, w.tr, st))) return rc;
+    } else {
         const int64_t blocks = split ? (P / 2 + 8) / 8 : (P + 7) / 8;
         const int64_t cap = (int64_t)p->sm_count * 16;
         const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);

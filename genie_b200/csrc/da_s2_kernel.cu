@@ -99,13 +99,15 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 }
 
 // BF16: the mean_src(v_b) rows `m2` are bf16 (32 bytes; genie_plan_set_storage), staged as they are and widened on read.
-template <bool STORE_LATENT, int CSLOT, bool BF16>
+// ASSOC: layer 2 of DataAggregationAssociationPhase (module.py:400-402) — the same gather and activation with the phase's slope
+// `*a2_assoc`, the rows stored as [o1(15) 0 | o2(15) 0] into `latent_out` (ld 32); no read-in follows.
+template <bool STORE_LATENT, int CSLOT, bool BF16, bool ASSOC = false>
 __global__ void __launch_bounds__(S2_THREADS, 1)
     da_layer2_s_kernel(const float* __restrict__ packed, const float* __restrict__ zc, const float* __restrict__ va,
                        const float* __restrict__ m2, const float* __restrict__ mask, const float* __restrict__ edge_attr,
                        float* __restrict__ latent_out, float* __restrict__ out, int ld_out, int S, int G, int NT,
                        const int32_t* __restrict__ tile_rows, const int32_t* __restrict__ tile_meta,
-                       const uint16_t* __restrict__ tile_nbr, const float* __restrict__ tile_invdeg) {
+                       const uint16_t* __restrict__ tile_nbr, const float* __restrict__ tile_invdeg, const float* __restrict__ a2_assoc) {
     extern __shared__ __align__(128) unsigned char smem[];
     const float* c_ri = c_ri_slots[CSLOT];     // compile-time slot: fc1 stays immediate constant-bank operands
     float* sW = reinterpret_cast<float*>(smem + SM_W);
@@ -114,7 +116,8 @@ __global__ void __launch_bounds__(S2_THREADS, 1)
     Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    for (int i = threadIdx.x; i < W_FLOATS; i += S2_THREADS) sW[i] = packed[RI_WFC1 + i];
+    if (!ASSOC)
+        for (int i = threadIdx.x; i < W_FLOATS; i += S2_THREADS) sW[i] = packed[RI_WFC1 + i];
     if (threadIdx.x < N_WG * 4) {       // zero rows of the v_a areas
         const int b = threadIdx.x >> 2, c = threadIdx.x & 3;
         *reinterpret_cast<float4*>(smem + SM_BUF + b * SB_SIZE + SB_VA + ROWS * 64 + c * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -127,9 +130,9 @@ __global__ void __launch_bounds__(S2_THREADS, 1)
         for (int s = 0; s < G_SLOTS; ++s) bars->count[s] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    const float a2 = packed[DA_SLOPES + SL_A2];
+    const float a2 = ASSOC ? __ldg(a2_assoc) : packed[DA_SLOPES + SL_A2];
     __syncthreads();
-    const float ri_a1 = sW[RI_SLOPES - RI_WFC1], ri_a2 = sW[RI_SLOPES - RI_WFC1 + 1];
+    const float ri_a1 = ASSOC ? 0.f : sW[RI_SLOPES - RI_WFC1], ri_a2 = ASSOC ? 0.f : sW[RI_SLOPES - RI_WFC1 + 1];
 
     // number of grid nodes of this CTA and of its tiles
     const int n_g = blockIdx.x < G ? (G - 1 - blockIdx.x) / gridDim.x + 1 : 0;
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1)
             const uint4 n0 = __ldg(nb), n1 = __ldg(nb + 1);
             const float invdeg = __ldg(tile_invdeg + T * 128 + r);
             float e0 = 0.f, e1 = 0.f, e2 = 0.f;
-            if (valid) {
+            if (!ASSOC && valid) {
                 e0 = __ldg(edge_attr + node * 3);
                 e1 = __ldg(edge_attr + node * 3 + 1);
                 e2 = __ldg(edge_attr + node * 3 + 2);
@@ -274,6 +277,16 @@ __global__ void __launch_bounds__(S2_THREADS, 1)
             }
             mbar_arrive(&bars->empty[wg]);           // release: every shared-memory read of this tile has completed
             // x[0..14] = first half, x[16..30] = second half (x[15], x[31] are padding)
+            if (ASSOC) {
+                if (valid) {
+                    x[15] = 0.f;
+                    x[31] = 0.f;
+                    float4* dst = reinterpret_cast<float4*>(latent_out + node * 32);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) __stcs(dst + c, make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]));
+                }
+                continue;
+            }
             if (STORE_LATENT && valid) {
                 float2* dst = reinterpret_cast<float2*>(latent_out + node * 30);       // 120-byte rows: 8-byte aligned
 #pragma unroll
@@ -372,7 +385,7 @@ int launch_da_layer2_s(const genie_plan* p, const float* packed, const float* zc
         if (L == (latent_out != nullptr) && C == p->cslot && B == bf)                                                           \
             da_layer2_s_kernel<L, C, B><<<grid, S2_THREADS, SM_TOTAL, st>>>(packed, zc, va, m2, mask, edge_attr, latent_out, out, ld_out, \
                                                                             g.n_sta, n_own, g.n_sta_tiles, g.sta_tile_rows,    \
-                                                                            g.sta_tile_meta, g.sta_tile_nbr, g.sta_tile_invdeg); \
+                                                                            g.sta_tile_meta, g.sta_tile_nbr, g.sta_tile_invdeg, nullptr); \
     } while (0)
 #define GENIE_S2_LAUNCH(L, C) GENIE_S2_LAUNCH_B(L, C, false); GENIE_S2_LAUNCH_B(L, C, true)
     GENIE_S2_LAUNCH(false, 0); GENIE_S2_LAUNCH(false, 1); GENIE_S2_LAUNCH(false, 2); GENIE_S2_LAUNCH(false, 3);
@@ -380,6 +393,30 @@ int launch_da_layer2_s(const genie_plan* p, const float* packed, const float* zc
 #undef GENIE_S2_LAUNCH
 #undef GENIE_S2_LAUNCH_B
     if (set_attr) attr_set.mark();
+    GENIE_LAUNCH_CHECK();
+    return GENIE_OK;
+}
+
+// Layer 2 of the association phase on a plan with tiling tables: s rows [P][32] = PReLU(zc + [mean_sta v_a | m2]) with padding
+// channels 15 and 31 zero.  m2: mean over source neighbours of v_b, [P][16] (src_mean_kernels.cu).
+int launch_assoc_layer2_s(const genie_plan* p, const float* slope_dev, const float* zc, const float* va, const float* m2, float* s_out,
+                          cudaStream_t st) {
+    const genie_graph_desc_t& g = p->g;
+    if (g.n_sta_tiles > NT_MAX) {
+        set_error("launch_assoc_layer2_s: too many station tiles");
+        return GENIE_ERR_UNSUPPORTED;
+    }
+    const int n_own = g.n_grid_owned > 0 ? g.n_grid_owned : g.n_grid;
+    const unsigned grid = (unsigned)(n_own < p->sm_count ? n_own : p->sm_count);
+    static PerDeviceOnce attr_set;
+    if (attr_set.need()) {
+        GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer2_s_kernel<false, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        attr_set.mark();
+    }
+    TimedLaunch tl(KID_ASSOC_LAYER2, st);
+    da_layer2_s_kernel<false, 0, false, true><<<grid, S2_THREADS, SM_TOTAL, st>>>(
+        nullptr, zc, va, m2, nullptr, nullptr, s_out, nullptr, 0, g.n_sta, n_own, g.n_sta_tiles, g.sta_tile_rows, g.sta_tile_meta,
+        g.sta_tile_nbr, g.sta_tile_invdeg, slope_dev);
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;
 }

@@ -218,6 +218,8 @@ AssocWorkspace carve_assoc_workspace(const genie_plan* p, void* base);
 int launch_assoc_pack_t2(const float* assoc_packed, float* blob, cudaStream_t st);
 int launch_assoc_layer1_s(const genie_plan* p, const float* blob, const float* tr, const float* a1, const float* msrc,
                           const float* mask, const float* mask_out, float* zc, float* va, float* vb, cudaStream_t st);
+int launch_assoc_layer2_s(const genie_plan* p, const float* slope_dev, const float* zc, const float* va, const float* m2, float* s_out,
+                          cudaStream_t st);
 size_t assoc_packed_floats();
 int assoc_layout(int32_t* out, int n);
 int launch_assoc_product(const genie_plan* p, const float* packed, const float* x_spatial, int ld_x, const float* y, int T,
