@@ -97,13 +97,69 @@ __global__ void __launch_bounds__(128) assoc_grid_pre_kernel(const float* __rest
 constexpr int K0_THREADS = 128;
 constexpr int K0_W0 = as::RO_WA;                       // first packed float staged in shared memory
 constexpr int K0_W_FLOATS = as::INIT_END - K0_W0;
-constexpr size_t K0_SMEM = (size_t)K0_W_FLOATS * sizeof(float);
+// Every thread owns NPT = 2 nodes (rows lane and lane + 32 of the warp's 64 consecutive nodes): a weight row read from shared
+// memory (a broadcast LDS.128 still returns 512 bytes per warp — the pipe that bounded the one-node version at 18.6 ms at
+// 1000 x 50000) feeds two accumulator sets.
+constexpr int K0_NPT = 2, K0_WROWS = 32 * K0_NPT;
+// per-warp staging (floats): the warp's x_latent rows and edge-attribute rows, and one 32 x 32 output tile
+constexpr int K0_XL = K0_WROWS * 30, K0_EA = K0_WROWS * 3, K0_OUT = 32 * 32;
+constexpr int K0_WARP_FLOATS = K0_XL + K0_EA + K0_OUT;
+constexpr size_t K0_SMEM = (size_t)(K0_W_FLOATS + (K0_THREADS / 32) * K0_WARP_FLOATS) * sizeof(float);
+static_assert(K0_W_FLOATS % 4 == 0 && K0_WARP_FLOATS % 4 == 0, "16-byte alignment of the staging areas");
 
-__device__ __forceinline__ void store_row32(float* __restrict__ dst, const float (&v)[30]) {
-    float4* d = reinterpret_cast<float4*>(dst);
+// acc_u[0..N) += a_u * wrow[0..N) for the thread's two nodes: one shared-memory read per weight chunk
+__device__ __forceinline__ void fma_row30x2(float (&acc)[K0_NPT][30], const float (&a)[K0_NPT], const float* __restrict__ wrow) {
+    const float4* w4 = reinterpret_cast<const float4*>(wrow);
 #pragma unroll
-    for (int c = 0; c < 7; ++c) d[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-    d[7] = make_float4(v[28], v[29], 0.f, 0.f);
+    for (int c = 0; c < 7; ++c) {
+        const float4 w = w4[c];
+#pragma unroll
+        for (int u = 0; u < K0_NPT; ++u) {
+            acc[u][4 * c + 0] = fmaf(a[u], w.x, acc[u][4 * c + 0]);
+            acc[u][4 * c + 1] = fmaf(a[u], w.y, acc[u][4 * c + 1]);
+            acc[u][4 * c + 2] = fmaf(a[u], w.z, acc[u][4 * c + 2]);
+            acc[u][4 * c + 3] = fmaf(a[u], w.w, acc[u][4 * c + 3]);
+        }
+    }
+    const float2 w = *reinterpret_cast<const float2*>(wrow + 28);
+#pragma unroll
+    for (int u = 0; u < K0_NPT; ++u) {
+        acc[u][28] = fmaf(a[u], w.x, acc[u][28]);
+        acc[u][29] = fmaf(a[u], w.y, acc[u][29]);
+    }
+}
+__device__ __forceinline__ void fma_row16x2(float (&acc)[K0_NPT][16], const float (&a)[K0_NPT], const float* __restrict__ wrow) {
+    const float4* w4 = reinterpret_cast<const float4*>(wrow);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float4 w = w4[c];
+#pragma unroll
+        for (int u = 0; u < K0_NPT; ++u) {
+            acc[u][4 * c + 0] = fmaf(a[u], w.x, acc[u][4 * c + 0]);
+            acc[u][4 * c + 1] = fmaf(a[u], w.y, acc[u][4 * c + 1]);
+            acc[u][4 * c + 2] = fmaf(a[u], w.z, acc[u][4 * c + 2]);
+            acc[u][4 * c + 3] = fmaf(a[u], w.w, acc[u][4 * c + 3]);
+        }
+    }
+}
+
+// Rows of 32 floats of 32 consecutive nodes (thread = node) -> global memory as 512-byte runs: the rows pass through a
+// warp-private 4 KB tile (16-byte chunks XOR-swizzled by row: conflict free both ways).  A thread-per-row STG.128 touches
+// 32 lines per instruction; this is 8 instructions of 4 lines each.
+__device__ __forceinline__ void store_rows32(float* __restrict__ dst_row0, const float (&v)[30], float* tile, int lane, int n_rows) {
+    float4* t4 = reinterpret_cast<float4*>(tile);
+#pragma unroll
+    for (int c = 0; c < 7; ++c) t4[lane * 8 + (c ^ (lane & 7))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    t4[lane * 8 + (7 ^ (lane & 7))] = make_float4(v[28], v[29], 0.f, 0.f);
+    __syncwarp();
+    float4* d = reinterpret_cast<float4*>(dst_row0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int row = 4 * j + (lane >> 3), c = lane & 7;
+        const float4 x = t4[row * 8 + (c ^ (row & 7))];
+        if (row < n_rows) __stcs(d + j * 32 + lane, x);
+    }
+    __syncwarp();
 }
 
 __global__ void __launch_bounds__(K0_THREADS)
@@ -118,89 +174,149 @@ __global__ void __launch_bounds__(K0_THREADS)
     const float a_in = packed[as::SL + as::SL_A], a11 = packed[as::SL + as::SL_A11], a12 = packed[as::SL + as::SL_A12];
     __syncthreads();
     const float* sW = sW0 - K0_W0;                     // index with the packed offsets
-    const int64_t i = (int64_t)blockIdx.x * K0_THREADS + threadIdx.x;
-    if (i >= gv.P) return;
-    const int g = node_grid(gv, i);
-    const float mo = mask_out[g];
-    float tr[30];
+    const int lane = threadIdx.x & 31;
+    const int64_t i0 = ((int64_t)blockIdx.x * (K0_THREADS / 32) + (threadIdx.x >> 5)) * K0_WROWS;      // first node of the warp
+    if (i0 >= gv.P) return;
+    const int n_rows = (int)min((int64_t)K0_WROWS, gv.P - i0);
+    // the warp's x_latent rows (30 floats each) and edge-attribute rows are contiguous: coalesced 16-byte loads into shared
+    // memory, then every thread reads its own rows (8-byte reads at a 120-byte stride: conflict free)
+    float* sXL = sW0 + K0_W_FLOATS + (threadIdx.x >> 5) * K0_WARP_FLOATS;
+    float* sEA = sXL + K0_XL;
+    float* sOUT = sEA + K0_EA;
+    {
+        const float4* src = reinterpret_cast<const float4*>(x_latent + i0 * 30);     // i0 is a multiple of 64: 16-byte aligned
+        const int n4 = n_rows * 30 / 4, rem = n_rows * 30 - 4 * n4;
+#pragma unroll
+        for (int j = 0; j < K0_XL / 128; ++j) {
+            const int k = j * 32 + lane;
+            if (k < n4) reinterpret_cast<float4*>(sXL)[k] = __ldg(src + k);
+        }
+        if (lane < rem) sXL[4 * n4 + lane] = __ldg(x_latent + i0 * 30 + 4 * n4 + lane);
+        const float* ea = edge_attr + i0 * 3;
+#pragma unroll
+        for (int j = 0; j < K0_EA / 32; ++j)
+            if (j * 32 + lane < n_rows * 3) sEA[j * 32 + lane] = __ldg(ea + j * 32 + lane);
+    }
+    __syncwarp();
+    bool live[K0_NPT];
+    int row[K0_NPT], g[K0_NPT];
+    int64_t node[K0_NPT];
+    float mo[K0_NPT];
+#pragma unroll
+    for (int u = 0; u < K0_NPT; ++u) {
+        live[u] = lane + 32 * u < n_rows;
+        row[u] = live[u] ? lane + 32 * u : 0;          // idle threads of the last warp shadow its first node (no stores)
+        node[u] = i0 + row[u];
+        g[u] = node_grid(gv, node[u]);
+        mo[u] = mask_out[g[u]];
+    }
+    float tr[K0_NPT][30];
     {
         // read-out: s0 = PReLU(fc2(mask_j * PReLU(fc1 [y_latent_g | attr_i])))       (module.py:346, 350-352)
-        float h[30];
-        const float4* yr = reinterpret_cast<const float4*>(yfc1 + (int64_t)g * 32);
+        float h[K0_NPT][30];
 #pragma unroll
-        for (int c = 0; c < 7; ++c) {
-            const float4 v = __ldg(yr + c);
-            h[4 * c] = v.x; h[4 * c + 1] = v.y; h[4 * c + 2] = v.z; h[4 * c + 3] = v.w;
-        }
-        {
+        for (int u = 0; u < K0_NPT; ++u) {
+            const float4* yr = reinterpret_cast<const float4*>(yfc1 + (int64_t)g[u] * 32);
+#pragma unroll
+            for (int c = 0; c < 7; ++c) {
+                const float4 v = __ldg(yr + c);
+                h[u][4 * c] = v.x; h[u][4 * c + 1] = v.y; h[u][4 * c + 2] = v.z; h[u][4 * c + 3] = v.w;
+            }
             const float4 v = __ldg(yr + 7);
-            h[28] = v.x; h[29] = v.y;
+            h[u][28] = v.x; h[u][29] = v.y;
         }
 #pragma unroll
-        for (int k = 0; k < 3; ++k) fma_row30(h, edge_attr[i * 3 + k], sW + as::RO_WA + k * 32);
-        float s[16];
+        for (int k = 0; k < 3; ++k) {
+            const float a[K0_NPT] = {sEA[row[0] * 3 + k], sEA[row[1] * 3 + k]};
+            fma_row30x2(h, a, sW + as::RO_WA + k * 32);
+        }
+        float s[K0_NPT][16];
 #pragma unroll
-        for (int o = 0; o < 16; ++o) s[o] = sW[as::RO_B2 + o];
+        for (int u = 0; u < K0_NPT; ++u)
 #pragma unroll
-        for (int k = 0; k < 30; ++k) fma_row16(s, mo * prelu(h[k], a_ro1), sW + as::RO_W2 + k * 16);
+            for (int o = 0; o < 16; ++o) s[u][o] = sW[as::RO_B2 + o];
 #pragma unroll
-        for (int o = 0; o < 15; ++o) s[o] = prelu(s[o], a_ro2);
-        if (s0_out != nullptr) {
+        for (int k = 0; k < 30; ++k) {
+            const float a[K0_NPT] = {mo[0] * prelu(h[0][k], a_ro1), mo[1] * prelu(h[1][k], a_ro1)};
+            fma_row16x2(s, a, sW + as::RO_W2 + k * 16);
+        }
 #pragma unroll
-            for (int o = 0; o < 15; ++o) s0_out[i * 15 + o] = s[o];
+        for (int u = 0; u < K0_NPT; ++u) {
+#pragma unroll
+            for (int o = 0; o < 15; ++o) s[u][o] = prelu(s[u][o], a_ro2);
+            if (s0_out != nullptr && live[u]) {
+#pragma unroll
+                for (int o = 0; o < 15; ++o) s0_out[node[u] * 15 + o] = s[u][o];
+            }
         }
         // init_trns [s0 | x_latent | mask_out | Mask]                                (module.py:389-391)
 #pragma unroll
-        for (int o = 0; o < 30; ++o) tr[o] = sW[as::AI_B + o];
-        if (init_sta != nullptr) {
-            // use_absolute_pos (module.py:987-988): the six position channels of init_trns as additive terms
-            const float* ts = init_sta + (init_src != nullptr ? i - (int64_t)g * gv.S : i) * 32;
+        for (int u = 0; u < K0_NPT; ++u) {
 #pragma unroll
-            for (int o = 0; o < 30; ++o) tr[o] += __ldg(ts + o);
-            if (init_src != nullptr) {
-                const float* tg = init_src + (int64_t)g * 32;
+            for (int o = 0; o < 30; ++o) tr[u][o] = sW[as::AI_B + o];
+            if (init_sta != nullptr) {
+                // use_absolute_pos (module.py:987-988): the six position channels of init_trns as additive terms
+                const float* ts = init_sta + (init_src != nullptr ? node[u] - (int64_t)g[u] * gv.S : node[u]) * 32;
 #pragma unroll
-                for (int o = 0; o < 30; ++o) tr[o] += __ldg(tg + o);
+                for (int o = 0; o < 30; ++o) tr[u][o] += __ldg(ts + o);
+                if (init_src != nullptr) {
+                    const float* tg = init_src + (int64_t)g[u] * 32;
+#pragma unroll
+                    for (int o = 0; o < 30; ++o) tr[u][o] += __ldg(tg + o);
+                }
             }
         }
 #pragma unroll
-        for (int k = 0; k < 15; ++k) fma_row30(tr, s[k], sW + as::AI_W + k * 32);
-        const float2* xl = reinterpret_cast<const float2*>(x_latent + i * 30);
+        for (int k = 0; k < 15; ++k) {
+            const float a[K0_NPT] = {s[0][k], s[1][k]};
+            fma_row30x2(tr, a, sW + as::AI_W + k * 32);
+        }
+        const float2* xl0 = reinterpret_cast<const float2*>(sXL + row[0] * 30);
+        const float2* xl1 = reinterpret_cast<const float2*>(sXL + row[1] * 30);
 #pragma unroll 5
         for (int k = 0; k < 15; ++k) {
-            const float2 v = __ldg(xl + k);
-            fma_row30(tr, v.x, sW + as::AI_W + (15 + 2 * k) * 32);
-            fma_row30(tr, v.y, sW + as::AI_W + (16 + 2 * k) * 32);
+            const float2 v0 = xl0[k], v1 = xl1[k];
+            const float ax[K0_NPT] = {v0.x, v1.x}, ay[K0_NPT] = {v0.y, v1.y};
+            fma_row30x2(tr, ax, sW + as::AI_W + (15 + 2 * k) * 32);
+            fma_row30x2(tr, ay, sW + as::AI_W + (16 + 2 * k) * 32);
         }
-        fma_row30(tr, mo, sW + as::AI_W + 45 * 32);
-        const float4 mv = __ldg(reinterpret_cast<const float4*>(mask) + i);
-        fma_row30(tr, mv.x, sW + as::AI_W + 46 * 32);
-        fma_row30(tr, mv.y, sW + as::AI_W + 47 * 32);
-        fma_row30(tr, mv.z, sW + as::AI_W + 48 * 32);
-        fma_row30(tr, mv.w, sW + as::AI_W + 49 * 32);
+        fma_row30x2(tr, mo, sW + as::AI_W + 45 * 32);
+        const float4 mv0 = __ldg(reinterpret_cast<const float4*>(mask) + node[0]);
+        const float4 mv1 = __ldg(reinterpret_cast<const float4*>(mask) + node[1]);
+        {
+            const float m0[K0_NPT] = {mv0.x, mv1.x}, m1[K0_NPT] = {mv0.y, mv1.y}, m2[K0_NPT] = {mv0.z, mv1.z}, m3[K0_NPT] = {mv0.w, mv1.w};
+            fma_row30x2(tr, m0, sW + as::AI_W + 46 * 32);
+            fma_row30x2(tr, m1, sW + as::AI_W + 47 * 32);
+            fma_row30x2(tr, m2, sW + as::AI_W + 48 * 32);
+            fma_row30x2(tr, m3, sW + as::AI_W + 49 * 32);
+        }
 #pragma unroll
-        for (int o = 0; o < 30; ++o) tr[o] = prelu(tr[o], a_in);
+        for (int u = 0; u < K0_NPT; ++u)
+#pragma unroll
+            for (int o = 0; o < 30; ++o) tr[u][o] = prelu(tr[u][o], a_in);
     }
-    store_row32(tr_out + i * 32, tr);
-    {
-        float m[30];
 #pragma unroll
-        for (int o = 0; o < 30; ++o) m[o] = sW[as::M11_B + o];
+    for (int u = 0; u < K0_NPT; ++u) store_rows32(tr_out + (i0 + 32 * u) * 32, tr[u], sOUT, lane, n_rows - 32 * u);
+#pragma unroll 1
+    for (int br = 0; br < 2; ++br) {                   // the two layer-1 message maps, one after the other (register budget)
+        const int wo = br ? as::M12_W : as::M11_W, bo = br ? as::M12_B : as::M11_B;
+        const float sl = br ? a12 : a11;
+        float m[K0_NPT][30];
 #pragma unroll
-        for (int k = 0; k < 30; ++k) fma_row30(m, tr[k], sW + as::M11_W + k * 32);
+        for (int u = 0; u < K0_NPT; ++u)
 #pragma unroll
-        for (int o = 0; o < 30; ++o) m[o] = prelu(m[o], a11);
-        store_row32(a1_out + i * 32, m);
-    }
-    {
-        float m[30];
+            for (int o = 0; o < 30; ++o) m[u][o] = sW[bo + o];
 #pragma unroll
-        for (int o = 0; o < 30; ++o) m[o] = sW[as::M12_B + o];
+        for (int k = 0; k < 30; ++k) {
+            const float a[K0_NPT] = {tr[0][k], tr[1][k]};
+            fma_row30x2(m, a, sW + wo + k * 32);
+        }
 #pragma unroll
-        for (int k = 0; k < 30; ++k) fma_row30(m, tr[k], sW + as::M12_W + k * 32);
+        for (int u = 0; u < K0_NPT; ++u) {
 #pragma unroll
-        for (int o = 0; o < 30; ++o) m[o] = prelu(m[o], a12);
-        store_row32(a2_out + i * 32, m);
+            for (int o = 0; o < 30; ++o) m[u][o] = prelu(m[u][o], sl);
+            store_rows32((br ? a2_out : a1_out) + (i0 + 32 * u) * 32, m[u], sOUT, lane, n_rows - 32 * u);
+        }
     }
 }
 
@@ -515,7 +631,7 @@ int launch_assoc_product(const genie_plan* p, const float* packed, const float* 
         GENIE_CUDA_CHECK(cudaMemcpyAsync(mask_out_copy, w.mask_out, sizeof(float) * (size_t)G, cudaMemcpyDeviceToDevice, st));
     {
         TimedLaunch tl(KID_ASSOC_INIT, st);
-        assoc_init_kernel<<<(unsigned)((P + K0_THREADS - 1) / K0_THREADS), K0_THREADS, K0_SMEM, st>>>(
+        assoc_init_kernel<<<(unsigned)((P + K0_THREADS * K0_NPT - 1) / (K0_THREADS * K0_NPT)), K0_THREADS, K0_SMEM, st>>>(
             gv, packed, w.yfc1, w.mask_out, edge_attr, x_latent, mask, p->assoc_init_sta, p->assoc_init_src, s0_out, w.tr,
             w.a1, w.a2);
         GENIE_LAUNCH_CHECK();

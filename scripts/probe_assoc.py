@@ -58,7 +58,7 @@ def run(S, G, label, n_arv=600, n_src=2, Q=10000):
         f_fix()
     torch.cuda.synchronize()
     for k, (ms, n) in sorted(capi.timing_collect(reset=True).items()):
-        if n and k.startswith('assoc'):
+        if n:
             print('    %-28s %8.3f ms' % (k, ms / n), flush=True)
     capi.timing_enable(False)
     # algorithmic bytes per product node of the association kernels: init 12+120+16+4 + 3*128,
