@@ -12,6 +12,7 @@
 // ordering of an fp64 k-d tree query on the same fp32 points; ties keep the lower X index.  n_x * n_y = 2.5e9 pairs at
 // G = 50000 is ~25 GFLOP of fp64: a few milliseconds, once per station set.
 #include "common.cuh"
+#include <climits>
 
 namespace {
 
@@ -67,12 +68,103 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const float* __restric
     }
 }
 
+// Few query points (the association sources of forward_fixed, module.py:980: a handful of queries against 50000 grid nodes —
+// 2.7 ms on one thread per query): ONE CTA PER QUERY.  Thread t scans the X points t, t + 128, ... with the same sorted
+// insertion, then the 128 sorted lists are merged head by head: k rounds of a block-wide lexicographic (distance, index)
+// minimum, the winning thread drops its head.  Same result as the thread-per-query kernel: the k smallest by (distance, index).
+template <int K>
+__global__ void __launch_bounds__(KNN_THREADS) knn_few_kernel(const float* __restrict__ X, int n_x, const float* __restrict__ Y,
+                                                              int k, int64_t* __restrict__ idx_out) {
+    __shared__ double sd[KNN_THREADS / 32];
+    __shared__ int si[KNN_THREADS / 32];
+    __shared__ int s_win;
+    const int q = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double y0 = (double)Y[(int64_t)q * 3 + 0], y1 = (double)Y[(int64_t)q * 3 + 1], y2 = (double)Y[(int64_t)q * 3 + 2];
+    double bd[K];
+    int bi[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        bd[j] = INFINITY;
+        bi[j] = INT_MAX;
+    }
+    for (int i = threadIdx.x; i < n_x; i += KNN_THREADS) {
+        const double d0 = (double)__ldg(X + (int64_t)i * 3) - y0, d1 = (double)__ldg(X + (int64_t)i * 3 + 1) - y1,
+                     d2 = (double)__ldg(X + (int64_t)i * 3 + 2) - y2;
+        const double d = d0 * d0 + d1 * d1 + d2 * d2;
+        if (d < bd[K - 1]) {
+            bd[K - 1] = d;
+            bi[K - 1] = i;
+#pragma unroll
+            for (int j = K - 1; j > 0; --j) {
+                if (bd[j] < bd[j - 1]) {
+                    const double td = bd[j];
+                    bd[j] = bd[j - 1];
+                    bd[j - 1] = td;
+                    const int ti = bi[j];
+                    bi[j] = bi[j - 1];
+                    bi[j - 1] = ti;
+                }
+            }
+        }
+    }
+    for (int r = 0; r < k; ++r) {
+        double d = bd[0];
+        int i = bi[0];
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) {
+            const double od = __shfl_xor_sync(FULL_MASK, d, s);
+            const int oi = __shfl_xor_sync(FULL_MASK, i, s);
+            if (od < d || (od == d && oi < i)) {
+                d = od;
+                i = oi;
+            }
+        }
+        if (lane == 0) {
+            sd[warp] = d;
+            si[warp] = i;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double wd = sd[0];
+            int wi = si[0];
+#pragma unroll
+            for (int w = 1; w < KNN_THREADS / 32; ++w)
+                if (sd[w] < wd || (sd[w] == wd && si[w] < wi)) {
+                    wd = sd[w];
+                    wi = si[w];
+                }
+            s_win = wi;
+            idx_out[(int64_t)q * k + r] = wi == INT_MAX ? -1 : wi;
+        }
+        __syncthreads();
+        if (bi[0] == s_win && s_win != INT_MAX) {        // indices are unique across threads: exactly one list advances
+#pragma unroll
+            for (int j = 0; j < K - 1; ++j) {
+                bd[j] = bd[j + 1];
+                bi[j] = bi[j + 1];
+            }
+            bd[K - 1] = INFINITY;
+            bi[K - 1] = INT_MAX;
+        }
+    }
+}
+
+constexpr int KNN_FEW = 2048;        // up to this many queries: one CTA per query
+
 }  // namespace
 
 int launch_knn(const float* x, int n_x, const float* y, int n_y, int k, int64_t* idx_out, cudaStream_t st) {
     if (n_y == 0) return GENIE_OK;
     const unsigned grid = (unsigned)((n_y + KNN_THREADS - 1) / KNN_THREADS);
     TimedLaunch tl(KID_KNN, st);
+    if (n_y <= KNN_FEW && k <= 32) {
+        if (k <= 8) knn_few_kernel<8><<<n_y, KNN_THREADS, 0, st>>>(x, n_x, y, k, idx_out);
+        else if (k <= 12) knn_few_kernel<12><<<n_y, KNN_THREADS, 0, st>>>(x, n_x, y, k, idx_out);
+        else if (k <= 16) knn_few_kernel<16><<<n_y, KNN_THREADS, 0, st>>>(x, n_x, y, k, idx_out);
+        else knn_few_kernel<32><<<n_y, KNN_THREADS, 0, st>>>(x, n_x, y, k, idx_out);
+        GENIE_LAUNCH_CHECK();
+        return GENIE_OK;
+    }
     if (k <= 8)
         knn_kernel<8><<<grid, KNN_THREADS, 0, st>>>(x, n_x, y, n_y, k, idx_out);
     else if (k <= 12)

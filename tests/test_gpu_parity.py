@@ -927,9 +927,11 @@ def test_absolute_pos_matches_reference(name, explicit):
 
 # ---- device kNN --------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize('n_x,n_y,k', [(3000, 3000, 16), (500, 4100, 10), (9, 40, 9), (20000, 257, 8), (70, 70, 32)])
+@pytest.mark.parametrize('n_x,n_y,k', [(3000, 3000, 16), (500, 4100, 10), (9, 40, 9), (20000, 257, 8), (70, 70, 32), (50000, 2, 10),
+                                        (300, 2049, 12)])
 def test_device_knn_matches_kdtree(n_x, n_y, k):
-    """genie_knn_fwd against an fp64 k-d tree on the same fp32 points: identical indices, nearest first."""
+    """genie_knn_fwd against an fp64 k-d tree on the same fp32 points: identical indices, nearest first.  Up to 2048 queries
+    take the CTA-per-query kernel, more the thread-per-query kernel."""
     from scipy.spatial import cKDTree
     from genie_b200 import ops
     dev = _dev()
