@@ -108,37 +108,38 @@ constexpr size_t K0_SMEM = (size_t)(K0_W_FLOATS + (K0_THREADS / 32) * K0_WARP_FL
 static_assert(K0_W_FLOATS % 4 == 0 && K0_WARP_FLOATS % 4 == 0, "16-byte alignment of the staging areas");
 
 // acc_u[0..N) += a_u * wrow[0..N) for the thread's two nodes: one shared-memory read per weight chunk
+// (two-wide FFMA2 on adjacent output pairs: the same per-element fused multiply-adds in half the issue slots)
+__device__ __forceinline__ void fma2_pair(float& o0, float& o1, f32x2_t aa, float w0, float w1) {
+    f32x2_t acc = pack2(o0, o1);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(aa), "l"(pack2(w0, w1)));
+    unpack2(acc, o0, o1);
+}
 __device__ __forceinline__ void fma_row30x2(float (&acc)[K0_NPT][30], const float (&a)[K0_NPT], const float* __restrict__ wrow) {
     const float4* w4 = reinterpret_cast<const float4*>(wrow);
+    const f32x2_t aa[K0_NPT] = {pack2(a[0], a[0]), pack2(a[1], a[1])};
 #pragma unroll
     for (int c = 0; c < 7; ++c) {
         const float4 w = w4[c];
 #pragma unroll
         for (int u = 0; u < K0_NPT; ++u) {
-            acc[u][4 * c + 0] = fmaf(a[u], w.x, acc[u][4 * c + 0]);
-            acc[u][4 * c + 1] = fmaf(a[u], w.y, acc[u][4 * c + 1]);
-            acc[u][4 * c + 2] = fmaf(a[u], w.z, acc[u][4 * c + 2]);
-            acc[u][4 * c + 3] = fmaf(a[u], w.w, acc[u][4 * c + 3]);
+            fma2_pair(acc[u][4 * c + 0], acc[u][4 * c + 1], aa[u], w.x, w.y);
+            fma2_pair(acc[u][4 * c + 2], acc[u][4 * c + 3], aa[u], w.z, w.w);
         }
     }
     const float2 w = *reinterpret_cast<const float2*>(wrow + 28);
 #pragma unroll
-    for (int u = 0; u < K0_NPT; ++u) {
-        acc[u][28] = fmaf(a[u], w.x, acc[u][28]);
-        acc[u][29] = fmaf(a[u], w.y, acc[u][29]);
-    }
+    for (int u = 0; u < K0_NPT; ++u) fma2_pair(acc[u][28], acc[u][29], aa[u], w.x, w.y);
 }
 __device__ __forceinline__ void fma_row16x2(float (&acc)[K0_NPT][16], const float (&a)[K0_NPT], const float* __restrict__ wrow) {
     const float4* w4 = reinterpret_cast<const float4*>(wrow);
+    const f32x2_t aa[K0_NPT] = {pack2(a[0], a[0]), pack2(a[1], a[1])};
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         const float4 w = w4[c];
 #pragma unroll
         for (int u = 0; u < K0_NPT; ++u) {
-            acc[u][4 * c + 0] = fmaf(a[u], w.x, acc[u][4 * c + 0]);
-            acc[u][4 * c + 1] = fmaf(a[u], w.y, acc[u][4 * c + 1]);
-            acc[u][4 * c + 2] = fmaf(a[u], w.z, acc[u][4 * c + 2]);
-            acc[u][4 * c + 3] = fmaf(a[u], w.w, acc[u][4 * c + 3]);
+            fma2_pair(acc[u][4 * c + 0], acc[u][4 * c + 1], aa[u], w.x, w.y);
+            fma2_pair(acc[u][4 * c + 2], acc[u][4 * c + 3], aa[u], w.z, w.w);
         }
     }
 }
