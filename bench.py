@@ -411,12 +411,17 @@ def bf16_mode(wl, windows, W, K, use_graph, args):
     torch.cuda.synchronize()
     capi.timing_enable(True)
     capi.timing_collect(reset=True)
+    profile = os.environ.get('GENIE_BENCH_PROFILE') == 'bf16'      # ncu --profile-from-start off: this mode's timed loop only
+    if profile:
+        torch.cuda.profiler.start()
     beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     beg.record()
     for w in windows[W:W + K]:
         wl.window_resident(w)
     end.record()
     torch.cuda.synchronize()
+    if profile:
+        torch.cuda.profiler.stop()
     ms = beg.elapsed_time(end)
     kt = capi.timing_collect(reset=True)
     capi.timing_enable(False)

@@ -20,4 +20,18 @@ GENIE_BENCH_PROFILE=1 timeout 1200 ncu --profile-from-start off --set full \
   --clock-control none --import-source on \
   -k regex:'input_gather|da_init|src_mean|da_layer1_s|da_layer2_s|window_' -c 7 -o gpurun_out/${tag}_prof -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity-check --day-seconds 2000 > gpurun_out/${tag}_ncu_full.log 2>&1
 tail -3 gpurun_out/${tag}_ncu_full.log
+# the same capture of the bf16-storage mode's kernels (bench.py's second mode)
+GENIE_BENCH_PROFILE=bf16 timeout 1200 ncu --profile-from-start off --set full \
+  --metrics sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum,sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_uniform.sum \
+  --clock-control none --import-source on \
+  -k regex:'da_init|src_mean|da_layer1_s|da_layer2_s' -c 5 -o gpurun_out/${tag}_prof_bf16 -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity-check --day-seconds 2000 > gpurun_out/${tag}_ncu_full_bf16.log 2>&1
+tail -3 gpurun_out/${tag}_ncu_full_bf16.log
+# association branch (scripts/probe_assoc.py at 1000 x 5000): one forward_fixed = the front end's two station passes, then
+# assoc_init and the ASSOC instances of the two station-pass kernels
+timeout 900 ncu --set full --metrics sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum \
+  --clock-control none --import-source on -k regex:'assoc_init|da_layer1_s|da_layer2_s' -c 5 \
+  -o gpurun_out/${tag}_prof_assoc -f python scripts/probe_assoc.py c4s > gpurun_out/${tag}_ncu_assoc.log 2>&1
+tail -3 gpurun_out/${tag}_ncu_assoc.log
+timeout 300 python scripts/probe_assoc.py c2 c4 > gpurun_out/${tag}_assoc_probe.log 2>&1
+tail -22 gpurun_out/${tag}_assoc_probe.log
 fi
