@@ -11,6 +11,9 @@ want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread', 'launch__grid_size',
         'sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 'sm__cycles_elapsed.max',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_tensor.sum',
+        'sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_uniform.sum',
+        'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
         'smsp__inst_executed.sum', 'sm__inst_executed_pipe_lsu.sum', 'l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed',
         'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed']
 for r in rows[2:]:

@@ -1,13 +1,14 @@
 """Prints the key roofline / stall metrics of an .ncu-rep (first kernel matching a substring). Dev + profiles/ helper."""
 import csv, subprocess, sys
 rep, pat = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else '')
-out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+# a .csv argument is the output of `ncu -i X.ncu-rep --page raw --csv` (what scripts/gpu_round.sh brings back from the GPU box)
+out = open(rep).read() if rep.endswith('.csv') else subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
 ki = hdr.index('Kernel Name')
-for r in rows[2:]:
-    if pat in r[ki]:
-        break
+nth = int(sys.argv[3]) if len(sys.argv) > 3 else 0      # n-th launch matching the pattern
+hits = [r for r in rows[2:] if pat in r[ki]]
+r = hits[min(nth, len(hits) - 1)]
 want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'dram__throughput.avg.pct_of_peak_sustained_elapsed',
         'lts__t_sector_hit_rate.pct', 'lts__t_bytes.sum', 'l1tex__t_sector_hit_rate.pct', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed.sum', 'smsp__inst_executed.sum', 'sm__warps_active.avg.pct_of_peak_sustained_active',
