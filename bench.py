@@ -276,12 +276,12 @@ class Workload(object):
 class ShardedWorkload(object):
     """One network sharded by grid nodes over all ranks (BASELINE.json configs[4]); same interface as Workload."""
 
-    def __init__(self, name, dev, rank, world, day_s=DAY_S):
+    def __init__(self, name, dev, rank, world, day_s=DAY_S, storage='fp32', exchange='peer'):
         import torch
         from genie_b200 import synth
         from genie_b200.module import GCN_Detection_Network_extended
         from genie_b200.process_utils import InputExtractor, extract_inputs_adjacencies_cartesian
-        from genie_b200.sharded import CudaBackend, GridPartition, ShardedFrontEnd
+        from genie_b200.sharded import CudaBackend, GridPartition, PeerHalo, ShardedFrontEnd
         S, G, k_s, k_g = WORKLOADS[name]
         self.S, self.G, self.dev, self.rank = S, G, dev, rank
         net = synth.Network(S, G, seed=0)
@@ -305,7 +305,12 @@ class ShardedWorkload(object):
         torch.manual_seed(2)
         self.model = GCN_Detection_Network_extended(None, None, scale_rel=SCALE_REL, device=dev).eval()
         be = CudaBackend(self.model, A_sta, part.local_graph(rank), S, self.n_local, self.n_owned, attr, A_src, G, dev)
-        self.fe = ShardedFrontEnd(part, rank, be, dev)
+        if storage == 'bf16':
+            self.model._plan = be.plan
+            self.model.set_storage('bf16')
+        # halo rows: stored into the peers' memory by the layer-1 kernel itself (PeerHalo), or one all_to_all_single per window
+        self.peer_halo = PeerHalo(part, rank, be.plan, S, dev) if (exchange == 'peer' and world > 1) else None
+        self.fe = ShardedFrontEnd(part, rank, be, dev, peer_halo=self.peer_halo)
         self.halo_rows = [len(h) for h in part.halo]
         self.exchange_events = None
         self.max_t = net.max_moveout()
@@ -346,6 +351,17 @@ class ShardedWorkload(object):
             d2h = (y.numel() + x.numel()) * 4
         torch.cuda.current_stream().synchronize()
         return (hi - lo) * 5 * 8, d2h
+
+    def use_collective_exchange(self):
+        """Switch the halo rows back to the NCCL all-to-all (the comparison leg)."""
+        if self.peer_halo is not None:
+            self.fe.peer_halo = None
+            self.fe.backend.plan.set_halo_export(None, None, None, None, None)
+
+    def close(self):
+        if self.peer_halo is not None:
+            self.peer_halo.close()
+            self.peer_halo = None
 
 
 def closure_parity(wl, w, n_clusters=5, cluster=4, tol=1e-4):
@@ -452,48 +468,65 @@ def sharded_leg(args, dev, rank, world, dist, name='c5_2000x200000_sharded'):
     from genie_b200 import capi
     S, G, k_s, k_g = WORKLOADS[name]
     t_a = time.time()
-    wl = ShardedWorkload(name, dev, rank, world, day_s=min(args.day_seconds, 3600.0))
-    if args.sharded_storage == 'bf16':
-        wl.model._plan = wl.fe.backend.plan
-        wl.model.set_storage('bf16')
+    wl = ShardedWorkload(name, dev, rank, world, day_s=min(args.day_seconds, 3600.0), storage=args.sharded_storage,
+                         exchange=args.sharded_exchange)
     torch.cuda.synchronize()
     setup = time.time() - t_a
     K, W = max(2, min(args.steps, 6)), 3
-    for w in range(W):
-        wl.window_resident(w)
-    dist.barrier()
-    torch.cuda.synchronize()
-    wl.exchange_events = []
-    capi.timing_enable(True)
-    capi.timing_collect(reset=True)
-    beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    beg.record()
-    for w in range(W, W + K):
-        wl.window_resident(w)
-    end.record()
-    dist.barrier()
-    torch.cuda.synchronize()
-    ms = beg.elapsed_time(end)
-    kt = capi.timing_collect(reset=True)
-    capi.timing_enable(False)
-    ex_ms = sum(a.elapsed_time(b) for a, b in wl.exchange_events)
-    kern_ms = sum(v[0] for v in kt.values())
-    t = torch.tensor([ms, ex_ms, kern_ms, float(wl.fe.exchange_bytes), float(wl.n_local), float(wl.n_owned)],
-                     dtype=torch.float64, device=dev)
-    tmax = t.clone()
-    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    ms = float(tmax[0])
     peak = _peaks()[0]
+
+    def timed():
+        for w in range(W):
+            wl.window_resident(w)
+        dist.barrier()
+        torch.cuda.synchronize()
+        wl.exchange_events = []
+        capi.timing_enable(True)
+        capi.timing_collect(reset=True)
+        beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        beg.record()
+        for w in range(W, W + K):
+            wl.window_resident(w)
+        end.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = beg.elapsed_time(end)
+        kt = capi.timing_collect(reset=True)
+        capi.timing_enable(False)
+        ex_ms = sum(a.elapsed_time(b) for a, b in wl.exchange_events)
+        wl.exchange_events = None
+        kern_ms = sum(v[0] for v in kt.values())
+        l1_ms = kt.get('da_layer1_s_kernel', (0.0, 0))[0]
+        t = torch.tensor([ms, ex_ms, kern_ms, float(wl.fe.exchange_bytes), float(wl.n_local), float(wl.n_owned), l1_ms],
+                         dtype=torch.float64, device=dev)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms = float(tmax[0])
+        return {'value': K / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms / K,
+                'exchange_bytes_per_step_sum': float(t[3]), 'exchange_ms_per_step_max': float(tmax[1]) / K,
+                'exchange_share_of_step': float(tmax[1]) / ms, 'library_kernels_share_of_step_rank_max': float(tmax[2]) / ms,
+                'layer1_station_pass_ms_per_step_max': float(tmax[6]) / K,
+                'product_nodes_per_s': S * G * K / (ms * 1e-3),
+                'window_roofline_frac': BYTES_PER_NODE_WINDOW * S * G / (ms / K * 1e-3) / 1e9 / (peak * world)}, tmax
+
+    main, tmax = timed()
+    peer = wl.peer_halo is not None
     rep = {'workload': name, 'stations': S, 'grid_nodes': G, 'product_nodes': S * G, 'n_gpus': world, 'steps': K, 'warmup': W,
-           'storage': args.sharded_storage, 'value': K / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms / K, 'scaling': 'strong',
+           'storage': args.sharded_storage, 'scaling': 'strong',
            'halo_grid_nodes_per_rank': wl.halo_rows, 'owned_grid_nodes_max': int(tmax[5]), 'local_grid_nodes_max': int(tmax[4]),
-           'exchange_bytes_per_step_sum': float(t[3]), 'exchange_ms_per_step_max': float(tmax[1]) / K,
-           'exchange_share_of_step': float(tmax[1]) / ms, 'library_kernels_share_of_step_rank_max': float(tmax[2]) / ms,
-           'product_nodes_per_s': S * G * K / (ms * 1e-3),
-           'window_roofline_frac': BYTES_PER_NODE_WINDOW * S * G / (ms / K * 1e-3) / 1e9 / (peak * world),
-           'collectives': 'all_to_all_single (v_b halo rows) + all_gather_into_tensor (read-in rows) per window, NCCL',
+           'exchange': ('peer stores: the layer-1 station pass writes the v_b rows of boundary grid nodes straight into the peers\' '
+                        'landing buffers over NVLink (genie_plan_set_halo_export); exchange_ms = the one-element all-reduce that '
+                        'orders layer 2 after every rank\'s layer 1') if peer else
+                       'all_to_all_single (v_b halo rows), NCCL',
+           'collectives': ('all_reduce of one element (fence) + ' if peer else 'all_to_all_single (v_b halo rows) + ') +
+                          'all_gather_into_tensor (read-in rows) per window, NCCL',
            'setup_s': round(setup, 1)}
+    rep.update(main)
+    if peer:
+        wl.use_collective_exchange()                       # the same windows with the NCCL all-to-all, for comparison
+        rep['with_nccl_all_to_all'] = timed()[0]
+    wl.close()
     del wl
     torch.cuda.empty_cache()
     return rep
@@ -518,7 +551,8 @@ def run_genie(args):
     if sharded:
         if world < 2:
             raise RuntimeError('bench.py: %s is the grid-sharded workload, launch it with --gpus >= 2' % args.workload)
-        wl = ShardedWorkload(args.workload, dev, rank, world, day_s=args.day_seconds)
+        wl = ShardedWorkload(args.workload, dev, rank, world, day_s=args.day_seconds, storage=args.sharded_storage,
+                             exchange=args.sharded_exchange)
         # every rank works on the SAME window (its shard of the grid): fixed total work, strong scaling
         windows = [i % wl.n_windows for i in range(2 * (args.steps + args.warmup))]
         units = 1
@@ -706,6 +740,8 @@ def main():
     ap.add_argument('--no-parity-check', action='store_true')
     ap.add_argument('--no-bf16', action='store_true', help='skip the bf16-storage second mode')
     ap.add_argument('--no-sharded-leg', action='store_true', help='N > 1: skip the grid-sharded C5 leg after the replica legs')
+    ap.add_argument('--sharded-exchange', default='peer', choices=['peer', 'nccl'],
+                    help='halo rows of the sharded leg: peer stores from inside the layer-1 kernel, or an NCCL all-to-all')
     ap.add_argument('--sharded-storage', default='fp32', choices=['fp32', 'bf16'])
     ap.add_argument('--graph', default='auto', choices=['auto', 'on', 'off'], help='replay each window as one CUDA graph')
     args = ap.parse_args()

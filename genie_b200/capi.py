@@ -17,7 +17,8 @@ _LIB_PATH = os.path.join(_HERE, 'libgenie_b200.so')
 _lib = None
 
 GRAPH_CARTESIAN, GRAPH_EXPLICIT = 0, 1
-ABI_VERSION = 7
+ABI_VERSION = 8
+PEER_HANDLE_BYTES = 64         # GENIE_PEER_HANDLE_BYTES
 EDGE_TERM_LD = 48           # GENIE_EDGE_TERM_LD
 STORAGE_FP32, STORAGE_BF16 = 0, 1
 
@@ -102,6 +103,11 @@ SIGNATURES = {
     'genie_plan_destroy': (None, [_P]),
     'genie_plan_workspace_bytes': (ctypes.c_size_t, [_P]),
     'genie_plan_set_storage': (ctypes.c_int, [_P, ctypes.c_int32]),
+    'genie_peer_alloc': (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),
+    'genie_peer_open': (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
+    'genie_peer_close': (ctypes.c_int, [_P]),
+    'genie_peer_free': (ctypes.c_int, [_P]),
+    'genie_plan_set_halo_export': (ctypes.c_int, [_P, _P, _P, _P, _P, _P]),
     'genie_plan_set_edge_terms': (ctypes.c_int, [_P, _P, _P]),
     'genie_plan_set_init_terms': (ctypes.c_int, [_P, _P, _P]),
     'genie_frontend_packed_floats': (ctypes.c_size_t, []),

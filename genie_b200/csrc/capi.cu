@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "internal.h"
+#include <cstring>
 #include "input.cuh"
 
 using namespace gl;
@@ -147,7 +148,7 @@ static int launch_da_layer2(const genie_plan* plan, const float* packed, const W
     int rc;
     if (split_supported(plan) && plan->g.n_sta_tiles <= 32 && edge_attr != nullptr) {
         float* m2 = w.tr0;                                 // layer-0 features are dead: re-use their buffer
-        if ((rc = launch_src_mean(plan, 16, w.vb, m2, nullptr, st, plan->storage))) return rc;
+        if ((rc = launch_src_mean(plan, 16, w.vb, m2, nullptr, st, plan->storage, plan->halo_vb))) return rc;
         return launch_da_layer2_s(plan, packed, w.zc, w.va, m2, mask, edge_attr, latent_out, readin_out ? readin_out : w.r,
                                   readin_out ? ld_r : 16, st);
     }
@@ -555,6 +556,73 @@ int genie_da_layer1_fwd(const genie_plan_t* plan, const float* packed_dev, const
     }
     Workspace w = carve_workspace(plan, workspace_dev);
     return launch_da_layers01(plan, packed_dev, slice_dev, mask_dev, w, static_cast<cudaStream_t>(stream));
+}
+
+// ---- grid sharding: halo rows over peer memory ------------------------------------------------------------------------------
+int genie_peer_alloc(size_t bytes, void** ptr_out, unsigned char* handle_out) {
+    if (!ptr_out || !handle_out || bytes == 0) {
+        set_error("genie_peer_alloc: bad argument");
+        return GENIE_ERR_INVALID;
+    }
+    void* ptr = nullptr;
+    GENIE_CUDA_CHECK(cudaMalloc(&ptr, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+    if (e != cudaSuccess) {
+        cudaFree(ptr);
+        set_error(std::string("genie_peer_alloc: cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+        return GENIE_ERR_CUDA;
+    }
+    static_assert(sizeof(h) == GENIE_PEER_HANDLE_BYTES, "handle size");
+    memcpy(handle_out, &h, sizeof(h));
+    *ptr_out = ptr;
+    return GENIE_OK;
+}
+
+int genie_peer_open(const unsigned char* handle, void** ptr_out) {
+    if (!handle || !ptr_out) {
+        set_error("genie_peer_open: bad argument");
+        return GENIE_ERR_INVALID;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    GENIE_CUDA_CHECK(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return GENIE_OK;
+}
+
+int genie_peer_close(void* ptr) {
+    if (ptr) GENIE_CUDA_CHECK(cudaIpcCloseMemHandle(ptr));
+    return GENIE_OK;
+}
+
+int genie_peer_free(void* ptr) {
+    if (ptr) GENIE_CUDA_CHECK(cudaFree(ptr));
+    return GENIE_OK;
+}
+
+int genie_plan_set_halo_export(genie_plan_t* plan, const int32_t* exp_ptr_dev, const int32_t* exp_peer_dev,
+                               const int32_t* exp_row_dev, float* const* peer_base_dev, const float* halo_vb_dev) {
+    if (!plan) {
+        set_error("genie_plan_set_halo_export: null plan");
+        return GENIE_ERR_INVALID;
+    }
+    if (exp_ptr_dev == nullptr && halo_vb_dev == nullptr) {
+        plan->exp_ptr = plan->exp_peer = plan->exp_row = nullptr;
+        plan->peer_base = nullptr;
+        plan->halo_vb = nullptr;
+        return GENIE_OK;
+    }
+    if (!exp_ptr_dev || !exp_peer_dev || !exp_row_dev || !peer_base_dev || !halo_vb_dev || plan->g.n_grid_owned <= 0 ||
+        !split_supported(plan)) {
+        set_error("genie_plan_set_halo_export: needs all five tables and a CARTESIAN plan with tiling tables and n_grid_owned > 0");
+        return GENIE_ERR_INVALID;
+    }
+    plan->exp_ptr = exp_ptr_dev;
+    plan->exp_peer = exp_peer_dev;
+    plan->exp_row = exp_row_dev;
+    plan->peer_base = peer_base_dev;
+    plan->halo_vb = halo_vb_dev;
+    return GENIE_OK;
 }
 
 int genie_workspace_region(const genie_plan_t* plan, void* workspace_dev, int32_t which, void** ptr_out,

@@ -357,7 +357,9 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                        const int32_t* __restrict__ tile_meta, const uint16_t* __restrict__ tile_nbr,
                        const float* __restrict__ tile_invdeg, int64_t n_tiles, const float* __restrict__ edge_sta,
                        const float* __restrict__ edge_src, const float* __restrict__ tr_own,
-                       const float* __restrict__ mask_out, long long* __restrict__ trace, int trace_tiles, int trace_start) {
+                       const float* __restrict__ mask_out, const int32_t* __restrict__ exp_ptr,
+                       const int32_t* __restrict__ exp_peer, const int32_t* __restrict__ exp_row, float* const* __restrict__ peer_base,
+                       long long* __restrict__ trace, int trace_tiles, int trace_start) {
     static_assert(!(ASSOC && BF16), "the association rows are fp32");
     extern __shared__ __align__(1024) unsigned char smem[];
     using F = Fmt<BF16>;
@@ -868,6 +870,17 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                 tmem_ld_wait();
                 if (BF16 && c) store16_rows_bf16(v, scr, lane, sid2, vb, node0);      // v_b is a gathered tensor: bf16 rows
                 else store16_rows(v, scr, lane, sid, c ? vb : va, node0, LD_V);
+                if (c && exp_ptr != nullptr) {
+                    // grid-sharded plan: the v_b rows of a grid node that peers hold as halo also go straight into the peers'
+                    // landing buffers (peer stores over NVLink; the transfer rides on this kernel instead of an all-to-all)
+                    const int eb = __ldg(exp_ptr + g), ee = __ldg(exp_ptr + g + 1);
+                    for (int e = eb; e < ee; ++e) {
+                        float* pb = peer_base[__ldg(exp_peer + e)];
+                        const int64_t rnode0 = (int64_t)__ldg(exp_row + e) * S;
+                        if (BF16) store16_rows_bf16(v, scr, lane, sid2, pb, rnode0);
+                        else store16_rows(v, scr, lane, sid, pb, rnode0, LD_V);
+                    }
+                }
             }
             tc_fence_before_sync();
             mbar_arrive(&bars->d_free[q]);
@@ -914,7 +927,7 @@ void set_s1_trace(long long* buf, int tiles) {
 
 static int launch_s1(const genie_plan* p, bool assoc, const float* blob, const float* pfeat, const float* msrc, const float* mask,
                      float* zc, float* va, float* vb, const float* edge_sta, const float* edge_src, const float* tr_own,
-                     const float* mask_out, cudaStream_t st) {
+                     const float* mask_out, bool export_halo, cudaStream_t st) {
     const genie_graph_desc_t& g = p->g;
     const int64_t n_tiles = (int64_t)g.n_sta_tiles * (g.n_grid_owned > 0 ? g.n_grid_owned : g.n_grid);
     static PerDeviceOnce attr_set;
@@ -934,7 +947,8 @@ static int launch_s1(const genie_plan* p, bool assoc, const float* blob, const f
     if (edge == E && bf == B && assoc == A)                                                                                     \
         da_layer1_s_kernel<E, B, A><<<(unsigned)grid, S1_THREADS, Fmt<B>::SM_TOTAL, st>>>(                                      \
             blob, pfeat, msrc, mask, zc, va, vb, g.n_sta, g.n_sta_tiles, g.sta_tile_rows, g.sta_tile_meta, g.sta_tile_nbr,      \
-            g.sta_tile_invdeg, n_tiles, edge_sta, edge_src, tr_own, mask_out, g_s1_trace, g_s1_trace_tiles, g_s1_trace_start);
+            g.sta_tile_invdeg, n_tiles, edge_sta, edge_src, tr_own, mask_out, export_halo ? p->exp_ptr : nullptr, p->exp_peer,      \
+            p->exp_row, p->peer_base, g_s1_trace, g_s1_trace_tiles, g_s1_trace_start);
     GENIE_S1_LAUNCH(false, false, false) GENIE_S1_LAUNCH(true, false, false) GENIE_S1_LAUNCH(false, true, false)
     GENIE_S1_LAUNCH(true, true, false) GENIE_S1_LAUNCH(false, false, true) GENIE_S1_LAUNCH(true, false, true)
 #undef GENIE_S1_LAUNCH
@@ -944,12 +958,12 @@ static int launch_s1(const genie_plan* p, bool assoc, const float* blob, const f
 
 int launch_da_layer1_s(const genie_plan* p, const float* packed, const float* pfeat, const float* msrc,
                        const float* mask, float* zc, float* va, float* vb, cudaStream_t st) {
-    return launch_s1(p, false, packed + T2_BASE, pfeat, msrc, mask, zc, va, vb, p->edge_sta, p->edge_src, nullptr, nullptr, st);
+    return launch_s1(p, false, packed + T2_BASE, pfeat, msrc, mask, zc, va, vb, p->edge_sta, p->edge_src, nullptr, nullptr, true, st);
 }
 
 // Layer 1 of the association phase on a plan with tiling tables.  blob: T2_FLOATS + 96 floats built by launch_assoc_pack_t2;
 // a1 = PReLU(l1_t1_1 tr) rows, msrc = mean over source neighbours of PReLU(l1_t2_1 tr), mask [P,4], mask_out [G].
 int launch_assoc_layer1_s(const genie_plan* p, const float* blob, const float* tr, const float* a1, const float* msrc,
                           const float* mask, const float* mask_out, float* zc, float* va, float* vb, cudaStream_t st) {
-    return launch_s1(p, true, blob, a1, msrc, mask, zc, va, vb, p->assoc_edge_sta, p->assoc_edge_src, tr, mask_out, st);
+    return launch_s1(p, true, blob, a1, msrc, mask, zc, va, vb, p->assoc_edge_sta, p->assoc_edge_src, tr, mask_out, false, st);
 }

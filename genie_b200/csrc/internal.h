@@ -31,6 +31,14 @@ struct genie_plan {
     const float* assoc_init_src;
     const float* assoc_edge_sta;
     const float* assoc_edge_src;
+    // Grid-sharded plans (genie_plan_set_halo_export): the layer-1 station pass stores the layer-2 message rows v_b of the owned
+    // grid nodes that peers hold as halo straight into the peers' landing buffers (NVLink peer stores), and the layer-2 source
+    // pass reads this rank's halo rows from its own landing buffer.  NULL = off.
+    const int32_t* exp_ptr;    // [n_grid_owned + 1] CSR over the owned grid nodes
+    const int32_t* exp_peer;   // [n_exports] peer slot of every export
+    const int32_t* exp_row;    // [n_exports] row (halo position) of the node in that peer's landing buffer
+    float* const* peer_base;   // [n_peers] device array of the peers' landing-buffer base addresses
+    const float* halo_vb;      // this rank's landing buffer: [n_grid - n_grid_owned][S][16 fp32 | 16 bf16]
 };
 
 // Device-side view of the product graph.  CARTESIAN: node i = g*S + s; sta neighbours g*S + col, src neighbours
@@ -187,8 +195,9 @@ int launch_spatial_aggregation(const genie_plan* p, const float* packed, int lay
 // split source-pass / station-pass kernels (plans with tiling tables; src_mean_kernels.cu, da_s1_kernel.cu, da_s2_kernel.cu)
 bool split_supported(const genie_plan* p);
 // out[g,s,:] = mean_{g' in N_src(g)} X[g',s,:], rows of `width` floats (32 or 16); gate: optional device flag, 0 = skip
+// halo != NULL: rows of grid nodes >= n_grid_owned are read from `halo` (row 0 = node n_grid_owned) instead of X
 int launch_src_mean(const genie_plan* p, int width, const float* X, float* out, const float* gate, cudaStream_t st,
-                    int storage = GENIE_STORAGE_FP32);
+                    int storage = GENIE_STORAGE_FP32, const float* halo = nullptr);
 int launch_da_layer1_s(const genie_plan* p, const float* packed, const float* pfeat, const float* msrc,
                        const float* mask, float* zc, float* va, float* vb, cudaStream_t st);
 void set_s1_trace(long long* buf, int tiles);

@@ -14,6 +14,7 @@
 // into L1 while the stragglers finish.
 #include "bf16.cuh"
 #include "common.cuh"
+#include <climits>
 
 using namespace gl;
 
@@ -26,13 +27,16 @@ template <int W, int SB>
 __global__ void __launch_bounds__(SM_THREADS, 1)
     src_mean_kernel(const float* __restrict__ X, float* __restrict__ out, int S, const int64_t* __restrict__ rowptr,
                     const int32_t* __restrict__ col, const int32_t* __restrict__ grp_ptr,
-                    const int32_t* __restrict__ grp_nodes, int n_groups, int n_slabs, const float* __restrict__ gate) {
+                    const int32_t* __restrict__ grp_nodes, int n_groups, int n_slabs, const float* __restrict__ gate,
+                    const float* __restrict__ halo, int n_owned) {
     if (gate != nullptr && *gate == 0.f) return;     // the one-pass kernels run instead (layout.h TCS_OK)
     constexpr int LPR = W / 4;                       // lanes (16-byte chunks) per row
     constexpr int PAIRS = SB / 2;                    // every lane sums the same chunk of TWO stations (s and s + PAIRS)
     const float4* __restrict__ X4 = reinterpret_cast<const float4*>(X);
     float4* __restrict__ O4 = reinterpret_cast<float4*>(out);
     const uint32_t gstride = (uint32_t)S * LPR;      // float4 units between consecutive grid nodes (P * LPR < 2^32 checked)
+    // grid-sharded plans: rows of halo grid nodes (ids >= n_owned; n_owned = INT_MAX otherwise) live in the landing buffer
+    const float4* __restrict__ H4 = reinterpret_cast<const float4*>(halo);
     const int64_t n_tiles = (int64_t)n_groups * n_slabs;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int slab = (int)(t / n_groups);
@@ -60,9 +64,11 @@ __global__ void __launch_bounds__(SM_THREADS, 1)
                 float4 v0[5], v1[5];
 #pragma unroll
                 for (int u = 0; u < 5; ++u) {
-                    const uint32_t base = (uint32_t)__ldg(cp + j + u) * gstride;
-                    v0[u] = __ldg(X4 + (base + off));
-                    v1[u] = __ldg(X4 + (base + off2));
+                    const int cj = __ldg(cp + j + u);
+                    const float4* __restrict__ B = cj >= n_owned ? H4 : X4;
+                    const uint32_t base = (uint32_t)(cj >= n_owned ? cj - n_owned : cj) * gstride;
+                    v0[u] = __ldg(B + (base + off));
+                    v1[u] = __ldg(B + (base + off2));
                 }
 #pragma unroll
                 for (int u = 0; u < 5; ++u) {
@@ -71,8 +77,10 @@ __global__ void __launch_bounds__(SM_THREADS, 1)
                 }
             }
             for (; j < deg; ++j) {
-                const uint32_t base = (uint32_t)__ldg(cp + j) * gstride;
-                const float4 v0 = __ldg(X4 + (base + off)), v1 = __ldg(X4 + (base + off2));
+                const int cj = __ldg(cp + j);
+                const float4* __restrict__ B = cj >= n_owned ? H4 : X4;
+                const uint32_t base = (uint32_t)(cj >= n_owned ? cj - n_owned : cj) * gstride;
+                const float4 v0 = __ldg(B + (base + off)), v1 = __ldg(B + (base + off2));
                 a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
                 a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
             }
@@ -90,7 +98,8 @@ template <int W, int SB>
 __global__ void __launch_bounds__(SM_THREADS, 1)
     src_mean_bf16_kernel(const uint4* __restrict__ X4, uint4* __restrict__ O4, int S, const int64_t* __restrict__ rowptr,
                          const int32_t* __restrict__ col, const int32_t* __restrict__ grp_ptr,
-                         const int32_t* __restrict__ grp_nodes, int n_groups, int n_slabs, const float* __restrict__ gate) {
+                         const int32_t* __restrict__ grp_nodes, int n_groups, int n_slabs, const float* __restrict__ gate,
+                         const uint4* __restrict__ H4, int n_owned) {
     if (gate != nullptr && *gate == 0.f) return;
     constexpr int LPR = W / 8;                       // lanes (16-byte chunks) per row
     constexpr int PAIRS = SB / 2;
@@ -124,9 +133,11 @@ __global__ void __launch_bounds__(SM_THREADS, 1)
                 uint4 v0[3], v1[3];
 #pragma unroll
                 for (int u = 0; u < 3; ++u) {
-                    const uint32_t base = (uint32_t)__ldg(cp + j + u) * gstride;
-                    v0[u] = __ldg(X4 + (base + off));
-                    v1[u] = __ldg(X4 + (base + off2));
+                    const int cj = __ldg(cp + j + u);
+                    const uint4* __restrict__ B = cj >= n_owned ? H4 : X4;
+                    const uint32_t base = (uint32_t)(cj >= n_owned ? cj - n_owned : cj) * gstride;
+                    v0[u] = __ldg(B + (base + off));
+                    v1[u] = __ldg(B + (base + off2));
                 }
 #pragma unroll
                 for (int u = 0; u < 3; ++u) {
@@ -140,12 +151,14 @@ __global__ void __launch_bounds__(SM_THREADS, 1)
                 }
             }
             for (; j < deg; ++j) {
-                const uint32_t base = (uint32_t)__ldg(cp + j) * gstride;
+                const int cj = __ldg(cp + j);
+                const uint4* __restrict__ B = cj >= n_owned ? H4 : X4;
+                const uint32_t base = (uint32_t)(cj >= n_owned ? cj - n_owned : cj) * gstride;
                 float f[8];
-                bf16_unpack8(__ldg(X4 + (base + off)), f);
+                bf16_unpack8(__ldg(B + (base + off)), f);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) a0[e] += f[e];
-                bf16_unpack8(__ldg(X4 + (base + off2)), f);
+                bf16_unpack8(__ldg(B + (base + off2)), f);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) a1[e] += f[e];
             }
@@ -172,41 +185,45 @@ bool split_supported(const genie_plan* p) {
 }
 
 template <int W, int SB>
-static void launch_src_mean_t(const genie_plan* p, const float* X, float* out, const float* gate, cudaStream_t st) {
+static void launch_src_mean_t(const genie_plan* p, const float* X, float* out, const float* gate, cudaStream_t st,
+                              const float* halo) {
     const genie_graph_desc_t& g = p->g;
     const int n_slabs = (g.n_sta + SB - 1) / SB;
     const int64_t n_tiles = (int64_t)g.n_grid_groups * n_slabs;
     const unsigned grid = (unsigned)(n_tiles < p->sm_count ? n_tiles : p->sm_count);
     src_mean_kernel<W, SB><<<grid, SM_THREADS, 0, st>>>(X, out, g.n_sta, g.src_rowptr, g.src_col, g.grid_grp_ptr,
-                                                        g.grid_grp_nodes, g.n_grid_groups, n_slabs, gate);
+                                                        g.grid_grp_nodes, g.n_grid_groups, n_slabs, gate, halo,
+                                                        halo ? g.n_grid_owned : INT_MAX);
 }
 
 template <int W, int SB>
-static void launch_src_mean_bf16_t(const genie_plan* p, const float* X, float* out, const float* gate, cudaStream_t st) {
+static void launch_src_mean_bf16_t(const genie_plan* p, const float* X, float* out, const float* gate, cudaStream_t st,
+                                   const float* halo) {
     const genie_graph_desc_t& g = p->g;
     const int n_slabs = (g.n_sta + SB - 1) / SB;
     const int64_t n_tiles = (int64_t)g.n_grid_groups * n_slabs;
     const unsigned grid = (unsigned)(n_tiles < p->sm_count ? n_tiles : p->sm_count);
     src_mean_bf16_kernel<W, SB><<<grid, SM_THREADS, 0, st>>>(reinterpret_cast<const uint4*>(X), reinterpret_cast<uint4*>(out),
                                                              g.n_sta, g.src_rowptr, g.src_col, g.grid_grp_ptr, g.grid_grp_nodes,
-                                                             g.n_grid_groups, n_slabs, gate);
+                                                             g.n_grid_groups, n_slabs, gate, reinterpret_cast<const uint4*>(halo),
+                                                             halo ? g.n_grid_owned : INT_MAX);
 }
 
 // X / out: fp32 rows, or (storage == GENIE_STORAGE_BF16) bf16 rows of the same channel count
 int launch_src_mean(const genie_plan* p, int width, const float* X, float* out, const float* gate, cudaStream_t st,
-                    int storage) {
+                    int storage, const float* halo) {
     // One slab = 8 stations of every neighbour row (1024 B of 128-byte rows, 512 B of 64-byte rows): measured best on B200
     // together with groups of 256 grid nodes (sweeps of 64..4096 nodes x 256..2048 bytes, gpurun r1zd-r1zf: 5.2 -> 3.9 ms and
     // 3.6 -> 3.3 ms at C4).  bf16 rows: 16 / 32 stations, the same bytes per slab.
     const bool bf = storage == GENIE_STORAGE_BF16;
     if (width == 32) {
         TimedLaunch tl(KID_SRC_MEAN32, st);
-        if (bf) launch_src_mean_bf16_t<32, 16>(p, X, out, gate, st);
-        else launch_src_mean_t<32, 8>(p, X, out, gate, st);
+        if (bf) launch_src_mean_bf16_t<32, 16>(p, X, out, gate, st, halo);
+        else launch_src_mean_t<32, 8>(p, X, out, gate, st, halo);
     } else if (width == 16) {
         TimedLaunch tl(KID_SRC_MEAN16, st);
-        if (bf) launch_src_mean_bf16_t<16, 16>(p, X, out, gate, st);
-        else launch_src_mean_t<16, 8>(p, X, out, gate, st);
+        if (bf) launch_src_mean_bf16_t<16, 16>(p, X, out, gate, st, halo);
+        else launch_src_mean_t<16, 8>(p, X, out, gate, st, halo);
     } else {
         set_error("launch_src_mean: unsupported row width");
         return GENIE_ERR_INVALID;

@@ -283,6 +283,21 @@ class GraphPlan(object):
             self.workspace_bytes = int(capi.load().genie_plan_workspace_bytes(self.handle))
             self._workspace = None
 
+    def set_halo_export(self, exp_ptr, exp_peer, exp_row, peer_base, halo_ptr):
+        """genie_plan_set_halo_export (grid sharding): int32 device tensors of the export CSR, an int64 device tensor of the
+        peers' landing-buffer addresses and the address of this rank's landing buffer; all None switches the export off."""
+        if exp_ptr is None:
+            capi.check(capi.load().genie_plan_set_halo_export(self.handle, None, None, None, None, None))
+            self._halo_export = None
+            return
+        if exp_ptr.numel() != self.n_grid_owned + 1 or exp_peer.numel() != exp_row.numel():
+            raise capi.GenieError('halo export tables do not match the plan')
+        capi.check(capi.load().genie_plan_set_halo_export(
+            self.handle, capi.dptr(exp_ptr, torch.int32, 'exp_ptr'), capi.dptr(exp_peer, torch.int32, 'exp_peer'),
+            capi.dptr(exp_row, torch.int32, 'exp_row'), capi.dptr(peer_base, torch.int64, 'peer_base'),
+            ctypes.c_void_p(int(halo_ptr))))
+        self._halo_export = (exp_ptr, exp_peer, exp_row, peer_base)      # keep the tensors alive
+
     def set_edge_terms(self, t_sta, t_src):
         """genie_plan_set_edge_terms: per-node additive terms of the edge-feature model ([n, 48] fp32 each), or None, None."""
         if t_sta is None:

@@ -14,6 +14,9 @@ exceed one GPU (2000 stations x 200000 grid nodes = 4e8 product nodes) the grid 
     3. layer 2 + Bipartite_ReadIn for the owned nodes (a grid node's stations all live on its rank, so the sum over stations
        never crosses shards: no all-reduce of station partials is needed in this layout),
     4. all-gather of the `[G,15]` read-in rows; SpatialAggregation x3 (0.1 % of the work) runs replicated on every rank.
+  With `PeerHalo` (the product path on several GPUs) step 2 is no collective at all: every rank's layer-1 station pass stores
+  the rows its peers need straight into the peers' landing buffers while it produces them (peer stores over NVLink,
+  genie_plan_set_halo_export), and a one-element all-reduce orders "all layer-1 passes done" before layer 2.
 The compute steps go through a backend object; the product backend is `CudaBackend` (C-ABI kernels).  Tests substitute a CPU
 backend to check the partition / exchange logic with world_size 2 over gloo.
 """
@@ -76,6 +79,83 @@ class GridPartition(object):
         return np.concatenate(send), send_counts, recv_counts
 
 
+class PeerHalo(object):
+    """Halo rows over peer memory: landing buffers (genie_peer_alloc), their handles exchanged over the process group, the
+    peers' buffers mapped (genie_peer_open) and the export tables of this rank installed on its plan.  Works for ranks on
+    different GPUs of one node and for ranks sharing a GPU (the tests)."""
+
+    def __init__(self, partition, rank, plan, n_sta, device, group=None):
+        import ctypes
+        from . import capi
+        lib = capi.load()
+        self.lib, self.device, self.group = lib, torch.device(device), group
+        world = partition.world
+        n_halo = len(partition.halo[rank])
+        row_bytes = n_sta * 16 * (2 if plan.storage == 'bf16' else 4)
+        self.bytes = max(n_halo, 1) * row_bytes
+        with torch.cuda.device(self.device):
+            ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(capi.PEER_HANDLE_BYTES)
+            capi.check(lib.genie_peer_alloc(self.bytes, ctypes.byref(ptr), handle))
+            self.local_ptr = ptr.value
+            handles = [None] * world
+            dist.all_gather_object(handles, handle.raw, group=group)
+            self.peer_ptrs = []
+            for q in range(world):
+                if q == rank:
+                    self.peer_ptrs.append(self.local_ptr)
+                    continue
+                pq = ctypes.c_void_p()
+                capi.check(lib.genie_peer_open(handles[q], ctypes.byref(pq)))
+                self.peer_ptrs.append(pq.value)
+        ptr_, peer, row = self.export_tables(partition, rank)
+        dev = self.device
+        self.exp_ptr = torch.from_numpy(ptr_).to(dev)
+        self.exp_peer = torch.from_numpy(peer).to(dev)
+        self.exp_row = torch.from_numpy(row).to(dev)
+        self.peer_base = torch.tensor(self.peer_ptrs, dtype=torch.int64, device=dev)
+        self.export_bytes = int(len(row)) * row_bytes                # bytes this rank stores into peer memory per window
+        plan.set_halo_export(self.exp_ptr, self.exp_peer, self.exp_row, self.peer_base, self.local_ptr)
+        self.plan, self.rank = plan, rank
+        self._flag = torch.zeros(1, device=dev)
+
+    @staticmethod
+    def export_tables(partition, rank):
+        """Export CSR over the owned nodes of `rank` (int32 arrays): exp_ptr [n_owned + 1], and per export the peer rank and
+        the position of the node in that peer's halo list (= row of its landing buffer)."""
+        own = partition.owned[rank]
+        g2l = -np.ones(partition.n_grid, dtype=np.int64)
+        g2l[own] = np.arange(len(own))
+        loc, peer, row = [], [], []
+        for q in range(partition.world):
+            if q == rank:
+                continue
+            pos = np.nonzero(partition.owner[partition.halo[q]] == rank)[0]
+            loc.append(g2l[partition.halo[q][pos]])
+            peer.append(np.full(len(pos), q, dtype=np.int64))
+            row.append(pos)
+        loc, peer, row = (np.concatenate(a) if a else np.zeros(0, np.int64) for a in (loc, peer, row))
+        order = np.argsort(loc, kind='stable')
+        counts = np.zeros(len(own) + 1, dtype=np.int64)
+        np.add.at(counts, loc + 1, 1)
+        return np.cumsum(counts).astype(np.int32), peer[order].astype(np.int32), row[order].astype(np.int32)
+
+    def fence(self):
+        """Stream-ordered: returns (on the stream) once every rank's work enqueued before its own fence has completed."""
+        dist.all_reduce(self._flag, group=self.group)
+
+    def close(self):
+        if self.plan is not None:
+            self.plan.set_halo_export(None, None, None, None, None)
+            with torch.cuda.device(self.device):
+                torch.cuda.synchronize()
+                dist.barrier(group=self.group)                      # nobody still stores into a buffer that is about to go
+                for q, p in enumerate(self.peer_ptrs):
+                    if q != self.rank:
+                        self.lib.genie_peer_close(p)
+                self.lib.genie_peer_free(self.local_ptr)
+            self.plan = None
+
+
 class CudaBackend(object):
     """The product compute path: libgenie_b200 kernels on the local plan (see include/genie_b200.h)."""
 
@@ -113,8 +193,11 @@ class CudaBackend(object):
 class ShardedFrontEnd(object):
     """DataAggregation -> Bipartite_ReadIn -> SpatialAggregation x3 with the grid nodes sharded over the process group."""
 
-    def __init__(self, partition, rank, backend, device, group=None):
+    def __init__(self, partition, rank, backend, device, group=None, peer_halo=None):
+        """peer_halo: a PeerHalo installed on the backend's plan — the halo rows then travel inside the layer-1 kernel and
+        `forward` only fences; None: one all_to_all_single per window."""
         self.part, self.rank, self.backend, self.group = partition, int(rank), backend, group
+        self.peer_halo = peer_halo
         self.device = torch.device(device)
         self.n_owned = len(partition.owned[rank])
         send_rows, self.send_counts, self.recv_counts = partition.exchange_lists(rank)
@@ -148,7 +231,11 @@ class ShardedFrontEnd(object):
         if events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        self.exchange_bytes = self.exchange(be.message_rows())
+        if self.peer_halo is not None:
+            self.peer_halo.fence()
+            self.exchange_bytes = self.peer_halo.export_bytes
+        else:
+            self.exchange_bytes = self.exchange(be.message_rows())
         if events is not None:
             e1.record()
             events.append((e0, e1))

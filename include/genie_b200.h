@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GENIE_B200_ABI_VERSION 7
+#define GENIE_B200_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define GENIE_API __attribute__((visibility("default")))
@@ -164,6 +164,33 @@ typedef struct genie_frontend_weights {
 #define GENIE_STORAGE_FP32 0
 #define GENIE_STORAGE_BF16 1
 GENIE_API int genie_plan_set_storage(genie_plan_t* plan, int32_t storage);
+
+/* ---- grid sharding over the GPUs of one node: halo rows over peer memory ----------------------------------------------
+ * The reference runs on one device (module.py:2) and has no counterpart.  On a grid-sharded plan (n_grid_owned > 0: the local
+ * grid = owned grid nodes followed by the 1-hop halo of their source-graph in-neighbours) layer 2 of DataAggregation
+ * (module.py:95: propagate(A_in_src, ...)) needs the layer-2 message rows v_b of the halo nodes, which their owners compute.
+ * Instead of a collective after the kernel, the layer-1 station pass of the OWNER stores those rows straight into the peers'
+ * landing buffers while it produces them (peer stores over NVLink / NVSwitch), tile by tile:
+ *   genie_peer_alloc   cudaMalloc of a landing buffer + its inter-process handle (GENIE_PEER_HANDLE_BYTES bytes, to be passed
+ *                      to the other ranks by any host channel); genie_peer_free releases it
+ *   genie_peer_open    maps a peer's buffer from its handle (lazy peer access); genie_peer_close unmaps it
+ *   genie_plan_set_halo_export
+ *       exp_ptr_dev   int32 [n_grid_owned + 1]  CSR over the owned grid nodes: exports of node g are [exp_ptr[g], exp_ptr[g+1])
+ *       exp_peer_dev  int32 [n_exports]         index into peer_base_dev
+ *       exp_row_dev   int32 [n_exports]         position of the node in that peer's halo list (row of its landing buffer)
+ *       peer_base_dev float* [n_peers]          DEVICE array of the mapped base addresses of the peers' landing buffers
+ *       halo_vb_dev   this rank's landing buffer, [n_grid - n_grid_owned][n_sta][16] fp32 (bf16 storage: 16 x 2 bytes): the
+ *                     layer-2 source pass reads the rows of halo grid nodes from it
+ *   All NULL switches the export off.  The caller orders "every peer has finished its layer-1 pass" before layer 2 (any
+ *   stream-ordered barrier, e.g. a one-element all-reduce) and "every peer has finished its layer-2 source pass" before the
+ *   next window's layer 1 (the all-gather of the read-in rows does it). */
+#define GENIE_PEER_HANDLE_BYTES 64
+GENIE_API int genie_peer_alloc(size_t bytes, void** ptr_out, unsigned char* handle_out);
+GENIE_API int genie_peer_open(const unsigned char* handle, void** ptr_out);
+GENIE_API int genie_peer_close(void* ptr);
+GENIE_API int genie_peer_free(void* ptr);
+GENIE_API int genie_plan_set_halo_export(genie_plan_t* plan, const int32_t* exp_ptr_dev, const int32_t* exp_peer_dev,
+                                         const int32_t* exp_row_dev, float* const* peer_base_dev, const float* halo_vb_dev);
 
 /* Number of floats of the packed (kernel-layout) weight buffer. */
 GENIE_API size_t genie_frontend_packed_floats(void);

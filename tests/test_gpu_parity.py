@@ -738,6 +738,80 @@ def test_sharded_front_end_single_process():
     assert rel_err(xs.cpu().numpy(), want_xs.cpu().numpy()) < 1e-5
 
 
+class _RawDeviceBytes(object):
+    """Zero-copy uint8 view of raw device memory for torch.as_tensor."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {'shape': (nbytes,), 'typestr': '|u1', 'data': (int(ptr), False), 'version': 2}
+
+
+@pytest.mark.parametrize('storage', ['fp32', 'bf16'])
+def test_sharded_halo_rows_over_peer_stores(storage):
+    """genie_plan_set_halo_export: the layer-1 station pass of every rank stores the v_b rows its peers hold as halo straight
+    into the peers' landing buffers (genie_peer_alloc), the layer-2 source pass reads them from there.  Three ranks emulated in
+    one process on one GPU (the peers' buffers are then plain device pointers); the landing buffers must equal the owners' rows
+    bit for bit and the read-in rows the unsharded front end's."""
+    import ctypes
+    from genie_b200 import capi, ops
+    from genie_b200.plan import GraphPlan
+    from genie_b200.sharded import CudaBackend, GridPartition, PeerHalo
+    from oracle import genie_oracle as go
+    dev = _dev()
+    S, G, world = 160, 900, 3
+    net, A_sta, A_src, Slice, Mask, attr = _random_case(S, G, 15, 15, 43, dev)
+    sd = go.init_state(seed=7)
+    from genie_b200.module import GCN_Detection_Network_extended
+    m = GCN_Detection_Network_extended(None, None, device=dev)
+    m.load_state_dict(sd, strict=False)
+    grid = torch.from_numpy(net.grid).float().to(dev)
+    plan = GraphPlan.cartesian(A_sta, A_src, S, G, device=dev)
+    plan.set_storage(storage)
+    want_r = ops.frontend_fwd(plan, m._packed_weights(dev), Slice.to(dev), Mask.to(dev), attr.to(dev), grid, 30000.0,
+                              want_readin=True)[2].clone()
+    part = GridPartition(A_src, G, world)
+    lib = capi.load()
+    row_bytes = S * 16 * (2 if storage == 'bf16' else 4)
+    bes, bufs, keep = [], [], []
+    for r in range(world):
+        nd = torch.from_numpy(part.local_nodes(r))
+        loc = lambda x: x.view(G, S, -1).index_select(0, nd).reshape(len(nd) * S, -1).contiguous().to(dev)
+        be = CudaBackend(m, A_sta, part.local_graph(r), S, len(nd), len(part.owned[r]), loc(attr), A_src, G, dev)
+        be.plan.set_storage(storage)
+        ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(capi.PEER_HANDLE_BYTES)
+        capi.check(lib.genie_peer_alloc(max(len(part.halo[r]), 1) * row_bytes, ctypes.byref(ptr), handle))
+        bes.append((be, loc(Slice), loc(Mask)))
+        bufs.append(ptr.value)
+    try:
+        peer_base = torch.tensor(bufs, dtype=torch.int64, device=dev)
+        for r in range(world):
+            ep, eq, er = (torch.from_numpy(a).to(dev) for a in PeerHalo.export_tables(part, r))
+            assert int(ep[-1]) == eq.numel() and eq.numel() > 0
+            bes[r][0].plan.set_halo_export(ep, eq, er, peer_base, bufs[r])
+        for be, sl, mk in bes:                               # every rank's layer 1 (fills the peers' landing buffers) ...
+            be.layer1(sl, mk)
+        torch.cuda.synchronize()
+        # ... the landing buffer of rank r = the owners' rows of its halo nodes
+        rows = [be.message_rows() for be, _, _ in bes]
+        for r in range(world):
+            n_halo = len(part.halo[r])
+            got = torch.as_tensor(_RawDeviceBytes(bufs[r], n_halo * row_bytes), device=dev).view(rows[r].dtype).view(n_halo, -1)
+            for i, g in enumerate(part.halo[r].tolist()):
+                q = int(part.owner[g])
+                j = int(np.nonzero(part.owned[q] == g)[0][0])
+                assert torch.equal(got[i], rows[q][j]), (r, i, g)
+            rows[r][len(part.owned[r]):] = float('nan') if storage == 'fp32' else 0xff    # the local halo rows are NOT used
+        read_in = torch.empty((G, 15), device=dev)
+        for r in range(world):
+            read_in[torch.from_numpy(part.owned[r]).to(dev)] = bes[r][0].layer2_readin()
+        assert rel_err(read_in.cpu().numpy(), want_r.cpu().numpy()) < (1e-5 if storage == 'fp32' else 2e-3)
+        assert torch.isfinite(read_in).all()
+    finally:
+        torch.cuda.synchronize()
+        for r in range(world):
+            bes[r][0].plan.set_halo_export(None, None, None, None, None)
+            lib.genie_peer_free(ctypes.c_void_p(bufs[r]))
+
+
 # ---- association branch (SURVEY.md §8f rank 2): forward_fixed / forward ------------------------------------------------------
 
 ASSOC = ['assoc_10x100', 'assoc_18of20x160']
