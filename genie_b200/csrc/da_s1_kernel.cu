@@ -349,7 +349,7 @@ __device__ __forceinline__ float4 s1_own_operands(const unsigned char* sb, int r
     return mk;
 }
 
-template <bool EDGE, bool BF16, bool ASSOC>
+template <bool EDGE, bool BF16, bool ASSOC, bool EXPORT>
 __global__ void __launch_bounds__(S1_THREADS, 1)
     da_layer1_s_kernel(const float* __restrict__ tcw, const float* __restrict__ p, const float* __restrict__ msrc,
                        const float* __restrict__ mask, float* __restrict__ zc, float* __restrict__ va,
@@ -769,6 +769,12 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                     sid2[j] = (BF16 && rw < n_own) ? __ldg(tile_rows + (int64_t)T * ROWS + rw) : -1;
                 }
             }
+            // grid-sharded plan: the export range of this tile's grid node (fetched here, long before the stage-D epilogue uses it)
+            int exp_b = 0, exp_e = 0;
+            if (EXPORT) {
+                exp_b = __ldg(exp_ptr + g);
+                exp_e = __ldg(exp_ptr + g + 1);
+            }
             // edge-feature model (genie_plan_set_edge_terms): rows of the additive terms of this thread's station / grid node
             const float* et_sta = nullptr;
             const float* et_src = nullptr;
@@ -870,11 +876,10 @@ __global__ void __launch_bounds__(S1_THREADS, 1)
                 tmem_ld_wait();
                 if (BF16 && c) store16_rows_bf16(v, scr, lane, sid2, vb, node0);      // v_b is a gathered tensor: bf16 rows
                 else store16_rows(v, scr, lane, sid, c ? vb : va, node0, LD_V);
-                if (c && exp_ptr != nullptr) {
+                if (EXPORT && c) {
                     // grid-sharded plan: the v_b rows of a grid node that peers hold as halo also go straight into the peers'
                     // landing buffers (peer stores over NVLink; the transfer rides on this kernel instead of an all-to-all)
-                    const int eb = __ldg(exp_ptr + g), ee = __ldg(exp_ptr + g + 1);
-                    for (int e = eb; e < ee; ++e) {
+                    for (int e = exp_b; e < exp_e; ++e) {
                         float* pb = peer_base[__ldg(exp_peer + e)];
                         const int64_t rnode0 = (int64_t)__ldg(exp_row + e) * S;
                         if (BF16) store16_rows_bf16(v, scr, lane, sid2, pb, rnode0);
@@ -932,25 +937,30 @@ static int launch_s1(const genie_plan* p, bool assoc, const float* blob, const f
     const int64_t n_tiles = (int64_t)g.n_sta_tiles * (g.n_grid_owned > 0 ? g.n_grid_owned : g.n_grid);
     static PerDeviceOnce attr_set;
     if (attr_set.need()) {
-#define GENIE_S1_ATTR(E, B, A)                                                                                    \
-    GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer1_s_kernel<E, B, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+#define GENIE_S1_ATTR(E, B, A, X)                                                                                    \
+    GENIE_CUDA_CHECK(cudaFuncSetAttribute(da_layer1_s_kernel<E, B, A, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           Fmt<B>::SM_TOTAL));
-        GENIE_S1_ATTR(false, false, false) GENIE_S1_ATTR(true, false, false) GENIE_S1_ATTR(false, true, false)
-        GENIE_S1_ATTR(true, true, false) GENIE_S1_ATTR(false, false, true) GENIE_S1_ATTR(true, false, true)
+        GENIE_S1_ATTR(false, false, false, false) GENIE_S1_ATTR(true, false, false, false) GENIE_S1_ATTR(false, true, false, false)
+        GENIE_S1_ATTR(true, true, false, false) GENIE_S1_ATTR(false, false, true, false) GENIE_S1_ATTR(true, false, true, false)
+        GENIE_S1_ATTR(false, false, false, true) GENIE_S1_ATTR(true, false, false, true) GENIE_S1_ATTR(false, true, false, true)
+        GENIE_S1_ATTR(true, true, false, true)
 #undef GENIE_S1_ATTR
         attr_set.mark();
     }
     const int64_t grid = n_tiles < p->sm_count ? n_tiles : p->sm_count;
     const bool edge = edge_sta != nullptr, bf = !assoc && p->storage == GENIE_STORAGE_BF16;
+    const bool exp = export_halo && p->exp_ptr != nullptr;
     TimedLaunch tl(assoc ? KID_ASSOC_LAYER1 : KID_DA_LAYER1_S, st);
-#define GENIE_S1_LAUNCH(E, B, A)                                                                                               \
-    if (edge == E && bf == B && assoc == A)                                                                                     \
-        da_layer1_s_kernel<E, B, A><<<(unsigned)grid, S1_THREADS, Fmt<B>::SM_TOTAL, st>>>(                                      \
+#define GENIE_S1_LAUNCH(E, B, A, X)                                                                                            \
+    if (edge == E && bf == B && assoc == A && exp == X)                                                                         \
+        da_layer1_s_kernel<E, B, A, X><<<(unsigned)grid, S1_THREADS, Fmt<B>::SM_TOTAL, st>>>(                                   \
             blob, pfeat, msrc, mask, zc, va, vb, g.n_sta, g.n_sta_tiles, g.sta_tile_rows, g.sta_tile_meta, g.sta_tile_nbr,      \
-            g.sta_tile_invdeg, n_tiles, edge_sta, edge_src, tr_own, mask_out, export_halo ? p->exp_ptr : nullptr, p->exp_peer,      \
+            g.sta_tile_invdeg, n_tiles, edge_sta, edge_src, tr_own, mask_out, p->exp_ptr, p->exp_peer,                              \
             p->exp_row, p->peer_base, g_s1_trace, g_s1_trace_tiles, g_s1_trace_start);
-    GENIE_S1_LAUNCH(false, false, false) GENIE_S1_LAUNCH(true, false, false) GENIE_S1_LAUNCH(false, true, false)
-    GENIE_S1_LAUNCH(true, true, false) GENIE_S1_LAUNCH(false, false, true) GENIE_S1_LAUNCH(true, false, true)
+    GENIE_S1_LAUNCH(false, false, false, false) GENIE_S1_LAUNCH(true, false, false, false) GENIE_S1_LAUNCH(false, true, false, false)
+    GENIE_S1_LAUNCH(true, true, false, false) GENIE_S1_LAUNCH(false, false, true, false) GENIE_S1_LAUNCH(true, false, true, false)
+    GENIE_S1_LAUNCH(false, false, false, true) GENIE_S1_LAUNCH(true, false, false, true) GENIE_S1_LAUNCH(false, true, false, true)
+    GENIE_S1_LAUNCH(true, true, false, true)
 #undef GENIE_S1_LAUNCH
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;
