@@ -304,7 +304,8 @@ class ShardedWorkload(object):
             attr[lo * S:hi * S] = (diff / SCALE_REL).reshape(-1, 3).float()
         torch.manual_seed(2)
         self.model = GCN_Detection_Network_extended(None, None, scale_rel=SCALE_REL, device=dev).eval()
-        be = CudaBackend(self.model, A_sta, part.local_graph(rank), S, self.n_local, self.n_owned, attr, A_src, G, dev)
+        be = CudaBackend(self.model, A_sta, part.local_graph(rank), S, self.n_local, self.n_owned, attr, A_src, G, dev,
+                         grid_groups=part.local_groups(rank))
         if storage == 'bf16':
             self.model._plan = be.plan
             self.model.set_storage('bf16')
@@ -502,8 +503,15 @@ def sharded_leg(args, dev, rank, world, dist, name='c5_2000x200000_sharded'):
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        # per-rank picture: where the ranks differ (ms per step: wait at the exchange / fence, then the kernels by name)
+        names = ['da_init_kernel', 'src_mean32_kernel', 'da_layer1_s_kernel', 'src_mean16_kernel', 'da_layer2_s_kernel',
+                 'input_gather_kernel', 'sa_main_kernel', 'heads_grid_kernel', 'heads_query_kernel']
+        mine = torch.tensor([ex_ms / K] + [kt.get(n, (0.0, 0))[0] / K for n in names], dtype=torch.float64, device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {'columns': ['exchange_wait'] + names, 'ms_per_step': [[round(float(v), 3) for v in r] for r in allr]}
         ms = float(tmax[0])
-        return {'value': K / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms / K,
+        return {'value': K / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms / K, 'per_rank': per_rank,
                 'exchange_bytes_per_step_sum': float(t[3]), 'exchange_ms_per_step_max': float(tmax[1]) / K,
                 'exchange_share_of_step': float(tmax[1]) / ms, 'library_kernels_share_of_step_rank_max': float(tmax[2]) / ms,
                 'layer1_station_pass_ms_per_step_max': float(tmax[6]) / K,

@@ -196,7 +196,7 @@ class GraphPlan(object):
     """Owns the device index arrays and the C-side plan handle (genie_plan_t)."""
 
     def __init__(self, mode, n_sta, n_grid, n_prod, sta, src, grid, grid_outdeg, prod_grid, device, grid_order=None,
-                 tiling=True, group_size=GROUP_SIZE, n_grid_owned=0):
+                 tiling=True, group_size=GROUP_SIZE, n_grid_owned=0, grid_groups=None):
         self.mode, self.n_sta, self.n_grid, self.n_prod = mode, int(n_sta), int(n_grid), int(n_prod)
         self.n_grid_owned = int(n_grid_owned)          # grid sharding: nodes >= n_grid_owned are halo copies (0 = none)
         self.device = torch.device(device)
@@ -215,8 +215,14 @@ class GraphPlan(object):
         if mode == capi.GRAPH_CARTESIAN and n_sta >= 32 and n_grid > 0 and 1 <= self.sta_max_deg <= 16 and tiling:
             st = station_tiles(sta[0], sta[1], self.n_sta)
             if st is not None:
-                gp, gn = bisection_groups(src[0], src[1], self.n_grid, int(group_size))
-                if self.n_grid_owned:                       # halo nodes are gathered FROM, never computed: drop them
+                if grid_groups is not None:                 # the caller's groups (grid sharding: the groups of the WHOLE grid's
+                    gp, gn = (np.ascontiguousarray(a, dtype=np.int32) for a in grid_groups)      # bisection that a rank owns)
+                    if gp[0] != 0 or gp[-1] != len(gn) or (np.diff(gp) <= 0).any() or \
+                            not np.array_equal(np.sort(gn), np.arange(self.n_grid_owned or self.n_grid)):
+                        raise ValueError('grid_groups must partition the (owned) grid nodes into non-empty groups')
+                else:
+                    gp, gn = bisection_groups(src[0], src[1], self.n_grid, int(group_size))
+                if self.n_grid_owned and grid_groups is None:   # halo nodes are gathered FROM, never computed: drop them
                     keep = gn < self.n_grid_owned
                     cnt = np.add.reduceat(keep.astype(np.int64), gp[:-1]) if len(gp) > 1 else np.zeros(0, np.int64)
                     cnt = cnt[cnt > 0]
@@ -349,7 +355,7 @@ class GraphPlan(object):
 
     @classmethod
     def cartesian(cls, A_sta_sta, A_src_src, n_sta, n_grid, A_src=None, device=None, grid_order=None, tiling=True,
-                  group_size=GROUP_SIZE, n_grid_owned=0):
+                  group_size=GROUP_SIZE, n_grid_owned=0, grid_groups=None):
         """Dense mode from the two small kNN graphs (process_utils.py:718-719); product edges stay implicit."""
         device = torch.device(device if device is not None else A_sta_sta.device)
         A_sta_sta, A_src_src = A_sta_sta.to(device), A_src_src.to(device)
@@ -361,7 +367,8 @@ class GraphPlan(object):
         else:
             grid, outdeg = cls._grid_parts(A_src.to(device), n_grid)
         return cls(capi.GRAPH_CARTESIAN, n_sta, n_grid, n_sta * n_grid, sta, src, grid, outdeg, None, device,
-                   grid_order=grid_order, tiling=tiling, group_size=group_size, n_grid_owned=n_grid_owned)
+                   grid_order=grid_order, tiling=tiling, group_size=group_size, n_grid_owned=n_grid_owned,
+                   grid_groups=grid_groups)
 
     @classmethod
     def grid_only(cls, A_src, n_grid, device):

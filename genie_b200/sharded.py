@@ -39,6 +39,9 @@ class GridPartition(object):
         bounds = np.searchsorted(gp, np.arange(1, world) * (n_grid / float(world)), side='left')
         bounds = np.concatenate(([0], np.clip(bounds, 0, len(gp) - 1), [len(gp) - 1]))
         self.owned = [np.ascontiguousarray(gn[gp[bounds[r]]:gp[bounds[r + 1]]].astype(np.int64)) for r in range(world)]
+        # the groups a rank owns, as ranges of its local ids (its owned nodes are those groups' nodes, in group order)
+        self.group_ptr = [np.ascontiguousarray(gp[bounds[r]:bounds[r + 1] + 1] - gp[bounds[r]]).astype(np.int32)
+                          for r in range(world)]
         self.owner = np.empty(n_grid, dtype=np.int64)
         for r in range(world):
             self.owner[self.owned[r]] = r
@@ -52,6 +55,14 @@ class GridPartition(object):
     def local_nodes(self, rank):
         """Global ids of the local grid of `rank`: owned nodes first, then the halo."""
         return np.concatenate((self.owned[rank], self.halo[rank]))
+
+    def local_groups(self, rank):
+        """(grp_ptr, grp_nodes) of the local plan: the compact groups of the WHOLE grid's bisection that `rank` owns.  (A
+        bisection of the local graph, whose halo nodes have no in-edges, gives ragged groups: the layer-1 source pass of the
+        eight ranks of C5 took 4.1 - 6.7 ms with it against 3.9 ms for the same node count on one GPU.)"""
+        gp = self.group_ptr[rank]
+        keep = np.concatenate(([True], np.diff(gp) > 0))
+        return gp[keep], np.arange(len(self.owned[rank]), dtype=np.int32)
 
     def local_graph(self, rank):
         """Source graph restricted to the local grid (local ids): in-edges of owned nodes only; halo rows are empty."""
@@ -160,10 +171,12 @@ class CudaBackend(object):
     """The product compute path: libgenie_b200 kernels on the local plan (see include/genie_b200.h)."""
 
     def __init__(self, model, A_sta_sta, A_src_local, n_sta, n_local, n_owned, read_in_attr_local, A_src_global, n_grid,
-                 device):
+                 device, grid_groups=None):
+        """grid_groups: GridPartition.local_groups(rank) — the source-pass groups of the local plan."""
         from .plan import GraphPlan
         self.model, self.device = model, torch.device(device)
-        self.plan = GraphPlan.cartesian(A_sta_sta, A_src_local, n_sta, n_local, device=device, n_grid_owned=n_owned)
+        self.plan = GraphPlan.cartesian(A_sta_sta, A_src_local, n_sta, n_local, device=device, n_grid_owned=n_owned,
+                                        grid_groups=grid_groups)
         self.plan_grid = GraphPlan.grid_only(A_src_global, n_grid, device)
         self.attr = read_in_attr_local.to(device).float().contiguous()
         self._mask = None

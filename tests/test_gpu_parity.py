@@ -775,7 +775,8 @@ def test_sharded_halo_rows_over_peer_stores(storage):
     for r in range(world):
         nd = torch.from_numpy(part.local_nodes(r))
         loc = lambda x: x.view(G, S, -1).index_select(0, nd).reshape(len(nd) * S, -1).contiguous().to(dev)
-        be = CudaBackend(m, A_sta, part.local_graph(r), S, len(nd), len(part.owned[r]), loc(attr), A_src, G, dev)
+        be = CudaBackend(m, A_sta, part.local_graph(r), S, len(nd), len(part.owned[r]), loc(attr), A_src, G, dev,
+                         grid_groups=part.local_groups(r))
         be.plan.set_storage(storage)
         ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(capi.PEER_HANDLE_BYTES)
         capi.check(lib.genie_peer_alloc(max(len(part.halo[r]), 1) * row_bytes, ctypes.byref(ptr), handle))

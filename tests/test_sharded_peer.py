@@ -38,7 +38,8 @@ def _worker(rank, world, port, ret):
     part = GridPartition(A_src, G, world)
     nd = torch.from_numpy(part.local_nodes(rank))
     loc = lambda x: x.view(G, S, -1).index_select(0, nd).reshape(len(nd) * S, -1).contiguous().to(dev)
-    be = CudaBackend(m, A_sta, part.local_graph(rank), S, len(nd), len(part.owned[rank]), loc(attr), A_src, G, dev)
+    be = CudaBackend(m, A_sta, part.local_graph(rank), S, len(nd), len(part.owned[rank]), loc(attr), A_src, G, dev,
+                     grid_groups=part.local_groups(rank))
     halo = PeerHalo(part, rank, be.plan, S, dev)
     fe = ShardedFrontEnd(part, rank, be, dev, peer_halo=halo)
     plan = GraphPlan.cartesian(A_sta, A_src, S, G, device=dev)
