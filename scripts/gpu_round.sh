@@ -34,7 +34,7 @@ tail -3 gpurun_out/${tag}_ncu_full_bf16.log
 export_rep ${tag}_prof_bf16
 # association branch (scripts/probe_assoc.py at 1000 x 5000): one forward_fixed = the front end's two station passes, then
 # assoc_init and the ASSOC instances of the two station-pass kernels
-timeout 900 ncu --set full --metrics sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum \
+GENIE_PROBE_ASSOC_ONLY=1 timeout 900 ncu --set full --metrics sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum \
   --clock-control none -k regex:'assoc_init|da_layer1_s|da_layer2_s' -c 5 \
   -o gpurun_out/${tag}_prof_assoc -f python scripts/probe_assoc.py c4s > gpurun_out/${tag}_ncu_assoc.log 2>&1
 tail -3 gpurun_out/${tag}_ncu_assoc.log

@@ -48,7 +48,7 @@ def run(S, G, label, n_arv=600, n_src=2, Q=10000):
     tqs = torch.zeros(n_src, device=dev)
     f_src = lambda: m.forward_fixed_source(Slice, Mask, None, None, None, locs, pos, xq, tq)
     f_fix = lambda: m.forward_fixed(Slice, Mask, tpick, ipick, phase, locs, pos, xq, x_src, tq, tqs, trv_q)
-    med_s, _ = timed(f_src)
+    med_s = 0.0 if os.environ.get('GENIE_PROBE_ASSOC_ONLY') == '1' else timed(f_src)[0]      # (ncu captures: forward_fixed first)
     med_f, _ = timed(f_fix)
     print('%s: S=%d G=%d P=%d picks=%d sources=%d: forward_fixed_source %.3f ms, forward_fixed %.3f ms (association adds %.3f ms)'
           % (label, S, G, P, n_arv, n_src, med_s, med_f, med_f - med_s), flush=True)
