@@ -310,7 +310,7 @@ class ShardedWorkload(object):
             self.model._plan = be.plan
             self.model.set_storage('bf16')
         # halo rows: stored into the peers' memory by the layer-1 kernel itself (PeerHalo), or one all_to_all_single per window
-        self.peer_halo = PeerHalo(part, rank, be.plan, S, dev) if (exchange == 'peer' and world > 1) else None
+        self.peer_halo = PeerHalo.create(part, rank, be.plan, S, dev) if (exchange == 'peer' and world > 1) else None
         self.fe = ShardedFrontEnd(part, rank, be, dev, peer_halo=self.peer_halo)
         self.halo_rows = [len(h) for h in part.halo]
         self.exchange_events = None

@@ -212,7 +212,7 @@ class GraphPlan(object):
             self.grid_order = torch.from_numpy(grid_order).to(self.device).contiguous()
         # on-chip tiling tables of the split kernels (dense mode; None -> the one-pass kernels are used)
         self.tiles = None
-        if mode == capi.GRAPH_CARTESIAN and n_sta >= 32 and n_grid > 0 and 1 <= self.sta_max_deg <= 16 and tiling:
+        if mode == capi.GRAPH_CARTESIAN and n_sta >= 2 and n_grid > 0 and 1 <= self.sta_max_deg <= 16 and tiling:
             st = station_tiles(sta[0], sta[1], self.n_sta)
             if st is not None:
                 if grid_groups is not None:                 # the caller's groups (grid sharding: the groups of the WHOLE grid's

@@ -104,20 +104,37 @@ class PeerHalo(object):
         n_halo = len(partition.halo[rank])
         row_bytes = n_sta * 16 * (2 if plan.storage == 'bf16' else 4)
         self.bytes = max(n_halo, 1) * row_bytes
+        # Every rank goes through the same collectives whatever happens locally, and all ranks agree on the outcome: a rank that
+        # cannot allocate, export or map a buffer (no peer access between two GPUs, inter-process handles disabled) makes the
+        # whole group fall back — `PeerHalo.create` then returns None and the caller keeps the all-to-all.
+        self.local_ptr, self.peer_ptrs, err = None, [], None
         with torch.cuda.device(self.device):
             ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(capi.PEER_HANDLE_BYTES)
-            capi.check(lib.genie_peer_alloc(self.bytes, ctypes.byref(ptr), handle))
-            self.local_ptr = ptr.value
+            try:
+                capi.check(lib.genie_peer_alloc(self.bytes, ctypes.byref(ptr), handle))
+                self.local_ptr = ptr.value
+            except capi.GenieError as e:
+                err = str(e)
             handles = [None] * world
-            dist.all_gather_object(handles, handle.raw, group=group)
-            self.peer_ptrs = []
+            dist.all_gather_object(handles, handle.raw if err is None else None, group=group)
             for q in range(world):
                 if q == rank:
                     self.peer_ptrs.append(self.local_ptr)
                     continue
                 pq = ctypes.c_void_p()
-                capi.check(lib.genie_peer_open(handles[q], ctypes.byref(pq)))
+                try:
+                    if handles[q] is None:
+                        raise capi.GenieError('rank %d has no landing buffer' % q)
+                    capi.check(lib.genie_peer_open(handles[q], ctypes.byref(pq)))
+                except capi.GenieError as e:
+                    err = err or str(e)
                 self.peer_ptrs.append(pq.value)
+            errs = [None] * world
+            dist.all_gather_object(errs, err, group=group)
+        self.plan, self.rank = None, rank
+        if any(e is not None for e in errs):
+            self._release()
+            raise capi.GenieError('halo rows over peer memory are not available: %s' % next(e for e in errs if e is not None))
         ptr_, peer, row = self.export_tables(partition, rank)
         dev = self.device
         self.exp_ptr = torch.from_numpy(ptr_).to(dev)
@@ -154,16 +171,31 @@ class PeerHalo(object):
         """Stream-ordered: returns (on the stream) once every rank's work enqueued before its own fence has completed."""
         dist.all_reduce(self._flag, group=self.group)
 
+    @classmethod
+    def create(cls, partition, rank, plan, n_sta, device, group=None):
+        """A PeerHalo, or None (on every rank alike) when peer memory cannot be set up on this node."""
+        from . import capi
+        try:
+            return cls(partition, rank, plan, n_sta, device, group)
+        except capi.GenieError:
+            return None
+
+    def _release(self):
+        with torch.cuda.device(self.device):
+            for q, p in enumerate(self.peer_ptrs):
+                if q != self.rank and p:
+                    self.lib.genie_peer_close(p)
+            if self.local_ptr:
+                self.lib.genie_peer_free(self.local_ptr)
+        self.peer_ptrs, self.local_ptr = [], None
+
     def close(self):
         if self.plan is not None:
             self.plan.set_halo_export(None, None, None, None, None)
             with torch.cuda.device(self.device):
                 torch.cuda.synchronize()
                 dist.barrier(group=self.group)                      # nobody still stores into a buffer that is about to go
-                for q, p in enumerate(self.peer_ptrs):
-                    if q != self.rank:
-                        self.lib.genie_peer_close(p)
-                self.lib.genie_peer_free(self.local_ptr)
+            self._release()
             self.plan = None
 
 

@@ -53,7 +53,7 @@ class WindowRunner(object):
         plan = mz._plan
         if plan is None or plan is not extractor.plan:
             raise capi.GenieError('WindowRunner: the model and the extractor must share one GraphPlan')
-        # genie_window_fwd needs a dense plan with tiling tables (>= 32 stations); other plans (tiny networks, sub-graph mode)
+        # genie_window_fwd needs a dense plan with tiling tables; other plans (station in-degree > 16, sub-graph mode)
         # run the reference-shaped two-step sequence eagerly: extract_input -> Slice / Mask -> forward_fixed_source
         self.fused = plan.mode == capi.GRAPH_CARTESIAN and plan.tiles is not None and extractor.node_sta is None
         if not self.fused:
@@ -175,7 +175,7 @@ class DayProcessor(object):
         self.use_runner, self.use_graph, self._run = use_runner, use_graph, None
 
     def _runner(self):
-        """WindowRunner for dense plans with tiling tables (>= 32 stations); None -> the two-step path."""
+        """WindowRunner for dense plans with tiling tables; None -> the two-step path."""
         if self.use_runner is False:
             return None
         plan = self.mz._plan
