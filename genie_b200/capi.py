@@ -19,6 +19,7 @@ _lib = None
 GRAPH_CARTESIAN, GRAPH_EXPLICIT = 0, 1
 ABI_VERSION = 8
 PEER_HANDLE_BYTES = 64         # GENIE_PEER_HANDLE_BYTES
+HEADS_PROJ_LD = 160            # GENIE_HEADS_PROJ_LD
 EDGE_TERM_LD = 48           # GENIE_EDGE_TERM_LD
 STORAGE_FP32, STORAGE_BF16 = 0, 1
 
@@ -114,9 +115,9 @@ SIGNATURES = {
     'genie_frontend_pack_weights': (ctypes.c_int, [ctypes.POINTER(FrontendWeights), _P, _P]),
     'genie_heads_packed_floats': (ctypes.c_size_t, []),
     'genie_heads_layout': (ctypes.c_int, [_P, ctypes.c_int]),
-    'genie_heads_grid_fwd': (ctypes.c_int, [_P, _P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int, _P, _P]),
+    'genie_heads_grid_fwd': (ctypes.c_int, [_P, _P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int, _P, _P, _P]),
     'genie_heads_query_fwd': (ctypes.c_int, [_P, _P, ctypes.c_int, _P, ctypes.c_int, _P, _P, _P, ctypes.c_int, ctypes.c_int,
-                                            ctypes.c_float, _P, _P]),
+                                            ctypes.c_float, _P, _P, _P]),
     'genie_kron_spmm_fwd': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, _P, _P, _P, _P, ctypes.c_int,
                                            ctypes.c_int, _P, ctypes.c_int, _P]),
     'genie_node_mlp_partial_rows': (ctypes.c_int, []),

@@ -371,25 +371,25 @@ int genie_heads_layout(int32_t* offsets_out, int n) {
 }
 
 int genie_heads_grid_fwd(const float* heads_packed_dev, const float* fold_dev, int n_t, const float* x_spatial_dev, int ld_x,
-                         int n_grid, float* y_out_dev, void* stream) {
+                         int n_grid, float* y_out_dev, float* proj_out_dev, void* stream) {
     if (!heads_packed_dev || !fold_dev || !x_spatial_dev || !y_out_dev || n_t < 0 || n_grid < 0 || ld_x < 30) {
         set_error("genie_heads_grid_fwd: bad argument");
         return GENIE_ERR_INVALID;
     }
-    return launch_heads_grid(heads_packed_dev, fold_dev, n_t, x_spatial_dev, ld_x, n_grid, y_out_dev,
+    return launch_heads_grid(heads_packed_dev, fold_dev, n_t, x_spatial_dev, ld_x, n_grid, y_out_dev, proj_out_dev,
                              static_cast<cudaStream_t>(stream));
 }
 
 int genie_heads_query_fwd(const float* heads_packed_dev, const float* fold_dev, int n_t, const float* x_spatial_dev, int ld_x,
                           const float* x_context_dev, const float* x_query_dev, const int64_t* nbr_dev, int k_nbr, int n_query,
-                          float scale_rel, float* x_out_dev, void* stream) {
+                          float scale_rel, float* x_out_dev, const float* proj_dev, void* stream) {
     if (!heads_packed_dev || !fold_dev || !x_spatial_dev || !x_context_dev || !x_query_dev || !nbr_dev || !x_out_dev ||
         n_t < 0 || n_query < 0 || ld_x < 30 || !(scale_rel > 0.f)) {
         set_error("genie_heads_query_fwd: bad argument");
         return GENIE_ERR_INVALID;
     }
     return launch_heads_query(heads_packed_dev, fold_dev, n_t, x_spatial_dev, ld_x, x_context_dev, x_query_dev, nbr_dev, k_nbr,
-                              n_query, scale_rel, x_out_dev, static_cast<cudaStream_t>(stream));
+                              n_query, scale_rel, x_out_dev, proj_dev, static_cast<cudaStream_t>(stream));
 }
 
 int genie_input_nearest_fwd(const genie_nearest_params_t* prm, const double* times_all_dev, const double* times_p_dev,

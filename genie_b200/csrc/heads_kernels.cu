@@ -109,10 +109,15 @@ __device__ __forceinline__ void load_heads(float* sW, float* sAt, float* sA0, co
     __syncthreads();
 }
 
+constexpr int PROJ_LD = 160;                   // per grid node: f_context(x_j) part at 0-74, f_values(x_j) part at 80-154
+
 // y[g, t] for every grid node: SpatialDirect -> TemporalAttention.
+// proj != NULL: also the x_j parts of SpatialAttention's per-edge layers, f_context[:, :30] x_g and f_values[:, :30] x_g
+// (module.py:288-290: both are linear in [x_j | edge attr], and the x_j part does not depend on the query) — one 30 -> 75
+// product per grid node here instead of one per (query, neighbour) pair in heads_query_kernel.
 __global__ void __launch_bounds__(HEADS_THREADS)
     heads_grid_kernel(const float* __restrict__ packed, const float* __restrict__ fold, int T,
-                      const float* __restrict__ x_spatial, int ld_x, int G, float* __restrict__ y) {
+                      const float* __restrict__ x_spatial, int ld_x, int G, float* __restrict__ y, float* __restrict__ proj) {
     extern __shared__ __align__(16) float smem[];
     float* sW = smem;
     float* sAt = smem + HD_FLOATS;
@@ -122,17 +127,31 @@ __global__ void __launch_bounds__(HEADS_THREADS)
     const int lane = threadIdx.x & 31;
     for (int g = blockIdx.x * HW + (threadIdx.x >> 5); g < G; g += gridDim.x * HW) {
         const float x = lane < 30 ? __ldg(x_spatial + (int64_t)g * ld_x + lane) : 0.f;
+        if (proj != nullptr) {
+            float pc[3] = {0.f, 0.f, 0.f}, pv[3] = {0.f, 0.f, 0.f};
+            mv75(x, 30, sW + HD_SA_WC, pc, lane);
+            mv75(x, 30, sW + HD_SA_WV, pv, lane);
+            float* pr = proj + (int64_t)g * PROJ_LD;
+            pr[lane] = pc[0];
+            pr[32 + lane] = pc[1];
+            if (lane < 11) pr[64 + lane] = pc[2];
+            pr[80 + lane] = pv[0];
+            pr[112 + lane] = pv[1];
+            if (lane < 11) pr[144 + lane] = pv[2];
+        }
         const float yl = prelu(mv30(x, 30, sW + HD_SD_W, sW + HD_SD_B, lane), sW[HD_SD_SL]);        // module.py:258-260
         temporal_attention_warp(sW, sAt, sA0, T, yl, scr, lane, y + (int64_t)g * T);
     }
 }
 
 // x[q, t] for every query point: SpatialAttention over its k nearest context nodes -> TemporalAttention.
+// PROJ: the x_j parts of f_context / f_values come from heads_grid_kernel's table (one row per context node).
+template <bool PROJ>
 __global__ void __launch_bounds__(HEADS_THREADS)
     heads_query_kernel(const float* __restrict__ packed, const float* __restrict__ fold, int T,
                        const float* __restrict__ x_spatial, int ld_x, const float* __restrict__ x_context,
                        const float* __restrict__ x_query, const int64_t* __restrict__ nbr, int k_nbr, int Q,
-                       float scale_rel, float* __restrict__ x_out) {
+                       float scale_rel, float* __restrict__ x_out, const float* __restrict__ proj) {
     extern __shared__ __align__(16) float smem[];
     float* sW = smem;
     float* sAt = smem + HD_FLOATS;
@@ -152,7 +171,7 @@ __global__ void __launch_bounds__(HEADS_THREADS)
             const int64_t j = __ldg(nbr + (int64_t)qi * k_nbr + e);
             const float ea[3] = {(qx - __ldg(x_context + j * 3)) / scale_rel, (qy - __ldg(x_context + j * 3 + 1)) / scale_rel,
                                  (qz - __ldg(x_context + j * 3 + 2)) / scale_rel};
-            const float xj = lane < 30 ? __ldg(x_spatial + j * ld_x + lane) : 0.f;
+            const float xj = (!PROJ && lane < 30) ? __ldg(x_spatial + j * ld_x + lane) : 0.f;
             float c[3], qv[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
@@ -166,7 +185,14 @@ __global__ void __launch_bounds__(HEADS_THREADS)
                     qv[r] = fmaf(ea[d], ok ? sW[HD_SA_WQ + d * 76 + o] : 0.f, qv[r]);
                 }
             }
-            mv75(xj, 30, sW + HD_SA_WC, c, lane);
+            if (PROJ) {
+                const float* pr = proj + j * PROJ_LD;
+                c[0] += __ldg(pr + lane);
+                c[1] += __ldg(pr + 32 + lane);
+                if (lane < 11) c[2] += __ldg(pr + 64 + lane);
+            } else {
+                mv75(xj, 30, sW + HD_SA_WC, c, lane);
+            }
             sprod[lane] = qv[0] * c[0];
             sprod[32 + lane] = qv[1] * c[1];
             if (lane < 11) sprod[64 + lane] = qv[2] * c[2];
@@ -198,7 +224,7 @@ __global__ void __launch_bounds__(HEADS_THREADS)
             const int64_t j = __ldg(nbr + (int64_t)qi * k_nbr + e);
             const float ea[3] = {(qx - __ldg(x_context + j * 3)) / scale_rel, (qy - __ldg(x_context + j * 3 + 1)) / scale_rel,
                                  (qz - __ldg(x_context + j * 3 + 2)) / scale_rel};
-            const float xj = lane < 30 ? __ldg(x_spatial + j * ld_x + lane) : 0.f;
+            const float xj = (!PROJ && lane < 30) ? __ldg(x_spatial + j * ld_x + lane) : 0.f;
             float v[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
@@ -208,7 +234,14 @@ __global__ void __launch_bounds__(HEADS_THREADS)
 #pragma unroll
                 for (int d = 0; d < 3; ++d) v[r] = fmaf(ea[d], ok ? sW[HD_SA_WV + (30 + d) * 76 + o] : 0.f, v[r]);
             }
-            mv75(xj, 30, sW + HD_SA_WV, v, lane);
+            if (PROJ) {
+                const float* pr = proj + j * PROJ_LD + 80;
+                v[0] += __ldg(pr + lane);
+                v[1] += __ldg(pr + 32 + lane);
+                if (lane < 11) v[2] += __ldg(pr + 64 + lane);
+            } else {
+                mv75(xj, 30, sW + HD_SA_WV, v, lane);
+            }
             scr[lane] = v[0];
             scr[32 + lane] = v[1];
             if (lane < 11) scr[64 + lane] = v[2];
@@ -237,7 +270,7 @@ int heads_blocks(int n) {
 }  // namespace
 
 int launch_heads_grid(const float* packed, const float* fold, int T, const float* x_spatial, int ld_x, int G, float* y,
-                      cudaStream_t st) {
+                      float* proj, cudaStream_t st) {
     if (G == 0 || T == 0) return GENIE_OK;
     const size_t smem = heads_smem_bytes(T);
     if (T * NH > 32 * TH_NC) {
@@ -247,14 +280,14 @@ int launch_heads_grid(const float* packed, const float* fold, int T, const float
     GENIE_CUDA_CHECK(cudaFuncSetAttribute(heads_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int blocks = heads_blocks(G);
     TimedLaunch tl(KID_HEADS_GRID, st);
-    heads_grid_kernel<<<blocks, HEADS_THREADS, smem, st>>>(packed, fold, T, x_spatial, ld_x, G, y);
+    heads_grid_kernel<<<blocks, HEADS_THREADS, smem, st>>>(packed, fold, T, x_spatial, ld_x, G, y, proj);
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;
 }
 
 int launch_heads_query(const float* packed, const float* fold, int T, const float* x_spatial, int ld_x, const float* x_context,
                        const float* x_query, const int64_t* nbr, int k_nbr, int Q, float scale_rel, float* x_out,
-                       cudaStream_t st) {
+                       const float* proj, cudaStream_t st) {
     if (Q == 0 || T == 0) return GENIE_OK;
     if (k_nbr < 1 || k_nbr > 16) {
         set_error("heads: the query read-out supports 1..16 context neighbours per query");
@@ -265,11 +298,16 @@ int launch_heads_query(const float* packed, const float* fold, int T, const floa
         set_error("heads: at most 25 query times (T * 5 <= 128 columns of the folded query table)");
         return GENIE_ERR_UNSUPPORTED;
     }
-    GENIE_CUDA_CHECK(cudaFuncSetAttribute(heads_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GENIE_CUDA_CHECK(cudaFuncSetAttribute(heads_query_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GENIE_CUDA_CHECK(cudaFuncSetAttribute(heads_query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int blocks = heads_blocks(Q);
     TimedLaunch tl(KID_HEADS_QUERY, st);
-    heads_query_kernel<<<blocks, HEADS_THREADS, smem, st>>>(packed, fold, T, x_spatial, ld_x, x_context, x_query, nbr, k_nbr, Q,
-                                                            scale_rel, x_out);
+    if (proj != nullptr)
+        heads_query_kernel<true><<<blocks, HEADS_THREADS, smem, st>>>(packed, fold, T, x_spatial, ld_x, x_context, x_query, nbr,
+                                                                      k_nbr, Q, scale_rel, x_out, proj);
+    else
+        heads_query_kernel<false><<<blocks, HEADS_THREADS, smem, st>>>(packed, fold, T, x_spatial, ld_x, x_context, x_query, nbr,
+                                                                       k_nbr, Q, scale_rel, x_out, nullptr);
     GENIE_LAUNCH_CHECK();
     return GENIE_OK;
 }

@@ -205,10 +205,10 @@ int launch_da_layer2_s(const genie_plan* p, const float* packed, const float* zc
                        const float* mask, const float* edge_attr, float* latent_out, float* out, int ld_out,
                        cudaStream_t st);
 int launch_heads_grid(const float* packed, const float* fold, int T, const float* x_spatial, int ld_x, int G, float* y,
-                      cudaStream_t st);
+                      float* proj, cudaStream_t st);
 int launch_heads_query(const float* packed, const float* fold, int T, const float* x_spatial, int ld_x, const float* x_context,
                        const float* x_query, const int64_t* nbr, int k_nbr, int Q, float scale_rel, float* x_out,
-                       cudaStream_t st);
+                       const float* proj, cudaStream_t st);
 // association branch (assoc_kernels.cu)
 struct AssocWorkspace {
     float* tr;        // [P][32]   init_trns output; re-used for the branch output s [P][32] = [o1(15) 0 | o2(15) 0]

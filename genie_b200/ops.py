@@ -174,15 +174,19 @@ def heads_fwd(hw, packed, fold, T, x_spatial, x_context, x_query, nbr, scale_rel
     G, Q = x_spatial.shape[0], x_query.shape[0]
     y = torch.empty((G, T, 1), dtype=F32, device=dev)
     x = torch.empty((Q, T, 1), dtype=F32, device=dev)
+    # the query-independent halves of SpatialAttention's per-edge layers, once per context node (GENIE_HEADS_PROJ_LD); worth
+    # it whenever the queries touch more (query, neighbour) pairs than there are context nodes — always, in practice
+    proj = torch.empty((G, capi.HEADS_PROJ_LD), dtype=F32, device=dev) if Q * max(int(nbr.shape[1]), 1) >= G else None
     lib = capi.load()
     with torch.cuda.device(dev):
         capi.check(lib.genie_heads_grid_fwd(capi.dptr(packed, F32), capi.dptr(fold, F32), int(T), capi.dptr(x_spatial, F32),
-                                            int(x_spatial.stride(0)), int(G), capi.dptr(y), capi.stream_ptr(dev)))
+                                            int(x_spatial.stride(0)), int(G), capi.dptr(y), capi.dptr(proj),
+                                            capi.stream_ptr(dev)))
         if Q > 0:
             capi.check(lib.genie_heads_query_fwd(
                 capi.dptr(packed, F32), capi.dptr(fold, F32), int(T), capi.dptr(x_spatial, F32), int(x_spatial.stride(0)),
                 capi.dptr(_f32c(x_context, 'x_context'), F32), capi.dptr(_f32c(x_query, 'x_query'), F32),
-                capi.dptr(nbr, torch.int64), int(nbr.shape[1]), int(Q), float(scale_rel), capi.dptr(x),
+                capi.dptr(nbr, torch.int64), int(nbr.shape[1]), int(Q), float(scale_rel), capi.dptr(x), capi.dptr(proj),
                 capi.stream_ptr(dev)))
     return y, x
 

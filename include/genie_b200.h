@@ -245,14 +245,20 @@ GENIE_API int genie_input_scatter_fwd(const genie_plan_t* plan, const genie_inpu
  *                     f_context_2.bias[h*15:(h+1)*15] / sqrt(15), q = temporal_query_2(activate3(temporal_query_1(t/scale_t))).
  *   nbr_dev           int64 [n_query][k_nbr] context node of every query edge, nearest first (knn(...).flip(0), module.py:282).
  *   y_out_dev [n_grid][n_t], x_out_dev [n_query][n_t].
+ *   proj_out_dev / proj_dev  optional fp32 [n_grid][GENIE_HEADS_PROJ_LD] (NULL = off): f_context and f_values of SpatialAttention
+ *                     (module.py:288-290) are linear in [x_j | edge attr], and their x_j parts do not depend on the query — the
+ *                     grid kernel computes them once per context node (columns 0-74 and 80-154) and the query kernel adds the
+ *                     edge-attribute part per (query, neighbour) pair, instead of two 33 -> 75 layers per pair.
  */
+#define GENIE_HEADS_PROJ_LD 160
 GENIE_API size_t genie_heads_packed_floats(void);
 GENIE_API int genie_heads_layout(int32_t* offsets_out, int n);
 GENIE_API int genie_heads_grid_fwd(const float* heads_packed_dev, const float* fold_dev, int n_t, const float* x_spatial_dev,
-                                   int ld_x, int n_grid, float* y_out_dev, void* stream);
+                                   int ld_x, int n_grid, float* y_out_dev, float* proj_out_dev, void* stream);
 GENIE_API int genie_heads_query_fwd(const float* heads_packed_dev, const float* fold_dev, int n_t, const float* x_spatial_dev,
                                     int ld_x, const float* x_context_dev, const float* x_query_dev, const int64_t* nbr_dev,
-                                    int k_nbr, int n_query, float scale_rel, float* x_out_dev, void* stream);
+                                    int k_nbr, int n_query, float scale_rel, float* x_out_dev, const float* proj_dev,
+                                    void* stream);
 
 /* ---- product-graph message passing of the training path (BASELINE.json configs[2]) -----------------------------------------
  * Replaces `MessagePassing.propagate(A_in_sta / A_in_src, x=...)` with aggr='mean' (module.py:90-95, 394-400) AND its
