@@ -241,8 +241,10 @@ class Workload(object):
         self.n_windows = int((day_s - self.max_t) // STEP_S)
         # host-side staging for the end-to-end leg
         self.picks_host = torch.from_numpy(self.ex._day[1].cpu().numpy()).pin_memory()
-        self.y_host = torch.empty((G, self.tq.shape[0], 1), dtype=torch.float32).pin_memory()
-        self.x_host = torch.empty((N_QUERY, self.tq.shape[0], 1), dtype=torch.float32).pin_memory()
+        # two sets of pinned result buffers: the host takes window w - 1 while the device works on window w
+        self.y_host = [torch.empty((G, self.tq.shape[0], 1), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.x_host = [torch.empty((N_QUERY, self.tq.shape[0], 1), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._e2e_ev, self._e2e_n = [None, None], 0
 
     def runners(self, use_graph):
         """The streaming fast path (genie_b200.streaming.WindowRunner): a1 fused into the front end + heads, one parameter
@@ -262,9 +264,18 @@ class Workload(object):
         import torch
         lo, hi = self.ex.window_rows(w * STEP_S)
         y, x = self.runner_e2e.run(w * STEP_S, self.picks_host[lo:hi])
-        self.y_host.copy_(y, non_blocking=True)
-        self.x_host.copy_(x, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        # as a streaming caller does it (process_continuous_days.py:797-805 consumes window w while w + 1 is computed): this
+        # window's results are copied to one of two pinned buffer sets in stream order, and the host waits for the PREVIOUS
+        # window's copy — so the launches of the next window are queued while the device is still busy with this one
+        b = self._e2e_n & 1
+        self._e2e_n += 1
+        self.y_host[b].copy_(y, non_blocking=True)
+        self.x_host[b].copy_(x, non_blocking=True)
+        if self._e2e_ev[b] is None:
+            self._e2e_ev[b] = torch.cuda.Event()
+        self._e2e_ev[b].record()
+        if self._e2e_ev[b ^ 1] is not None:
+            self._e2e_ev[b ^ 1].synchronize()
         return (hi - lo) * 5 * 8 + self.runner_e2e.sz, (y.numel() + x.numel()) * 4
 
     def window_two_step(self, w):
@@ -698,7 +709,10 @@ def run_genie(args):
                        'api': 'streaming.WindowRunner: genie_window_fwd (a1 fused into the front end) + genie_heads_*'
                        if not sharded else 'sharded.ShardedFrontEnd'},
             'e2e': {'value': units * K / (ms2 * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d // K,
-                    'd2h_bytes_per_step': d2h // K, 'ms_per_step': ms2 / K},
+                    'd2h_bytes_per_step': d2h // K, 'ms_per_step': ms2 / K,
+                    'host_sync': 'every step copies its picks from pinned host memory and its y, x back to pinned host memory; '
+                                 'the host waits for window w - 1 while window w runs (two pinned result sets)'
+                                 if not sharded else 'every step: picks H2D, y, x D2H, stream synchronize'},
             'gpu_launches': launches,
             'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak,
