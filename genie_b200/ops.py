@@ -167,11 +167,23 @@ class HeadsWeights(object):
         return self.buf, self._fold[1], self._fold[2]
 
 
+HEADS_T_MAX = 25               # query times per kernel launch (T * 5 <= 128 columns of the folded query table)
+
+
 def heads_fwd(hw, packed, fold, T, x_spatial, x_context, x_query, nbr, scale_rel):
-    """y [G,T,1], x [Q,T,1] of forward_fixed_source (module.py:1015-1020) in two kernels."""
+    """y [G,T,1], x [Q,T,1] of forward_fixed_source (module.py:1015-1020) in two kernels (per block of 25 query times)."""
     dev = x_spatial.device
     x_spatial = _f32c(x_spatial, 'x_spatial')
     G, Q = x_spatial.shape[0], x_query.shape[0]
+    if T > HEADS_T_MAX:
+        ys, xs = [], []
+        for t0 in range(0, T, HEADS_T_MAX):
+            t1 = min(T, t0 + HEADS_T_MAX)
+            part = torch.cat((fold[t0 * 5 * 32:t1 * 5 * 32], fold[T * 5 * 32 + t0 * 5:T * 5 * 32 + t1 * 5])).contiguous()
+            yp, xp = heads_fwd(hw, packed, part, t1 - t0, x_spatial, x_context, x_query, nbr, scale_rel)
+            ys.append(yp)
+            xs.append(xp)
+        return torch.cat(ys, dim=1), torch.cat(xs, dim=1)
     y = torch.empty((G, T, 1), dtype=F32, device=dev)
     x = torch.empty((Q, T, 1), dtype=F32, device=dev)
     # the query-independent halves of SpatialAttention's per-edge layers, once per context node (GENIE_HEADS_PROJ_LD); worth

@@ -244,7 +244,8 @@ GENIE_API int genie_input_scatter_fwd(const genie_plan_t* plan, const genie_inpu
  *                     used) = q[t,h,:] . f_context_2.weight[h*15:(h+1)*15, :] / sqrt(15), then a0[t*5+h] = q[t,h,:] .
  *                     f_context_2.bias[h*15:(h+1)*15] / sqrt(15), q = temporal_query_2(activate3(temporal_query_1(t/scale_t))).
  *   nbr_dev           int64 [n_query][k_nbr] context node of every query edge, nearest first (knn(...).flip(0), module.py:282).
- *   y_out_dev [n_grid][n_t], x_out_dev [n_query][n_t].
+ *   y_out_dev [n_grid][n_t], x_out_dev [n_query][n_t].  n_t <= 25 per call (GENIE_ERR_UNSUPPORTED beyond: split the query
+ *                     times into blocks — the fold table is per query time — as genie_b200/ops.py heads_fwd does).
  *   proj_out_dev / proj_dev  optional fp32 [n_grid][GENIE_HEADS_PROJ_LD] (NULL = off): f_context and f_values of SpatialAttention
  *                     (module.py:288-290) are linear in [x_j | edge attr], and their x_j parts do not depend on the query — the
  *                     grid kernel computes them once per context node (columns 0-74 and 80-154) and the query kernel adds the

@@ -298,12 +298,13 @@ def _random_case(S, G, k_s, k_g, seed, dev):
     return net, A_sta, A_src, torch.from_numpy(Slice), torch.from_numpy(Mask), torch.from_numpy(attr)
 
 
-@pytest.mark.parametrize('G,Q,T', [(7, 5, 3), (300, 77, 5), (1000, 130, 12), (3000, 40, 9)])
+@pytest.mark.parametrize('G,Q,T', [(7, 5, 3), (300, 77, 5), (1000, 130, 12), (3000, 40, 9), (200, 60, 31)])
 def test_head_kernels_match_the_torch_restatement(G, Q, T):
     """genie_heads_grid_fwd / genie_heads_query_fwd against the torch restatement of SpatialDirect, SpatialAttention and
     TemporalAttention (module.py:251-331; itself checked against the reference's y, x in the golden tests): ragged sizes,
     fewer context nodes than k = 10, other numbers of query times; the last case has fewer (query, neighbour) pairs than
-    context nodes and takes the per-edge kernel instead of the per-context-node table of the x_j projections."""
+    context nodes and takes the per-edge kernel instead of the per-context-node table of the x_j projections; 31 query
+    times run as two launches (25 per launch)."""
     from genie_b200 import ops
     from genie_b200.module import GCN_Detection_Network_extended
     dev = _dev()
