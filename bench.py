@@ -294,7 +294,7 @@ class ShardedWorkload(object):
         from genie_b200.process_utils import InputExtractor, extract_inputs_adjacencies_cartesian
         from genie_b200.sharded import CudaBackend, GridPartition, PeerHalo, ShardedFrontEnd
         S, G, k_s, k_g = WORKLOADS[name]
-        self.S, self.G, self.dev, self.rank = S, G, dev, rank
+        self.S, self.G, self.dev, self.rank, self.world = S, G, dev, rank, world
         net = synth.Network(S, G, seed=0)
         A_sta, A_src = extract_inputs_adjacencies_cartesian(net.sta, net.grid, k_s, k_g)
         part = GridPartition(A_src, G, world)
@@ -339,12 +339,13 @@ class ShardedWorkload(object):
 
     def _window(self, Slice, Mask):
         import torch
+        from genie_b200.sharded import sharded_heads
         m = self.model
         with torch.no_grad():
             x_spatial, _ = self.fe.forward(Slice, Mask, self.grid, SCALE_REL, events=self.exchange_events)
-            if self.rank != 0:                      # the read-out heads are per grid node / query point: rank 0 emits them
-                return None, None
-            return m._heads(x_spatial, self.grid, self.xq, self.tq)         # genie_heads_grid_fwd / genie_heads_query_fwd
+            # the read-out heads are per grid node / query point: every rank computes its block of rows, two all-gathers
+            y, x = sharded_heads(m, x_spatial, self.grid, self.xq, self.tq, self.rank, self.world)
+            return (y, x) if self.rank == 0 else (None, None)
 
     def window_resident(self, w):
         Slice, Mask = self.ex(w * STEP_S)

@@ -170,10 +170,31 @@ class HeadsWeights(object):
 HEADS_T_MAX = 25               # query times per kernel launch (T * 5 <= 128 columns of the folded query table)
 
 
-def heads_fwd(hw, packed, fold, T, x_spatial, x_context, x_query, nbr, scale_rel):
-    """y [G,T,1], x [Q,T,1] of forward_fixed_source (module.py:1015-1020) in two kernels (per block of 25 query times)."""
+def heads_fwd(hw, packed, fold, T, x_spatial, x_context, x_query, nbr, scale_rel, grid_rows=None, query_rows=None):
+    """y [G,T,1], x [Q,T,1] of forward_fixed_source (module.py:1015-1020) in two kernels (per block of 25 query times).
+    grid_rows = (g0, g1) / query_rows = (q0, q1): only those rows of y / x (the heads split over the ranks of a sharded run)."""
     dev = x_spatial.device
     x_spatial = _f32c(x_spatial, 'x_spatial')
+    if grid_rows is not None or query_rows is not None:
+        g0, g1 = grid_rows
+        q0, q1 = query_rows
+        y = torch.empty((g1 - g0, T, 1), dtype=F32, device=dev)
+        x = torch.empty((q1 - q0, T, 1), dtype=F32, device=dev)
+        if T > HEADS_T_MAX:
+            raise capi.GenieError('heads_fwd: row ranges support at most %d query times' % HEADS_T_MAX)
+        lib = capi.load()
+        with torch.cuda.device(dev):
+            if g1 > g0:
+                capi.check(lib.genie_heads_grid_fwd(capi.dptr(packed, F32), capi.dptr(fold, F32), int(T),
+                                                    capi.dptr(x_spatial[g0:g1], F32), int(x_spatial.stride(0)), int(g1 - g0),
+                                                    capi.dptr(y), None, capi.stream_ptr(dev)))
+            if q1 > q0:
+                capi.check(lib.genie_heads_query_fwd(
+                    capi.dptr(packed, F32), capi.dptr(fold, F32), int(T), capi.dptr(x_spatial, F32), int(x_spatial.stride(0)),
+                    capi.dptr(_f32c(x_context, 'x_context'), F32), capi.dptr(_f32c(x_query, 'x_query')[q0:q1], F32),
+                    capi.dptr(nbr[q0:q1], torch.int64), int(nbr.shape[1]), int(q1 - q0), float(scale_rel), capi.dptr(x), None,
+                    capi.stream_ptr(dev)))
+        return y, x
     G, Q = x_spatial.shape[0], x_query.shape[0]
     if T > HEADS_T_MAX:
         ys, xs = [], []

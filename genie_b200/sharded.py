@@ -235,6 +235,32 @@ class CudaBackend(object):
         return x
 
 
+def sharded_heads(model, x_spatial, x_grid_cart, x_query_cart, t_query, rank, world, group=None):
+    """The read-out heads of forward_fixed_source (module.py:1015-1020) split by rows over the ranks: rank r computes y for its
+    block of grid nodes and x for its block of query points from the (replicated) x_spatial, two all-gathers assemble
+    (y [G,T,1], x [Q,T,1]) on every rank.  Needs the kernel-supported head shapes (ops.HeadsWeights.supported)."""
+    from . import ops
+    dev = x_spatial.device
+    if model._heads_w is None or model._heads_w.device != dev:
+        model._heads_w = ops.HeadsWeights(dev)
+    hp, fold, T = model._heads_w.update(model, t_query)
+    G, Q = x_spatial.shape[0], x_query_cart.shape[0]
+    gs, qs = -(-G // world), -(-Q // world)
+    g0, g1 = min(G, rank * gs), min(G, (rank + 1) * gs)
+    q0, q1 = min(Q, rank * qs), min(Q, (rank + 1) * qs)
+    nbr = model.SpatialAttention._nbr_table(model.SpatialAttention._edges(x_query_cart, x_grid_cart, 10), Q)
+    y, x = ops.heads_fwd(model._heads_w, hp, fold, T, x_spatial, x_grid_cart, x_query_cart, nbr,
+                         float(model.SpatialAttention.scale_rel), grid_rows=(g0, g1), query_rows=(q0, q1))
+    out = []
+    for part, n, blk in ((y, G, gs), (x, Q, qs)):
+        pad = torch.zeros((blk, T), dtype=part.dtype, device=dev)
+        pad[:part.shape[0]] = part.view(-1, T)
+        full = torch.empty((world * blk, T), dtype=part.dtype, device=dev)
+        dist.all_gather_into_tensor(full, pad, group=group)
+        out.append(full[:n].unsqueeze(-1))
+    return out[0], out[1]
+
+
 class ShardedFrontEnd(object):
     """DataAggregation -> Bipartite_ReadIn -> SpatialAggregation x3 with the grid nodes sharded over the process group."""
 

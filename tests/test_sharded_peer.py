@@ -21,7 +21,7 @@ def _worker(rank, world, port, ret):
     from genie_b200.module import GCN_Detection_Network_extended
     from genie_b200.plan import GraphPlan
     from genie_b200.process_utils import extract_inputs_adjacencies_cartesian
-    from genie_b200.sharded import CudaBackend, GridPartition, PeerHalo, ShardedFrontEnd
+    from genie_b200.sharded import CudaBackend, GridPartition, PeerHalo, ShardedFrontEnd, sharded_heads
     from oracle import genie_oracle as go
     os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -51,6 +51,14 @@ def _worker(rank, world, port, ret):
         want_xs, _, want_r = ops.frontend_fwd(plan, m._packed_weights(dev), Slice.to(dev), Mask.to(dev), attr.to(dev), grid,
                                               30000.0, want_readin=True)
         errs.append((rel_err(r.cpu().numpy(), want_r.cpu().numpy()), rel_err(xs.cpu().numpy(), want_xs.cpu().numpy())))
+    # the read-out heads split by rows over the ranks against the single-device heads (ragged blocks: 800 / 2, 77 / 2 rows)
+    xq = torch.rand((77, 3), generator=g).to(dev) * torch.tensor([net.width, net.width, -40000.0], device=dev)
+    tq = torch.arange(-3.0, 3.01, 0.75, device=dev).reshape(-1, 1)
+    with torch.no_grad():
+        y_s, x_s = sharded_heads(m, xs, grid, xq, tq, rank, world)
+        y_1, x_1 = m._heads(xs, grid, xq, tq)
+    errs.append((rel_err(y_s.cpu().numpy(), y_1.cpu().numpy()), rel_err(x_s.cpu().numpy(), x_1.cpu().numpy())))
+    assert y_s.shape == y_1.shape and x_s.shape == x_1.shape
     ret[rank] = (errs, fe.exchange_bytes, int(halo.exp_row.numel()))
     halo.close()
     dist.barrier()
