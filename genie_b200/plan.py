@@ -296,7 +296,7 @@ class GraphPlan(object):
             capi.check(capi.load().genie_plan_set_halo_export(self.handle, None, None, None, None, None))
             self._halo_export = None
             return
-        if exp_ptr.numel() != self.n_grid_owned + 1 or exp_peer.numel() != exp_row.numel():
+        if exp_ptr.numel() != self.n_grid_owned + 1 or exp_peer.numel() != exp_row.numel() or exp_peer.numel() == 0:
             raise capi.GenieError('halo export tables do not match the plan')
         capi.check(capi.load().genie_plan_set_halo_export(
             self.handle, capi.dptr(exp_ptr, torch.int32, 'exp_ptr'), capi.dptr(exp_peer, torch.int32, 'exp_peer'),

@@ -138,8 +138,9 @@ class PeerHalo(object):
         ptr_, peer, row = self.export_tables(partition, rank)
         dev = self.device
         self.exp_ptr = torch.from_numpy(ptr_).to(dev)
-        self.exp_peer = torch.from_numpy(peer).to(dev)
-        self.exp_row = torch.from_numpy(row).to(dev)
+        pad = lambda v: v if len(v) else np.zeros(1, dtype=np.int32)       # (a rank that exports nothing still passes tables)
+        self.exp_peer = torch.from_numpy(pad(peer)).to(dev)
+        self.exp_row = torch.from_numpy(pad(row)).to(dev)
         self.peer_base = torch.tensor(self.peer_ptrs, dtype=torch.int64, device=dev)
         self.export_bytes = int(len(row)) * row_bytes                # bytes this rank stores into peer memory per window
         plan.set_halo_export(self.exp_ptr, self.exp_peer, self.exp_row, self.peer_base, self.local_ptr)
