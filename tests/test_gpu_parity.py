@@ -960,6 +960,41 @@ def test_association_matches_oracle_seeded(explicit):
     assert rel_err(arv_s.cpu().numpy(), want[3].numpy()) < TOL
 
 
+def test_association_station_passes_with_halo_equal_generic_kernels():
+    """The association phase on the station-pass kernels (ASSOC instances of da_layer1_s_kernel / da_layer2_s_kernel) at a
+    station count with several tiles per grid node — halo rows, ragged last tile — against the generic association kernels
+    (a plan without tiling tables: L2 gathers, FFMA) on the same inputs: 300 stations x 500 grid nodes, random activations,
+    about half of the source mask set, the trained Ferndale weights of the fixtures."""
+    from genie_b200 import ops, synth
+    from genie_b200.plan import GraphPlan
+    from genie_b200.process_utils import extract_inputs_adjacencies_cartesian
+    dev = _dev()
+    S, G, T = 300, 500, 9
+    net = synth.Network(S, G, seed=21)
+    A_sta, A_src = extract_inputs_adjacencies_cartesian(net.sta, net.grid, 15, 15)
+    d0, sd = load_golden(ASSOC[0])
+    m = _model(sd, dev, float(d0['scale_rel']), float(d0['scale_t']))
+    P = S * G
+    g = torch.Generator(device=dev).manual_seed(5)
+    x_spatial = torch.randn((G, 30), device=dev, generator=g)
+    y = torch.rand((G, T), device=dev, generator=g) * 0.0115                     # mask_out = (max_t y > 0.01): about half set
+    attr = torch.rand((P, 3), device=dev, generator=g) - 0.5
+    x_latent = torch.randn((P, 30), device=dev, generator=g)
+    Mask = (torch.rand((P, 4), device=dev, generator=g) < 0.3).float()
+    packed = ops.AssocWeights(dev).update(m)
+    outs = []
+    for tiling in (True, False):
+        plan = GraphPlan.cartesian(A_sta, A_src, S, G, device=dev, tiling=tiling)
+        assert (plan.tiles is not None) == tiling and (not tiling or plan.tiles['n_tiles'] >= 3)
+        s_rows, s0, mask_out = ops.assoc_product_fwd(plan, packed, x_spatial, y, attr, x_latent, Mask, want_parts=True)
+        outs.append((s_rows.clone(), s0.clone(), mask_out.clone()))
+    (s_t, s0_t, mo_t), (s_g, s0_g, mo_g) = outs
+    assert 0.2 < float(mo_t.mean()) < 0.8 and torch.equal(mo_t, mo_g)
+    assert rel_err(s0_t.cpu().numpy(), s0_g.cpu().numpy()) < 1e-6
+    assert not s_t[:, 15].any() and not s_t[:, 31].any()
+    assert rel_err(s_t.cpu().numpy(), s_g.cpu().numpy()) < 2e-5
+
+
 # ---- use_absolute_pos: True (module.py:913-914) --------------------------------------------------------------------------
 
 def _abspos_model(sd, dev, d):
