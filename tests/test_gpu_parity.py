@@ -160,18 +160,19 @@ def test_window_runner_equals_the_two_step_path():
         assert torch.equal(out[1], lat) and torch.equal(out[2], rin)
 
 
-def test_bf16_storage_mode_tracks_the_fp32_path():
+@pytest.mark.parametrize('S,G', [(100, 1500), (300, 400)])
+def test_bf16_storage_mode_tracks_the_fp32_path(S, G):
     """GENIE_STORAGE_BF16 (BASELINE.json configs[1]: bf16 inference): the gathered intermediate rows kept as bf16, fp32
     arithmetic.  A SECOND mode — it never stands in for the 1e-4 parity tests: here it is held to 2e-2 of the fp32 path and
     of the oracle, must differ from fp32 (it really stores bf16), must agree bit for bit between the fused window call and
-    the two-step call, and switching back to fp32 must restore the fp32 results exactly."""
+    the two-step call, and switching back to fp32 must restore the fp32 results exactly.  300 stations: three station tiles per
+    grid node, i.e. the bf16 rows of the halo and the double-buffered staging."""
     from genie_b200 import synth
     from genie_b200.module import GCN_Detection_Network_extended
     from genie_b200.process_utils import InputExtractor, extract_inputs_adjacencies_cartesian, product_edge_lists
     from genie_b200.streaming import WindowRunner
     from oracle import genie_oracle as go
     dev = _dev()
-    S, G = 100, 1500
     net = synth.Network(S, G, seed=3)
     A_sta, A_src = extract_inputs_adjacencies_cartesian(net.sta, net.grid, 15, 15)
     attr = torch.from_numpy(net.read_in_offsets(30000.0)).to(dev)
