@@ -240,8 +240,10 @@ def sharded_heads(model, x_spatial, x_grid_cart, x_query_cart, t_query, rank, wo
     """The read-out heads of forward_fixed_source (module.py:1015-1020) split by rows over the ranks: rank r computes y for its
     block of grid nodes and x for its block of query points from the (replicated) x_spatial, two all-gathers assemble
     (y [G,T,1], x [Q,T,1]) on every rank.  Needs the kernel-supported head shapes (ops.HeadsWeights.supported)."""
-    from . import ops
+    from . import capi, ops
     dev = x_spatial.device
+    if not ops.HeadsWeights.supported(model):
+        raise capi.GenieError('sharded_heads: head shapes without a kernel (use model._heads on one rank)')
     if model._heads_w is None or model._heads_w.device != dev:
         model._heads_w = ops.HeadsWeights(dev)
     hp, fold, T = model._heads_w.update(model, t_query)
