@@ -166,11 +166,21 @@ __global__ void __launch_bounds__(HEADS_THREADS)
     for (int qi = blockIdx.x * HW + (threadIdx.x >> 5); qi < Q; qi += gridDim.x * HW) {
         const float qx = __ldg(x_query + (int64_t)qi * 3), qy = __ldg(x_query + (int64_t)qi * 3 + 1),
                     qz = __ldg(x_query + (int64_t)qi * 3 + 2);
+        // lane e < k fetches neighbour e and its edge attribute once (one coalesced id load, the coordinate loads of all edges in
+        // flight together); the edge loops below broadcast them with shuffles instead of chaining id -> coordinates -> row loads
+        int64_t jl = 0;
+        float eal[3] = {0.f, 0.f, 0.f};
+        if (lane < k_nbr) {
+            jl = __ldg(nbr + (int64_t)qi * k_nbr + lane);
+            eal[0] = (qx - __ldg(x_context + jl * 3)) / scale_rel;
+            eal[1] = (qy - __ldg(x_context + jl * 3 + 1)) / scale_rel;
+            eal[2] = (qz - __ldg(x_context + jl * 3 + 2)) / scale_rel;
+        }
         // ---- pass 1: attention scores of the k edges (module.py:288-292) --------------------------------------------------
         for (int e = 0; e < k_nbr; ++e) {
-            const int64_t j = __ldg(nbr + (int64_t)qi * k_nbr + e);
-            const float ea[3] = {(qx - __ldg(x_context + j * 3)) / scale_rel, (qy - __ldg(x_context + j * 3 + 1)) / scale_rel,
-                                 (qz - __ldg(x_context + j * 3 + 2)) / scale_rel};
+            const int64_t j = __shfl_sync(FULL_MASK, jl, e);
+            const float ea[3] = {__shfl_sync(FULL_MASK, eal[0], e), __shfl_sync(FULL_MASK, eal[1], e),
+                                 __shfl_sync(FULL_MASK, eal[2], e)};
             const float xj = (!PROJ && lane < 30) ? __ldg(x_spatial + j * ld_x + lane) : 0.f;
             float c[3], qv[3];
 #pragma unroll
@@ -221,9 +231,9 @@ __global__ void __launch_bounds__(HEADS_THREADS)
         // ---- pass 2: weighted values, mean over heads, projection (module.py:293-297) --------------------------------------
         float outl = 0.f;                            // lanes l < NL
         for (int e = 0; e < k_nbr; ++e) {
-            const int64_t j = __ldg(nbr + (int64_t)qi * k_nbr + e);
-            const float ea[3] = {(qx - __ldg(x_context + j * 3)) / scale_rel, (qy - __ldg(x_context + j * 3 + 1)) / scale_rel,
-                                 (qz - __ldg(x_context + j * 3 + 2)) / scale_rel};
+            const int64_t j = __shfl_sync(FULL_MASK, jl, e);
+            const float ea[3] = {__shfl_sync(FULL_MASK, eal[0], e), __shfl_sync(FULL_MASK, eal[1], e),
+                                 __shfl_sync(FULL_MASK, eal[2], e)};
             const float xj = (!PROJ && lane < 30) ? __ldg(x_spatial + j * ld_x + lane) : 0.f;
             float v[3];
 #pragma unroll
